@@ -1,0 +1,365 @@
+"""Pin the CPU oracle against the reference's own known-answer tests
+(/root/reference/test/runtests.jl, transcribed to tests/golden/runtests_known_answers.json)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import pmf_oracle as O
+
+G = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "runtests_known_answers.json")))
+
+
+def jr(pair):
+    """Julia 1-based inclusive [a, b] -> Python range."""
+    return range(pair[0] - 1, pair[1])
+
+
+def test_is_contiguous():
+    for c in G["is_contiguous"]["cases"]:
+        assert O.is_contiguous(c["vec"]) == c["expect"]
+
+
+def test_ids_to_ranges():
+    for c in G["ids_to_ranges"]["cases"]:
+        assert O.ids_to_ranges(c["vec"]) == [jr(p) for p in c["expect"]]
+
+
+def test_subset_ranges():
+    for c in G["subset_ranges"]["cases"]:
+        new, lo, hi = O.subset_ranges([jr(p) for p in c["ranges"]], jr(c["rng"]))
+        assert new == [jr(p) for p in c["expect"]["ranges"]]
+        assert (lo + 1, hi + 1) == (c["expect"]["r_min"], c["expect"]["r_max"])
+
+
+def test_ids_to_ind_mat():
+    g = G["ids_to_ind_mat"]
+    assert np.array_equal(O.ids_to_ind_mat(g["vec"]), np.array(g["expect"], dtype=bool))
+
+
+def test_keymatch():
+    g = G["keymatch"]
+    li, ri = O.keymatch(g["l_keys"], g["r_keys"])
+    assert [i + 1 for i in li] == g["l_idx"] and [i + 1 for i in ri] == g["r_idx"]
+
+
+def test_nanstats():
+    g = G["nanstats"]
+    v = [np.nan if x is None else x for x in g["vec"]]
+    assert O.nansum(v) == g["nansum"] and O.nanmean(v) == g["nanmean"] and O.nanvar(v) == g["nanvar"]
+
+
+def test_edgelist_to_spmat():
+    g = G["edgelist_to_spmat"]
+    n2i = {c: i for i, c in enumerate(g["nodes"])}
+    sp = O.edgelist_to_spmat(g["edgelist"], n2i, epsilon=g["epsilon"])
+    assert np.allclose(sp.toarray(), np.array(g["expect"]))
+
+
+def _ba(g, key_cols="col_batches"):
+    vals = []
+    ranges = O.ids_to_ranges(g[key_cols])
+    for vd, cr in zip(g["values"], ranges):
+        vals.append({int(k): np.full(len(cr), v) for k, v in vd.items()})
+    return O.BatchArray.construct(g[key_cols], g["row_batches"], vals)
+
+
+def test_batch_array_ctor_view_zero():
+    g = G["batch_array"]
+    ba = _ba(g)
+    assert ba.col_ranges == [jr(p) for p in g["col_ranges"]]
+    for rb, e in zip(ba.row_batches, g["indicators"]):
+        assert np.array_equal(rb, np.array(e, dtype=bool))
+    for v, e in zip(ba.values, g["values_expect"]):
+        assert np.array_equal(v, np.array(e))
+    bv = ba.view(jr(g["view_rows"]), jr(g["view_cols"]))
+    assert bv.col_ranges == [jr(p) for p in g["view_col_ranges"]]
+    for rb, e in zip(bv.row_batches, g["indicators"][:2]):
+        assert np.array_equal(rb, np.array(e, dtype=bool)[1:4])
+    for v, e in zip(bv.values, g["view_values"]):
+        assert np.array_equal(v, np.array(e))
+    # Vector{Int} rows and nested views
+    bv2 = ba.view(np.array([1, 2, 3]), jr(g["view_cols"]))
+    assert bv2.col_ranges == bv.col_ranges
+    bvv = bv.view(range(0, 2), range(0, 3))
+    assert bvv.col_ranges[0] == range(0, 2)
+    # gap columns / empty view
+    gg = dict(g, values=g["values"])
+    gappy = _ba(gg, "gappy_col_batches")
+    assert gappy.col_ranges == [jr(p) for p in g["gappy_col_ranges"]]
+    ev = gappy.view(range(0, 5), jr(g["gappy_empty_view_cols"]))
+    assert ev.col_ranges == [] and ev.values == [] and ev.row_batches == []
+    z = ba.zero()
+    assert all(np.all(v == 0) for v in z.values) and z.col_ranges == ba.col_ranges
+
+
+def test_batch_array_arithmetic_and_pullbacks():
+    g = G["batch_array"]
+    ba = _ba(g)
+    A = np.zeros((5, 7))
+    test_mat = np.array(g["add_expect"])
+    assert np.array_equal(ba.add_to(A), test_mat)
+    A_bar, vb = ba.add_pullback(np.ones((5, 7)))
+    assert np.array_equal(A_bar, np.ones((5, 7)))
+    for b, e in zip(vb, g["grad_sum_values"]):
+        assert np.array_equal(b, np.array(e, dtype=float))
+    other = test_mat.copy()
+    other[:, 3] = 1
+    ones = np.ones((5, 7))
+    assert np.allclose(ba.mul_to(ones), other)
+    A_bar, vb = ba.mul_pullback(ones, np.ones((5, 7)))
+    assert np.allclose(A_bar, other)
+    for b, e in zip(vb, g["grad_sum_values"]):
+        assert np.array_equal(b, np.array(e, dtype=float))
+    # exp and its gradient n_b * exp(v)  (runtests.jl:229-236)
+    assert np.array_equal(ba.exp().mul_to(ones), np.exp(test_mat))
+    eb = ba.exp()
+    _, vb = eb.mul_pullback(ones, np.ones((5, 7)))
+    for b, ev, e, v in zip(vb, eb.values, g["grad_sum_values"], ba.values):
+        assert np.allclose(b * ev, np.array(e, dtype=float) * np.exp(v))
+    res = O.ba_map(lambda a: a, ba, test_mat)
+    for r, e in zip(res, g["ba_map_identity"]):
+        assert np.allclose(r, np.array(e))
+
+
+def test_layers_forward_and_grads():
+    """test/runtests.jl:348-453 (inputs there are unseeded randn; the assertions
+    are formulas, re-evaluated here on seeded inputs)."""
+    rng = np.random.default_rng(0)
+    M, N, K = 20, 30, 4
+    X, Y = rng.standard_normal((K, M)), rng.standard_normal((K, N))
+    xy = X.T @ Y
+    col_batches = ["colbatch1"] * 15 + ["colbatch2"] * 15
+    rbs = [f"rowbatch{i}" for i in range(1, 5) for _ in range(5)]
+    bd = {"colbatch1": rbs, "colbatch2": rbs}
+    vds = [{b: np.zeros(15) for b in O.unique_in_order(rbs)} for _ in range(2)]
+    ld = O.BatchArray.construct(col_batches, bd, vds)
+    for v in ld.values:
+        v[...] = rng.standard_normal(v.shape) * 0.3
+    th = ld.copy()
+    nm = O.NoiseModel.from_distributions(["normal"] * N)
+    logsigma, mu = rng.standard_normal(N) * 0.2, rng.standard_normal(N)
+    m = O.OracleModel(X=X, Y=Y, logsigma=logsigma, mu=mu, logdelta=ld, theta=th, noise=nm)
+    # forward = fixed composition order
+    Z = xy * np.exp(logsigma)[None, :]
+    Z = Z * (ld.row_batches[0].astype(float) @ np.exp(np.hstack(ld.values)))
+    Z = Z + mu[None, :] + th.row_batches[0].astype(float) @ np.hstack(th.values)
+    assert np.allclose(O.forward(m), Z)
+    # BatchShift grads of sum(f(x)): theta grad = batch size, Z grad = ones  (:412-414)
+    A_bar, vb = th.add_pullback(np.ones((M, N)))
+    assert all(np.array_equal(b, np.full((4, 15), 5.0)) for b in vb) and np.array_equal(A_bar, np.ones((M, N)))
+    # BatchScale grads (:401-403)
+    ed = ld.exp()
+    A_bar, vb = ed.mul_pullback(xy, np.ones((M, N)))
+    assert np.allclose(A_bar, ed.mul_to(np.ones((M, N))))
+    assert np.allclose((vb[-1] * ed.values[-1])[-1, :],
+                       (xy[15:20, 15:30] * np.exp(ld.values[-1][-1, :])[None, :]).sum(axis=0))
+    # frozen layer => no gradient through the optimiser, loss unchanged
+    D = Z + 0.1
+    out = O.data_loss_grads(m, D)
+    assert np.isclose(out["loss"], 0.5 * M * N * 0.01)
+    # ColScale quirk: dlogsigma_j = sum_i sigma_j * Gbar_ij
+    G1 = (Z - D) * (ld.row_batches[0].astype(float) @ np.exp(np.hstack(ld.values)))
+    assert np.allclose(out["dlogsigma"], (np.exp(logsigma)[None, :] * G1).sum(axis=0))
+    assert np.allclose(out["dmu"], (Z - D).sum(axis=0))
+
+
+def test_data_grads_match_finite_differences():
+    """Everything except the documented ColScale quirk must be the true derivative."""
+    m, D, _ = O.simulate_model(12, {"mutation": ("bernoulli", 5), "methylation": ("normal", 6),
+                                    "counts": ("poisson", 4)}, K=3, seed=3,
+                               batch_views=["methylation", "counts"], n_batches=3, missing=0.2)
+    out = O.data_loss_grads(m, D)
+    eps = 1e-6
+
+    def fd(arr, idx):
+        old = arr[idx]
+        arr[idx] = old + eps
+        lp = O.data_loss_grads(m, D, want_grads=False)["loss"]
+        arr[idx] = old - eps
+        lm = O.data_loss_grads(m, D, want_grads=False)["loss"]
+        arr[idx] = old
+        return (lp - lm) / (2 * eps)
+
+    for idx in [(0, 0), (2, 7), (1, 11)]:
+        assert np.isclose(out["dX"][idx], fd(m.X, idx), rtol=1e-5, atol=1e-6)
+    for idx in [(0, 0), (2, 7), (1, 14)]:
+        assert np.isclose(out["dY"][idx], fd(m.Y, idx), rtol=1e-5, atol=1e-6)
+    for j in [0, 6, 14]:
+        assert np.isclose(out["dmu"][j], fd(m.mu, j), rtol=1e-5, atol=1e-6)
+    for v in range(2):
+        assert np.isclose(out["dtheta"][v][1, 2], fd(m.theta.values[v], (1, 2)), rtol=1e-5, atol=1e-6)
+        assert np.isclose(out["dlogdelta"][v][1, 1], fd(m.logdelta.values[v], (1, 1)), rtol=1e-5, atol=1e-6)
+
+
+def test_row_minibatching_is_exact():
+    m, D, _ = O.simulate_model(40, {"methylation": ("normal", 9), "counts": ("poisson", 4)}, K=3, seed=4,
+                               batch_views=["methylation"], n_batches=4, missing=0.3)
+    a = O.data_loss_grads(m, D, capacity=10 ** 8)
+    b = O.data_loss_grads(m, D, capacity=13 * 7)
+    assert np.isclose(a["loss"], b["loss"])
+    for k in ("dX", "dY", "dmu", "dlogsigma"):
+        assert np.allclose(a[k], b[k])
+    assert np.allclose(a["dtheta"][0], b["dtheta"][0])
+
+
+def test_network_regularizer_blocks_and_values():
+    g = G["network_regularizer"]
+    p = g["path"]
+    nr = O.NetworkRegularizer(p["data_features"], p["edgelists"])
+    assert len(nr.AA) == 2
+    assert np.allclose(nr.AA[0].toarray(), p["AA1"]) and np.allclose(nr.AB[0].toarray(), p["AB1"])
+    assert np.allclose(nr.BB[0].toarray(), p["BB1"])
+    nr2 = O.NetworkRegularizer(p["all_observed_features"], p["edgelists"])
+    assert nr2.AA[0].shape == (4, 4) and nr2.AB[0].shape == (4, 0) and nr2.BB[0].shape == (0, 0)
+    s = g["star"]
+    ns = O.NetworkRegularizer(s["data_features"], s["edgelists"])
+    assert np.allclose(ns.AA[0].toarray(), s["AA1"]) and np.allclose(ns.AB[0].toarray(), s["AB1"])
+    assert np.allclose(ns.BB[0].toarray(), s["BB1"])
+    d = g["derived"]
+    loss, grad = ns.value_grad(np.array([d["star_y"]]))
+    assert grad.shape == (1, 3)
+    assert np.isclose(loss, d["star_loss"], atol=1e-6) and np.allclose(grad[0], d["star_grad"], atol=1e-6)
+    assert np.isclose(-ns.x_virtual[0][0], -d["star_u"], atol=1e-6) or np.isclose(ns.x_virtual[0][0], d["star_u"], atol=1e-6)
+    np1 = O.NetworkRegularizer(p["data_features"], p["edgelists"][:1])
+    loss, grad = np1.value_grad(np.array([d["path_y"]]))
+    assert np.isclose(loss, d["path_loss"], atol=1e-6) and np.allclose(grad[0], d["path_grad"], atol=1e-6)
+    assert np.isclose(np1.value(np.array([d["path_y"]])), d["path_loss"], atol=1e-6)
+    # old suite, epsilon = 0
+    n0 = O.NetworkRegularizer(s["data_features"], s["edgelists"], epsilon=0.0)
+    loss, grad = n0.value_grad(np.array([[1.0, 1.0, 1.0]]))
+    # with eps=0: AA=I, AB=-1, BB=3: u = 1, loss = 0.5*3 - 3 + 1.5 = 0 ; the old suite used
+    # y=[1,0,0]-style inputs; keep only the structural check here
+    assert np.isfinite(loss)
+
+
+def test_selective_l1():
+    g = G["selective_l1"]
+    reg = O.SelectiveL1Reg(g["data_features"], g["edgelists"])
+    assert np.array_equal(reg.l1_idx, np.array(g["l1_idx"], dtype=bool))
+    Y = np.random.default_rng(1).standard_normal((2, 5))
+    assert np.isclose(reg.value(Y), np.sum(np.abs(reg.l1_idx * Y)))
+    assert np.allclose(reg.grad(np.ones((2, 5))), np.array(g["grad_at_ones"], dtype=float))
+
+
+def test_group_ard_batcharray_composite_regs():
+    rng = np.random.default_rng(2)
+    Y = rng.standard_normal((3, 6))
+    reg = O.GroupRegularizer(G["group_regularizer"]["data_groups"], K=3)
+    assert np.isclose(reg.value(Y), 0.5 * np.sum(Y ** 2)) and np.allclose(reg.grad(Y), Y)
+    a = G["ard_regularizer"]
+    Y = rng.standard_normal((3, 5))
+    ard = O.ARDRegularizer(a["groups"])
+    b = 1 + (0.5 / ard.beta[0]) * Y * Y
+    assert np.isclose(ard.value(Y), (0.5 + ard.alpha[0]) * np.sum(np.log(b)))
+    assert np.allclose(ard.grad(Y), ((0.5 + ard.alpha[0]) / ard.beta[0]) * Y / b)
+    assert np.isclose(ard.alpha[0], a["alpha"]) and np.isclose(ard.beta[0], a["beta"])
+    ba = _ba(G["batch_array_reg"])
+    br = O.BatchArrayReg(ba, weight=1.0)
+    assert np.isclose(br.value(ba), 0.5 * sum(np.sum(w[:, None] * v * v) for w, v in zip(br.weights, ba.values)))
+    for gr, w, v in zip(br.grad(ba), br.weights, ba.values):
+        assert np.allclose(gr, w[:, None] * v)
+    s = G["selective_l1"]
+    Y = rng.standard_normal((2, 5))
+    l1 = O.SelectiveL1Reg(s["data_features"], s["edgelists"])
+    net = O.NetworkRegularizer(s["data_features"], s["edgelists"])
+    comp = O.CompositeRegularizer([l1, net], [0.5, 0.5])
+    assert np.isclose(comp.value(Y), 0.5 * (l1.value(Y) + net.value(Y)))
+    v, gsum = O._value_grad(comp, Y)
+    assert np.isclose(v, comp.value(Y)) and np.allclose(gsum, 0.5 * (l1.grad(Y) + net.grad(Y)))
+
+
+def test_construct_regs_mixture_weights():
+    """src/regularizers.jl:655-739: 3 slots, mixture_p normalised over the enabled ones."""
+    fv = [1] * 3 + [2] * 2
+    el = G["selective_l1"]["edgelists"]
+    yr = O.construct_Y_reg(2, 5, [1, 2, 3, 4, 5], fv, None, el, 1.0, 1.0, 1.0, False, False, None, 1.001, 0.8)
+    assert len(yr.regularizers) == 3 and np.allclose(yr.mixture_p, [1 / 3] * 3)
+    yr = O.construct_Y_reg(2, 5, [1, 2, 3, 4, 5], fv, None, None, 1.0, None, None, False, False, None, 1.001, 0.8)
+    assert np.allclose(yr.mixture_p, [1, 0, 0])
+    xr = O.construct_X_reg(2, 4, [1, 2, 3, 4], [1, 1, 2, 2], None, None, 1.0, 1.0, False, False)
+    assert np.allclose(xr.mixture_p, [0, 1, 0]) and isinstance(xr.regularizers[1], O.GroupRegularizer)
+    assert isinstance(O.construct_X_reg(2, 4, None, [1, 1, 2, 2], None, None, 1.0, 1.0, True, False), O.GroupRegularizer)
+    assert isinstance(O.construct_X_reg(2, 4, None, None, None, None, 1.0, 1.0, False, True), O.L2Regularizer)
+    assert isinstance(O.construct_Y_reg(2, 5, None, fv, None, None, 1.0, None, None, True, False, None, 1.001, 0.8),
+                      O.ARDRegularizer)
+
+
+def test_featureset_ard():
+    g = G["featureset_ard"]
+    N, K = g["N"], g["K"]
+    fids = list(range(1, N + 1))
+    views = [1] * 20 + [2] * 20
+    reg = O.construct_featureset_ard(K, fids, views, g["feature_sets"], alpha0=g["alpha0"], lr=0.1, v0=g["v0"],
+                                     dtype=np.float64)
+    assert len(reg.col_ranges) == 2 and reg.featureset_ids == [[1, 2, 3, 4], [1, 2, 3, 4]]
+    assert reg.alpha0 == np.float32(g["alpha0"]) and reg.v0 == np.float32(g["v0"])
+    assert np.allclose(reg.beta, np.float32(g["alpha0"]) - np.float32(1))
+    for i, fs in enumerate(g["feature_sets"]):
+        S = np.zeros((len(fs), 20))
+        for l, s in enumerate(fs):
+            S[l, np.array(s) - 1 - i * 20] = 1 / np.sqrt(len(s))
+        assert np.allclose(reg.S[i].toarray(), S)
+        assert reg.A[i].shape == (len(fs), K)
+    rng = np.random.default_rng(5)
+    Y = rng.standard_normal((K, N)) * 0.3
+
+    def gnl(beta, Y_):
+        return -np.sum(reg.alpha[None, :] * np.log(beta)) + np.sum(
+            (reg.alpha + 0.5)[None, :] * np.log(beta + 0.5 * Y_ * Y_))
+    assert np.isclose(reg.value(Y), gnl(reg.beta, Y) - gnl(reg.beta, np.zeros_like(Y)))
+    # grad == d/dY of the un-calibrated formula
+    eps = 1e-6
+    gr = reg.grad(Y)
+    for idx in [(0, 0), (3, 17), (9, 39)]:
+        Yp, Ym = Y.copy(), Y.copy()
+        Yp[idx] += eps
+        Ym[idx] -= eps
+        assert np.isclose(gr[idx], (gnl(reg.beta, Yp) - gnl(reg.beta, Ym)) / (2 * eps), rtol=1e-5)
+    # gamma_normal_loss gradient wrt A matches finite differences; update_A! runs and improves
+    A = np.abs(rng.standard_normal(reg.A[0].shape)) * 0.1
+    Yv = Y[:, :20]
+    gA = O.gamma_normal_grad_A(A, reg.S[0], reg.alpha[:20], reg.alpha0, reg.v0, Yv)
+    for idx in [(0, 0), (2, 5)]:
+        Ap, Am = A.copy(), A.copy()
+        Ap[idx] += eps
+        Am[idx] -= eps
+        fdv = (O.gamma_normal_loss(Ap, reg.S[0], reg.alpha[:20], reg.alpha0, reg.v0, Yv)
+               - O.gamma_normal_loss(Am, reg.S[0], reg.alpha[:20], reg.alpha0, reg.v0, Yv)) / (2 * eps)
+        assert np.isclose(gA[idx], fdv, rtol=1e-4)
+    O.update_lambda(reg, Y)
+    res = O.update_A(reg, Y, max_epochs=200, term_iter=20)
+    assert len(res) == 2 and all(np.isfinite(r[0]) for r in res)
+    assert np.all(reg.A[0] >= 0) and np.all(reg.beta > 0)
+
+
+def test_ista_and_adagrad_rules():
+    """src/optimizers.jl:6-13, 46-62."""
+    p = np.array([[0.5, -0.2], [0.05, 1.0]], dtype=np.float32)
+    g = np.array([[0.1, 0.1], [1.0, -0.5]], dtype=np.float32)
+    opt = O.ISTAOptimiser(p, 0.1, np.array([2.0, 0.5], dtype=np.float32))
+    ssq = np.float32(1e-8) + g * g
+    eta = np.float32(0.1) / np.sqrt(ssq)
+    e = np.maximum(p - eta * g, 0)
+    e = np.maximum(np.abs(e) - np.array([2.0, 0.5], dtype=np.float32)[None, :] * eta, 0)
+    opt.update(p, g)
+    assert np.allclose(p, e)
+    ad = O.AdaGrad(1.0)
+    q = np.ones(3)
+    gq = np.array([1.0, -2.0, 0.0])
+    ad.apply("q", q, gq)
+    acc = 1e-8 + gq * gq
+    assert np.allclose(q, 1 - gq / (np.sqrt(acc) + 1e-8))
+
+
+def test_fit_loop_contract():
+    m, D, _ = O.simulate_model(30, {"methylation": ("normal", 20)}, K=3, seed=7)
+    m.X_reg = O.L2Regularizer(3, 1.0)
+    m.Y_reg = O.GroupRegularizer(["methylation"] * 20, K=3)
+    hist = O.mf_fit_adapt_lr(m, D, lr=1.0, min_lr=0.01, max_epochs=60, update_X=True, update_Y=True)
+    assert hist[-1]["term_code"] in ("max_epochs", "abs_tol", "rel_tol", "loss_increase")
+    first, last = hist[0]["loss"][0], hist[-1]["loss"][-1]
+    assert last < first
+    for a, b in zip(hist[:-1], hist[1:]):
+        assert a["term_code"] == "loss_increase" and np.isclose(b["lr"], a["lr"] * 0.5)
