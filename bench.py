@@ -1,0 +1,305 @@
+#!/usr/bin/env python
+"""Benchmark of the fit-loop hot path (BASELINE.json metric: fit iters/sec, loss+grad+step).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A "step" is one full-batch epoch (fused loss+gradient pass, regulariser pullbacks, AdaGrad
+update) on the C2 workload: 10 000 samples x 30 000 features, K=64, mixed
+bernoulli/normal/poisson assays, 30% missing.  With N>1 (torchrun, one rank per GPU) every rank
+owns a C2-sized block of samples (weak scaling; Y and column parameters replicated, one NCCL
+all-reduce of dY + column gradients per step) and `value` is in C2-equivalent iterations/sec:
+(samples processed per second by the whole job) / 10 000.
+
+Rank 0 prints ONE JSON line."""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+C2 = dict(M=10000, N=30000, K=64, missing=0.3)
+METRIC = "fit iters/sec (loss+grad+step) at 10kx30k K=64"
+UNIT = "iter/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "ffma", "tc"])
+    ap.add_argument("--precision", type=int, default=0)
+    ap.add_argument("--M", type=int, default=C2["M"])
+    ap.add_argument("--N", type=int, default=C2["N"])
+    ap.add_argument("--K", type=int, default=C2["K"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.stop_flag = False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                for line in out.strip().splitlines():
+                    self.rows.append([x.strip() for x in line.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        self.stop_flag = True
+        self.join(timeout=6)
+        sm = sorted(int(float(r[1])) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit())
+        mx = [int(float(r[2])) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 8:
+                for n, v in zip(names, r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def to_oracle(model, rows, dtype):
+    """Product model -> oracle model restricted to a block of samples (cpu_baseline only)."""
+    import numpy as np
+    from oracle import pmf_oracle as O
+    mf = model.matfac
+    ct = mf.col_transform
+    nm = O.NoiseModel.from_distributions(model.feature_distributions)
+    nm.weights = mf.noise_model.weights().astype(dtype)
+    om = O.OracleModel(X=mf.X[:, rows.start:rows.stop].astype(dtype), Y=mf.Y.astype(dtype),
+                       logsigma=ct.unwrapped(0).logsigma.astype(dtype), mu=ct.unwrapped(2).mu.astype(dtype),
+                       logdelta=None, theta=None, noise=nm)
+    om.X_reg = O.L2Regularizer(mf.X.shape[0], 1.0)
+    om.Y_reg = O.GroupRegularizer(model.feature_views, K=mf.X.shape[0], weight=1.0)
+    om.layer_regs = [O.ColParamReg(model.feature_views), O.ZeroReg(), O.ColParamReg(model.feature_views), O.ZeroReg()]
+    D = np.ascontiguousarray(model.data[rows.start:rows.stop, :]).astype(dtype)
+    return om, D
+
+
+def cpu_iterations(model, sample_rows, steps, warmup):
+    """Time `steps` full oracle iterations (loss + all gradients + AdaGrad) on a block of
+    samples; returns seconds per iteration on that block."""
+    import numpy as np
+    from oracle import pmf_oracle as O
+    om, D = to_oracle(model, sample_rows, np.float32)
+    opt = O.AdaGrad(0.05)
+    ts = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        O.mf_fit(om, D, opt, max_epochs=1, update_X=True, update_Y=True, update_col_layers=True)
+        ts.append(time.perf_counter() - t0)
+    ts = ts[warmup:]
+    return sum(ts) / len(ts)
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's CPU implementation of the path.  Julia and MatFac.jl
+    are not available in this image, so this times the CPU restatement (the oracle,
+    kind "port") with every host thread NumPy/BLAS can use, on a bounded block of samples."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from pathmatfac_b200.simulate import C2_BLOCKS, scale_blocks, simulate_problem
+    cores = os.cpu_count() or 1
+    Ms = min(args.M, 500)
+    model = simulate_problem(Ms, blocks=scale_blocks(C2_BLOCKS, args.N), K=args.K, seed=2, missing=C2["missing"],
+                             model_kwargs=dict(lambda_X_l2=1.0))
+    steps = max(1, min(args.steps, 5))
+    warm = max(1, min(args.warmup, 1))
+    sec = cpu_iterations(model, range(0, Ms), steps, warm)
+    scale = args.M / Ms
+    value = 1.0 / (sec * scale)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": steps, "warmup": warm, "ms_per_step": sec * scale * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"C2 {args.M}x{args.N} K={args.K} mixed bernoulli/normal/poisson 30% missing",
+                       "note": "Julia/MatFac.jl unavailable: CPU restatement of the reference algorithm (oracle)"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{Ms} of {args.M} samples x all {args.N} features, {steps} timed iterations, "
+                                       f"time scaled x{scale:.0f}"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import pathmatfac_b200 as P
+    from pathmatfac_b200 import _lib
+    from pathmatfac_b200.dist import ShardedFit
+    from pathmatfac_b200.simulate import C2_BLOCKS, scale_blocks, simulate_problem
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (libpmf has no CPU path)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    kernel = {"auto": _lib.KERNEL_AUTO, "ffma": _lib.KERNEL_FFMA, "tc": _lib.KERNEL_TC}[args.kernel]
+    M, N, K = args.M, args.N, args.K
+    # pinned host buffer for the data so the end-to-end leg copies at PCIe speed
+    pinned = torch.empty((N, M), dtype=torch.float32, pin_memory=True)
+    D = pinned.numpy().T            # (M, N) Fortran-ordered view of the pinned [N][M] buffer
+    model = simulate_problem(M, blocks=scale_blocks(C2_BLOCKS, N), K=K, seed=2 + rank, missing=C2["missing"],
+                             data_out=D, model_kwargs=dict(lambda_X_l2=1.0))
+    if world > 1:   # replicated parameters must be identical on every rank
+        import torch.distributed as dist
+        for arr in (model.matfac.Y, model.matfac.col_transform.layers[0].logsigma, model.matfac.col_transform.layers[2].mu):
+            t = torch.from_numpy(arr).cuda()
+            dist.broadcast(t, 0)
+            arr[...] = t.cpu().numpy()
+    X0, Y0 = model.matfac.X.copy(), model.matfac.Y.copy()
+
+    eng = P.Engine(model, device=local)
+    lr = 0.05
+    common = dict(lr=lr, update_X=1, update_Y=1, update_col_layers=1, kernel=kernel, precision=args.precision,
+                  no_terminate=1, check_every=1 << 20, rel_tol=0.0, abs_tol=0.0)
+
+    def run_epochs(first, last):
+        o = eng.make_opts(epoch=first, max_epochs=last, **common)
+        if world > 1:
+            return sharded.fit(o)
+        return eng.fit(o)
+
+    sharded = ShardedFit(eng) if world > 1 else None
+    eng.reset_opt_state(1e-8)
+    # ---- warm-up ---------------------------------------------------------------------------------
+    run_epochs(1, args.warmup)
+    torch.cuda.synchronize()
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    # ---- timed region: exactly K steps, device-timed, max over ranks -------------------------------
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    eng.set_profiling(True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stream = torch.cuda.current_stream()
+    if world == 1:
+        eng.set_stream(stream.cuda_stream)
+    torch.cuda.synchronize()
+    ev0.record(stream)
+    h = run_epochs(args.warmup + 1, args.warmup + args.steps)
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        dist.barrier()
+    clocks = sampler.summary() if sampler else None
+    n_prof, dp_mean_ms, dp_min_ms = eng.get_profile()
+    eng.set_profiling(False)
+    launches = h["kernel_launches"]
+    sec_per_step = ms / 1e3 / args.steps
+    value = world / sec_per_step            # C2-equivalent iterations/sec of the whole job
+    assert len(h["loss"]) == args.steps and all(np.isfinite(h["loss"])), "timed steps did not all run"
+
+    if rank != 0:
+        eng.close()
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (fused data pass) ---------------------------------------------
+    peak, peak_src = peaks()
+    Kp = (K + 7) // 8 * 8
+    alg_bytes = 4.0 * M * N + 2 * 4.0 * Kp * (M + N)     # A once + X,Y read + dX,dY written
+    achieved = alg_bytes / (dp_mean_ms * 1e-3) / 1e9 if dp_mean_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "fused data pass", "kernel_ms": dp_mean_ms, "kernel_min_ms": dp_min_ms,
+                "launches_timed": n_prof, "algorithmic_bytes": alg_bytes, "peak_source": peak_src,
+                "kernel_share_of_step": dp_mean_ms / (sec_per_step * 1e3)}
+
+    # ---- end to end through the reference-facing call with host buffers ---------------------------
+    e2e = None
+    eng.close()
+    if not args.no_e2e and world == 1:
+        model.matfac.X[...] = X0
+        model.matfac.Y[...] = Y0
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        he = P.mf_fit(model, lr=lr, max_epochs=args.steps, update_X=True, update_Y=True, update_col_layers=True,
+                      kernel=kernel, precision=args.precision, rel_tol=-1.0, abs_tol=-1.0, verbosity=0, device=local,
+                      check_every=1 << 20)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        e2e = {"value": he["epochs"] / dt, "unit": UNIT,
+               "h2d_bytes_per_step": he["h2d_bytes"] / max(he["epochs"], 1),
+               "d2h_bytes_per_step": he["d2h_bytes"] / max(he["epochs"], 1),
+               "call": f"mf_fit(model; max_epochs={args.steps}) on a host-resident model: create handle, H2D of "
+                       f"data (pinned) + parameters, {he['epochs']} epochs, D2H of parameters + history",
+               "epochs_run": he["epochs"], "seconds": dt}
+
+    # ---- CPU baseline beside it (bounded sample, rank 0) -----------------------------------------------
+    cpu = None
+    if not args.no_cpu:
+        Ms = 250
+        sec = cpu_iterations(model, range(0, Ms), 2, 1)
+        scale = M / Ms
+        cpu = {"value": 1.0 / (sec * scale), "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+               "sample": f"first {Ms} of {M} samples x all {N} features, 2 timed iterations of the NumPy restatement "
+                         f"(float32, BLAS threads = all cores), time scaled x{scale:.0f}"}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": sec_per_step * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"C2 (BASELINE configs[1]): {M}x{N} K={K}, bernoulli/normal/normal/poisson views, "
+                                   f"{int(C2['missing'] * 100)}% missing, L2 on X, per-view L2 on Y, column-layer regs",
+                       "per_rank_samples": M, "parallelism": f"sample-sharded x{world}" if world > 1 else "single GPU",
+                       "kernel": args.kernel, "precision": args.precision,
+                       "l2_flush": "inputs (1.2 GB of A per step) exceed the 126 MB L2",
+                       "value_definition": "C2-equivalent iterations/sec = n_gpus / seconds per step"},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
+            "loss_first_last": [h["loss"][0], h["loss"][-1]]}
+    print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

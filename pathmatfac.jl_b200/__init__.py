@@ -1,0 +1,17 @@
+"""pathmatfac.jl_b200 -- B200-native fit-loop hot path of PathMatFac.jl.
+
+Holds the CUDA kernels + C ABI (``csrc/``, built into ``libpmf.so``) and the host-side
+mirror of the reference interface for that path (``PathMatFacModel``, ``mf_fit``,
+``mf_fit_adapt_lr``).  Import it as ``pathmatfac_b200`` (the directory name carries a dot;
+``pathmatfac_b200.py`` at the repo root is the import alias)."""
+from .fit import AdaGrad, Engine, cpu, gpu, mf_fit, mf_fit_adapt_lr
+from .layers import (BatchArray, BatchScale, BatchShift, ColScale, ColShift, FrozenLayer,
+                     ViewableComposition, construct_model_layers, freeze_layer, unfreeze_layer)
+from .model import CompositeNoise, MatFacModel, PathMatFacModel
+from .regularizers import (ARDRegularizer, BatchArrayReg, ColParamReg, CompositeRegularizer,
+                           FeatureSetARDReg, FrozenRegularizer, GroupRegularizer, L2Regularizer,
+                           NetworkRegularizer, SelectiveL1Reg, SequenceReg, ZeroReg,
+                           construct_featureset_ard, construct_layer_reg, construct_X_reg,
+                           construct_Y_reg, freeze_reg, unfreeze_reg)
+
+__all__ = [n for n in dir() if not n.startswith("_")]

@@ -1,0 +1,973 @@
+// C ABI of libpmf (include/pmf.h): handle, marshalling, epoch orchestration.
+// The only execution engine behind this ABI is CUDA; there is no CPU path.
+#include "../../include/pmf.h"
+#include "pmf_internal.h"
+#include "pmf_host.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace pmf;
+
+static thread_local std::string g_last_error;
+
+static int fail(pmf_model_s* h, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf;
+    g_last_error = buf;
+    return code;
+}
+
+#define CU(h, expr)                                                                              \
+    do {                                                                                         \
+        cudaError_t e__ = (expr);                                                                \
+        if (e__ != cudaSuccess) {                                                                \
+            (h)->cuda_failed = true;                                                             \
+            return fail((h), PMF_ERR_CUDA, "CUDA error %s at %s:%d (%s)", cudaGetErrorString(e__), \
+                        __FILE__, __LINE__, #expr);                                              \
+        }                                                                                        \
+    } while (0)
+
+#define CHECK_H(h)                                                              \
+    do {                                                                        \
+        if (!(h)) return fail(nullptr, PMF_ERR_ARG, "null handle");             \
+        if ((h)->cuda_failed) return PMF_ERR_CUDA;                              \
+        cudaError_t e0__ = cudaSetDevice((h)->dims.device);                     \
+        if (e0__ != cudaSuccess) {                                              \
+            return fail((h), PMF_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e0__)); \
+        }                                                                       \
+    } while (0)
+
+static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+template <class T>
+static cudaError_t dev_alloc(T** p, size_t n) {
+    *p = nullptr;
+    if (n == 0) return cudaSuccess;
+    return cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T));
+}
+template <class T>
+static void dev_free(T*& p) {
+    if (p) cudaFree((void*)p);
+    p = nullptr;
+}
+
+// host [rows][w] (pitch w) -> device [rows][wd] (pitch wd)
+static cudaError_t up2d(float* dst, int wd, const float* src, int w, int rows, cudaStream_t s) {
+    return cudaMemcpy2DAsync(dst, (size_t)wd * 4, src, (size_t)w * 4, (size_t)w * 4, rows, cudaMemcpyHostToDevice, s);
+}
+static cudaError_t down2d(float* dst, int w, const float* src, int wd, int rows, cudaStream_t s) {
+    return cudaMemcpy2DAsync(dst, (size_t)w * 4, src, (size_t)wd * 4, (size_t)w * 4, rows, cudaMemcpyDeviceToHost, s);
+}
+
+extern "C" {
+
+const char* pmf_version(void) { return "libpmf 0.1 (sm_100a)"; }
+
+const char* pmf_last_error(pmf_handle h) { return h ? h->err.c_str() : g_last_error.c_str(); }
+
+int pmf_create(const pmf_dims* d, pmf_handle* out) {
+    if (!d || !out) return fail(nullptr, PMF_ERR_ARG, "null argument");
+    if (d->M <= 0 || d->N <= 0 || d->K <= 0) return fail(nullptr, PMF_ERR_ARG, "M, N, K must be positive");
+    if (d->K > 256) return fail(nullptr, PMF_ERR_ARG, "K > 256 is not supported");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, PMF_ERR_CUDA, "no CUDA device: libpmf has no CPU path (%s)", cudaGetErrorString(e));
+    if (d->device < 0 || d->device >= ndev) return fail(nullptr, PMF_ERR_ARG, "bad device ordinal %d", d->device);
+    pmf_model_s* h = new pmf_model_s();
+    h->dims = *d;
+    h->M = d->M; h->N = d->N; h->K = d->K;
+    h->Kp = round_up(d->K, 8);
+    h->lda = round_up(d->M, 32);
+    h->Mp = round_up(d->M, 128);
+    h->Np = round_up(d->N, 128);
+    if ((e = cudaSetDevice(d->device)) != cudaSuccess) {
+        delete h;
+        return fail(nullptr, PMF_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    }
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, d->device);
+    h->n_sms = prop.multiProcessorCount;
+    h->cc_major = prop.major;
+    cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
+    h->stream = h->own_stream;
+    cudaEventCreate(&h->ev0);
+    cudaEventCreate(&h->ev1);
+    const size_t xk = (size_t)h->Mp * h->Kp, yk = (size_t)h->Np * h->Kp;
+    bool ok = true;
+    ok &= dev_alloc(&h->A, (size_t)h->N * h->lda) == cudaSuccess;
+    ok &= dev_alloc(&h->X, xk) == cudaSuccess && dev_alloc(&h->dX, xk) == cudaSuccess && dev_alloc(&h->accX, xk) == cudaSuccess;
+    ok &= dev_alloc(&h->Y, yk) == cudaSuccess && dev_alloc(&h->accY, yk) == cudaSuccess;
+    ok &= dev_alloc(&h->weight, h->Np) == cudaSuccess && dev_alloc(&h->colinfo, h->Np) == cudaSuccess;
+    ok &= dev_alloc(&h->scalars, SC_COUNT) == cudaSuccess && dev_alloc(&h->ctrl, 1) == cudaSuccess;
+    ok &= dev_alloc(&h->thresholds, 4) == cudaSuccess;
+    if (!ok) {
+        pmf_destroy(h);
+        return fail(nullptr, PMF_ERR_ALLOC, "device allocation failed (A needs %.2f GB)", (double)h->N * h->lda * 4e-9);
+    }
+    cudaMemset(h->X, 0, xk * 4); cudaMemset(h->Y, 0, yk * 4);
+    cudaMemset(h->colinfo, 0, (size_t)h->Np * 4);
+    cudaMemset(h->thresholds, 0, 16);
+    cudaMemset(h->ctrl, 0, sizeof(FitControl));
+    std::vector<float> ones(h->Np, 1.f);
+    cudaMemcpy(h->weight, ones.data(), (size_t)h->Np * 4, cudaMemcpyHostToDevice);
+    cudaMallocHost((void**)&h->ctrl_host, sizeof(FitControl));
+    int rc = h->realloc_vectors(0);   // no batch views yet
+    if (rc != 0) { pmf_destroy(h); return fail(nullptr, PMF_ERR_ALLOC, "device allocation failed"); }
+    pmf_reset_opt_state(h, 1e-8f);
+    if (cudaDeviceSynchronize() != cudaSuccess) { pmf_destroy(h); return fail(nullptr, PMF_ERR_CUDA, "init failed"); }
+    *out = h;
+    return PMF_OK;
+}
+
+int pmf_destroy(pmf_handle h) {
+    if (!h) return PMF_OK;
+    cudaSetDevice(h->dims.device);
+    cudaDeviceSynchronize();
+    dev_free(h->A); dev_free(h->X); dev_free(h->dX); dev_free(h->accX); dev_free(h->Y); dev_free(h->accY);
+    dev_free(h->XT); dev_free(h->YT);
+    dev_free(h->weight); dev_free(h->colinfo); dev_free(h->thresholds); dev_free(h->scalars); dev_free(h->ctrl);
+    dev_free(h->vp); dev_free(h->sg); dev_free(h->accvp); dev_free(h->regw); dev_free(h->regc);
+    dev_free(h->bcol_off); dev_free(h->bcol_view); dev_free(h->bcol_nb); dev_free(h->batch_of_sample);
+    dev_free(h->hist); dev_free(h->col_ssq); dev_free(h->col_cnt);
+    for (int s = 0; s < 2; ++s) h->reg[s].free_all();
+    if (h->ctrl_host) cudaFreeHost(h->ctrl_host);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    for (cudaEvent_t ev : h->prof_ev) cudaEventDestroy(ev);
+    delete h;
+    return PMF_OK;
+}
+
+int pmf_set_stream(pmf_handle h, void* s) {
+    CHECK_H(h);
+    h->stream = s ? (cudaStream_t)s : h->own_stream;
+    return PMF_OK;
+}
+
+int pmf_set_data(pmf_handle h, const float* A) {
+    CHECK_H(h);
+    if (!A) return fail(h, PMF_ERR_ARG, "null data");
+    CU(h, cudaMemsetAsync(h->A, 0xFF, (size_t)h->N * h->lda * 4, h->stream));   // NaN padding
+    CU(h, up2d(h->A, h->lda, A, h->M, h->N, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    h->have_data = true;
+    return PMF_OK;
+}
+
+int pmf_set_factors(pmf_handle h, const float* X, const float* Y) {
+    CHECK_H(h);
+    if (X) CU(h, up2d(h->X, h->Kp, X, h->K, h->M, h->stream));
+    if (Y) CU(h, up2d(h->Y, h->Kp, Y, h->K, h->N, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    h->transposes_stale = true;
+    return PMF_OK;
+}
+
+int pmf_get_factors(pmf_handle h, float* X, float* Y) {
+    CHECK_H(h);
+    if (X) CU(h, down2d(X, h->K, h->X, h->Kp, h->M, h->stream));
+    if (Y) CU(h, down2d(Y, h->K, h->Y, h->Kp, h->N, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return PMF_OK;
+}
+
+int pmf_set_noise(pmf_handle h, int32_t n_ranges, const int32_t* cs, const int32_t* ce, const int32_t* dist,
+                  const float* thresholds, const float* weight) {
+    CHECK_H(h);
+    if (n_ranges <= 0 || !cs || !ce || !dist) return fail(h, PMF_ERR_ARG, "bad noise ranges");
+    std::vector<int32_t> ci(h->Np, 0);
+    std::vector<char> seen(h->N, 0);
+    for (int r = 0; r < n_ranges; ++r) {
+        if (cs[r] < 0 || ce[r] > h->N || cs[r] > ce[r]) return fail(h, PMF_ERR_ARG, "noise range %d out of bounds", r);
+        if (dist[r] < 0 || dist[r] > 5) return fail(h, PMF_ERR_ARG, "unknown distribution code %d", dist[r]);
+        for (int j = cs[r]; j < ce[r]; ++j) {
+            if (seen[j]) return fail(h, PMF_ERR_ARG, "noise ranges overlap at column %d", j);
+            seen[j] = 1;
+            ci[j] = dist[r] | (r << 8);
+        }
+    }
+    for (int j = 0; j < h->N; ++j)
+        if (!seen[j]) return fail(h, PMF_ERR_ARG, "column %d has no noise model", j);
+    dev_free(h->thresholds);
+    CU(h, dev_alloc(&h->thresholds, (size_t)4 * n_ranges));
+    std::vector<float> th(4 * (size_t)n_ranges, 0.f);
+    if (thresholds) std::memcpy(th.data(), thresholds, th.size() * 4);
+    CU(h, cudaMemcpy(h->thresholds, th.data(), th.size() * 4, cudaMemcpyHostToDevice));
+    CU(h, cudaMemcpy(h->colinfo, ci.data(), (size_t)h->Np * 4, cudaMemcpyHostToDevice));
+    if (weight) CU(h, cudaMemcpy(h->weight, weight, (size_t)h->N * 4, cudaMemcpyHostToDevice));
+    h->have_noise = true;
+    return PMF_OK;
+}
+
+int pmf_set_col_params(pmf_handle h, const float* logsigma, const float* mu) {
+    CHECK_H(h);
+    if (logsigma) CU(h, cudaMemcpy(h->logsigma(), logsigma, (size_t)h->N * 4, cudaMemcpyHostToDevice));
+    if (mu) CU(h, cudaMemcpy(h->mu(), mu, (size_t)h->N * 4, cudaMemcpyHostToDevice));
+    return PMF_OK;
+}
+
+int pmf_get_col_params(pmf_handle h, float* logsigma, float* mu) {
+    CHECK_H(h);
+    CU(h, cudaStreamSynchronize(h->stream));
+    if (logsigma) CU(h, cudaMemcpy(logsigma, h->logsigma(), (size_t)h->N * 4, cudaMemcpyDeviceToHost));
+    if (mu) CU(h, cudaMemcpy(mu, h->mu(), (size_t)h->N * 4, cudaMemcpyDeviceToHost));
+    return PMF_OK;
+}
+
+int pmf_set_batch_layout(pmf_handle h, int32_t n_views, const int32_t* cs, const int32_t* ce, const int32_t* nb,
+                         const int32_t* bos) {
+    CHECK_H(h);
+    if (n_views < 0 || (n_views > 0 && (!cs || !ce || !nb || !bos))) return fail(h, PMF_ERR_ARG, "bad batch layout");
+    CU(h, cudaStreamSynchronize(h->stream));
+    // keep logsigma / mu across the re-allocation
+    std::vector<float> ls(h->N), mu(h->N);
+    CU(h, cudaMemcpy(ls.data(), h->logsigma(), (size_t)h->N * 4, cudaMemcpyDeviceToHost));
+    CU(h, cudaMemcpy(mu.data(), h->mu(), (size_t)h->N * 4, cudaMemcpyDeviceToHost));
+    h->views.clear();
+    int64_t off = 0;
+    int prev_end = 0, nb_max = 0;
+    for (int v = 0; v < n_views; ++v) {
+        if (cs[v] < prev_end || ce[v] > h->N || cs[v] >= ce[v] || nb[v] <= 0)
+            return fail(h, PMF_ERR_ARG, "batch view %d: bad column range or batch count", v);
+        prev_end = ce[v];
+        BatchView bv{cs[v], ce[v], nb[v], off};
+        off += (int64_t)(ce[v] - cs[v]) * nb[v];
+        nb_max = std::max(nb_max, nb[v]);
+        h->views.push_back(bv);
+    }
+    if (off > (int64_t)INT32_MAX) return fail(h, PMF_ERR_ARG, "batch table too large");
+    h->nb_max = nb_max;
+    if (h->realloc_vectors((int)off) != 0) return fail(h, PMF_ERR_ALLOC, "device allocation failed");
+    CU(h, cudaMemcpy(h->logsigma(), ls.data(), (size_t)h->N * 4, cudaMemcpyHostToDevice));
+    CU(h, cudaMemcpy(h->mu(), mu.data(), (size_t)h->N * 4, cudaMemcpyHostToDevice));
+    dev_free(h->bcol_off); dev_free(h->bcol_view); dev_free(h->bcol_nb); dev_free(h->batch_of_sample);
+    if (n_views > 0) {
+        std::vector<int32_t> coff(h->Np, -1), cview(h->Np, -1), cnb(h->Np, 0);
+        for (int v = 0; v < n_views; ++v)
+            for (int j = cs[v]; j < ce[v]; ++j) {
+                coff[j] = (int32_t)(h->views[v].offset + (int64_t)(j - cs[v]) * nb[v]);
+                cview[j] = v;
+                cnb[j] = nb[v];
+            }
+        std::vector<int32_t> b((size_t)n_views * h->Mp, 0);
+        for (int v = 0; v < n_views; ++v)
+            for (int i = 0; i < h->M; ++i) {
+                int32_t x = bos[(size_t)v * h->M + i];
+                if (x < 0 || x >= nb[v]) return fail(h, PMF_ERR_ARG, "batch_of_sample[%d][%d]=%d out of range", v, i, x);
+                b[(size_t)v * h->Mp + i] = x;
+            }
+        CU(h, dev_alloc(&h->bcol_off, h->Np)); CU(h, dev_alloc(&h->bcol_view, h->Np)); CU(h, dev_alloc(&h->bcol_nb, h->Np));
+        CU(h, dev_alloc(&h->batch_of_sample, b.size()));
+        CU(h, cudaMemcpy(h->bcol_off, coff.data(), (size_t)h->Np * 4, cudaMemcpyHostToDevice));
+        CU(h, cudaMemcpy(h->bcol_view, cview.data(), (size_t)h->Np * 4, cudaMemcpyHostToDevice));
+        CU(h, cudaMemcpy(h->bcol_nb, cnb.data(), (size_t)h->Np * 4, cudaMemcpyHostToDevice));
+        CU(h, cudaMemcpy(h->batch_of_sample, b.data(), b.size() * 4, cudaMemcpyHostToDevice));
+    }
+    return PMF_OK;
+}
+
+static int check_view(pmf_model_s* h, int v) {
+    if (v < 0 || v >= (int)h->views.size()) return fail(h, PMF_ERR_ARG, "batch view %d does not exist", v);
+    return 0;
+}
+
+int pmf_set_batch_values(pmf_handle h, int32_t v, const float* logdelta, const float* theta) {
+    CHECK_H(h);
+    if (check_view(h, v)) return PMF_ERR_ARG;
+    const BatchView& bv = h->views[v];
+    size_t n = (size_t)(bv.col_stop - bv.col_start) * bv.n_batches;
+    if (logdelta) CU(h, cudaMemcpy(h->logdelta() + bv.offset, logdelta, n * 4, cudaMemcpyHostToDevice));
+    if (theta) CU(h, cudaMemcpy(h->theta() + bv.offset, theta, n * 4, cudaMemcpyHostToDevice));
+    return PMF_OK;
+}
+
+int pmf_get_batch_values(pmf_handle h, int32_t v, float* logdelta, float* theta) {
+    CHECK_H(h);
+    if (check_view(h, v)) return PMF_ERR_ARG;
+    CU(h, cudaStreamSynchronize(h->stream));
+    const BatchView& bv = h->views[v];
+    size_t n = (size_t)(bv.col_stop - bv.col_start) * bv.n_batches;
+    if (logdelta) CU(h, cudaMemcpy(logdelta, h->logdelta() + bv.offset, n * 4, cudaMemcpyDeviceToHost));
+    if (theta) CU(h, cudaMemcpy(theta, h->theta() + bv.offset, n * 4, cudaMemcpyDeviceToHost));
+    return PMF_OK;
+}
+
+int pmf_get_batch_grads(pmf_handle h, int32_t v, float* dlogdelta, float* dtheta) {
+    CHECK_H(h);
+    if (check_view(h, v)) return PMF_ERR_ARG;
+    CU(h, cudaStreamSynchronize(h->stream));
+    const BatchView& bv = h->views[v];
+    size_t n = (size_t)(bv.col_stop - bv.col_start) * bv.n_batches;
+    if (dlogdelta) CU(h, cudaMemcpy(dlogdelta, h->g_logdelta() + bv.offset, n * 4, cudaMemcpyDeviceToHost));
+    if (dtheta) CU(h, cudaMemcpy(dtheta, h->g_theta() + bv.offset, n * 4, cudaMemcpyDeviceToHost));
+    return PMF_OK;
+}
+
+int pmf_set_frozen(pmf_handle h, uint32_t layer_mask, uint32_t reg_mask) {
+    CHECK_H(h);
+    h->frozen_layers = layer_mask & 0xF;
+    h->frozen_regs = reg_mask & 0xF;
+    return PMF_OK;
+}
+
+// ---- regularisers ----------------------------------------------------------------------------
+static int side_n(pmf_model_s* h, int which) { return which == 0 ? h->M : h->N; }
+
+int pmf_clear_reg(pmf_handle h, int32_t which) {
+    CHECK_H(h);
+    if (which < 0 || which > 1) return fail(h, PMF_ERR_ARG, "which must be 0 (X) or 1 (Y)");
+    CU(h, cudaStreamSynchronize(h->stream));
+    h->reg[which].free_all();
+    return PMF_OK;
+}
+
+static std::vector<float> pad_scale(const float* w, int K, int Kp, float p) {
+    std::vector<float> o(Kp, 0.f);
+    for (int k = 0; k < K; ++k) o[k] = p * w[k];
+    return o;
+}
+
+int pmf_set_reg_l2(pmf_handle h, int32_t which, const float* w, float p) {
+    CHECK_H(h);
+    if (which < 0 || which > 1 || !w) return fail(h, PMF_ERR_ARG, "bad L2 regulariser arguments");
+    SideReg& r = h->reg[which];
+    dev_free(r.l2_w);
+    auto o = pad_scale(w, h->K, h->Kp, p);
+    CU(h, dev_alloc(&r.l2_w, h->Kp));
+    CU(h, cudaMemcpy(r.l2_w, o.data(), (size_t)h->Kp * 4, cudaMemcpyHostToDevice));
+    return PMF_OK;
+}
+
+int pmf_set_reg_group(pmf_handle h, int32_t which, int32_t ng, const int32_t* st, const int32_t* en, const float* w, float p) {
+    CHECK_H(h);
+    if (which < 0 || which > 1 || ng <= 0 || !st || !en || !w) return fail(h, PMF_ERR_ARG, "bad group regulariser arguments");
+    const int n = side_n(h, which);
+    std::vector<int32_t> gid(n, -1);
+    for (int g = 0; g < ng; ++g) {
+        if (st[g] < 0 || en[g] > n || st[g] > en[g]) return fail(h, PMF_ERR_ARG, "group %d range out of bounds", g);
+        for (int i = st[g]; i < en[g]; ++i) gid[i] = g;
+    }
+    std::vector<float> gw((size_t)ng * h->Kp, 0.f);
+    for (int g = 0; g < ng; ++g)
+        for (int k = 0; k < h->K; ++k) gw[(size_t)g * h->Kp + k] = p * w[(size_t)g * h->K + k];
+    SideReg& r = h->reg[which];
+    dev_free(r.group_id); dev_free(r.group_w);
+    CU(h, dev_alloc(&r.group_id, n)); CU(h, dev_alloc(&r.group_w, gw.size()));
+    CU(h, cudaMemcpy(r.group_id, gid.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
+    CU(h, cudaMemcpy(r.group_w, gw.data(), gw.size() * 4, cudaMemcpyHostToDevice));
+    return PMF_OK;
+}
+
+int pmf_set_reg_sel_l1(pmf_handle h, int32_t which, const uint8_t* idx, const float* w, float p) {
+    CHECK_H(h);
+    if (which < 0 || which > 1 || !idx || !w) return fail(h, PMF_ERR_ARG, "bad selective-L1 arguments");
+    const int n = side_n(h, which);
+    std::vector<uint8_t> m((size_t)n * h->Kp, 0);
+    for (int i = 0; i < n; ++i)
+        for (int k = 0; k < h->K; ++k) m[(size_t)i * h->Kp + k] = idx[(size_t)i * h->K + k] ? 1 : 0;
+    SideReg& r = h->reg[which];
+    dev_free(r.l1_mask); dev_free(r.l1_w);
+    auto o = pad_scale(w, h->K, h->Kp, p);
+    CU(h, dev_alloc(&r.l1_mask, m.size())); CU(h, dev_alloc(&r.l1_w, h->Kp));
+    CU(h, cudaMemcpy(r.l1_mask, m.data(), m.size(), cudaMemcpyHostToDevice));
+    CU(h, cudaMemcpy(r.l1_w, o.data(), (size_t)h->Kp * 4, cudaMemcpyHostToDevice));
+    return PMF_OK;
+}
+
+int pmf_set_reg_ard(pmf_handle h, int32_t which, int32_t nr, const int32_t* st, const int32_t* en, const float* alpha,
+                    const float* beta) {
+    CHECK_H(h);
+    if (which < 0 || which > 1 || nr <= 0 || !st || !en || !alpha || !beta) return fail(h, PMF_ERR_ARG, "bad ARD arguments");
+    const int n = side_n(h, which);
+    // rows outside every range get no penalty: alpha = -0.5 makes (0.5 + alpha) vanish
+    std::vector<float> a(n, -0.5f), b(n, 1.f);
+    for (int r = 0; r < nr; ++r) {
+        if (st[r] < 0 || en[r] > n || st[r] > en[r]) return fail(h, PMF_ERR_ARG, "ARD range %d out of bounds", r);
+        for (int i = st[r]; i < en[r]; ++i) { a[i] = alpha[r]; b[i] = beta[r]; }
+    }
+    SideReg& r = h->reg[which];
+    dev_free(r.ard_alpha); dev_free(r.ard_beta_row); dev_free(r.ard_beta_full);
+    CU(h, dev_alloc(&r.ard_alpha, n)); CU(h, dev_alloc(&r.ard_beta_row, n));
+    CU(h, cudaMemcpy(r.ard_alpha, a.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
+    CU(h, cudaMemcpy(r.ard_beta_row, b.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
+    return PMF_OK;
+}
+
+int pmf_set_reg_fsard(pmf_handle h, int32_t which, const float* alpha, const float* beta) {
+    CHECK_H(h);
+    if (which < 0 || which > 1 || !alpha || !beta) return fail(h, PMF_ERR_ARG, "bad FSARD arguments");
+    const int n = side_n(h, which);
+    const int npad = which == 0 ? h->Mp : h->Np;
+    SideReg& r = h->reg[which];
+    dev_free(r.ard_alpha); dev_free(r.ard_beta_row); dev_free(r.ard_beta_full);
+    CU(h, dev_alloc(&r.ard_alpha, n)); CU(h, dev_alloc(&r.ard_beta_full, (size_t)npad * h->Kp));
+    CU(h, cudaMemcpy(r.ard_alpha, alpha, (size_t)n * 4, cudaMemcpyHostToDevice));
+    std::vector<float> ones((size_t)npad * h->Kp, 1.f);
+    CU(h, cudaMemcpy(r.ard_beta_full, ones.data(), ones.size() * 4, cudaMemcpyHostToDevice));
+    CU(h, up2d(r.ard_beta_full, h->Kp, beta, h->K, n, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return PMF_OK;
+}
+
+int pmf_get_fsard_beta(pmf_handle h, float* beta) {
+    CHECK_H(h);
+    SideReg& r = h->reg[1];
+    if (!r.ard_beta_full || !beta) return fail(h, PMF_ERR_STATE, "no FSARD regulariser on Y");
+    CU(h, down2d(beta, h->K, r.ard_beta_full, h->Kp, h->N, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return PMF_OK;
+}
+
+// builds the device copy of K concatenated CSR matrices
+static cudaError_t upload_csr(DevCsr& d, int K, const std::vector<int64_t>& rp_base, const std::vector<int64_t>& nnz_base,
+                              const int32_t* rowptr, int64_t rp_total, const int32_t* col, const float* val, int64_t nnz_total) {
+    cudaError_t e;
+    if ((e = dev_alloc(&d.rowptr, (size_t)rp_total)) != cudaSuccess) return e;
+    if ((e = dev_alloc(&d.col, (size_t)std::max<int64_t>(nnz_total, 1))) != cudaSuccess) return e;
+    if ((e = dev_alloc(&d.val, (size_t)std::max<int64_t>(nnz_total, 1))) != cudaSuccess) return e;
+    if ((e = dev_alloc(&d.rowptr_base, K)) != cudaSuccess) return e;
+    if ((e = dev_alloc(&d.nnz_base, K)) != cudaSuccess) return e;
+    cudaMemcpy(d.rowptr, rowptr, (size_t)rp_total * 4, cudaMemcpyHostToDevice);
+    if (nnz_total > 0) {
+        cudaMemcpy(d.col, col, (size_t)nnz_total * 4, cudaMemcpyHostToDevice);
+        cudaMemcpy(d.val, val, (size_t)nnz_total * 4, cudaMemcpyHostToDevice);
+    }
+    cudaMemcpy(d.rowptr_base, rp_base.data(), (size_t)K * 8, cudaMemcpyHostToDevice);
+    return cudaMemcpy(d.nnz_base, nnz_base.data(), (size_t)K * 8, cudaMemcpyHostToDevice);
+}
+
+int pmf_set_reg_network(pmf_handle h, int32_t which, const int32_t* nv, const int32_t* aa_rp, const int32_t* aa_c,
+                        const float* aa_v, const int32_t* ab_rp, const int32_t* ab_c, const float* ab_v,
+                        const int32_t* bb_rp, const int32_t* bb_c, const float* bb_v, const float* xv, float p,
+                        float rtol, float atol, int32_t itmax) {
+    CHECK_H(h);
+    if (which < 0 || which > 1 || !nv || !aa_rp || !ab_rp || !bb_rp) return fail(h, PMF_ERR_ARG, "bad network regulariser arguments");
+    const int n = side_n(h, which), K = h->K;
+    SideReg& r = h->reg[which];
+    r.net.free_all();
+    DevNetwork& net = r.net;
+    std::vector<int64_t> aa_rb(K), aa_nb(K), ab_rb(K), ab_nb(K), bb_rb(K), bb_nb(K), vb(K);
+    int64_t aa_rt = 0, aa_nt = 0, ab_rt = 0, ab_nt = 0, bb_rt = 0, bb_nt = 0, vt = 0;
+    for (int k = 0; k < K; ++k) {
+        if (nv[k] < 0) return fail(h, PMF_ERR_ARG, "nv[%d] < 0", k);
+        aa_rb[k] = aa_rt; aa_nb[k] = aa_nt; aa_nt += aa_rp[aa_rt + n]; aa_rt += n + 1;
+        ab_rb[k] = ab_rt; ab_nb[k] = ab_nt; ab_nt += ab_rp[ab_rt + n]; ab_rt += n + 1;
+        bb_rb[k] = bb_rt; bb_nb[k] = bb_nt; bb_nt += bb_rp[bb_rt + nv[k]]; bb_rt += nv[k] + 1;
+        vb[k] = vt; vt += nv[k];
+    }
+    // AB^T per factor (CSR with nv rows) built on the host
+    std::vector<int32_t> abt_rp((size_t)bb_rt, 0), abt_c((size_t)std::max<int64_t>(ab_nt, 1));
+    std::vector<float> abt_v((size_t)std::max<int64_t>(ab_nt, 1));
+    for (int k = 0; k < K; ++k) {
+        const int32_t* rp = ab_rp + ab_rb[k];
+        const int32_t* c = ab_c + ab_nb[k];
+        const float* v = ab_v + ab_nb[k];
+        int32_t* trp = abt_rp.data() + bb_rb[k];
+        for (int j = 0; j < n; ++j)
+            for (int e = rp[j]; e < rp[j + 1]; ++e) {
+                if (c[e] < 0 || c[e] >= nv[k]) return fail(h, PMF_ERR_ARG, "AB column index out of range (factor %d)", k);
+                trp[c[e] + 1]++;
+            }
+        for (int u = 0; u < nv[k]; ++u) trp[u + 1] += trp[u];
+        std::vector<int32_t> fill(trp, trp + nv[k]);
+        for (int j = 0; j < n; ++j)
+            for (int e = rp[j]; e < rp[j + 1]; ++e) {
+                int32_t pos = fill[c[e]]++;
+                abt_c[ab_nb[k] + pos] = j;
+                abt_v[ab_nb[k] + pos] = v[e];
+            }
+    }
+    CU(h, upload_csr(net.AA, K, aa_rb, aa_nb, aa_rp, aa_rt, aa_c, aa_v, aa_nt));
+    CU(h, upload_csr(net.AB, K, ab_rb, ab_nb, ab_rp, ab_rt, ab_c, ab_v, ab_nt));
+    CU(h, upload_csr(net.BB, K, bb_rb, bb_nb, bb_rp, bb_rt, bb_c, bb_v, bb_nt));
+    CU(h, upload_csr(net.ABt, K, bb_rb, ab_nb, abt_rp.data(), bb_rt, abt_c.data(), abt_v.data(), ab_nt));
+    CU(h, dev_alloc(&net.nv, K)); CU(h, dev_alloc(&net.virt_base, K));
+    CU(h, cudaMemcpy(net.nv, nv, (size_t)K * 4, cudaMemcpyHostToDevice));
+    CU(h, cudaMemcpy(net.virt_base, vb.data(), (size_t)K * 8, cudaMemcpyHostToDevice));
+    CU(h, dev_alloc(&net.u, (size_t)std::max<int64_t>(vt, 1))); CU(h, dev_alloc(&net.work, (size_t)std::max<int64_t>(4 * vt, 1)));
+    CU(h, cudaMemset(net.u, 0, (size_t)std::max<int64_t>(vt, 1) * 4));
+    if (xv && vt > 0) CU(h, cudaMemcpy(net.u, xv, (size_t)vt * 4, cudaMemcpyHostToDevice));
+    net.nv_total = vt;
+    net.p = p;
+    const float deps = std::sqrt(1.1920929e-7f);
+    net.rtol = rtol > 0 ? rtol : deps;
+    net.atol = atol > 0 ? atol : deps;
+    net.itmax = itmax;
+    net.present = true;
+    return PMF_OK;
+}
+
+int pmf_get_network_virtual(pmf_handle h, int32_t which, float* xv) {
+    CHECK_H(h);
+    if (which < 0 || which > 1 || !h->reg[which].net.present) return fail(h, PMF_ERR_STATE, "no network regulariser");
+    CU(h, cudaStreamSynchronize(h->stream));
+    DevNetwork& net = h->reg[which].net;
+    if (net.nv_total > 0) CU(h, cudaMemcpy(xv, net.u, (size_t)net.nv_total * 4, cudaMemcpyDeviceToHost));
+    return PMF_OK;
+}
+
+int pmf_set_layer_reg_col(pmf_handle h, int32_t slot, const float* w, const float* c) {
+    CHECK_H(h);
+    if (slot != 1 && slot != 3) return fail(h, PMF_ERR_ARG, "column layer regulariser slot must be 1 or 3");
+    size_t off = slot == 1 ? 0 : (size_t)h->Np;
+    h->layer_reg_present[slot - 1] = (w != nullptr);
+    if (!w) return PMF_OK;
+    CU(h, cudaMemcpy(h->regw + off, w, (size_t)h->N * 4, cudaMemcpyHostToDevice));
+    if (c) CU(h, cudaMemcpy(h->regc + off, c, (size_t)h->N * 4, cudaMemcpyHostToDevice));
+    else CU(h, cudaMemset(h->regc + off, 0, (size_t)h->N * 4));
+    return PMF_OK;
+}
+
+int pmf_set_layer_reg_batch(pmf_handle h, int32_t slot, const float* w, const float* c) {
+    CHECK_H(h);
+    if (slot != 2 && slot != 4) return fail(h, PMF_ERR_ARG, "batch layer regulariser slot must be 2 or 4");
+    h->layer_reg_present[slot - 1] = (w != nullptr);
+    if (!w) return PMF_OK;
+    if (h->nbp == 0) return fail(h, PMF_ERR_STATE, "no batch layout set");
+    // expand per-(view, batch) weights / centres to one value per table entry
+    std::vector<float> ew((size_t)h->nbp), ec((size_t)h->nbp, 0.f);
+    size_t src = 0;
+    for (const BatchView& bv : h->views) {
+        for (int jl = 0; jl < bv.col_stop - bv.col_start; ++jl)
+            for (int b = 0; b < bv.n_batches; ++b) {
+                ew[bv.offset + (size_t)jl * bv.n_batches + b] = w[src + b];
+                if (c) ec[bv.offset + (size_t)jl * bv.n_batches + b] = c[src + b];
+            }
+        src += bv.n_batches;
+    }
+    size_t off = 2 * (size_t)h->Np + (slot == 2 ? 0 : (size_t)h->nbp);
+    CU(h, cudaMemcpy(h->regw + off, ew.data(), ew.size() * 4, cudaMemcpyHostToDevice));
+    CU(h, cudaMemcpy(h->regc + off, ec.data(), ec.size() * 4, cudaMemcpyHostToDevice));
+    return PMF_OK;
+}
+
+// ---- optimiser state -----------------------------------------------------------------------
+__global__ static void fill_kernel(float* p, size_t n, float v) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+int pmf_reset_opt_state(pmf_handle h, float eps) {
+    CHECK_H(h);
+    fill_kernel<<<296, 256, 0, h->stream>>>(h->accX, (size_t)h->Mp * h->Kp, eps);
+    fill_kernel<<<296, 256, 0, h->stream>>>(h->accY, (size_t)h->Np * h->Kp, eps);
+    fill_kernel<<<296, 256, 0, h->stream>>>(h->accvp, h->vp_len(), eps);
+    CU(h, cudaGetLastError());
+    CU(h, cudaStreamSynchronize(h->stream));
+    return PMF_OK;
+}
+
+static int opt_locate(pmf_model_s* h, int which, int view, float** base, int* rows, int* w, int* wd) {
+    switch (which) {
+    case 0: *base = h->accX; *rows = h->M; *w = h->K; *wd = h->Kp; return 0;
+    case 1: *base = h->accY; *rows = h->N; *w = h->K; *wd = h->Kp; return 0;
+    case 2: *base = h->accvp; *rows = 1; *w = h->N; *wd = h->N; return 0;
+    case 3: *base = h->accvp + h->Np; *rows = 1; *w = h->N; *wd = h->N; return 0;
+    case 4: case 5: {
+        if (check_view(h, view)) return -1;
+        const BatchView& bv = h->views[view];
+        *base = h->accvp + 2 * (size_t)h->Np + (which == 5 ? (size_t)h->nbp : 0) + bv.offset;
+        *rows = 1; *w = *wd = (bv.col_stop - bv.col_start) * bv.n_batches;
+        return 0;
+    }
+    default: fail(h, PMF_ERR_ARG, "bad optimiser-state selector %d", which); return -1;
+    }
+}
+
+int pmf_get_opt_state(pmf_handle h, int32_t which, int32_t view, float* acc) {
+    CHECK_H(h);
+    float* base; int rows, w, wd;
+    if (opt_locate(h, which, view, &base, &rows, &w, &wd)) return PMF_ERR_ARG;
+    CU(h, down2d(acc, w, base, wd, rows, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return PMF_OK;
+}
+
+int pmf_set_opt_state(pmf_handle h, int32_t which, int32_t view, const float* acc) {
+    CHECK_H(h);
+    float* base; int rows, w, wd;
+    if (opt_locate(h, which, view, &base, &rows, &w, &wd)) return PMF_ERR_ARG;
+    CU(h, up2d(base, wd, acc, w, rows, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return PMF_OK;
+}
+
+// ---- epoch orchestration ----------------------------------------------------------------------
+void pmf_default_fit_opts(pmf_fit_opts* o) {
+    std::memset(o, 0, sizeof *o);
+    o->max_epochs = 1000; o->epoch = 1; o->lr = 1.0f; o->adagrad_eps = 1e-8f;
+    o->rel_tol = 1e-5; o->abs_tol = 1e-5;       // src/fit.jl:934-935
+    o->kernel = PMF_KERNEL_AUTO; o->precision = 0; o->check_every = 8; o->no_terminate = 0;
+}
+
+static int ready(pmf_model_s* h) {
+    if (!h->have_data) return fail(h, PMF_ERR_STATE, "pmf_set_data has not been called");
+    if (!h->have_noise) return fail(h, PMF_ERR_STATE, "pmf_set_noise has not been called");
+    return 0;
+}
+
+static void fill_data_params(pmf_model_s* h, DataPassParams& p, bool use_stop) {
+    std::memset(&p, 0, sizeof p);
+    p.M = h->M; p.N = h->N; p.Kp = h->Kp; p.lda = h->lda; p.Mp = h->Mp; p.Np = h->Np;
+    p.A = h->A; p.X = h->X; p.Y = h->Y;
+    p.logsigma = h->logsigma(); p.mu = h->mu(); p.weight = h->weight;
+    p.colinfo = h->colinfo; p.thresholds = h->thresholds;
+    p.n_batch_views = (int)h->views.size(); p.nb_max = h->nb_max;
+    p.bcol_off = h->bcol_off; p.bcol_view = h->bcol_view; p.bcol_nb = h->bcol_nb;
+    p.batch_of_sample = h->batch_of_sample;
+    p.logdelta = h->logdelta(); p.theta = h->theta();
+    p.dX = h->dX; p.dY = h->g_Y(); p.dlogsigma = h->g_logsigma(); p.dmu = h->g_mu();
+    p.dlogdelta = h->g_logdelta(); p.dtheta = h->g_theta();
+    p.scalars = h->scalars;
+    p.stop_flag = use_stop ? &h->ctrl->stop : nullptr;
+    p.sample_chunks = 0;
+    p.ordinal_eps = 1e-10f; p.hinge_margin = 1.0f;
+}
+
+// zero gradients + data pass (+ X-side penalties: loss and pullback added into dX)
+static int phase_begin(pmf_model_s* h, const pmf_fit_opts* o, bool use_stop, bool include_reg) {
+    cudaStream_t s = h->stream;
+    CU(h, cudaMemsetAsync(h->dX, 0, (size_t)h->Mp * h->Kp * 4, s));
+    CU(h, cudaMemsetAsync(h->sg, 0, h->sg_len() * 4, s));
+    CU(h, cudaMemsetAsync(h->scalars, 0, SC_COUNT * 8, s));
+    DataPassParams p;
+    fill_data_params(h, p, use_stop);
+    int kind = o ? o->kernel : PMF_KERNEL_AUTO;
+    int rc = h->run_data_pass(p, kind, o ? o->precision : 0);
+    if (rc != 0) return rc;
+    if (include_reg) {
+        const int* stop = use_stop ? &h->ctrl->stop : nullptr;
+        rc = h->run_factor_reg(0, stop);
+        if (rc != 0) return rc;
+    }
+    return 0;
+}
+
+// Y-side / layer penalties (loss + pullbacks added in place into the gradient buffers)
+static int phase_reg_shared(pmf_model_s* h, bool use_stop) {
+    const int* stop = use_stop ? &h->ctrl->stop : nullptr;
+    int rc = h->run_factor_reg(1, stop);
+    if (rc != 0) return rc;
+    return h->run_vector_pass(/*reg=*/true, /*update=*/false, 0.f, 0.f, stop, false);
+}
+
+static int phase_update(pmf_model_s* h, const pmf_fit_opts* o) {
+    const int* stop = &h->ctrl->stop;
+    int rc;
+    if (o->update_X && (rc = h->run_factor_update(0, o->lr, o->adagrad_eps, stop)) != 0) return rc;
+    if (o->update_Y && (rc = h->run_factor_update(1, o->lr, o->adagrad_eps, stop)) != 0) return rc;
+    if (o->update_col_layers && (rc = h->run_vector_pass(false, true, o->lr, o->adagrad_eps, stop, true)) != 0) return rc;
+    return 0;
+}
+
+int pmf_loss_grad(pmf_handle h, int32_t include_reg, pmf_losses* out, float* dX, float* dY, float* dls, float* dmu) {
+    CHECK_H(h);
+    if (ready(h)) return PMF_ERR_STATE;
+    pmf_fit_opts o;
+    pmf_default_fit_opts(&o);
+    o.kernel = h->loss_grad_kernel; o.precision = h->loss_grad_precision;
+    int rc = phase_begin(h, &o, false, include_reg != 0);
+    if (rc != 0) return rc;
+    if (include_reg && (rc = phase_reg_shared(h, false)) != 0) return rc;
+    CU(h, cudaStreamSynchronize(h->stream));
+    double sc[SC_COUNT];
+    CU(h, cudaMemcpy(sc, h->scalars, sizeof sc, cudaMemcpyDeviceToHost));
+    if (out) {
+        out->data = sc[SC_DATA]; out->x_reg = sc[SC_XREG]; out->y_reg = sc[SC_YREG]; out->layer_reg = sc[SC_LAYERREG];
+        out->total = sc[SC_DATA] + sc[SC_XREG] + sc[SC_YREG] + sc[SC_LAYERREG];
+    }
+    if (dX) CU(h, down2d(dX, h->K, h->dX, h->Kp, h->M, h->stream));
+    if (dY) CU(h, down2d(dY, h->K, h->g_Y(), h->Kp, h->N, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    if (dls) CU(h, cudaMemcpy(dls, h->g_logsigma(), (size_t)h->N * 4, cudaMemcpyDeviceToHost));
+    if (dmu) CU(h, cudaMemcpy(dmu, h->g_mu(), (size_t)h->N * 4, cudaMemcpyDeviceToHost));
+    return PMF_OK;
+}
+
+int pmf_fit_start(pmf_handle h, const pmf_fit_opts* o) {
+    CHECK_H(h);
+    if (!o) return fail(h, PMF_ERR_ARG, "null options");
+    if (ready(h)) return PMF_ERR_STATE;
+    if (o->epoch < 1 || o->max_epochs < o->epoch - 1) return fail(h, PMF_ERR_ARG, "bad epoch range [%d, %d]", o->epoch, o->max_epochs);
+    int cap = std::max(1, o->max_epochs - o->epoch + 1);
+    if (cap > h->hist_cap) {
+        dev_free(h->hist);
+        CU(h, dev_alloc(&h->hist, (size_t)5 * cap));
+        h->hist_cap = cap;
+    }
+    FitControl c;
+    std::memset(&c, 0, sizeof c);
+    c.term_code = PMF_TERM_MAX_EPOCHS;
+    c.epochs = o->epoch;
+    CU(h, cudaMemcpyAsync(h->ctrl, &c, sizeof c, cudaMemcpyHostToDevice, h->stream));
+    h->cur_epoch = o->epoch;
+    h->launches = 0;
+    return PMF_OK;
+}
+
+int pmf_epoch_begin(pmf_handle h, const pmf_fit_opts* o) {
+    CHECK_H(h);
+    if (!o) return fail(h, PMF_ERR_ARG, "null options");
+    return phase_begin(h, o, true, true);
+}
+
+int pmf_epoch_end(pmf_handle h, const pmf_fit_opts* o) {
+    CHECK_H(h);
+    if (!o) return fail(h, PMF_ERR_ARG, "null options");
+    int rc = phase_reg_shared(h, true);
+    if (rc != 0) return rc;
+    CU(h, launch_control(h->ctrl, h->scalars, h->hist, h->hist_cap, h->cur_epoch, o->no_terminate ? -1 : o->max_epochs, o->rel_tol, o->abs_tol, h->stream));
+    h->launches++;
+    rc = phase_update(h, o);
+    if (rc != 0) return rc;
+    h->cur_epoch++;
+    return PMF_OK;
+}
+
+int pmf_fit_poll(pmf_handle h, pmf_history* out, int32_t* stopped) {
+    CHECK_H(h);
+    CU(h, cudaMemcpyAsync(h->ctrl_host, h->ctrl, sizeof(FitControl), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    const FitControl& c = *h->ctrl_host;
+    if (stopped) *stopped = c.stop;
+    if (out) {
+        out->term_code = c.stop ? c.term_code : PMF_TERM_MAX_EPOCHS;
+        out->epochs = c.epochs;
+        int n = std::min(c.n_recorded, out->capacity);
+        n = std::min(n, h->hist_cap);
+        out->n_recorded = n;
+        if (n > 0) {
+            std::vector<double> hst((size_t)5 * n);
+            CU(h, cudaMemcpy(hst.data(), h->hist, hst.size() * 8, cudaMemcpyDeviceToHost));
+            for (int i = 0; i < n; ++i) {
+                if (out->loss_total) out->loss_total[i] = hst[5 * i + 0];
+                if (out->loss_data) out->loss_data[i] = hst[5 * i + 1];
+                if (out->loss_x_reg) out->loss_x_reg[i] = hst[5 * i + 2];
+                if (out->loss_y_reg) out->loss_y_reg[i] = hst[5 * i + 3];
+                if (out->loss_layer_reg) out->loss_layer_reg[i] = hst[5 * i + 4];
+            }
+        }
+        out->kernel_launches = h->launches;
+    }
+    return PMF_OK;
+}
+
+int pmf_fit(pmf_handle h, const pmf_fit_opts* o, pmf_history* out) {
+    CHECK_H(h);
+    int rc = pmf_fit_start(h, o);
+    if (rc != 0) return rc;
+    const int check = o->check_every > 0 ? o->check_every : 8;
+    CU(h, cudaEventRecord(h->ev0, h->stream));
+    int since = 0;
+    for (int e = o->epoch; e <= o->max_epochs; ++e) {
+        if ((rc = pmf_epoch_begin(h, o)) != 0) return rc;
+        if ((rc = pmf_epoch_end(h, o)) != 0) return rc;
+        if (++since >= check && e < o->max_epochs) {
+            since = 0;
+            CU(h, cudaMemcpyAsync(h->ctrl_host, h->ctrl, sizeof(FitControl), cudaMemcpyDeviceToHost, h->stream));
+            CU(h, cudaStreamSynchronize(h->stream));
+            if (h->ctrl_host->stop) break;
+        }
+    }
+    CU(h, cudaEventRecord(h->ev1, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    float ms = 0.f;
+    CU(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    pmf_history tmp;
+    std::memset(&tmp, 0, sizeof tmp);
+    pmf_history* dst = out ? out : &tmp;
+    rc = pmf_fit_poll(h, dst, nullptr);
+    dst->device_ms = ms;
+    return rc;
+}
+
+int pmf_shared_grad_buffer(pmf_handle h, void** p, int64_t* n) {
+    CHECK_H(h);
+    if (p) *p = h->sg;
+    if (n) *n = (int64_t)h->sg_len();
+    return PMF_OK;
+}
+
+int pmf_shared_scalar_buffer(pmf_handle h, void** p, int64_t* n) {
+    CHECK_H(h);
+    if (p) *p = h->scalars;
+    if (n) *n = 2;   // SC_DATA, SC_XREG are rank-local partial sums; the rest is replicated
+    return PMF_OK;
+}
+
+int pmf_column_stats(pmf_handle h, float* ssq, float* nonnan) {
+    CHECK_H(h);
+    if (ready(h)) return PMF_ERR_STATE;
+    if (!h->col_ssq) { CU(h, dev_alloc(&h->col_ssq, h->Np)); CU(h, dev_alloc(&h->col_cnt, h->Np)); }
+    CU(h, cudaMemsetAsync(h->col_ssq, 0, (size_t)h->Np * 4, h->stream));
+    CU(h, cudaMemsetAsync(h->col_cnt, 0, (size_t)h->Np * 4, h->stream));
+    DataPassParams p;
+    fill_data_params(h, p, false);
+    p.col_ssq = h->col_ssq; p.col_cnt = h->col_cnt;
+    CU(h, launch_data_pass_ffma(p, h->stream, h->n_sms));
+    CU(h, cudaStreamSynchronize(h->stream));
+    if (ssq) CU(h, cudaMemcpy(ssq, h->col_ssq, (size_t)h->N * 4, cudaMemcpyDeviceToHost));
+    if (nonnan) CU(h, cudaMemcpy(nonnan, h->col_cnt, (size_t)h->N * 4, cudaMemcpyDeviceToHost));
+    return PMF_OK;
+}
+
+/* test / bench hook (not part of the reference-facing surface): which kernel and precision
+ * pmf_loss_grad uses. */
+int pmf_set_loss_grad_kernel(pmf_handle h, int32_t kernel, int32_t precision) {
+    CHECK_H(h);
+    h->loss_grad_kernel = kernel;
+    h->loss_grad_precision = precision;
+    return PMF_OK;
+}
+
+int pmf_set_profiling(pmf_handle h, int32_t enable) {
+    CHECK_H(h);
+    h->profiling = enable != 0;
+    h->prof_used = 0;
+    return PMF_OK;
+}
+
+int pmf_get_profile(pmf_handle h, int32_t* n, float* mean_ms, float* min_ms) {
+    CHECK_H(h);
+    CU(h, cudaStreamSynchronize(h->stream));
+    double sum = 0.0;
+    float mn = 1e30f;
+    int cnt = 0;
+    for (size_t i = 0; i + 1 < h->prof_used; i += 2) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, h->prof_ev[i], h->prof_ev[i + 1]) == cudaSuccess) {
+            sum += ms; mn = ms < mn ? ms : mn; cnt++;
+        }
+    }
+    if (n) *n = cnt;
+    if (mean_ms) *mean_ms = cnt ? (float)(sum / cnt) : 0.f;
+    if (min_ms) *min_ms = cnt ? mn : 0.f;
+    return PMF_OK;
+}
+
+}  // extern "C"
+
+// ---- pmf_model_s members -------------------------------------------------------------------
+int pmf_model_s::realloc_vectors(int new_nbp) {
+    dev_free(vp); dev_free(sg); dev_free(accvp); dev_free(regw); dev_free(regc);
+    nbp = new_nbp;
+    const size_t nv = vp_len(), ng = sg_len();
+    if (dev_alloc(&vp, nv) != cudaSuccess || dev_alloc(&sg, ng) != cudaSuccess || dev_alloc(&accvp, nv) != cudaSuccess ||
+        dev_alloc(&regw, nv) != cudaSuccess || dev_alloc(&regc, nv) != cudaSuccess)
+        return -1;
+    cudaMemset(vp, 0, nv * 4); cudaMemset(sg, 0, ng * 4); cudaMemset(regw, 0, nv * 4); cudaMemset(regc, 0, nv * 4);
+    fill_kernel<<<64, 256>>>(accvp, nv, 1e-8f);
+    return cudaDeviceSynchronize() == cudaSuccess ? 0 : -1;
+}
+
+int pmf_model_s::run_data_pass(DataPassParams& p, int kind, int precision) {
+    (void)precision;
+    if (kind == PMF_KERNEL_TC) return fail(this, PMF_ERR_ARG, "tcgen05 kernel is not built into this library");
+    size_t smem = sizeof(float) * ((size_t)128 * (Kp + 4) + 64 * 68 + 2 * (size_t)64 * nb_max);
+    if (smem > 227 * 1024) return fail(this, PMF_ERR_ARG, "too many batches per view (%d) for K=%d", nb_max, K);
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (profiling) {
+        if (prof_used + 2 > prof_ev.size()) {
+            for (int i = 0; i < 2; ++i) { cudaEvent_t ev; cudaEventCreate(&ev); prof_ev.push_back(ev); }
+        }
+        e0 = prof_ev[prof_used]; e1 = prof_ev[prof_used + 1];
+        prof_used += 2;
+        cudaEventRecord(e0, stream);
+    }
+    cudaError_t e = launch_data_pass_ffma(p, stream, n_sms);
+    if (profiling) cudaEventRecord(e1, stream);
+    if (e != cudaSuccess) { cuda_failed = true; return fail(this, PMF_ERR_CUDA, "data pass launch: %s", cudaGetErrorString(e)); }
+    launches++;
+    return 0;
+}
+
+void pmf_model_s::fill_factor_params(int which, FactorUpdateParams& q) {
+    std::memset(&q, 0, sizeof q);
+    q.n = which == 0 ? M : N; q.Kp = Kp; q.K = K;
+    q.P = which == 0 ? X : Y;
+    q.grad = which == 0 ? dX : g_Y();
+    q.acc = which == 0 ? accX : accY;
+}
+
+int pmf_model_s::run_factor_reg(int which, const int* stop) {
+    SideReg& r = reg[which];
+    double* loss_out = scalars + (which == 0 ? SC_XREG : SC_YREG);
+    float* grad = which == 0 ? dX : g_Y();
+    if (r.net.present) {
+        NetworkParams q;
+        std::memset(&q, 0, sizeof q);
+        q.n = which == 0 ? M : N; q.Kp = Kp; q.K = K;
+        q.P = which == 0 ? X : Y; q.grad = grad;
+        auto cv = [](const DevCsr& d) { CsrBlock b{d.rowptr, d.col, d.val, d.rowptr_base, d.nnz_base}; return b; };
+        q.AA = cv(r.net.AA); q.AB = cv(r.net.AB); q.BB = cv(r.net.BB); q.ABt = cv(r.net.ABt);
+        q.nv = r.net.nv; q.virt_base = r.net.virt_base; q.u = r.net.u; q.work = r.net.work; q.nv_total = r.net.nv_total;
+        q.p = r.net.p; q.rtol = r.net.rtol; q.atol = r.net.atol; q.itmax = r.net.itmax;
+        q.loss_out = loss_out; q.stop_flag = stop;
+        cudaError_t e = launch_network_reg(q, stream);
+        if (e != cudaSuccess) { cuda_failed = true; return fail(this, PMF_ERR_CUDA, "network reg launch: %s", cudaGetErrorString(e)); }
+        launches++;
+    }
+    if (!r.any_elementwise()) return 0;
+    FactorUpdateParams q;
+    fill_factor_params(which, q);
+    q.grad_out = grad;                      // in-place: data gradient + penalty pullback
+    q.l2_w = r.l2_w; q.group_id = r.group_id; q.group_w = r.group_w;
+    q.l1_mask = r.l1_mask; q.l1_w = r.l1_w;
+    q.ard_alpha = r.ard_alpha; q.ard_beta_row = r.ard_beta_row; q.ard_beta_full = r.ard_beta_full;
+    q.loss_out = loss_out; q.do_update = 0; q.stop_flag = stop;
+    cudaError_t e = launch_factor_update(q, stream);
+    if (e != cudaSuccess) { cuda_failed = true; return fail(this, PMF_ERR_CUDA, "factor reg launch: %s", cudaGetErrorString(e)); }
+    launches++;
+    return 0;
+}
+
+int pmf_model_s::run_factor_update(int which, float lr, float eps, const int* stop) {
+    FactorUpdateParams q;
+    fill_factor_params(which, q);
+    q.do_update = 1; q.lr = lr; q.eps = eps; q.stop_flag = stop;
+    if (which == 0 && XT) { q.PT = XT; q.ldt = Mp; }
+    if (which == 1 && YT) { q.PT = YT; q.ldt = Np; }
+    cudaError_t e = launch_factor_update(q, stream);
+    if (e != cudaSuccess) { cuda_failed = true; return fail(this, PMF_ERR_CUDA, "factor update launch: %s", cudaGetErrorString(e)); }
+    launches++;
+    return 0;
+}
+
+// segments of the vector-parameter block: slot 1 logsigma, slot 3 mu, slot 2 logdelta, slot 4 theta
+int pmf_model_s::run_vector_pass(bool reg_pass, bool update, float lr, float eps, const int* stop, bool respect_frozen) {
+    struct Seg { size_t off; int n; int slot; };
+    Seg segs[4] = {{0, N, 1}, {(size_t)Np, N, 3}, {2 * (size_t)Np, (int)nbp, 2}, {2 * (size_t)Np + (size_t)nbp, (int)nbp, 4}};
+    for (const Seg& sgm : segs) {
+        if (sgm.n <= 0) continue;
+        const unsigned bit = 1u << (sgm.slot - 1);
+        VectorUpdateParams q;
+        std::memset(&q, 0, sizeof q);
+        q.n = sgm.n; q.p = vp + sgm.off; q.grad = sg + (size_t)Np * Kp + sgm.off; q.acc = accvp + sgm.off;
+        q.stop_flag = stop;
+        if (reg_pass) {
+            if (!layer_reg_present[sgm.slot - 1] || (frozen_regs & bit)) continue;
+            q.reg_w = regw + sgm.off; q.reg_c = regc + sgm.off; q.reg_active = 1;
+            q.grad_out = sg + (size_t)Np * Kp + sgm.off;
+            q.loss_out = scalars + SC_LAYERREG;
+        }
+        if (update) {
+            if (respect_frozen && (frozen_layers & bit)) continue;
+            q.do_update = 1; q.lr = lr; q.eps = eps;
+        }
+        cudaError_t e = launch_vector_update(q, stream);
+        if (e != cudaSuccess) { cuda_failed = true; return fail(this, PMF_ERR_CUDA, "vector pass launch: %s", cudaGetErrorString(e)); }
+        launches++;
+    }
+    return 0;
+}

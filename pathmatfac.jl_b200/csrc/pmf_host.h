@@ -1,0 +1,130 @@
+// Host-side handle behind the C ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/pmf.h"
+#include "pmf_internal.h"
+
+struct BatchView {
+    int col_start, col_stop, n_batches;
+    int64_t offset;   // into the flattened [column][batch] tables
+};
+
+struct DevCsr {
+    int32_t* rowptr = nullptr;
+    int32_t* col = nullptr;
+    float* val = nullptr;
+    int64_t* rowptr_base = nullptr;
+    int64_t* nnz_base = nullptr;
+    void free_all() {
+        cudaFree(rowptr); cudaFree(col); cudaFree(val); cudaFree(rowptr_base); cudaFree(nnz_base);
+        rowptr = col = nullptr; val = nullptr; rowptr_base = nnz_base = nullptr;
+    }
+};
+
+struct DevNetwork {
+    bool present = false;
+    DevCsr AA, AB, BB, ABt;
+    int32_t* nv = nullptr;
+    int64_t* virt_base = nullptr;
+    float* u = nullptr;
+    float* work = nullptr;
+    int64_t nv_total = 0;
+    float p = 1.f, rtol = 0.f, atol = 0.f;
+    int itmax = 0;
+    void free_all() {
+        AA.free_all(); AB.free_all(); BB.free_all(); ABt.free_all();
+        cudaFree(nv); cudaFree(virt_base); cudaFree(u); cudaFree(work);
+        nv = nullptr; virt_base = nullptr; u = work = nullptr;
+        present = false; nv_total = 0;
+    }
+};
+
+struct SideReg {
+    float* l2_w = nullptr;
+    int32_t* group_id = nullptr;
+    float* group_w = nullptr;
+    uint8_t* l1_mask = nullptr;
+    float* l1_w = nullptr;
+    float* ard_alpha = nullptr;
+    float* ard_beta_row = nullptr;
+    float* ard_beta_full = nullptr;
+    DevNetwork net;
+    bool any_elementwise() const { return l2_w || group_id || l1_mask || ard_alpha; }
+    void free_all() {
+        cudaFree(l2_w); cudaFree(group_id); cudaFree(group_w); cudaFree(l1_mask); cudaFree(l1_w);
+        cudaFree(ard_alpha); cudaFree(ard_beta_row); cudaFree(ard_beta_full);
+        l2_w = group_w = l1_w = ard_alpha = ard_beta_row = ard_beta_full = nullptr;
+        group_id = nullptr; l1_mask = nullptr;
+        net.free_all();
+    }
+};
+
+struct pmf_model_s {
+    pmf_dims dims{};
+    int M = 0, N = 0, K = 0, Kp = 0, lda = 0, Mp = 0, Np = 0;
+    int n_sms = 148, cc_major = 0;
+    std::string err;
+    bool cuda_failed = false;
+    bool have_data = false, have_noise = false;
+    bool transposes_stale = true;
+
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+    // data and factors
+    float* A = nullptr;
+    float *X = nullptr, *dX = nullptr, *accX = nullptr;
+    float *Y = nullptr, *accY = nullptr;
+    float *XT = nullptr, *YT = nullptr;      // k-major copies for the tcgen05 path (lazy)
+    // per-column noise description
+    float* weight = nullptr;
+    int32_t* colinfo = nullptr;
+    float* thresholds = nullptr;
+    // vector parameters  vp = [logsigma Np | mu Np | logdelta nbp | theta nbp]
+    // shared gradients   sg = [dY Np*Kp | dlogsigma Np | dmu Np | dlogdelta nbp | dtheta nbp]
+    float *vp = nullptr, *sg = nullptr, *accvp = nullptr, *regw = nullptr, *regc = nullptr;
+    int64_t nbp = 0;
+    int nb_max = 0;
+    std::vector<BatchView> views;
+    int32_t *bcol_off = nullptr, *bcol_view = nullptr, *bcol_nb = nullptr, *batch_of_sample = nullptr;
+    bool layer_reg_present[4] = {false, false, false, false};
+    uint32_t frozen_layers = 0, frozen_regs = 0;
+    SideReg reg[2];
+
+    double* scalars = nullptr;
+    pmf::FitControl* ctrl = nullptr;
+    pmf::FitControl* ctrl_host = nullptr;   // pinned
+    double* hist = nullptr;
+    int hist_cap = 0;
+    int cur_epoch = 1;
+    int64_t launches = 0;
+    float *col_ssq = nullptr, *col_cnt = nullptr;
+    int loss_grad_kernel = 0, loss_grad_precision = 0;
+    bool profiling = false;
+    std::vector<cudaEvent_t> prof_ev;    // pairs (start, stop) per bracketed data pass
+    size_t prof_used = 0;
+
+    size_t vp_len() const { return 2 * (size_t)Np + 2 * (size_t)nbp; }
+    size_t sg_len() const { return (size_t)Np * Kp + vp_len(); }
+    float* logsigma() { return vp; }
+    float* mu() { return vp + Np; }
+    float* logdelta() { return vp + 2 * (size_t)Np; }
+    float* theta() { return vp + 2 * (size_t)Np + nbp; }
+    float* g_Y() { return sg; }
+    float* g_logsigma() { return sg + (size_t)Np * Kp; }
+    float* g_mu() { return sg + (size_t)Np * Kp + Np; }
+    float* g_logdelta() { return sg + (size_t)Np * Kp + 2 * (size_t)Np; }
+    float* g_theta() { return sg + (size_t)Np * Kp + 2 * (size_t)Np + nbp; }
+
+    int realloc_vectors(int new_nbp);
+    int run_data_pass(pmf::DataPassParams& p, int kind, int precision);
+    void fill_factor_params(int which, pmf::FactorUpdateParams& q);
+    int run_factor_reg(int which, const int* stop);
+    int run_factor_update(int which, float lr, float eps, const int* stop);
+    int run_vector_pass(bool reg_pass, bool update, float lr, float eps, const int* stop, bool respect_frozen);
+};

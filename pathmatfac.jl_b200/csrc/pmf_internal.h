@@ -1,0 +1,136 @@
+// Internal device-side views shared by the kernels and the C-ABI translation unit.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pmf {
+
+// Number of double scalars in the shared scalar buffer.
+enum { SC_DATA = 0, SC_XREG = 1, SC_YREG = 2, SC_LAYERREG = 3, SC_COUNT = 8 };
+
+// Everything the fused data pass reads / accumulates.  Layouts:
+//   A  [N][lda]   feature-major, lda = roundup(M,32), padding = NaN (missing)
+//   X  [Mp][Kp], Y [Np][Kp]   row = sample / feature, k contiguous, zero padded
+//   per-column vectors have Np entries; batch tables are [view columns][n_b] flattened.
+struct DataPassParams {
+    int M, N, Kp, lda, Mp, Np;
+    const float* __restrict__ A;
+    const float* __restrict__ X;
+    const float* __restrict__ Y;
+    const float* __restrict__ logsigma;
+    const float* __restrict__ mu;
+    const float* __restrict__ weight;
+    const int32_t* __restrict__ colinfo;      // dist | range_id << 8
+    const float* __restrict__ thresholds;     // [n_ranges][4]
+    // batch layers (null / -1 when absent)
+    int n_batch_views;
+    int nb_max;                               // max n_batches over views
+    const int32_t* __restrict__ bcol_off;     // [Np] offset of column's n_b block, -1 = unbatched
+    const int32_t* __restrict__ bcol_view;    // [Np] view index of the column (-1)
+    const int32_t* __restrict__ bcol_nb;      // [Np] n_batches of the column's view
+    const int32_t* __restrict__ batch_of_sample;  // [n_views][Mp]
+    const float* __restrict__ logdelta;
+    const float* __restrict__ theta;
+    // outputs (accumulated with atomics; zeroed by the caller)
+    float* dX;          // [Mp][Kp]
+    float* dY;          // [Np][Kp]
+    float* dlogsigma;   // [Np]
+    float* dmu;         // [Np]
+    float* dlogdelta;   // batch table layout
+    float* dtheta;
+    double* scalars;    // SC_* ; data loss accumulated into scalars[SC_DATA]
+    // optional per-column statistics pass (pmf_column_stats)
+    float* col_ssq;     // [Np] sum_i g^2 or null
+    float* col_cnt;     // [Np] count of finite entries or null
+    const int* stop_flag;   // device flag: non-zero => the fit has terminated, do nothing
+    int sample_chunks;      // grid.y: number of sample chunks per feature tile
+    float ordinal_eps, hinge_margin;
+};
+
+// Elementwise regulariser + AdaGrad pass over a factor matrix P [n_pad][Kp].
+struct FactorUpdateParams {
+    int n, Kp, K;
+    float* P;
+    float* PT;                  // optional transposed copy [Kp][n_pad_t] kept in sync (TC path) or null
+    int ldt;
+    const float* grad;          // data gradient (already reduced over ranks)
+    float* grad_out;            // if non-null: data+reg gradient is written here (parity hook)
+    float* acc;                 // AdaGrad accumulator
+    // quadratic penalties
+    const float* l2_w;          // [Kp] (mixture weight folded in) or null
+    const int32_t* group_id;    // [n] or null
+    const float* group_w;       // [n_groups][Kp]
+    // selective L1
+    const uint8_t* l1_mask;     // [n][Kp] or null
+    const float* l1_w;          // [Kp]
+    // (FS)ARD
+    const float* ard_alpha;     // [n] or null
+    const float* ard_beta_row;  // [n] or null
+    const float* ard_beta_full; // [n][Kp] or null
+    double* loss_out;           // scalar accumulated (pre-update value of the penalty)
+    int do_update;
+    float lr, eps;
+    const int* stop_flag;
+};
+
+// 1-D parameters (logsigma | mu | logdelta | theta) with optional quadratic penalty.
+struct VectorUpdateParams {
+    int n;
+    float* p;
+    const float* grad;
+    float* grad_out;
+    float* acc;
+    const float* reg_w;         // per-element weight or null
+    const float* reg_c;         // per-element centre
+    double* loss_out;
+    int reg_active;             // 0 when the slot's regulariser is frozen / absent
+    int do_update;
+    float lr, eps;
+    const int* stop_flag;
+};
+
+struct FitControl {
+    int stop;            // set by the control kernel when a termination test fires
+    int term_code;
+    int epochs;          // index of the last epoch evaluated
+    int n_recorded;
+    double prev_loss;
+    int have_prev;
+    int pad;
+};
+
+struct CsrBlock {        // K concatenated CSR matrices
+    const int32_t* rowptr;   // per factor segment of (rows+1) entries, local offsets
+    const int32_t* col;
+    const float* val;
+    const int64_t* rowptr_base;  // [K] start of factor's rowptr segment
+    const int64_t* nnz_base;     // [K] start of factor's col/val segment
+};
+
+struct NetworkParams {
+    int n, Kp, K;
+    const float* P;          // [n_pad][Kp]
+    float* grad;             // += p * (AA y + AB u)
+    CsrBlock AA, AB, BB, ABt;  // ABt: CSR of AB^T (nv rows)
+    const int32_t* nv;       // [K]
+    const int64_t* virt_base;    // [K] offset into the virtual-node vectors
+    float* u;                // x_virtual (sign-flipped convention of the reference)
+    float* work;             // 4 * sum(nv) scratch: r, pvec, Ap, rhs
+    int64_t nv_total;
+    float p;
+    float rtol, atol;
+    int itmax;
+    double* loss_out;
+    const int* stop_flag;
+};
+
+// launchers (each defined next to its kernel)
+cudaError_t launch_data_pass_ffma(const DataPassParams& p, cudaStream_t s, int n_sms);
+cudaError_t launch_factor_update(const FactorUpdateParams& p, cudaStream_t s);
+cudaError_t launch_vector_update(const VectorUpdateParams& p, cudaStream_t s);
+cudaError_t launch_control(FitControl* ctrl, const double* scalars, double* hist, int hist_cap,
+                           int epoch, int max_epochs, double rel_tol, double abs_tol, cudaStream_t s);
+cudaError_t launch_network_reg(const NetworkParams& p, cudaStream_t s);
+cudaError_t launch_transpose_sync(const float* P, float* PT, int n, int Kp, int ldt, cudaStream_t s);
+
+}  // namespace pmf

@@ -1,0 +1,308 @@
+// Regulariser gradients + AdaGrad step (one fused elementwise pass per parameter array), the
+// device-side termination test, and the per-factor graph-Laplacian regulariser.
+//
+// Reference formulas: L2Regularizer (src/regularizers.jl:11-55), GroupRegularizer (:423-446),
+// SelectiveL1Reg (:106-163), ARDRegularizer (:526-609), FeatureSetARDReg value/pullback
+// (src/featureset_ard.jl:135-150), ColParamReg (:462-519), BatchArrayReg (:781-889),
+// NetworkRegularizer (:249-306), AdaGrad (src/optimizers.jl:6-13: acc += g^2;
+// p -= eta*g/(sqrt(acc)+eps)).
+#include "pmf_internal.h"
+#include "pmf_epilogue.cuh"
+
+namespace pmf {
+
+namespace {
+
+constexpr int UT = 256;
+
+__global__ void __launch_bounds__(UT) factor_update_kernel(FactorUpdateParams q) {
+    if (q.stop_flag != nullptr && *q.stop_flag != 0) return;
+    __shared__ double red_smem[UT / 32];
+    const int K4 = q.Kp >> 2;
+    const size_t total4 = (size_t)q.n * K4;
+    double lsum = 0.0;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total4;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        const int row = (int)(idx / K4), c4 = (int)(idx - (size_t)row * K4);
+        const size_t off = (size_t)row * q.Kp + 4 * c4;
+        float4 pv = *reinterpret_cast<const float4*>(q.P + off);
+        float4 gv = *reinterpret_cast<const float4*>(q.grad + off);
+        float pa[4] = {pv.x, pv.y, pv.z, pv.w};
+        float ga[4] = {gv.x, gv.y, gv.z, gv.w};
+        float loss = 0.f;
+        const int gid = q.group_id ? q.group_id[row] : -1;
+        const float al = q.ard_alpha ? q.ard_alpha[row] : 0.f;
+        const float brow = q.ard_beta_row ? q.ard_beta_row[row] : 1.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int k = 4 * c4 + c;
+            const float x = pa[c];
+            float w = 0.f;
+            if (q.l2_w) w += q.l2_w[k];
+            if (gid >= 0) w += q.group_w[(size_t)gid * q.Kp + k];
+            float g = ga[c] + w * x;
+            loss += 0.5f * w * x * x;
+            if (q.l1_mask && q.l1_mask[off + c]) {
+                float w1 = q.l1_w[k];
+                loss += w1 * fabsf(x);
+                g += w1 * (x > 0.f ? 1.f : (x < 0.f ? -1.f : 0.f));
+            }
+            if (q.ard_alpha && k < q.K) {
+                float beta = q.ard_beta_full ? q.ard_beta_full[off + c] : brow;
+                float b = 1.f + (0.5f / beta) * x * x;
+                loss += (0.5f + al) * logf(b);
+                g += (al + 0.5f) * x / (b * beta);
+            }
+            ga[c] = g;
+        }
+        lsum += (double)loss;
+        if (q.grad_out) *reinterpret_cast<float4*>(q.grad_out + off) = make_float4(ga[0], ga[1], ga[2], ga[3]);
+        if (q.do_update) {
+            float4 av = *reinterpret_cast<const float4*>(q.acc + off);
+            float aa[4] = {av.x, av.y, av.z, av.w};
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                aa[c] += ga[c] * ga[c];
+                pa[c] -= q.lr * ga[c] / (sqrtf(aa[c]) + q.eps);
+            }
+            *reinterpret_cast<float4*>(q.acc + off) = make_float4(aa[0], aa[1], aa[2], aa[3]);
+            *reinterpret_cast<float4*>(q.P + off) = make_float4(pa[0], pa[1], pa[2], pa[3]);
+            if (q.PT) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) q.PT[(size_t)(4 * c4 + c) * q.ldt + row] = pa[c];
+            }
+        }
+    }
+    double tot = block_reduce_sum_double(lsum, red_smem);
+    if (threadIdx.x == 0 && q.loss_out && tot != 0.0) atomicAdd(q.loss_out, tot);
+}
+
+__global__ void __launch_bounds__(UT) vector_update_kernel(VectorUpdateParams q) {
+    if (q.stop_flag != nullptr && *q.stop_flag != 0) return;
+    __shared__ double red_smem[UT / 32];
+    double lsum = 0.0;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < q.n; idx += gridDim.x * blockDim.x) {
+        float x = q.p[idx];
+        float g = q.grad[idx];
+        if (q.reg_active && q.reg_w) {
+            float w = q.reg_w[idx], d = x - q.reg_c[idx];
+            g += w * d;
+            lsum += (double)(0.5f * w * d * d);
+        }
+        if (q.grad_out) q.grad_out[idx] = g;
+        if (q.do_update) {
+            float a = q.acc[idx] + g * g;
+            q.acc[idx] = a;
+            q.p[idx] = x - q.lr * g / (sqrtf(a) + q.eps);
+        }
+    }
+    double tot = block_reduce_sum_double(lsum, red_smem);
+    if (threadIdx.x == 0 && q.loss_out && tot != 0.0) atomicAdd(q.loss_out, tot);
+}
+
+// Termination test of MF.fit!, evaluated on the device so the epoch loop
+// needs no host round trip: loss of this epoch (pre-update parameters) vs the previous one.
+__global__ void control_kernel(FitControl* c, const double* sc, double* hist, int hist_cap, int epoch,
+                               int max_epochs, double rel_tol, double abs_tol) {
+    if (c->stop) return;
+    const double total = sc[SC_DATA] + sc[SC_XREG] + sc[SC_YREG] + sc[SC_LAYERREG];
+    const int r = c->n_recorded;
+    if (r < hist_cap) {
+        hist[5 * r + 0] = total;
+        hist[5 * r + 1] = sc[SC_DATA];
+        hist[5 * r + 2] = sc[SC_XREG];
+        hist[5 * r + 3] = sc[SC_YREG];
+        hist[5 * r + 4] = sc[SC_LAYERREG];
+    }
+    c->n_recorded = r + 1;
+    c->epochs = epoch;
+    int code = -1;
+    if (max_epochs < 0) {
+        // bench hook (no_terminate): record the loss, never stop
+    } else if (!isfinite(total)) code = 4;                // nonfinite
+    else if (c->have_prev) {
+        double d = c->prev_loss - total;
+        if (d < 0) code = 3;                              // loss_increase
+        else if (fabs(d) < abs_tol) code = 1;             // abs_tol
+        else if (fabs(d / total) < rel_tol) code = 2;     // rel_tol
+    }
+    if (code >= 0) {
+        c->stop = 1;
+        c->term_code = code;
+        return;
+    }
+    c->prev_loss = total;
+    c->have_prev = 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Graph-Laplacian regulariser.  One CTA per latent factor k (the K Laplacians are independent,
+// src/regularizers.jl:169-183).  For its factor the CTA
+//   rhs  = AB_k' y_k                      (CSR of AB_k^T, sub-warp per row)
+//   u    = -cg(BB_k, rhs, warm start)     (Krylov.cg semantics, src/regularizers.jl:284)
+//   grad = AA_k y_k + AB_k u              (:285-299)      loss = .5 y'AAy + y'ABu + .5 u'BBu
+// with every vector of the solve living in L2-resident global scratch.
+// ---------------------------------------------------------------------------------------------
+constexpr int NTH = 512;
+
+__device__ __forceinline__ float block_sum(float v, float* sm) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) sm[w] = v;
+    __syncthreads();
+    float t = (threadIdx.x < NTH / 32) ? sm[threadIdx.x] : 0.f;
+    if (w == 0) {
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (l == 0) sm[0] = t;
+    }
+    __syncthreads();
+    t = sm[0];
+    __syncthreads();
+    return t;
+}
+
+// y = M x for a CSR segment; x gathered through (ptr, stride)
+__device__ __forceinline__ float csr_row_dot(const int32_t* __restrict__ rp, const int32_t* __restrict__ col,
+                                             const float* __restrict__ val, int row,
+                                             const float* __restrict__ x, int xstride) {
+    float s = 0.f;
+    for (int e = rp[row]; e < rp[row + 1]; ++e) s = fmaf(val[e], x[(size_t)col[e] * xstride], s);
+    return s;
+}
+
+__global__ void __launch_bounds__(NTH) network_reg_kernel(NetworkParams q) {
+    if (q.stop_flag != nullptr && *q.stop_flag != 0) return;
+    __shared__ float sm[NTH / 32];
+    const int k = blockIdx.x;
+    const int n = q.n, nv = q.nv[k];
+    const float* y = q.P + k;                 // y_k[j] = P[j*Kp + k]
+    const int ys = q.Kp;
+    const int32_t* aa_rp = q.AA.rowptr + q.AA.rowptr_base[k];
+    const int32_t* aa_c = q.AA.col + q.AA.nnz_base[k];
+    const float* aa_v = q.AA.val + q.AA.nnz_base[k];
+    const int32_t* ab_rp = q.AB.rowptr + q.AB.rowptr_base[k];
+    const int32_t* ab_c = q.AB.col + q.AB.nnz_base[k];
+    const float* ab_v = q.AB.val + q.AB.nnz_base[k];
+    const int32_t* abt_rp = q.ABt.rowptr + q.ABt.rowptr_base[k];
+    const int32_t* abt_c = q.ABt.col + q.ABt.nnz_base[k];
+    const float* abt_v = q.ABt.val + q.ABt.nnz_base[k];
+    const int32_t* bb_rp = q.BB.rowptr + q.BB.rowptr_base[k];
+    const int32_t* bb_c = q.BB.col + q.BB.nnz_base[k];
+    const float* bb_v = q.BB.val + q.BB.nnz_base[k];
+    float* u = q.u + q.virt_base[k];
+    float* r = q.work + q.virt_base[k];
+    float* pv = q.work + q.nv_total + q.virt_base[k];
+    float* Ap = q.work + 2 * q.nv_total + q.virt_base[k];
+    float* rhs = q.work + 3 * q.nv_total + q.virt_base[k];
+
+    if (nv > 0) {
+        // rhs = AB' y ; x0 = stored (sign-flipped) vector, reference quirk (vi)
+        for (int v = threadIdx.x; v < nv; v += NTH) rhs[v] = csr_row_dot(abt_rp, abt_c, abt_v, v, y, ys);
+        __syncthreads();
+        float rr = 0.f;
+        for (int v = threadIdx.x; v < nv; v += NTH) {
+            float res = rhs[v] - csr_row_dot(bb_rp, bb_c, bb_v, v, u, 1);
+            r[v] = res;
+            pv[v] = res;
+            rr += res * res;
+        }
+        float gamma = block_sum(rr, sm);
+        float rnorm = sqrtf(gamma);
+        const float tol = q.atol + q.rtol * rnorm;
+        const int itmax = q.itmax > 0 ? q.itmax : 2 * nv;
+        int it = 0;
+        while (rnorm > tol && it < itmax) {
+            float pap = 0.f;
+            for (int v = threadIdx.x; v < nv; v += NTH) {
+                float a = csr_row_dot(bb_rp, bb_c, bb_v, v, pv, 1);
+                Ap[v] = a;
+                pap += pv[v] * a;
+            }
+            pap = block_sum(pap, sm);
+            if (!(pap > 0.f)) break;
+            float alpha = gamma / pap;
+            float rr2 = 0.f;
+            for (int v = threadIdx.x; v < nv; v += NTH) {
+                u[v] += alpha * pv[v];
+                float res = r[v] - alpha * Ap[v];
+                r[v] = res;
+                rr2 += res * res;
+            }
+            float gnext = block_sum(rr2, sm);
+            float beta = gnext / gamma;
+            gamma = gnext;
+            rnorm = sqrtf(gamma);
+            for (int v = threadIdx.x; v < nv; v += NTH) pv[v] = r[v] + beta * pv[v];
+            __syncthreads();
+            ++it;
+        }
+        // x_virtual = -cg(...)
+        for (int v = threadIdx.x; v < nv; v += NTH) u[v] = -u[v];
+        __syncthreads();
+    }
+    // gradient and loss
+    float l1 = 0.f, l2 = 0.f;
+    for (int j = threadIdx.x; j < n; j += NTH) {
+        float yj = y[(size_t)j * ys];
+        float xaa = csr_row_dot(aa_rp, aa_c, aa_v, j, y, ys);
+        float abu = nv > 0 ? csr_row_dot(ab_rp, ab_c, ab_v, j, u, 1) : 0.f;
+        l1 += 0.5f * xaa * yj + yj * abu;
+        q.grad[(size_t)j * q.Kp + k] += q.p * (xaa + abu);
+    }
+    for (int v = threadIdx.x; v < nv; v += NTH) l2 += 0.5f * u[v] * csr_row_dot(bb_rp, bb_c, bb_v, v, u, 1);
+    float tot = block_sum(l1 + l2, sm);
+    if (threadIdx.x == 0) atomicAdd(q.loss_out, (double)(q.p * tot));
+}
+
+__global__ void transpose_sync_kernel(const float* __restrict__ P, float* __restrict__ PT, int n, int Kp, int ldt) {
+    __shared__ float t[32][33];
+    int r0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+    for (int rr = threadIdx.y; rr < 32; rr += blockDim.y) {
+        int r = r0 + rr, k = k0 + threadIdx.x;
+        t[rr][threadIdx.x] = (r < n && k < Kp) ? P[(size_t)r * Kp + k] : 0.f;
+    }
+    __syncthreads();
+    for (int kk = threadIdx.y; kk < 32; kk += blockDim.y) {
+        int k = k0 + kk, r = r0 + threadIdx.x;
+        if (k < Kp && r < ldt) PT[(size_t)k * ldt + r] = (r < n) ? t[threadIdx.x][kk] : 0.f;
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_factor_update(const FactorUpdateParams& p, cudaStream_t s) {
+    size_t total4 = (size_t)p.n * (p.Kp >> 2);
+    int blocks = (int)((total4 + UT - 1) / UT);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks < 1) blocks = 1;
+    factor_update_kernel<<<blocks, UT, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_vector_update(const VectorUpdateParams& p, cudaStream_t s) {
+    if (p.n <= 0) return cudaSuccess;
+    int blocks = (p.n + UT - 1) / UT;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    vector_update_kernel<<<blocks, UT, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_control(FitControl* ctrl, const double* scalars, double* hist, int hist_cap, int epoch,
+                           int max_epochs, double rel_tol, double abs_tol, cudaStream_t s) {
+    control_kernel<<<1, 1, 0, s>>>(ctrl, scalars, hist, hist_cap, epoch, max_epochs, rel_tol, abs_tol);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_network_reg(const NetworkParams& p, cudaStream_t s) {
+    network_reg_kernel<<<p.K, NTH, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_transpose_sync(const float* P, float* PT, int n, int Kp, int ldt, cudaStream_t s) {
+    dim3 grid((ldt + 31) / 32, (Kp + 31) / 32), block(32, 8);
+    transpose_sync_kernel<<<grid, block, 0, s>>>(P, PT, n, Kp, ldt);
+    return cudaGetLastError();
+}
+
+}  // namespace pmf

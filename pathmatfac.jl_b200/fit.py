@@ -1,0 +1,456 @@
+"""The drop-in boundary: ``mf_fit`` / ``mf_fit_adapt_lr`` with the reference's keyword
+surface (src/fit.jl:9-75), executing on a libpmf handle (``Engine``).  ``gpu(model)`` /
+``cpu(model)`` mirror the reference's device placement (fit_matfac.jl:325-340)."""
+from __future__ import annotations
+
+import ctypes as C
+import time
+from typing import Dict, List, Optional
+
+import numpy as np
+import scipy.sparse as sp
+
+from . import _lib
+from ._lib import (KERNEL_AUTO, TERM_CODES, c_double_p, check, fptr, iptr, pmf_dims, pmf_fit_opts,
+                   pmf_history, pmf_losses)
+from .layers import BatchScale, BatchShift, FrozenLayer, Identity
+from .regularizers import (ARDRegularizer, BatchArrayReg, ColParamReg, CompositeRegularizer,
+                           FeatureSetARDReg, FrozenRegularizer, GroupRegularizer, L2Regularizer,
+                           NetworkRegularizer, SelectiveL1Reg, ZeroReg)
+from .util import DIST_CODE
+
+
+def _f32(a, order="C"):
+    return np.ascontiguousarray(a, dtype=np.float32) if order == "C" else np.asfortranarray(a, dtype=np.float32)
+
+
+def _jl(a):
+    """numpy (rows, cols) array -> float32 buffer in the reference's column-major layout."""
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float32).T)
+
+
+class AdaGrad:
+    """Flux.Optimise.AdaGrad(lr) as built by construct_optimizer (src/fit.jl:41-43).  The
+    accumulators live on the device (libpmf handle); a new AdaGrad object means fresh state,
+    the same object across LR-halving restarts keeps it (src/fit.jl:55-64)."""
+
+    def __init__(self, eta=1.0, epsilon=1e-8):
+        self.eta = float(eta)
+        self.epsilon = float(epsilon)
+        self._owner = None
+
+
+class Engine:
+    """A PathMatFacModel resident on one GPU (one libpmf handle).  ``rows`` restricts the
+    handle to a contiguous block of samples (sample-sharded multi-GPU, see dist.py)."""
+
+    def __init__(self, model, device: int = 0, rows: Optional[range] = None, upload_data=True):
+        self.lib = _lib.load()
+        self.model = model
+        mf = model.matfac
+        K, M_all = mf.X.shape
+        N = mf.Y.shape[1]
+        self.rows = range(0, M_all) if rows is None else rows
+        self.M, self.N, self.K = len(self.rows), N, K
+        self.h = C.c_void_p()
+        dims = pmf_dims(self.M, N, K, device)
+        rc = self.lib.pmf_create(C.byref(dims), C.byref(self.h))
+        if rc != 0:
+            msg = self.lib.pmf_last_error(None)
+            raise _lib.PmfError(f"pmf_create failed ({rc}): {msg.decode() if msg else '?'}")
+        self.n_views = 0
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+        if upload_data:
+            self.push_data(model.data)
+        self.push_structure()
+        self.push_params()
+
+    # -- helpers ---------------------------------------------------------------------------
+    def _ck(self, rc):
+        check(self.lib, self.h, rc)
+
+    def close(self):
+        if self.h:
+            self.lib.pmf_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream_ptr: int):
+        self._ck(self.lib.pmf_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
+
+    # -- uploads ---------------------------------------------------------------------------
+    def push_data(self, D):
+        """model.data (M x N).  A Fortran-ordered float32 array is passed without a copy."""
+        D = np.asarray(D)[self.rows.start:self.rows.stop, :]
+        buf = _jl(D)        # [N][M]; no copy when D is float32 and column-major
+        self.h2d_bytes += buf.nbytes
+        self._ck(self.lib.pmf_set_data(self.h, fptr(buf)))
+
+    def push_data_buffer(self, buf_NM: np.ndarray):
+        """Already marshalled [N][M] float32 buffer (e.g. pinned host memory)."""
+        assert buf_NM.shape == (self.N, self.M) and buf_NM.dtype == np.float32
+        self.h2d_bytes += buf_NM.nbytes
+        self._ck(self.lib.pmf_set_data(self.h, fptr(buf_NM)))
+
+    def _batch_arrays(self):
+        ct = self.model.matfac.col_transform
+        l2, l4 = ct.unwrapped(1), ct.unwrapped(3)
+        return (l2.logdelta if isinstance(l2, BatchScale) else None,
+                l4.theta if isinstance(l4, BatchShift) else None)
+
+    def push_structure(self):
+        """Everything that is not a trainable value: noise ranges/weights, batch layout,
+        regularisers, frozen masks."""
+        mf = self.model.matfac
+        nm = mf.noise_model
+        nr = len(nm.col_ranges)
+        cs = np.array([r.start for r in nm.col_ranges], np.int32)
+        ce = np.array([r.stop for r in nm.col_ranges], np.int32)
+        dc = np.array([DIST_CODE[n.dist] for n in nm.noises], np.int32)
+        th = np.zeros((nr, 4), np.float32)
+        for i, n in enumerate(nm.noises):
+            if n.ext_thresholds is not None:
+                th[i, :] = n.ext_thresholds
+        w = nm.weights()
+        self._ck(self.lib.pmf_set_noise(self.h, nr, iptr(cs), iptr(ce), iptr(dc), fptr(th), fptr(w)))
+        # batch layout (logdelta and theta share it)
+        ld, thb = self._batch_arrays()
+        ba = ld if ld is not None else thb
+        if ba is not None and len(ba.col_ranges) > 0:
+            nv = len(ba.col_ranges)
+            bcs = np.array([r.start for r in ba.col_ranges], np.int32)
+            bce = np.array([r.stop for r in ba.col_ranges], np.int32)
+            nb = np.array([v.shape[0] for v in ba.values], np.int32)
+            bos = np.ascontiguousarray(np.stack([b[self.rows.start:self.rows.stop] for b in ba.batch_index]).astype(np.int32))
+            self._ck(self.lib.pmf_set_batch_layout(self.h, nv, iptr(bcs), iptr(bce), iptr(nb), iptr(bos)))
+            self.n_views = nv
+        else:
+            self._ck(self.lib.pmf_set_batch_layout(self.h, 0, None, None, None, None))
+            self.n_views = 0
+        self.push_regs()
+
+    def push_regs(self):
+        mf = self.model.matfac
+        self._install_factor_reg(0, mf.X_reg)
+        self._install_factor_reg(1, mf.Y_reg)
+        # layer regularisers + frozen masks
+        ct = mf.col_transform
+        frozen_layers = 0
+        for s, l in enumerate(ct.layers):
+            if isinstance(l, FrozenLayer):
+                frozen_layers |= 1 << s
+        frozen_regs = 0
+        regs = mf.col_transform_reg.regs if mf.col_transform_reg is not None else [ZeroReg()] * 4
+        for s, r in enumerate(regs):
+            slot = s + 1
+            if isinstance(r, FrozenRegularizer):
+                frozen_regs |= 1 << s
+                r = r.reg
+            if isinstance(r, ColParamReg):
+                wv, cv = r.expanded(self.N)
+                self._ck(self.lib.pmf_set_layer_reg_col(self.h, slot, fptr(wv), fptr(cv)))
+            elif isinstance(r, BatchArrayReg) and self.n_views > 0:
+                wv = _f32(np.concatenate(r.weights))
+                cv = _f32(np.concatenate(r.centers))
+                self._ck(self.lib.pmf_set_layer_reg_batch(self.h, slot, fptr(wv), fptr(cv)))
+            elif slot in (1, 3):
+                self._ck(self.lib.pmf_set_layer_reg_col(self.h, slot, None, None))
+            elif self.n_views > 0:
+                self._ck(self.lib.pmf_set_layer_reg_batch(self.h, slot, None, None))
+        self._ck(self.lib.pmf_set_frozen(self.h, frozen_layers, frozen_regs))
+        w = mf.noise_model.weights()
+        # weights can change between calls (reweight_col_losses!, src/fit.jl:151-187)
+        nm = mf.noise_model
+        nr = len(nm.col_ranges)
+        cs = np.array([r.start for r in nm.col_ranges], np.int32)
+        ce = np.array([r.stop for r in nm.col_ranges], np.int32)
+        dc = np.array([DIST_CODE[n.dist] for n in nm.noises], np.int32)
+        th = np.zeros((nr, 4), np.float32)
+        for i, n in enumerate(nm.noises):
+            if n.ext_thresholds is not None:
+                th[i, :] = n.ext_thresholds
+        self._ck(self.lib.pmf_set_noise(self.h, nr, iptr(cs), iptr(ce), iptr(dc), fptr(th), fptr(w)))
+
+    def _install_factor_reg(self, which, reg):
+        lib, h = self.lib, self.h
+        self._ck(lib.pmf_clear_reg(h, which))
+        n = self.M if which == 0 else self.N
+        lo = self.rows.start if which == 0 else 0
+
+        def install(r, p):
+            if r is None or isinstance(r, ZeroReg) or callable(r) or p == 0.0:
+                return
+            if isinstance(r, L2Regularizer):
+                self._ck(lib.pmf_set_reg_l2(h, which, fptr(_f32(r.weights)), p))
+            elif isinstance(r, GroupRegularizer):
+                st, en, ws = [], [], []
+                for rng, w in zip(r.group_idx, r.group_weights):
+                    a, b = max(rng.start - lo, 0), min(rng.stop - lo, n)
+                    if a < b:
+                        st.append(a), en.append(b), ws.append(w)
+                if st:
+                    self._ck(lib.pmf_set_reg_group(h, which, len(st), iptr(np.array(st, np.int32)),
+                                                   iptr(np.array(en, np.int32)), fptr(_f32(np.stack(ws))), p))
+            elif isinstance(r, SelectiveL1Reg):
+                idx = np.ascontiguousarray(r.l1_idx.T.astype(np.uint8))
+                self._ck(lib.pmf_set_reg_sel_l1(h, which, idx.ctypes.data_as(_lib.c_uint8_p), fptr(_f32(r.weight)), p))
+            elif isinstance(r, ARDRegularizer):
+                st = np.array([x.start for x in r.col_ranges], np.int32)
+                en = np.array([x.stop for x in r.col_ranges], np.int32)
+                self._ck(lib.pmf_set_reg_ard(h, which, len(st), iptr(st), iptr(en),
+                                             fptr(_f32(np.array(r.alpha))), fptr(_f32(np.array(r.beta)))))
+            elif isinstance(r, FeatureSetARDReg):
+                self._ck(lib.pmf_set_reg_fsard(h, which, fptr(_f32(r.alpha)), fptr(_jl(r.beta))))
+            elif isinstance(r, NetworkRegularizer):
+                if which == 0 and (self.rows.start != 0 or self.M != self.model.matfac.X.shape[1]):
+                    raise _lib.PmfError("a network regulariser on X couples samples: not shardable (replicas only)")
+                self._install_network(which, r, p)
+            else:
+                raise _lib.PmfError(f"unsupported regulariser {type(r).__name__}")
+
+        if isinstance(reg, CompositeRegularizer):
+            for r, p in zip(reg.regularizers, reg.mixture_p):
+                install(r, float(p))
+        else:
+            install(reg, 1.0)
+
+    def _install_network(self, which, r: NetworkRegularizer, p):
+        def cat(mats):
+            rp = np.concatenate([sp.csr_matrix(m).indptr.astype(np.int32) for m in mats])
+            ci = np.concatenate([sp.csr_matrix(m).indices.astype(np.int32) for m in mats] + [np.zeros(0, np.int32)])
+            va = np.concatenate([sp.csr_matrix(m).data.astype(np.float32) for m in mats] + [np.zeros(0, np.float32)])
+            return np.ascontiguousarray(rp), np.ascontiguousarray(ci), np.ascontiguousarray(va)
+        for m in list(r.AA) + list(r.AB) + list(r.BB):
+            m.sort_indices()
+        aa, ab, bb = cat(r.AA), cat(r.AB), cat(r.BB)
+        nv = np.array([b.shape[0] for b in r.BB], np.int32)
+        xv = _f32(np.concatenate(list(r.x_virtual) + [np.zeros(0, np.float32)]))
+        dummy_i, dummy_f = np.zeros(1, np.int32), np.zeros(1, np.float32)
+        P = lambda a, d: a if a.size else d
+        self._ck(self.lib.pmf_set_reg_network(
+            self.h, which, iptr(nv), iptr(aa[0]), iptr(P(aa[1], dummy_i)), fptr(P(aa[2], dummy_f)),
+            iptr(ab[0]), iptr(P(ab[1], dummy_i)), fptr(P(ab[2], dummy_f)),
+            iptr(bb[0]), iptr(P(bb[1], dummy_i)), fptr(P(bb[2], dummy_f)),
+            fptr(P(xv, dummy_f)), p, r.cg_rtol, r.cg_atol, r.cg_itmax))
+
+    def push_params(self):
+        mf = self.model.matfac
+        X = _jl(mf.X[:, self.rows.start:self.rows.stop])
+        Y = _jl(mf.Y)
+        self._ck(self.lib.pmf_set_factors(self.h, fptr(X), fptr(Y)))
+        ct = mf.col_transform
+        self._ck(self.lib.pmf_set_col_params(self.h, fptr(_f32(ct.unwrapped(0).logsigma)), fptr(_f32(ct.unwrapped(2).mu))))
+        ld, th = self._batch_arrays()
+        for v in range(self.n_views):
+            a = _jl(ld.values[v]) if ld is not None else None
+            b = _jl(th.values[v]) if th is not None else None
+            self._ck(self.lib.pmf_set_batch_values(self.h, v, fptr(a), fptr(b)))
+        self.h2d_bytes += X.nbytes + Y.nbytes + 8 * self.N
+
+    # -- downloads --------------------------------------------------------------------------
+    def pull_params(self):
+        """Write the fitted parameters back into the host model (in place)."""
+        mf = self.model.matfac
+        X = np.empty((self.M, self.K), np.float32)
+        Y = np.empty((self.N, self.K), np.float32)
+        self._ck(self.lib.pmf_get_factors(self.h, fptr(X), fptr(Y)))
+        mf.X[:, self.rows.start:self.rows.stop] = X.T
+        mf.Y[...] = Y.T
+        ls = np.empty(self.N, np.float32)
+        mu = np.empty(self.N, np.float32)
+        self._ck(self.lib.pmf_get_col_params(self.h, fptr(ls), fptr(mu)))
+        ct = mf.col_transform
+        ct.unwrapped(0).logsigma[...] = ls
+        ct.unwrapped(2).mu[...] = mu
+        ld, th = self._batch_arrays()
+        for v in range(self.n_views):
+            shape = (ld if ld is not None else th).values[v].shape
+            a = np.empty(shape[::-1], np.float32)
+            b = np.empty(shape[::-1], np.float32)
+            self._ck(self.lib.pmf_get_batch_values(self.h, v, fptr(a), fptr(b)))
+            if ld is not None:
+                ld.values[v][...] = a.T
+            if th is not None:
+                th.values[v][...] = b.T
+        self.d2h_bytes += X.nbytes + Y.nbytes + 8 * self.N
+        for reg in (mf.X_reg, mf.Y_reg):
+            nets = [reg] if isinstance(reg, NetworkRegularizer) else (
+                [r for r in reg.regularizers if isinstance(r, NetworkRegularizer)]
+                if isinstance(reg, CompositeRegularizer) else [])
+            for net in nets:
+                tot = sum(len(x) for x in net.x_virtual)
+                if tot:
+                    buf = np.empty(tot, np.float32)
+                    which = 0 if reg is mf.X_reg else 1
+                    self._ck(self.lib.pmf_get_network_virtual(self.h, which, fptr(buf)))
+                    o = 0
+                    for x in net.x_virtual:
+                        x[...] = buf[o:o + len(x)]
+                        o += len(x)
+
+    # -- compute ------------------------------------------------------------------------------
+    def set_loss_grad_kernel(self, kernel=KERNEL_AUTO, precision=0):
+        self._ck(self.lib.pmf_set_loss_grad_kernel(self.h, kernel, precision))
+
+    def loss_grad(self, include_reg=True) -> Dict:
+        """Parity hook: loss components and every gradient at the current parameters."""
+        out = pmf_losses()
+        dX = np.empty((self.M, self.K), np.float32)
+        dY = np.empty((self.N, self.K), np.float32)
+        dls = np.empty(self.N, np.float32)
+        dmu = np.empty(self.N, np.float32)
+        self._ck(self.lib.pmf_loss_grad(self.h, int(include_reg), C.byref(out), fptr(dX), fptr(dY), fptr(dls), fptr(dmu)))
+        res = {"loss": out.total, "components": {"data": out.data, "X_reg": out.x_reg, "Y_reg": out.y_reg,
+                                                 "layer_reg": out.layer_reg},
+               "dX": dX.T.copy(), "dY": dY.T.copy(), "dlogsigma": dls, "dmu": dmu,
+               "dlogdelta": [], "dtheta": []}
+        ld, th = self._batch_arrays()
+        for v in range(self.n_views):
+            shape = (ld if ld is not None else th).values[v].shape
+            a = np.empty(shape[::-1], np.float32)
+            b = np.empty(shape[::-1], np.float32)
+            self._ck(self.lib.pmf_get_batch_grads(self.h, v, fptr(a), fptr(b)))
+            res["dlogdelta"].append(a.T.copy())
+            res["dtheta"].append(b.T.copy())
+        return res
+
+    def reset_opt_state(self, epsilon=1e-8):
+        self._ck(self.lib.pmf_reset_opt_state(self.h, epsilon))
+
+    def make_opts(self, **kw) -> pmf_fit_opts:
+        o = pmf_fit_opts()
+        self.lib.pmf_default_fit_opts(C.byref(o))
+        for k, v in kw.items():
+            setattr(o, k, v)
+        return o
+
+    def fit(self, opts: pmf_fit_opts) -> Dict:
+        cap = max(1, opts.max_epochs - opts.epoch + 1)
+        arrs = [np.zeros(cap, np.float64) for _ in range(5)]
+        hist = pmf_history()
+        hist.capacity = cap
+        (hist.loss_total, hist.loss_data, hist.loss_x_reg, hist.loss_y_reg, hist.loss_layer_reg) = [
+            a.ctypes.data_as(c_double_p) for a in arrs]
+        self._ck(self.lib.pmf_fit(self.h, C.byref(opts), C.byref(hist)))
+        n = hist.n_recorded
+        return {"term_code": TERM_CODES[hist.term_code], "epochs": int(hist.epochs),
+                "loss": arrs[0][:n].tolist(), "data_loss": arrs[1][:n].tolist(), "X_reg": arrs[2][:n].tolist(),
+                "Y_reg": arrs[3][:n].tolist(), "layer_reg": arrs[4][:n].tolist(),
+                "device_ms": float(hist.device_ms), "kernel_launches": int(hist.kernel_launches)}
+
+    def set_profiling(self, enable=True):
+        self._ck(self.lib.pmf_set_profiling(self.h, int(enable)))
+
+    def get_profile(self):
+        """(n bracketed data-pass launches, mean ms, min ms) since set_profiling(True)."""
+        n, mean, mn = C.c_int32(0), C.c_float(0), C.c_float(0)
+        self._ck(self.lib.pmf_get_profile(self.h, C.byref(n), C.byref(mean), C.byref(mn)))
+        return int(n.value), float(mean.value), float(mn.value)
+
+    def column_stats(self):
+        """(sum_i (dl/dz)^2, count of finite entries) per column -- MF.batched_column_ssq_grads
+        / MF.column_nonnan (src/fit.jl:166, :140)."""
+        ssq = np.empty(self.N, np.float32)
+        cnt = np.empty(self.N, np.float32)
+        self._ck(self.lib.pmf_column_stats(self.h, fptr(ssq), fptr(cnt)))
+        return ssq, cnt
+
+
+# ---- device placement (the reference's gpu(model) / cpu(model)) -----------------------------------
+
+def gpu(model, device: int = 0):
+    if model._engine is None:
+        model._engine = Engine(model, device=device)
+    return model
+
+
+def cpu(model):
+    if model._engine is not None:
+        model._engine.pull_params()
+        model._engine.close()
+        model._engine = None
+    return model
+
+
+# ---- the boundary ----------------------------------------------------------------------------------
+
+def mf_fit(model, *, scale_column_losses=False, update_X=False, update_Y=False, update_row_layers=False,
+           update_col_layers=False, update_noise_models=True, reg_relative_weighting=False,
+           update_X_reg=False, update_Y_reg=False, update_row_layers_reg=False, update_col_layers_reg=False,
+           keep_history=True, opt: Optional[AdaGrad] = None, lr=1.0, max_epochs=1000, epoch=1,
+           rel_tol=1e-5, abs_tol=1e-5, capacity=None, verbosity=1, print_prefix="", print_iter=10,
+           kernel=KERNEL_AUTO, precision=0, check_every=8, device=0, **kwargs) -> Dict:
+    """``mf_fit!`` (src/fit.jl:9-38): one ``MF.fit!`` call on the model.
+
+    Same keyword surface and defaults.  ``capacity`` is accepted and ignored (the fused pass
+    never materialises Z).  ``update_noise_models`` only concerns ordinal thresholds, which this
+    build keeps fixed.  A model that is not device-resident (``gpu(model)`` not called) is
+    uploaded, fitted and written back within the call -- the end-to-end path."""
+    if scale_column_losses:
+        raise NotImplementedError("scale_column_losses=true is never used by the reference (src/fit.jl:9)")
+    transient = model._engine is None
+    eng = Engine(model, device=device) if transient else model._engine
+    try:
+        if not transient:
+            eng.push_regs()      # stages swap regularisers / freeze layers between calls
+        if opt is None:
+            opt = AdaGrad(lr)
+        if opt._owner is not eng:
+            eng.reset_opt_state(opt.epsilon)
+            opt._owner = eng
+        t0 = time.time()
+        o = eng.make_opts(max_epochs=int(max_epochs), epoch=int(epoch), lr=float(opt.eta),
+                          adagrad_eps=float(opt.epsilon), rel_tol=float(rel_tol), abs_tol=float(abs_tol),
+                          update_X=int(update_X), update_Y=int(update_Y),
+                          update_col_layers=int(update_col_layers), kernel=int(kernel),
+                          precision=int(precision), check_every=int(check_every))
+        h = eng.fit(o)
+        h["time"] = time.time() - t0
+        h["lr"] = opt.eta
+        if verbosity > 1:
+            print(f"{print_prefix}mf_fit: epochs={h['epochs']} term={h['term_code']} loss={h['loss'][-1] if h['loss'] else None}")
+        if transient:
+            eng.pull_params()
+            opt._owner = None
+        h["h2d_bytes"], h["d2h_bytes"] = eng.h2d_bytes, eng.d2h_bytes
+        return h
+    finally:
+        if transient:
+            eng.close()
+
+
+def mf_fit_adapt_lr(model, *, lr=1.0, min_lr=0.001, max_epochs=1000, history=None, keep_history=True,
+                    verbosity=1, print_prefix="", **kwargs) -> List[Dict]:
+    """``mf_fit_adapt_lr!`` (src/fit.jl:46-75): on "loss_increase" halve the learning rate
+    (AdaGrad state kept) and resume at h["epochs"]; stop below ``min_lr``."""
+    made_resident = model._engine is None
+    if made_resident:
+        gpu(model, device=kwargs.get("device", 0))
+    try:
+        opt = AdaGrad(lr)
+        epoch = 1
+        hs = [] if history is None else history
+        while epoch <= max_epochs:
+            h = mf_fit(model, opt=opt, max_epochs=max_epochs, epoch=epoch, keep_history=True,
+                       print_prefix=print_prefix, verbosity=verbosity, **kwargs)
+            h["name"] = f"mf_fit_lr={opt.eta}"
+            hs.append(h)
+            if h["term_code"] == "loss_increase":
+                opt.eta *= 0.5
+                if opt.eta < min_lr:
+                    break
+                if verbosity > 0:
+                    print(f"{print_prefix}Resuming with smaller learning rate ({opt.eta})")
+                epoch = h["epochs"]
+            else:
+                break
+        return hs
+    finally:
+        if made_resident:
+            cpu(model)

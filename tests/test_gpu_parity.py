@@ -1,0 +1,240 @@
+"""Parity of the CUDA path (through the host mirror and the C ABI) against the CPU oracle.
+Tolerance: north_star asks for per-iteration loss and gradients within 1e-4 relative in FP32;
+gradients are compared norm-wise (||g - g_ref|| / ||g_ref||), losses relatively."""
+import numpy as np
+import pytest
+
+import pathmatfac_b200 as P
+from pathmatfac_b200 import _lib
+from oracle import pmf_oracle as O
+from tests.helpers import make_pair, relerr
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def check_loss_grads(model, om, D, kernel=_lib.KERNEL_FFMA, precision=0, tol=TOL):
+    eng = P.Engine(model)
+    try:
+        eng.set_loss_grad_kernel(kernel, precision)
+        got = eng.loss_grad(include_reg=True)
+    finally:
+        eng.close()
+    ref = O.total_loss_grads(om, D)
+    for k in ("data", "X_reg", "Y_reg", "layer_reg"):
+        r, g = ref["components"][k], got["components"][k]
+        assert abs(g - r) <= tol * max(abs(r), 1e-6), (k, g, r)
+    assert abs(got["loss"] - ref["loss"]) <= tol * abs(ref["loss"])
+    for k in ("dX", "dY", "dlogsigma", "dmu"):
+        assert relerr(got[k], ref[k]) < tol, (k, relerr(got[k], ref[k]))
+    if om.logdelta is not None:
+        for v in range(len(om.logdelta.values)):
+            assert relerr(got["dlogdelta"][v], ref["dlogdelta"][v]) < tol
+            assert relerr(got["dtheta"][v], ref["dtheta"][v]) < tol
+    return got, ref
+
+
+def test_c1_runtests_scale_normal():
+    """BASELINE config 1: ~100 x 200, normal noise, per-view L2 on Y."""
+    model, om, D = make_pair(100, {"mrnaseq": ("normal", 200)}, K=8, seed=1, lambda_X_l2=1.0)
+    check_loss_grads(model, om, D)
+
+
+def test_mixed_noise_missing_batches_conditions():
+    """C2/C3 in miniature: mixed assays, 30% missing, batch shift/scale, condition regulariser;
+    K=10 (the reference default) exercises the K padding, M/N are ragged vs the 64-tiles."""
+    views = {"mutation": ("bernoulli", 37), "methylation": ("normal", 101), "mrnaseq": ("normal", 70),
+             "counts": ("poisson", 45)}
+    model, om, D = make_pair(203, views, K=10, seed=2, batch_views=["methylation", "mrnaseq", "counts"],
+                             n_batches=7, n_conditions=5, missing=0.3, lambda_X_l2=0.5)
+    check_loss_grads(model, om, D)
+
+
+def test_ordinal_and_hinge_losses():
+    views = {"mutation": ("bernoulli_sq_hinge", 33), "cna": ("ordinal3", 40), "methylation": ("ordinal_sq_hinge3", 29)}
+    # (distribution, view) sorted order: bernoulli_sq_hinge < ordinal3 < ordinal_sq_hinge3
+    model, om, D = make_pair(77, views, K=4, seed=3, missing=0.1)
+    check_loss_grads(model, om, D)
+
+
+def test_empty_and_all_missing_columns():
+    model, om, D = make_pair(70, {"methylation": ("normal", 66)}, K=4, seed=4, missing=0.2)
+    D[:, 5] = np.nan
+    D[17, :] = np.nan
+    model.data[:, 5] = np.nan
+    model.data[17, :] = np.nan
+    got, ref = check_loss_grads(model, om, D)
+    # an all-missing column gets no data gradient: only the penalty's pullback remains
+    assert relerr(got["dY"][:, 5], O._value_grad(om.Y_reg, om.Y)[1][:, 5]) < 1e-6
+    assert got["dmu"][5] == pytest.approx(om.layer_regs[2].grad(om.mu)[5], rel=1e-5, abs=1e-7)
+
+
+def _graphs(N, K, rng, n_virtual=6, n_edges=60):
+    graphs = []
+    for k in range(K):
+        el = []
+        for _ in range(n_edges):
+            a, b = rng.integers(1, N + 1, size=2)
+            if a != b:
+                el.append([int(a), int(b), float(rng.choice([-1.0, 1.0]))])
+        for v in range(n_virtual):
+            for _ in range(3):
+                el.append([int(rng.integers(1, N + 1)), f"virt{k}_{v}", 1.0])
+        el.append([f"virt{k}_0", f"virt{k}_1", -1.0])
+        graphs.append(el)
+    return graphs
+
+
+def test_network_and_selective_l1_regularisers():
+    rng = np.random.default_rng(11)
+    N, K = 90, 5
+    graphs = _graphs(N, K, rng)
+    model, om, D = make_pair(60, {"mrnaseq": ("normal", N)}, K=K, seed=5, feature_graphs=graphs,
+                             lambda_Y_selective_l1=0.7, lambda_Y_graph=1.3)
+    # tighten the CG on both sides so the comparison is not limited by Krylov's loose Float32 default
+    for r in model.matfac.Y_reg.regularizers:
+        if isinstance(r, P.NetworkRegularizer):
+            r.cg_rtol = 1e-7
+            r.cg_atol = 1e-10
+    check_loss_grads(model, om, D)
+
+
+def test_ard_regulariser():
+    model, om, D = make_pair(50, {"methylation": ("normal", 40), "mrnaseq": ("normal", 30)}, K=6, seed=6, Y_ard=True)
+    check_loss_grads(model, om, D)
+
+
+def test_fsard_regulariser_and_update_A():
+    N, K = 40, 6
+    sets = {"methylation": [list(range(1, 6)), list(range(6, 11)), list(range(11, 16)), list(range(16, 21))],
+            "mrnaseq": [list(range(21, 26)), list(range(25, 31)), list(range(31, 36)), list(range(36, 41))]}
+    model, om, D = make_pair(50, {"methylation": ("normal", 20), "mrnaseq": ("normal", 20)}, K=K, seed=7,
+                             feature_sets=sets)
+    rng = np.random.default_rng(3)
+    beta = (0.001 + 0.2 * rng.random((K, N))).astype(np.float32)
+    model.matfac.Y_reg.beta[...] = beta
+    om.Y_reg.beta[...] = beta
+    check_loss_grads(model, om, D)
+    # update_A!: same ISTA trajectory on both sides
+    from pathmatfac_b200.featureset_ard import update_A
+    P.gpu(model)
+    try:
+        res = update_A(model.matfac.Y_reg, model, max_epochs=150, term_iter=20, atol=1e-5)
+    finally:
+        P.cpu(model)
+    ref = O.update_A(om.Y_reg, om.Y.astype(np.float32), max_epochs=150, term_iter=20, atol=1e-5)
+    for (bl, ep), (rbl, rep), A, Ar in zip(res, ref, model.matfac.Y_reg.A, om.Y_reg.A):
+        assert abs(bl - rbl) <= 1e-4 * abs(rbl) + 1e-3
+        assert relerr(A, Ar) < 5e-3
+    assert relerr(model.matfac.Y_reg.beta, om.Y_reg.beta) < 5e-3
+
+
+def test_fit_loss_curve_and_parameters():
+    views = {"mutation": ("bernoulli", 30), "methylation": ("normal", 60), "counts": ("poisson", 25)}
+    model, om, D = make_pair(120, views, K=5, seed=8, batch_views=["methylation"], n_batches=4,
+                             n_conditions=3, missing=0.25, lambda_X_l2=1.0)
+    opt = O.AdaGrad(0.3)
+    href = O.mf_fit(om, D, opt, max_epochs=25, update_X=True, update_Y=True, update_col_layers=True,
+                    rel_tol=1e-9, abs_tol=1e-9)
+    P.gpu(model)
+    try:
+        h = P.mf_fit(model, opt=P.AdaGrad(0.3), max_epochs=25, update_X=True, update_Y=True,
+                     update_col_layers=True, rel_tol=1e-9, abs_tol=1e-9, kernel=_lib.KERNEL_FFMA, verbosity=0)
+    finally:
+        P.cpu(model)
+    assert h["term_code"] == href["term_code"] and h["epochs"] == href["epochs"]
+    assert len(h["loss"]) == len(href["loss"])
+    assert relerr(h["loss"], href["loss"]) < TOL
+    assert np.max(np.abs(np.array(h["loss"]) / np.array(href["loss"]) - 1)) < 5 * TOL
+    assert relerr(model.matfac.X, om.X) < 1e-3 and relerr(model.matfac.Y, om.Y) < 1e-3
+    assert relerr(model.matfac.col_transform.layers[2].mu, om.mu) < 1e-3
+    assert relerr(model.matfac.col_transform.layers[3].theta.values[0], om.theta.values[0]) < 1e-3
+
+
+def test_frozen_layers_and_flags():
+    model, om, D = make_pair(64, {"methylation": ("normal", 50)}, K=4, seed=9, batch_views=["methylation"],
+                             n_batches=3, lambda_X_l2=1.0)
+    P.freeze_layer(model.matfac.col_transform, [1, 2, 3])
+    P.freeze_reg(model.matfac.col_transform_reg, [1, 2, 3])
+    om.frozen = [True, True, True, False]
+    X0, Y0 = model.matfac.X.copy(), model.matfac.Y.copy()
+    ls0 = model.matfac.col_transform.unwrapped(0).logsigma.copy()
+    th0 = model.matfac.col_transform.unwrapped(3).theta.values[0].copy()
+    href = O.mf_fit(om, D, O.AdaGrad(0.2), max_epochs=6, update_col_layers=True, rel_tol=0, abs_tol=0)
+    h = P.mf_fit(model, lr=0.2, max_epochs=6, update_col_layers=True, rel_tol=0, abs_tol=0,
+                 kernel=_lib.KERNEL_FFMA, verbosity=0)
+    assert np.array_equal(model.matfac.X, X0) and np.array_equal(model.matfac.Y, Y0)     # update_X/Y false
+    assert np.array_equal(model.matfac.col_transform.unwrapped(0).logsigma, ls0)         # frozen
+    assert not np.array_equal(model.matfac.col_transform.unwrapped(3).theta.values[0], th0)
+    assert relerr(h["loss"], href["loss"]) < TOL
+    assert relerr(model.matfac.col_transform.unwrapped(3).theta.values[0], om.theta.values[0]) < 1e-3
+
+
+def test_lr_halving_restart_policy():
+    """mf_fit_adapt_lr! (src/fit.jl:46-75): same term codes / resume epochs as the oracle."""
+    model, om, D = make_pair(80, {"counts": ("poisson", 40), }, K=4, seed=10, lambda_X_l2=1.0)
+    ref = O.mf_fit_adapt_lr(om, D, lr=4.0, min_lr=0.2, max_epochs=30, update_X=True, update_Y=True,
+                            rel_tol=1e-9, abs_tol=1e-9)
+    hs = P.mf_fit_adapt_lr(model, lr=4.0, min_lr=0.2, max_epochs=30, update_X=True, update_Y=True,
+                           rel_tol=1e-9, abs_tol=1e-9, kernel=_lib.KERNEL_FFMA, verbosity=0)
+    assert [h["term_code"] for h in hs] == [h["term_code"] for h in ref]
+    assert [h["epochs"] for h in hs] == [h["epochs"] for h in ref]
+    assert any(h["term_code"] == "loss_increase" for h in hs)
+    for a, b in zip(hs, ref):
+        assert np.isclose(a["lr"], b["lr"])
+        assert relerr(a["loss"], b["loss"]) < 5 * TOL
+
+
+def test_row_shards_sum_to_full():
+    """Sample sharding (multi-GPU decomposition) emulated on one GPU: the data loss and the
+    shared gradients of row shards add up to the full-batch values; dX is shard-local."""
+    views = {"mutation": ("bernoulli", 40), "methylation": ("normal", 90)}
+    model, om, D = make_pair(300, views, K=8, seed=12, batch_views=["methylation"], n_batches=5, missing=0.3)
+    full = P.Engine(model)
+    g = full.loss_grad(include_reg=False)
+    full.close()
+    acc = None
+    for rows in (range(0, 97), range(97, 300)):
+        e = P.Engine(model, rows=rows)
+        s = e.loss_grad(include_reg=False)
+        e.close()
+        assert relerr(s["dX"], g["dX"][:, rows.start:rows.stop]) < 1e-5
+        if acc is None:
+            acc = {k: np.array(s[k], dtype=np.float64) for k in ("dY", "dmu", "dlogsigma")}
+            acc["loss"] = s["components"]["data"]
+            acc["dtheta"] = s["dtheta"][0].astype(np.float64)
+        else:
+            for k in ("dY", "dmu", "dlogsigma"):
+                acc[k] += s[k]
+            acc["loss"] += s["components"]["data"]
+            acc["dtheta"] += s["dtheta"][0]
+    assert abs(acc["loss"] - g["components"]["data"]) < 1e-5 * abs(acc["loss"])
+    for k in ("dY", "dmu", "dlogsigma"):
+        assert relerr(acc[k], g[k]) < 1e-5
+    assert relerr(acc["dtheta"], g["dtheta"][0]) < 1e-5
+
+
+def test_column_stats():
+    model, om, D = make_pair(90, {"mutation": ("bernoulli", 20), "methylation": ("normal", 50)}, K=4, seed=13, missing=0.4)
+    eng = P.Engine(model)
+    ssq, cnt = eng.column_stats()
+    eng.close()
+    assert np.array_equal(cnt, np.isfinite(D).sum(axis=0).astype(np.float32))       # bit-exact mask bookkeeping
+    Z = O.forward(om)
+    ref = np.zeros(D.shape[1])
+    for cr, dist, th in zip(om.noise.col_ranges, om.noise.dists, om.noise.thresholds):
+        sl = slice(cr.start, cr.stop)
+        _, gg = O.noise_loss_grad(dist, Z[:, sl], D[:, sl], th)
+        ref[sl] = (gg ** 2).sum(axis=0)
+    assert relerr(ssq, ref) < TOL
+
+
+def test_abi_error_paths():
+    lib = _lib.load()
+    model, om, D = make_pair(20, {"methylation": ("normal", 10)}, K=2, seed=14)
+    eng = P.Engine(model, upload_data=False)
+    with pytest.raises(_lib.PmfError, match="pmf_set_data"):
+        eng.loss_grad()
+    with pytest.raises(_lib.PmfError):
+        eng._ck(lib.pmf_get_batch_values(eng.h, 3, None, None))
+    eng.close()

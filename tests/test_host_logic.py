@@ -1,0 +1,179 @@
+"""CPU-side tests: host bookkeeping is bit-exact with the oracle and the reference's golden
+vectors, the constructor mirrors the reference, and libpmf.so loads and exports every symbol
+that include/pmf.h declares (no compute calls: there is no GPU here)."""
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+import pathmatfac_b200 as P
+from pathmatfac_b200 import _lib, util
+from oracle import pmf_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = json.load(open(os.path.join(ROOT, "tests", "golden", "runtests_known_answers.json")))
+
+
+def jr(p):
+    return range(p[0] - 1, p[1])
+
+
+def test_bookkeeping_matches_golden_and_oracle():
+    for c in G["is_contiguous"]["cases"]:
+        assert util.is_contiguous(c["vec"]) == c["expect"]
+    for c in G["ids_to_ranges"]["cases"]:
+        assert util.ids_to_ranges(c["vec"]) == [jr(p) for p in c["expect"]] == O.ids_to_ranges(c["vec"])
+    for c in G["subset_ranges"]["cases"]:
+        new, lo, hi = util.subset_ranges([jr(p) for p in c["ranges"]], jr(c["rng"]))
+        assert new == [jr(p) for p in c["expect"]["ranges"]]
+        assert (lo + 1, hi + 1) == (c["expect"]["r_min"], c["expect"]["r_max"])
+    g = G["ids_to_ind_mat"]
+    assert np.array_equal(util.ids_to_ind_mat(g["vec"]), np.array(g["expect"], dtype=bool))
+    rng = np.random.default_rng(0)
+    for _ in range(20):   # randomised agreement with the oracle (bit-exact integer bookkeeping)
+        ids = list(np.repeat(rng.permutation(6), rng.integers(1, 5, size=6)))
+        assert util.ids_to_ranges(ids) == O.ids_to_ranges(ids)
+        labels = list(rng.integers(0, 4, size=17))
+        assert np.array_equal(util.ids_to_ind_mat(labels), O.ids_to_ind_mat(labels))
+        ranges = O.ids_to_ranges(ids)
+        a, b = sorted(rng.integers(0, len(ids) + 1, size=2))
+        if a < b:
+            assert util.subset_ranges(ranges, range(a, b)) == O.subset_ranges(ranges, range(a, b))
+
+
+def test_laplacian_and_featureset_matrices():
+    g = G["edgelist_to_spmat"]
+    n2i = {c: i for i, c in enumerate(g["nodes"])}
+    assert np.allclose(util.edgelist_to_spmat(g["edgelist"], n2i, epsilon=g["epsilon"]).toarray(), g["expect"])
+    rng = np.random.default_rng(1)
+    nodes = list(range(12))
+    el = [[int(a), int(b), float(rng.choice([-1, 1]))] for a, b in rng.integers(0, 12, size=(30, 2)) if a != b]
+    el.append(el[0][:2] + [-el[0][2]])   # duplicate edge: the latest weight wins
+    a = util.edgelist_to_spmat(el, {n: i for i, n in enumerate(nodes)}, epsilon=0.1)
+    b = O.edgelist_to_spmat(el, {n: i for i, n in enumerate(nodes)}, epsilon=0.1)
+    assert np.array_equal(a.toarray(), b.toarray())
+    fs = G["featureset_ard"]["feature_sets"][0]
+    assert np.array_equal(util.featuresets_to_csc(list(range(1, 21)), fs).toarray(),
+                          O.featuresets_to_csc(list(range(1, 21)), fs).toarray())
+
+
+def test_network_regularizer_blocks():
+    g = G["network_regularizer"]
+    for key in ("path", "star"):
+        c = g[key]
+        nr = P.NetworkRegularizer(c["data_features"], c["edgelists"])
+        assert np.allclose(nr.AA[0].toarray(), c["AA1"]) and np.allclose(nr.AB[0].toarray(), c["AB1"])
+        assert np.allclose(nr.BB[0].toarray(), c["BB1"])
+    nr = P.NetworkRegularizer(g["path"]["all_observed_features"], g["path"]["edgelists"])
+    assert nr.AA[0].shape == (4, 4) and nr.AB[0].shape == (4, 0) and nr.BB[0].shape == (0, 0)
+    s = G["selective_l1"]
+    assert np.array_equal(P.SelectiveL1Reg(s["data_features"], s["edgelists"]).l1_idx, np.array(s["l1_idx"], bool))
+
+
+def test_batch_array_bookkeeping():
+    g = G["batch_array"]
+    ranges = util.ids_to_ranges(g["col_batches"])
+    vds = [{int(k): np.full(len(cr), v) for k, v in vd.items()} for vd, cr in zip(g["values"], ranges)]
+    ba = P.BatchArray.from_dicts(g["col_batches"], g["row_batches"], vds)
+    assert ba.col_ranges == [jr(p) for p in g["col_ranges"]]
+    for rb, e in zip(ba.row_batches, g["indicators"]):
+        assert np.array_equal(rb, np.array(e, dtype=bool))
+    for v, e in zip(ba.values, g["values_expect"]):
+        assert np.allclose(v, np.array(e))
+    bv = ba.view(jr(g["view_rows"]), jr(g["view_cols"]))
+    assert bv.col_ranges == [jr(p) for p in g["view_col_ranges"]]
+    for v, e in zip(bv.values, g["view_values"]):
+        assert np.allclose(v, np.array(e))
+    gappy = P.BatchArray.from_dicts(g["gappy_col_batches"], g["row_batches"], vds)
+    assert gappy.col_ranges == [jr(p) for p in g["gappy_col_ranges"]]
+    assert gappy.view(range(0, 5), jr(g["gappy_empty_view_cols"])).col_ranges == []
+    # batch ordinals agree with the oracle's indicator matrices (unique() order)
+    ob = O.BatchArray.construct(g["col_batches"], g["row_batches"], vds)
+    for v in range(3):
+        assert np.array_equal(ba.batch_index[v], ob.batch_index(v))
+
+
+def test_model_constructor_mirrors_reference():
+    """test/runtests.jl:939-1084: default K, layer types, regulariser layout, column sort."""
+    rng = np.random.default_rng(0)
+    D = rng.standard_normal((20, 9)).astype(np.float32)
+    m = P.PathMatFacModel(D.copy())
+    assert m.matfac.X.shape == (10, 20) and m.matfac.Y.shape == (10, 9)
+    assert isinstance(m.matfac.col_transform.layers[0], P.ColScale)
+    assert isinstance(m.matfac.col_transform.layers[2], P.ColShift)
+    assert m.matfac.noise_model.noises[0].dist == "normal"
+    assert len(m.matfac.X_reg.regularizers) == 3 and len(m.matfac.Y_reg.regularizers) == 3
+    assert m.matfac.Y_reg.mixture_p == (1.0, 0.0, 0.0)
+    views = ["b", "a", "b", "a", "c", "c", "a", "b", "c"]
+    dist_of = {"a": "normal", "b": "bernoulli", "c": "poisson"}
+    dists = [dist_of[v] for v in views]
+    D2 = np.arange(20 * 9, dtype=np.float32).reshape(20, 9)
+    raw = D2.copy()
+    m = P.PathMatFacModel(D2, K=3, feature_views=list(views), feature_distributions=list(dists),
+                          sample_conditions=[0] * 10 + [1] * 10, batch_dict={"a": [0] * 5 + [1] * 15})
+    order = sorted(range(9), key=lambda j: (dists[j], views[j]))
+    assert list(m.data_idx) == order
+    assert np.array_equal(m.data, raw[:, order]) and np.array_equal(D2, raw[:, order])   # in place
+    assert util.is_contiguous(m.feature_distributions)
+    assert isinstance(m.matfac.col_transform.layers[1], P.BatchScale)
+    assert isinstance(m.matfac.col_transform.layers[3], P.BatchShift)
+    assert isinstance(m.matfac.X_reg.regularizers[1], P.GroupRegularizer)
+    ba = m.matfac.col_transform.layers[3].theta
+    assert ba.col_range_ids == ["a"] and ba.col_ranges == [range(3, 6)] and ba.values[0].shape == (2, 3)
+    with pytest.raises(AssertionError, match="sample_conditions"):
+        P.PathMatFacModel(D.copy(), feature_views=[1] * 9, batch_dict={1: [0] * 20})
+    with pytest.raises(AssertionError, match="feature_distributions"):
+        P.PathMatFacModel(D.copy(), feature_distributions=["gauss"] * 9)
+    m = P.PathMatFacModel(D.copy(), Y_ard=True, sample_conditions=[0] * 20)
+    assert isinstance(m.matfac.Y_reg, P.ARDRegularizer) and isinstance(m.matfac.X_reg, P.GroupRegularizer)
+    m = P.PathMatFacModel(D.copy(), Y_ard=True)
+    assert isinstance(m.matfac.X_reg, P.L2Regularizer)
+
+
+def test_freeze_helpers():
+    m = P.PathMatFacModel(np.zeros((6, 4), np.float32), K=2, feature_views=[1, 1, 2, 2],
+                          sample_conditions=[0] * 6, batch_dict={1: [0, 0, 0, 1, 1, 1]})
+    P.freeze_layer(m.matfac.col_transform, [1, 2, 3])
+    assert all(isinstance(m.matfac.col_transform.layers[i], P.FrozenLayer) for i in range(3))
+    assert isinstance(m.matfac.col_transform.unwrapped(0), P.ColScale)
+    P.unfreeze_layer(m.matfac.col_transform, 1)
+    assert isinstance(m.matfac.col_transform.layers[0], P.ColScale)
+    P.freeze_reg(m.matfac.col_transform_reg, 4)
+    assert isinstance(m.matfac.col_transform_reg.regs[3], P.FrozenRegularizer)
+    P.unfreeze_reg(m.matfac.col_transform_reg, [4])
+    assert isinstance(m.matfac.col_transform_reg.regs[3], P.BatchArrayReg)
+
+
+def test_libpmf_loads_and_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "pmf.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(pmf_[a-z_A-Z0-9]+)\s*\(", hdr))
+    assert len(declared) >= 40
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/pmf.h but not exported by libpmf.so"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert b"sm_100a" in lib.pmf_version()
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the product path must fail loudly, never fall back."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    m = P.PathMatFacModel(np.zeros((6, 4), np.float32), K=2)
+    with pytest.raises(_lib.PmfError, match="no CUDA device"):
+        P.mf_fit(m, update_X=True, max_epochs=2)
+    with pytest.raises(_lib.PmfError):
+        P.gpu(m)
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "pathmatfac.jl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".h", ".cuh")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f
