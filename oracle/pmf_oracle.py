@@ -620,9 +620,10 @@ def construct_X_reg(K, M, sample_ids, sample_conditions, sample_graphs, lambda_X
     if sample_graphs is not None:
         regs[2] = NetworkRegularizer(sample_ids, sample_graphs, weight=lambda_X_graph)
         p[2] = 1
-    with np.errstate(invalid="ignore", divide="ignore"):
-        p = p / p.sum()   # the reference divides unguarded (NaN if nothing enabled)
-    return CompositeRegularizer(regs, p)
+    # the reference divides unguarded here (0/0 = NaN mixture when nothing is enabled, which its
+    # fit! stages never evaluate because they install their own X_reg); guard like construct_Y_reg
+    s = p.sum()
+    return CompositeRegularizer(regs, p / (s if s > 0 else 1))
 
 
 def construct_Y_reg(K, N, feature_ids, feature_views, feature_sets_dict, feature_graphs,
