@@ -1,0 +1,552 @@
+// Fused data pass on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), K = 64.
+//
+// One persistent CTA per SM walks work items (feature tile of 128 x chunk of samples).  Per
+// 128x128 tile of A (64 KB, streamed once through TMA-staged shared memory):
+//
+//   MMA1  Z'[j,i]  = sum_k Y[j,k] X[i,k]     A = Y tile in TMEM (hi / lo), B = X tile in smem
+//                                            3xTF32: Yh*Xh + Yl*Xh + Yh*Xl, FP32 accumulate in TMEM
+//   epilogue (4 warps, TMEM lane = feature j, so every column parameter is a per-thread
+//            register and every column-gradient sum is a private accumulator):
+//            ColScale/ColShift, noise loss, dL/dz with the NaN mask (src/layers.jl:9-90,
+//            Appendix B of SURVEY.md), G0 written back to TMEM in place of Z and, transposed,
+//            into the shared-memory buffer the A tile came from
+//   MMA3  dY[j,k] += sum_i G0[j,i] X[i,k]    A = G0 in TMEM, B = X' tile (k-major copy) in smem
+//   MMA2  dX[i,k]  = sum_j G0[j,i] Y[j,k]    A = G0' in smem, B = Y' tile (k-major copy) in smem
+//
+// Z and dL/dZ never exist in HBM.  dY stays in TMEM across the sample loop of an item; the
+// per-tile dX block is read back from TMEM and reduced into global memory with 128-bit REDs.
+// Gradient contractions use single-pass TF32 with round-to-nearest operands (precision mode 1);
+// the Z contraction is 3xTF32 unless precision mode 2 asks for plain TF32.
+//
+// Shared memory (192 KB, one CTA per SM), all operands K-major with the 128-byte swizzle:
+//   XS  64 KB  X tile raw FP32 (the tensor core truncates it to its TF32 "hi") + X_lo = X - trunc(X)
+//   XTS 32 KB  X' tile, YTS 32 KB Y' tile (RN-rounded TF32, produced by prep_operands_kernel)
+//   AG  64 KB  A tile as 16 TMA boxes of 32x32; box (jq,iq) sits at (jq*4+iq)*4 KB so that the
+//              slice a warp reads as A is exactly the slice it later overwrites with G0'.
+// TMEM (512 columns): Yh 0-63 | Yl 64-127 | Z0 128-255 | Z1 256-383 | dY 384-447 | dX 448-511.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "pmf_epilogue.cuh"
+#include "pmf_internal.h"
+
+namespace pmf {
+
+namespace {
+
+constexpr int BJ = 128, BI = 128, KK = 64;
+constexpr int NTHREADS = 192;            // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+constexpr uint32_t XS_BYTES = 65536, XTS_BYTES = 32768, YTS_BYTES = 32768, AG_BYTES = 65536;
+constexpr uint32_t SMEM_DATA = XS_BYTES + XTS_BYTES + YTS_BYTES + AG_BYTES;
+constexpr uint32_t SMEM_TOTAL = SMEM_DATA + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr uint32_t TM_YH = 0, TM_YL = 64, TM_Z0 = 128, TM_Z1 = 256, TM_DY = 384, TM_DX = 448;
+
+enum Bar { B_FULL_X = 0, B_EMPTY_X, B_FULL_XT, B_EMPTY_XT, B_FULL_A, B_EMPTY_AG, B_Z_FULL0, B_Z_FULL1,
+           B_G_READY, B_DX_FULL, B_DX_EMPTY, B_Y_READY, B_YT_FULL, B_YT_EMPTY, B_DY_FULL, B_DY_EMPTY, B_COUNT };
+
+// ---- PTX wrappers --------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// D[tmem] (+)= A[tmem] * B[smem]   (kind::tf32, cta_group::1)
+__device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d), "r"(a), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]
+__device__ __forceinline__ void mma_ss(uint32_t d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+
+// K-major operand, 128-byte swizzle: rows are 128 B, 8-row groups are 1024 B apart.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3fffu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor: TF32 x TF32 -> F32, both operands K-major
+__host__ __device__ constexpr uint32_t umma_idesc(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+#define TMEM_LD32(taddr, r)                                                                                       \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                        \
+                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,"  \
+                 "%26,%27,%28,%29,%30,%31}, [%32];"                                                               \
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),  \
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),        \
+                   "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]),      \
+                   "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]),      \
+                   "=r"(r[29]), "=r"(r[30]), "=r"(r[31])                                                          \
+                 : "r"(taddr))
+#define TMEM_ST32(taddr, r)                                                                                       \
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "                                                  \
+                 "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26," \
+                 "%27,%28,%29,%30,%31,%32};"                                                                      \
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]),        \
+                 "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]),      \
+                 "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]),   \
+                 "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]),   \
+                 "r"(r[31]) : "memory")
+
+__device__ __forceinline__ uint32_t rna_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+
+struct TcParams {
+    DataPassParams dp;
+    int n_jt, n_it, chunks, n_items;
+    int z_passes;      // 3 = 3xTF32 for the Z contraction, 1 = plain TF32
+};
+
+__device__ __forceinline__ void item_range(const TcParams& p, int item, int& jt, int& it0, int& it1) {
+    jt = item / p.chunks;
+    int c = item - jt * p.chunks;
+    it0 = (int)((long long)p.n_it * c / p.chunks);
+    it1 = (int)((long long)p.n_it * (c + 1) / p.chunks);
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmXlo,
+                    const __grid_constant__ CUtensorMap tmXT, const __grid_constant__ CUtensorMap tmYT,
+                    const __grid_constant__ CUtensorMap tmA, const TcParams p) {
+    const DataPassParams& dp = p.dp;
+    if (dp.stop_flag != nullptr && *dp.stop_flag != 0) return;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t XS = base, XTS = XS + XS_BYTES, YTS = XTS + XTS_BYTES, AG = YTS + YTS_BYTES;
+    const uint32_t BARS = AG + AG_BYTES;
+    uint8_t* ag_ptr = gbase + XS_BYTES + XTS_BYTES + YTS_BYTES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + SMEM_DATA + 8 * B_COUNT);
+    __shared__ double red_smem[NTHREADS / 32];
+    auto bar = [&](int b) { return BARS + 8u * (uint32_t)b; };
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int b = 0; b < B_COUNT; ++b) {
+            uint32_t cnt = (b == B_G_READY || b == B_DX_EMPTY || b == B_Y_READY || b == B_DY_EMPTY) ? 128u : 1u;
+            mbar_init(bar(b), cnt);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tm = *tmem_slot;
+
+    if (warp == 0) {
+        // ================================ TMA producer ============================================
+        if (lane == 0) {
+            uint32_t g = 0, q = 0;
+            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+                int jt, it0, it1;
+                item_range(p, item, jt, it0, it1);
+                const int j0 = jt * BJ;
+                mbar_wait(bar(B_YT_EMPTY), (q & 1) ^ 1);
+                mbar_expect_tx(bar(B_YT_FULL), YTS_BYTES);
+                for (int b = 0; b < 4; ++b) tma_load_2d(YTS + b * 8192, &tmYT, bar(B_YT_FULL), j0 + 32 * b, 0);
+                for (int it = it0; it < it1; ++it, ++g) {
+                    const int i0 = it * BI;
+                    mbar_wait(bar(B_EMPTY_X), (g & 1) ^ 1);
+                    mbar_expect_tx(bar(B_FULL_X), XS_BYTES);
+                    for (int kb = 0; kb < 2; ++kb) {
+                        tma_load_2d(XS + kb * 16384, &tmX, bar(B_FULL_X), 32 * kb, i0);
+                        tma_load_2d(XS + 32768 + kb * 16384, &tmXlo, bar(B_FULL_X), 32 * kb, i0);
+                    }
+                    mbar_wait(bar(B_EMPTY_XT), (g & 1) ^ 1);
+                    mbar_expect_tx(bar(B_FULL_XT), XTS_BYTES);
+                    for (int b = 0; b < 4; ++b) tma_load_2d(XTS + b * 8192, &tmXT, bar(B_FULL_XT), i0 + 32 * b, 0);
+                    mbar_wait(bar(B_EMPTY_AG), (g & 1) ^ 1);
+                    mbar_expect_tx(bar(B_FULL_A), AG_BYTES);
+                    for (int jq = 0; jq < 4; ++jq)
+                        for (int iq = 0; iq < 4; ++iq)
+                            tma_load_2d(AG + (jq * 4 + iq) * 4096, &tmA, bar(B_FULL_A), i0 + 32 * iq, j0 + 32 * jq);
+                }
+                ++q;
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer ===============================================
+        const uint32_t id_z = umma_idesc(128, 128), id_g = umma_idesc(128, 64);
+        uint32_t g = 0, q = 0;
+        auto issue_mma1 = [&](uint32_t gg) {
+            mbar_wait(bar(B_FULL_X), gg & 1);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t zt = tm + ((gg & 1) ? TM_Z1 : TM_Z0);
+                uint32_t acc = 0;
+                for (int pass = 0; pass < p.z_passes; ++pass) {
+                    const uint32_t ya = tm + (pass == 1 ? TM_YL : TM_YH);
+                    const uint32_t xb = XS + (pass == 2 ? 32768u : 0u);
+#pragma unroll
+                    for (int s = 0; s < 8; ++s) {
+                        mma_ts(zt, ya + 8 * s, umma_desc(xb + (s >> 2) * 16384 + (s & 3) * 32), id_z, acc);
+                        acc = 1;
+                    }
+                }
+                tc_commit(bar(B_EMPTY_X));
+                tc_commit(bar((gg & 1) ? B_Z_FULL1 : B_Z_FULL0));
+            }
+            __syncwarp();
+        };
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+            int jt, it0, it1;
+            item_range(p, item, jt, it0, it1);
+            mbar_wait(bar(B_Y_READY), q & 1);
+            mbar_wait(bar(B_YT_FULL), q & 1);
+            mbar_wait(bar(B_DY_EMPTY), (q & 1) ^ 1);
+            tc_fence_after();
+            issue_mma1(g);
+            for (int it = it0; it < it1; ++it, ++g) {
+                if (it + 1 < it1) issue_mma1(g + 1);
+                mbar_wait(bar(B_G_READY), g & 1);
+                mbar_wait(bar(B_FULL_XT), g & 1);
+                mbar_wait(bar(B_DX_EMPTY), (g & 1) ^ 1);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t ga = tm + ((g & 1) ? TM_Z1 : TM_Z0);
+                    // MMA3: dY += G0 * X'
+#pragma unroll
+                    for (int s = 0; s < 16; ++s)
+                        mma_ts(tm + TM_DY, ga + 8 * s, umma_desc(XTS + (s >> 2) * 8192 + (s & 3) * 32), id_g,
+                               (it > it0 || s > 0) ? 1u : 0u);
+                    tc_commit(bar(B_EMPTY_XT));
+                    // MMA2: dX = G0' * Y'
+#pragma unroll
+                    for (int s = 0; s < 16; ++s)
+                        mma_ss(tm + TM_DX, umma_desc(AG + (s >> 2) * 16384 + (s & 3) * 32),
+                               umma_desc(YTS + (s >> 2) * 8192 + (s & 3) * 32), id_g, s > 0 ? 1u : 0u);
+                    tc_commit(bar(B_EMPTY_AG));
+                    tc_commit(bar(B_DX_FULL));
+                }
+                __syncwarp();
+            }
+            if (lane == 0) {
+                tc_commit(bar(B_DY_FULL));
+                tc_commit(bar(B_YT_EMPTY));
+            }
+            __syncwarp();
+            ++q;
+        }
+    } else {
+        // ================================ epilogue warps ===========================================
+        const int quarter = warp & 3;                 // TMEM lanes 32*quarter .. +31
+        const int lrow = 32 * quarter + lane;         // feature lane (G epilogue) / sample lane (dX read-out)
+        const uint32_t lane_addr = ((uint32_t)(32 * quarter)) << 16;
+        uint32_t g = 0, q = 0;
+        double loss_d = 0.0;
+        // dX read-out of the tile whose MMA2 was issued last (deferred by one tile)
+        auto dx_out = [&](uint32_t gg, int i0) {
+            mbar_wait(bar(B_DX_FULL), gg & 1);
+            tc_fence_after();
+            const int i = i0 + lrow;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                uint32_t r[32];
+                TMEM_LD32(tm + lane_addr + TM_DX + 32 * half, r);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (i < dp.M) {
+                    float* dst = dp.dX + (size_t)i * KK + 32 * half;
+#pragma unroll
+                    for (int v = 0; v < 8; ++v)
+                        atomicAdd(reinterpret_cast<float4*>(dst) + v,
+                                  make_float4(__uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]),
+                                              __uint_as_float(r[4 * v + 2]), __uint_as_float(r[4 * v + 3])));
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(bar(B_DX_EMPTY));
+        };
+
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+            int jt, it0, it1;
+            item_range(p, item, jt, it0, it1);
+            const int j = jt * BJ + lrow;
+            const bool jok = j < dp.N;
+            const int jj = jok ? j : 0;
+            // per-thread column constants (lane = feature)
+            const float sigma = __expf(dp.logsigma[jj]);
+            const float muj = dp.mu[jj];
+            const float wj = jok ? dp.weight[jj] : 0.f;
+            const int ci = dp.colinfo[jj];
+            const int dist = ci & 0xff;
+            const float* thp = dp.thresholds + 4 * (ci >> 8);
+            const float gscale = sigma;            // G0 = sigma_j * dL/dz4  (no batch layers on this path)
+            float dmu_acc = 0.f, loss_acc = 0.f;
+
+            // ---- Y tile -> TMEM (hi = TF32 truncation as the tensor core would read it, lo = rest)
+            {
+                const float4* yrow = reinterpret_cast<const float4*>(dp.Y + (size_t)(jt * BJ + lrow) * KK);
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t hi[32], lo[32];
+#pragma unroll
+                    for (int v = 0; v < 8; ++v) {
+                        float4 y4 = __ldg(yrow + 8 * half + v);
+                        float ys[4] = {y4.x, y4.y, y4.z, y4.w};
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            uint32_t hb = __float_as_uint(ys[c]) & 0xffffe000u;
+                            hi[4 * v + c] = hb;
+                            lo[4 * v + c] = __float_as_uint(ys[c] - __uint_as_float(hb));
+                        }
+                    }
+                    TMEM_ST32(tm + lane_addr + TM_YH + 32 * half, hi);
+                    TMEM_ST32(tm + lane_addr + TM_YL + 32 * half, lo);
+                }
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                tc_fence_before();
+                mbar_arrive(bar(B_Y_READY));
+            }
+
+            for (int it = it0; it < it1; ++it, ++g) {
+                const int i0 = it * BI;
+                mbar_wait(bar((g & 1) ? B_Z_FULL1 : B_Z_FULL0), (g >> 1) & 1);
+                mbar_wait(bar(B_FULL_A), g & 1);
+                tc_fence_after();
+                const uint32_t zt = tm + lane_addr + ((g & 1) ? TM_Z1 : TM_Z0);
+#pragma unroll 1
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t z[32];
+                    TMEM_LD32(zt + 32 * c, z);
+                    // A chunk: box (jq = quarter, iq = c), row = lane, 128-byte swizzle on 16-byte chunks
+                    const uint8_t* box = ag_ptr + (quarter * 4 + c) * 4096;
+                    float a[32];
+#pragma unroll
+                    for (int v = 0; v < 8; ++v) {
+                        float4 a4 = *reinterpret_cast<const float4*>(box + lane * 128 + ((v ^ (lane & 7)) << 4));
+                        a[4 * v] = a4.x; a[4 * v + 1] = a4.y; a[4 * v + 2] = a4.z; a[4 * v + 3] = a4.w;
+                    }
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (dist == DIST_NORMAL) {
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) {
+                            float z4 = fmaf(__uint_as_float(z[e]), sigma, muj);
+                            float d = is_observed(a[e]) ? z4 - a[e] : 0.f;
+                            float gv = d * wj;
+                            loss_acc = fmaf(gv, d, loss_acc);             // w (z-a)^2, halved at flush
+                            dmu_acc += gv;
+                            z[e] = rna_tf32(gv * gscale);
+                        }
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) {
+                            float gv = 0.f;
+                            if (is_observed(a[e])) {
+                                float z4 = fmaf(__uint_as_float(z[e]), sigma, muj);
+                                float l;
+                                noise_eval(dist, z4, a[e], thp, dp.ordinal_eps, dp.hinge_margin, l, gv);
+                                gv *= wj;
+                                loss_acc = fmaf(2.f * wj, l, loss_acc);   // keep the common 1/2 factor at flush
+                                dmu_acc += gv;
+                            }
+                            z[e] = rna_tf32(gv * gscale);
+                        }
+                    }
+                    // G0 back to TMEM in place of Z (A operand of MMA3)
+                    TMEM_ST32(zt + 32 * c, z);
+                    // every lane of the warp has pulled its A row of this slice into registers
+                    __syncwarp();
+                    // G0' : rows i = 32c..32c+31 of K-atom box `quarter`, column = lane
+                    uint8_t* gbox = ag_ptr + quarter * 16384 + (32 * c) * 128;
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) {
+                        *reinterpret_cast<uint32_t*>(gbox + e * 128 + (((lane >> 2) ^ (e & 7)) << 4) + ((lane & 3) << 2)) = z[e];
+                    }
+                }
+                loss_d += (double)loss_acc;
+                loss_acc = 0.f;
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                tc_fence_before();
+                fence_async_smem();
+                mbar_arrive(bar(B_G_READY));
+                if (it > it0) dx_out(g - 1, (it - 1) * BI);
+            }
+            dx_out(g - 1, (it1 - 1) * BI);
+
+            // ---- item epilogue: dY tile out of TMEM, column sums --------------------------------------
+            mbar_wait(bar(B_DY_FULL), q & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                uint32_t r[32];
+                TMEM_LD32(tm + lane_addr + TM_DY + 32 * half, r);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (jok) {
+                    float* dst = dp.dY + (size_t)j * KK + 32 * half;
+#pragma unroll
+                    for (int v = 0; v < 8; ++v) {
+                        float4 val = make_float4(__uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]),
+                                                 __uint_as_float(r[4 * v + 2]), __uint_as_float(r[4 * v + 3]));
+                        if (p.chunks == 1) reinterpret_cast<float4*>(dst)[v] = val;
+                        else atomicAdd(reinterpret_cast<float4*>(dst) + v, val);
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(bar(B_DY_EMPTY));
+            if (jok) {
+                // dmu_j = sum_i g ; dlogsigma_j = sum_i sigma_j * g  (the reference's ColScale quirk)
+                atomicAdd(dp.dmu + j, dmu_acc);
+                atomicAdd(dp.dlogsigma + j, dmu_acc * sigma);
+            }
+            ++q;
+        }
+        // data loss: sum over this warp group (warps 2-5), 0.5 factor applied here
+        loss_d *= 0.5;
+        for (int o = 16; o > 0; o >>= 1) loss_d += __shfl_xor_sync(0xffffffffu, loss_d, o);
+        if (lane == 0) red_smem[warp] = loss_d;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x == 64) {
+        double t = red_smem[2] + red_smem[3] + red_smem[4] + red_smem[5];
+        atomicAdd(dp.scalars + SC_DATA, t);
+    }
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"(512u) : "memory");
+    }
+}
+
+// X_lo = X - trunc_tf32(X); XT = rna_tf32(X)' ; YT = rna_tf32(Y)'   (operands of the TC data pass)
+__global__ void prep_operands_kernel(const float* __restrict__ X, float* __restrict__ Xlo, float* __restrict__ XT,
+                                     int Mp, const float* __restrict__ Y, float* __restrict__ YT, int Np,
+                                     const int* stop_flag) {
+    if (stop_flag != nullptr && *stop_flag != 0) return;
+    __shared__ float t[32][33];
+    const bool isY = blockIdx.y >= 2;
+    const float* P = isY ? Y : X;
+    float* PT = isY ? YT : XT;
+    const int n = isY ? Np : Mp;
+    const int r0 = blockIdx.x * 32, k0 = (blockIdx.y & 1) * 32;
+    if (r0 >= n) return;
+    for (int rr = threadIdx.y; rr < 32; rr += blockDim.y) {
+        float v = P[(size_t)(r0 + rr) * KK + k0 + threadIdx.x];
+        if (!isY) Xlo[(size_t)(r0 + rr) * KK + k0 + threadIdx.x] = v - __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+        t[rr][threadIdx.x] = __uint_as_float(rna_tf32(v));
+    }
+    __syncthreads();
+    for (int kk = threadIdx.y; kk < 32; kk += blockDim.y)
+        PT[(size_t)(k0 + kk) * n + r0 + threadIdx.x] = t[threadIdx.x][kk];
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn) return fn;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+        return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    return fn;
+}
+
+// 2-D FP32 tensor [rows][cols] (cols contiguous, row pitch = pitch floats), box = box_rows x 32 floats
+bool make_map(CUtensorMap* m, const float* base, uint64_t cols, uint64_t rows, uint64_t pitch, uint32_t box_rows,
+              bool nan_fill) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return false;
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {pitch * sizeof(float)};
+    cuuint32_t box[2] = {32, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     nan_fill ? CU_TENSOR_MAP_FLOAT_OOB_FILL_NAN_REQUEST_ZERO_FMA : CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+}  // namespace
+
+bool tc_supported(const DataPassParams& p) {
+    return p.Kp == KK && p.n_batch_views == 0 && p.col_ssq == nullptr;
+}
+
+// Xlo: [Mp][64], XT: [64][Mp], YT: [64][Np] scratch owned by the handle
+cudaError_t launch_data_pass_tc(const DataPassParams& dp, float* Xlo, float* XT, float* YT, int precision,
+                                cudaStream_t s, int n_sms) {
+    if (!tc_supported(dp)) return cudaErrorInvalidValue;
+    dim3 pb(32, 8), pg((unsigned)((dp.Mp > dp.Np ? dp.Mp : dp.Np) / 32), 4);
+    prep_operands_kernel<<<pg, pb, 0, s>>>(dp.X, Xlo, XT, dp.Mp, dp.Y, YT, dp.Np, dp.stop_flag);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+
+    CUtensorMap tmX, tmXlo, tmXT, tmYT, tmA;
+    bool ok = make_map(&tmX, dp.X, KK, dp.Mp, KK, 128, false) && make_map(&tmXlo, Xlo, KK, dp.Mp, KK, 128, false) &&
+              make_map(&tmXT, XT, dp.Mp, KK, dp.Mp, 64, false) && make_map(&tmYT, YT, dp.Np, KK, dp.Np, 64, false) &&
+              make_map(&tmA, dp.A, dp.lda, dp.N, dp.lda, 32, true);
+    if (!ok) return cudaErrorUnknown;
+
+    TcParams p;
+    p.dp = dp;
+    p.n_jt = (dp.N + BJ - 1) / BJ;
+    p.n_it = (dp.M + BI - 1) / BI;
+    p.z_passes = precision >= 2 ? 1 : 3;
+    // sample chunks: maximise the fill of the last wave, at least 4 tiles per chunk
+    int best_c = 1;
+    double best_eff = 0.0;
+    const int max_c = p.n_it / 4 > 0 ? p.n_it / 4 : 1;
+    for (int c = 1; c <= max_c && c <= 16; ++c) {
+        long long items = (long long)p.n_jt * c;
+        long long waves = (items + n_sms - 1) / n_sms;
+        double eff = (double)items / (double)(waves * n_sms) - 0.002 * c;   // mild preference for fewer chunks
+        if (eff > best_eff) { best_eff = eff; best_c = c; }
+    }
+    p.chunks = dp.sample_chunks > 0 ? dp.sample_chunks : best_c;
+    p.n_items = p.n_jt * p.chunks;
+    e = cudaFuncSetAttribute(data_pass_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TOTAL);
+    if (e != cudaSuccess) return e;
+    int grid = p.n_items < n_sms ? p.n_items : n_sms;
+    data_pass_tc_kernel<<<grid, NTHREADS, SMEM_TOTAL, s>>>(tmX, tmXlo, tmXT, tmYT, tmA, p);
+    return cudaGetLastError();
+}
+
+}  // namespace pmf

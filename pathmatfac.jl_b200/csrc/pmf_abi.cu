@@ -135,7 +135,7 @@ int pmf_destroy(pmf_handle h) {
     cudaSetDevice(h->dims.device);
     cudaDeviceSynchronize();
     dev_free(h->A); dev_free(h->X); dev_free(h->dX); dev_free(h->accX); dev_free(h->Y); dev_free(h->accY);
-    dev_free(h->XT); dev_free(h->YT);
+    dev_free(h->Xlo); dev_free(h->XT); dev_free(h->YT);
     dev_free(h->weight); dev_free(h->colinfo); dev_free(h->thresholds); dev_free(h->scalars); dev_free(h->ctrl);
     dev_free(h->vp); dev_free(h->sg); dev_free(h->accvp); dev_free(h->regw); dev_free(h->regc);
     dev_free(h->bcol_off); dev_free(h->bcol_view); dev_free(h->bcol_nb); dev_free(h->batch_of_sample);
@@ -872,8 +872,31 @@ int pmf_model_s::realloc_vectors(int new_nbp) {
 }
 
 int pmf_model_s::run_data_pass(DataPassParams& p, int kind, int precision) {
-    (void)precision;
-    if (kind == PMF_KERNEL_TC) return fail(this, PMF_ERR_ARG, "tcgen05 kernel is not built into this library");
+    const bool tc_ok = tc_supported(p) && cc_major == 10;
+    if (kind == PMF_KERNEL_TC && !tc_ok)
+        return fail(this, PMF_ERR_ARG, "tcgen05 data pass needs K == 64 (padded), no batch layers and an sm_100 device");
+    const bool use_tc = kind == PMF_KERNEL_TC || (kind == PMF_KERNEL_AUTO && tc_ok && auto_tc);
+    if (use_tc) {
+        if (!Xlo) {
+            if (dev_alloc(&Xlo, (size_t)Mp * Kp) != cudaSuccess || dev_alloc(&XT, (size_t)Mp * Kp) != cudaSuccess ||
+                dev_alloc(&YT, (size_t)Np * Kp) != cudaSuccess)
+                return fail(this, PMF_ERR_ALLOC, "device allocation failed");
+        }
+        cudaEvent_t t0 = nullptr, t1 = nullptr;
+        if (profiling) {
+            if (prof_used + 2 > prof_ev.size()) {
+                for (int i = 0; i < 2; ++i) { cudaEvent_t ev; cudaEventCreate(&ev); prof_ev.push_back(ev); }
+            }
+            t0 = prof_ev[prof_used]; t1 = prof_ev[prof_used + 1];
+            prof_used += 2;
+            cudaEventRecord(t0, stream);
+        }
+        cudaError_t e = launch_data_pass_tc(p, Xlo, XT, YT, precision, stream, n_sms);
+        if (profiling) cudaEventRecord(t1, stream);
+        if (e != cudaSuccess) { cuda_failed = true; return fail(this, PMF_ERR_CUDA, "tcgen05 data pass launch: %s", cudaGetErrorString(e)); }
+        launches += 2;
+        return 0;
+    }
     size_t smem = sizeof(float) * ((size_t)128 * (Kp + 4) + 64 * 68 + 2 * (size_t)64 * nb_max);
     if (smem > 227 * 1024) return fail(this, PMF_ERR_ARG, "too many batches per view (%d) for K=%d", nb_max, K);
     cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -936,8 +959,6 @@ int pmf_model_s::run_factor_update(int which, float lr, float eps, const int* st
     FactorUpdateParams q;
     fill_factor_params(which, q);
     q.do_update = 1; q.lr = lr; q.eps = eps; q.stop_flag = stop;
-    if (which == 0 && XT) { q.PT = XT; q.ldt = Mp; }
-    if (which == 1 && YT) { q.PT = YT; q.ldt = Np; }
     cudaError_t e = launch_factor_update(q, stream);
     if (e != cudaSuccess) { cuda_failed = true; return fail(this, PMF_ERR_CUDA, "factor update launch: %s", cudaGetErrorString(e)); }
     launches++;

@@ -80,7 +80,8 @@ struct pmf_model_s {
     float* A = nullptr;
     float *X = nullptr, *dX = nullptr, *accX = nullptr;
     float *Y = nullptr, *accY = nullptr;
-    float *XT = nullptr, *YT = nullptr;      // k-major copies for the tcgen05 path (lazy)
+    float *Xlo = nullptr, *XT = nullptr, *YT = nullptr;   // operand scratch of the tcgen05 path (lazy)
+    bool auto_tc = false;                    // PMF_KERNEL_AUTO picks the tcgen05 path when it applies
     // per-column noise description
     float* weight = nullptr;
     int32_t* colinfo = nullptr;
