@@ -36,7 +36,8 @@ namespace pmf {
 namespace {
 
 constexpr int BJ = 128, BI = 128, KK = 64;
-constexpr int NTHREADS = 192;            // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+constexpr int NEPI = 8;                   // epilogue warps: two per TMEM lane quarter
+constexpr int NTHREADS = 64 + 32 * NEPI;  // warp 0 TMA, warp 1 MMA, warps 2.. epilogue
 constexpr uint32_t XS_BYTES = 65536, XTS_BYTES = 32768, YTS_BYTES = 32768, AG_BYTES = 65536;
 constexpr uint32_t SMEM_DATA = XS_BYTES + XTS_BYTES + YTS_BYTES + AG_BYTES;
 constexpr uint32_t SMEM_TOTAL = SMEM_DATA + 1024 /*align slack*/ + 256 /*barriers*/;
@@ -129,6 +130,16 @@ __device__ __forceinline__ uint32_t rna_tf32(float x) {
     return r;
 }
 
+// ordinal / hinge noise models: rare on the hot path, kept out of line to bound code size.
+// Returns (loss, dloss/dz); (0, 0) for a missing entry.
+__device__ __noinline__ float2 noise_eval_slow(int dist, float z, float a, float4 th4, float ord_eps, float margin) {
+    if (!is_observed(a)) return make_float2(0.f, 0.f);
+    const float th[4] = {th4.x, th4.y, th4.z, th4.w};
+    float l, g;
+    noise_eval(dist, z, a, th, ord_eps, margin, l, g);
+    return make_float2(l, g);
+}
+
 struct TcParams {
     DataPassParams dp;
     int n_jt, n_it, chunks, n_items;
@@ -162,7 +173,7 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
 
     if (threadIdx.x == 0) {
         for (int b = 0; b < B_COUNT; ++b) {
-            uint32_t cnt = (b == B_G_READY || b == B_DX_EMPTY || b == B_Y_READY || b == B_DY_EMPTY) ? 128u : 1u;
+            uint32_t cnt = (b == B_G_READY || b == B_DX_EMPTY || b == B_Y_READY || b == B_DY_EMPTY) ? 32u * NEPI : 1u;
             mbar_init(bar(b), cnt);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -247,19 +258,19 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                 tc_fence_after();
                 if (lane == 0) {
                     const uint32_t ga = tm + ((g & 1) ? TM_Z1 : TM_Z0);
-                    // MMA3: dY += G0 * X'
-#pragma unroll
-                    for (int s = 0; s < 16; ++s)
-                        mma_ts(tm + TM_DY, ga + 8 * s, umma_desc(XTS + (s >> 2) * 8192 + (s & 3) * 32), id_g,
-                               (it > it0 || s > 0) ? 1u : 0u);
-                    tc_commit(bar(B_EMPTY_XT));
-                    // MMA2: dX = G0' * Y'
+                    // MMA2 first (dX = G0' * Y'): its completion releases the A/G buffer for the next TMA load
 #pragma unroll
                     for (int s = 0; s < 16; ++s)
                         mma_ss(tm + TM_DX, umma_desc(AG + (s >> 2) * 16384 + (s & 3) * 32),
                                umma_desc(YTS + (s >> 2) * 8192 + (s & 3) * 32), id_g, s > 0 ? 1u : 0u);
                     tc_commit(bar(B_EMPTY_AG));
                     tc_commit(bar(B_DX_FULL));
+                    // MMA3: dY += G0 * X'
+#pragma unroll
+                    for (int s = 0; s < 16; ++s)
+                        mma_ts(tm + TM_DY, ga + 8 * s, umma_desc(XTS + (s >> 2) * 8192 + (s & 3) * 32), id_g,
+                               (it > it0 || s > 0) ? 1u : 0u);
+                    tc_commit(bar(B_EMPTY_XT));
                 }
                 __syncwarp();
             }
@@ -272,7 +283,10 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         }
     } else {
         // ================================ epilogue warps ===========================================
+        // Two warps share a TMEM lane quarter: warp (quarter, half) owns the 32-column chunks
+        // c = 2*half, 2*half+1 of every tile (and columns 32*half.. of the 64-wide dX/dY/Y tiles).
         const int quarter = warp & 3;                 // TMEM lanes 32*quarter .. +31
+        const int half = (warp - 2) >> 2;
         const int lrow = 32 * quarter + lane;         // feature lane (G epilogue) / sample lane (dX read-out)
         const uint32_t lane_addr = ((uint32_t)(32 * quarter)) << 16;
         uint32_t g = 0, q = 0;
@@ -282,22 +296,19 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
             mbar_wait(bar(B_DX_FULL), gg & 1);
             tc_fence_after();
             const int i = i0 + lrow;
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                uint32_t r[32];
-                TMEM_LD32(tm + lane_addr + TM_DX + 32 * half, r);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (i < dp.M) {
-                    float* dst = dp.dX + (size_t)i * KK + 32 * half;
-#pragma unroll
-                    for (int v = 0; v < 8; ++v)
-                        atomicAdd(reinterpret_cast<float4*>(dst) + v,
-                                  make_float4(__uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]),
-                                              __uint_as_float(r[4 * v + 2]), __uint_as_float(r[4 * v + 3])));
-                }
-            }
+            uint32_t r[32];
+            TMEM_LD32(tm + lane_addr + TM_DX + 32 * half, r);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             tc_fence_before();
             mbar_arrive(bar(B_DX_EMPTY));
+            if (i < dp.M) {
+                float* dst = dp.dX + (size_t)i * KK + 32 * half;
+#pragma unroll
+                for (int v = 0; v < 8; ++v)
+                    atomicAdd(reinterpret_cast<float4*>(dst) + v,
+                              make_float4(__uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]),
+                                          __uint_as_float(r[4 * v + 2]), __uint_as_float(r[4 * v + 3])));
+            }
         };
 
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
@@ -312,30 +323,27 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
             const float wj = jok ? dp.weight[jj] : 0.f;
             const int ci = dp.colinfo[jj];
             const int dist = ci & 0xff;
-            const float* thp = dp.thresholds + 4 * (ci >> 8);
+            const float4 th4 = __ldg(reinterpret_cast<const float4*>(dp.thresholds + 4 * (ci >> 8)));
             const float gscale = sigma;            // G0 = sigma_j * dL/dz4  (no batch layers on this path)
             float dmu_acc = 0.f, loss_acc = 0.f;
 
             // ---- Y tile -> TMEM (hi = TF32 truncation as the tensor core would read it, lo = rest)
             {
-                const float4* yrow = reinterpret_cast<const float4*>(dp.Y + (size_t)(jt * BJ + lrow) * KK);
+                const float4* yrow = reinterpret_cast<const float4*>(dp.Y + (size_t)(jt * BJ + lrow) * KK) + 8 * half;
+                uint32_t hi[32], lo[32];
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    uint32_t hi[32], lo[32];
+                for (int v = 0; v < 8; ++v) {
+                    float4 y4 = __ldg(yrow + v);
+                    float ys[4] = {y4.x, y4.y, y4.z, y4.w};
 #pragma unroll
-                    for (int v = 0; v < 8; ++v) {
-                        float4 y4 = __ldg(yrow + 8 * half + v);
-                        float ys[4] = {y4.x, y4.y, y4.z, y4.w};
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            uint32_t hb = __float_as_uint(ys[c]) & 0xffffe000u;
-                            hi[4 * v + c] = hb;
-                            lo[4 * v + c] = __float_as_uint(ys[c] - __uint_as_float(hb));
-                        }
+                    for (int c = 0; c < 4; ++c) {
+                        uint32_t hb = __float_as_uint(ys[c]) & 0xffffe000u;
+                        hi[4 * v + c] = hb;
+                        lo[4 * v + c] = __float_as_uint(ys[c] - __uint_as_float(hb));
                     }
-                    TMEM_ST32(tm + lane_addr + TM_YH + 32 * half, hi);
-                    TMEM_ST32(tm + lane_addr + TM_YL + 32 * half, lo);
                 }
+                TMEM_ST32(tm + lane_addr + TM_YH + 32 * half, hi);
+                TMEM_ST32(tm + lane_addr + TM_YL + 32 * half, lo);
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 tc_fence_before();
                 mbar_arrive(bar(B_Y_READY));
@@ -348,7 +356,8 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                 tc_fence_after();
                 const uint32_t zt = tm + lane_addr + ((g & 1) ? TM_Z1 : TM_Z0);
 #pragma unroll 1
-                for (int c = 0; c < 4; ++c) {
+                for (int cc = 0; cc < 2; ++cc) {
+                    const int c = 2 * half + cc;
                     uint32_t z[32];
                     TMEM_LD32(zt + 32 * c, z);
                     // A chunk: box (jq = quarter, iq = c), row = lane, 128-byte swizzle on 16-byte chunks
@@ -370,18 +379,42 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                             dmu_acc += gv;
                             z[e] = rna_tf32(gv * gscale);
                         }
+                    } else if (dist == DIST_BERNOULLI) {
+                        // softplus(z) - a z ; sigmoid(z) - a ; branch-free (missing entries select 0)
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) {
+                            const bool ob = is_observed(a[e]);
+                            const float a0 = ob ? a[e] : 0.f;
+                            float z4 = fmaf(__uint_as_float(z[e]), sigma, muj);
+                            float ex = __expf(-fabsf(z4));
+                            float r = __frcp_rn(1.0f + ex);
+                            float sg = z4 >= 0.f ? r : ex * r;
+                            float l = fmaxf(z4, 0.f) + __logf(1.0f + ex) - a0 * z4;
+                            float gv = ob ? (sg - a0) * wj : 0.f;
+                            loss_acc += ob ? 2.f * wj * l : 0.f;
+                            dmu_acc += gv;
+                            z[e] = rna_tf32(gv * gscale);
+                        }
+                    } else if (dist == DIST_POISSON) {
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) {
+                            const bool ob = is_observed(a[e]);
+                            const float a0 = ob ? a[e] : 0.f;
+                            float z4 = fmaf(__uint_as_float(z[e]), sigma, muj);
+                            float ez = __expf(z4);
+                            float gv = ob ? (ez - a0) * wj : 0.f;
+                            loss_acc += ob ? 2.f * wj * (ez - a0 * z4) : 0.f;
+                            dmu_acc += gv;
+                            z[e] = rna_tf32(gv * gscale);
+                        }
                     } else {
 #pragma unroll
                         for (int e = 0; e < 32; ++e) {
-                            float gv = 0.f;
-                            if (is_observed(a[e])) {
-                                float z4 = fmaf(__uint_as_float(z[e]), sigma, muj);
-                                float l;
-                                noise_eval(dist, z4, a[e], thp, dp.ordinal_eps, dp.hinge_margin, l, gv);
-                                gv *= wj;
-                                loss_acc = fmaf(2.f * wj, l, loss_acc);   // keep the common 1/2 factor at flush
-                                dmu_acc += gv;
-                            }
+                            float z4 = fmaf(__uint_as_float(z[e]), sigma, muj);
+                            float2 lg = noise_eval_slow(dist, z4, a[e], th4, dp.ordinal_eps, dp.hinge_margin);
+                            float gv = lg.y * wj;
+                            loss_acc = fmaf(2.f * wj, lg.x, loss_acc);   // keep the common 1/2 factor at flush
+                            dmu_acc += gv;
                             z[e] = rna_tf32(gv * gscale);
                         }
                     }
@@ -409,11 +442,12 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
             // ---- item epilogue: dY tile out of TMEM, column sums --------------------------------------
             mbar_wait(bar(B_DY_FULL), q & 1);
             tc_fence_after();
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
+            {
                 uint32_t r[32];
                 TMEM_LD32(tm + lane_addr + TM_DY + 32 * half, r);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                tc_fence_before();
+                mbar_arrive(bar(B_DY_EMPTY));
                 if (jok) {
                     float* dst = dp.dY + (size_t)j * KK + 32 * half;
 #pragma unroll
@@ -425,8 +459,6 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                     }
                 }
             }
-            tc_fence_before();
-            mbar_arrive(bar(B_DY_EMPTY));
             if (jok) {
                 // dmu_j = sum_i g ; dlogsigma_j = sum_i sigma_j * g  (the reference's ColScale quirk)
                 atomicAdd(dp.dmu + j, dmu_acc);
@@ -434,7 +466,7 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
             }
             ++q;
         }
-        // data loss: sum over this warp group (warps 2-5), 0.5 factor applied here
+        // data loss: sum over the epilogue warps, 0.5 factor applied here
         loss_d *= 0.5;
         for (int o = 16; o > 0; o >>= 1) loss_d += __shfl_xor_sync(0xffffffffu, loss_d, o);
         if (lane == 0) red_smem[warp] = loss_d;
@@ -442,7 +474,8 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     tc_fence_before();
     __syncthreads();
     if (threadIdx.x == 64) {
-        double t = red_smem[2] + red_smem[3] + red_smem[4] + red_smem[5];
+        double t = 0.0;
+        for (int w = 2; w < 2 + NEPI; ++w) t += red_smem[w];
         atomicAdd(dp.scalars + SC_DATA, t);
     }
     if (warp == 1) {
