@@ -38,12 +38,12 @@ namespace {
 constexpr int BJ = 128, BI = 128, KK = 64;
 constexpr int NEPI = 8;                   // epilogue warps: two per TMEM lane quarter
 constexpr int NTHREADS = 64 + 32 * NEPI;  // warp 0 TMA, warp 1 MMA, warps 2.. epilogue
-constexpr uint32_t XS_BYTES = 65536, XTS_BYTES = 32768, YTS_BYTES = 32768, AG_BYTES = 65536;
-constexpr uint32_t SMEM_DATA = XS_BYTES + XTS_BYTES + YTS_BYTES + AG_BYTES;
+constexpr uint32_t XS_BYTES = 32768, XTS_BYTES = 32768, YTS_BYTES = 32768, AG_BYTES = 65536;
+constexpr uint32_t SMEM_DATA = XS_BYTES + XTS_BYTES + YTS_BYTES + 2 * AG_BYTES;   // A/G buffer is double-buffered
 constexpr uint32_t SMEM_TOTAL = SMEM_DATA + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr uint32_t TM_YH = 0, TM_YL = 64, TM_Z0 = 128, TM_Z1 = 256, TM_DY = 384, TM_DX = 448;
 
-enum Bar { B_FULL_X = 0, B_EMPTY_X, B_FULL_XT, B_EMPTY_XT, B_FULL_A, B_EMPTY_AG, B_Z_FULL0, B_Z_FULL1,
+enum Bar { B_FULL_X = 0, B_EMPTY_X, B_FULL_XT, B_EMPTY_XT, B_FULL_A0, B_FULL_A1, B_EMPTY_AG0, B_EMPTY_AG1, B_Z_FULL0, B_Z_FULL1,
            B_G_READY, B_DX_FULL, B_DX_EMPTY, B_Y_READY, B_YT_FULL, B_YT_EMPTY, B_DY_FULL, B_DY_EMPTY, B_COUNT };
 
 // ---- PTX wrappers --------------------------------------------------------------------------
@@ -163,8 +163,8 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
     const uint32_t XS = base, XTS = XS + XS_BYTES, YTS = XTS + XTS_BYTES, AG = YTS + YTS_BYTES;
-    const uint32_t BARS = AG + AG_BYTES;
-    uint8_t* ag_ptr = gbase + XS_BYTES + XTS_BYTES + YTS_BYTES;
+    const uint32_t BARS = AG + 2 * AG_BYTES;
+    uint8_t* ag_ptr0 = gbase + XS_BYTES + XTS_BYTES + YTS_BYTES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + SMEM_DATA + 8 * B_COUNT);
     __shared__ double red_smem[NTHREADS / 32];
     auto bar = [&](int b) { return BARS + 8u * (uint32_t)b; };
@@ -200,47 +200,58 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                 for (int b = 0; b < 4; ++b) tma_load_2d(YTS + b * 8192, &tmYT, bar(B_YT_FULL), j0 + 32 * b, 0);
                 for (int it = it0; it < it1; ++it, ++g) {
                     const int i0 = it * BI;
-                    mbar_wait(bar(B_EMPTY_X), (g & 1) ^ 1);
-                    mbar_expect_tx(bar(B_FULL_X), XS_BYTES);
-                    for (int kb = 0; kb < 2; ++kb) {
-                        tma_load_2d(XS + kb * 16384, &tmX, bar(B_FULL_X), 32 * kb, i0);
-                        tma_load_2d(XS + 32768 + kb * 16384, &tmXlo, bar(B_FULL_X), 32 * kb, i0);
+                    const uint32_t ab = g & 1;
+                    // A tile into buffer g&1 (released by MMA2 of tile g-2)
+                    mbar_wait(bar(ab ? B_EMPTY_AG1 : B_EMPTY_AG0), ((g >> 1) & 1) ^ 1);
+                    mbar_expect_tx(bar(ab ? B_FULL_A1 : B_FULL_A0), AG_BYTES);
+                    for (int jq = 0; jq < 4; ++jq)
+                        for (int iq = 0; iq < 4; ++iq)
+                            tma_load_2d(AG + ab * AG_BYTES + (jq * 4 + iq) * 4096, &tmA, bar(ab ? B_FULL_A1 : B_FULL_A0),
+                                        i0 + 32 * iq, j0 + 32 * jq);
+                    // X operands of MMA1, one 64-sample half at a time (single 32 KB buffer)
+                    for (int h = 0; h < 2; ++h) {
+                        const uint32_t xi = 2 * g + h;
+                        mbar_wait(bar(B_EMPTY_X), (xi & 1) ^ 1);
+                        mbar_expect_tx(bar(B_FULL_X), XS_BYTES);
+                        for (int kb = 0; kb < 2; ++kb) {
+                            tma_load_2d(XS + kb * 8192, &tmX, bar(B_FULL_X), 32 * kb, i0 + 64 * h);
+                            tma_load_2d(XS + 16384 + kb * 8192, &tmXlo, bar(B_FULL_X), 32 * kb, i0 + 64 * h);
+                        }
                     }
                     mbar_wait(bar(B_EMPTY_XT), (g & 1) ^ 1);
                     mbar_expect_tx(bar(B_FULL_XT), XTS_BYTES);
                     for (int b = 0; b < 4; ++b) tma_load_2d(XTS + b * 8192, &tmXT, bar(B_FULL_XT), i0 + 32 * b, 0);
-                    mbar_wait(bar(B_EMPTY_AG), (g & 1) ^ 1);
-                    mbar_expect_tx(bar(B_FULL_A), AG_BYTES);
-                    for (int jq = 0; jq < 4; ++jq)
-                        for (int iq = 0; iq < 4; ++iq)
-                            tma_load_2d(AG + (jq * 4 + iq) * 4096, &tmA, bar(B_FULL_A), i0 + 32 * iq, j0 + 32 * jq);
                 }
                 ++q;
             }
         }
     } else if (warp == 1) {
         // ================================ MMA issuer ===============================================
-        const uint32_t id_z = umma_idesc(128, 128), id_g = umma_idesc(128, 64);
+        const uint32_t id_g = umma_idesc(128, 64);
         uint32_t g = 0, q = 0;
+        const uint32_t id_zh = umma_idesc(128, 64);
         auto issue_mma1 = [&](uint32_t gg) {
-            mbar_wait(bar(B_FULL_X), gg & 1);
-            tc_fence_after();
-            if (lane == 0) {
-                const uint32_t zt = tm + ((gg & 1) ? TM_Z1 : TM_Z0);
-                uint32_t acc = 0;
-                for (int pass = 0; pass < p.z_passes; ++pass) {
-                    const uint32_t ya = tm + (pass == 1 ? TM_YL : TM_YH);
-                    const uint32_t xb = XS + (pass == 2 ? 32768u : 0u);
+            for (int h = 0; h < 2; ++h) {
+                const uint32_t xi = 2 * gg + h;
+                mbar_wait(bar(B_FULL_X), xi & 1);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t zt = tm + ((gg & 1) ? TM_Z1 : TM_Z0) + 64 * h;
+                    uint32_t acc = 0;
+                    for (int pass = 0; pass < p.z_passes; ++pass) {
+                        const uint32_t ya = tm + (pass == 1 ? TM_YL : TM_YH);
+                        const uint32_t xb = XS + (pass == 2 ? 16384u : 0u);
 #pragma unroll
-                    for (int s = 0; s < 8; ++s) {
-                        mma_ts(zt, ya + 8 * s, umma_desc(xb + (s >> 2) * 16384 + (s & 3) * 32), id_z, acc);
-                        acc = 1;
+                        for (int s = 0; s < 8; ++s) {
+                            mma_ts(zt, ya + 8 * s, umma_desc(xb + (s >> 2) * 8192 + (s & 3) * 32), id_zh, acc);
+                            acc = 1;
+                        }
                     }
+                    tc_commit(bar(B_EMPTY_X));
+                    if (h == 1) tc_commit(bar((gg & 1) ? B_Z_FULL1 : B_Z_FULL0));
                 }
-                tc_commit(bar(B_EMPTY_X));
-                tc_commit(bar((gg & 1) ? B_Z_FULL1 : B_Z_FULL0));
+                __syncwarp();
             }
-            __syncwarp();
         };
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
             int jt, it0, it1;
@@ -253,17 +264,17 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
             for (int it = it0; it < it1; ++it, ++g) {
                 if (it + 1 < it1) issue_mma1(g + 1);
                 mbar_wait(bar(B_G_READY), g & 1);
-                mbar_wait(bar(B_FULL_XT), g & 1);
                 mbar_wait(bar(B_DX_EMPTY), (g & 1) ^ 1);
+                mbar_wait(bar(B_FULL_XT), g & 1);
                 tc_fence_after();
                 if (lane == 0) {
                     const uint32_t ga = tm + ((g & 1) ? TM_Z1 : TM_Z0);
                     // MMA2 first (dX = G0' * Y'): its completion releases the A/G buffer for the next TMA load
 #pragma unroll
                     for (int s = 0; s < 16; ++s)
-                        mma_ss(tm + TM_DX, umma_desc(AG + (s >> 2) * 16384 + (s & 3) * 32),
+                        mma_ss(tm + TM_DX, umma_desc(AG + (g & 1) * AG_BYTES + (s >> 2) * 16384 + (s & 3) * 32),
                                umma_desc(YTS + (s >> 2) * 8192 + (s & 3) * 32), id_g, s > 0 ? 1u : 0u);
-                    tc_commit(bar(B_EMPTY_AG));
+                    tc_commit(bar((g & 1) ? B_EMPTY_AG1 : B_EMPTY_AG0));
                     tc_commit(bar(B_DX_FULL));
                     // MMA3: dY += G0 * X'
 #pragma unroll
@@ -324,7 +335,7 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
             const int ci = dp.colinfo[jj];
             const int dist = ci & 0xff;
             const float4 th4 = __ldg(reinterpret_cast<const float4*>(dp.thresholds + 4 * (ci >> 8)));
-            const float gscale = sigma;            // G0 = sigma_j * dL/dz4  (no batch layers on this path)
+            const float gscale = sigma * wj;       // G0 = w_j sigma_j * dloss/dz4  (no batch layers on this path)
             float dmu_acc = 0.f, loss_acc = 0.f;
 
             // ---- Y tile -> TMEM (hi = TF32 truncation as the tensor core would read it, lo = rest)
@@ -352,8 +363,9 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
             for (int it = it0; it < it1; ++it, ++g) {
                 const int i0 = it * BI;
                 mbar_wait(bar((g & 1) ? B_Z_FULL1 : B_Z_FULL0), (g >> 1) & 1);
-                mbar_wait(bar(B_FULL_A), g & 1);
+                mbar_wait(bar((g & 1) ? B_FULL_A1 : B_FULL_A0), (g >> 1) & 1);
                 tc_fence_after();
+                uint8_t* ag_ptr = ag_ptr0 + (g & 1) * AG_BYTES;
                 const uint32_t zt = tm + lane_addr + ((g & 1) ? TM_Z1 : TM_Z0);
 #pragma unroll 1
                 for (int cc = 0; cc < 2; ++cc) {
@@ -369,41 +381,42 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                         a[4 * v] = a4.x; a[4 * v + 1] = a4.y; a[4 * v + 2] = a4.z; a[4 * v + 3] = a4.w;
                     }
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    // dmu_acc / loss_acc collect the unweighted sums; the column weight w_j (a per-thread
+                    // constant) is applied once per tile.  G0 = (w_j sigma_j) * dloss/dz.
                     if (dist == DIST_NORMAL) {
 #pragma unroll
                         for (int e = 0; e < 32; ++e) {
-                            float z4 = fmaf(__uint_as_float(z[e]), sigma, muj);
-                            float d = is_observed(a[e]) ? z4 - a[e] : 0.f;
-                            float gv = d * wj;
-                            loss_acc = fmaf(gv, d, loss_acc);             // w (z-a)^2, halved at flush
-                            dmu_acc += gv;
-                            z[e] = rna_tf32(gv * gscale);
+                            float d = fmaf(__uint_as_float(z[e]), sigma, muj) - a[e];
+                            d = fabsf(a[e]) < INFINITY ? d : 0.f;        // NaN / Inf => missing (ordered compare)
+                            loss_acc = fmaf(d, d, loss_acc);              // (z-a)^2, halved and weighted at flush
+                            dmu_acc += d;
+                            z[e] = rna_tf32(d * gscale);
                         }
                     } else if (dist == DIST_BERNOULLI) {
                         // softplus(z) - a z ; sigmoid(z) - a ; branch-free (missing entries select 0)
 #pragma unroll
                         for (int e = 0; e < 32; ++e) {
-                            const bool ob = is_observed(a[e]);
+                            const bool ob = fabsf(a[e]) < INFINITY;
                             const float a0 = ob ? a[e] : 0.f;
                             float z4 = fmaf(__uint_as_float(z[e]), sigma, muj);
                             float ex = __expf(-fabsf(z4));
-                            float r = __frcp_rn(1.0f + ex);
+                            float r = __fdividef(1.0f, 1.0f + ex);
                             float sg = z4 >= 0.f ? r : ex * r;
                             float l = fmaxf(z4, 0.f) + __logf(1.0f + ex) - a0 * z4;
-                            float gv = ob ? (sg - a0) * wj : 0.f;
-                            loss_acc += ob ? 2.f * wj * l : 0.f;
+                            float gv = ob ? sg - a0 : 0.f;
+                            loss_acc += ob ? 2.f * l : 0.f;
                             dmu_acc += gv;
                             z[e] = rna_tf32(gv * gscale);
                         }
                     } else if (dist == DIST_POISSON) {
 #pragma unroll
                         for (int e = 0; e < 32; ++e) {
-                            const bool ob = is_observed(a[e]);
+                            const bool ob = fabsf(a[e]) < INFINITY;
                             const float a0 = ob ? a[e] : 0.f;
                             float z4 = fmaf(__uint_as_float(z[e]), sigma, muj);
                             float ez = __expf(z4);
-                            float gv = ob ? (ez - a0) * wj : 0.f;
-                            loss_acc += ob ? 2.f * wj * (ez - a0 * z4) : 0.f;
+                            float gv = ob ? ez - a0 : 0.f;
+                            loss_acc += ob ? 2.f * fmaf(-a0, z4, ez) : 0.f;
                             dmu_acc += gv;
                             z[e] = rna_tf32(gv * gscale);
                         }
@@ -412,8 +425,8 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                         for (int e = 0; e < 32; ++e) {
                             float z4 = fmaf(__uint_as_float(z[e]), sigma, muj);
                             float2 lg = noise_eval_slow(dist, z4, a[e], th4, dp.ordinal_eps, dp.hinge_margin);
-                            float gv = lg.y * wj;
-                            loss_acc = fmaf(2.f * wj, lg.x, loss_acc);   // keep the common 1/2 factor at flush
+                            float gv = lg.y;
+                            loss_acc = fmaf(2.f, lg.x, loss_acc);        // keep the common 1/2 factor at flush
                             dmu_acc += gv;
                             z[e] = rna_tf32(gv * gscale);
                         }
@@ -429,7 +442,7 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                         *reinterpret_cast<uint32_t*>(gbox + e * 128 + (((lane >> 2) ^ (e & 7)) << 4) + ((lane & 3) << 2)) = z[e];
                     }
                 }
-                loss_d += (double)loss_acc;
+                loss_d += (double)(loss_acc * wj);
                 loss_acc = 0.f;
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 tc_fence_before();
@@ -461,8 +474,8 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
             }
             if (jok) {
                 // dmu_j = sum_i g ; dlogsigma_j = sum_i sigma_j * g  (the reference's ColScale quirk)
-                atomicAdd(dp.dmu + j, dmu_acc);
-                atomicAdd(dp.dlogsigma + j, dmu_acc * sigma);
+                atomicAdd(dp.dmu + j, dmu_acc * wj);
+                atomicAdd(dp.dlogsigma + j, dmu_acc * wj * sigma);
             }
             ++q;
         }
@@ -553,7 +566,7 @@ cudaError_t launch_data_pass_tc(const DataPassParams& dp, float* Xlo, float* XT,
     if (e != cudaSuccess) return e;
 
     CUtensorMap tmX, tmXlo, tmXT, tmYT, tmA;
-    bool ok = make_map(&tmX, dp.X, KK, dp.Mp, KK, 128, false) && make_map(&tmXlo, Xlo, KK, dp.Mp, KK, 128, false) &&
+    bool ok = make_map(&tmX, dp.X, KK, dp.Mp, KK, 64, false) && make_map(&tmXlo, Xlo, KK, dp.Mp, KK, 64, false) &&
               make_map(&tmXT, XT, dp.Mp, KK, dp.Mp, 64, false) && make_map(&tmYT, YT, dp.Np, KK, dp.Np, 64, false) &&
               make_map(&tmA, dp.A, dp.lda, dp.N, dp.lda, 32, true);
     if (!ok) return cudaErrorUnknown;
