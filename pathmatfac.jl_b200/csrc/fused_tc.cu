@@ -1,29 +1,31 @@
 // Fused data pass on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), K = 64.
 //
 // One persistent CTA per SM walks work items (feature tile of 128 x chunk of samples).  Per
-// 128x128 tile of A (64 KB, streamed once through TMA-staged shared memory):
+// 128-feature x 64-sample tile of A (32 KB, streamed once through TMA-staged shared memory):
 //
 //   MMA1  Z'[j,i]  = sum_k Y[j,k] X[i,k]     A = Y tile in TMEM (hi / lo), B = X tile in smem
 //                                            3xTF32: Yh*Xh + Yl*Xh + Yh*Xl, FP32 accumulate in TMEM
-//   epilogue (4 warps, TMEM lane = feature j, so every column parameter is a per-thread
+//   epilogue (8 warps, TMEM lane = feature j, so every column parameter is a per-thread
 //            register and every column-gradient sum is a private accumulator):
 //            ColScale/ColShift, noise loss, dL/dz with the NaN mask (src/layers.jl:9-90,
 //            Appendix B of SURVEY.md), G0 written back to TMEM in place of Z and, transposed,
 //            into the shared-memory buffer the A tile came from
-//   MMA3  dY[j,k] += sum_i G0[j,i] X[i,k]    A = G0 in TMEM, B = X' tile (k-major copy) in smem
 //   MMA2  dX[i,k]  = sum_j G0[j,i] Y[j,k]    A = G0' in smem, B = Y' tile (k-major copy) in smem
+//   MMA3  dY[j,k] += sum_i G0[j,i] X[i,k]    A = G0 in TMEM, B = X' tile (k-major copy) in smem
 //
 // Z and dL/dZ never exist in HBM.  dY stays in TMEM across the sample loop of an item; the
 // per-tile dX block is read back from TMEM and reduced into global memory with 128-bit REDs.
-// Gradient contractions use single-pass TF32 with round-to-nearest operands (precision mode 1);
-// the Z contraction is 3xTF32 unless precision mode 2 asks for plain TF32.
+// Gradient contractions use single-pass TF32 with round-to-nearest operands; the Z contraction
+// is 3xTF32 unless precision mode 2 asks for plain TF32.
 //
-// Shared memory (192 KB, one CTA per SM), all operands K-major with the 128-byte swizzle:
-//   XS  64 KB  X tile raw FP32 (the tensor core truncates it to its TF32 "hi") + X_lo = X - trunc(X)
-//   XTS 32 KB  X' tile, YTS 32 KB Y' tile (RN-rounded TF32, produced by prep_operands_kernel)
-//   AG  64 KB  A tile as 16 TMA boxes of 32x32; box (jq,iq) sits at (jq*4+iq)*4 KB so that the
-//              slice a warp reads as A is exactly the slice it later overwrites with G0'.
-// TMEM (512 columns): Yh 0-63 | Yl 64-127 | Z0 128-255 | Z1 256-383 | dY 384-447 | dX 448-511.
+// Everything that is streamed per tile is double-buffered (TMA runs up to two tiles ahead):
+//   XS  2 x 32 KB  X tile raw FP32 (the tensor core truncates it to its TF32 "hi") + X_lo = X - trunc(X)
+//   XTS 2 x 16 KB  X' tile;  YTS 32 KB  Y' tile (resident per item)   (RN-rounded TF32 operands)
+//   AG  2 x 32 KB  A tile as 8 TMA boxes of 32x32; box (jq,iq) sits at (jq*2+iq)*4 KB so that the
+//                  slice a warp reads as A is exactly the slice it later overwrites with G0'.
+//   MMA2 runs with M = 128 over the 64 valid rows of G0' (the upper 64 accumulator lanes are junk
+//   and never read), hence the 8 KB pad behind the last A/G buffer.
+// TMEM (512 columns): Yh 0 | Yl 64 | Z0 128 | Z1 192 | dY 256 | dX0 320 | dX1 384.
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -35,16 +37,18 @@ namespace pmf {
 
 namespace {
 
-constexpr int BJ = 128, BI = 128, KK = 64;
-constexpr int NEPI = 8;                   // epilogue warps: two per TMEM lane quarter
+constexpr int BJ = 128, BI = 64, KK = 64;
+constexpr int NEPI = 8;                   // epilogue warps: (TMEM lane quarter, 32-column chunk)
 constexpr int NTHREADS = 64 + 32 * NEPI;  // warp 0 TMA, warp 1 MMA, warps 2.. epilogue
-constexpr uint32_t XS_BYTES = 32768, XTS_BYTES = 32768, YTS_BYTES = 32768, AG_BYTES = 65536;
-constexpr uint32_t SMEM_DATA = XS_BYTES + XTS_BYTES + YTS_BYTES + 2 * AG_BYTES;   // A/G buffer is double-buffered
+constexpr uint32_t XS_BYTES = 32768, XTS_BYTES = 16384, YTS_BYTES = 32768, AG_BYTES = 32768, AG_PAD = 8192;
+constexpr uint32_t SMEM_DATA = 2 * XS_BYTES + 2 * XTS_BYTES + YTS_BYTES + 2 * AG_BYTES + AG_PAD;
 constexpr uint32_t SMEM_TOTAL = SMEM_DATA + 1024 /*align slack*/ + 256 /*barriers*/;
-constexpr uint32_t TM_YH = 0, TM_YL = 64, TM_Z0 = 128, TM_Z1 = 256, TM_DY = 384, TM_DX = 448;
+constexpr uint32_t TM_YH = 0, TM_YL = 64, TM_Z0 = 128, TM_DY = 256, TM_DX0 = 320;   // Z1 = Z0+64, dX1 = dX0+64
 
-enum Bar { B_FULL_X = 0, B_EMPTY_X, B_FULL_XT, B_EMPTY_XT, B_FULL_A0, B_FULL_A1, B_EMPTY_AG0, B_EMPTY_AG1, B_Z_FULL0, B_Z_FULL1,
-           B_G_READY, B_DX_FULL, B_DX_EMPTY, B_Y_READY, B_YT_FULL, B_YT_EMPTY, B_DY_FULL, B_DY_EMPTY, B_COUNT };
+// barriers that exist twice are indexed  B_xxx + (tile & 1)
+enum Bar { B_FULL_X = 0, B_EMPTY_X = 2, B_FULL_XT = 4, B_EMPTY_XT = 6, B_FULL_A = 8, B_EMPTY_AG = 10, B_Z_FULL = 12,
+           B_G_READY = 14, B_DX_FULL = 16, B_DX_EMPTY = 18, B_Y_READY = 20, B_YT_FULL, B_YT_EMPTY, B_DY_FULL,
+           B_DY_EMPTY, B_COUNT };
 
 // ---- PTX wrappers --------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -162,9 +166,9 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
-    const uint32_t XS = base, XTS = XS + XS_BYTES, YTS = XTS + XTS_BYTES, AG = YTS + YTS_BYTES;
-    const uint32_t BARS = AG + 2 * AG_BYTES;
-    uint8_t* ag_ptr0 = gbase + XS_BYTES + XTS_BYTES + YTS_BYTES;
+    const uint32_t XS = base, XTS = XS + 2 * XS_BYTES, YTS = XTS + 2 * XTS_BYTES, AG = YTS + YTS_BYTES;
+    const uint32_t BARS = base + SMEM_DATA;
+    uint8_t* ag_ptr0 = gbase + (AG - base);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + SMEM_DATA + 8 * B_COUNT);
     __shared__ double red_smem[NTHREADS / 32];
     auto bar = [&](int b) { return BARS + 8u * (uint32_t)b; };
@@ -173,7 +177,9 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
 
     if (threadIdx.x == 0) {
         for (int b = 0; b < B_COUNT; ++b) {
-            uint32_t cnt = (b == B_G_READY || b == B_DX_EMPTY || b == B_Y_READY || b == B_DY_EMPTY) ? 32u * NEPI : 1u;
+            uint32_t cnt = 1u;
+            if (b == B_G_READY || b == B_G_READY + 1 || b == B_Y_READY || b == B_DY_EMPTY) cnt = 32u * NEPI;
+            if (b == B_DX_EMPTY || b == B_DX_EMPTY + 1) cnt = 128u;      // the 4 warps that read dX out
             mbar_init(bar(b), cnt);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -200,58 +206,52 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                 for (int b = 0; b < 4; ++b) tma_load_2d(YTS + b * 8192, &tmYT, bar(B_YT_FULL), j0 + 32 * b, 0);
                 for (int it = it0; it < it1; ++it, ++g) {
                     const int i0 = it * BI;
-                    const uint32_t ab = g & 1;
-                    // A tile into buffer g&1 (released by MMA2 of tile g-2)
-                    mbar_wait(bar(ab ? B_EMPTY_AG1 : B_EMPTY_AG0), ((g >> 1) & 1) ^ 1);
-                    mbar_expect_tx(bar(ab ? B_FULL_A1 : B_FULL_A0), AG_BYTES);
-                    for (int jq = 0; jq < 4; ++jq)
-                        for (int iq = 0; iq < 4; ++iq)
-                            tma_load_2d(AG + ab * AG_BYTES + (jq * 4 + iq) * 4096, &tmA, bar(ab ? B_FULL_A1 : B_FULL_A0),
-                                        i0 + 32 * iq, j0 + 32 * jq);
-                    // X operands of MMA1, one 64-sample half at a time (single 32 KB buffer)
-                    for (int h = 0; h < 2; ++h) {
-                        const uint32_t xi = 2 * g + h;
-                        mbar_wait(bar(B_EMPTY_X), (xi & 1) ^ 1);
-                        mbar_expect_tx(bar(B_FULL_X), XS_BYTES);
-                        for (int kb = 0; kb < 2; ++kb) {
-                            tma_load_2d(XS + kb * 8192, &tmX, bar(B_FULL_X), 32 * kb, i0 + 64 * h);
-                            tma_load_2d(XS + 16384 + kb * 8192, &tmXlo, bar(B_FULL_X), 32 * kb, i0 + 64 * h);
-                        }
+                    const uint32_t b = g & 1, ph = ((g >> 1) & 1) ^ 1;
+                    // every buffer was last used two tiles ago
+                    mbar_wait(bar(B_EMPTY_X + b), ph);
+                    mbar_expect_tx(bar(B_FULL_X + b), XS_BYTES);
+                    for (int kb = 0; kb < 2; ++kb) {
+                        tma_load_2d(XS + b * XS_BYTES + kb * 8192, &tmX, bar(B_FULL_X + b), 32 * kb, i0);
+                        tma_load_2d(XS + b * XS_BYTES + 16384 + kb * 8192, &tmXlo, bar(B_FULL_X + b), 32 * kb, i0);
                     }
-                    mbar_wait(bar(B_EMPTY_XT), (g & 1) ^ 1);
-                    mbar_expect_tx(bar(B_FULL_XT), XTS_BYTES);
-                    for (int b = 0; b < 4; ++b) tma_load_2d(XTS + b * 8192, &tmXT, bar(B_FULL_XT), i0 + 32 * b, 0);
+                    mbar_wait(bar(B_EMPTY_AG + b), ph);
+                    mbar_expect_tx(bar(B_FULL_A + b), AG_BYTES);
+                    for (int jq = 0; jq < 4; ++jq)
+                        for (int iq = 0; iq < 2; ++iq)
+                            tma_load_2d(AG + b * AG_BYTES + (jq * 2 + iq) * 4096, &tmA, bar(B_FULL_A + b), i0 + 32 * iq,
+                                        j0 + 32 * jq);
+                    mbar_wait(bar(B_EMPTY_XT + b), ph);
+                    mbar_expect_tx(bar(B_FULL_XT + b), XTS_BYTES);
+                    for (int ib = 0; ib < 2; ++ib)
+                        tma_load_2d(XTS + b * XTS_BYTES + ib * 8192, &tmXT, bar(B_FULL_XT + b), i0 + 32 * ib, 0);
                 }
                 ++q;
             }
         }
     } else if (warp == 1) {
         // ================================ MMA issuer ===============================================
-        const uint32_t id_g = umma_idesc(128, 64);
+        const uint32_t id_g = umma_idesc(128, 64);     // every MMA here is 128 x 64 x 8
         uint32_t g = 0, q = 0;
-        const uint32_t id_zh = umma_idesc(128, 64);
         auto issue_mma1 = [&](uint32_t gg) {
-            for (int h = 0; h < 2; ++h) {
-                const uint32_t xi = 2 * gg + h;
-                mbar_wait(bar(B_FULL_X), xi & 1);
-                tc_fence_after();
-                if (lane == 0) {
-                    const uint32_t zt = tm + ((gg & 1) ? TM_Z1 : TM_Z0) + 64 * h;
-                    uint32_t acc = 0;
-                    for (int pass = 0; pass < p.z_passes; ++pass) {
-                        const uint32_t ya = tm + (pass == 1 ? TM_YL : TM_YH);
-                        const uint32_t xb = XS + (pass == 2 ? 16384u : 0u);
+            const uint32_t b = gg & 1;
+            mbar_wait(bar(B_FULL_X + b), (gg >> 1) & 1);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t zt = tm + TM_Z0 + 64 * b;
+                uint32_t acc = 0;
+                for (int pass = 0; pass < p.z_passes; ++pass) {
+                    const uint32_t ya = tm + (pass == 1 ? TM_YL : TM_YH);
+                    const uint32_t xb = XS + b * XS_BYTES + (pass == 2 ? 16384u : 0u);
 #pragma unroll
-                        for (int s = 0; s < 8; ++s) {
-                            mma_ts(zt, ya + 8 * s, umma_desc(xb + (s >> 2) * 8192 + (s & 3) * 32), id_zh, acc);
-                            acc = 1;
-                        }
+                    for (int s = 0; s < 8; ++s) {
+                        mma_ts(zt, ya + 8 * s, umma_desc(xb + (s >> 2) * 8192 + (s & 3) * 32), id_g, acc);
+                        acc = 1;
                     }
-                    tc_commit(bar(B_EMPTY_X));
-                    if (h == 1) tc_commit(bar((gg & 1) ? B_Z_FULL1 : B_Z_FULL0));
                 }
-                __syncwarp();
+                tc_commit(bar(B_EMPTY_X + b));
+                tc_commit(bar(B_Z_FULL + b));
             }
+            __syncwarp();
         };
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
             int jt, it0, it1;
@@ -263,25 +263,30 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
             issue_mma1(g);
             for (int it = it0; it < it1; ++it, ++g) {
                 if (it + 1 < it1) issue_mma1(g + 1);
-                mbar_wait(bar(B_G_READY), g & 1);
-                mbar_wait(bar(B_DX_EMPTY), (g & 1) ^ 1);
-                mbar_wait(bar(B_FULL_XT), g & 1);
+                const uint32_t b = g & 1, ph = (g >> 1) & 1;
+                mbar_wait(bar(B_G_READY + b), ph);
+                mbar_wait(bar(B_DX_EMPTY + b), ph ^ 1);
                 tc_fence_after();
                 if (lane == 0) {
-                    const uint32_t ga = tm + ((g & 1) ? TM_Z1 : TM_Z0);
-                    // MMA2 first (dX = G0' * Y'): its completion releases the A/G buffer for the next TMA load
+                    // MMA2 first (dX = G0' * Y'): its completion releases the A/G buffer for the TMA producer
 #pragma unroll
                     for (int s = 0; s < 16; ++s)
-                        mma_ss(tm + TM_DX, umma_desc(AG + (g & 1) * AG_BYTES + (s >> 2) * 16384 + (s & 3) * 32),
+                        mma_ss(tm + TM_DX0 + 64 * b, umma_desc(AG + b * AG_BYTES + (s >> 2) * 8192 + (s & 3) * 32),
                                umma_desc(YTS + (s >> 2) * 8192 + (s & 3) * 32), id_g, s > 0 ? 1u : 0u);
-                    tc_commit(bar((g & 1) ? B_EMPTY_AG1 : B_EMPTY_AG0));
-                    tc_commit(bar(B_DX_FULL));
+                    tc_commit(bar(B_EMPTY_AG + b));
+                    tc_commit(bar(B_DX_FULL + b));
+                }
+                __syncwarp();
+                mbar_wait(bar(B_FULL_XT + b), ph);
+                tc_fence_after();
+                if (lane == 0) {
                     // MMA3: dY += G0 * X'
+                    const uint32_t ga = tm + TM_Z0 + 64 * b;
 #pragma unroll
-                    for (int s = 0; s < 16; ++s)
-                        mma_ts(tm + TM_DY, ga + 8 * s, umma_desc(XTS + (s >> 2) * 8192 + (s & 3) * 32), id_g,
+                    for (int s = 0; s < 8; ++s)
+                        mma_ts(tm + TM_DY, ga + 8 * s, umma_desc(XTS + b * XTS_BYTES + (s >> 2) * 8192 + (s & 3) * 32), id_g,
                                (it > it0 || s > 0) ? 1u : 0u);
-                    tc_commit(bar(B_EMPTY_XT));
+                    tc_commit(bar(B_EMPTY_XT + b));
                 }
                 __syncwarp();
             }
@@ -294,24 +299,25 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         }
     } else {
         // ================================ epilogue warps ===========================================
-        // Two warps share a TMEM lane quarter: warp (quarter, half) owns the 32-column chunks
-        // c = 2*half, 2*half+1 of every tile (and columns 32*half.. of the 64-wide dX/dY/Y tiles).
-        const int quarter = warp & 3;                 // TMEM lanes 32*quarter .. +31
+        // warp (quarter, half): TMEM lanes 32*quarter.., columns 32*half.. of every 64-wide tile.
+        const int quarter = warp & 3;
         const int half = (warp - 2) >> 2;
         const int lrow = 32 * quarter + lane;         // feature lane (G epilogue) / sample lane (dX read-out)
         const uint32_t lane_addr = ((uint32_t)(32 * quarter)) << 16;
         uint32_t g = 0, q = 0;
         double loss_d = 0.0;
-        // dX read-out of the tile whose MMA2 was issued last (deferred by one tile)
+        // dX read-out (deferred by one tile); only lanes 0..63 of the accumulator are valid rows
         auto dx_out = [&](uint32_t gg, int i0) {
-            mbar_wait(bar(B_DX_FULL), gg & 1);
+            if (quarter >= 2) return;
+            const uint32_t b = gg & 1;
+            mbar_wait(bar(B_DX_FULL + b), (gg >> 1) & 1);
             tc_fence_after();
             const int i = i0 + lrow;
             uint32_t r[32];
-            TMEM_LD32(tm + lane_addr + TM_DX + 32 * half, r);
+            TMEM_LD32(tm + lane_addr + TM_DX0 + 64 * b + 32 * half, r);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             tc_fence_before();
-            mbar_arrive(bar(B_DX_EMPTY));
+            mbar_arrive(bar(B_DX_EMPTY + b));
             if (i < dp.M) {
                 float* dst = dp.dX + (size_t)i * KK + 32 * half;
 #pragma unroll
@@ -361,93 +367,88 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
             }
 
             for (int it = it0; it < it1; ++it, ++g) {
-                const int i0 = it * BI;
-                mbar_wait(bar((g & 1) ? B_Z_FULL1 : B_Z_FULL0), (g >> 1) & 1);
-                mbar_wait(bar((g & 1) ? B_FULL_A1 : B_FULL_A0), (g >> 1) & 1);
+                const uint32_t b = g & 1, ph = (g >> 1) & 1;
+                mbar_wait(bar(B_Z_FULL + b), ph);
+                mbar_wait(bar(B_FULL_A + b), ph);
                 tc_fence_after();
-                uint8_t* ag_ptr = ag_ptr0 + (g & 1) * AG_BYTES;
-                const uint32_t zt = tm + lane_addr + ((g & 1) ? TM_Z1 : TM_Z0);
-#pragma unroll 1
-                for (int cc = 0; cc < 2; ++cc) {
-                    const int c = 2 * half + cc;
-                    uint32_t z[32];
-                    TMEM_LD32(zt + 32 * c, z);
-                    // A chunk: box (jq = quarter, iq = c), row = lane, 128-byte swizzle on 16-byte chunks
-                    const uint8_t* box = ag_ptr + (quarter * 4 + c) * 4096;
-                    float a[32];
+                const uint32_t zt = tm + lane_addr + TM_Z0 + 64 * b + 32 * half;
+                uint8_t* ag_ptr = ag_ptr0 + b * AG_BYTES;
+                uint32_t z[32];
+                TMEM_LD32(zt, z);
+                // A chunk: box (jq = quarter, iq = half), row = lane, 128-byte swizzle on 16-byte chunks
+                const uint8_t* box = ag_ptr + (quarter * 2 + half) * 4096;
+                float a[32];
 #pragma unroll
-                    for (int v = 0; v < 8; ++v) {
-                        float4 a4 = *reinterpret_cast<const float4*>(box + lane * 128 + ((v ^ (lane & 7)) << 4));
-                        a[4 * v] = a4.x; a[4 * v + 1] = a4.y; a[4 * v + 2] = a4.z; a[4 * v + 3] = a4.w;
-                    }
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    // dmu_acc / loss_acc collect the unweighted sums; the column weight w_j (a per-thread
-                    // constant) is applied once per tile.  G0 = (w_j sigma_j) * dloss/dz.
-                    if (dist == DIST_NORMAL) {
-#pragma unroll
-                        for (int e = 0; e < 32; ++e) {
-                            float d = fmaf(__uint_as_float(z[e]), sigma, muj) - a[e];
-                            d = fabsf(a[e]) < INFINITY ? d : 0.f;        // NaN / Inf => missing (ordered compare)
-                            loss_acc = fmaf(d, d, loss_acc);              // (z-a)^2, halved and weighted at flush
-                            dmu_acc += d;
-                            z[e] = rna_tf32(d * gscale);
-                        }
-                    } else if (dist == DIST_BERNOULLI) {
-                        // softplus(z) - a z ; sigmoid(z) - a ; branch-free (missing entries select 0)
-#pragma unroll
-                        for (int e = 0; e < 32; ++e) {
-                            const bool ob = fabsf(a[e]) < INFINITY;
-                            const float a0 = ob ? a[e] : 0.f;
-                            float z4 = fmaf(__uint_as_float(z[e]), sigma, muj);
-                            float ex = __expf(-fabsf(z4));
-                            float r = __fdividef(1.0f, 1.0f + ex);
-                            float sg = z4 >= 0.f ? r : ex * r;
-                            float l = fmaxf(z4, 0.f) + __logf(1.0f + ex) - a0 * z4;
-                            float gv = ob ? sg - a0 : 0.f;
-                            loss_acc += ob ? 2.f * l : 0.f;
-                            dmu_acc += gv;
-                            z[e] = rna_tf32(gv * gscale);
-                        }
-                    } else if (dist == DIST_POISSON) {
-#pragma unroll
-                        for (int e = 0; e < 32; ++e) {
-                            const bool ob = fabsf(a[e]) < INFINITY;
-                            const float a0 = ob ? a[e] : 0.f;
-                            float z4 = fmaf(__uint_as_float(z[e]), sigma, muj);
-                            float ez = __expf(z4);
-                            float gv = ob ? ez - a0 : 0.f;
-                            loss_acc += ob ? 2.f * fmaf(-a0, z4, ez) : 0.f;
-                            dmu_acc += gv;
-                            z[e] = rna_tf32(gv * gscale);
-                        }
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < 32; ++e) {
-                            float z4 = fmaf(__uint_as_float(z[e]), sigma, muj);
-                            float2 lg = noise_eval_slow(dist, z4, a[e], th4, dp.ordinal_eps, dp.hinge_margin);
-                            float gv = lg.y;
-                            loss_acc = fmaf(2.f, lg.x, loss_acc);        // keep the common 1/2 factor at flush
-                            dmu_acc += gv;
-                            z[e] = rna_tf32(gv * gscale);
-                        }
-                    }
-                    // G0 back to TMEM in place of Z (A operand of MMA3)
-                    TMEM_ST32(zt + 32 * c, z);
-                    // every lane of the warp has pulled its A row of this slice into registers
-                    __syncwarp();
-                    // G0' : rows i = 32c..32c+31 of K-atom box `quarter`, column = lane
-                    uint8_t* gbox = ag_ptr + quarter * 16384 + (32 * c) * 128;
+                for (int v = 0; v < 8; ++v) {
+                    float4 a4 = *reinterpret_cast<const float4*>(box + lane * 128 + ((v ^ (lane & 7)) << 4));
+                    a[4 * v] = a4.x; a[4 * v + 1] = a4.y; a[4 * v + 2] = a4.z; a[4 * v + 3] = a4.w;
+                }
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                // dmu_acc / loss_acc collect the unweighted sums; the column weight w_j (a per-thread
+                // constant) is applied once per tile.  G0 = (w_j sigma_j) * dloss/dz.
+                if (dist == DIST_NORMAL) {
 #pragma unroll
                     for (int e = 0; e < 32; ++e) {
-                        *reinterpret_cast<uint32_t*>(gbox + e * 128 + (((lane >> 2) ^ (e & 7)) << 4) + ((lane & 3) << 2)) = z[e];
+                        float d = fmaf(__uint_as_float(z[e]), sigma, muj) - a[e];
+                        d = fabsf(a[e]) < INFINITY ? d : 0.f;        // NaN / Inf => missing (ordered compare)
+                        loss_acc = fmaf(d, d, loss_acc);              // (z-a)^2, halved and weighted at flush
+                        dmu_acc += d;
+                        z[e] = rna_tf32(d * gscale);
                     }
+                } else if (dist == DIST_BERNOULLI) {
+                    // softplus(z) - a z ; sigmoid(z) - a ; branch-free (missing entries select 0)
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) {
+                        const bool ob = fabsf(a[e]) < INFINITY;
+                        const float a0 = ob ? a[e] : 0.f;
+                        float z4 = fmaf(__uint_as_float(z[e]), sigma, muj);
+                        float ex = __expf(-fabsf(z4));
+                        float r = __fdividef(1.0f, 1.0f + ex);
+                        float sg = z4 >= 0.f ? r : ex * r;
+                        float l = fmaxf(z4, 0.f) + __logf(1.0f + ex) - a0 * z4;
+                        float gv = ob ? sg - a0 : 0.f;
+                        loss_acc += ob ? 2.f * l : 0.f;
+                        dmu_acc += gv;
+                        z[e] = rna_tf32(gv * gscale);
+                    }
+                } else if (dist == DIST_POISSON) {
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) {
+                        const bool ob = fabsf(a[e]) < INFINITY;
+                        const float a0 = ob ? a[e] : 0.f;
+                        float z4 = fmaf(__uint_as_float(z[e]), sigma, muj);
+                        float ez = __expf(z4);
+                        float gv = ob ? ez - a0 : 0.f;
+                        loss_acc += ob ? 2.f * fmaf(-a0, z4, ez) : 0.f;
+                        dmu_acc += gv;
+                        z[e] = rna_tf32(gv * gscale);
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) {
+                        float z4 = fmaf(__uint_as_float(z[e]), sigma, muj);
+                        float2 lg = noise_eval_slow(dist, z4, a[e], th4, dp.ordinal_eps, dp.hinge_margin);
+                        loss_acc = fmaf(2.f, lg.x, loss_acc);        // keep the common 1/2 factor at flush
+                        dmu_acc += lg.y;
+                        z[e] = rna_tf32(lg.y * gscale);
+                    }
+                }
+                // G0 back to TMEM in place of Z (A operand of MMA3)
+                TMEM_ST32(zt, z);
+                // every lane of the warp has pulled its A row of this slice into registers
+                __syncwarp();
+                // G0' : rows i = 32*half .. +31 of K-atom box `quarter` (8 KB per box), column = lane
+                uint8_t* gbox = ag_ptr + quarter * 8192 + (32 * half) * 128;
+#pragma unroll
+                for (int e = 0; e < 32; ++e) {
+                    *reinterpret_cast<uint32_t*>(gbox + e * 128 + (((lane >> 2) ^ (e & 7)) << 4) + ((lane & 3) << 2)) = z[e];
                 }
                 loss_d += (double)(loss_acc * wj);
                 loss_acc = 0.f;
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 tc_fence_before();
                 fence_async_smem();
-                mbar_arrive(bar(B_G_READY));
+                mbar_arrive(bar(B_G_READY + b));
                 if (it > it0) dx_out(g - 1, (it - 1) * BI);
             }
             dx_out(g - 1, (it1 - 1) * BI);
