@@ -84,19 +84,26 @@ __device__ __forceinline__ void tc_commit(uint32_t bar) {
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// The MMA warp stays converged and every operand is warp-uniform; `elect.sync` inside the asm picks
+// the issuing lane, so the compiler keeps descriptors in uniform registers (no per-MMA R2UR).
 // D[tmem] (+)= A[tmem] * B[smem]   (kind::tf32, cta_group::1)
 __device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
     asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        "{\n\t.reg .pred p, e;\n\telect.sync _|e, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
         ::"r"(d), "r"(a), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
 // D[tmem] (+)= A[smem] * B[smem]
 __device__ __forceinline__ void mma_ss(uint32_t d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
     asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        "{\n\t.reg .pred p, e;\n\telect.sync _|e, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tc_commit_elect(uint32_t bar) {
+    asm volatile(
+        "{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar) : "memory");
 }
 
 // K-major operand, 128-byte swizzle: rows are 128 B, 8-row groups are 1024 B apart.
@@ -173,7 +180,10 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     __shared__ double red_smem[NTHREADS / 32];
     auto bar = [&](int b) { return BARS + 8u * (uint32_t)b; };
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp index through a shuffle: the compiler then treats role branches as warp-uniform and keeps
+    // MMA descriptors / barrier addresses in uniform registers
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
         for (int b = 0; b < B_COUNT; ++b) {
@@ -194,64 +204,71 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     const uint32_t tm = *tmem_slot;
 
     if (warp == 0) {
-        // ================================ TMA producer ============================================
-        if (lane == 0) {
+        // ================================ TMA producers ===========================================
+        // Three independent lanes, one per stream, so that a buffer that is released late (the A/G
+        // tile waits for MMA2) never holds back the loads of the other streams.
+        if (lane < 3) {
             uint32_t g = 0, q = 0;
             for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
                 int jt, it0, it1;
                 item_range(p, item, jt, it0, it1);
                 const int j0 = jt * BJ;
-                mbar_wait(bar(B_YT_EMPTY), (q & 1) ^ 1);
-                mbar_expect_tx(bar(B_YT_FULL), YTS_BYTES);
-                for (int b = 0; b < 4; ++b) tma_load_2d(YTS + b * 8192, &tmYT, bar(B_YT_FULL), j0 + 32 * b, 0);
+                if (lane == 2) {
+                    mbar_wait(bar(B_YT_EMPTY), (q & 1) ^ 1);
+                    mbar_expect_tx(bar(B_YT_FULL), YTS_BYTES);
+                    for (int b = 0; b < 4; ++b) tma_load_2d(YTS + b * 8192, &tmYT, bar(B_YT_FULL), j0 + 32 * b, 0);
+                }
                 for (int it = it0; it < it1; ++it, ++g) {
                     const int i0 = it * BI;
-                    const uint32_t b = g & 1, ph = ((g >> 1) & 1) ^ 1;
-                    // every buffer was last used two tiles ago
-                    mbar_wait(bar(B_EMPTY_X + b), ph);
-                    mbar_expect_tx(bar(B_FULL_X + b), XS_BYTES);
-                    for (int kb = 0; kb < 2; ++kb) {
-                        tma_load_2d(XS + b * XS_BYTES + kb * 8192, &tmX, bar(B_FULL_X + b), 32 * kb, i0);
-                        tma_load_2d(XS + b * XS_BYTES + 16384 + kb * 8192, &tmXlo, bar(B_FULL_X + b), 32 * kb, i0);
+                    const uint32_t b = g & 1, ph = ((g >> 1) & 1) ^ 1;      // every buffer was last used two tiles ago
+                    if (lane == 0) {
+                        mbar_wait(bar(B_EMPTY_X + b), ph);
+                        mbar_expect_tx(bar(B_FULL_X + b), XS_BYTES);
+                        for (int kb = 0; kb < 2; ++kb) {
+                            tma_load_2d(XS + b * XS_BYTES + kb * 8192, &tmX, bar(B_FULL_X + b), 32 * kb, i0);
+                            tma_load_2d(XS + b * XS_BYTES + 16384 + kb * 8192, &tmXlo, bar(B_FULL_X + b), 32 * kb, i0);
+                        }
+                    } else if (lane == 1) {
+                        mbar_wait(bar(B_EMPTY_AG + b), ph);
+                        mbar_expect_tx(bar(B_FULL_A + b), AG_BYTES);
+                        for (int jq = 0; jq < 4; ++jq)
+                            for (int iq = 0; iq < 2; ++iq)
+                                tma_load_2d(AG + b * AG_BYTES + (jq * 2 + iq) * 4096, &tmA, bar(B_FULL_A + b), i0 + 32 * iq,
+                                            j0 + 32 * jq);
+                    } else {
+                        mbar_wait(bar(B_EMPTY_XT + b), ph);
+                        mbar_expect_tx(bar(B_FULL_XT + b), XTS_BYTES);
+                        for (int ib = 0; ib < 2; ++ib)
+                            tma_load_2d(XTS + b * XTS_BYTES + ib * 8192, &tmXT, bar(B_FULL_XT + b), i0 + 32 * ib, 0);
                     }
-                    mbar_wait(bar(B_EMPTY_AG + b), ph);
-                    mbar_expect_tx(bar(B_FULL_A + b), AG_BYTES);
-                    for (int jq = 0; jq < 4; ++jq)
-                        for (int iq = 0; iq < 2; ++iq)
-                            tma_load_2d(AG + b * AG_BYTES + (jq * 2 + iq) * 4096, &tmA, bar(B_FULL_A + b), i0 + 32 * iq,
-                                        j0 + 32 * jq);
-                    mbar_wait(bar(B_EMPTY_XT + b), ph);
-                    mbar_expect_tx(bar(B_FULL_XT + b), XTS_BYTES);
-                    for (int ib = 0; ib < 2; ++ib)
-                        tma_load_2d(XTS + b * XTS_BYTES + ib * 8192, &tmXT, bar(B_FULL_XT + b), i0 + 32 * ib, 0);
                 }
                 ++q;
             }
         }
     } else if (warp == 1) {
         // ================================ MMA issuer ===============================================
+        // All 32 lanes run this code converged with warp-uniform values; one elected lane issues.
         const uint32_t id_g = umma_idesc(128, 64);     // every MMA here is 128 x 64 x 8
+        const uint32_t tmu = __shfl_sync(0xffffffffu, tm, 0);
+        // descriptor of k-step s inside a K-major operand whose 32-wide K-atoms are `atom` bytes apart
+        auto kstep = [](uint64_t d0, int s, uint32_t atom) { return d0 + (uint64_t)((((s >> 2) * atom) + (s & 3) * 32) >> 4); };
         uint32_t g = 0, q = 0;
         auto issue_mma1 = [&](uint32_t gg) {
             const uint32_t b = gg & 1;
             mbar_wait(bar(B_FULL_X + b), (gg >> 1) & 1);
             tc_fence_after();
-            if (lane == 0) {
-                const uint32_t zt = tm + TM_Z0 + 64 * b;
-                uint32_t acc = 0;
-                for (int pass = 0; pass < p.z_passes; ++pass) {
-                    const uint32_t ya = tm + (pass == 1 ? TM_YL : TM_YH);
-                    const uint32_t xb = XS + b * XS_BYTES + (pass == 2 ? 16384u : 0u);
+            const uint32_t zt = tmu + TM_Z0 + 64 * b;
+            const uint64_t xraw = umma_desc(XS + b * XS_BYTES), xlo = umma_desc(XS + b * XS_BYTES + 16384u);
 #pragma unroll
-                    for (int s = 0; s < 8; ++s) {
-                        mma_ts(zt, ya + 8 * s, umma_desc(xb + (s >> 2) * 8192 + (s & 3) * 32), id_g, acc);
-                        acc = 1;
-                    }
-                }
-                tc_commit(bar(B_EMPTY_X + b));
-                tc_commit(bar(B_Z_FULL + b));
+            for (int s = 0; s < 8; ++s) mma_ts(zt, tmu + TM_YH + 8 * s, kstep(xraw, s, 8192), id_g, s > 0 ? 1u : 0u);
+            if (p.z_passes == 3) {
+#pragma unroll
+                for (int s = 0; s < 8; ++s) mma_ts(zt, tmu + TM_YL + 8 * s, kstep(xraw, s, 8192), id_g, 1u);
+#pragma unroll
+                for (int s = 0; s < 8; ++s) mma_ts(zt, tmu + TM_YH + 8 * s, kstep(xlo, s, 8192), id_g, 1u);
             }
-            __syncwarp();
+            tc_commit_elect(bar(B_EMPTY_X + b));
+            tc_commit_elect(bar(B_Z_FULL + b));
         };
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
             int jt, it0, it1;
@@ -261,40 +278,36 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
             mbar_wait(bar(B_DY_EMPTY), (q & 1) ^ 1);
             tc_fence_after();
             issue_mma1(g);
+            const uint64_t ytd = umma_desc(YTS);
             for (int it = it0; it < it1; ++it, ++g) {
                 if (it + 1 < it1) issue_mma1(g + 1);
                 const uint32_t b = g & 1, ph = (g >> 1) & 1;
                 mbar_wait(bar(B_G_READY + b), ph);
                 mbar_wait(bar(B_DX_EMPTY + b), ph ^ 1);
                 tc_fence_after();
-                if (lane == 0) {
+                {
                     // MMA2 first (dX = G0' * Y'): its completion releases the A/G buffer for the TMA producer
+                    const uint64_t gd = umma_desc(AG + b * AG_BYTES);
+                    const uint32_t dxt = tmu + TM_DX0 + 64 * b;
 #pragma unroll
-                    for (int s = 0; s < 16; ++s)
-                        mma_ss(tm + TM_DX0 + 64 * b, umma_desc(AG + b * AG_BYTES + (s >> 2) * 8192 + (s & 3) * 32),
-                               umma_desc(YTS + (s >> 2) * 8192 + (s & 3) * 32), id_g, s > 0 ? 1u : 0u);
-                    tc_commit(bar(B_EMPTY_AG + b));
-                    tc_commit(bar(B_DX_FULL + b));
+                    for (int s = 0; s < 16; ++s) mma_ss(dxt, kstep(gd, s, 8192), kstep(ytd, s, 8192), id_g, s > 0 ? 1u : 0u);
+                    tc_commit_elect(bar(B_EMPTY_AG + b));
+                    tc_commit_elect(bar(B_DX_FULL + b));
                 }
-                __syncwarp();
                 mbar_wait(bar(B_FULL_XT + b), ph);
                 tc_fence_after();
-                if (lane == 0) {
+                {
                     // MMA3: dY += G0 * X'
-                    const uint32_t ga = tm + TM_Z0 + 64 * b;
+                    const uint32_t ga = tmu + TM_Z0 + 64 * b;
+                    const uint64_t xtd = umma_desc(XTS + b * XTS_BYTES);
+                    const uint32_t first = it > it0 ? 1u : 0u;
 #pragma unroll
-                    for (int s = 0; s < 8; ++s)
-                        mma_ts(tm + TM_DY, ga + 8 * s, umma_desc(XTS + b * XTS_BYTES + (s >> 2) * 8192 + (s & 3) * 32), id_g,
-                               (it > it0 || s > 0) ? 1u : 0u);
-                    tc_commit(bar(B_EMPTY_XT + b));
+                    for (int s = 0; s < 8; ++s) mma_ts(tmu + TM_DY, ga + 8 * s, kstep(xtd, s, 8192), id_g, s > 0 ? 1u : first);
+                    tc_commit_elect(bar(B_EMPTY_XT + b));
                 }
-                __syncwarp();
             }
-            if (lane == 0) {
-                tc_commit(bar(B_DY_FULL));
-                tc_commit(bar(B_YT_EMPTY));
-            }
-            __syncwarp();
+            tc_commit_elect(bar(B_DY_FULL));
+            tc_commit_elect(bar(B_YT_EMPTY));
             ++q;
         }
     } else {
