@@ -38,7 +38,7 @@ namespace pmf {
 namespace {
 
 constexpr int BJ = 128, BI = 64, KK = 64;
-constexpr int NEPI = 8;                   // epilogue warps: (TMEM lane quarter, 32-column chunk)
+constexpr int NEPI = 16;                  // epilogue warps: (TMEM lane quarter, 16-column chunk)
 constexpr int NTHREADS = 64 + 32 * NEPI;  // warp 0 TMA, warp 1 MMA, warps 2.. epilogue
 constexpr uint32_t XS_BYTES = 32768, XTS_BYTES = 16384, YTS_BYTES = 32768, AG_BYTES = 32768, AG_PAD = 8192;
 constexpr uint32_t SMEM_DATA = 2 * XS_BYTES + 2 * XTS_BYTES + YTS_BYTES + 2 * AG_BYTES + AG_PAD;
@@ -135,6 +135,20 @@ __host__ __device__ constexpr uint32_t umma_idesc(int M, int N) {
                  "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]),   \
                  "r"(r[31]) : "memory")
 
+#define TMEM_LD16(taddr, r)                                                                                       \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "                                                        \
+                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"                                  \
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),  \
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),        \
+                   "=r"(r[15])                                                                                    \
+                 : "r"(taddr))
+#define TMEM_ST16(taddr, r)                                                                                       \
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "                                                  \
+                 "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"                                        \
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]),        \
+                 "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]),      \
+                 "r"(r[15]) : "memory")
+
 __device__ __forceinline__ uint32_t rna_tf32(float x) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -189,7 +203,7 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         for (int b = 0; b < B_COUNT; ++b) {
             uint32_t cnt = 1u;
             if (b == B_G_READY || b == B_G_READY + 1 || b == B_Y_READY || b == B_DY_EMPTY) cnt = 32u * NEPI;
-            if (b == B_DX_EMPTY || b == B_DX_EMPTY + 1) cnt = 128u;      // the 4 warps that read dX out
+            if (b == B_DX_EMPTY || b == B_DX_EMPTY + 1) cnt = 256u;      // the 8 warps that read dX out
             mbar_init(bar(b), cnt);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -312,11 +326,14 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         }
     } else {
         // ================================ epilogue warps ===========================================
-        // warp (quarter, half): TMEM lanes 32*quarter.., columns 32*half.. of every 64-wide tile.
+        // warp (quarter, c16): TMEM lanes 32*quarter.., columns 16*c16.. of every 64-wide tile.  Four
+        // warps per scheduler hide the TMEM / shared-memory latencies of one another.
         const int quarter = warp & 3;
-        const int half = (warp - 2) >> 2;
+        const int c16 = (warp - 2) >> 2;              // 0..3
+        const int iq = c16 >> 1;                      // which 32-sample A box of the tile
         const int lrow = 32 * quarter + lane;         // feature lane (G epilogue) / sample lane (dX read-out)
         const uint32_t lane_addr = ((uint32_t)(32 * quarter)) << 16;
+        const uint32_t pair_bar = 1u + (uint32_t)(quarter * 2 + iq);   // named barrier of the two warps sharing an A box
         uint32_t g = 0, q = 0;
         double loss_d = 0.0;
         // dX read-out (deferred by one tile); only lanes 0..63 of the accumulator are valid rows
@@ -326,15 +343,15 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
             mbar_wait(bar(B_DX_FULL + b), (gg >> 1) & 1);
             tc_fence_after();
             const int i = i0 + lrow;
-            uint32_t r[32];
-            TMEM_LD32(tm + lane_addr + TM_DX0 + 64 * b + 32 * half, r);
+            uint32_t r[16];
+            TMEM_LD16(tm + lane_addr + TM_DX0 + 64 * b + 16 * c16, r);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             tc_fence_before();
             mbar_arrive(bar(B_DX_EMPTY + b));
             if (i < dp.M) {
-                float* dst = dp.dX + (size_t)i * KK + 32 * half;
+                float* dst = dp.dX + (size_t)i * KK + 16 * c16;
 #pragma unroll
-                for (int v = 0; v < 8; ++v)
+                for (int v = 0; v < 4; ++v)
                     atomicAdd(reinterpret_cast<float4*>(dst) + v,
                               make_float4(__uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]),
                                           __uint_as_float(r[4 * v + 2]), __uint_as_float(r[4 * v + 3])));
@@ -355,14 +372,14 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
             const int dist = ci & 0xff;
             const float4 th4 = __ldg(reinterpret_cast<const float4*>(dp.thresholds + 4 * (ci >> 8)));
             const float gscale = sigma * wj;       // G0 = w_j sigma_j * dloss/dz4  (no batch layers on this path)
-            float dmu_acc = 0.f, loss_acc = 0.f;
+            float dmu_acc = 0.f, loss_acc = 0.f;   // unweighted sums over this item (<= a few thousand terms)
 
             // ---- Y tile -> TMEM (hi = TF32 truncation as the tensor core would read it, lo = rest)
             {
-                const float4* yrow = reinterpret_cast<const float4*>(dp.Y + (size_t)(jt * BJ + lrow) * KK) + 8 * half;
-                uint32_t hi[32], lo[32];
+                const float4* yrow = reinterpret_cast<const float4*>(dp.Y + (size_t)(jt * BJ + lrow) * KK) + 4 * c16;
+                uint32_t hi[16], lo[16];
 #pragma unroll
-                for (int v = 0; v < 8; ++v) {
+                for (int v = 0; v < 4; ++v) {
                     float4 y4 = __ldg(yrow + v);
                     float ys[4] = {y4.x, y4.y, y4.z, y4.w};
 #pragma unroll
@@ -372,8 +389,8 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                         lo[4 * v + c] = __float_as_uint(ys[c] - __uint_as_float(hb));
                     }
                 }
-                TMEM_ST32(tm + lane_addr + TM_YH + 32 * half, hi);
-                TMEM_ST32(tm + lane_addr + TM_YL + 32 * half, lo);
+                TMEM_ST16(tm + lane_addr + TM_YH + 16 * c16, hi);
+                TMEM_ST16(tm + lane_addr + TM_YL + 16 * c16, lo);
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 tc_fence_before();
                 mbar_arrive(bar(B_Y_READY));
@@ -384,24 +401,24 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                 mbar_wait(bar(B_Z_FULL + b), ph);
                 mbar_wait(bar(B_FULL_A + b), ph);
                 tc_fence_after();
-                const uint32_t zt = tm + lane_addr + TM_Z0 + 64 * b + 32 * half;
+                const uint32_t zt = tm + lane_addr + TM_Z0 + 64 * b + 16 * c16;
                 uint8_t* ag_ptr = ag_ptr0 + b * AG_BYTES;
-                uint32_t z[32];
-                TMEM_LD32(zt, z);
-                // A chunk: box (jq = quarter, iq = half), row = lane, 128-byte swizzle on 16-byte chunks
-                const uint8_t* box = ag_ptr + (quarter * 2 + half) * 4096;
-                float a[32];
+                uint32_t z[16];
+                TMEM_LD16(zt, z);
+                // A: box (jq = quarter, iq), row = lane, this warp's 16 columns = 4 swizzled 16-byte chunks
+                const uint8_t* box = ag_ptr + (quarter * 2 + iq) * 4096;
+                float a[16];
 #pragma unroll
-                for (int v = 0; v < 8; ++v) {
-                    float4 a4 = *reinterpret_cast<const float4*>(box + lane * 128 + ((v ^ (lane & 7)) << 4));
+                for (int v = 0; v < 4; ++v) {
+                    float4 a4 = *reinterpret_cast<const float4*>(box + lane * 128 + (((4 * (c16 & 1) + v) ^ (lane & 7)) << 4));
                     a[4 * v] = a4.x; a[4 * v + 1] = a4.y; a[4 * v + 2] = a4.z; a[4 * v + 3] = a4.w;
                 }
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 // dmu_acc / loss_acc collect the unweighted sums; the column weight w_j (a per-thread
-                // constant) is applied once per tile.  G0 = (w_j sigma_j) * dloss/dz.
+                // constant) is applied at the item flush.  G0 = (w_j sigma_j) * dloss/dz.
                 if (dist == DIST_NORMAL) {
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) {
+                    for (int e = 0; e < 16; ++e) {
                         float d = fmaf(__uint_as_float(z[e]), sigma, muj) - a[e];
                         d = fabsf(a[e]) < INFINITY ? d : 0.f;        // NaN / Inf => missing (ordered compare)
                         loss_acc = fmaf(d, d, loss_acc);              // (z-a)^2, halved and weighted at flush
@@ -411,7 +428,7 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                 } else if (dist == DIST_BERNOULLI) {
                     // softplus(z) - a z ; sigmoid(z) - a ; branch-free (missing entries select 0)
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) {
+                    for (int e = 0; e < 16; ++e) {
                         const bool ob = fabsf(a[e]) < INFINITY;
                         const float a0 = ob ? a[e] : 0.f;
                         float z4 = fmaf(__uint_as_float(z[e]), sigma, muj);
@@ -426,7 +443,7 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                     }
                 } else if (dist == DIST_POISSON) {
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) {
+                    for (int e = 0; e < 16; ++e) {
                         const bool ob = fabsf(a[e]) < INFINITY;
                         const float a0 = ob ? a[e] : 0.f;
                         float z4 = fmaf(__uint_as_float(z[e]), sigma, muj);
@@ -438,7 +455,7 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                     }
                 } else {
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) {
+                    for (int e = 0; e < 16; ++e) {
                         float z4 = fmaf(__uint_as_float(z[e]), sigma, muj);
                         float2 lg = noise_eval_slow(dist, z4, a[e], th4, dp.ordinal_eps, dp.hinge_margin);
                         loss_acc = fmaf(2.f, lg.x, loss_acc);        // keep the common 1/2 factor at flush
@@ -447,17 +464,15 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                     }
                 }
                 // G0 back to TMEM in place of Z (A operand of MMA3)
-                TMEM_ST32(zt, z);
-                // every lane of the warp has pulled its A row of this slice into registers
-                __syncwarp();
-                // G0' : rows i = 32*half .. +31 of K-atom box `quarter` (8 KB per box), column = lane
-                uint8_t* gbox = ag_ptr + quarter * 8192 + (32 * half) * 128;
+                TMEM_ST16(zt, z);
+                // both warps that share this A box have pulled their data into registers
+                asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+                // G0' : rows i = 16*c16 .. +15 of K-atom box `quarter` (8 KB per box), column = lane
+                uint8_t* gbox = ag_ptr + quarter * 8192 + (16 * c16) * 128;
 #pragma unroll
-                for (int e = 0; e < 32; ++e) {
+                for (int e = 0; e < 16; ++e) {
                     *reinterpret_cast<uint32_t*>(gbox + e * 128 + (((lane >> 2) ^ (e & 7)) << 4) + ((lane & 3) << 2)) = z[e];
                 }
-                loss_d += (double)(loss_acc * wj);
-                loss_acc = 0.f;
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 tc_fence_before();
                 fence_async_smem();
@@ -465,20 +480,21 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                 if (it > it0) dx_out(g - 1, (it - 1) * BI);
             }
             dx_out(g - 1, (it1 - 1) * BI);
+            loss_d += (double)(loss_acc * wj);
 
             // ---- item epilogue: dY tile out of TMEM, column sums --------------------------------------
             mbar_wait(bar(B_DY_FULL), q & 1);
             tc_fence_after();
             {
-                uint32_t r[32];
-                TMEM_LD32(tm + lane_addr + TM_DY + 32 * half, r);
+                uint32_t r[16];
+                TMEM_LD16(tm + lane_addr + TM_DY + 16 * c16, r);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 tc_fence_before();
                 mbar_arrive(bar(B_DY_EMPTY));
                 if (jok) {
-                    float* dst = dp.dY + (size_t)j * KK + 32 * half;
+                    float* dst = dp.dY + (size_t)j * KK + 16 * c16;
 #pragma unroll
-                    for (int v = 0; v < 8; ++v) {
+                    for (int v = 0; v < 4; ++v) {
                         float4 val = make_float4(__uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]),
                                                  __uint_as_float(r[4 * v + 2]), __uint_as_float(r[4 * v + 3]));
                         if (p.chunks == 1) reinterpret_cast<float4*>(dst)[v] = val;
