@@ -81,7 +81,7 @@ struct pmf_model_s {
     float *X = nullptr, *dX = nullptr, *accX = nullptr;
     float *Y = nullptr, *accY = nullptr;
     float *Xlo = nullptr, *XT = nullptr, *YT = nullptr;   // operand scratch of the tcgen05 path (lazy)
-    bool auto_tc = false;                    // PMF_KERNEL_AUTO picks the tcgen05 path when it applies
+    bool auto_tc = true;                     // PMF_KERNEL_AUTO picks the tcgen05 path when it applies
     // per-column noise description
     float* weight = nullptr;
     int32_t* colinfo = nullptr;

@@ -238,3 +238,94 @@ def test_abi_error_paths():
     with pytest.raises(_lib.PmfError):
         eng._ck(lib.pmf_get_batch_values(eng.h, 3, None, None))
     eng.close()
+
+
+# ---- tcgen05 path (K = 64) -------------------------------------------------------------------------
+# Z is contracted in 3xTF32 (FP32-equivalent: loss and column gradients match to ~1e-6); dX / dY use a
+# single TF32 pass with round-to-nearest operands, whose rounding noise averages out with the number
+# of terms: ~2e-4 at a few hundred samples, ~1e-4 at 1000, 3-4e-5 at the 10k x 30k benchmark shape.
+# PMF_KERNEL_AUTO therefore only selects this path for large problems (M >= 1024, M*N >= 4e6).
+
+def _tc_views(n):
+    return {"mutation": ("bernoulli", n // 6), "methylation": ("normal", n // 3), "mrnaseq": ("normal", n // 3),
+            "counts": ("poisson", n - n // 6 - 2 * (n // 3))}
+
+
+def test_tc_kernel_against_oracle_midsize():
+    model, om, D = make_pair(1500, _tc_views(1100), K=64, seed=31, missing=0.3, lambda_X_l2=1.0)
+    eng = P.Engine(model)
+    try:
+        eng.set_loss_grad_kernel(_lib.KERNEL_TC, 0)
+        got = eng.loss_grad(include_reg=True)
+        eng.set_loss_grad_kernel(_lib.KERNEL_FFMA, 0)
+        ffma = eng.loss_grad(include_reg=True)
+    finally:
+        eng.close()
+    ref = O.total_loss_grads(om, D)
+    assert abs(got["loss"] - ref["loss"]) <= 1e-5 * abs(ref["loss"])
+    assert relerr(got["dmu"], ref["dmu"]) < 1e-4 and relerr(got["dlogsigma"], ref["dlogsigma"]) < 1e-4
+    assert relerr(got["dY"], ref["dY"]) < 2e-4 and relerr(got["dX"], ref["dX"]) < 2e-4
+    for k in ("dX", "dY", "dmu", "dlogsigma"):
+        assert relerr(ffma[k], ref[k]) < 1e-5
+
+
+def test_tc_ragged_edges_and_all_missing():
+    """M, N not multiples of the 128 x 64 tile, an all-missing column and an all-missing sample."""
+    model, om, D = make_pair(1091, _tc_views(333), K=64, seed=32, missing=0.2, lambda_X_l2=1.0)
+    D[:, 7] = np.nan
+    D[500, :] = np.nan
+    model.data[:, 7] = np.nan
+    model.data[500, :] = np.nan
+    eng = P.Engine(model)
+    try:
+        eng.set_loss_grad_kernel(_lib.KERNEL_TC, 0)
+        got = eng.loss_grad(include_reg=False)
+    finally:
+        eng.close()
+    ref = O.data_loss_grads(om, D)
+    assert abs(got["loss"] - ref["loss"]) <= 1e-5 * abs(ref["loss"])
+    assert relerr(got["dY"], ref["dY"]) < 3e-4 and relerr(got["dX"], ref["dX"]) < 3e-4
+    assert np.all(got["dY"][:, 7] == 0) and np.all(got["dX"][:, 500] == 0) and got["dmu"][7] == 0
+
+
+def test_tc_fit_curve_auto_kernel():
+    model, om, D = make_pair(1300, _tc_views(3200), K=64, seed=33, missing=0.3, lambda_X_l2=1.0)
+    href = O.mf_fit(om, D, O.AdaGrad(0.1), max_epochs=8, update_X=True, update_Y=True, update_col_layers=True,
+                    rel_tol=0, abs_tol=0)
+    h = P.mf_fit(model, lr=0.1, max_epochs=8, update_X=True, update_Y=True, update_col_layers=True, rel_tol=0,
+                 abs_tol=0, verbosity=0)          # AUTO -> tcgen05 path (M >= 1024, M*N >= 4e6, K = 64)
+    assert h["epochs"] == href["epochs"] and h["term_code"] == href["term_code"]
+    assert np.max(np.abs(np.array(h["loss"]) / np.array(href["loss"]) - 1)) < 1e-4
+    assert relerr(model.matfac.Y, om.Y) < 1e-3 and relerr(model.matfac.X, om.X) < 1e-3
+
+
+def test_tc_benchmark_shape_properties():
+    """BASELINE configs[1] at full size (10 000 x 30 000, K = 64): the oracle is too slow here, so the
+    exact-FP32 FFMA kernel is the reference, plus size-independent properties: row shards add up,
+    repeated evaluation is reproducible to rounding."""
+    from pathmatfac_b200.simulate import C2_BLOCKS, simulate_problem
+    model = simulate_problem(10000, blocks=C2_BLOCKS, K=64, seed=5, missing=0.3, model_kwargs=dict(lambda_X_l2=1.0))
+    eng = P.Engine(model)
+    try:
+        eng.set_loss_grad_kernel(_lib.KERNEL_FFMA, 0)
+        ref = eng.loss_grad(include_reg=False)
+        eng.set_loss_grad_kernel(_lib.KERNEL_TC, 0)
+        got = eng.loss_grad(include_reg=False)
+        again = eng.loss_grad(include_reg=False)
+    finally:
+        eng.close()
+    assert abs(got["loss"] - ref["loss"]) <= 1e-5 * abs(ref["loss"])
+    for k in ("dmu", "dlogsigma"):
+        assert relerr(got[k], ref[k]) < 2e-5
+    assert relerr(got["dY"], ref["dY"]) < 1e-4 and relerr(got["dX"], ref["dX"]) < 1e-4
+    assert relerr(again["dY"], got["dY"]) < 1e-6 and abs(again["loss"] - got["loss"]) <= 1e-9 * abs(got["loss"])
+    # sample shards (the multi-GPU decomposition): shared gradients add up
+    parts = []
+    for rows in (range(0, 4000), range(4000, 10000)):
+        e = P.Engine(model, rows=rows)
+        e.set_loss_grad_kernel(_lib.KERNEL_TC, 0)
+        parts.append(e.loss_grad(include_reg=False))
+        e.close()
+    assert abs(parts[0]["loss"] + parts[1]["loss"] - got["loss"]) <= 1e-6 * abs(got["loss"])
+    assert relerr(parts[0]["dY"] + parts[1]["dY"], got["dY"]) < 2e-5
+    assert relerr(np.concatenate([parts[0]["dX"], parts[1]["dX"]], axis=1), got["dX"]) < 2e-5
