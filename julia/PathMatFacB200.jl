@@ -1,0 +1,200 @@
+# PathMatFacB200.jl -- Julia shim that drops libpmf (include/pmf.h) in for the fit-loop hot path
+# of PathMatFac.jl.  It overrides ONLY `PathMatFac.mf_fit!` (src/fit.jl:9-38); the staging code
+# (`fit!`, `mf_fit_adapt_lr!`, `basic_fit!`, ... src/fit.jl) keeps running in Julia unchanged.
+#
+# WRITE-ONLY in this repository: the build image has no Julia runtime, so this file is exercised
+# only indirectly -- the Python mirror (pathmatfac.jl_b200/fit.py) drives the very same C ABI
+# with the very same marshalling rules (INTEGRATION.md, SURVEY.md Appendix C).
+module PathMatFacB200
+
+using SparseArrays
+import PathMatFac
+const PM = PathMatFac
+
+const LIBPMF = get(ENV, "LIBPMF", joinpath(@__DIR__, "..", "pathmatfac.jl_b200", "libpmf.so"))
+const TERM_CODES = ("max_epochs", "abs_tol", "rel_tol", "loss_increase", "nonfinite")
+const DIST_CODE = Dict("NormalNoise" => 0, "BernoulliNoise" => 1, "PoissonNoise" => 2, "OrdinalNoise" => 3,
+                       "SquaredHingeNoise" => 4, "OrdinalSqHingeNoise" => 5)
+
+struct PmfDims
+    M::Int32; N::Int32; K::Int32; device::Int32
+end
+
+mutable struct PmfFitOpts            # mirrors pmf_fit_opts
+    max_epochs::Int32; epoch::Int32; lr::Float32; adagrad_eps::Float32
+    rel_tol::Float64; abs_tol::Float64
+    update_X::Int32; update_Y::Int32; update_col_layers::Int32
+    kernel::Int32; precision::Int32; check_every::Int32; no_terminate::Int32
+end
+
+mutable struct PmfHistory            # mirrors pmf_history
+    term_code::Int32; epochs::Int32; n_recorded::Int32; capacity::Int32
+    loss_total::Ptr{Float64}; loss_data::Ptr{Float64}; loss_x_reg::Ptr{Float64}
+    loss_y_reg::Ptr{Float64}; loss_layer_reg::Ptr{Float64}
+    device_ms::Float32; kernel_launches::Int64
+end
+
+const Handle = Ptr{Cvoid}
+
+function check(h::Handle, rc::Integer)
+    rc == 0 && return
+    msg = ccall((:pmf_last_error, LIBPMF), Cstring, (Handle,), h)
+    error("libpmf error $rc: ", msg == C_NULL ? "?" : unsafe_string(msg))
+end
+
+unwrap(l) = isa(l, PM.FrozenLayer) ? l.layer : l
+unwrap_reg(r) = isa(r, PM.FrozenRegularizer) ? r.reg : r
+f32(a) = convert(Array{Float32}, a)
+i32(a) = convert(Vector{Int32}, a)
+
+"""gpu(model) equivalent (fit_matfac.jl:325-340): create the handle and upload the data once."""
+function to_device(model::PM.PathMatFacModel; device::Integer=0)
+    M, N = size(model.data); K = size(model.matfac.X, 1)
+    h = Ref{Handle}(C_NULL)
+    check(C_NULL, ccall((:pmf_create, LIBPMF), Cint, (Ref{PmfDims}, Ref{Handle}), PmfDims(M, N, K, device), h))
+    A = f32(model.data)                                    # M x N column-major, NaN = missing
+    check(h[], ccall((:pmf_set_data, LIBPMF), Cint, (Handle, Ptr{Float32}), h[], A))
+    return h[]
+end
+
+release(h::Handle) = ccall((:pmf_destroy, LIBPMF), Cint, (Handle,), h)
+
+function push_params!(h::Handle, model)
+    mf = model.matfac
+    check(h, ccall((:pmf_set_factors, LIBPMF), Cint, (Handle, Ptr{Float32}, Ptr{Float32}), h, f32(mf.X), f32(mf.Y)))
+    layers = mf.col_transform.layers
+    check(h, ccall((:pmf_set_col_params, LIBPMF), Cint, (Handle, Ptr{Float32}, Ptr{Float32}), h,
+                   f32(unwrap(layers[1]).logsigma), f32(unwrap(layers[3]).mu)))
+    if isa(unwrap(layers[2]), PM.BatchScale)
+        ld = unwrap(layers[2]).logdelta; th = unwrap(layers[4]).theta
+        nv = length(ld.col_ranges); M = size(model.data, 1)
+        cs = i32([r.start - 1 for r in ld.col_ranges]); ce = i32([r.stop for r in ld.col_ranges])
+        nb = i32([size(v, 1) for v in ld.values])
+        bos = Matrix{Int32}(undef, M, nv)                  # column v = batch ordinal (0-based) of every sample
+        for v in 1:nv
+            I, J, _ = findnz(sparse(ld.row_batches[v]))
+            bos[I, v] .= Int32.(J .- 1)
+        end
+        check(h, ccall((:pmf_set_batch_layout, LIBPMF), Cint, (Handle, Int32, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}),
+                       h, nv, cs, ce, nb, bos))
+        for v in 1:nv
+            check(h, ccall((:pmf_set_batch_values, LIBPMF), Cint, (Handle, Int32, Ptr{Float32}, Ptr{Float32}),
+                           h, v - 1, f32(ld.values[v]), f32(th.values[v])))
+        end
+    else
+        check(h, ccall((:pmf_set_batch_layout, LIBPMF), Cint, (Handle, Int32, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}),
+                       h, 0, C_NULL, C_NULL, C_NULL, C_NULL))
+    end
+end
+
+function pull_params!(h::Handle, model)
+    mf = model.matfac
+    X = Matrix{Float32}(undef, size(mf.X)...); Y = Matrix{Float32}(undef, size(mf.Y)...)
+    check(h, ccall((:pmf_get_factors, LIBPMF), Cint, (Handle, Ptr{Float32}, Ptr{Float32}), h, X, Y))
+    mf.X .= X; mf.Y .= Y
+    layers = mf.col_transform.layers
+    ls = Vector{Float32}(undef, size(mf.Y, 2)); mu = similar(ls)
+    check(h, ccall((:pmf_get_col_params, LIBPMF), Cint, (Handle, Ptr{Float32}, Ptr{Float32}), h, ls, mu))
+    unwrap(layers[1]).logsigma .= ls; unwrap(layers[3]).mu .= mu
+    if isa(unwrap(layers[2]), PM.BatchScale)
+        ld = unwrap(layers[2]).logdelta; th = unwrap(layers[4]).theta
+        for v in 1:length(ld.values)
+            a = Matrix{Float32}(undef, size(ld.values[v])...); b = similar(a)
+            check(h, ccall((:pmf_get_batch_values, LIBPMF), Cint, (Handle, Int32, Ptr{Float32}, Ptr{Float32}), h, v - 1, a, b))
+            ld.values[v] .= a; th.values[v] .= b
+        end
+    end
+end
+
+# one regulariser object -> ABI calls; `which` 0 = X_reg, 1 = Y_reg; p = mixture weight
+function install_reg!(h::Handle, which::Integer, r, p::Real)
+    p == 0 && return
+    if isa(r, PM.L2Regularizer)
+        check(h, ccall((:pmf_set_reg_l2, LIBPMF), Cint, (Handle, Int32, Ptr{Float32}, Float32), h, which, f32(r.weights), p))
+    elseif isa(r, PM.GroupRegularizer)
+        st = i32([g.start - 1 for g in r.group_idx]); en = i32([g.stop for g in r.group_idx])
+        w = f32(hcat(r.group_weights...))                  # K x n_groups column-major == n_groups x K row-major
+        check(h, ccall((:pmf_set_reg_group, LIBPMF), Cint, (Handle, Int32, Int32, Ptr{Int32}, Ptr{Int32}, Ptr{Float32}, Float32),
+                       h, which, length(st), st, en, w, p))
+    elseif isa(r, PM.SelectiveL1Reg)
+        check(h, ccall((:pmf_set_reg_sel_l1, LIBPMF), Cint, (Handle, Int32, Ptr{UInt8}, Ptr{Float32}, Float32),
+                       h, which, convert(Matrix{UInt8}, r.l1_idx), f32(r.weight), p))
+    elseif isa(r, PM.ARDRegularizer)
+        st = i32([g.start - 1 for g in r.col_ranges]); en = i32([g.stop for g in r.col_ranges])
+        check(h, ccall((:pmf_set_reg_ard, LIBPMF), Cint, (Handle, Int32, Int32, Ptr{Int32}, Ptr{Int32}, Ptr{Float32}, Ptr{Float32}),
+                       h, which, length(st), st, en, f32(collect(r.alpha)), f32(collect(r.beta))))
+    elseif isa(r, PM.FeatureSetARDReg)
+        check(h, ccall((:pmf_set_reg_fsard, LIBPMF), Cint, (Handle, Int32, Ptr{Float32}, Ptr{Float32}), h, which, f32(r.alpha), f32(r.beta)))
+    elseif isa(r, PM.NetworkRegularizer)
+        csr(m) = (mt = SparseMatrixCSC(transpose(m)); (i32(mt.colptr .- 1), i32(mt.rowval .- 1), f32(mt.nzval)))
+        cat3(ms) = (t = [csr(m) for m in ms]; (vcat(first.(t)...), vcat(getindex.(t, 2)...), vcat(last.(t)...)))
+        aa = cat3(r.AA); ab = cat3(r.AB); bb = cat3(r.BB)
+        nv = i32([size(b, 1) for b in r.BB]); xv = f32(vcat(r.x_virtual...))
+        check(h, ccall((:pmf_set_reg_network, LIBPMF), Cint,
+                       (Handle, Int32, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Float32}, Ptr{Int32}, Ptr{Int32}, Ptr{Float32},
+                        Ptr{Int32}, Ptr{Int32}, Ptr{Float32}, Ptr{Float32}, Float32, Float32, Float32, Int32),
+                       h, which, nv, aa[1], aa[2], aa[3], ab[1], ab[2], ab[3], bb[1], bb[2], bb[3], xv, p, 0f0, 0f0, 0))
+    elseif isa(r, Function)
+        # `x->0` closures installed by the stages (src/fit.jl:415,769): nothing to install
+    else
+        error("PathMatFacB200: unsupported regulariser ", typeof(r))
+    end
+end
+
+function push_regs!(h::Handle, model)
+    mf = model.matfac
+    for (which, reg) in ((0, mf.X_reg), (1, mf.Y_reg))
+        check(h, ccall((:pmf_clear_reg, LIBPMF), Cint, (Handle, Int32), h, which))
+        if isa(reg, PM.CompositeRegularizer)
+            for (r, p) in zip(reg.regularizers, reg.mixture_p); install_reg!(h, which, r, p); end
+        else
+            install_reg!(h, which, reg, 1.0)
+        end
+    end
+    frozen_layers = UInt32(0); frozen_regs = UInt32(0)
+    N = size(mf.Y, 2)
+    for (s, l) in enumerate(mf.col_transform.layers); isa(l, PM.FrozenLayer) && (frozen_layers |= UInt32(1) << (s - 1)); end
+    for (s, r0) in enumerate(mf.col_transform_reg.regs)
+        isa(r0, PM.FrozenRegularizer) && (frozen_regs |= UInt32(1) << (s - 1))
+        r = unwrap_reg(r0)
+        if isa(r, PM.ColParamReg)
+            w = zeros(Float32, N); c = zeros(Float32, N)
+            for (rng, wi, ci) in zip(r.col_ranges, r.weights, r.centers); w[rng] .= wi; c[rng] .= ci; end
+            check(h, ccall((:pmf_set_layer_reg_col, LIBPMF), Cint, (Handle, Int32, Ptr{Float32}, Ptr{Float32}), h, s, w, c))
+        elseif isa(r, PM.BatchArrayReg)
+            check(h, ccall((:pmf_set_layer_reg_batch, LIBPMF), Cint, (Handle, Int32, Ptr{Float32}, Ptr{Float32}),
+                           h, s, f32(vcat(r.weights...)), f32(vcat(r.centers...))))
+        end
+    end
+    check(h, ccall((:pmf_set_frozen, LIBPMF), Cint, (Handle, UInt32, UInt32), h, frozen_layers, frozen_regs))
+    nm = mf.noise_model
+    cs = i32([r.start - 1 for r in nm.col_ranges]); ce = i32([r.stop for r in nm.col_ranges])
+    dc = i32([DIST_CODE[string(nameof(typeof(n)))] for n in nm.noises])
+    th = zeros(Float32, 4, length(nm.noises))
+    for (i, n) in enumerate(nm.noises); hasproperty(n, :ext_thresholds) && (th[:, i] .= n.ext_thresholds); end
+    w = f32(vcat([n.weight for n in nm.noises]...))
+    check(h, ccall((:pmf_set_noise, LIBPMF), Cint, (Handle, Int32, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Float32}, Ptr{Float32}),
+                   h, length(cs), cs, ce, dc, th, w))
+end
+
+const OPT_OWNER = IdDict{Any,Handle}()   # a fresh Flux AdaGrad object => fresh accumulators (src/fit.jl:55)
+
+"""Replacement for `PathMatFac.mf_fit!` (src/fit.jl:9-38) on a device-resident model."""
+function mf_fit!(model::PM.PathMatFacModel, h::Handle; opt, max_epochs=1000, epoch=1, update_X=false, update_Y=false,
+                 update_col_layers=false, rel_tol=1e-5, abs_tol=1e-5, kwargs...)
+    push_params!(h, model); push_regs!(h, model)
+    if get(OPT_OWNER, opt, C_NULL) != h
+        check(h, ccall((:pmf_reset_opt_state, LIBPMF), Cint, (Handle, Float32), h, opt.epsilon)); OPT_OWNER[opt] = h
+    end
+    cap = max(1, max_epochs - epoch + 1)
+    losses = [zeros(Float64, cap) for _ in 1:5]
+    hist = PmfHistory(0, 0, 0, cap, pointer.(losses)..., 0f0, 0)
+    opts = PmfFitOpts(max_epochs, epoch, opt.eta, opt.epsilon, rel_tol, abs_tol, update_X, update_Y, update_col_layers, 0, 0, 8, 0)
+    GC.@preserve losses check(h, ccall((:pmf_fit, LIBPMF), Cint, (Handle, Ref{PmfFitOpts}, Ref{PmfHistory}), h, opts, hist))
+    pull_params!(h, model)
+    n = hist.n_recorded
+    return Dict("term_code" => TERM_CODES[hist.term_code + 1], "epochs" => Int(hist.epochs), "loss" => losses[1][1:n],
+                "data_loss" => losses[2][1:n], "X_reg" => losses[3][1:n], "Y_reg" => losses[4][1:n], "layer_reg" => losses[5][1:n])
+end
+
+end # module
