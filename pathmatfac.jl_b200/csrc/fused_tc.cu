@@ -3,29 +3,31 @@
 // One persistent CTA per SM walks work items (feature tile of 128 x chunk of samples).  Per
 // 128-feature x 64-sample tile of A (32 KB, streamed once through TMA-staged shared memory):
 //
-//   MMA1  Z'[j,i]  = sum_k Y[j,k] X[i,k]     A = Y tile in TMEM (hi / lo), B = X tile in smem
+//   MMA1  Z[j,i]   = sum_k Y[j,k] X[i,k]     A = Y tile in TMEM (hi / lo), B = X tile in smem (K-major)
 //                                            3xTF32: Yh*Xh + Yl*Xh + Yh*Xl, FP32 accumulate in TMEM
-//   epilogue (8 warps, TMEM lane = feature j, so every column parameter is a per-thread
+//   epilogue (16 warps, TMEM lane = feature j, so every column parameter is a per-thread
 //            register and every column-gradient sum is a private accumulator):
 //            ColScale/ColShift, noise loss, dL/dz with the NaN mask (src/layers.jl:9-90,
-//            Appendix B of SURVEY.md), G0 written back to TMEM in place of Z and, transposed,
-//            into the shared-memory buffer the A tile came from
-//   MMA2  dX[i,k]  = sum_j G0[j,i] Y[j,k]    A = G0' in smem, B = Y' tile (k-major copy) in smem
-//   MMA3  dY[j,k] += sum_i G0[j,i] X[i,k]    A = G0 in TMEM, B = X' tile (k-major copy) in smem
+//            Appendix B of SURVEY.md).  G0 is written back to TMEM in place of Z and, with 128-bit
+//            stores, into shared memory IN PLACE of the A values the same thread just read.
+//   MMA2  dX[i,k]  = sum_j G0[j,i] Y[j,k]    A = G0 in smem read MN-major (M = 64 samples), B = Yh tile
+//                                            in smem read MN-major -- no transposed copies exist
+//   MMA3  dY[j,k] += sum_i G0[j,i] X[i,k]    A = G0 in TMEM, B = the same Xh tile read MN-major
 //
 // Z and dL/dZ never exist in HBM.  dY stays in TMEM across the sample loop of an item; the
 // per-tile dX block is read back from TMEM and reduced into global memory with 128-bit REDs.
-// Gradient contractions use single-pass TF32 with round-to-nearest operands; the Z contraction
-// is 3xTF32 unless precision mode 2 asks for plain TF32.
+// Operand split: h = rna_tf32(v), l = v - h (exact); gradient contractions use h only
+// (single-pass TF32, round-to-nearest operands); the Z contraction is 3xTF32 unless precision
+// mode 2 asks for plain TF32.
 //
-// Everything that is streamed per tile is double-buffered (TMA runs up to two tiles ahead):
-//   XS  2 x 32 KB  X tile raw FP32 (the tensor core truncates it to its TF32 "hi") + X_lo = X - trunc(X)
-//   XTS 2 x 16 KB  X' tile;  YTS 32 KB  Y' tile (resident per item)   (RN-rounded TF32 operands)
-//   AG  2 x 32 KB  A tile as 8 TMA boxes of 32x32; box (jq,iq) sits at (jq*2+iq)*4 KB so that the
-//                  slice a warp reads as A is exactly the slice it later overwrites with G0'.
-//   MMA2 runs with M = 128 over the 64 valid rows of G0' (the upper 64 accumulator lanes are junk
-//   and never read), hence the 8 KB pad behind the last A/G buffer.
+// Shared memory (every TMA box is 32 floats = one 128-byte swizzle row wide):
+//   X   3 stages x (Xh 16 KB | Xl 16 KB)   tile [64 samples][64 k] as 2 boxes (32 k x 64 rows)
+//   YS  32 KB   Yh tile [128 features][64 k] as 2 boxes (32 k x 128 rows), written by the epilogue warps
+//   AG  3 stages x 32 KB   A tile as 2 boxes (32 samples x 128 feature rows); becomes G0 in place
+// The same box is a K-major operand when the contraction runs along its 128-byte rows (MMA1) and an
+// MN-major operand when it runs across rows (MMA2, MMA3): 8-row groups are 1024 B apart either way.
 // TMEM (512 columns): Yh 0 | Yl 64 | Z0 128 | Z1 192 | dY 256 | dX0 320 | dX1 384.
+// dX accumulators are M = 64 tiles: sample row r lives in lane (r % 16) + 32 * (r / 16).
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -40,15 +42,14 @@ namespace {
 constexpr int BJ = 128, BI = 64, KK = 64;
 constexpr int NEPI = 16;                  // epilogue warps: (TMEM lane quarter, 16-column chunk)
 constexpr int NTHREADS = 64 + 32 * NEPI;  // warp 0 TMA, warp 1 MMA, warps 2.. epilogue
-constexpr uint32_t XS_BYTES = 32768, XTS_BYTES = 16384, YTS_BYTES = 32768, AG_BYTES = 32768, AG_PAD = 8192;
-constexpr uint32_t SMEM_DATA = 2 * XS_BYTES + 2 * XTS_BYTES + YTS_BYTES + 2 * AG_BYTES + AG_PAD;
+constexpr int SX = 2, SA = 3;             // pipeline depth of the X streams and of the A/G stream
+constexpr uint32_t XH_BYTES = 16384, XK_BYTES = 32768 /* Xh | Xl */, XM_BYTES = 16384, YS_BYTES = 32768, AG_BYTES = 32768;
+constexpr uint32_t SMEM_DATA = SX * XK_BYTES + SX * XM_BYTES + YS_BYTES + SA * AG_BYTES;
 constexpr uint32_t SMEM_TOTAL = SMEM_DATA + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr uint32_t TM_YH = 0, TM_YL = 64, TM_Z0 = 128, TM_DY = 256, TM_DX0 = 320;   // Z1 = Z0+64, dX1 = dX0+64
 
-// barriers that exist twice are indexed  B_xxx + (tile & 1)
-enum Bar { B_FULL_X = 0, B_EMPTY_X = 2, B_FULL_XT = 4, B_EMPTY_XT = 6, B_FULL_A = 8, B_EMPTY_AG = 10, B_Z_FULL = 12,
-           B_G_READY = 14, B_DX_FULL = 16, B_DX_EMPTY = 18, B_Y_READY = 20, B_YT_FULL, B_YT_EMPTY, B_DY_FULL,
-           B_DY_EMPTY, B_COUNT };
+enum Bar { B_FULL_XK = 0, B_EMPTY_XK = 2, B_FULL_XM = 4, B_EMPTY_XM = 6, B_FULL_A = 8, B_EMPTY_AG = 11, B_Z_FULL = 14,
+           B_G_READY = 16, B_DX_FULL = 18, B_DX_EMPTY = 20, B_Y_READY = 22, B_DY_FULL, B_DY_EMPTY, B_COUNT };
 
 // ---- PTX wrappers --------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -106,13 +107,24 @@ __device__ __forceinline__ void tc_commit_elect(uint32_t bar) {
         "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar) : "memory");
 }
 
-// K-major operand, 128-byte swizzle: rows are 128 B, 8-row groups are 1024 B apart.
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+// Shared-memory operand descriptors, 128-byte swizzle (rows of 32 floats, 8-row groups 1024 B apart).
+// K-major: the contraction runs along the 128-byte rows; SBO = 1024 separates 8-row groups of M / N.
+__device__ __forceinline__ uint64_t umma_desc_k(uint32_t saddr) {
     return (uint64_t)((saddr >> 4) & 0x3fffu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
-// instruction descriptor: TF32 x TF32 -> F32, both operands K-major
-__host__ __device__ constexpr uint32_t umma_idesc(int M, int N) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// MN-major FP32/TF32 operand: M / N runs along the 128-byte rows, the contraction across rows.  The only
+// layout the tensor core accepts here is "128B swizzle with 32-byte atoms" (layout type 1): 32-byte
+// chunk index ^= row & 3, i.e. a 4-row x 128 B atom (TMA: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B).
+// LBO = distance between consecutive 32-element chunks of M / N (one TMA box), SBO = 512 between the
+// two 4-row groups of one k-step (8 rows).
+__device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr, uint32_t lbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)(lbo_bytes >> 4) << 16) | (32ull << 32) | (1ull << 46) |
+           (1ull << 61);
+}
+// instruction descriptor: TF32 x TF32 -> F32; bit 15 / 16 = A / B operand is MN-major
+__host__ __device__ constexpr uint32_t umma_idesc(int M, int N, bool a_mn, bool b_mn) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | (a_mn ? (1u << 15) : 0u) | (b_mn ? (1u << 16) : 0u) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 #define TMEM_LD32(taddr, r)                                                                                       \
@@ -178,17 +190,23 @@ __device__ __forceinline__ void item_range(const TcParams& p, int item, int& jt,
     it1 = (int)((long long)p.n_it * (c + 1) / p.chunks);
 }
 
+// stage / parity bookkeeping of a ring of `n` buffers (avoids a modulo per tile)
+struct Ring {
+    uint32_t s = 0, ph = 0;
+    __device__ __forceinline__ void next(uint32_t n) { if (++s == n) { s = 0; ph ^= 1u; } }
+};
+
 __global__ void __launch_bounds__(NTHREADS, 1)
-data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmXlo,
-                    const __grid_constant__ CUtensorMap tmXT, const __grid_constant__ CUtensorMap tmYT,
-                    const __grid_constant__ CUtensorMap tmA, const TcParams p) {
+data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUtensorMap tmXl,
+                    const __grid_constant__ CUtensorMap tmXm, const __grid_constant__ CUtensorMap tmA, const TcParams p) {
     const DataPassParams& dp = p.dp;
     if (dp.stop_flag != nullptr && *dp.stop_flag != 0) return;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
-    const uint32_t XS = base, XTS = XS + 2 * XS_BYTES, YTS = XTS + 2 * XTS_BYTES, AG = YTS + YTS_BYTES;
+    const uint32_t XK = base, XM = XK + SX * XK_BYTES, YS = XM + SX * XM_BYTES, AG = YS + YS_BYTES;
     const uint32_t BARS = base + SMEM_DATA;
+    uint8_t* ys_ptr = gbase + (YS - base);
     uint8_t* ag_ptr0 = gbase + (AG - base);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + SMEM_DATA + 8 * B_COUNT);
     __shared__ double red_smem[NTHREADS / 32];
@@ -202,8 +220,9 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     if (threadIdx.x == 0) {
         for (int b = 0; b < B_COUNT; ++b) {
             uint32_t cnt = 1u;
-            if (b == B_G_READY || b == B_G_READY + 1 || b == B_Y_READY || b == B_DY_EMPTY) cnt = 32u * NEPI;
-            if (b == B_DX_EMPTY || b == B_DX_EMPTY + 1) cnt = 256u;      // the 8 warps that read dX out
+            if (b == B_G_READY || b == B_G_READY + 1 || b == B_Y_READY || b == B_DY_EMPTY || b == B_DX_EMPTY ||
+                b == B_DX_EMPTY + 1)
+                cnt = 32u * NEPI;
             mbar_init(bar(b), cnt);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -222,77 +241,72 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         // Three independent lanes, one per stream, so that a buffer that is released late (the A/G
         // tile waits for MMA2) never holds back the loads of the other streams.
         if (lane < 3) {
-            uint32_t g = 0, q = 0;
+            Ring r;
+            const uint32_t depth = lane == 1 ? SA : SX;
             for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
                 int jt, it0, it1;
                 item_range(p, item, jt, it0, it1);
                 const int j0 = jt * BJ;
-                if (lane == 2) {
-                    mbar_wait(bar(B_YT_EMPTY), (q & 1) ^ 1);
-                    mbar_expect_tx(bar(B_YT_FULL), YTS_BYTES);
-                    for (int b = 0; b < 4; ++b) tma_load_2d(YTS + b * 8192, &tmYT, bar(B_YT_FULL), j0 + 32 * b, 0);
-                }
-                for (int it = it0; it < it1; ++it, ++g) {
+                for (int it = it0; it < it1; ++it, r.next(depth)) {
                     const int i0 = it * BI;
-                    const uint32_t b = g & 1, ph = ((g >> 1) & 1) ^ 1;      // every buffer was last used two tiles ago
                     if (lane == 0) {
-                        mbar_wait(bar(B_EMPTY_X + b), ph);
-                        mbar_expect_tx(bar(B_FULL_X + b), XS_BYTES);
+                        mbar_wait(bar(B_EMPTY_XK + r.s), r.ph ^ 1);
+                        mbar_expect_tx(bar(B_FULL_XK + r.s), XK_BYTES);
+                        const uint32_t dst = XK + r.s * XK_BYTES;
                         for (int kb = 0; kb < 2; ++kb) {
-                            tma_load_2d(XS + b * XS_BYTES + kb * 8192, &tmX, bar(B_FULL_X + b), 32 * kb, i0);
-                            tma_load_2d(XS + b * XS_BYTES + 16384 + kb * 8192, &tmXlo, bar(B_FULL_X + b), 32 * kb, i0);
+                            tma_load_2d(dst + kb * 8192, &tmXh, bar(B_FULL_XK + r.s), 32 * kb, i0);
+                            tma_load_2d(dst + XH_BYTES + kb * 8192, &tmXl, bar(B_FULL_XK + r.s), 32 * kb, i0);
                         }
                     } else if (lane == 1) {
-                        mbar_wait(bar(B_EMPTY_AG + b), ph);
-                        mbar_expect_tx(bar(B_FULL_A + b), AG_BYTES);
-                        for (int jq = 0; jq < 4; ++jq)
-                            for (int iq = 0; iq < 2; ++iq)
-                                tma_load_2d(AG + b * AG_BYTES + (jq * 2 + iq) * 4096, &tmA, bar(B_FULL_A + b), i0 + 32 * iq,
-                                            j0 + 32 * jq);
+                        mbar_wait(bar(B_EMPTY_AG + r.s), r.ph ^ 1);
+                        mbar_expect_tx(bar(B_FULL_A + r.s), AG_BYTES);
+                        for (int iq = 0; iq < 2; ++iq)
+                            tma_load_2d(AG + r.s * AG_BYTES + iq * 16384, &tmA, bar(B_FULL_A + r.s), i0 + 32 * iq, j0);
                     } else {
-                        mbar_wait(bar(B_EMPTY_XT + b), ph);
-                        mbar_expect_tx(bar(B_FULL_XT + b), XTS_BYTES);
-                        for (int ib = 0; ib < 2; ++ib)
-                            tma_load_2d(XTS + b * XTS_BYTES + ib * 8192, &tmXT, bar(B_FULL_XT + b), i0 + 32 * ib, 0);
+                        mbar_wait(bar(B_EMPTY_XM + r.s), r.ph ^ 1);
+                        mbar_expect_tx(bar(B_FULL_XM + r.s), XM_BYTES);
+                        for (int kb = 0; kb < 2; ++kb)
+                            tma_load_2d(XM + r.s * XM_BYTES + kb * 8192, &tmXm, bar(B_FULL_XM + r.s), 32 * kb, i0);
                     }
                 }
-                ++q;
             }
         }
     } else if (warp == 1) {
         // ================================ MMA issuer ===============================================
         // All 32 lanes run this code converged with warp-uniform values; one elected lane issues.
-        const uint32_t id_g = umma_idesc(128, 64);     // every MMA here is 128 x 64 x 8
+        const uint32_t id_z = umma_idesc(128, 64, false, false);   // Z  = Y(tmem) * Xh' : B K-major
+        const uint32_t id_dx = umma_idesc(64, 64, true, true);     // dX = G0'(smem, MN) * Yh(smem, MN)
+        const uint32_t id_dy = umma_idesc(128, 64, false, true);   // dY = G0(tmem) * Xh(smem, MN)
         const uint32_t tmu = __shfl_sync(0xffffffffu, tm, 0);
-        // descriptor of k-step s inside a K-major operand whose 32-wide K-atoms are `atom` bytes apart
+        // k-step s of a K-major operand whose 32-wide K-atoms (boxes) are `atom` bytes apart
         auto kstep = [](uint64_t d0, int s, uint32_t atom) { return d0 + (uint64_t)((((s >> 2) * atom) + (s & 3) * 32) >> 4); };
         uint32_t g = 0, q = 0;
+        Ring rx1;          // XK stage of the next MMA1
+        Ring rx3, ra;      // XM stage of the next MMA3, A/G stage of the next MMA2
         auto issue_mma1 = [&](uint32_t gg) {
-            const uint32_t b = gg & 1;
-            mbar_wait(bar(B_FULL_X + b), (gg >> 1) & 1);
+            mbar_wait(bar(B_FULL_XK + rx1.s), rx1.ph);
             tc_fence_after();
-            const uint32_t zt = tmu + TM_Z0 + 64 * b;
-            const uint64_t xraw = umma_desc(XS + b * XS_BYTES), xlo = umma_desc(XS + b * XS_BYTES + 16384u);
+            const uint32_t zt = tmu + TM_Z0 + 64 * (gg & 1);
+            const uint64_t xh = umma_desc_k(XK + rx1.s * XK_BYTES), xl = umma_desc_k(XK + rx1.s * XK_BYTES + XH_BYTES);
 #pragma unroll
-            for (int s = 0; s < 8; ++s) mma_ts(zt, tmu + TM_YH + 8 * s, kstep(xraw, s, 8192), id_g, s > 0 ? 1u : 0u);
+            for (int s = 0; s < 8; ++s) mma_ts(zt, tmu + TM_YH + 8 * s, kstep(xh, s, 8192), id_z, s > 0 ? 1u : 0u);
             if (p.z_passes == 3) {
 #pragma unroll
-                for (int s = 0; s < 8; ++s) mma_ts(zt, tmu + TM_YL + 8 * s, kstep(xraw, s, 8192), id_g, 1u);
+                for (int s = 0; s < 8; ++s) mma_ts(zt, tmu + TM_YL + 8 * s, kstep(xh, s, 8192), id_z, 1u);
 #pragma unroll
-                for (int s = 0; s < 8; ++s) mma_ts(zt, tmu + TM_YH + 8 * s, kstep(xlo, s, 8192), id_g, 1u);
+                for (int s = 0; s < 8; ++s) mma_ts(zt, tmu + TM_YH + 8 * s, kstep(xl, s, 8192), id_z, 1u);
             }
-            tc_commit_elect(bar(B_EMPTY_X + b));
-            tc_commit_elect(bar(B_Z_FULL + b));
+            tc_commit_elect(bar(B_EMPTY_XK + rx1.s));
+            tc_commit_elect(bar(B_Z_FULL + (gg & 1)));
+            rx1.next(SX);
         };
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
             int jt, it0, it1;
             item_range(p, item, jt, it0, it1);
             mbar_wait(bar(B_Y_READY), q & 1);
-            mbar_wait(bar(B_YT_FULL), q & 1);
             mbar_wait(bar(B_DY_EMPTY), (q & 1) ^ 1);
             tc_fence_after();
             issue_mma1(g);
-            const uint64_t ytd = umma_desc(YTS);
             for (int it = it0; it < it1; ++it, ++g) {
                 if (it + 1 < it1) issue_mma1(g + 1);
                 const uint32_t b = g & 1, ph = (g >> 1) & 1;
@@ -300,28 +314,29 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                 mbar_wait(bar(B_DX_EMPTY + b), ph ^ 1);
                 tc_fence_after();
                 {
-                    // MMA2 first (dX = G0' * Y'): its completion releases the A/G buffer for the TMA producer
-                    const uint64_t gd = umma_desc(AG + b * AG_BYTES);
+                    // MMA2 first (dX = G0' * Yh): its completion releases the A/G buffer for the TMA producer
+                    const uint64_t gd = umma_desc_mn(AG + ra.s * AG_BYTES, 16384u), yd = umma_desc_mn(YS, 16384u);
                     const uint32_t dxt = tmu + TM_DX0 + 64 * b;
 #pragma unroll
-                    for (int s = 0; s < 16; ++s) mma_ss(dxt, kstep(gd, s, 8192), kstep(ytd, s, 8192), id_g, s > 0 ? 1u : 0u);
-                    tc_commit_elect(bar(B_EMPTY_AG + b));
+                    for (int s = 0; s < 16; ++s) mma_ss(dxt, gd + (uint64_t)(s * 64), yd + (uint64_t)(s * 64), id_dx, s > 0 ? 1u : 0u);
+                    tc_commit_elect(bar(B_EMPTY_AG + ra.s));
                     tc_commit_elect(bar(B_DX_FULL + b));
+                    ra.next(SA);
                 }
-                mbar_wait(bar(B_FULL_XT + b), ph);
-                tc_fence_after();
                 {
-                    // MMA3: dY += G0 * X'
+                    // MMA3: dY += G0 * Xh  (MN-major copy of the Xh tile)
+                    mbar_wait(bar(B_FULL_XM + rx3.s), rx3.ph);
+                    tc_fence_after();
                     const uint32_t ga = tmu + TM_Z0 + 64 * b;
-                    const uint64_t xtd = umma_desc(XTS + b * XTS_BYTES);
+                    const uint64_t xd = umma_desc_mn(XM + rx3.s * XM_BYTES, 8192u);
                     const uint32_t first = it > it0 ? 1u : 0u;
 #pragma unroll
-                    for (int s = 0; s < 8; ++s) mma_ts(tmu + TM_DY, ga + 8 * s, kstep(xtd, s, 8192), id_g, s > 0 ? 1u : first);
-                    tc_commit_elect(bar(B_EMPTY_XT + b));
+                    for (int s = 0; s < 8; ++s) mma_ts(tmu + TM_DY, ga + 8 * s, xd + (uint64_t)(s * 64), id_dy, s > 0 ? 1u : first);
+                    tc_commit_elect(bar(B_EMPTY_XM + rx3.s));
+                    rx3.next(SX);
                 }
             }
             tc_commit_elect(bar(B_DY_FULL));
-            tc_commit_elect(bar(B_YT_EMPTY));
             ++q;
         }
     } else {
@@ -330,25 +345,30 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         // warps per scheduler hide the TMEM / shared-memory latencies of one another.
         const int quarter = warp & 3;
         const int c16 = (warp - 2) >> 2;              // 0..3
-        const int iq = c16 >> 1;                      // which 32-sample A box of the tile
-        const int lrow = 32 * quarter + lane;         // feature lane (G epilogue) / sample lane (dX read-out)
+        const int lrow = 32 * quarter + lane;         // feature row of the tile
         const uint32_t lane_addr = ((uint32_t)(32 * quarter)) << 16;
-        const uint32_t pair_bar = 1u + (uint32_t)(quarter * 2 + iq);   // named barrier of the two warps sharing an A box
+        // this thread's four 16-byte chunks inside a 128-byte box row (A in, G0 out, Yh out): logical chunk
+        // c = 4*(c16&1) + v sits in 32-byte slot (c>>1) ^ (row&3), half c&1  (128B swizzle with 32-byte atoms)
+        uint32_t choff[4];
+#pragma unroll
+        for (int v = 0; v < 4; ++v)
+            choff[v] = (uint32_t)(lrow * 128 + ((((2 * (c16 & 1) + (v >> 1)) ^ (lane & 3)) << 5) | ((v & 1) << 4)));
+        const uint32_t boxoff = (uint32_t)(c16 >> 1) * 16384u;
         uint32_t g = 0, q = 0;
+        Ring ra;
         double loss_d = 0.0;
-        // dX read-out (deferred by one tile); only lanes 0..63 of the accumulator are valid rows
+        // dX read-out (deferred by one tile).  M = 64 accumulator: sample row r sits in lane (r%16) + 32*(r/16)
         auto dx_out = [&](uint32_t gg, int i0) {
-            if (quarter >= 2) return;
             const uint32_t b = gg & 1;
             mbar_wait(bar(B_DX_FULL + b), (gg >> 1) & 1);
             tc_fence_after();
-            const int i = i0 + lrow;
             uint32_t r[16];
             TMEM_LD16(tm + lane_addr + TM_DX0 + 64 * b + 16 * c16, r);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             tc_fence_before();
             mbar_arrive(bar(B_DX_EMPTY + b));
-            if (i < dp.M) {
+            const int i = i0 + 16 * quarter + lane;
+            if (lane < 16 && i < dp.M) {
                 float* dst = dp.dX + (size_t)i * KK + 16 * c16;
 #pragma unroll
                 for (int v = 0; v < 4; ++v)
@@ -374,7 +394,8 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
             const float gscale = sigma * wj;       // G0 = w_j sigma_j * dloss/dz4  (no batch layers on this path)
             float dmu_acc = 0.f, loss_acc = 0.f;   // unweighted sums over this item (<= a few thousand terms)
 
-            // ---- Y tile -> TMEM (hi = TF32 truncation as the tensor core would read it, lo = rest)
+            // ---- Y tile: h = rna_tf32(y) -> TMEM (A of MMA1) and shared memory (B of MMA2); l = y - h -> TMEM.
+            // The previous item's MMAs have all completed (B_DY_FULL was waited on), so both are free.
             {
                 const float4* yrow = reinterpret_cast<const float4*>(dp.Y + (size_t)(jt * BJ + lrow) * KK) + 4 * c16;
                 uint32_t hi[16], lo[16];
@@ -384,33 +405,33 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                     float ys[4] = {y4.x, y4.y, y4.z, y4.w};
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
-                        uint32_t hb = __float_as_uint(ys[c]) & 0xffffe000u;
+                        uint32_t hb = rna_tf32(ys[c]);
                         hi[4 * v + c] = hb;
                         lo[4 * v + c] = __float_as_uint(ys[c] - __uint_as_float(hb));
                     }
+                    *reinterpret_cast<uint4*>(ys_ptr + boxoff + choff[v]) = make_uint4(hi[4 * v], hi[4 * v + 1], hi[4 * v + 2], hi[4 * v + 3]);
                 }
                 TMEM_ST16(tm + lane_addr + TM_YH + 16 * c16, hi);
                 TMEM_ST16(tm + lane_addr + TM_YL + 16 * c16, lo);
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 tc_fence_before();
+                fence_async_smem();
                 mbar_arrive(bar(B_Y_READY));
             }
 
-            for (int it = it0; it < it1; ++it, ++g) {
+            for (int it = it0; it < it1; ++it, ++g, ra.next(SA)) {
                 const uint32_t b = g & 1, ph = (g >> 1) & 1;
                 mbar_wait(bar(B_Z_FULL + b), ph);
-                mbar_wait(bar(B_FULL_A + b), ph);
+                mbar_wait(bar(B_FULL_A + ra.s), ra.ph);
                 tc_fence_after();
                 const uint32_t zt = tm + lane_addr + TM_Z0 + 64 * b + 16 * c16;
-                uint8_t* ag_ptr = ag_ptr0 + b * AG_BYTES;
+                uint8_t* abox = ag_ptr0 + ra.s * AG_BYTES + boxoff;
                 uint32_t z[16];
                 TMEM_LD16(zt, z);
-                // A: box (jq = quarter, iq), row = lane, this warp's 16 columns = 4 swizzled 16-byte chunks
-                const uint8_t* box = ag_ptr + (quarter * 2 + iq) * 4096;
                 float a[16];
 #pragma unroll
                 for (int v = 0; v < 4; ++v) {
-                    float4 a4 = *reinterpret_cast<const float4*>(box + lane * 128 + (((4 * (c16 & 1) + v) ^ (lane & 7)) << 4));
+                    float4 a4 = *reinterpret_cast<const float4*>(abox + choff[v]);
                     a[4 * v] = a4.x; a[4 * v + 1] = a4.y; a[4 * v + 2] = a4.z; a[4 * v + 3] = a4.w;
                 }
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -463,16 +484,12 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                         z[e] = rna_tf32(lg.y * gscale);
                     }
                 }
-                // G0 back to TMEM in place of Z (A operand of MMA3)
+                // G0 back to TMEM in place of Z (A operand of MMA3) and over the A values this thread
+                // read (MN-major A operand of MMA2): same addresses, 128-bit stores, no transposition
                 TMEM_ST16(zt, z);
-                // both warps that share this A box have pulled their data into registers
-                asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
-                // G0' : rows i = 16*c16 .. +15 of K-atom box `quarter` (8 KB per box), column = lane
-                uint8_t* gbox = ag_ptr + quarter * 8192 + (16 * c16) * 128;
 #pragma unroll
-                for (int e = 0; e < 16; ++e) {
-                    *reinterpret_cast<uint32_t*>(gbox + e * 128 + (((lane >> 2) ^ (e & 7)) << 4) + ((lane & 3) << 2)) = z[e];
-                }
+                for (int v = 0; v < 4; ++v)
+                    *reinterpret_cast<uint4*>(abox + choff[v]) = make_uint4(z[4 * v], z[4 * v + 1], z[4 * v + 2], z[4 * v + 3]);
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 tc_fence_before();
                 fence_async_smem();
@@ -527,26 +544,19 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     }
 }
 
-// X_lo = X - trunc_tf32(X); XT = rna_tf32(X)' ; YT = rna_tf32(Y)'   (operands of the TC data pass)
-__global__ void prep_operands_kernel(const float* __restrict__ X, float* __restrict__ Xlo, float* __restrict__ XT,
-                                     int Mp, const float* __restrict__ Y, float* __restrict__ YT, int Np,
-                                     const int* stop_flag) {
+// TF32 operand split of X:  Xh = rna_tf32(X),  Xl = X - Xh  (exact in FP32)
+__global__ void prep_operands_kernel(const float4* __restrict__ X, float4* __restrict__ Xh, float4* __restrict__ Xl,
+                                     size_t n4, const int* stop_flag) {
     if (stop_flag != nullptr && *stop_flag != 0) return;
-    __shared__ float t[32][33];
-    const bool isY = blockIdx.y >= 2;
-    const float* P = isY ? Y : X;
-    float* PT = isY ? YT : XT;
-    const int n = isY ? Np : Mp;
-    const int r0 = blockIdx.x * 32, k0 = (blockIdx.y & 1) * 32;
-    if (r0 >= n) return;
-    for (int rr = threadIdx.y; rr < 32; rr += blockDim.y) {
-        float v = P[(size_t)(r0 + rr) * KK + k0 + threadIdx.x];
-        if (!isY) Xlo[(size_t)(r0 + rr) * KK + k0 + threadIdx.x] = v - __uint_as_float(__float_as_uint(v) & 0xffffe000u);
-        t[rr][threadIdx.x] = __uint_as_float(rna_tf32(v));
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 v = X[i];
+        float4 h, l;
+        h.x = __uint_as_float(rna_tf32(v.x)); h.y = __uint_as_float(rna_tf32(v.y));
+        h.z = __uint_as_float(rna_tf32(v.z)); h.w = __uint_as_float(rna_tf32(v.w));
+        l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+        Xh[i] = h;
+        Xl[i] = l;
     }
-    __syncthreads();
-    for (int kk = threadIdx.y; kk < 32; kk += blockDim.y)
-        PT[(size_t)(k0 + kk) * n + r0 + threadIdx.x] = t[threadIdx.x][kk];
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -566,8 +576,9 @@ EncodeTiledFn get_encode() {
 }
 
 // 2-D FP32 tensor [rows][cols] (cols contiguous, row pitch = pitch floats), box = box_rows x 32 floats
+// atom32: 128B swizzle with 32-byte atoms (MN-major TF32 operands), else the standard 16-byte atoms
 bool make_map(CUtensorMap* m, const float* base, uint64_t cols, uint64_t rows, uint64_t pitch, uint32_t box_rows,
-              bool nan_fill) {
+              bool nan_fill, bool atom32) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return false;
     cuuint64_t dims[2] = {cols, rows};
@@ -575,7 +586,8 @@ bool make_map(CUtensorMap* m, const float* base, uint64_t cols, uint64_t rows, u
     cuuint32_t box[2] = {32, box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      nan_fill ? CU_TENSOR_MAP_FLOAT_OOB_FILL_NAN_REQUEST_ZERO_FMA : CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
 }
@@ -586,19 +598,20 @@ bool tc_supported(const DataPassParams& p) {
     return p.Kp == KK && p.n_batch_views == 0 && p.col_ssq == nullptr;
 }
 
-// Xlo: [Mp][64], XT: [64][Mp], YT: [64][Np] scratch owned by the handle
-cudaError_t launch_data_pass_tc(const DataPassParams& dp, float* Xlo, float* XT, float* YT, int precision,
-                                cudaStream_t s, int n_sms) {
+// Xh, Xl: [Mp][64] operand scratch owned by the handle, refreshed here every launch
+cudaError_t launch_data_pass_tc(const DataPassParams& dp, float* Xh, float* Xl, int precision, cudaStream_t s,
+                                int n_sms) {
     if (!tc_supported(dp)) return cudaErrorInvalidValue;
-    dim3 pb(32, 8), pg((unsigned)((dp.Mp > dp.Np ? dp.Mp : dp.Np) / 32), 4);
-    prep_operands_kernel<<<pg, pb, 0, s>>>(dp.X, Xlo, XT, dp.Mp, dp.Y, YT, dp.Np, dp.stop_flag);
+    const size_t n4 = (size_t)dp.Mp * KK / 4;
+    prep_operands_kernel<<<(unsigned)((n4 + 255) / 256 < 1184 ? (n4 + 255) / 256 : 1184), 256, 0, s>>>(
+        reinterpret_cast<const float4*>(dp.X), reinterpret_cast<float4*>(Xh), reinterpret_cast<float4*>(Xl), n4,
+        dp.stop_flag);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
 
-    CUtensorMap tmX, tmXlo, tmXT, tmYT, tmA;
-    bool ok = make_map(&tmX, dp.X, KK, dp.Mp, KK, 64, false) && make_map(&tmXlo, Xlo, KK, dp.Mp, KK, 64, false) &&
-              make_map(&tmXT, XT, dp.Mp, KK, dp.Mp, 64, false) && make_map(&tmYT, YT, dp.Np, KK, dp.Np, 64, false) &&
-              make_map(&tmA, dp.A, dp.lda, dp.N, dp.lda, 32, true);
+    CUtensorMap tmXh, tmXl, tmXm, tmA;
+    bool ok = make_map(&tmXh, Xh, KK, dp.Mp, KK, 64, false, false) && make_map(&tmXl, Xl, KK, dp.Mp, KK, 64, false, false) &&
+              make_map(&tmXm, Xh, KK, dp.Mp, KK, 64, false, true) && make_map(&tmA, dp.A, dp.lda, dp.N, dp.lda, 128, true, true);
     if (!ok) return cudaErrorUnknown;
 
     TcParams p;
@@ -621,7 +634,7 @@ cudaError_t launch_data_pass_tc(const DataPassParams& dp, float* Xlo, float* XT,
     e = cudaFuncSetAttribute(data_pass_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TOTAL);
     if (e != cudaSuccess) return e;
     int grid = p.n_items < n_sms ? p.n_items : n_sms;
-    data_pass_tc_kernel<<<grid, NTHREADS, SMEM_TOTAL, s>>>(tmX, tmXlo, tmXT, tmYT, tmA, p);
+    data_pass_tc_kernel<<<grid, NTHREADS, SMEM_TOTAL, s>>>(tmXh, tmXl, tmXm, tmA, p);
     return cudaGetLastError();
 }
 

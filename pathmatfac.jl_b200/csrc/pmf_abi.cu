@@ -135,7 +135,7 @@ int pmf_destroy(pmf_handle h) {
     cudaSetDevice(h->dims.device);
     cudaDeviceSynchronize();
     dev_free(h->A); dev_free(h->X); dev_free(h->dX); dev_free(h->accX); dev_free(h->Y); dev_free(h->accY);
-    dev_free(h->Xlo); dev_free(h->XT); dev_free(h->YT);
+    dev_free(h->Xl); dev_free(h->Xh);
     dev_free(h->weight); dev_free(h->colinfo); dev_free(h->thresholds); dev_free(h->scalars); dev_free(h->ctrl);
     dev_free(h->vp); dev_free(h->sg); dev_free(h->accvp); dev_free(h->regw); dev_free(h->regc);
     dev_free(h->bcol_off); dev_free(h->bcol_view); dev_free(h->bcol_nb); dev_free(h->batch_of_sample);
@@ -880,9 +880,8 @@ int pmf_model_s::run_data_pass(DataPassParams& p, int kind, int precision) {
     const bool big = (double)M * (double)N >= 4.0e6 && M >= 1024;
     const bool use_tc = kind == PMF_KERNEL_TC || (kind == PMF_KERNEL_AUTO && tc_ok && auto_tc && big);
     if (use_tc) {
-        if (!Xlo) {
-            if (dev_alloc(&Xlo, (size_t)Mp * Kp) != cudaSuccess || dev_alloc(&XT, (size_t)Mp * Kp) != cudaSuccess ||
-                dev_alloc(&YT, (size_t)Np * Kp) != cudaSuccess)
+        if (!Xh) {
+            if (dev_alloc(&Xh, (size_t)Mp * Kp) != cudaSuccess || dev_alloc(&Xl, (size_t)Mp * Kp) != cudaSuccess)
                 return fail(this, PMF_ERR_ALLOC, "device allocation failed");
         }
         cudaEvent_t t0 = nullptr, t1 = nullptr;
@@ -894,7 +893,7 @@ int pmf_model_s::run_data_pass(DataPassParams& p, int kind, int precision) {
             prof_used += 2;
             cudaEventRecord(t0, stream);
         }
-        cudaError_t e = launch_data_pass_tc(p, Xlo, XT, YT, precision, stream, n_sms);
+        cudaError_t e = launch_data_pass_tc(p, Xh, Xl, precision, stream, n_sms);
         if (profiling) cudaEventRecord(t1, stream);
         if (e != cudaSuccess) { cuda_failed = true; return fail(this, PMF_ERR_CUDA, "tcgen05 data pass launch: %s", cudaGetErrorString(e)); }
         launches += 2;

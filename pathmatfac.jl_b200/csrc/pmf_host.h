@@ -80,7 +80,7 @@ struct pmf_model_s {
     float* A = nullptr;
     float *X = nullptr, *dX = nullptr, *accX = nullptr;
     float *Y = nullptr, *accY = nullptr;
-    float *Xlo = nullptr, *XT = nullptr, *YT = nullptr;   // operand scratch of the tcgen05 path (lazy)
+    float *Xh = nullptr, *Xl = nullptr;   // TF32 operand split of X for the tcgen05 path (lazy)
     bool auto_tc = true;                     // PMF_KERNEL_AUTO picks the tcgen05 path when it applies
     // per-column noise description
     float* weight = nullptr;

@@ -126,12 +126,12 @@ struct NetworkParams {
 
 // launchers (each defined next to its kernel)
 cudaError_t launch_data_pass_ffma(const DataPassParams& p, cudaStream_t s, int n_sms);
-// tcgen05 path (fused_tc.cu): K == 64, no batch layers.  Xlo [Mp][64], XT [64][Mp], YT [64][Np]
-// are scratch operands refreshed by the launcher.  precision: 0/1 = 3xTF32 Z + TF32 gradients,
-// 2 = TF32 everywhere.
+// tcgen05 path (fused_tc.cu): K == 64, no batch layers.  Xh = rna_tf32(X), Xl = X - Xh, both
+// [Mp][64], are scratch operands refreshed by the launcher.  precision: 0/1 = 3xTF32 Z + TF32
+// gradients, 2 = TF32 everywhere.
 bool tc_supported(const DataPassParams& p);
-cudaError_t launch_data_pass_tc(const DataPassParams& p, float* Xlo, float* XT, float* YT, int precision,
-                                cudaStream_t s, int n_sms);
+cudaError_t launch_data_pass_tc(const DataPassParams& p, float* Xh, float* Xl, int precision, cudaStream_t s,
+                                int n_sms);
 cudaError_t launch_factor_update(const FactorUpdateParams& p, cudaStream_t s);
 cudaError_t launch_vector_update(const VectorUpdateParams& p, cudaStream_t s);
 cudaError_t launch_control(FitControl* ctrl, const double* scalars, double* hist, int hist_cap,
