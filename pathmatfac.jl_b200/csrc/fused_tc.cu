@@ -167,6 +167,19 @@ __device__ __forceinline__ uint32_t rna_tf32(float x) {
     return r;
 }
 
+// TF32 operand rounding for values the tensor core will truncate anyway: adding half a TF32 ulp to the
+// bit pattern makes that truncation a round-to-nearest (ties away); one integer add per entry.
+__device__ __forceinline__ uint32_t rn_bits(float x) { return __float_as_uint(x) + 0x1000u; }
+
+// single-instruction SFU forms (flush-to-zero: no denormal range fix-up code around the MUFU)
+__device__ __forceinline__ float ex2_fast(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2_fast(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_fast(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// all-ones when the datum is observed (finite), zero when it is missing: ANDed into results that are
+// NaN for a missing datum, so the mask costs no branch
+__device__ __forceinline__ uint32_t obs_mask(float a) { return fabsf(a) < INFINITY ? 0xffffffffu : 0u; }
+__device__ __forceinline__ float and_mask(float x, uint32_t m) { return __uint_as_float(__float_as_uint(x) & m); }
+
 // ordinal / hinge noise models: rare on the hot path, kept out of line to bound code size.
 // Returns (loss, dloss/dz); (0, 0) for a missing entry.
 __device__ __noinline__ float2 noise_eval_slow(int dist, float z, float a, float4 th4, float ord_eps, float margin) {
@@ -391,10 +404,12 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
             const int ci = dp.colinfo[jj];
             const int dist = ci & 0xff;
             const float4 th4 = __ldg(reinterpret_cast<const float4*>(dp.thresholds + 4 * (ci >> 8)));
-            const float gscale = sigma * wj;       // G0 = w_j sigma_j * dloss/dz4  (no batch layers on this path)
+            // G0 = (w_j sigma_j) * dloss/dz4 (no batch layers on this path).  The per-feature factor never
+            // touches the per-entry path: MMA2 reads Yh scaled by it, the dY tile is scaled at the flush.
+            const float gscale = sigma * wj;
             float dmu_acc = 0.f, loss_acc = 0.f;   // unweighted sums over this item (<= a few thousand terms)
 
-            // ---- Y tile: h = rna_tf32(y) -> TMEM (A of MMA1) and shared memory (B of MMA2); l = y - h -> TMEM.
+            // ---- Y tile: h = rna_tf32(y), l = y - h -> TMEM (A of MMA1); gscale * y -> shared memory (B of MMA2).
             // The previous item's MMAs have all completed (B_DY_FULL was waited on), so both are free.
             {
                 const float4* yrow = reinterpret_cast<const float4*>(dp.Y + (size_t)(jt * BJ + lrow) * KK) + 4 * c16;
@@ -409,7 +424,8 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
                         hi[4 * v + c] = hb;
                         lo[4 * v + c] = __float_as_uint(ys[c] - __uint_as_float(hb));
                     }
-                    *reinterpret_cast<uint4*>(ys_ptr + boxoff + choff[v]) = make_uint4(hi[4 * v], hi[4 * v + 1], hi[4 * v + 2], hi[4 * v + 3]);
+                    *reinterpret_cast<uint4*>(ys_ptr + boxoff + choff[v]) =
+                        make_uint4(rna_tf32(gscale * y4.x), rna_tf32(gscale * y4.y), rna_tf32(gscale * y4.z), rna_tf32(gscale * y4.w));
                 }
                 TMEM_ST16(tm + lane_addr + TM_YH + 16 * c16, hi);
                 TMEM_ST16(tm + lane_addr + TM_YL + 16 * c16, lo);
@@ -444,35 +460,36 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
                         d = fabsf(a[e]) < INFINITY ? d : 0.f;        // NaN / Inf => missing (ordered compare)
                         loss_acc = fmaf(d, d, loss_acc);              // (z-a)^2, halved and weighted at flush
                         dmu_acc += d;
-                        z[e] = rna_tf32(d * gscale);
+                        z[e] = rn_bits(d);
                     }
                 } else if (dist == DIST_BERNOULLI) {
-                    // softplus(z) - a z ; sigmoid(z) - a ; branch-free (missing entries select 0)
+                    // softplus(z) - a z ; sigmoid(z) - a, sharing e = exp(-|z|); a missing entry makes both NaN
+                    // and is masked away once at the end
 #pragma unroll
                     for (int e = 0; e < 16; ++e) {
-                        const bool ob = fabsf(a[e]) < INFINITY;
-                        const float a0 = ob ? a[e] : 0.f;
+                        const uint32_t m = obs_mask(a[e]);
                         float z4 = fmaf(__uint_as_float(z[e]), sigma, muj);
-                        float ex = __expf(-fabsf(z4));
-                        float r = __fdividef(1.0f, 1.0f + ex);
+                        float ex = ex2_fast(fabsf(z4) * -1.4426950408889634f);
+                        float w = 1.0f + ex;
+                        float r = rcp_fast(w);
                         float sg = z4 >= 0.f ? r : ex * r;
-                        float l = fmaxf(z4, 0.f) + __logf(1.0f + ex) - a0 * z4;
-                        float gv = ob ? sg - a0 : 0.f;
-                        loss_acc += ob ? 2.f * l : 0.f;
+                        float l = fmaf(-a[e], z4, fmaf(lg2_fast(w), 0.6931471805599453f, fmaxf(z4, 0.f)));
+                        float gv = and_mask(sg - a[e], m);
+                        loss_acc = fmaf(2.f, and_mask(l, m), loss_acc);
                         dmu_acc += gv;
-                        z[e] = rna_tf32(gv * gscale);
+                        z[e] = rn_bits(gv);
                     }
                 } else if (dist == DIST_POISSON) {
 #pragma unroll
                     for (int e = 0; e < 16; ++e) {
-                        const bool ob = fabsf(a[e]) < INFINITY;
-                        const float a0 = ob ? a[e] : 0.f;
+                        const uint32_t m = obs_mask(a[e]);
                         float z4 = fmaf(__uint_as_float(z[e]), sigma, muj);
-                        float ez = __expf(z4);
-                        float gv = ob ? ez - a0 : 0.f;
-                        loss_acc += ob ? 2.f * fmaf(-a0, z4, ez) : 0.f;
+                        float ez = ex2_fast(z4 * 1.4426950408889634f);
+                        float gv = and_mask(ez - a[e], m);
+                        float l = and_mask(fmaf(-a[e], z4, ez), m);
+                        loss_acc = fmaf(2.f, l, loss_acc);
                         dmu_acc += gv;
-                        z[e] = rna_tf32(gv * gscale);
+                        z[e] = rn_bits(gv);
                     }
                 } else {
 #pragma unroll
@@ -481,10 +498,10 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
                         float2 lg = noise_eval_slow(dist, z4, a[e], th4, dp.ordinal_eps, dp.hinge_margin);
                         loss_acc = fmaf(2.f, lg.x, loss_acc);        // keep the common 1/2 factor at flush
                         dmu_acc += lg.y;
-                        z[e] = rna_tf32(lg.y * gscale);
+                        z[e] = rn_bits(lg.y);
                     }
                 }
-                // G0 back to TMEM in place of Z (A operand of MMA3) and over the A values this thread
+                // dloss/dz back to TMEM in place of Z (A operand of MMA3) and over the A values this thread
                 // read (MN-major A operand of MMA2): same addresses, 128-bit stores, no transposition
                 TMEM_ST16(zt, z);
 #pragma unroll
@@ -512,8 +529,8 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
                     float* dst = dp.dY + (size_t)j * KK + 16 * c16;
 #pragma unroll
                     for (int v = 0; v < 4; ++v) {
-                        float4 val = make_float4(__uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]),
-                                                 __uint_as_float(r[4 * v + 2]), __uint_as_float(r[4 * v + 3]));
+                        float4 val = make_float4(gscale * __uint_as_float(r[4 * v]), gscale * __uint_as_float(r[4 * v + 1]),
+                                                 gscale * __uint_as_float(r[4 * v + 2]), gscale * __uint_as_float(r[4 * v + 3]));
                         if (p.chunks == 1) reinterpret_cast<float4*>(dst)[v] = val;
                         else atomicAdd(reinterpret_cast<float4*>(dst) + v, val);
                     }
