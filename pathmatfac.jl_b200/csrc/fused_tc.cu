@@ -31,6 +31,8 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 #include "pmf_epilogue.cuh"
 #include "pmf_internal.h"
@@ -40,16 +42,18 @@ namespace pmf {
 namespace {
 
 constexpr int BJ = 128, BI = 64, KK = 64;
-constexpr int NEPI = 16;                  // epilogue warps: (TMEM lane quarter, 16-column chunk)
-constexpr int NTHREADS = 64 + 32 * NEPI;  // warp 0 TMA, warp 1 MMA, warps 2.. epilogue
+constexpr int NEPI = 16;                  // epilogue warps: 2 groups x (TMEM lane quarter, 32-column half)
+constexpr int NPRE = 4;                   // warp 0 TMA A, warp 1 MMA, warp 2 TMA XK, warp 3 TMA XM
+constexpr int NTHREADS = 32 * (NPRE + NEPI);
 constexpr int SX = 2, SA = 3;             // pipeline depth of the X streams and of the A/G stream
 constexpr uint32_t XH_BYTES = 16384, XK_BYTES = 32768 /* Xh | Xl */, XM_BYTES = 16384, YS_BYTES = 32768, AG_BYTES = 32768;
 constexpr uint32_t SMEM_DATA = SX * XK_BYTES + SX * XM_BYTES + YS_BYTES + SA * AG_BYTES;
 constexpr uint32_t SMEM_TOTAL = SMEM_DATA + 1024 /*align slack*/ + 256 /*barriers*/;
-constexpr uint32_t TM_YH = 0, TM_YL = 64, TM_Z0 = 128, TM_DY = 256, TM_DX0 = 320;   // Z1 = Z0+64, dX1 = dX0+64
+constexpr int SZ = 3;                     // Z / G0 accumulators in TMEM
+constexpr uint32_t TM_YH = 0, TM_YL = 64, TM_Z0 = 128, TM_DY = 320, TM_DX0 = 384;   // Z_b = Z0+64b, dX1 = dX0+64
 
 enum Bar { B_FULL_XK = 0, B_EMPTY_XK = 2, B_FULL_XM = 4, B_EMPTY_XM = 6, B_FULL_A = 8, B_EMPTY_AG = 11, B_Z_FULL = 14,
-           B_G_READY = 16, B_DX_FULL = 18, B_DX_EMPTY = 20, B_Y_READY = 22, B_DY_FULL, B_DY_EMPTY, B_COUNT };
+           B_G_READY = 17, B_DX_FULL = 20, B_DX_EMPTY = 22, B_Y_READY = 24, B_DY_FULL, B_DY_EMPTY, B_COUNT };
 
 // ---- PTX wrappers --------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -85,26 +89,27 @@ __device__ __forceinline__ void tc_commit(uint32_t bar) {
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// The MMA warp stays converged and every operand is warp-uniform; `elect.sync` inside the asm picks
-// the issuing lane, so the compiler keeps descriptors in uniform registers (no per-MMA R2UR).
+// tcgen05.mma / commit are issued by ONE thread of the MMA warp (the whole role runs under a single
+// elect), so no per-instruction election or vote is needed around them.
 // D[tmem] (+)= A[tmem] * B[smem]   (kind::tf32, cta_group::1)
 __device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
     asm volatile(
-        "{\n\t.reg .pred p, e;\n\telect.sync _|e, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
         ::"r"(d), "r"(a), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
 // D[tmem] (+)= A[smem] * B[smem]
 __device__ __forceinline__ void mma_ss(uint32_t d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
     asm volatile(
-        "{\n\t.reg .pred p, e;\n\telect.sync _|e, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
-__device__ __forceinline__ void tc_commit_elect(uint32_t bar) {
-    asm volatile(
-        "{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
-        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar) : "memory");
+__device__ __forceinline__ void tc_commit_elect(uint32_t bar) { tc_commit(bar); }
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\tselp.u32 %0, 1, 0, e;\n\t}" : "=r"(pred));
+    return pred != 0;
 }
 
 // Shared-memory operand descriptors, 128-byte swizzle (rows of 32 floats, 8-row groups 1024 B apart).
@@ -194,7 +199,11 @@ struct TcParams {
     DataPassParams dp;
     int n_jt, n_it, chunks, n_items;
     int z_passes;      // 3 = 3xTF32 for the Z contraction, 1 = plain TF32
+    int ablate;        // PMF_TC_ABLATE (performance experiments only; results are wrong when non-zero)
+    long long* trace;  // PMF_TC_TRACE: per-tile clock64 stamps of one CTA (16 events x TRACE_TILES), else null
+    int trace_cta;
 };
+constexpr int TRACE_TILES = 96, TRACE_EV = 16;
 
 __device__ __forceinline__ void item_range(const TcParams& p, int item, int& jt, int& it0, int& it1) {
     jt = item / p.chunks;
@@ -224,6 +233,10 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + SMEM_DATA + 8 * B_COUNT);
     __shared__ double red_smem[NTHREADS / 32];
     auto bar = [&](int b) { return BARS + 8u * (uint32_t)b; };
+    // event stamp of CTA 0 (timeline experiments; the branch is CTA-uniform)
+    auto stamp = [&](uint32_t gg, int ev) {
+        if (p.trace != nullptr && blockIdx.x == (unsigned)p.trace_cta && gg < (uint32_t)TRACE_TILES) p.trace[gg * TRACE_EV + ev] = clock64();
+    };
 
     // warp index through a shuffle: the compiler then treats role branches as warp-uniform and keeps
     // MMA descriptors / barrier addresses in uniform registers
@@ -233,9 +246,9 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
     if (threadIdx.x == 0) {
         for (int b = 0; b < B_COUNT; ++b) {
             uint32_t cnt = 1u;
-            if (b == B_G_READY || b == B_G_READY + 1 || b == B_Y_READY || b == B_DY_EMPTY || b == B_DX_EMPTY ||
-                b == B_DX_EMPTY + 1)
-                cnt = 32u * NEPI;
+            if (b == B_Y_READY || b == B_DY_EMPTY) cnt = 32u * NEPI;                       // every epilogue thread
+            if ((b >= B_G_READY && b < B_G_READY + SZ) || b == B_DX_EMPTY || b == B_DX_EMPTY + 1)
+                cnt = 16u * NEPI;                                                         // one epilogue group
             mbar_init(bar(b), cnt);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -249,20 +262,22 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
     tc_fence_after();
     const uint32_t tm = *tmem_slot;
 
-    if (warp == 0) {
+    if (warp == 0 || warp == 2 || warp == 3) {
         // ================================ TMA producers ===========================================
-        // Three independent lanes, one per stream, so that a buffer that is released late (the A/G
-        // tile waits for MMA2) never holds back the loads of the other streams.
-        if (lane < 3) {
+        // One warp per stream (A tiles, K-major X operands, MN-major X operand): a buffer that is released
+        // late never holds back the loads of another stream, and no producer shares a warp with another
+        // producer's barrier wait.
+        if (lane == 0) {
             Ring r;
-            const uint32_t depth = lane == 1 ? SA : SX;
+            uint32_t gcount = 0;
+            const uint32_t depth = warp == 0 ? SA : SX;
             for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
                 int jt, it0, it1;
                 item_range(p, item, jt, it0, it1);
                 const int j0 = jt * BJ;
-                for (int it = it0; it < it1; ++it, r.next(depth)) {
+                for (int it = it0; it < it1; ++it, r.next(depth), ++gcount) {
                     const int i0 = it * BI;
-                    if (lane == 0) {
+                    if (warp == 2) {
                         mbar_wait(bar(B_EMPTY_XK + r.s), r.ph ^ 1);
                         mbar_expect_tx(bar(B_FULL_XK + r.s), XK_BYTES);
                         const uint32_t dst = XK + r.s * XK_BYTES;
@@ -270,11 +285,13 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
                             tma_load_2d(dst + kb * 8192, &tmXh, bar(B_FULL_XK + r.s), 32 * kb, i0);
                             tma_load_2d(dst + XH_BYTES + kb * 8192, &tmXl, bar(B_FULL_XK + r.s), 32 * kb, i0);
                         }
-                    } else if (lane == 1) {
+                    } else if (warp == 0) {
                         mbar_wait(bar(B_EMPTY_AG + r.s), r.ph ^ 1);
+                        stamp(gcount, 0);
                         mbar_expect_tx(bar(B_FULL_A + r.s), AG_BYTES);
                         for (int iq = 0; iq < 2; ++iq)
-                            tma_load_2d(AG + r.s * AG_BYTES + iq * 16384, &tmA, bar(B_FULL_A + r.s), i0 + 32 * iq, j0);
+                            tma_load_2d(AG + r.s * AG_BYTES + iq * 16384, &tmA, bar(B_FULL_A + r.s),
+                                        (p.ablate & 32) ? 32 * iq : i0 + 32 * iq, (p.ablate & 32) ? 0 : j0);
                     } else {
                         mbar_wait(bar(B_EMPTY_XM + r.s), r.ph ^ 1);
                         mbar_expect_tx(bar(B_FULL_XM + r.s), XM_BYTES);
@@ -285,21 +302,27 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
             }
         }
     } else if (warp == 1) {
+      if (elect_one()) {
         // ================================ MMA issuer ===============================================
-        // All 32 lanes run this code converged with warp-uniform values; one elected lane issues.
+        // One elected thread runs the whole role: barrier waits, tcgen05.mma, tcgen05.commit.
         const uint32_t id_z = umma_idesc(128, 64, false, false);   // Z  = Y(tmem) * Xh' : B K-major
         const uint32_t id_dx = umma_idesc(64, 64, true, true);     // dX = G0'(smem, MN) * Yh(smem, MN)
         const uint32_t id_dy = umma_idesc(128, 64, false, true);   // dY = G0(tmem) * Xh(smem, MN)
-        const uint32_t tmu = __shfl_sync(0xffffffffu, tm, 0);
+        // All 512 columns are allocated by the only CTA on the SM, so the TMEM base is 0 (checked): a literal
+        // keeps every tcgen05.mma operand in uniform registers (no per-instruction R2UR).
+        if (tm != 0u) __trap();
+        const uint32_t tmu = 0u;
         // k-step s of a K-major operand whose 32-wide K-atoms (boxes) are `atom` bytes apart
         auto kstep = [](uint64_t d0, int s, uint32_t atom) { return d0 + (uint64_t)((((s >> 2) * atom) + (s & 3) * 32) >> 4); };
-        uint32_t g = 0, q = 0;
-        Ring rx1;          // XK stage of the next MMA1
-        Ring rx3, ra;      // XM stage of the next MMA3, A/G stage of the next MMA2
-        auto issue_mma1 = [&](uint32_t gg) {
+        uint32_t g = 0, q = 0, g1 = 0;
+        Ring rx1, rz1;         // XK stage / Z buffer of the next MMA1
+        Ring rx3, ra, rz;      // XM stage of the next MMA3, A/G stage of the next MMA2, Z buffer of the next MMA2/3
+        auto issue_mma1 = [&]() {
             mbar_wait(bar(B_FULL_XK + rx1.s), rx1.ph);
             tc_fence_after();
-            const uint32_t zt = tmu + TM_Z0 + 64 * (gg & 1);
+            stamp(g1, 1);
+            ++g1;
+            const uint32_t zt = tmu + TM_Z0 + 64 * rz1.s;
             const uint64_t xh = umma_desc_k(XK + rx1.s * XK_BYTES), xl = umma_desc_k(XK + rx1.s * XK_BYTES + XH_BYTES);
 #pragma unroll
             for (int s = 0; s < 8; ++s) mma_ts(zt, tmu + TM_YH + 8 * s, kstep(xh, s, 8192), id_z, s > 0 ? 1u : 0u);
@@ -310,8 +333,9 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
                 for (int s = 0; s < 8; ++s) mma_ts(zt, tmu + TM_YH + 8 * s, kstep(xl, s, 8192), id_z, 1u);
             }
             tc_commit_elect(bar(B_EMPTY_XK + rx1.s));
-            tc_commit_elect(bar(B_Z_FULL + (gg & 1)));
+            tc_commit_elect(bar(B_Z_FULL + rz1.s));
             rx1.next(SX);
+            rz1.next(SZ);
         };
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
             int jt, it0, it1;
@@ -319,19 +343,26 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
             mbar_wait(bar(B_Y_READY), q & 1);
             mbar_wait(bar(B_DY_EMPTY), (q & 1) ^ 1);
             tc_fence_after();
-            issue_mma1(g);
+            // MMA1 runs two tiles ahead of the epilogue (three Z accumulators), never across an item boundary
+            issue_mma1();
+            if (it0 + 1 < it1) issue_mma1();
             for (int it = it0; it < it1; ++it, ++g) {
-                if (it + 1 < it1) issue_mma1(g + 1);
+                if (it + 2 < it1) issue_mma1();
                 const uint32_t b = g & 1, ph = (g >> 1) & 1;
-                mbar_wait(bar(B_G_READY + b), ph);
+                mbar_wait(bar(B_G_READY + rz.s), rz.ph);
+                stamp(g, 2);
                 mbar_wait(bar(B_DX_EMPTY + b), ph ^ 1);
                 tc_fence_after();
+                stamp(g, 3);
                 {
                     // MMA2 first (dX = G0' * Yh): its completion releases the A/G buffer for the TMA producer
                     const uint64_t gd = umma_desc_mn(AG + ra.s * AG_BYTES, 16384u), yd = umma_desc_mn(YS, 16384u);
                     const uint32_t dxt = tmu + TM_DX0 + 64 * b;
 #pragma unroll
-                    for (int s = 0; s < 16; ++s) mma_ss(dxt, gd + (uint64_t)(s * 64), yd + (uint64_t)(s * 64), id_dx, s > 0 ? 1u : 0u);
+                    for (int s = 0; s < 16; ++s) {
+                        if ((p.ablate & 1) && s > 0) break;
+                        mma_ss(dxt, gd + (uint64_t)(s * 64), yd + (uint64_t)(s * 64), id_dx, s > 0 ? 1u : 0u);
+                    }
                     tc_commit_elect(bar(B_EMPTY_AG + ra.s));
                     tc_commit_elect(bar(B_DX_FULL + b));
                     ra.next(SA);
@@ -340,56 +371,74 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
                     // MMA3: dY += G0 * Xh  (MN-major copy of the Xh tile)
                     mbar_wait(bar(B_FULL_XM + rx3.s), rx3.ph);
                     tc_fence_after();
-                    const uint32_t ga = tmu + TM_Z0 + 64 * b;
+                    stamp(g, 4);
+                    const uint32_t ga = tmu + TM_Z0 + 64 * rz.s;
                     const uint64_t xd = umma_desc_mn(XM + rx3.s * XM_BYTES, 8192u);
                     const uint32_t first = it > it0 ? 1u : 0u;
 #pragma unroll
-                    for (int s = 0; s < 8; ++s) mma_ts(tmu + TM_DY, ga + 8 * s, xd + (uint64_t)(s * 64), id_dy, s > 0 ? 1u : first);
+                    for (int s = 0; s < 8; ++s) {
+                        if ((p.ablate & 2) && s > 0) break;
+                        mma_ts(tmu + TM_DY, ga + 8 * s, xd + (uint64_t)(s * 64), id_dy, s > 0 ? 1u : first);
+                    }
                     tc_commit_elect(bar(B_EMPTY_XM + rx3.s));
                     rx3.next(SX);
+                    rz.next(SZ);
                 }
             }
             tc_commit_elect(bar(B_DY_FULL));
             ++q;
         }
+      }
+      __syncwarp();
     } else {
         // ================================ epilogue warps ===========================================
-        // warp (quarter, c16): TMEM lanes 32*quarter.., columns 16*c16.. of every 64-wide tile.  Four
-        // warps per scheduler hide the TMEM / shared-memory latencies of one another.
+        // Two groups of 8 warps work on alternating tiles, so that the load / compute / store-drain
+        // phases of one tile overlap those of the next.  Inside a tile a warp owns (TMEM lane quarter,
+        // 32-sample half): TMEM lanes 32*quarter.., columns 32*h32.. = one row of A box h32 per thread.
+        // Item prologue / flush (Y operands in, dY tile out) are spread over all 16 warps by 16-column chunk.
         const int quarter = warp & 3;
-        const int c16 = (warp - 2) >> 2;              // 0..3
+        const int c16 = (warp - NPRE) >> 2;           // 0..3
+        const int grp = c16 >> 1, h32 = c16 & 1;
         const int lrow = 32 * quarter + lane;         // feature row of the tile
         const uint32_t lane_addr = ((uint32_t)(32 * quarter)) << 16;
-        // this thread's four 16-byte chunks inside a 128-byte box row (A in, G0 out, Yh out): logical chunk
-        // c = 4*(c16&1) + v sits in 32-byte slot (c>>1) ^ (row&3), half c&1  (128B swizzle with 32-byte atoms)
-        uint32_t choff[4];
-#pragma unroll
-        for (int v = 0; v < 4; ++v)
-            choff[v] = (uint32_t)(lrow * 128 + ((((2 * (c16 & 1) + (v >> 1)) ^ (lane & 3)) << 5) | ((v & 1) << 4)));
-        const uint32_t boxoff = (uint32_t)(c16 >> 1) * 16384u;
+        // byte offset of logical 16-byte chunk c of this thread's 128-byte box row:
+        // 32-byte slot (c>>1) ^ (row&3), half c&1   (128B swizzle with 32-byte atoms)
+        auto chunk_off = [&](int c) { return (uint32_t)(lrow * 128 + ((((c >> 1) ^ (lane & 3)) << 5) | ((c & 1) << 4))); };
+        const uint32_t tile_box = (uint32_t)h32 * 16384u;
         uint32_t g = 0, q = 0;
-        Ring ra;
+        Ring ra, rz;
+        if (grp == 1) { ra.next(SA); rz.next(SZ); }
         double loss_d = 0.0;
-        // dX read-out (deferred by one tile).  M = 64 accumulator: sample row r sits in lane (r%16) + 32*(r/16)
+        // dX read-out of one of this group's tiles.  M = 64 accumulator: sample row r sits in lane (r%16) + 32*(r/16)
         auto dx_out = [&](uint32_t gg, int i0) {
             const uint32_t b = gg & 1;
+            const bool tr = quarter == 0 && h32 == 0 && lane == 0;
+            if (tr) stamp(gg, 10);
             mbar_wait(bar(B_DX_FULL + b), (gg >> 1) & 1);
             tc_fence_after();
-            uint32_t r[16];
-            TMEM_LD16(tm + lane_addr + TM_DX0 + 64 * b + 16 * c16, r);
+            if (tr) stamp(gg, 11);
+            uint32_t r0[16], r1[16];
+            TMEM_LD16(tm + lane_addr + TM_DX0 + 64 * b + 32 * h32, r0);
+            TMEM_LD16(tm + lane_addr + TM_DX0 + 64 * b + 32 * h32 + 16, r1);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             tc_fence_before();
             mbar_arrive(bar(B_DX_EMPTY + b));
             const int i = i0 + 16 * quarter + lane;
-            if (lane < 16 && i < dp.M) {
-                float* dst = dp.dX + (size_t)i * KK + 16 * c16;
+            if (lane < 16 && i < dp.M && !(p.ablate & 16)) {
+                float4* dst = reinterpret_cast<float4*>(dp.dX + (size_t)i * KK + 32 * h32);
 #pragma unroll
                 for (int v = 0; v < 4; ++v)
-                    atomicAdd(reinterpret_cast<float4*>(dst) + v,
-                              make_float4(__uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]),
-                                          __uint_as_float(r[4 * v + 2]), __uint_as_float(r[4 * v + 3])));
+                    atomicAdd(dst + v, make_float4(__uint_as_float(r0[4 * v]), __uint_as_float(r0[4 * v + 1]),
+                                                   __uint_as_float(r0[4 * v + 2]), __uint_as_float(r0[4 * v + 3])));
+#pragma unroll
+                for (int v = 0; v < 4; ++v)
+                    atomicAdd(dst + 4 + v, make_float4(__uint_as_float(r1[4 * v]), __uint_as_float(r1[4 * v + 1]),
+                                                       __uint_as_float(r1[4 * v + 2]), __uint_as_float(r1[4 * v + 3])));
             }
+            if (tr) stamp(gg, 12);
         };
+        int pend_i0 = -1;          // sample offset of this group's tile whose dX is still in TMEM
+        uint32_t pend_g = 0;
 
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
             int jt, it0, it1;
@@ -424,7 +473,7 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
                         hi[4 * v + c] = hb;
                         lo[4 * v + c] = __float_as_uint(ys[c] - __uint_as_float(hb));
                     }
-                    *reinterpret_cast<uint4*>(ys_ptr + boxoff + choff[v]) =
+                    *reinterpret_cast<uint4*>(ys_ptr + (uint32_t)(c16 >> 1) * 16384u + chunk_off(4 * (c16 & 1) + v)) =
                         make_uint4(rna_tf32(gscale * y4.x), rna_tf32(gscale * y4.y), rna_tf32(gscale * y4.z), rna_tf32(gscale * y4.w));
                 }
                 TMEM_ST16(tm + lane_addr + TM_YH + 16 * c16, hi);
@@ -435,24 +484,10 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
                 mbar_arrive(bar(B_Y_READY));
             }
 
-            for (int it = it0; it < it1; ++it, ++g, ra.next(SA)) {
-                const uint32_t b = g & 1, ph = (g >> 1) & 1;
-                mbar_wait(bar(B_Z_FULL + b), ph);
-                mbar_wait(bar(B_FULL_A + ra.s), ra.ph);
-                tc_fence_after();
-                const uint32_t zt = tm + lane_addr + TM_Z0 + 64 * b + 16 * c16;
-                uint8_t* abox = ag_ptr0 + ra.s * AG_BYTES + boxoff;
-                uint32_t z[16];
-                TMEM_LD16(zt, z);
-                float a[16];
-#pragma unroll
-                for (int v = 0; v < 4; ++v) {
-                    float4 a4 = *reinterpret_cast<const float4*>(abox + choff[v]);
-                    a[4 * v] = a4.x; a[4 * v + 1] = a4.y; a[4 * v + 2] = a4.z; a[4 * v + 3] = a4.w;
-                }
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            // per-entry math on 16 consecutive samples: z[] (TMEM columns) in, dloss/dz (TF32-rounded bits) out
+            auto epi16 = [&](uint32_t (&z)[16], const float (&a)[16]) {
                 // dmu_acc / loss_acc collect the unweighted sums; the column weight w_j (a per-thread
-                // constant) is applied at the item flush.  G0 = (w_j sigma_j) * dloss/dz.
+                // constant) is applied at the item flush.
                 if (dist == DIST_NORMAL) {
 #pragma unroll
                     for (int e = 0; e < 16; ++e) {
@@ -501,19 +536,51 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
                         z[e] = rn_bits(lg.y);
                     }
                 }
-                // dloss/dz back to TMEM in place of Z (A operand of MMA3) and over the A values this thread
-                // read (MN-major A operand of MMA2): same addresses, 128-bit stores, no transposition
-                TMEM_ST16(zt, z);
+            };
+
+            for (int it = it0; it < it1; ++it, ++g) {
+                if ((g & 1u) != (uint32_t)grp) continue;             // the other group's tile
+                const bool tr = quarter == 0 && h32 == 0 && lane == 0;
+                if (tr) stamp(g, 5);
+                mbar_wait(bar(B_Z_FULL + rz.s), rz.ph);
+                if (tr) stamp(g, 6);
+                mbar_wait(bar(B_FULL_A + ra.s), ra.ph);
+                tc_fence_after();
+                if (tr) stamp(g, 7);
+                const uint32_t zt = tm + lane_addr + TM_Z0 + 64 * rz.s + 32 * h32;
+                uint8_t* abox = ag_ptr0 + ra.s * AG_BYTES + tile_box;
+#pragma unroll 1
+                for (int hh = 0; hh < 2; ++hh) {
+                    uint32_t z[16];
+                    float a[16];
+                    TMEM_LD16(zt + 16 * hh, z);
 #pragma unroll
-                for (int v = 0; v < 4; ++v)
-                    *reinterpret_cast<uint4*>(abox + choff[v]) = make_uint4(z[4 * v], z[4 * v + 1], z[4 * v + 2], z[4 * v + 3]);
+                    for (int v = 0; v < 4; ++v) {
+                        float4 a4 = *reinterpret_cast<const float4*>(abox + chunk_off(4 * hh + v));
+                        a[4 * v] = a4.x; a[4 * v + 1] = a4.y; a[4 * v + 2] = a4.z; a[4 * v + 3] = a4.w;
+                    }
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (!(p.ablate & 8)) epi16(z, a);
+                    // dloss/dz back to TMEM in place of Z (A operand of MMA3) and over the A values this thread
+                    // read (MN-major A operand of MMA2): same addresses, 128-bit stores, no transposition
+                    TMEM_ST16(zt + 16 * hh, z);
+#pragma unroll
+                    for (int v = 0; v < 4; ++v)
+                        *reinterpret_cast<uint4*>(abox + chunk_off(4 * hh + v)) = make_uint4(z[4 * v], z[4 * v + 1], z[4 * v + 2], z[4 * v + 3]);
+                }
+                if (tr) stamp(g, 8);
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 tc_fence_before();
                 fence_async_smem();
-                mbar_arrive(bar(B_G_READY + b));
-                if (it > it0) dx_out(g - 1, (it - 1) * BI);
+                mbar_arrive(bar(B_G_READY + rz.s));
+                if (tr) stamp(g, 9);
+                ra.next(SA); ra.next(SA);
+                rz.next(SZ); rz.next(SZ);
+                if (pend_i0 >= 0) dx_out(pend_g, pend_i0);
+                pend_g = g; pend_i0 = it * BI;
             }
-            dx_out(g - 1, (it1 - 1) * BI);
+            // every dX tile of the item leaves TMEM before the item's accumulators are flushed
+            if (pend_i0 >= 0) { dx_out(pend_g, pend_i0); pend_i0 = -1; }
             loss_d += (double)(loss_acc * wj);
 
             // ---- item epilogue: dY tile out of TMEM, column sums --------------------------------------
@@ -550,9 +617,9 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
     }
     tc_fence_before();
     __syncthreads();
-    if (threadIdx.x == 64) {
+    if (threadIdx.x == 32 * NPRE) {
         double t = 0.0;
-        for (int w = 2; w < 2 + NEPI; ++w) t += red_smem[w];
+        for (int w = NPRE; w < NPRE + NEPI; ++w) t += red_smem[w];
         atomicAdd(dp.scalars + SC_DATA, t);
     }
     if (warp == 1) {
@@ -636,6 +703,21 @@ cudaError_t launch_data_pass_tc(const DataPassParams& dp, float* Xh, float* Xl, 
     p.n_jt = (dp.N + BJ - 1) / BJ;
     p.n_it = (dp.M + BI - 1) / BI;
     p.z_passes = precision >= 2 ? 1 : 3;
+    {
+        static const char* ab = getenv("PMF_TC_ABLATE");
+        p.ablate = ab ? atoi(ab) : 0;
+        if (p.ablate & 4) p.z_passes = 1;
+    }
+    p.trace = nullptr;
+    static const char* trace_path = getenv("PMF_TC_TRACE");
+    static long long* trace_dev = nullptr;
+    if (trace_path) {
+        if (!trace_dev) cudaMalloc(&trace_dev, sizeof(long long) * TRACE_TILES * TRACE_EV);
+        cudaMemsetAsync(trace_dev, 0, sizeof(long long) * TRACE_TILES * TRACE_EV, s);
+        p.trace = trace_dev;
+        const char* tc = getenv("PMF_TC_TRACE_CTA");
+        p.trace_cta = tc ? atoi(tc) : 0;
+    }
     // sample chunks: maximise the fill of the last wave, at least 4 tiles per chunk
     int best_c = 1;
     double best_eff = 0.0;
@@ -652,6 +734,12 @@ cudaError_t launch_data_pass_tc(const DataPassParams& dp, float* Xh, float* Xl, 
     if (e != cudaSuccess) return e;
     int grid = p.n_items < n_sms ? p.n_items : n_sms;
     data_pass_tc_kernel<<<grid, NTHREADS, SMEM_TOTAL, s>>>(tmXh, tmXl, tmXm, tmA, p);
+    if (trace_path) {      // experiments only: dump the stamps of this launch (synchronises the stream)
+        static long long host[TRACE_TILES * TRACE_EV];
+        cudaStreamSynchronize(s);
+        cudaMemcpy(host, trace_dev, sizeof host, cudaMemcpyDeviceToHost);
+        if (FILE* f = fopen(trace_path, "wb")) { fwrite(host, sizeof host, 1, f); fclose(f); }
+    }
     return cudaGetLastError();
 }
 

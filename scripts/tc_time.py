@@ -1,0 +1,20 @@
+"""Time the tcgen05 data pass alone at the C2 shape (CUDA events inside libpmf); PMF_TC_ABLATE for experiments."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import pathmatfac_b200 as P
+from pathmatfac_b200 import _lib
+from pathmatfac_b200.simulate import C2_BLOCKS, scale_blocks, simulate_problem
+M, N = 10000, 30000
+prec = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+model = simulate_problem(M, blocks=scale_blocks(C2_BLOCKS, N), K=64, seed=5, missing=0.3, model_kwargs=dict(lambda_X_l2=1.0))
+eng = P.Engine(model)
+eng.set_loss_grad_kernel(_lib.KERNEL_TC, prec)
+for _ in range(3):
+    eng.loss_grad(include_reg=False)
+eng.set_profiling(True)
+for _ in range(10):
+    eng.loss_grad(include_reg=False)
+n, mean_ms, min_ms = eng.get_profile()
+print(f"ablate={os.environ.get('PMF_TC_ABLATE','0')} prec={prec}: n={n} mean {mean_ms:.4f} ms min {min_ms:.4f} ms", flush=True)
+eng.close()

@@ -1,0 +1,24 @@
+"""Decode gpurun_out/tc_trace.bin (PMF_TC_TRACE): per-tile event times of CTA 0, in cycles relative to the first stamp."""
+import sys
+import numpy as np
+EV = ["tmaA_issue", "M1_issue", "G_seen", "M2_issue", "M3_issue", "epi_top", "Z_seen", "A_seen", "epi_done", "G_arrived",
+      "dx_begin", "DXFULL_seen", "dx_end"]
+a = np.fromfile(sys.argv[1], dtype=np.int64).reshape(-1, 16)
+t0 = a[a > 0].min()
+lo, hi = (int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv) > 3 else (20, 44)
+print("tile " + " ".join(f"{e:>11}" for e in EV))
+for g in range(lo, hi):
+    print(f"{g:4d} " + " ".join(f"{(a[g, i] - t0) if a[g, i] > 0 else -1:11d}" for i in range(len(EV))))
+d = a[lo:hi]
+print("per-tile period (G_arrived):", np.diff(d[:, 9]).mean())
+for name, x, y in [("A wait (A_seen - Z_seen)", 7, 6), ("Z wait (Z_seen - epi_top)", 6, 5), ("epi body (epi_done - A_seen)", 8, 7),
+                   ("drain+arrive (G_arrived - epi_done)", 9, 8), ("MMA sees G (G_seen - G_arrived)", 2, 9),
+                   ("M2 issue after G_seen", 3, 2), ("M3 issue after M2", 4, 3), ("DXFULL wait", 11, 10), ("dx_out body", 12, 11),
+                   ("TMA A issue(g+3) - M2_issue(g)", None, None)]:
+    if x is None:
+        v = a[lo + 3:hi + 3, 0] - a[lo:hi, 3]
+    else:
+        v = d[:, x] - d[:, y]
+    print(f"{name:40s} mean {v.mean():9.1f}  min {v.min():7d}  max {v.max():7d}")
+v = a[lo + 3:hi + 3, 7] - a[lo + 3:hi + 3, 0]
+print(f"{'A_seen(g) - tmaA_issue(g)':40s} mean {v.mean():9.1f}  min {v.min():7d}  max {v.max():7d}")
