@@ -30,8 +30,8 @@ UNIT = "iter/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--kernel", default="auto", choices=["auto", "ffma", "tc"])
     ap.add_argument("--precision", type=int, default=0)
@@ -52,7 +52,11 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """SM clock / throttle reasons sampled DURING the timed region.  In-process NVML (pynvml, ~0.1 ms per
+    query) so that short timed regions still get many samples and no external process holds the driver
+    while the benchmark allocates; falls back to one `nvidia-smi` query per sample."""
+    REASONS = (("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40),
+               ("hw_power_brake_slowdown", 0x80), ("sw_power_cap", 0x4))
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -60,34 +64,75 @@ class ClockSampler(threading.Thread):
     def __init__(self, index=0):
         super().__init__(daemon=True)
         self.index = index
-        self.rows = []
+        self.sm, self.power, self.reasons = [], [], set()
+        self.sm_max = None
         self.stop_flag = False
+        self.source = "nvml"
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(index))
+            self.sm_max = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+            self.source = "nvidia-smi"
+
+    @staticmethod
+    def _physical_index(local):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if local < len(ids) and ids[local].isdigit():
+                return int(ids[local])
+        return local
+
+    def _sample_nvml(self):
+        nv = self.nv
+        self.sm.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+        try:
+            self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+        except Exception:
+            pass
+        try:
+            get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            mask = int(get(self.h))
+            for name, bit in self.REASONS:
+                if mask & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                              "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+        for line in out.strip().splitlines():
+            r = [x.strip() for x in line.split(",")]
+            if len(r) >= 8 and r[1].replace(".", "").isdigit():
+                self.sm.append(int(float(r[1])))
+                self.sm_max = int(float(r[2]))
+                for n, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[4:8]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(n)
 
     def run(self):
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
-                for line in out.strip().splitlines():
-                    self.rows.append([x.strip() for x in line.split(",")])
+                if self.nv is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.002 if self.nv is not None else 0.1)
 
     def summary(self):
         self.stop_flag = True
-        self.join(timeout=6)
-        sm = sorted(int(float(r[1])) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit())
-        mx = [int(float(r[2])) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
-        reasons = set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            if len(r) >= 8:
-                for n, v in zip(names, r[4:8]):
-                    if v.lower().startswith("active"):
-                        reasons.add(n)
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        self.join(timeout=10)
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_min_mhz": sm[0] if sm else None,
+                "sm_max_mhz": self.sm_max, "power_w_max": max(self.power) if self.power else None,
+                "reasons": sorted(self.reasons), "samples": len(sm), "source": self.source}
 
 
 def to_oracle(model, rows, dtype):

@@ -43,17 +43,23 @@ namespace {
 
 constexpr int BJ = 128, BI = 64, KK = 64;
 constexpr int NEPI = 16;                  // epilogue warps: 2 groups x (TMEM lane quarter, 32-column half)
-constexpr int NPRE = 4;                   // warp 0 TMA A, warp 1 MMA, warp 2 TMA XK, warp 3 TMA XM
+constexpr int NPRE = 5;                   // warp 0 TMA A, 1 MMA, 2 TMA XK, 3 TMA XM, 4 dX reduce-add issuer
 constexpr int NTHREADS = 32 * (NPRE + NEPI);
-constexpr int SX = 2, SA = 3;             // pipeline depth of the X streams and of the A/G stream
-constexpr uint32_t XH_BYTES = 16384, XK_BYTES = 32768 /* Xh | Xl */, XM_BYTES = 16384, YS_BYTES = 32768, AG_BYTES = 32768;
-constexpr uint32_t SMEM_DATA = SX * XK_BYTES + SX * XM_BYTES + YS_BYTES + SA * AG_BYTES;
-constexpr uint32_t SMEM_TOTAL = SMEM_DATA + 1024 /*align slack*/ + 256 /*barriers*/;
+// Pipeline depths.  The X operands come from L2 and are re-loaded while the tensor pipe works on the other
+// contractions of the neighbouring tiles, so one stage each suffices; the A/G ring is the HBM stream and
+// stays occupied from the TMA issue until MMA2 has consumed G0, so it gets every byte that is left.
+constexpr int SXK = 2, SXM = 1, SA = 3;
 constexpr int SZ = 3;                     // Z / G0 accumulators in TMEM
+constexpr uint32_t XH_BYTES = 16384, XK_BYTES = 32768 /* Xh | Xl */, XM_BYTES = 16384, YS_BYTES = 32768, AG_BYTES = 32768,
+                   DXS_BYTES = 16384 /* dX tile staged for the TMA reduce-add */;
+constexpr uint32_t SMEM_DATA = SXK * XK_BYTES + SXM * XM_BYTES + YS_BYTES + SA * AG_BYTES + DXS_BYTES;
+constexpr uint32_t SMEM_TOTAL = SMEM_DATA + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr uint32_t TM_YH = 0, TM_YL = 64, TM_Z0 = 128, TM_DY = 320, TM_DX0 = 384;   // Z_b = Z0+64b, dX1 = dX0+64
 
-enum Bar { B_FULL_XK = 0, B_EMPTY_XK = 2, B_FULL_XM = 4, B_EMPTY_XM = 6, B_FULL_A = 8, B_EMPTY_AG = 11, B_Z_FULL = 14,
-           B_G_READY = 17, B_DX_FULL = 20, B_DX_EMPTY = 22, B_Y_READY = 24, B_DY_FULL, B_DY_EMPTY, B_COUNT };
+enum Bar { B_FULL_XK = 0, B_EMPTY_XK = B_FULL_XK + SXK, B_FULL_XM = B_EMPTY_XK + SXK, B_EMPTY_XM = B_FULL_XM + SXM,
+           B_FULL_A = B_EMPTY_XM + SXM, B_EMPTY_AG = B_FULL_A + SA, B_Z_FULL = B_EMPTY_AG + SA, B_G_READY = B_Z_FULL + SZ,
+           B_DX_FULL = B_G_READY + SZ, B_DX_EMPTY = B_DX_FULL + 2, B_Y_READY = B_DX_EMPTY + 2, B_DY_FULL, B_DY_EMPTY,
+           B_DXS_FULL, B_DXS_DONE /* one per group */, B_COUNT = B_DXS_DONE + 2 };
 
 // ---- PTX wrappers --------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -81,6 +87,11 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+// shared -> global tile, element-wise f32 add performed by the memory system (bulk async-group completion)
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -220,16 +231,18 @@ struct Ring {
 
 __global__ void __launch_bounds__(NTHREADS, 1)
 data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUtensorMap tmXl,
-                    const __grid_constant__ CUtensorMap tmXm, const __grid_constant__ CUtensorMap tmA, const TcParams p) {
+                    const __grid_constant__ CUtensorMap tmXm, const __grid_constant__ CUtensorMap tmA,
+                    const __grid_constant__ CUtensorMap tmDX, const TcParams p) {
     const DataPassParams& dp = p.dp;
     if (dp.stop_flag != nullptr && *dp.stop_flag != 0) return;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
-    const uint32_t XK = base, XM = XK + SX * XK_BYTES, YS = XM + SX * XM_BYTES, AG = YS + YS_BYTES;
+    const uint32_t XK = base, XM = XK + SXK * XK_BYTES, YS = XM + SXM * XM_BYTES, AG = YS + YS_BYTES, DXS = AG + SA * AG_BYTES;
     const uint32_t BARS = base + SMEM_DATA;
     uint8_t* ys_ptr = gbase + (YS - base);
     uint8_t* ag_ptr0 = gbase + (AG - base);
+    uint8_t* dxs_ptr = gbase + (DXS - base);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + SMEM_DATA + 8 * B_COUNT);
     __shared__ double red_smem[NTHREADS / 32];
     auto bar = [&](int b) { return BARS + 8u * (uint32_t)b; };
@@ -247,7 +260,7 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
         for (int b = 0; b < B_COUNT; ++b) {
             uint32_t cnt = 1u;
             if (b == B_Y_READY || b == B_DY_EMPTY) cnt = 32u * NEPI;                       // every epilogue thread
-            if ((b >= B_G_READY && b < B_G_READY + SZ) || b == B_DX_EMPTY || b == B_DX_EMPTY + 1)
+            if ((b >= B_G_READY && b < B_G_READY + SZ) || b == B_DX_EMPTY || b == B_DX_EMPTY + 1 || b == B_DXS_FULL)
                 cnt = 16u * NEPI;                                                         // one epilogue group
             mbar_init(bar(b), cnt);
         }
@@ -270,7 +283,7 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
         if (lane == 0) {
             Ring r;
             uint32_t gcount = 0;
-            const uint32_t depth = warp == 0 ? SA : SX;
+            const uint32_t depth = warp == 0 ? SA : (warp == 2 ? SXK : SXM);
             for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
                 int jt, it0, it1;
                 item_range(p, item, jt, it0, it1);
@@ -301,6 +314,30 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
                 }
             }
         }
+    } else if (warp == 4) {
+        // ================================ dX reduce-add issuer =====================================
+        // The epilogue groups stage each dX tile in shared memory; this thread turns it into ONE TMA
+        // reduce-add per 32-column box and waits for the engine to have read the staging buffer, so no
+        // epilogue warp ever blocks on the memory system.
+        if (lane == 0) {
+            uint32_t g = 0;
+            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+                int jt, it0, it1;
+                item_range(p, item, jt, it0, it1);
+                for (int it = it0; it < it1; ++it, ++g) {
+                    mbar_wait(bar(B_DXS_FULL), g & 1);
+                    if (!(p.ablate & 16)) {
+                        tma_reduce_add_2d(&tmDX, DXS, 0, it * BI);
+                        tma_reduce_add_2d(&tmDX, DXS + 8192, 32, it * BI);
+                    }
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    mbar_arrive(bar(B_DXS_DONE + (g & 1)));
+                    stamp(g, 12);
+                }
+            }
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // every reduce-add has been performed
+        }
     } else if (warp == 1) {
       if (elect_one()) {
         // ================================ MMA issuer ===============================================
@@ -318,6 +355,7 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
         Ring rx1, rz1;         // XK stage / Z buffer of the next MMA1
         Ring rx3, ra, rz;      // XM stage of the next MMA3, A/G stage of the next MMA2, Z buffer of the next MMA2/3
         auto issue_mma1 = [&]() {
+            stamp(g1, 13);
             mbar_wait(bar(B_FULL_XK + rx1.s), rx1.ph);
             tc_fence_after();
             stamp(g1, 1);
@@ -334,7 +372,8 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
             }
             tc_commit_elect(bar(B_EMPTY_XK + rx1.s));
             tc_commit_elect(bar(B_Z_FULL + rz1.s));
-            rx1.next(SX);
+            stamp(g1 - 1, 14);
+            rx1.next(SXK);
             rz1.next(SZ);
         };
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
@@ -381,7 +420,8 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
                         mma_ts(tmu + TM_DY, ga + 8 * s, xd + (uint64_t)(s * 64), id_dy, s > 0 ? 1u : first);
                     }
                     tc_commit_elect(bar(B_EMPTY_XM + rx3.s));
-                    rx3.next(SX);
+                    stamp(g, 15);
+                    rx3.next(SXM);
                     rz.next(SZ);
                 }
             }
@@ -409,7 +449,12 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
         Ring ra, rz;
         if (grp == 1) { ra.next(SA); rz.next(SZ); }
         double loss_d = 0.0;
-        // dX read-out of one of this group's tiles.  M = 64 accumulator: sample row r sits in lane (r%16) + 32*(r/16)
+        // dX tile of one of this group's tiles: TMEM -> registers -> swizzled staging buffer, from where warp 4
+        // issues a TMA reduce-add into global dX (the L2 does the additions on full lines; no per-lane REDs
+        // through the LSU).
+        // M = 64 accumulator: sample row r sits in lane (r%16) + 32*(r/16).  The staging buffer is shared by the
+        // two groups: flush(g) waits until the TMA reads of flush(g-1) (other group) and flush(g-2) (own group,
+        // whose issuing thread may lag behind) are over.  Each group counts its flushes on its own barrier.
         auto dx_out = [&](uint32_t gg, int i0) {
             const uint32_t b = gg & 1;
             const bool tr = quarter == 0 && h32 == 0 && lane == 0;
@@ -423,19 +468,22 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             tc_fence_before();
             mbar_arrive(bar(B_DX_EMPTY + b));
-            const int i = i0 + 16 * quarter + lane;
-            if (lane < 16 && i < dp.M && !(p.ablate & 16)) {
-                float4* dst = reinterpret_cast<float4*>(dp.dX + (size_t)i * KK + 32 * h32);
-#pragma unroll
-                for (int v = 0; v < 4; ++v)
-                    atomicAdd(dst + v, make_float4(__uint_as_float(r0[4 * v]), __uint_as_float(r0[4 * v + 1]),
-                                                   __uint_as_float(r0[4 * v + 2]), __uint_as_float(r0[4 * v + 3])));
-#pragma unroll
-                for (int v = 0; v < 4; ++v)
-                    atomicAdd(dst + 4 + v, make_float4(__uint_as_float(r1[4 * v]), __uint_as_float(r1[4 * v + 1]),
-                                                       __uint_as_float(r1[4 * v + 2]), __uint_as_float(r1[4 * v + 3])));
+            {
+                const uint32_t n_other = grp == 0 ? (gg >> 1) : ((gg + 1) >> 1), n_own = gg >> 1;   // flushes before tile gg
+                mbar_wait(bar(B_DXS_DONE + (grp ^ 1)), (n_other - 1u) & 1u);     // n == 0: parity 1 passes on a fresh barrier
+                mbar_wait(bar(B_DXS_DONE + grp), (n_own - 1u) & 1u);
             }
-            if (tr) stamp(gg, 12);
+            if (lane < 16 && !(p.ablate & 16)) {
+                const int r = 16 * quarter + lane;                       // sample row of the tile
+                uint8_t* row = dxs_ptr + h32 * 8192 + r * 128;
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    *reinterpret_cast<uint4*>(row + ((v ^ (r & 7)) << 4)) = make_uint4(r0[4 * v], r0[4 * v + 1], r0[4 * v + 2], r0[4 * v + 3]);
+                    *reinterpret_cast<uint4*>(row + (((4 + v) ^ (r & 7)) << 4)) = make_uint4(r1[4 * v], r1[4 * v + 1], r1[4 * v + 2], r1[4 * v + 3]);
+                }
+            }
+            fence_async_smem();
+            mbar_arrive(bar(B_DXS_FULL));
         };
         int pend_i0 = -1;          // sample offset of this group's tile whose dX is still in TMEM
         uint32_t pend_g = 0;
@@ -693,9 +741,10 @@ cudaError_t launch_data_pass_tc(const DataPassParams& dp, float* Xh, float* Xl, 
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
 
-    CUtensorMap tmXh, tmXl, tmXm, tmA;
+    CUtensorMap tmXh, tmXl, tmXm, tmA, tmDX;
     bool ok = make_map(&tmXh, Xh, KK, dp.Mp, KK, 64, false, false) && make_map(&tmXl, Xl, KK, dp.Mp, KK, 64, false, false) &&
-              make_map(&tmXm, Xh, KK, dp.Mp, KK, 64, false, true) && make_map(&tmA, dp.A, dp.lda, dp.N, dp.lda, 128, true, true);
+              make_map(&tmXm, Xh, KK, dp.Mp, KK, 64, false, true) && make_map(&tmA, dp.A, dp.lda, dp.N, dp.lda, 128, true, true) &&
+              make_map(&tmDX, dp.dX, KK, dp.Mp, KK, 64, false, false);
     if (!ok) return cudaErrorUnknown;
 
     TcParams p;
@@ -733,7 +782,7 @@ cudaError_t launch_data_pass_tc(const DataPassParams& dp, float* Xh, float* Xl, 
     e = cudaFuncSetAttribute(data_pass_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TOTAL);
     if (e != cudaSuccess) return e;
     int grid = p.n_items < n_sms ? p.n_items : n_sms;
-    data_pass_tc_kernel<<<grid, NTHREADS, SMEM_TOTAL, s>>>(tmXh, tmXl, tmXm, tmA, p);
+    data_pass_tc_kernel<<<grid, NTHREADS, SMEM_TOTAL, s>>>(tmXh, tmXl, tmXm, tmA, tmDX, p);
     if (trace_path) {      // experiments only: dump the stamps of this launch (synchronises the stream)
         static long long host[TRACE_TILES * TRACE_EV];
         cudaStreamSynchronize(s);

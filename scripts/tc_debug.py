@@ -28,3 +28,5 @@ for k in ("dY", "dX"):
         rn = r / (np.linalg.norm(r, axis=0, keepdims=True) + 1e-30)
         C = gn.T @ rn
         print(" col of got best matches ref col:", np.argmax(np.abs(C), axis=1)[:24], np.max(np.abs(C), axis=1)[:8])
+err = np.linalg.norm(got["dX"] - ref["dX"], axis=0) / (np.linalg.norm(ref["dX"], axis=0) + 1e-30)
+print("per-sample relerr by 16-sample block:", [f"{err[i:i+16].max():.1e}" for i in range(0, M, 16)])

@@ -2,7 +2,7 @@
 import sys
 import numpy as np
 EV = ["tmaA_issue", "M1_issue", "G_seen", "M2_issue", "M3_issue", "epi_top", "Z_seen", "A_seen", "epi_done", "G_arrived",
-      "dx_begin", "DXFULL_seen", "dx_end"]
+      "dx_begin", "DXFULL_seen", "dx_end", "M1_top", "M1_issued", "M3_issued"]
 a = np.fromfile(sys.argv[1], dtype=np.int64).reshape(-1, 16)
 t0 = a[a > 0].min()
 lo, hi = (int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv) > 3 else (20, 44)
@@ -19,6 +19,10 @@ for name, x, y in [("A wait (A_seen - Z_seen)", 7, 6), ("Z wait (Z_seen - epi_to
         v = a[lo + 3:hi + 3, 0] - a[lo:hi, 3]
     else:
         v = d[:, x] - d[:, y]
+    print(f"{name:40s} mean {v.mean():9.1f}  min {v.min():7d}  max {v.max():7d}")
+for name, x, y in [("M1: XK wait (M1_issue - M1_top)", 1, 13), ("M1: 24 MMAs issue (M1_issued - M1_issue)", 14, 1),
+                   ("M3: 8 MMAs issue (M3_issued - M3_issue)", 15, 4), ("M2 16 MMAs+XM wait (M3_issue - M2_issue)", 4, 3)]:
+    v = d[:, x] - d[:, y]
     print(f"{name:40s} mean {v.mean():9.1f}  min {v.min():7d}  max {v.max():7d}")
 v = a[lo + 3:hi + 3, 7] - a[lo + 3:hi + 3, 0]
 print(f"{'A_seen(g) - tmaA_issue(g)':40s} mean {v.mean():9.1f}  min {v.min():7d}  max {v.max():7d}")
