@@ -19,5 +19,5 @@ eng.set_profiling(True)
 for _ in range(10):
     eng.loss_grad(include_reg=False)
 n, mean_ms, min_ms = eng.get_profile()
-print(f"blocks={os.environ.get('PMF_BLOCKS','C2')} ablate={os.environ.get('PMF_TC_ABLATE','0')} prec={prec}: n={n} mean {mean_ms:.4f} ms min {min_ms:.4f} ms", flush=True)
+print(f"flags={os.environ.get('PMF_TC_FLAGS','0')} blocks={os.environ.get('PMF_BLOCKS','C2')} ablate={os.environ.get('PMF_TC_ABLATE','0')} prec={prec}: n={n} mean {mean_ms:.4f} ms min {min_ms:.4f} ms", flush=True)
 eng.close()
