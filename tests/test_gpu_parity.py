@@ -329,3 +329,46 @@ def test_tc_benchmark_shape_properties():
     assert abs(parts[0]["loss"] + parts[1]["loss"] - got["loss"]) <= 1e-6 * abs(got["loss"])
     assert relerr(parts[0]["dY"] + parts[1]["dY"], got["dY"]) < 2e-5
     assert relerr(np.concatenate([parts[0]["dX"], parts[1]["dX"]], axis=1), got["dX"]) < 2e-5
+
+
+@pytest.mark.parametrize("M,N", [(64, 128), (65, 130), (50, 1), (1, 300), (200, 700), (130, 1300), (3000, 140)])
+def test_tc_tile_bookkeeping_shapes(M, N):
+    """Shapes that stress the tcgen05 kernel's tile bookkeeping: a single tile, one sample / one
+    feature, work items of one or two sample tiles (the two epilogue groups alternate tiles and
+    share the dX staging buffer), many tiles per item, items that end on an odd tile."""
+    n1 = max(1, N // 3)
+    views = {"mutation": ("bernoulli", n1), "methylation": ("normal", max(1, N - 2 * n1)), "counts": ("poisson", n1)} \
+        if N >= 3 else {"methylation": ("normal", N)}
+    model, om, D = make_pair(M, views, K=64, seed=100 + M + N, missing=0.25, lambda_X_l2=1.0)
+    eng = P.Engine(model)
+    try:
+        eng.set_loss_grad_kernel(_lib.KERNEL_TC, 0)
+        got = eng.loss_grad(include_reg=False)
+        again = eng.loss_grad(include_reg=False)
+    finally:
+        eng.close()
+    ref = O.data_loss_grads(om, D)
+    assert abs(got["loss"] - ref["loss"]) <= 1e-5 * abs(ref["loss"])
+    for k in ("dmu", "dlogsigma"):
+        assert relerr(got[k], ref[k]) < 1e-4, (k, relerr(got[k], ref[k]))
+    for k in ("dX", "dY"):          # single-pass TF32 contractions: little averaging at these sizes
+        assert relerr(got[k], ref[k]) < 1e-3, (k, relerr(got[k], ref[k]))
+        assert relerr(again[k], got[k]) < 1e-5
+    assert got["dX"].shape == (64, M) and np.isfinite(got["dX"]).all() and np.isfinite(got["dY"]).all()
+
+
+def test_tc_ordinal_and_hinge_columns():
+    """The rare noise models take the out-of-line path of the tcgen05 epilogue."""
+    views = {"mutation": ("bernoulli_sq_hinge", 70), "mrnaseq": ("normal", 150), "cna": ("ordinal3", 60),
+             "methylation": ("ordinal_sq_hinge3", 40)}
+    model, om, D = make_pair(700, views, K=64, seed=41, missing=0.2, lambda_X_l2=1.0)
+    eng = P.Engine(model)
+    try:
+        eng.set_loss_grad_kernel(_lib.KERNEL_TC, 0)
+        got = eng.loss_grad(include_reg=False)
+    finally:
+        eng.close()
+    ref = O.data_loss_grads(om, D)
+    assert abs(got["loss"] - ref["loss"]) <= 1e-5 * abs(ref["loss"])
+    assert relerr(got["dmu"], ref["dmu"]) < 1e-4 and relerr(got["dlogsigma"], ref["dlogsigma"]) < 1e-4
+    assert relerr(got["dY"], ref["dY"]) < 5e-4 and relerr(got["dX"], ref["dX"]) < 5e-4
