@@ -207,7 +207,7 @@ def main():
     import torch
     import pathmatfac_b200 as P
     from pathmatfac_b200 import _lib
-    from pathmatfac_b200.dist import ShardedFit
+    from pathmatfac_b200.dist import NcclFit
     from pathmatfac_b200.simulate import C2_BLOCKS, scale_blocks, simulate_problem
 
     rank = int(os.environ.get("RANK", "0"))
@@ -246,7 +246,7 @@ def main():
             return sharded.fit(o)
         return eng.fit(o)
 
-    sharded = ShardedFit(eng) if world > 1 else None
+    sharded = NcclFit(eng) if world > 1 else None   # ncclAllReduce issued inside pmf_fit
     eng.reset_opt_state(1e-8)
     # ---- warm-up ---------------------------------------------------------------------------------
     run_epochs(1, args.warmup)
@@ -261,9 +261,11 @@ def main():
     eng.set_profiling(True)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     stream = torch.cuda.current_stream()
-    if world == 1:
-        eng.set_stream(stream.cuda_stream)
+    eng.set_stream(stream.cuda_stream)      # the library (kernels + its ncclAllReduce) runs on the timed stream
     torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
     ev0.record(stream)
     h = run_epochs(args.warmup + 1, args.warmup + args.steps)
     ev1.record(stream)

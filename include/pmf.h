@@ -234,6 +234,18 @@ int pmf_fsard_update_A(pmf_handle h, int32_t col_start, int32_t col_stop, int32_
                        float atol, double* best_loss, int32_t* epochs_run);
 int pmf_get_fsard_beta(pmf_handle h, float* beta_host /* K x N */);
 
+/* ---- sample-sharded multi-GPU (one process per GPU) -----------------------------
+ * The path has one exchange step per epoch: the sum over ranks of the shared gradient buffer
+ * [dY | dlogsigma | dmu | dlogdelta | dtheta] and of the rank-local loss scalars.  With a
+ * communicator attached, pmf_fit issues it itself (ncclAllReduce on the handle's stream, between
+ * the data pass and the update), so the epoch loop never returns to the host.  NCCL is loaded
+ * with dlopen("libnccl.so.2") on first use; single-GPU callers do not need it.
+ * pmf_comm_unique_id: rank 0 creates the 128-byte ncclUniqueId, the host language broadcasts it
+ * (MPI / torch.distributed / Distributed.jl), every rank calls pmf_comm_init_rank. */
+int pmf_comm_unique_id(uint8_t id_out[128]);
+int pmf_comm_init_rank(pmf_handle h, int32_t n_ranks, int32_t rank, const uint8_t id[128]);
+int pmf_comm_destroy(pmf_handle h);
+
 /* Next-tier O(MN) passes of the staging code that reuse the tile kernel:
  * per-column sum_i (dl/dz)^2 (MF.batched_column_ssq_grads, src/fit.jl:166) and per-column
  * count of finite entries (MF.column_nonnan, src/fit.jl:140). */

@@ -101,6 +101,9 @@ SIGNATURES = {
     "pmf_set_loss_grad_kernel": (C.c_int, [H, C.c_int32, C.c_int32]),
     "pmf_set_profiling": (C.c_int, [H, C.c_int32]),
     "pmf_get_profile": (C.c_int, [H, c_int32_p, c_float_p, c_float_p]),
+    "pmf_comm_unique_id": (C.c_int, [C.POINTER(C.c_uint8)]),
+    "pmf_comm_init_rank": (C.c_int, [H, C.c_int32, C.c_int32, C.POINTER(C.c_uint8)]),
+    "pmf_comm_destroy": (C.c_int, [H]),
 }
 
 _lib = None

@@ -4,6 +4,8 @@
 #include "pmf_internal.h"
 #include "pmf_host.h"
 
+#include <dlfcn.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
@@ -68,6 +70,43 @@ static cudaError_t up2d(float* dst, int wd, const float* src, int w, int rows, c
 static cudaError_t down2d(float* dst, int w, const float* src, int wd, int rows, cudaStream_t s) {
     return cudaMemcpy2DAsync(dst, (size_t)w * 4, src, (size_t)wd * 4, (size_t)w * 4, rows, cudaMemcpyDeviceToHost, s);
 }
+
+// ---- NCCL through dlopen ------------------------------------------------------------------------
+// Only the five entry points of the exchange step; types restated from nccl.h (ABI-stable since 2.x).
+struct Id128 { char bytes[128]; };   // ncclUniqueId (passed by value)
+namespace {
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(void**, int, Id128, int) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+};
+NcclApi& nccl() {
+    static NcclApi api;
+    if (!api.lib) {
+        api.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!api.lib) api.lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (api.lib) {
+            api.GetUniqueId = reinterpret_cast<int (*)(void*)>(dlsym(api.lib, "ncclGetUniqueId"));
+            api.CommInitRank = reinterpret_cast<int (*)(void**, int, Id128, int)>(dlsym(api.lib, "ncclCommInitRank"));
+            api.AllReduce = reinterpret_cast<int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t)>(dlsym(api.lib, "ncclAllReduce"));
+            api.CommDestroy = reinterpret_cast<int (*)(void*)>(dlsym(api.lib, "ncclCommDestroy"));
+            api.GetErrorString = reinterpret_cast<const char* (*)(int)>(dlsym(api.lib, "ncclGetErrorString"));
+            api.GroupStart = reinterpret_cast<int (*)()>(dlsym(api.lib, "ncclGroupStart"));
+            api.GroupEnd = reinterpret_cast<int (*)()>(dlsym(api.lib, "ncclGroupEnd"));
+        }
+    }
+    return api;
+}
+bool nccl_ok(const NcclApi& a) {
+    return a.lib && a.GetUniqueId && a.CommInitRank && a.AllReduce && a.CommDestroy && a.GroupStart && a.GroupEnd;
+}
+constexpr int NCCL_FLOAT32 = 7, NCCL_FLOAT64 = 8, NCCL_SUM = 0;   // ncclDataType_t / ncclRedOp_t (nccl.h)
+}  // namespace
 
 extern "C" {
 
@@ -141,6 +180,7 @@ int pmf_destroy(pmf_handle h) {
     dev_free(h->bcol_off); dev_free(h->bcol_view); dev_free(h->bcol_nb); dev_free(h->batch_of_sample);
     dev_free(h->hist); dev_free(h->col_ssq); dev_free(h->col_cnt);
     for (int s = 0; s < 2; ++s) h->reg[s].free_all();
+    if (h->comm) { nccl().CommDestroy(h->comm); h->comm = nullptr; }
     if (h->ctrl_host) cudaFreeHost(h->ctrl_host);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -772,6 +812,7 @@ int pmf_fit(pmf_handle h, const pmf_fit_opts* o, pmf_history* out) {
     int since = 0;
     for (int e = o->epoch; e <= o->max_epochs; ++e) {
         if ((rc = pmf_epoch_begin(h, o)) != 0) return rc;
+        if ((rc = h->exchange_gradients()) != 0) return rc;     // no-op without a communicator
         if ((rc = pmf_epoch_end(h, o)) != 0) return rc;
         if (++since >= check && e < o->max_epochs) {
             since = 0;
@@ -790,6 +831,55 @@ int pmf_fit(pmf_handle h, const pmf_fit_opts* o, pmf_history* out) {
     rc = pmf_fit_poll(h, dst, nullptr);
     dst->device_ms = ms;
     return rc;
+}
+
+int pmf_comm_unique_id(uint8_t id_out[128]) {
+    NcclApi& a = nccl();
+    if (!nccl_ok(a)) return fail(nullptr, PMF_ERR_STATE, "libnccl.so.2 could not be loaded: %s", dlerror());
+    if (!id_out) return fail(nullptr, PMF_ERR_ARG, "null id buffer");
+    int rc = a.GetUniqueId(id_out);
+    if (rc != 0) return fail(nullptr, PMF_ERR_CUDA, "ncclGetUniqueId: %s", a.GetErrorString ? a.GetErrorString(rc) : "?");
+    return PMF_OK;
+}
+
+int pmf_comm_init_rank(pmf_handle h, int32_t n_ranks, int32_t rank, const uint8_t id[128]) {
+    CHECK_H(h);
+    NcclApi& a = nccl();
+    if (!nccl_ok(a)) return fail(h, PMF_ERR_STATE, "libnccl.so.2 could not be loaded");
+    if (n_ranks < 1 || rank < 0 || rank >= n_ranks || !id) return fail(h, PMF_ERR_ARG, "bad communicator arguments");
+    if (h->comm) pmf_comm_destroy(h);
+    Id128 uid;
+    std::memcpy(uid.bytes, id, 128);
+    void* comm = nullptr;
+    int rc = a.CommInitRank(&comm, n_ranks, uid, rank);
+    if (rc != 0) return fail(h, PMF_ERR_CUDA, "ncclCommInitRank: %s", a.GetErrorString ? a.GetErrorString(rc) : "?");
+    h->comm = comm;
+    h->comm_ranks = n_ranks;
+    return PMF_OK;
+}
+
+int pmf_comm_destroy(pmf_handle h) {
+    CHECK_H(h);
+    if (h->comm) {
+        cudaStreamSynchronize(h->stream);
+        nccl().CommDestroy(h->comm);
+        h->comm = nullptr;
+        h->comm_ranks = 1;
+    }
+    return PMF_OK;
+}
+
+int pmf_model_s::exchange_gradients() {
+    if (!comm || comm_ranks <= 1) return 0;
+    NcclApi& a = nccl();
+    int rc = a.GroupStart();
+    if (rc == 0) rc = a.AllReduce(sg, sg, sg_len(), NCCL_FLOAT32, NCCL_SUM, comm, stream);
+    if (rc == 0) rc = a.AllReduce(scalars, scalars, SC_COUNT, NCCL_FLOAT64, NCCL_SUM, comm, stream);
+    int rc2 = a.GroupEnd();
+    if (rc == 0) rc = rc2;
+    if (rc != 0) { cuda_failed = true; return fail(this, PMF_ERR_CUDA, "ncclAllReduce: %s", a.GetErrorString ? a.GetErrorString(rc) : "?"); }
+    launches += 2;
+    return 0;
 }
 
 int pmf_shared_grad_buffer(pmf_handle h, void** p, int64_t* n) {

@@ -110,6 +110,11 @@ struct pmf_model_s {
     std::vector<cudaEvent_t> prof_ev;    // pairs (start, stop) per bracketed data pass
     size_t prof_used = 0;
 
+    // sample-sharded multi-GPU: NCCL communicator (opaque; loaded with dlopen) or null
+    void* comm = nullptr;
+    int comm_ranks = 1;
+    int exchange_gradients();   // all-reduce of sg and of the rank-local loss scalars on `stream`
+
     size_t vp_len() const { return 2 * (size_t)Np + 2 * (size_t)nbp; }
     size_t sg_len() const { return (size_t)Np * Kp + vp_len(); }
     float* logsigma() { return vp; }

@@ -2,8 +2,11 @@
 contiguous block of samples (its rows of the data, its columns of X, its AdaGrad state for X);
 Y, the column / batch parameters and the Y-side regulariser data are replicated.  Per epoch
 there is exactly one exchange step: an all-reduce (sum) of the shared gradient buffer
-[dY | dlogsigma | dmu | dlogdelta | dtheta] and of the two rank-local loss scalars, issued by
-``torch.distributed`` (NCCL over NVLink on GPUs; gloo in the CPU tests of the sharding logic).
+[dY | dlogsigma | dmu | dlogdelta | dtheta] and of the two rank-local loss scalars.  On GPUs the
+library issues it itself (``NcclFit``: ncclAllReduce over NVLink on the handle's stream, inside
+``pmf_fit``, so the epoch loop never returns to the host; ``torch.distributed`` only carries the
+128-byte NCCL id at start-up).  ``ShardedFit`` is the same step driven from the host through
+``torch.distributed`` collectives (any backend; gloo in the CPU tests of the sharding logic).
 Every rank then applies the identical update, so the replicas never diverge.
 
 This mirrors the reference's only spelled-out sharding pattern: row blocks with one Y-gradient
@@ -83,6 +86,33 @@ class ShardedFit:
         return {"term_code": TERM_CODES[hist.term_code], "epochs": int(hist.epochs), "loss": arrs[0][:n].tolist(),
                 "data_loss": arrs[1][:n].tolist(), "X_reg": arrs[2][:n].tolist(), "Y_reg": arrs[3][:n].tolist(),
                 "layer_reg": arrs[4][:n].tolist(), "kernel_launches": int(hist.kernel_launches)}
+
+
+class NcclFit:
+    """Attach an NCCL communicator to the engine's handle (one rank per process / GPU); afterwards
+    ``engine.fit`` runs the sharded epoch loop entirely inside libpmf.  ``torch.distributed`` (any
+    backend) is used once, to broadcast rank 0's ncclUniqueId."""
+
+    def __init__(self, engine, group=None):
+        import torch
+        import torch.distributed as dist
+        self.eng = engine
+        lib = engine.lib
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        ident = (C.c_uint8 * 128)()
+        if rank == 0:
+            engine._ck(lib.pmf_comm_unique_id(ident))
+        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+        t = torch.tensor(list(ident), dtype=torch.uint8, device=dev)
+        dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        ident = (C.c_uint8 * 128)(*t.cpu().tolist())
+        engine._ck(lib.pmf_comm_init_rank(engine.h, world, rank, ident))
+
+    def fit(self, opts) -> Dict:
+        return self.eng.fit(opts)
+
+    def close(self):
+        self.eng._ck(self.eng.lib.pmf_comm_destroy(self.eng.h))
 
 
 def allreduce_plan_check(per_rank: List[Dict[str, np.ndarray]], full: Dict[str, np.ndarray]) -> bool:

@@ -372,3 +372,28 @@ def test_tc_ordinal_and_hinge_columns():
     assert abs(got["loss"] - ref["loss"]) <= 1e-5 * abs(ref["loss"])
     assert relerr(got["dmu"], ref["dmu"]) < 1e-4 and relerr(got["dlogsigma"], ref["dlogsigma"]) < 1e-4
     assert relerr(got["dY"], ref["dY"]) < 5e-4 and relerr(got["dX"], ref["dX"]) < 5e-4
+
+
+def test_nccl_exchange_single_rank_matches_plain_fit():
+    """The in-library exchange step (dlopen'd NCCL, ncclAllReduce inside pmf_fit) with a one-rank
+    communicator must leave the fit unchanged (sum over one rank)."""
+    import ctypes as C
+    views = {"mutation": ("bernoulli", 40), "methylation": ("normal", 90)}
+    model, om, D = make_pair(150, views, K=6, seed=51, missing=0.2, lambda_X_l2=1.0)
+    import copy
+    model2 = copy.deepcopy(model)
+    h_plain = P.mf_fit(model, lr=0.2, max_epochs=6, update_X=True, update_Y=True, update_col_layers=True,
+                       rel_tol=0, abs_tol=0, verbosity=0)
+    eng = P.Engine(model2)
+    try:
+        ident = (C.c_uint8 * 128)()
+        eng._ck(eng.lib.pmf_comm_unique_id(ident))
+        eng._ck(eng.lib.pmf_comm_init_rank(eng.h, 1, 0, ident))
+        eng.reset_opt_state(1e-8)
+        o = eng.make_opts(epoch=1, max_epochs=6, lr=0.2, update_X=1, update_Y=1, update_col_layers=1, rel_tol=0.0, abs_tol=0.0)
+        h = eng.fit(o)
+        eng._ck(eng.lib.pmf_comm_destroy(eng.h))
+    finally:
+        eng.close()
+    assert h["epochs"] == h_plain["epochs"]
+    assert np.max(np.abs(np.array(h["loss"]) / np.array(h_plain["loss"]) - 1)) < 1e-6
