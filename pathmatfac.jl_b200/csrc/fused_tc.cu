@@ -77,6 +77,12 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// Arrive that publishes nothing: the arriving thread only reports that it has finished READING (TMEM
+// accumulators, after tcgen05.wait::ld + fence).  No release fence, so it does not wait for the thread's
+// outstanding global loads / stores the way the default (release) arrive does.
+__device__ __forceinline__ void mbar_arrive_relaxed(uint32_t bar) {
+    asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t hint = 0) {
     uint32_t done;
     do {
@@ -96,6 +102,22 @@ __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     return done != 0;
+}
+// Four barrier probes issued back to back (their shared-memory round trips overlap); bit k of the result
+// is set when barrier k has completed the phase with parity par_k.
+__device__ __forceinline__ uint32_t mbar_probe4(uint32_t b0, uint32_t p0, uint32_t b1, uint32_t p1, uint32_t b2,
+                                                uint32_t p2, uint32_t b3, uint32_t p3) {
+    uint32_t m;
+    asm volatile(
+        "{\n\t.reg .pred q0, q1, q2, q3;\n\t.reg .u32 t0, t1, t2, t3;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 q0, [%1], %2;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 q1, [%3], %4;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 q2, [%5], %6;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 q3, [%7], %8;\n\t"
+        "selp.u32 t0, 1, 0, q0;\n\tselp.u32 t1, 2, 0, q1;\n\tselp.u32 t2, 4, 0, q2;\n\tselp.u32 t3, 8, 0, q3;\n\t"
+        "or.b32 t0, t0, t1;\n\tor.b32 t2, t2, t3;\n\tor.b32 %0, t0, t2;\n\t}"
+        : "=r"(m) : "r"(b0), "r"(p0), "r"(b1), "r"(p1), "r"(b2), "r"(p2), "r"(b3), "r"(p3) : "memory");
+    return m;
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
     asm volatile(
@@ -212,8 +234,10 @@ __device__ __forceinline__ float and_mask(float x, uint32_t m) { return __uint_a
 
 // ordinal / hinge noise models: rare on the hot path, kept out of line to bound code size.
 // Returns (loss, dloss/dz); (0, 0) for a missing entry.
-__device__ __noinline__ float2 noise_eval_slow(int dist, float z, float a, float4 th4, float ord_eps, float margin) {
+__device__ __noinline__ float2 noise_eval_slow(int dist, float z, float a, const float* __restrict__ th_range,
+                                                float ord_eps, float margin) {
     if (!is_observed(a)) return make_float2(0.f, 0.f);
+    const float4 th4 = __ldg(reinterpret_cast<const float4*>(th_range));
     const float th[4] = {th4.x, th4.y, th4.z, th4.w};
     float l, g;
     noise_eval(dist, z, a, th, ord_eps, margin, l, g);
@@ -227,9 +251,9 @@ struct TcParams {
     int ablate;        // PMF_TC_ABLATE (performance experiments only; results are wrong when non-zero)
     long long* trace;  // PMF_TC_TRACE: per-tile clock64 stamps of one CTA (16 events x TRACE_TILES), else null
     int trace_cta;
-    int flags;         // PMF_TC_FLAGS experiments: 1 = batch the MMA-thread waits
+    int flags;         // PMF_TC_FLAGS experiments (try_wait suspend hints)
 };
-constexpr int TRACE_TILES = 96, TRACE_EV = 16;
+constexpr int TRACE_TILES = 96, TRACE_EV = 32;
 
 __device__ __forceinline__ void item_range(const TcParams& p, int item, int& jt, int& it0, int& it1) {
     jt = item / p.chunks;
@@ -421,29 +445,26 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
             issue_mma1();
             if (it0 + 1 < it1) issue_mma1();
             for (int it = it0; it < it1; ++it, ++g) {
-                // Every barrier of this iteration is probed BEFORE any of its MMAs are issued while the tensor
-                // queue still holds the previous tile's work, so the 48 MMAs below go out back to back.  Only
-                // when this tile's G0 is not there yet does MMA1 of tile g+2 go first, to fill the wait.
+                // In steady state the MMA thread is the pacing role and every barrier of the iteration has
+                // already completed when it gets here: one batched probe replaces four serial waits (each a
+                // shared-memory round trip during which the tensor queue drains); a barrier that is still
+                // open is waited for where the old code did, MMA1 of tile g+2 going first to fill the wait.
                 const uint32_t b = g & 1, ph = (g >> 1) & 1;
                 const bool m1 = it + 2 < it1;
-                bool m1_done = false;
+                const uint32_t ok = mbar_probe4(bar(B_FULL_XK + rx1.s), rx1.ph, bar(B_G_READY + rz.s), rz.ph,
+                                                bar(B_DX_EMPTY + b), ph ^ 1, bar(B_FULL_XM + rx3.s), rx3.ph);
                 if (m1) {
                     stamp(g1, 13);
-                    mbar_wait(bar(B_FULL_XK + rx1.s), rx1.ph, hint_m);
+                    if (!(ok & 1u)) mbar_wait(bar(B_FULL_XK + rx1.s), rx1.ph);
+                    tc_fence_after();
                     stamp(g1, 1);
-                    if (!(p.flags & 1) || !mbar_test(bar(B_G_READY + rz.s), rz.ph)) {
-                        tc_fence_after();
-                        issue_mma1_nowait();
-                        m1_done = true;
-                    }
+                    issue_mma1_nowait();
                 }
-                mbar_wait(bar(B_G_READY + rz.s), rz.ph, hint_m);
+                if (!(ok & 2u)) mbar_wait(bar(B_G_READY + rz.s), rz.ph);
                 stamp(g, 2);
-                mbar_wait(bar(B_DX_EMPTY + b), ph ^ 1, hint_m);
-                if (p.flags & 1) mbar_wait(bar(B_FULL_XM + rx3.s), rx3.ph, hint_m);
+                if (!(ok & 4u)) mbar_wait(bar(B_DX_EMPTY + b), ph ^ 1);
                 tc_fence_after();
                 stamp(g, 3);
-                if (m1 && !m1_done) issue_mma1_nowait();
                 {
                     // MMA2 first (dX = G0' * Yh): its completion releases the A/G buffer for the TMA producer
                     const uint64_t gd = umma_desc_mn(AG + ra.s * AG_BYTES, 16384u), yd = umma_desc_mn(YS, 16384u);
@@ -459,7 +480,7 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
                 }
                 {
                     // MMA3: dY += G0 * Xh  (MN-major copy of the Xh tile)
-                    if (!(p.flags & 1)) { mbar_wait(bar(B_FULL_XM + rx3.s), rx3.ph, hint_m); tc_fence_after(); }
+                    if (!(ok & 8u)) { mbar_wait(bar(B_FULL_XM + rx3.s), rx3.ph); tc_fence_after(); }
                     stamp(g, 4);
                     const uint32_t ga = tmu + TM_Z0 + 64 * rz.s;
                     const uint64_t xd = umma_desc_mn(XM + rx3.s * XM_BYTES, 8192u);
@@ -519,7 +540,7 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
             TMEM_LD16(tm + lane_addr + TM_DX0 + 64 * b + 32 * h32 + 16, r1);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             tc_fence_before();
-            mbar_arrive(bar(B_DX_EMPTY + b));
+            mbar_arrive_relaxed(bar(B_DX_EMPTY + b));
             {
                 const uint32_t n_other = grp == 0 ? (gg >> 1) : ((gg + 1) >> 1), n_own = gg >> 1;   // flushes before tile gg
                 mbar_wait(bar(B_DXS_DONE + (grp ^ 1)), (n_other - 1u) & 1u);     // n == 0: parity 1 passes on a fresh barrier
@@ -540,19 +561,55 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
         int pend_i0 = -1;          // sample offset of this group's tile whose dX is still in TMEM
         uint32_t pend_g = 0;
 
+        // Per-item operands of this thread (lane = feature): column constants and its 16-column chunk of
+        // the Y row.  They are fetched one item AHEAD, right before the wait for the current item's last
+        // contraction, so the two global round trips are off the item-to-item critical path.
+        struct ItemRegs { float logsigma, mu, w; int ci; float4 y[4]; };
+        auto load_item = [&](int item_, ItemRegs& r) {
+            const int jt_ = item_ / p.chunks;
+            const int j_ = jt_ * BJ + lrow;
+            const int jj_ = j_ < dp.N ? j_ : 0;
+            r.logsigma = __ldg(dp.logsigma + jj_);
+            r.mu = __ldg(dp.mu + jj_);
+            r.w = j_ < dp.N ? __ldg(dp.weight + jj_) : 0.f;
+            r.ci = __ldg(dp.colinfo + jj_);
+            const float4* yrow = reinterpret_cast<const float4*>(dp.Y + (size_t)(jt_ * BJ + lrow) * KK) + 4 * c16;
+#pragma unroll
+            for (int v = 0; v < 4; ++v) r.y[v] = __ldg(yrow + v);
+        };
+        ItemRegs cur;
+        if ((int)blockIdx.x < p.n_items) load_item(blockIdx.x, cur);
+        // column-side results of the previous item, reduced into global memory one item late (see the item
+        // epilogue): 128-bit REDs for the dY tile (plain stores when a feature tile has a single chunk)
+        float4 pend_dy[4];
+        float pend_dmu = 0.f, pend_dls = 0.f;
+        int pend_j = -1;
+        auto store_partials = [&]() {
+            if (pend_j >= 0) {
+                float4* dst = reinterpret_cast<float4*>(dp.dY + (size_t)pend_j * KK + 16 * c16);
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    if (p.chunks == 1) dst[v] = pend_dy[v];
+                    else atomicAdd(dst + v, pend_dy[v]);
+                }
+                atomicAdd(dp.dmu + pend_j, pend_dmu);
+                atomicAdd(dp.dlogsigma + pend_j, pend_dls);
+            }
+            pend_j = -1;
+        };
+
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
             int jt, it0, it1;
             item_range(p, item, jt, it0, it1);
             const int j = jt * BJ + lrow;
             const bool jok = j < dp.N;
-            const int jj = jok ? j : 0;
             // per-thread column constants (lane = feature)
-            const float sigma = __expf(dp.logsigma[jj]);
-            const float muj = dp.mu[jj];
-            const float wj = jok ? dp.weight[jj] : 0.f;
-            const int ci = dp.colinfo[jj];
+            const float sigma = __expf(cur.logsigma);
+            const float muj = cur.mu;
+            const float wj = cur.w;
+            const int ci = cur.ci;
             const int dist = ci & 0xff;
-            const float4 th4 = __ldg(reinterpret_cast<const float4*>(dp.thresholds + 4 * (ci >> 8)));
+            const float* th_range = dp.thresholds + 4 * (ci >> 8);
             // G0 = (w_j sigma_j) * dloss/dz4 (no batch layers on this path).  The per-feature factor never
             // touches the per-entry path: MMA2 reads Yh scaled by it, the dY tile is scaled at the flush.
             const float gscale = sigma * wj;
@@ -561,11 +618,10 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
             // ---- Y tile: h = rna_tf32(y), l = y - h -> TMEM (A of MMA1); gscale * y -> shared memory (B of MMA2).
             // The previous item's MMAs have all completed (B_DY_FULL was waited on), so both are free.
             {
-                const float4* yrow = reinterpret_cast<const float4*>(dp.Y + (size_t)(jt * BJ + lrow) * KK) + 4 * c16;
                 uint32_t hi[16], lo[16];
 #pragma unroll
                 for (int v = 0; v < 4; ++v) {
-                    float4 y4 = __ldg(yrow + v);
+                    const float4 y4 = cur.y[v];
                     float ys[4] = {y4.x, y4.y, y4.z, y4.w};
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
@@ -576,12 +632,17 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
                     *reinterpret_cast<uint4*>(ys_ptr + (uint32_t)(c16 >> 1) * 16384u + chunk_off(4 * (c16 & 1) + v)) =
                         make_uint4(rna_tf32(gscale * y4.x), rna_tf32(gscale * y4.y), rna_tf32(gscale * y4.z), rna_tf32(gscale * y4.w));
                 }
+                const bool trp = quarter == 0 && h32 == 0 && lane == 0;
+                if (trp) stamp(g, 19 + 6 * grp);
                 TMEM_ST16(tm + lane_addr + TM_YH + 16 * c16, hi);
                 TMEM_ST16(tm + lane_addr + TM_YL + 16 * c16, lo);
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 tc_fence_before();
                 fence_async_smem();
+                if (trp) stamp(g, 20 + 6 * grp);
                 mbar_arrive(bar(B_Y_READY));
+                if (trp) stamp(g, 21 + 6 * grp);
+                store_partials();
             }
 
             // per-entry math on 16 consecutive samples: z[] (TMEM columns) in, dloss/dz (TF32-rounded bits) out
@@ -630,7 +691,7 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
 #pragma unroll
                     for (int e = 0; e < 16; ++e) {
                         float z4 = fmaf(__uint_as_float(z[e]), sigma, muj);
-                        float2 lg = noise_eval_slow(dist, z4, a[e], th4, dp.ordinal_eps, dp.hinge_margin);
+                        float2 lg = noise_eval_slow(dist, z4, a[e], th_range, dp.ordinal_eps, dp.hinge_margin);
                         loss_acc = fmaf(2.f, lg.x, loss_acc);        // keep the common 1/2 factor at flush
                         dmu_acc += lg.y;
                         z[e] = rn_bits(lg.y);
@@ -695,35 +756,44 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
             }
             // every dX tile of the item leaves TMEM before the item's accumulators are flushed
             if (pend_i0 >= 0) { dx_out(pend_g, pend_i0); pend_i0 = -1; }
+            const bool trb = quarter == 0 && h32 == 0 && lane == 0;
+            if (trb) stamp(g, 16 + 6 * grp);
             loss_d += (double)(loss_acc * wj);
+            ItemRegs nxt;
+            nxt.logsigma = nxt.mu = nxt.w = 0.f; nxt.ci = 0;
+#pragma unroll
+            for (int v = 0; v < 4; ++v) nxt.y[v] = make_float4(0.f, 0.f, 0.f, 0.f);
 
             // ---- item epilogue: dY tile out of TMEM, column sums --------------------------------------
             mbar_wait(bar(B_DY_FULL), q & 1);
             tc_fence_after();
+            if (trb) stamp(g, 17 + 6 * grp);
             {
                 uint32_t r[16];
                 TMEM_LD16(tm + lane_addr + TM_DY + 16 * c16, r);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 tc_fence_before();
-                mbar_arrive(bar(B_DY_EMPTY));
-                if (jok) {
-                    float* dst = dp.dY + (size_t)j * KK + 16 * c16;
+                mbar_arrive_relaxed(bar(B_DY_EMPTY));
+                // next item's operands: issued after the last arrive of this item so that no fence waits on them
+                if (item + (int)gridDim.x < p.n_items) load_item(item + gridDim.x, nxt);
+                // The results stay in registers and are reduced into global memory AFTER the next item's Y
+                // operands have been published: REDs issued here would sit in front of that release-arrive's
+                // memory fence and serialise the item boundary.
 #pragma unroll
-                    for (int v = 0; v < 4; ++v) {
-                        float4 val = make_float4(gscale * __uint_as_float(r[4 * v]), gscale * __uint_as_float(r[4 * v + 1]),
-                                                 gscale * __uint_as_float(r[4 * v + 2]), gscale * __uint_as_float(r[4 * v + 3]));
-                        if (p.chunks == 1) reinterpret_cast<float4*>(dst)[v] = val;
-                        else atomicAdd(reinterpret_cast<float4*>(dst) + v, val);
-                    }
-                }
+                for (int v = 0; v < 4; ++v)
+                    pend_dy[v] = make_float4(gscale * __uint_as_float(r[4 * v]), gscale * __uint_as_float(r[4 * v + 1]),
+                                             gscale * __uint_as_float(r[4 * v + 2]), gscale * __uint_as_float(r[4 * v + 3]));
             }
-            if (jok) {
-                // dmu_j = sum_i g ; dlogsigma_j = sum_i sigma_j * g  (the reference's ColScale quirk)
-                atomicAdd(dp.dmu + j, dmu_acc * wj);
-                atomicAdd(dp.dlogsigma + j, dmu_acc * wj * sigma);
-            }
+            // dmu_j = sum_i g ; dlogsigma_j = sum_i sigma_j * g  (the reference's ColScale quirk).  The four warps that
+            // share a feature row (two groups x two sample halves) each store their own partial.
+            pend_dmu = dmu_acc * wj;
+            pend_dls = dmu_acc * wj * sigma;
+            pend_j = jok ? j : -1;
+            if (trb) stamp(g, 18 + 6 * grp);
+            cur = nxt;
             ++q;
         }
+        store_partials();
         // data loss: sum over the epilogue warps, 0.5 factor applied here
         loss_d *= 0.5;
         for (int o = 16; o > 0; o >>= 1) loss_d += __shfl_xor_sync(0xffffffffu, loss_d, o);
@@ -796,6 +866,21 @@ bool tc_supported(const DataPassParams& p) {
     return p.Kp == KK && p.n_batch_views == 0 && p.col_ssq == nullptr;
 }
 
+// sample chunks per feature tile: maximise the fill of the last wave, at least 4 tiles per chunk
+int tc_chunks(const DataPassParams& dp, int n_sms) {
+    if (dp.sample_chunks > 0) return dp.sample_chunks;
+    const int n_jt = (dp.N + BJ - 1) / BJ, n_it = (dp.M + BI - 1) / BI;
+    int best_c = 1;
+    double best_eff = 0.0;
+    const int max_c = n_it / 4 > 0 ? n_it / 4 : 1;
+    for (int c = 1; c <= max_c && c <= 16; ++c) {
+        long long items = (long long)n_jt * c;
+        long long waves = (items + n_sms - 1) / n_sms;
+        double eff = (double)items / (double)(waves * n_sms) - 0.002 * c;   // mild preference for fewer chunks
+        if (eff > best_eff) { best_eff = eff; best_c = c; }
+    }
+    return best_c;
+}
 // Xh, Xl: [Mp][64] operand scratch owned by the handle, refreshed here every launch
 cudaError_t launch_data_pass_tc(const DataPassParams& dp, float* Xh, float* Xl, int precision, cudaStream_t s,
                                 int n_sms) {
@@ -835,17 +920,7 @@ cudaError_t launch_data_pass_tc(const DataPassParams& dp, float* Xh, float* Xl, 
         const char* tc = getenv("PMF_TC_TRACE_CTA");
         p.trace_cta = tc ? atoi(tc) : 0;
     }
-    // sample chunks: maximise the fill of the last wave, at least 4 tiles per chunk
-    int best_c = 1;
-    double best_eff = 0.0;
-    const int max_c = p.n_it / 4 > 0 ? p.n_it / 4 : 1;
-    for (int c = 1; c <= max_c && c <= 16; ++c) {
-        long long items = (long long)p.n_jt * c;
-        long long waves = (items + n_sms - 1) / n_sms;
-        double eff = (double)items / (double)(waves * n_sms) - 0.002 * c;   // mild preference for fewer chunks
-        if (eff > best_eff) { best_eff = eff; best_c = c; }
-    }
-    p.chunks = dp.sample_chunks > 0 ? dp.sample_chunks : best_c;
+    p.chunks = tc_chunks(dp, n_sms);
     p.n_items = p.n_jt * p.chunks;
     const bool dbg = p.ablate != 0 || p.trace != nullptr;
     auto kern = dbg ? data_pass_tc_kernel<true> : data_pass_tc_kernel<false>;

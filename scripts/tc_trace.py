@@ -3,7 +3,7 @@ import sys
 import numpy as np
 EV = ["tmaA_issue", "M1_issue", "G_seen", "M2_issue", "M3_issue", "epi_top", "Z_seen", "A_seen", "epi_done", "G_arrived",
       "dx_begin", "DXFULL_seen", "dx_end", "M1_top", "M1_issued", "M3_issued"]
-a = np.fromfile(sys.argv[1], dtype=np.int64).reshape(-1, 16)
+a = np.fromfile(sys.argv[1], dtype=np.int64).reshape(-1, 32)
 t0 = a[a > 0].min()
 lo, hi = (int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv) > 3 else (20, 44)
 print("tile " + " ".join(f"{e:>11}" for e in EV))
@@ -26,3 +26,10 @@ for name, x, y in [("M1: XK wait (M1_issue - M1_top)", 1, 13), ("M1: 24 MMAs iss
     print(f"{name:40s} mean {v.mean():9.1f}  min {v.min():7d}  max {v.max():7d}")
 v = a[lo + 3:hi + 3, 7] - a[lo + 3:hi + 3, 0]
 print(f"{'A_seen(g) - tmaA_issue(g)':40s} mean {v.mean():9.1f}  min {v.min():7d}  max {v.max():7d}")
+
+print("item boundaries (events keyed by the first tile of the next item; A = group 0, B = group 1):")
+names = ["flushed", "DYFULL_seen", "dY_stored", "Y_computed", "Y_fenced", "Y_arrived"]
+for g in range(1, a.shape[0]):
+    if a[g, 17] > 0 or a[g, 23] > 0:
+        print(f" tile {g}: " + " | ".join(f"{grp}:" + ",".join(f"{n}={a[g, 16 + 6 * k + i] - t0 if a[g, 16 + 6 * k + i] > 0 else -1}" for i, n in enumerate(names)) for k, grp in enumerate("AB")),
+              f"| MMA Y_READY->M1_issue(g)={a[g, 1] - t0}")
