@@ -881,16 +881,19 @@ int tc_chunks(const DataPassParams& dp, int n_sms) {
     }
     return best_c;
 }
-// Xh, Xl: [Mp][64] operand scratch owned by the handle, refreshed here every launch
-cudaError_t launch_data_pass_tc(const DataPassParams& dp, float* Xh, float* Xl, int precision, cudaStream_t s,
-                                int n_sms) {
+// Xh, Xl: [Mp][64] operand scratch owned by the handle; refreshed here when `refresh_split`
+cudaError_t launch_data_pass_tc(const DataPassParams& dp, float* Xh, float* Xl, bool refresh_split, int precision,
+                                cudaStream_t s, int n_sms) {
     if (!tc_supported(dp)) return cudaErrorInvalidValue;
-    const size_t n4 = (size_t)dp.Mp * KK / 4;
-    prep_operands_kernel<<<(unsigned)((n4 + 255) / 256 < 1184 ? (n4 + 255) / 256 : 1184), 256, 0, s>>>(
-        reinterpret_cast<const float4*>(dp.X), reinterpret_cast<float4*>(Xh), reinterpret_cast<float4*>(Xl), n4,
-        dp.stop_flag);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
+    cudaError_t e = cudaSuccess;
+    if (refresh_split) {   // otherwise the previous epoch's update pass wrote Xh / Xl together with X
+        const size_t n4 = (size_t)dp.Mp * KK / 4;
+        prep_operands_kernel<<<(unsigned)((n4 + 255) / 256 < 1184 ? (n4 + 255) / 256 : 1184), 256, 0, s>>>(
+            reinterpret_cast<const float4*>(dp.X), reinterpret_cast<float4*>(Xh), reinterpret_cast<float4*>(Xl), n4,
+            dp.stop_flag);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
 
     CUtensorMap tmXh, tmXl, tmXm, tmA, tmDX;
     bool ok = make_map(&tmXh, Xh, KK, dp.Mp, KK, 64, false, false) && make_map(&tmXl, Xl, KK, dp.Mp, KK, 64, false, false) &&

@@ -212,6 +212,7 @@ int pmf_set_factors(pmf_handle h, const float* X, const float* Y) {
     if (Y) CU(h, up2d(h->Y, h->Kp, Y, h->K, h->N, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
     h->transposes_stale = true;
+    h->xsplit_valid = false;
     return PMF_OK;
 }
 
@@ -675,40 +676,41 @@ static void fill_data_params(pmf_model_s* h, DataPassParams& p, bool use_stop) {
     p.ordinal_eps = 1e-10f; p.hinge_margin = 1.0f;
 }
 
-// zero gradients + data pass (+ X-side penalties: loss and pullback added into dX)
-static int phase_begin(pmf_model_s* h, const pmf_fit_opts* o, bool use_stop, bool include_reg) {
+// zero gradients (unless the previous epoch's update pass already did) + data pass
+// (+ X-side penalties when `x_reg_now`: they are rank-local sums and must precede the exchange step)
+static int phase_begin(pmf_model_s* h, const pmf_fit_opts* o, bool use_stop, bool x_reg_now) {
     cudaStream_t s = h->stream;
-    CU(h, cudaMemsetAsync(h->dX, 0, (size_t)h->Mp * h->Kp * 4, s));
-    CU(h, cudaMemsetAsync(h->sg, 0, h->sg_len() * 4, s));
-    CU(h, cudaMemsetAsync(h->scalars, 0, SC_COUNT * 8, s));
+    if (!h->grads_clean) {
+        CU(h, cudaMemsetAsync(h->dX, 0, (size_t)h->Mp * h->Kp * 4, s));
+        CU(h, cudaMemsetAsync(h->sg, 0, h->sg_len() * 4, s));
+        CU(h, cudaMemsetAsync(h->scalars, 0, SC_COUNT * 8, s));
+    }
+    h->grads_clean = false;
     DataPassParams p;
     fill_data_params(h, p, use_stop);
     int kind = o ? o->kernel : PMF_KERNEL_AUTO;
     int rc = h->run_data_pass(p, kind, o ? o->precision : 0);
     if (rc != 0) return rc;
-    if (include_reg) {
+    if (x_reg_now) {
         const int* stop = use_stop ? &h->ctrl->stop : nullptr;
-        rc = h->run_factor_reg(0, stop);
-        if (rc != 0) return rc;
+        if ((rc = h->run_network_reg(0, stop)) != 0) return rc;
+        if ((rc = h->run_reg_multi(true, false, false, stop)) != 0) return rc;
     }
     return 0;
 }
 
-// Y-side / layer penalties (loss + pullbacks added in place into the gradient buffers)
-static int phase_reg_shared(pmf_model_s* h, bool use_stop) {
+// remaining penalties (loss + pullbacks added in place into the gradient buffers) in one launch
+static int phase_reg_shared(pmf_model_s* h, bool use_stop, bool with_x) {
     const int* stop = use_stop ? &h->ctrl->stop : nullptr;
-    int rc = h->run_factor_reg(1, stop);
-    if (rc != 0) return rc;
-    return h->run_vector_pass(/*reg=*/true, /*update=*/false, 0.f, 0.f, stop, false);
+    int rc;
+    if (with_x && (rc = h->run_network_reg(0, stop)) != 0) return rc;
+    if ((rc = h->run_network_reg(1, stop)) != 0) return rc;
+    return h->run_reg_multi(with_x, true, true, stop);
 }
 
 static int phase_update(pmf_model_s* h, const pmf_fit_opts* o) {
-    const int* stop = &h->ctrl->stop;
-    int rc;
-    if (o->update_X && (rc = h->run_factor_update(0, o->lr, o->adagrad_eps, stop)) != 0) return rc;
-    if (o->update_Y && (rc = h->run_factor_update(1, o->lr, o->adagrad_eps, stop)) != 0) return rc;
-    if (o->update_col_layers && (rc = h->run_vector_pass(false, true, o->lr, o->adagrad_eps, stop, true)) != 0) return rc;
-    return 0;
+    return h->run_update_multi(o->update_X != 0, o->update_Y != 0, o->update_col_layers != 0, o->lr, o->adagrad_eps,
+                               &h->ctrl->stop);
 }
 
 int pmf_loss_grad(pmf_handle h, int32_t include_reg, pmf_losses* out, float* dX, float* dY, float* dls, float* dmu) {
@@ -717,9 +719,10 @@ int pmf_loss_grad(pmf_handle h, int32_t include_reg, pmf_losses* out, float* dX,
     pmf_fit_opts o;
     pmf_default_fit_opts(&o);
     o.kernel = h->loss_grad_kernel; o.precision = h->loss_grad_precision;
+    h->grads_clean = false;
     int rc = phase_begin(h, &o, false, include_reg != 0);
     if (rc != 0) return rc;
-    if (include_reg && (rc = phase_reg_shared(h, false)) != 0) return rc;
+    if (include_reg && (rc = phase_reg_shared(h, false, false)) != 0) return rc;
     CU(h, cudaStreamSynchronize(h->stream));
     double sc[SC_COUNT];
     CU(h, cudaMemcpy(sc, h->scalars, sizeof sc, cudaMemcpyDeviceToHost));
@@ -753,19 +756,20 @@ int pmf_fit_start(pmf_handle h, const pmf_fit_opts* o) {
     CU(h, cudaMemcpyAsync(h->ctrl, &c, sizeof c, cudaMemcpyHostToDevice, h->stream));
     h->cur_epoch = o->epoch;
     h->launches = 0;
+    h->grads_clean = false;
     return PMF_OK;
 }
 
 int pmf_epoch_begin(pmf_handle h, const pmf_fit_opts* o) {
     CHECK_H(h);
     if (!o) return fail(h, PMF_ERR_ARG, "null options");
-    return phase_begin(h, o, true, true);
+    return phase_begin(h, o, true, true);     // X-side penalties before the caller's exchange step
 }
 
 int pmf_epoch_end(pmf_handle h, const pmf_fit_opts* o) {
     CHECK_H(h);
     if (!o) return fail(h, PMF_ERR_ARG, "null options");
-    int rc = phase_reg_shared(h, true);
+    int rc = phase_reg_shared(h, true, false);
     if (rc != 0) return rc;
     CU(h, launch_control(h->ctrl, h->scalars, h->hist, h->hist_cap, h->cur_epoch, o->no_terminate ? -1 : o->max_epochs, o->rel_tol, o->abs_tol, h->stream));
     h->launches++;
@@ -811,9 +815,16 @@ int pmf_fit(pmf_handle h, const pmf_fit_opts* o, pmf_history* out) {
     CU(h, cudaEventRecord(h->ev0, h->stream));
     int since = 0;
     for (int e = o->epoch; e <= o->max_epochs; ++e) {
-        if ((rc = pmf_epoch_begin(h, o)) != 0) return rc;
-        if ((rc = h->exchange_gradients()) != 0) return rc;     // no-op without a communicator
-        if ((rc = pmf_epoch_end(h, o)) != 0) return rc;
+        // Sharded: X-side penalties are rank-local sums and go before the exchange.  Single GPU: every
+        // penalty of the epoch is one launch, after the data pass.
+        const bool sharded = h->comm != nullptr && h->comm_ranks > 1;
+        if ((rc = phase_begin(h, o, true, sharded)) != 0) return rc;
+        if (sharded && (rc = h->exchange_gradients()) != 0) return rc;
+        if ((rc = phase_reg_shared(h, true, !sharded)) != 0) return rc;
+        CU(h, launch_control(h->ctrl, h->scalars, h->hist, h->hist_cap, h->cur_epoch, o->no_terminate ? -1 : o->max_epochs, o->rel_tol, o->abs_tol, h->stream));
+        h->launches++;
+        if ((rc = phase_update(h, o)) != 0) return rc;
+        h->cur_epoch++;
         if (++since >= check && e < o->max_epochs) {
             since = 0;
             CU(h, cudaMemcpyAsync(h->ctrl_host, h->ctrl, sizeof(FitControl), cudaMemcpyDeviceToHost, h->stream));
@@ -983,12 +994,15 @@ int pmf_model_s::run_data_pass(DataPassParams& p, int kind, int precision) {
             prof_used += 2;
             cudaEventRecord(t0, stream);
         }
-        cudaError_t e = launch_data_pass_tc(p, Xh, Xl, precision, stream, n_sms);
+        const bool refresh = !xsplit_valid;
+        cudaError_t e = launch_data_pass_tc(p, Xh, Xl, refresh, precision, stream, n_sms);
+        xsplit_valid = true;     // stays true only while every later change of X goes through run_update_multi
         if (profiling) cudaEventRecord(t1, stream);
         if (e != cudaSuccess) { cuda_failed = true; return fail(this, PMF_ERR_CUDA, "tcgen05 data pass launch: %s", cudaGetErrorString(e)); }
-        launches += 2;
+        launches += refresh ? 2 : 1;
         return 0;
     }
+    xsplit_valid = false;
     size_t smem = sizeof(float) * ((size_t)128 * (Kp + 4) + 64 * 68 + 2 * (size_t)64 * nb_max);
     if (smem > 227 * 1024) return fail(this, PMF_ERR_ARG, "too many batches per view (%d) for K=%d", nb_max, K);
     cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -1015,42 +1029,119 @@ void pmf_model_s::fill_factor_params(int which, FactorUpdateParams& q) {
     q.acc = which == 0 ? accX : accY;
 }
 
-int pmf_model_s::run_factor_reg(int which, const int* stop) {
+int pmf_model_s::run_network_reg(int which, const int* stop) {
     SideReg& r = reg[which];
-    double* loss_out = scalars + (which == 0 ? SC_XREG : SC_YREG);
-    float* grad = which == 0 ? dX : g_Y();
-    if (r.net.present) {
-        NetworkParams q;
-        std::memset(&q, 0, sizeof q);
-        q.n = which == 0 ? M : N; q.Kp = Kp; q.K = K;
-        q.P = which == 0 ? X : Y; q.grad = grad;
-        auto cv = [](const DevCsr& d) { CsrBlock b{d.rowptr, d.col, d.val, d.rowptr_base, d.nnz_base}; return b; };
-        q.AA = cv(r.net.AA); q.AB = cv(r.net.AB); q.BB = cv(r.net.BB); q.ABt = cv(r.net.ABt);
-        q.nv = r.net.nv; q.virt_base = r.net.virt_base; q.u = r.net.u; q.work = r.net.work; q.nv_total = r.net.nv_total;
-        q.p = r.net.p; q.rtol = r.net.rtol; q.atol = r.net.atol; q.itmax = r.net.itmax;
-        q.loss_out = loss_out; q.stop_flag = stop;
-        cudaError_t e = launch_network_reg(q, stream);
-        if (e != cudaSuccess) { cuda_failed = true; return fail(this, PMF_ERR_CUDA, "network reg launch: %s", cudaGetErrorString(e)); }
-        launches++;
-    }
-    if (!r.any_elementwise()) return 0;
-    FactorUpdateParams q;
-    fill_factor_params(which, q);
-    q.grad_out = grad;                      // in-place: data gradient + penalty pullback
+    if (!r.net.present) return 0;
+    NetworkParams q;
+    std::memset(&q, 0, sizeof q);
+    q.n = which == 0 ? M : N; q.Kp = Kp; q.K = K;
+    q.P = which == 0 ? X : Y; q.grad = which == 0 ? dX : g_Y();
+    auto cv = [](const DevCsr& d) { CsrBlock b{d.rowptr, d.col, d.val, d.rowptr_base, d.nnz_base}; return b; };
+    q.AA = cv(r.net.AA); q.AB = cv(r.net.AB); q.BB = cv(r.net.BB); q.ABt = cv(r.net.ABt);
+    q.nv = r.net.nv; q.virt_base = r.net.virt_base; q.u = r.net.u; q.work = r.net.work; q.nv_total = r.net.nv_total;
+    q.p = r.net.p; q.rtol = r.net.rtol; q.atol = r.net.atol; q.itmax = r.net.itmax;
+    q.loss_out = scalars + (which == 0 ? SC_XREG : SC_YREG); q.stop_flag = stop;
+    cudaError_t e = launch_network_reg(q, stream);
+    if (e != cudaSuccess) { cuda_failed = true; return fail(this, PMF_ERR_CUDA, "network reg launch: %s", cudaGetErrorString(e)); }
+    launches++;
+    return 0;
+}
+
+static void fill_factor_reg(pmf_model_s* h, int which, FactorUpdateParams& q, const int* stop) {
+    SideReg& r = h->reg[which];
+    h->fill_factor_params(which, q);
+    q.grad_out = which == 0 ? h->dX : h->g_Y();      // in-place: data gradient + penalty pullback
     q.l2_w = r.l2_w; q.group_id = r.group_id; q.group_w = r.group_w;
     q.l1_mask = r.l1_mask; q.l1_w = r.l1_w;
     q.ard_alpha = r.ard_alpha; q.ard_beta_row = r.ard_beta_row; q.ard_beta_full = r.ard_beta_full;
-    q.loss_out = loss_out; q.do_update = 0; q.stop_flag = stop;
-    cudaError_t e = launch_factor_update(q, stream);
-    if (e != cudaSuccess) { cuda_failed = true; return fail(this, PMF_ERR_CUDA, "factor reg launch: %s", cudaGetErrorString(e)); }
+    q.loss_out = h->scalars + (which == 0 ? SC_XREG : SC_YREG); q.do_update = 0; q.stop_flag = stop;
+}
+
+// segments of the vector-parameter block: slot 1 logsigma, slot 3 mu, slot 2 logdelta, slot 4 theta
+struct VecSeg { size_t off; int n; int slot; };
+static void vec_segments(pmf_model_s* h, VecSeg segs[4]) {
+    segs[0] = {0, h->N, 1};
+    segs[1] = {(size_t)h->Np, h->N, 3};
+    segs[2] = {2 * (size_t)h->Np, (int)h->nbp, 2};
+    segs[3] = {2 * (size_t)h->Np + (size_t)h->nbp, (int)h->nbp, 4};
+}
+
+// every elementwise penalty of the requested sides in ONE launch
+int pmf_model_s::run_reg_multi(bool x_side, bool y_side, bool vectors, const int* stop) {
+    MultiPassParams mp;
+    std::memset(&mp, 0, sizeof mp);
+    if (x_side && reg[0].any_elementwise()) fill_factor_reg(this, 0, mp.f[mp.nf++], stop);
+    if (y_side && reg[1].any_elementwise()) fill_factor_reg(this, 1, mp.f[mp.nf++], stop);
+    if (vectors) {
+        VecSeg segs[4];
+        vec_segments(this, segs);
+        for (const VecSeg& sgm : segs) {
+            const unsigned bit = 1u << (sgm.slot - 1);
+            if (sgm.n <= 0 || !layer_reg_present[sgm.slot - 1] || (frozen_regs & bit)) continue;
+            VectorUpdateParams& q = mp.v[mp.nv++];
+            q.n = sgm.n; q.p = vp + sgm.off; q.grad = sg + (size_t)Np * Kp + sgm.off; q.acc = accvp + sgm.off;
+            q.stop_flag = stop;
+            q.reg_w = regw + sgm.off; q.reg_c = regc + sgm.off; q.reg_active = 1;
+            q.grad_out = sg + (size_t)Np * Kp + sgm.off;
+            q.loss_out = scalars + SC_LAYERREG;
+        }
+    }
+    if (mp.nf == 0 && mp.nv == 0) return 0;
+    cudaError_t e = launch_multi_pass(mp, stream, n_sms);
+    if (e != cudaSuccess) { cuda_failed = true; return fail(this, PMF_ERR_CUDA, "penalty pass launch: %s", cudaGetErrorString(e)); }
     launches++;
     return 0;
+}
+
+// AdaGrad step of every enabled parameter array in ONE launch.  The same pass clears the gradient
+// buffers and the loss scalars for the next epoch and, for X, writes the TF32 operand split of the
+// updated values, so the next epoch starts directly with the data pass.
+int pmf_model_s::run_update_multi(bool upd_X, bool upd_Y, bool upd_layers, float lr, float eps, const int* stop) {
+    MultiPassParams mp;
+    std::memset(&mp, 0, sizeof mp);
+    {
+        FactorUpdateParams& q = mp.f[mp.nf++];
+        fill_factor_params(0, q);
+        q.do_update = upd_X ? 1 : 0; q.lr = lr; q.eps = eps; q.stop_flag = stop;
+        q.zero_buf = dX; q.n_pad = Mp;
+        if (Xh && xsplit_valid) { q.Ph = Xh; q.Pl = Xl; }
+    }
+    {
+        FactorUpdateParams& q = mp.f[mp.nf++];
+        fill_factor_params(1, q);
+        q.do_update = upd_Y ? 1 : 0; q.lr = lr; q.eps = eps; q.stop_flag = stop;
+        q.zero_buf = g_Y(); q.n_pad = Np;
+    }
+    VecSeg segs[4];
+    vec_segments(this, segs);
+    for (const VecSeg& sgm : segs) {
+        if (sgm.n <= 0) continue;
+        const unsigned bit = 1u << (sgm.slot - 1);
+        VectorUpdateParams& q = mp.v[mp.nv++];
+        q.n = sgm.n; q.p = vp + sgm.off; q.grad = sg + (size_t)Np * Kp + sgm.off; q.acc = accvp + sgm.off;
+        q.stop_flag = stop;
+        q.do_update = (upd_layers && !(frozen_layers & bit)) ? 1 : 0; q.lr = lr; q.eps = eps;
+        q.zero_buf = sg + (size_t)Np * Kp + sgm.off;
+    }
+    mp.zero_scalars = scalars;
+    cudaError_t e = launch_multi_pass(mp, stream, n_sms);
+    if (e != cudaSuccess) { cuda_failed = true; return fail(this, PMF_ERR_CUDA, "update pass launch: %s", cudaGetErrorString(e)); }
+    launches++;
+    grads_clean = true;     // valid for the next epoch of this fit only (pmf_fit_start / pmf_loss_grad reset it)
+    return 0;
+}
+
+int pmf_model_s::run_factor_reg(int which, const int* stop) {
+    int rc = run_network_reg(which, stop);
+    if (rc != 0) return rc;
+    return run_reg_multi(which == 0, which == 1, false, stop);
 }
 
 int pmf_model_s::run_factor_update(int which, float lr, float eps, const int* stop) {
     FactorUpdateParams q;
     fill_factor_params(which, q);
     q.do_update = 1; q.lr = lr; q.eps = eps; q.stop_flag = stop;
+    if (which == 0) xsplit_valid = false;
     cudaError_t e = launch_factor_update(q, stream);
     if (e != cudaSuccess) { cuda_failed = true; return fail(this, PMF_ERR_CUDA, "factor update launch: %s", cudaGetErrorString(e)); }
     launches++;

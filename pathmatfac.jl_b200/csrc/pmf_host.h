@@ -81,6 +81,8 @@ struct pmf_model_s {
     float *X = nullptr, *dX = nullptr, *accX = nullptr;
     float *Y = nullptr, *accY = nullptr;
     float *Xh = nullptr, *Xl = nullptr;   // TF32 operand split of X for the tcgen05 path (lazy)
+    bool xsplit_valid = false;            // Xh / Xl match X (written by the update pass); else the launcher refreshes them
+    bool grads_clean = false;             // dX, sg and the loss scalars were cleared by the previous epoch's update pass
     bool auto_tc = true;                     // PMF_KERNEL_AUTO picks the tcgen05 path when it applies
     // per-column noise description
     float* weight = nullptr;
@@ -131,6 +133,9 @@ struct pmf_model_s {
     int run_data_pass(pmf::DataPassParams& p, int kind, int precision);
     void fill_factor_params(int which, pmf::FactorUpdateParams& q);
     int run_factor_reg(int which, const int* stop);
+    int run_network_reg(int which, const int* stop);
+    int run_reg_multi(bool x_side, bool y_side, bool vectors, const int* stop);
+    int run_update_multi(bool upd_X, bool upd_Y, bool upd_layers, float lr, float eps, const int* stop);
     int run_factor_update(int which, float lr, float eps, const int* stop);
     int run_vector_pass(bool reg_pass, bool update, float lr, float eps, const int* stop, bool respect_frozen);
 };

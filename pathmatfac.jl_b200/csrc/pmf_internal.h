@@ -71,6 +71,11 @@ struct FactorUpdateParams {
     int do_update;
     float lr, eps;
     const int* stop_flag;
+    // optional by-products of the update pass
+    float* Ph;                  // rna_tf32(P) and P - rna_tf32(P) of the UPDATED parameters (operands of the
+    float* Pl;                  //   tcgen05 data pass) or null
+    float* zero_buf;            // gradient buffer to clear once it has been consumed ([n_pad][Kp]) or null
+    int n_pad;
 };
 
 // 1-D parameters (logsigma | mu | logdelta | theta) with optional quadratic penalty.
@@ -87,6 +92,17 @@ struct VectorUpdateParams {
     int do_update;
     float lr, eps;
     const int* stop_flag;
+    float* zero_buf;            // gradient segment to clear once consumed, or null
+};
+
+// Several factor / vector passes in ONE launch (the per-epoch penalty pass and the per-epoch update
+// pass): segments share the grid in proportion to their size, so the small column-parameter work
+// hides inside the factor passes instead of paying a launch each.
+struct MultiPassParams {
+    int nf, nv;
+    FactorUpdateParams f[2];
+    VectorUpdateParams v[4];
+    double* zero_scalars;       // SC_COUNT doubles cleared by block 0 after the pass (next epoch's accumulators), or null
 };
 
 struct FitControl {
@@ -130,8 +146,9 @@ cudaError_t launch_data_pass_ffma(const DataPassParams& p, cudaStream_t s, int n
 // [Mp][64], are scratch operands refreshed by the launcher.  precision: 0/1 = 3xTF32 Z + TF32
 // gradients, 2 = TF32 everywhere.
 bool tc_supported(const DataPassParams& p);
-cudaError_t launch_data_pass_tc(const DataPassParams& p, float* Xh, float* Xl, int precision, cudaStream_t s,
-                                int n_sms);
+cudaError_t launch_data_pass_tc(const DataPassParams& p, float* Xh, float* Xl, bool refresh_split, int precision,
+                                cudaStream_t s, int n_sms);
+cudaError_t launch_multi_pass(const MultiPassParams& p, cudaStream_t s, int n_sms);
 cudaError_t launch_factor_update(const FactorUpdateParams& p, cudaStream_t s);
 cudaError_t launch_vector_update(const VectorUpdateParams& p, cudaStream_t s);
 cudaError_t launch_control(FitControl* ctrl, const double* scalars, double* hist, int hist_cap,

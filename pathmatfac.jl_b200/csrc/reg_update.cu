@@ -15,14 +15,19 @@ namespace {
 
 constexpr int UT = 256;
 
-__global__ void __launch_bounds__(UT) factor_update_kernel(FactorUpdateParams q) {
+__device__ __forceinline__ float tf32_rna(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+// one factor pass executed by blocks [0, nblk) of a (sub-)grid
+__device__ __forceinline__ void factor_pass(const FactorUpdateParams& q, int bid, int nblk, double* red_smem) {
     if (q.stop_flag != nullptr && *q.stop_flag != 0) return;
-    __shared__ double red_smem[UT / 32];
     const int K4 = q.Kp >> 2;
     const size_t total4 = (size_t)q.n * K4;
     double lsum = 0.0;
-    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total4;
-         idx += (size_t)gridDim.x * blockDim.x) {
+    for (size_t idx = (size_t)bid * blockDim.x + threadIdx.x; idx < total4; idx += (size_t)nblk * blockDim.x) {
         const int row = (int)(idx / K4), c4 = (int)(idx - (size_t)row * K4);
         const size_t off = (size_t)row * q.Kp + 4 * c4;
         float4 pv = *reinterpret_cast<const float4*>(q.P + off);
@@ -72,16 +77,34 @@ __global__ void __launch_bounds__(UT) factor_update_kernel(FactorUpdateParams q)
                 for (int c = 0; c < 4; ++c) q.PT[(size_t)(4 * c4 + c) * q.ldt + row] = pa[c];
             }
         }
+        if (q.Ph) {   // TF32 operand split of the (updated) parameters for the next tcgen05 data pass
+            float h[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) h[c] = tf32_rna(pa[c]);
+            *reinterpret_cast<float4*>(q.Ph + off) = make_float4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<float4*>(q.Pl + off) = make_float4(pa[0] - h[0], pa[1] - h[1], pa[2] - h[2], pa[3] - h[3]);
+        }
+        if (q.zero_buf) *reinterpret_cast<float4*>(q.zero_buf + off) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (q.zero_buf) {   // padding rows of the gradient buffer (the data pass may have added into them)
+        const size_t pad4 = (size_t)(q.n_pad - q.n) * K4;
+        float4* z = reinterpret_cast<float4*>(q.zero_buf + (size_t)q.n * q.Kp);
+        for (size_t idx = (size_t)bid * blockDim.x + threadIdx.x; idx < pad4; idx += (size_t)nblk * blockDim.x)
+            z[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     double tot = block_reduce_sum_double(lsum, red_smem);
     if (threadIdx.x == 0 && q.loss_out && tot != 0.0) atomicAdd(q.loss_out, tot);
 }
 
-__global__ void __launch_bounds__(UT) vector_update_kernel(VectorUpdateParams q) {
-    if (q.stop_flag != nullptr && *q.stop_flag != 0) return;
+__global__ void __launch_bounds__(UT) factor_update_kernel(FactorUpdateParams q) {
     __shared__ double red_smem[UT / 32];
+    factor_pass(q, blockIdx.x, gridDim.x, red_smem);
+}
+
+__device__ __forceinline__ void vector_pass(const VectorUpdateParams& q, int bid, int nblk, double* red_smem) {
+    if (q.stop_flag != nullptr && *q.stop_flag != 0) return;
     double lsum = 0.0;
-    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < q.n; idx += gridDim.x * blockDim.x) {
+    for (int idx = bid * blockDim.x + threadIdx.x; idx < q.n; idx += nblk * blockDim.x) {
         float x = q.p[idx];
         float g = q.grad[idx];
         if (q.reg_active && q.reg_w) {
@@ -95,9 +118,35 @@ __global__ void __launch_bounds__(UT) vector_update_kernel(VectorUpdateParams q)
             q.acc[idx] = a;
             q.p[idx] = x - q.lr * g / (sqrtf(a) + q.eps);
         }
+        if (q.zero_buf) q.zero_buf[idx] = 0.f;
     }
     double tot = block_reduce_sum_double(lsum, red_smem);
     if (threadIdx.x == 0 && q.loss_out && tot != 0.0) atomicAdd(q.loss_out, tot);
+}
+
+__global__ void __launch_bounds__(UT) vector_update_kernel(VectorUpdateParams q) {
+    __shared__ double red_smem[UT / 32];
+    vector_pass(q, blockIdx.x, gridDim.x, red_smem);
+}
+
+// Segments share the grid: factor segment s owns blocks [fb[s], fb[s+1]); the vector segments share the
+// last `vblocks` blocks one after the other (they are tiny).
+__global__ void __launch_bounds__(UT) multi_pass_kernel(const __grid_constant__ MultiPassParams mp, int fb1, int fb2) {
+    __shared__ double red_smem[UT / 32];
+    const int b = blockIdx.x;
+    if (mp.nf > 0 && b < fb1) factor_pass(mp.f[0], b, fb1, red_smem);
+    else if (mp.nf > 1 && b < fb2) factor_pass(mp.f[1], b - fb1, fb2 - fb1, red_smem);
+    else {
+        const int vb = b - fb2, nvb = gridDim.x - fb2;
+        for (int i = 0; i < mp.nv; ++i) {
+            vector_pass(mp.v[i], vb, nvb, red_smem);
+            __syncthreads();
+        }
+        if (vb == 0 && mp.zero_scalars != nullptr && threadIdx.x < SC_COUNT) {
+            const int* stop = mp.nv > 0 ? mp.v[0].stop_flag : (mp.nf > 0 ? mp.f[0].stop_flag : nullptr);
+            if (stop == nullptr || *stop == 0) mp.zero_scalars[threadIdx.x] = 0.0;
+        }
+    }
 }
 
 // Termination test of MF.fit!, evaluated on the device so the epoch loop
@@ -270,6 +319,26 @@ __global__ void transpose_sync_kernel(const float* __restrict__ P, float* __rest
 }
 
 }  // namespace
+
+cudaError_t launch_multi_pass(const MultiPassParams& mp, cudaStream_t s, int n_sms) {
+    auto fblocks = [&](const FactorUpdateParams& q) {
+        size_t total4 = (size_t)(q.zero_buf ? q.n_pad : q.n) * (q.Kp >> 2);
+        long long b = (long long)((total4 + UT - 1) / UT);
+        const long long cap = (long long)n_sms * 6;
+        return (int)(b > cap ? cap : (b < 1 ? 1 : b));
+    };
+    int fb1 = mp.nf > 0 ? fblocks(mp.f[0]) : 0;
+    int fb2 = fb1 + (mp.nf > 1 ? fblocks(mp.f[1]) : 0);
+    int nmax = 0;
+    for (int i = 0; i < mp.nv; ++i) nmax = mp.v[i].n > nmax ? mp.v[i].n : nmax;
+    int vblocks = (mp.nv > 0 || mp.zero_scalars) ? (nmax + UT - 1) / UT : 0;
+    if (vblocks > n_sms) vblocks = n_sms;
+    if ((mp.nv > 0 || mp.zero_scalars) && vblocks < 1) vblocks = 1;
+    const int grid = fb2 + vblocks;
+    if (grid <= 0) return cudaSuccess;
+    multi_pass_kernel<<<grid, UT, 0, s>>>(mp, fb1, fb2);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_factor_update(const FactorUpdateParams& p, cudaStream_t s) {
     size_t total4 = (size_t)p.n * (p.Kp >> 2);
