@@ -4,7 +4,8 @@
 // 128-feature x 64-sample tile of A (32 KB, streamed once through TMA-staged shared memory):
 //
 //   MMA1  Z[j,i]   = sum_k Y[j,k] X[i,k]     A = Y tile in TMEM (hi / lo), B = X tile in smem (K-major)
-//                                            3xTF32: Yh*Xh + Yl*Xh + Yh*Xl, FP32 accumulate in TMEM
+//                                            Yh*Xh in TF32 + the two first-order corrections Yl*Xh + Yh*Xl as ONE
+//                                            BF16 contraction over K = 128 ([Yl|Yh] x [Xh|Xl]); FP32 accumulate
 //   epilogue (16 warps, TMEM lane = feature j, so every column parameter is a per-thread
 //            register and every column-gradient sum is a private accumulator):
 //            ColScale/ColShift, noise loss, dL/dz with the NaN mask (src/layers.jl:9-90,
@@ -145,6 +146,13 @@ __device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a, uint64_t bdesc, u
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
         ::"r"(d), "r"(a), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
+// same with 16-bit operands (kind::f16, here BF16 x BF16 -> F32, K = 16 per instruction)
+__device__ __forceinline__ void mma_ts_f16(uint32_t d, uint32_t a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d), "r"(a), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
 // D[tmem] (+)= A[smem] * B[smem]
 __device__ __forceinline__ void mma_ss(uint32_t d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
     asm volatile(
@@ -199,6 +207,11 @@ __host__ __device__ constexpr uint32_t umma_idesc(int M, int N, bool a_mn, bool 
                  "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]),   \
                  "r"(r[31]) : "memory")
 
+#define TMEM_ST8(taddr, r)                                                                                        \
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"                         \
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]),        \
+                 "r"(r[7]) : "memory")
+
 #define TMEM_LD16(taddr, r)                                                                                       \
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "                                                        \
                  "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"                                  \
@@ -213,6 +226,12 @@ __host__ __device__ constexpr uint32_t umma_idesc(int M, int N, bool a_mn, bool 
                  "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]),      \
                  "r"(r[15]) : "memory")
 
+// two floats -> packed BF16 pair, `lo` in bits 0..15 (the even k of a 16-bit tensor-core operand)
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
 __device__ __forceinline__ uint32_t rna_tf32(float x) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -359,7 +378,7 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
                     const uint32_t dst = XK + rk.s * XK_BYTES;
                     for (int kb = 0; kb < 2; ++kb) {
                         tma_load_2d(dst + kb * 8192, &tmXh, bar(B_FULL_XK + rk.s), 32 * kb, i0);
-                        tma_load_2d(dst + XH_BYTES + kb * 8192, &tmXl, bar(B_FULL_XK + rk.s), 32 * kb, i0);
+                        tma_load_2d(dst + XH_BYTES + kb * 8192, &tmXl, bar(B_FULL_XK + rk.s), 64 * kb, i0);   // bf16 [Xh | Xl]
                     }
                     rk.next(SXK);
                     if (pend[0] >= 0) load_xm(pend[0]);
@@ -399,6 +418,8 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
         // ================================ MMA issuer ===============================================
         // One elected thread runs the whole role: barrier waits, tcgen05.mma, tcgen05.commit.
         const uint32_t id_z = umma_idesc(128, 64, false, false);   // Z  = Y(tmem) * Xh' : B K-major
+        // BF16 x BF16 -> F32 (kind::f16): c_format F32, a_format = b_format = BF16, both K-major
+        const uint32_t id_zb = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         const uint32_t id_dx = umma_idesc(64, 64, true, true);     // dX = G0'(smem, MN) * Yh(smem, MN)
         const uint32_t id_dy = umma_idesc(128, 64, false, true);   // dY = G0(tmem) * Xh(smem, MN)
         // All 512 columns are allocated by the only CTA on the SM, so the TMEM base is 0 (checked): a literal
@@ -417,10 +438,9 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
 #pragma unroll
             for (int s = 0; s < 8; ++s) mma_ts(zt, tmu + TM_YH + 8 * s, kstep(xh, s, 8192), id_z, s > 0 ? 1u : 0u);
             if (p.z_passes == 3) {
+                // [Yl | Yh] (bf16, TMEM) x [Xh | Xl] (bf16, smem): 128 k' = 8 instructions of K = 16
 #pragma unroll
-                for (int s = 0; s < 8; ++s) mma_ts(zt, tmu + TM_YL + 8 * s, kstep(xh, s, 8192), id_z, 1u);
-#pragma unroll
-                for (int s = 0; s < 8; ++s) mma_ts(zt, tmu + TM_YH + 8 * s, kstep(xl, s, 8192), id_z, 1u);
+                for (int s = 0; s < 8; ++s) mma_ts_f16(zt, tmu + TM_YL + 8 * s, kstep(xl, s, 8192), id_zb, 1u);
             }
             tc_commit_elect(bar(B_EMPTY_XK + rx1.s));
             tc_commit_elect(bar(B_Z_FULL + rz1.s));
@@ -618,24 +638,30 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
             // ---- Y tile: h = rna_tf32(y), l = y - h -> TMEM (A of MMA1); gscale * y -> shared memory (B of MMA2).
             // The previous item's MMAs have all completed (B_DY_FULL was waited on), so both are free.
             {
-                uint32_t hi[16], lo[16];
+                uint32_t hi[16], lob[8], hib[8];      // Yh (tf32), packed bf16 pairs of Yl and of Yh
 #pragma unroll
                 for (int v = 0; v < 4; ++v) {
                     const float4 y4 = cur.y[v];
                     float ys[4] = {y4.x, y4.y, y4.z, y4.w};
+                    float ls[4];
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         uint32_t hb = rna_tf32(ys[c]);
                         hi[4 * v + c] = hb;
-                        lo[4 * v + c] = __float_as_uint(ys[c] - __uint_as_float(hb));
+                        ls[c] = ys[c] - __uint_as_float(hb);
                     }
+                    lob[2 * v] = pack_bf16(ls[0], ls[1]);
+                    lob[2 * v + 1] = pack_bf16(ls[2], ls[3]);
+                    hib[2 * v] = pack_bf16(__uint_as_float(hi[4 * v]), __uint_as_float(hi[4 * v + 1]));
+                    hib[2 * v + 1] = pack_bf16(__uint_as_float(hi[4 * v + 2]), __uint_as_float(hi[4 * v + 3]));
                     *reinterpret_cast<uint4*>(ys_ptr + (uint32_t)(c16 >> 1) * 16384u + chunk_off(4 * (c16 & 1) + v)) =
                         make_uint4(rna_tf32(gscale * y4.x), rna_tf32(gscale * y4.y), rna_tf32(gscale * y4.z), rna_tf32(gscale * y4.w));
                 }
                 const bool trp = quarter == 0 && h32 == 0 && lane == 0;
                 if (trp) stamp(g, 19 + 6 * grp);
                 TMEM_ST16(tm + lane_addr + TM_YH + 16 * c16, hi);
-                TMEM_ST16(tm + lane_addr + TM_YL + 16 * c16, lo);
+                TMEM_ST8(tm + lane_addr + TM_YL + 8 * c16, lob);          // k' = 0..63  : Yl (pairs with Xh)
+                TMEM_ST8(tm + lane_addr + TM_YL + 32 + 8 * c16, hib);     // k' = 64..127: Yh (pairs with Xl)
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 tc_fence_before();
                 fence_async_smem();
@@ -812,18 +838,20 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
     }
 }
 
-// TF32 operand split of X:  Xh = rna_tf32(X),  Xl = X - Xh  (exact in FP32)
-__global__ void prep_operands_kernel(const float4* __restrict__ X, float4* __restrict__ Xh, float4* __restrict__ Xl,
+// Operand split of X:  Xh = rna_tf32(X) (FP32 array) and Xb = bf16([Xh | X - Xh]) ([Mp][128] BF16): the TF32
+// operand of every contraction and the BF16 operands of the first-order correction of Z
+__global__ void prep_operands_kernel(const float4* __restrict__ X, float4* __restrict__ Xh, uint2* __restrict__ Xb,
                                      size_t n4, const int* stop_flag) {
     if (stop_flag != nullptr && *stop_flag != 0) return;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
         const float4 v = X[i];
-        float4 h, l;
+        float4 h;
         h.x = __uint_as_float(rna_tf32(v.x)); h.y = __uint_as_float(rna_tf32(v.y));
         h.z = __uint_as_float(rna_tf32(v.z)); h.w = __uint_as_float(rna_tf32(v.w));
-        l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
         Xh[i] = h;
-        Xl[i] = l;
+        const size_t row = i >> 4, c4 = i & 15;            // 16 float4 per row of 64
+        Xb[row * 32 + c4] = make_uint2(pack_bf16(h.x, h.y), pack_bf16(h.z, h.w));
+        Xb[row * 32 + 16 + c4] = make_uint2(pack_bf16(v.x - h.x, v.y - h.y), pack_bf16(v.z - h.z, v.w - h.w));
     }
 }
 
@@ -844,6 +872,19 @@ EncodeTiledFn get_encode() {
 }
 
 // 2-D FP32 tensor [rows][cols] (cols contiguous, row pitch = pitch floats), box = box_rows x 32 floats
+// 2-D BF16 tensor [rows][cols], box = box_rows x 64 elements (one 128-byte swizzle row)
+bool make_map_bf16(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uint32_t box_rows) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return false;
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {cols * 2};
+    cuuint32_t box[2] = {64, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // atom32: 128B swizzle with 32-byte atoms (MN-major TF32 operands), else the standard 16-byte atoms
 bool make_map(CUtensorMap* m, const float* base, uint64_t cols, uint64_t rows, uint64_t pitch, uint32_t box_rows,
               bool nan_fill, bool atom32) {
@@ -889,14 +930,14 @@ cudaError_t launch_data_pass_tc(const DataPassParams& dp, float* Xh, float* Xl, 
     if (refresh_split) {   // otherwise the previous epoch's update pass wrote Xh / Xl together with X
         const size_t n4 = (size_t)dp.Mp * KK / 4;
         prep_operands_kernel<<<(unsigned)((n4 + 255) / 256 < 1184 ? (n4 + 255) / 256 : 1184), 256, 0, s>>>(
-            reinterpret_cast<const float4*>(dp.X), reinterpret_cast<float4*>(Xh), reinterpret_cast<float4*>(Xl), n4,
+            reinterpret_cast<const float4*>(dp.X), reinterpret_cast<float4*>(Xh), reinterpret_cast<uint2*>(Xl), n4,
             dp.stop_flag);
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }
 
     CUtensorMap tmXh, tmXl, tmXm, tmA, tmDX;
-    bool ok = make_map(&tmXh, Xh, KK, dp.Mp, KK, 64, false, false) && make_map(&tmXl, Xl, KK, dp.Mp, KK, 64, false, false) &&
+    bool ok = make_map(&tmXh, Xh, KK, dp.Mp, KK, 64, false, false) && make_map_bf16(&tmXl, Xl, 2 * KK, dp.Mp, 64) &&
               make_map(&tmXm, Xh, KK, dp.Mp, KK, 64, false, true) && make_map(&tmA, dp.A, dp.lda, dp.N, dp.lda, 128, true, true) &&
               make_map(&tmDX, dp.dX, KK, dp.Mp, KK, 64, false, false);
     if (!ok) return cudaErrorUnknown;

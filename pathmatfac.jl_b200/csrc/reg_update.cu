@@ -21,6 +21,12 @@ __device__ __forceinline__ float tf32_rna(float x) {
     return __uint_as_float(r);
 }
 
+__device__ __forceinline__ uint32_t bf16x2(float lo, float hi) {   // `lo` in bits 0..15
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+
 // one factor pass executed by blocks [0, nblk) of a (sub-)grid
 __device__ __forceinline__ void factor_pass(const FactorUpdateParams& q, int bid, int nblk, double* red_smem) {
     if (q.stop_flag != nullptr && *q.stop_flag != 0) return;
@@ -77,12 +83,14 @@ __device__ __forceinline__ void factor_pass(const FactorUpdateParams& q, int bid
                 for (int c = 0; c < 4; ++c) q.PT[(size_t)(4 * c4 + c) * q.ldt + row] = pa[c];
             }
         }
-        if (q.Ph) {   // TF32 operand split of the (updated) parameters for the next tcgen05 data pass
-            float h[4];
+        if (q.Ph) {   // operand split of the (updated) parameters for the next tcgen05 data pass (Kp == 64):
+            float h[4];   // Ph = rna_tf32(P) as FP32, Pl = bf16([Ph | P - Ph]) as [n][128] BF16
 #pragma unroll
             for (int c = 0; c < 4; ++c) h[c] = tf32_rna(pa[c]);
             *reinterpret_cast<float4*>(q.Ph + off) = make_float4(h[0], h[1], h[2], h[3]);
-            *reinterpret_cast<float4*>(q.Pl + off) = make_float4(pa[0] - h[0], pa[1] - h[1], pa[2] - h[2], pa[3] - h[3]);
+            uint2* pb = reinterpret_cast<uint2*>(q.Pl) + (size_t)row * 32 + c4;
+            pb[0] = make_uint2(bf16x2(h[0], h[1]), bf16x2(h[2], h[3]));
+            pb[16] = make_uint2(bf16x2(pa[0] - h[0], pa[1] - h[1]), bf16x2(pa[2] - h[2], pa[3] - h[3]));
         }
         if (q.zero_buf) *reinterpret_cast<float4*>(q.zero_buf + off) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
