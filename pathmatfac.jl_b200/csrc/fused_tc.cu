@@ -54,6 +54,7 @@ constexpr int NTHREADS = 32 * (NPRE + NEPI);
 // contractions of the neighbouring tiles, so one stage each suffices; the A/G ring is the HBM stream and
 // stays occupied from the TMA issue until MMA2 has consumed G0, so it gets every byte that is left.
 constexpr int SXK = 2, SXM = 1, SA = 3;
+static_assert(SXK >= 2, "the merged X producer loads XK(t) before XM(t-2): with one XK stage it deadlocks at item boundaries");
 constexpr int SZ = 3;                     // Z / G0 accumulators in TMEM
 constexpr uint32_t XH_BYTES = 16384, XK_BYTES = 32768 /* Xh | Xl */, XM_BYTES = 16384, YS_BYTES = 32768, AG_BYTES = 32768,
                    DXS_BYTES = 16384 /* dX tile staged for the TMA reduce-add */;
