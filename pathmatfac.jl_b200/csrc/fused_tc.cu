@@ -598,6 +598,19 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
 #pragma unroll
             for (int v = 0; v < 4; ++v) r.y[v] = __ldg(yrow + v);
         };
+        // L2 prefetch of the same addresses, issued a whole item earlier (the A stream evicts them from L2)
+        auto prefetch_item = [&](int item_) {
+            const int jt_ = item_ / p.chunks;
+            const int j_ = jt_ * BJ + lrow;
+            const int jj_ = j_ < dp.N ? j_ : 0;
+            if (c16 == 0) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(dp.logsigma + jj_));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(dp.mu + jj_));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(dp.weight + jj_));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(dp.colinfo + jj_));
+            }
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(dp.Y + (size_t)(jt_ * BJ + lrow) * KK + 16 * c16));
+        };
         ItemRegs cur;
         if ((int)blockIdx.x < p.n_items) load_item(blockIdx.x, cur);
         // column-side results of the previous item, reduced into global memory one item late (see the item
@@ -670,6 +683,7 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
                 mbar_arrive(bar(B_Y_READY));
                 if (trp) stamp(g, 21 + 6 * grp);
                 store_partials();
+                if (item + (int)gridDim.x < p.n_items) prefetch_item(item + gridDim.x);
             }
 
             // per-entry math on 16 consecutive samples: z[] (TMEM columns) in, dloss/dz (TF32-rounded bits) out
