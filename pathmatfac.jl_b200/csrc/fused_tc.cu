@@ -68,6 +68,11 @@ enum Bar { B_FULL_XK = 0, B_EMPTY_XK = B_FULL_XK + SXK, B_FULL_XM = B_EMPTY_XK +
            B_DXS_FULL, B_DXS_DONE /* one per group */, B_COUNT = B_DXS_DONE + 2 };
 
 // ---- PTX wrappers --------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -266,21 +271,58 @@ __device__ __noinline__ float2 noise_eval_slow(int dist, float z, float a, const
 
 struct TcParams {
     DataPassParams dp;
-    int n_jt, n_it, chunks, n_items;
+    int n_jt, n_it;
     int z_passes;      // 3 = 3xTF32 for the Z contraction, 1 = plain TF32
     int ablate;        // PMF_TC_ABLATE (performance experiments only; results are wrong when non-zero)
     long long* trace;  // PMF_TC_TRACE: per-tile clock64 stamps of one CTA (16 events x TRACE_TILES), else null
     int trace_cta;
     int flags;         // PMF_TC_FLAGS experiments (try_wait suspend hints)
 };
-constexpr int TRACE_TILES = 96, TRACE_EV = 32;
+constexpr int TRACE_TILES = 96, TRACE_EV = 32, TRACE_CTAS = 160;   // + per-CTA (start, end) clocks after the stamps
 
-__device__ __forceinline__ void item_range(const TcParams& p, int item, int& jt, int& it0, int& it1) {
-    jt = item / p.chunks;
-    int c = item - jt * p.chunks;
-    it0 = (int)((long long)p.n_it * c / p.chunks);
-    it1 = (int)((long long)p.n_it * (c + 1) / p.chunks);
-}
+// Work distribution.  The tiles, flattened feature-tile-major ([jt][it]), are cut into gridDim.x equal
+// contiguous ranges, one per CTA; a range is walked as ITEMS = maximal runs inside one feature tile (the Y
+// operands and the dY accumulator stay resident for an item).  Every CTA gets the same number of tiles
+// (+-1) and crosses at most a handful of feature-tile boundaries, where the pipeline has to drain.
+// The cut points are equidistant in COST: a tile of bernoulli columns (three MUFU per entry) takes longer
+// than a tile of normal columns, and a CTA's whole range may lie in one assay (tc_cost_cum, built by
+// pmf_set_noise, holds the cumulated per-feature-tile cost).
+struct ItemIter {
+    int t, t_end, n_it;
+    int jt, it0, it1;
+    // tile index at cost position  frac = num / den  of the whole pass
+    static __device__ __forceinline__ int cut(const TcParams& p, unsigned num, unsigned den) {
+        const int32_t* cum = p.dp.tc_cost_cum;
+        if (num >= den) return p.n_jt * p.n_it;
+        const long long W = (long long)cum[p.n_jt] * p.n_it;        // total cost in (cost x tile) units
+        const long long x = W * num / den;
+        int lo = 0, hi = p.n_jt;                                    // feature tile with cum[jt]*n_it <= x < cum[jt+1]*n_it
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if ((long long)cum[mid] * p.n_it <= x) lo = mid; else hi = mid;
+        }
+        const long long w = cum[lo + 1] - cum[lo];
+        int it = (int)((x - (long long)cum[lo] * p.n_it) / (w > 0 ? w : 1));
+        if (it > p.n_it) it = p.n_it;
+        return lo * p.n_it + it;
+    }
+    __device__ __forceinline__ explicit ItemIter(const TcParams& p) {
+        t = cut(p, blockIdx.x, gridDim.x);
+        t_end = cut(p, blockIdx.x + 1, gridDim.x);
+        n_it = p.n_it;
+        jt = it0 = it1 = 0;
+    }
+    __device__ __forceinline__ bool next() {
+        if (t >= t_end) return false;
+        jt = t / n_it;
+        it0 = t - jt * n_it;
+        const int len = min(n_it - it0, t_end - t);
+        it1 = it0 + len;
+        t += len;
+        return true;
+    }
+    __device__ __forceinline__ int peek_jt() const { return t < t_end ? t / n_it : -1; }   // feature tile of the NEXT item
+};
 
 // stage / parity bookkeeping of a ring of `n` buffers (avoids a modulo per tile)
 struct Ring {
@@ -308,11 +350,15 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
     auto bar = [&](int b) { return BARS + 8u * (uint32_t)b; };
     // event stamp of CTA 0 (timeline experiments; the branch is CTA-uniform)
     auto stamp = [&](uint32_t gg, int ev) {
-        if (DBG && p.trace != nullptr && blockIdx.x == (unsigned)p.trace_cta && gg < (uint32_t)TRACE_TILES) p.trace[gg * TRACE_EV + ev] = clock64();
+        if (DBG && p.trace != nullptr && blockIdx.x == (unsigned)p.trace_cta && gg < (uint32_t)TRACE_TILES &&
+            (!(p.flags & 16) || ev == 9))
+            p.trace[gg * TRACE_EV + ev] = clock64();
     };
 
     // warp index through a shuffle: the compiler then treats role branches as warp-uniform and keeps
     // MMA descriptors / barrier addresses in uniform registers
+    if (DBG && p.trace != nullptr && threadIdx.x == 0 && blockIdx.x < (unsigned)TRACE_CTAS)
+        p.trace[TRACE_TILES * TRACE_EV + 2 * blockIdx.x] = (long long)globaltimer_ns();
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const uint32_t hint_p = (p.flags & 2) ? 0x989680u : 0u, hint_m = (p.flags & 4) ? 0x989680u : 0u,
                    hint_e = (p.flags & 8) ? 0x989680u : 0u;   // try_wait suspend-time hints (experiments)
@@ -345,9 +391,8 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
         if (lane == 0 && warp == W_TMA_A) {
             Ring r;
             uint32_t gcount = 0;
-            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-                int jt, it0, it1;
-                item_range(p, item, jt, it0, it1);
+            for (ItemIter itx(p); itx.next();) {
+                const int jt = itx.jt, it0 = itx.it0, it1 = itx.it1;
                 const int j0 = jt * BJ;
                 for (int it = it0; it < it1; ++it, r.next(SA), ++gcount) {
                     const int i0 = it * BI;
@@ -369,9 +414,8 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
                     tma_load_2d(XM + rm.s * XM_BYTES + kb * 8192, &tmXm, bar(B_FULL_XM + rm.s), 32 * kb, i0);
                 rm.next(SXM);
             };
-            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-                int jt, it0, it1;
-                item_range(p, item, jt, it0, it1);
+            for (ItemIter itx(p); itx.next();) {
+                const int jt = itx.jt, it0 = itx.it0, it1 = itx.it1;
                 for (int it = it0; it < it1; ++it) {
                     const int i0 = it * BI;
                     mbar_wait(bar(B_EMPTY_XK + rk.s), rk.ph ^ 1, hint_p);
@@ -397,9 +441,8 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
         // epilogue warp ever blocks on the memory system.
         if (lane == 0) {
             uint32_t g = 0;
-            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-                int jt, it0, it1;
-                item_range(p, item, jt, it0, it1);
+            for (ItemIter itx(p); itx.next();) {
+                const int jt = itx.jt, it0 = itx.it0, it1 = itx.it1;
                 for (int it = it0; it < it1; ++it, ++g) {
                     mbar_wait(bar(B_DXS_FULL), g & 1, hint_p);
                     if (!(DBG && p.ablate & 16)) {
@@ -456,9 +499,8 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
             stamp(g1, 1);
             issue_mma1_nowait();
         };
-        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-            int jt, it0, it1;
-            item_range(p, item, jt, it0, it1);
+        for (ItemIter itx(p); itx.next();) {
+            const int jt = itx.jt, it0 = itx.it0, it1 = itx.it1;
             mbar_wait(bar(B_Y_READY), q & 1);
             mbar_wait(bar(B_DY_EMPTY), (q & 1) ^ 1);
             tc_fence_after();
@@ -586,10 +628,9 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
         // the Y row.  They are fetched one item AHEAD, right before the wait for the current item's last
         // contraction, so the two global round trips are off the item-to-item critical path.
         struct ItemRegs { float logsigma, mu, w; int ci; float4 y[4]; };
-        auto load_item = [&](int item_, ItemRegs& r) {
-            const int jt_ = item_ / p.chunks;
+        auto load_item = [&](int jt_, ItemRegs& r) {
             const int j_ = jt_ * BJ + lrow;
-            const int jj_ = j_ < dp.N ? j_ : 0;
+            const int jj_ = j_ < dp.N ? j_ : dp.N - 1;   // padding rows follow the last column (same noise model: no divergence)
             r.logsigma = __ldg(dp.logsigma + jj_);
             r.mu = __ldg(dp.mu + jj_);
             r.w = j_ < dp.N ? __ldg(dp.weight + jj_) : 0.f;
@@ -599,10 +640,9 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
             for (int v = 0; v < 4; ++v) r.y[v] = __ldg(yrow + v);
         };
         // L2 prefetch of the same addresses, issued a whole item earlier (the A stream evicts them from L2)
-        auto prefetch_item = [&](int item_) {
-            const int jt_ = item_ / p.chunks;
+        auto prefetch_item = [&](int jt_) {
             const int j_ = jt_ * BJ + lrow;
-            const int jj_ = j_ < dp.N ? j_ : 0;
+            const int jj_ = j_ < dp.N ? j_ : dp.N - 1;   // padding rows follow the last column (same noise model: no divergence)
             if (c16 == 0) {
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(dp.logsigma + jj_));
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(dp.mu + jj_));
@@ -612,9 +652,12 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
             asm volatile("prefetch.global.L2 [%0];" ::"l"(dp.Y + (size_t)(jt_ * BJ + lrow) * KK + 16 * c16));
         };
         ItemRegs cur;
-        if ((int)blockIdx.x < p.n_items) load_item(blockIdx.x, cur);
+        {
+            const int jt_first = ItemIter(p).peek_jt();
+            if (jt_first >= 0) load_item(jt_first, cur);
+        }
         // column-side results of the previous item, reduced into global memory one item late (see the item
-        // epilogue): 128-bit REDs for the dY tile (plain stores when a feature tile has a single chunk)
+        // epilogue): 128-bit REDs for the dY tile (several CTAs contribute to a feature tile)
         float4 pend_dy[4];
         float pend_dmu = 0.f, pend_dls = 0.f;
         int pend_j = -1;
@@ -623,8 +666,7 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
                 float4* dst = reinterpret_cast<float4*>(dp.dY + (size_t)pend_j * KK + 16 * c16);
 #pragma unroll
                 for (int v = 0; v < 4; ++v) {
-                    if (p.chunks == 1) dst[v] = pend_dy[v];
-                    else atomicAdd(dst + v, pend_dy[v]);
+                    atomicAdd(dst + v, pend_dy[v]);
                 }
                 atomicAdd(dp.dmu + pend_j, pend_dmu);
                 atomicAdd(dp.dlogsigma + pend_j, pend_dls);
@@ -632,9 +674,8 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
             pend_j = -1;
         };
 
-        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-            int jt, it0, it1;
-            item_range(p, item, jt, it0, it1);
+        for (ItemIter itx(p); itx.next();) {
+            const int jt = itx.jt, it0 = itx.it0, it1 = itx.it1;
             const int j = jt * BJ + lrow;
             const bool jok = j < dp.N;
             // per-thread column constants (lane = feature)
@@ -683,7 +724,7 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
                 mbar_arrive(bar(B_Y_READY));
                 if (trp) stamp(g, 21 + 6 * grp);
                 store_partials();
-                if (item + (int)gridDim.x < p.n_items) prefetch_item(item + gridDim.x);
+                if (itx.peek_jt() >= 0) prefetch_item(itx.peek_jt());
             }
 
             // per-entry math on 16 consecutive samples: z[] (TMEM columns) in, dloss/dz (TF32-rounded bits) out
@@ -816,7 +857,7 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
                 tc_fence_before();
                 mbar_arrive_relaxed(bar(B_DY_EMPTY));
                 // next item's operands: issued after the last arrive of this item so that no fence waits on them
-                if (item + (int)gridDim.x < p.n_items) load_item(item + gridDim.x, nxt);
+                if (itx.peek_jt() >= 0) load_item(itx.peek_jt(), nxt);
                 // The results stay in registers and are reduced into global memory AFTER the next item's Y
                 // operands have been published: REDs issued here would sit in front of that release-arrive's
                 // memory fence and serialise the item boundary.
@@ -842,6 +883,8 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
     }
     tc_fence_before();
     __syncthreads();
+    if (DBG && p.trace != nullptr && threadIdx.x == 0 && blockIdx.x < (unsigned)TRACE_CTAS)
+        p.trace[TRACE_TILES * TRACE_EV + 2 * blockIdx.x + 1] = (long long)globaltimer_ns();
     if (threadIdx.x == 0) {
         double t = 0.0;
         for (int w = 0; w < NEPI; ++w) t += red_smem[w];
@@ -922,21 +965,6 @@ bool tc_supported(const DataPassParams& p) {
     return p.Kp == KK && p.n_batch_views == 0 && p.col_ssq == nullptr;
 }
 
-// sample chunks per feature tile: maximise the fill of the last wave, at least 4 tiles per chunk
-int tc_chunks(const DataPassParams& dp, int n_sms) {
-    if (dp.sample_chunks > 0) return dp.sample_chunks;
-    const int n_jt = (dp.N + BJ - 1) / BJ, n_it = (dp.M + BI - 1) / BI;
-    int best_c = 1;
-    double best_eff = 0.0;
-    const int max_c = n_it / 4 > 0 ? n_it / 4 : 1;
-    for (int c = 1; c <= max_c && c <= 16; ++c) {
-        long long items = (long long)n_jt * c;
-        long long waves = (items + n_sms - 1) / n_sms;
-        double eff = (double)items / (double)(waves * n_sms) - 0.002 * c;   // mild preference for fewer chunks
-        if (eff > best_eff) { best_eff = eff; best_c = c; }
-    }
-    return best_c;
-}
 // Xh, Xl: [Mp][64] operand scratch owned by the handle; refreshed here when `refresh_split`
 cudaError_t launch_data_pass_tc(const DataPassParams& dp, float* Xh, float* Xl, bool refresh_split, int precision,
                                 cudaStream_t s, int n_sms) {
@@ -973,22 +1001,21 @@ cudaError_t launch_data_pass_tc(const DataPassParams& dp, float* Xh, float* Xl, 
     static const char* trace_path = getenv("PMF_TC_TRACE");
     static long long* trace_dev = nullptr;
     if (trace_path) {
-        if (!trace_dev) cudaMalloc(&trace_dev, sizeof(long long) * TRACE_TILES * TRACE_EV);
-        cudaMemsetAsync(trace_dev, 0, sizeof(long long) * TRACE_TILES * TRACE_EV, s);
+        if (!trace_dev) cudaMalloc(&trace_dev, sizeof(long long) * (TRACE_TILES * TRACE_EV + 2 * TRACE_CTAS));
+        cudaMemsetAsync(trace_dev, 0, sizeof(long long) * (TRACE_TILES * TRACE_EV + 2 * TRACE_CTAS), s);
         p.trace = trace_dev;
         const char* tc = getenv("PMF_TC_TRACE_CTA");
         p.trace_cta = tc ? atoi(tc) : 0;
     }
-    p.chunks = tc_chunks(dp, n_sms);
-    p.n_items = p.n_jt * p.chunks;
     const bool dbg = p.ablate != 0 || p.trace != nullptr;
     auto kern = dbg ? data_pass_tc_kernel<true> : data_pass_tc_kernel<false>;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TOTAL);
     if (e != cudaSuccess) return e;
-    int grid = p.n_items < n_sms ? p.n_items : n_sms;
+    const long long n_tiles = (long long)p.n_jt * p.n_it;
+    int grid = n_tiles < n_sms ? (int)n_tiles : n_sms;
     kern<<<grid, NTHREADS, SMEM_TOTAL, s>>>(tmXh, tmXl, tmXm, tmA, tmDX, p);
     if (trace_path) {      // experiments only: dump the stamps of this launch (synchronises the stream)
-        static long long host[TRACE_TILES * TRACE_EV];
+        static long long host[TRACE_TILES * TRACE_EV + 2 * TRACE_CTAS];
         cudaStreamSynchronize(s);
         cudaMemcpy(host, trace_dev, sizeof host, cudaMemcpyDeviceToHost);
         if (FILE* f = fopen(trace_path, "wb")) { fwrite(host, sizeof host, 1, f); fclose(f); }

@@ -87,6 +87,7 @@ struct pmf_model_s {
     // per-column noise description
     float* weight = nullptr;
     int32_t* colinfo = nullptr;
+    int32_t* tc_cost_cum = nullptr;          // cumulative per-feature-tile cost of the tcgen05 data pass (n_jt + 1)
     float* thresholds = nullptr;
     // vector parameters  vp = [logsigma Np | mu Np | logdelta nbp | theta nbp]
     // shared gradients   sg = [dY Np*Kp | dlogsigma Np | dmu Np | dlogdelta nbp | dtheta nbp]

@@ -22,6 +22,7 @@ struct DataPassParams {
     const float* __restrict__ weight;
     const int32_t* __restrict__ colinfo;      // dist | range_id << 8
     const float* __restrict__ thresholds;     // [n_ranges][4]
+    const int32_t* __restrict__ tc_cost_cum;  // [ceil(N/128) + 1] cumulative tile cost per feature tile (tcgen05 path)
     // batch layers (null / -1 when absent)
     int n_batch_views;
     int nb_max;                               // max n_batches over views
