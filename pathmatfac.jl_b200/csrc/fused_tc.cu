@@ -351,7 +351,7 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
     // event stamp of CTA 0 (timeline experiments; the branch is CTA-uniform)
     auto stamp = [&](uint32_t gg, int ev) {
         if (DBG && p.trace != nullptr && blockIdx.x == (unsigned)p.trace_cta && gg < (uint32_t)TRACE_TILES &&
-            (!(p.flags & 16) || ev == 9))
+            (!(p.flags & 16) || ev == 9) && (!(p.flags & 32) || ev == 1 || ev == 2 || ev == 3 || ev == 4 || ev >= 13))
             p.trace[gg * TRACE_EV + ev] = clock64();
     };
 
