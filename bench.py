@@ -43,6 +43,24 @@ def parse():
     return ap.parse_args()
 
 
+def ncu_traffic():
+    """DRAM bytes (read + write) per launch of the fused data pass, from the committed `ncu --set full`
+    capture of the same kernel on the same workload (profiles/); None when no capture is committed."""
+    path = os.path.join(ROOT, "profiles", "r1_tc_final_ncu_summary.csv")
+    if not os.path.exists(path):
+        return None, None
+    rd = wr = None
+    for line in open(path):
+        f = line.strip().split(",")
+        if len(f) == 3 and f[0] == "dram__bytes_read.sum":
+            rd = float(f[2]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[f[1]]
+        if len(f) == 3 and f[0] == "dram__bytes_write.sum":
+            wr = float(f[2]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[f[1]]
+    if rd is None or wr is None:
+        return None, None
+    return rd + wr, "profiles/r1_tc_final_ncu_summary.csv (ncu --set full, one launch at the C2 shape)"
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -296,8 +314,9 @@ def main():
     Kp = (K + 7) // 8 * 8
     alg_bytes = 4.0 * M * N + 2 * 4.0 * Kp * (M + N)     # A once + X,Y read + dX,dY written
     achieved = alg_bytes / (dp_mean_ms * 1e-3) / 1e9 if dp_mean_ms > 0 else 0.0
+    traffic, traffic_src = ncu_traffic() if (M, N, K) == (C2["M"], C2["N"], C2["K"]) and args.kernel != "ffma" else (None, None)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "fused data pass", "kernel_ms": dp_mean_ms, "kernel_min_ms": dp_min_ms,
+                "traffic": traffic, "traffic_source": traffic_src, "kernel": "fused data pass", "kernel_ms": dp_mean_ms, "kernel_min_ms": dp_min_ms,
                 "launches_timed": n_prof, "algorithmic_bytes": alg_bytes, "peak_source": peak_src,
                 "kernel_share_of_step": dp_mean_ms / (sec_per_step * 1e3)}
 
