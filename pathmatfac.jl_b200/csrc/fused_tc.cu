@@ -90,25 +90,15 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_arrive_relaxed(uint32_t bar) {
     asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t hint = 0) {
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done;
     do {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done) : "r"(bar), "r"(parity), "r"(hint) /* suspend-time hint */ : "memory");
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     } while (!done);
-}
-// non-blocking probe of a barrier phase
-__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
-    uint32_t done;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    return done != 0;
 }
 // Four barrier probes issued back to back (their shared-memory round trips overlap); bit k of the result
 // is set when barrier k has completed the phase with parity par_k.
@@ -276,7 +266,7 @@ struct TcParams {
     int ablate;        // PMF_TC_ABLATE (performance experiments only; results are wrong when non-zero)
     long long* trace;  // PMF_TC_TRACE: per-tile clock64 stamps of one CTA (16 events x TRACE_TILES), else null
     int trace_cta;
-    int flags;         // PMF_TC_FLAGS experiments (try_wait suspend hints)
+    int flags;         // PMF_TC_FLAGS: trace filters (16 = only the per-tile G_READY stamp, 32 = only the MMA thread)
 };
 constexpr int TRACE_TILES = 96, TRACE_EV = 32, TRACE_CTAS = 160;   // + per-CTA (start, end) clocks after the stamps
 
@@ -360,8 +350,6 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
     if (DBG && p.trace != nullptr && threadIdx.x == 0 && blockIdx.x < (unsigned)TRACE_CTAS)
         p.trace[TRACE_TILES * TRACE_EV + 2 * blockIdx.x] = (long long)globaltimer_ns();
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
-    const uint32_t hint_p = (p.flags & 2) ? 0x989680u : 0u, hint_m = (p.flags & 4) ? 0x989680u : 0u,
-                   hint_e = (p.flags & 8) ? 0x989680u : 0u;   // try_wait suspend-time hints (experiments)
     const int lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
@@ -392,11 +380,11 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
             Ring r;
             uint32_t gcount = 0;
             for (ItemIter itx(p); itx.next();) {
-                const int jt = itx.jt, it0 = itx.it0, it1 = itx.it1;
-                const int j0 = jt * BJ;
+                const int it0 = itx.it0, it1 = itx.it1;
+                const int j0 = itx.jt * BJ;
                 for (int it = it0; it < it1; ++it, r.next(SA), ++gcount) {
                     const int i0 = it * BI;
-                    mbar_wait(bar(B_EMPTY_AG + r.s), r.ph ^ 1, hint_p);
+                    mbar_wait(bar(B_EMPTY_AG + r.s), r.ph ^ 1);
                     stamp(gcount, 0);
                     mbar_expect_tx(bar(B_FULL_A + r.s), AG_BYTES);
                     for (int iq = 0; iq < 2; ++iq)
@@ -408,17 +396,17 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
             Ring rk, rm;
             int pend[2] = {-1, -1};       // sample offsets of the last two tiles whose MN-major copy is still due
             auto load_xm = [&](int i0) {
-                mbar_wait(bar(B_EMPTY_XM + rm.s), rm.ph ^ 1, hint_p);
+                mbar_wait(bar(B_EMPTY_XM + rm.s), rm.ph ^ 1);
                 mbar_expect_tx(bar(B_FULL_XM + rm.s), XM_BYTES);
                 for (int kb = 0; kb < 2; ++kb)
                     tma_load_2d(XM + rm.s * XM_BYTES + kb * 8192, &tmXm, bar(B_FULL_XM + rm.s), 32 * kb, i0);
                 rm.next(SXM);
             };
             for (ItemIter itx(p); itx.next();) {
-                const int jt = itx.jt, it0 = itx.it0, it1 = itx.it1;
+                const int it0 = itx.it0, it1 = itx.it1;
                 for (int it = it0; it < it1; ++it) {
                     const int i0 = it * BI;
-                    mbar_wait(bar(B_EMPTY_XK + rk.s), rk.ph ^ 1, hint_p);
+                    mbar_wait(bar(B_EMPTY_XK + rk.s), rk.ph ^ 1);
                     mbar_expect_tx(bar(B_FULL_XK + rk.s), XK_BYTES);
                     const uint32_t dst = XK + rk.s * XK_BYTES;
                     for (int kb = 0; kb < 2; ++kb) {
@@ -442,9 +430,9 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
         if (lane == 0) {
             uint32_t g = 0;
             for (ItemIter itx(p); itx.next();) {
-                const int jt = itx.jt, it0 = itx.it0, it1 = itx.it1;
+                const int it0 = itx.it0, it1 = itx.it1;
                 for (int it = it0; it < it1; ++it, ++g) {
-                    mbar_wait(bar(B_DXS_FULL), g & 1, hint_p);
+                    mbar_wait(bar(B_DXS_FULL), g & 1);
                     if (!(DBG && p.ablate & 16)) {
                         tma_reduce_add_2d(&tmDX, DXS, 0, it * BI);
                         tma_reduce_add_2d(&tmDX, DXS + 8192, 32, it * BI);
@@ -494,13 +482,13 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
         };
         auto issue_mma1 = [&]() {
             stamp(g1, 13);
-            mbar_wait(bar(B_FULL_XK + rx1.s), rx1.ph, hint_m);
+            mbar_wait(bar(B_FULL_XK + rx1.s), rx1.ph);
             tc_fence_after();
             stamp(g1, 1);
             issue_mma1_nowait();
         };
         for (ItemIter itx(p); itx.next();) {
-            const int jt = itx.jt, it0 = itx.it0, it1 = itx.it1;
+            const int it0 = itx.it0, it1 = itx.it1;
             mbar_wait(bar(B_Y_READY), q & 1);
             mbar_wait(bar(B_DY_EMPTY), (q & 1) ^ 1);
             tc_fence_after();
@@ -785,9 +773,9 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
                 if ((g & 1u) != (uint32_t)grp) continue;             // the other group's tile
                 const bool tr = quarter == 0 && h32 == 0 && lane == 0;
                 if (tr) stamp(g, 5);
-                mbar_wait(bar(B_Z_FULL + rz.s), rz.ph, hint_e);
+                mbar_wait(bar(B_Z_FULL + rz.s), rz.ph);
                 if (tr) stamp(g, 6);
-                mbar_wait(bar(B_FULL_A + ra.s), ra.ph, hint_e);
+                mbar_wait(bar(B_FULL_A + ra.s), ra.ph);
                 tc_fence_after();
                 if (tr) stamp(g, 7);
                 const uint32_t zt = tm + lane_addr + TM_Z0 + 64 * rz.s + 32 * h32;

@@ -211,7 +211,6 @@ int pmf_set_factors(pmf_handle h, const float* X, const float* Y) {
     if (X) CU(h, up2d(h->X, h->Kp, X, h->K, h->M, h->stream));
     if (Y) CU(h, up2d(h->Y, h->Kp, Y, h->K, h->N, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
-    h->transposes_stale = true;
     h->xsplit_valid = false;
     return PMF_OK;
 }
@@ -1153,47 +1152,3 @@ int pmf_model_s::run_update_multi(bool upd_X, bool upd_Y, bool upd_layers, float
     return 0;
 }
 
-int pmf_model_s::run_factor_reg(int which, const int* stop) {
-    int rc = run_network_reg(which, stop);
-    if (rc != 0) return rc;
-    return run_reg_multi(which == 0, which == 1, false, stop);
-}
-
-int pmf_model_s::run_factor_update(int which, float lr, float eps, const int* stop) {
-    FactorUpdateParams q;
-    fill_factor_params(which, q);
-    q.do_update = 1; q.lr = lr; q.eps = eps; q.stop_flag = stop;
-    if (which == 0) xsplit_valid = false;
-    cudaError_t e = launch_factor_update(q, stream);
-    if (e != cudaSuccess) { cuda_failed = true; return fail(this, PMF_ERR_CUDA, "factor update launch: %s", cudaGetErrorString(e)); }
-    launches++;
-    return 0;
-}
-
-// segments of the vector-parameter block: slot 1 logsigma, slot 3 mu, slot 2 logdelta, slot 4 theta
-int pmf_model_s::run_vector_pass(bool reg_pass, bool update, float lr, float eps, const int* stop, bool respect_frozen) {
-    struct Seg { size_t off; int n; int slot; };
-    Seg segs[4] = {{0, N, 1}, {(size_t)Np, N, 3}, {2 * (size_t)Np, (int)nbp, 2}, {2 * (size_t)Np + (size_t)nbp, (int)nbp, 4}};
-    for (const Seg& sgm : segs) {
-        if (sgm.n <= 0) continue;
-        const unsigned bit = 1u << (sgm.slot - 1);
-        VectorUpdateParams q;
-        std::memset(&q, 0, sizeof q);
-        q.n = sgm.n; q.p = vp + sgm.off; q.grad = sg + (size_t)Np * Kp + sgm.off; q.acc = accvp + sgm.off;
-        q.stop_flag = stop;
-        if (reg_pass) {
-            if (!layer_reg_present[sgm.slot - 1] || (frozen_regs & bit)) continue;
-            q.reg_w = regw + sgm.off; q.reg_c = regc + sgm.off; q.reg_active = 1;
-            q.grad_out = sg + (size_t)Np * Kp + sgm.off;
-            q.loss_out = scalars + SC_LAYERREG;
-        }
-        if (update) {
-            if (respect_frozen && (frozen_layers & bit)) continue;
-            q.do_update = 1; q.lr = lr; q.eps = eps;
-        }
-        cudaError_t e = launch_vector_update(q, stream);
-        if (e != cudaSuccess) { cuda_failed = true; return fail(this, PMF_ERR_CUDA, "vector pass launch: %s", cudaGetErrorString(e)); }
-        launches++;
-    }
-    return 0;
-}

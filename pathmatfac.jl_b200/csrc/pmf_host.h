@@ -71,7 +71,6 @@ struct pmf_model_s {
     std::string err;
     bool cuda_failed = false;
     bool have_data = false, have_noise = false;
-    bool transposes_stale = true;
 
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -133,10 +132,7 @@ struct pmf_model_s {
     int realloc_vectors(int new_nbp);
     int run_data_pass(pmf::DataPassParams& p, int kind, int precision);
     void fill_factor_params(int which, pmf::FactorUpdateParams& q);
-    int run_factor_reg(int which, const int* stop);
     int run_network_reg(int which, const int* stop);
     int run_reg_multi(bool x_side, bool y_side, bool vectors, const int* stop);
     int run_update_multi(bool upd_X, bool upd_Y, bool upd_layers, float lr, float eps, const int* stop);
-    int run_factor_update(int which, float lr, float eps, const int* stop);
-    int run_vector_pass(bool reg_pass, bool update, float lr, float eps, const int* stop, bool respect_frozen);
 };

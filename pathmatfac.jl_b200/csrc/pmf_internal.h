@@ -52,8 +52,6 @@ struct DataPassParams {
 struct FactorUpdateParams {
     int n, Kp, K;
     float* P;
-    float* PT;                  // optional transposed copy [Kp][n_pad_t] kept in sync (TC path) or null
-    int ldt;
     const float* grad;          // data gradient (already reduced over ranks)
     float* grad_out;            // if non-null: data+reg gradient is written here (parity hook)
     float* acc;                 // AdaGrad accumulator
@@ -150,11 +148,8 @@ bool tc_supported(const DataPassParams& p);
 cudaError_t launch_data_pass_tc(const DataPassParams& p, float* Xh, float* Xl, bool refresh_split, int precision,
                                 cudaStream_t s, int n_sms);
 cudaError_t launch_multi_pass(const MultiPassParams& p, cudaStream_t s, int n_sms);
-cudaError_t launch_factor_update(const FactorUpdateParams& p, cudaStream_t s);
-cudaError_t launch_vector_update(const VectorUpdateParams& p, cudaStream_t s);
 cudaError_t launch_control(FitControl* ctrl, const double* scalars, double* hist, int hist_cap,
                            int epoch, int max_epochs, double rel_tol, double abs_tol, cudaStream_t s);
 cudaError_t launch_network_reg(const NetworkParams& p, cudaStream_t s);
-cudaError_t launch_transpose_sync(const float* P, float* PT, int n, int Kp, int ldt, cudaStream_t s);
 
 }  // namespace pmf

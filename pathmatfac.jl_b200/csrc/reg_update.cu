@@ -78,10 +78,6 @@ __device__ __forceinline__ void factor_pass(const FactorUpdateParams& q, int bid
             }
             *reinterpret_cast<float4*>(q.acc + off) = make_float4(aa[0], aa[1], aa[2], aa[3]);
             *reinterpret_cast<float4*>(q.P + off) = make_float4(pa[0], pa[1], pa[2], pa[3]);
-            if (q.PT) {
-#pragma unroll
-                for (int c = 0; c < 4; ++c) q.PT[(size_t)(4 * c4 + c) * q.ldt + row] = pa[c];
-            }
         }
         if (q.Ph) {   // operand split of the (updated) parameters for the next tcgen05 data pass (Kp == 64):
             float h[4];   // Ph = rna_tf32(P) as FP32, Pl = bf16([Ph | P - Ph]) as [n][128] BF16
@@ -102,11 +98,6 @@ __device__ __forceinline__ void factor_pass(const FactorUpdateParams& q, int bid
     }
     double tot = block_reduce_sum_double(lsum, red_smem);
     if (threadIdx.x == 0 && q.loss_out && tot != 0.0) atomicAdd(q.loss_out, tot);
-}
-
-__global__ void __launch_bounds__(UT) factor_update_kernel(FactorUpdateParams q) {
-    __shared__ double red_smem[UT / 32];
-    factor_pass(q, blockIdx.x, gridDim.x, red_smem);
 }
 
 __device__ __forceinline__ void vector_pass(const VectorUpdateParams& q, int bid, int nblk, double* red_smem) {
@@ -130,11 +121,6 @@ __device__ __forceinline__ void vector_pass(const VectorUpdateParams& q, int bid
     }
     double tot = block_reduce_sum_double(lsum, red_smem);
     if (threadIdx.x == 0 && q.loss_out && tot != 0.0) atomicAdd(q.loss_out, tot);
-}
-
-__global__ void __launch_bounds__(UT) vector_update_kernel(VectorUpdateParams q) {
-    __shared__ double red_smem[UT / 32];
-    vector_pass(q, blockIdx.x, gridDim.x, red_smem);
 }
 
 // Segments share the grid: factor segment s owns blocks [fb[s], fb[s+1]); the vector segments share the
@@ -312,19 +298,6 @@ __global__ void __launch_bounds__(NTH) network_reg_kernel(NetworkParams q) {
     if (threadIdx.x == 0) atomicAdd(q.loss_out, (double)(q.p * tot));
 }
 
-__global__ void transpose_sync_kernel(const float* __restrict__ P, float* __restrict__ PT, int n, int Kp, int ldt) {
-    __shared__ float t[32][33];
-    int r0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
-    for (int rr = threadIdx.y; rr < 32; rr += blockDim.y) {
-        int r = r0 + rr, k = k0 + threadIdx.x;
-        t[rr][threadIdx.x] = (r < n && k < Kp) ? P[(size_t)r * Kp + k] : 0.f;
-    }
-    __syncthreads();
-    for (int kk = threadIdx.y; kk < 32; kk += blockDim.y) {
-        int k = k0 + kk, r = r0 + threadIdx.x;
-        if (k < Kp && r < ldt) PT[(size_t)k * ldt + r] = (r < n) ? t[threadIdx.x][kk] : 0.f;
-    }
-}
 
 }  // namespace
 
@@ -348,23 +321,6 @@ cudaError_t launch_multi_pass(const MultiPassParams& mp, cudaStream_t s, int n_s
     return cudaGetLastError();
 }
 
-cudaError_t launch_factor_update(const FactorUpdateParams& p, cudaStream_t s) {
-    size_t total4 = (size_t)p.n * (p.Kp >> 2);
-    int blocks = (int)((total4 + UT - 1) / UT);
-    if (blocks > 148 * 8) blocks = 148 * 8;
-    if (blocks < 1) blocks = 1;
-    factor_update_kernel<<<blocks, UT, 0, s>>>(p);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_vector_update(const VectorUpdateParams& p, cudaStream_t s) {
-    if (p.n <= 0) return cudaSuccess;
-    int blocks = (p.n + UT - 1) / UT;
-    if (blocks > 148 * 8) blocks = 148 * 8;
-    vector_update_kernel<<<blocks, UT, 0, s>>>(p);
-    return cudaGetLastError();
-}
-
 cudaError_t launch_control(FitControl* ctrl, const double* scalars, double* hist, int hist_cap, int epoch,
                            int max_epochs, double rel_tol, double abs_tol, cudaStream_t s) {
     control_kernel<<<1, 1, 0, s>>>(ctrl, scalars, hist, hist_cap, epoch, max_epochs, rel_tol, abs_tol);
@@ -376,10 +332,5 @@ cudaError_t launch_network_reg(const NetworkParams& p, cudaStream_t s) {
     return cudaGetLastError();
 }
 
-cudaError_t launch_transpose_sync(const float* P, float* PT, int n, int Kp, int ldt, cudaStream_t s) {
-    dim3 grid((ldt + 31) / 32, (Kp + 31) / 32), block(32, 8);
-    transpose_sync_kernel<<<grid, block, 0, s>>>(P, PT, n, Kp, ldt);
-    return cudaGetLastError();
-}
 
 }  // namespace pmf
