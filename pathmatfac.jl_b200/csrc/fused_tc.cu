@@ -1,4 +1,4 @@
-// Fused data pass on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), K = 64.
+// Fused data pass on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), K <= 64 (operands zero padded to 64).
 //
 // One persistent CTA per SM walks work items (feature tile of 128 x chunk of samples).  Per
 // 128-feature x 64-sample tile of A (32 KB, streamed once through TMA-staged shared memory):
@@ -435,7 +435,7 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
                     mbar_wait(bar(B_DXS_FULL), g & 1);
                     if (!(DBG && p.ablate & 16)) {
                         tma_reduce_add_2d(&tmDX, DXS, 0, it * BI);
-                        tma_reduce_add_2d(&tmDX, DXS + 8192, 32, it * BI);
+                        if (dp.Kp > 32) tma_reduce_add_2d(&tmDX, DXS + 8192, 32, it * BI);
                     }
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -623,9 +623,12 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
             r.mu = __ldg(dp.mu + jj_);
             r.w = j_ < dp.N ? __ldg(dp.weight + jj_) : 0.f;
             r.ci = __ldg(dp.colinfo + jj_);
-            const float4* yrow = reinterpret_cast<const float4*>(dp.Y + (size_t)(jt_ * BJ + lrow) * KK) + 4 * c16;
+            // K <= 64: the factor arrays keep their own pitch Kp; columns k >= Kp are zeros here, in the
+            // operand scratch (Xh / Xb are 64 / 128 wide and zero padded) and in every TMA box (OOB fill)
+            const float4* yrow = reinterpret_cast<const float4*>(dp.Y + (size_t)(jt_ * BJ + lrow) * dp.Kp) + 4 * c16;
 #pragma unroll
-            for (int v = 0; v < 4; ++v) r.y[v] = __ldg(yrow + v);
+            for (int v = 0; v < 4; ++v)
+                r.y[v] = (16 * c16 + 4 * v < dp.Kp) ? __ldg(yrow + v) : make_float4(0.f, 0.f, 0.f, 0.f);
         };
         // L2 prefetch of the same addresses, issued a whole item earlier (the A stream evicts them from L2)
         auto prefetch_item = [&](int jt_) {
@@ -637,7 +640,8 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(dp.weight + jj_));
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(dp.colinfo + jj_));
             }
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(dp.Y + (size_t)(jt_ * BJ + lrow) * KK + 16 * c16));
+            if (16 * c16 < dp.Kp)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(dp.Y + (size_t)(jt_ * BJ + lrow) * dp.Kp + 16 * c16));
         };
         ItemRegs cur;
         {
@@ -651,11 +655,10 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
         int pend_j = -1;
         auto store_partials = [&]() {
             if (pend_j >= 0) {
-                float4* dst = reinterpret_cast<float4*>(dp.dY + (size_t)pend_j * KK + 16 * c16);
+                float4* dst = reinterpret_cast<float4*>(dp.dY + (size_t)pend_j * dp.Kp + 16 * c16);
 #pragma unroll
-                for (int v = 0; v < 4; ++v) {
-                    atomicAdd(dst + v, pend_dy[v]);
-                }
+                for (int v = 0; v < 4; ++v)
+                    if (16 * c16 + 4 * v < dp.Kp) atomicAdd(dst + v, pend_dy[v]);
                 atomicAdd(dp.dmu + pend_j, pend_dmu);
                 atomicAdd(dp.dlogsigma + pend_j, pend_dls);
             }
@@ -887,15 +890,16 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
 // Operand split of X:  Xh = rna_tf32(X) (FP32 array) and Xb = bf16([Xh | X - Xh]) ([Mp][128] BF16): the TF32
 // operand of every contraction and the BF16 operands of the first-order correction of Z
 __global__ void prep_operands_kernel(const float4* __restrict__ X, float4* __restrict__ Xh, uint2* __restrict__ Xb,
-                                     size_t n4, const int* stop_flag) {
+                                     int rows, int K4 /* Kp / 4 */, const int* stop_flag) {
     if (stop_flag != nullptr && *stop_flag != 0) return;
+    const size_t n4 = (size_t)rows * K4;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
         const float4 v = X[i];
         float4 h;
         h.x = __uint_as_float(rna_tf32(v.x)); h.y = __uint_as_float(rna_tf32(v.y));
         h.z = __uint_as_float(rna_tf32(v.z)); h.w = __uint_as_float(rna_tf32(v.w));
-        Xh[i] = h;
-        const size_t row = i >> 4, c4 = i & 15;            // 16 float4 per row of 64
+        const size_t row = i / K4, c4 = i - row * K4;
+        Xh[row * 16 + c4] = h;                             // 16 float4 per 64-wide scratch row
         Xb[row * 32 + c4] = make_uint2(pack_bf16(h.x, h.y), pack_bf16(h.z, h.w));
         Xb[row * 32 + 16 + c4] = make_uint2(pack_bf16(v.x - h.x, v.y - h.y), pack_bf16(v.z - h.z, v.w - h.w));
     }
@@ -950,7 +954,7 @@ bool make_map(CUtensorMap* m, const float* base, uint64_t cols, uint64_t rows, u
 }  // namespace
 
 bool tc_supported(const DataPassParams& p) {
-    return p.Kp == KK && p.n_batch_views == 0 && p.col_ssq == nullptr;
+    return p.Kp <= KK && p.Kp >= 8 && p.n_batch_views == 0 && p.col_ssq == nullptr;
 }
 
 // Xh, Xl: [Mp][64] operand scratch owned by the handle; refreshed here when `refresh_split`
@@ -959,10 +963,10 @@ cudaError_t launch_data_pass_tc(const DataPassParams& dp, float* Xh, float* Xl, 
     if (!tc_supported(dp)) return cudaErrorInvalidValue;
     cudaError_t e = cudaSuccess;
     if (refresh_split) {   // otherwise the previous epoch's update pass wrote Xh / Xl together with X
-        const size_t n4 = (size_t)dp.Mp * KK / 4;
+        const size_t n4 = (size_t)dp.Mp * dp.Kp / 4;
         prep_operands_kernel<<<(unsigned)((n4 + 255) / 256 < 1184 ? (n4 + 255) / 256 : 1184), 256, 0, s>>>(
-            reinterpret_cast<const float4*>(dp.X), reinterpret_cast<float4*>(Xh), reinterpret_cast<uint2*>(Xl), n4,
-            dp.stop_flag);
+            reinterpret_cast<const float4*>(dp.X), reinterpret_cast<float4*>(Xh), reinterpret_cast<uint2*>(Xl), dp.Mp,
+            dp.Kp / 4, dp.stop_flag);
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }
@@ -970,7 +974,7 @@ cudaError_t launch_data_pass_tc(const DataPassParams& dp, float* Xh, float* Xl, 
     CUtensorMap tmXh, tmXl, tmXm, tmA, tmDX;
     bool ok = make_map(&tmXh, Xh, KK, dp.Mp, KK, 64, false, false) && make_map_bf16(&tmXl, Xl, 2 * KK, dp.Mp, 64) &&
               make_map(&tmXm, Xh, KK, dp.Mp, KK, 64, false, true) && make_map(&tmA, dp.A, dp.lda, dp.N, dp.lda, 128, true, true) &&
-              make_map(&tmDX, dp.dX, KK, dp.Mp, KK, 64, false, false);
+              make_map(&tmDX, dp.dX, dp.Kp, dp.Mp, dp.Kp, 64, false, false);
     if (!ok) return cudaErrorUnknown;
 
     TcParams p;

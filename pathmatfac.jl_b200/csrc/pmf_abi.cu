@@ -996,14 +996,17 @@ int pmf_model_s::realloc_vectors(int new_nbp) {
 int pmf_model_s::run_data_pass(DataPassParams& p, int kind, int precision) {
     const bool tc_ok = tc_supported(p) && cc_major == 10;
     if (kind == PMF_KERNEL_TC && !tc_ok)
-        return fail(this, PMF_ERR_ARG, "tcgen05 data pass needs K == 64 (padded), no batch layers and an sm_100 device");
+        return fail(this, PMF_ERR_ARG, "tcgen05 data pass needs K <= 64, no batch layers and an sm_100 device");
     // AUTO: the tcgen05 path pays off (and its single-pass TF32 gradient contractions average below
     // the 1e-4 parity bar) on large problems; small ones run the exact-FP32 FFMA kernel.
     const bool big = (double)M * (double)N >= 4.0e6 && M >= 1024;
     const bool use_tc = kind == PMF_KERNEL_TC || (kind == PMF_KERNEL_AUTO && tc_ok && auto_tc && big);
     if (use_tc) {
         if (!Xh) {
-            if (dev_alloc(&Xh, (size_t)Mp * Kp) != cudaSuccess || dev_alloc(&Xl, (size_t)Mp * Kp) != cudaSuccess)
+            // 64-wide FP32 and 128-wide BF16 operand scratch, zero padded beyond Kp (never written there)
+            if (dev_alloc(&Xh, (size_t)Mp * 64) != cudaSuccess || dev_alloc(&Xl, (size_t)Mp * 64) != cudaSuccess ||
+                cudaMemsetAsync(Xh, 0, (size_t)Mp * 64 * 4, stream) != cudaSuccess ||
+                cudaMemsetAsync(Xl, 0, (size_t)Mp * 64 * 4, stream) != cudaSuccess)
                 return fail(this, PMF_ERR_ALLOC, "device allocation failed");
         }
         cudaEvent_t t0 = nullptr, t1 = nullptr;

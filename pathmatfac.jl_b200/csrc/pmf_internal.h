@@ -141,9 +141,10 @@ struct NetworkParams {
 
 // launchers (each defined next to its kernel)
 cudaError_t launch_data_pass_ffma(const DataPassParams& p, cudaStream_t s, int n_sms);
-// tcgen05 path (fused_tc.cu): K == 64, no batch layers.  Xh = rna_tf32(X), Xl = X - Xh, both
-// [Mp][64], are scratch operands refreshed by the launcher.  precision: 0/1 = 3xTF32 Z + TF32
-// gradients, 2 = TF32 everywhere.
+// tcgen05 path (fused_tc.cu): K <= 64 (operands zero padded to 64), no batch layers.  Xh = rna_tf32(X)
+// ([Mp][64] FP32) and Xl = bf16([Xh | X - Xh]) ([Mp][128] BF16) are scratch operands kept by the update pass
+// (refreshed by the launcher when `refresh_split`).  precision: 0/1 = TF32 + BF16 first-order corrections for
+// Z and TF32 gradients, 2 = TF32 everywhere.
 bool tc_supported(const DataPassParams& p);
 cudaError_t launch_data_pass_tc(const DataPassParams& p, float* Xh, float* Xl, bool refresh_split, int precision,
                                 cudaStream_t s, int n_sms);

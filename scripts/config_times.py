@@ -40,6 +40,9 @@ def build(name, rng):
     if name == "C2":
         return simulate_problem(10000, blocks=C2_BLOCKS, K=64, seed=2, missing=0.3, model_kwargs=dict(lambda_X_l2=1.0)), \
             "10000x30000 K=64 mixed, 30% missing"
+    if name == "P25":
+        return simulate_problem(10000, blocks=C2_BLOCKS, K=25, seed=2, missing=0.3, model_kwargs=dict(lambda_X_l2=1.0)), \
+            "C2 shape at the reference's production latent dimension K=25 (fit_matfac.jl:150)"
     if name == "C3":
         views = [b[0] for b in C2_BLOCKS]
         return simulate_problem(10000, blocks=C2_BLOCKS, K=64, seed=3, missing=0.3, batch_views=views, n_batches=40,

@@ -397,3 +397,48 @@ def test_nccl_exchange_single_rank_matches_plain_fit():
         eng.close()
     assert h["epochs"] == h_plain["epochs"]
     assert np.max(np.abs(np.array(h["loss"]) / np.array(h_plain["loss"]) - 1)) < 1e-6
+
+
+@pytest.mark.parametrize("K", [8, 20, 25, 40, 64])
+def test_tc_small_latent_dimension(K):
+    """K <= 64 runs on the tcgen05 path with operands zero padded to 64 (the reference's production
+    runs use K = 20-25, analyses/scripts/julia/fit_matfac.jl:150)."""
+    views = {"mutation": ("bernoulli", 150), "methylation": ("normal", 300), "counts": ("poisson", 90)}
+    model, om, D = make_pair(700, views, K=K, seed=60 + K, missing=0.25, lambda_X_l2=1.0)
+    eng = P.Engine(model)
+    try:
+        eng.set_loss_grad_kernel(_lib.KERNEL_TC, 0)
+        got = eng.loss_grad(include_reg=True)
+    finally:
+        eng.close()
+    ref = O.total_loss_grads(om, D)
+    assert got["dX"].shape == (K, 700) and got["dY"].shape == (K, 540)
+    assert abs(got["loss"] - ref["loss"]) <= 1e-5 * abs(ref["loss"])
+    assert relerr(got["dmu"], ref["dmu"]) < 1e-4 and relerr(got["dlogsigma"], ref["dlogsigma"]) < 1e-4
+    assert relerr(got["dY"], ref["dY"]) < 5e-4 and relerr(got["dX"], ref["dX"]) < 5e-4
+    # and a short fit through the fused update pass (which maintains the padded operand scratch)
+    h = P.mf_fit(model, lr=0.1, max_epochs=4, update_X=True, update_Y=True, update_col_layers=True, rel_tol=0,
+                 abs_tol=0, verbosity=0, kernel=_lib.KERNEL_TC)
+    href = O.mf_fit(om, D, O.AdaGrad(0.1), max_epochs=4, update_X=True, update_Y=True, update_col_layers=True,
+                    rel_tol=0, abs_tol=0)
+    assert np.max(np.abs(np.array(h["loss"]) / np.array(href["loss"]) - 1)) < 1e-4
+
+
+def test_tc_refuses_unsupported_shapes():
+    """PMF_KERNEL_TC on a model the tcgen05 kernel does not cover is an error, never a silent fallback."""
+    model, om, D = make_pair(200, {"methylation": ("normal", 100)}, K=72, seed=70)
+    eng = P.Engine(model)
+    try:
+        eng.set_loss_grad_kernel(_lib.KERNEL_TC, 0)
+        with pytest.raises(_lib.PmfError):
+            eng.loss_grad(include_reg=False)
+    finally:
+        eng.close()
+    model, om, D = make_pair(200, {"methylation": ("normal", 100)}, K=16, seed=71, batch_views=["methylation"], n_batches=3)
+    eng = P.Engine(model)
+    try:
+        eng.set_loss_grad_kernel(_lib.KERNEL_TC, 0)
+        with pytest.raises(_lib.PmfError):
+            eng.loss_grad(include_reg=False)
+    finally:
+        eng.close()
