@@ -115,8 +115,17 @@ def load():
     if _lib is not None:
         return _lib
     if not os.path.exists(LIB_PATH):
-        raise PmfError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
-                       "(libpmf has no CPU fallback)")
+        # a source checkout without the built library: compile it in-tree (nvcc, sm_100a); there is no
+        # other execution path, so a failed build is a hard error
+        try:
+            import importlib.util
+            spec = importlib.util.spec_from_file_location("pmf_build", os.path.join(os.path.dirname(LIB_PATH), "build.py"))
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            mod.build(force=False)
+        except Exception as exc:   # noqa: BLE001
+            raise PmfError(f"{LIB_PATH} is missing and could not be built ({exc}): run "
+                           "`python -c 'import __graft_entry__ as g; g.build()'` (libpmf has no CPU fallback)")
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)

@@ -452,8 +452,10 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
         const uint32_t id_z = umma_idesc(128, 64, false, false);   // Z  = Y(tmem) * Xh' : B K-major
         // BF16 x BF16 -> F32 (kind::f16): c_format F32, a_format = b_format = BF16, both K-major
         const uint32_t id_zb = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-        const uint32_t id_dx = umma_idesc(64, 64, true, true);     // dX = G0'(smem, MN) * Yh(smem, MN)
-        const uint32_t id_dy = umma_idesc(128, 64, false, true);   // dY = G0(tmem) * Xh(smem, MN)
+        // K < 64: the contraction of MMA1 stops at Kp and the gradient tiles are only Kp columns wide
+        const int kn = dp.Kp;                                       // multiple of 8, <= 64
+        const uint32_t id_dx = umma_idesc(64, kn, true, true);     // dX = G0'(smem, MN) * Yh(smem, MN)
+        const uint32_t id_dy = umma_idesc(128, kn, false, true);   // dY = G0(tmem) * Xh(smem, MN)
         // All 512 columns are allocated by the only CTA on the SM, so the TMEM base is 0 (checked): a literal
         // keeps every tcgen05.mma operand in uniform registers (no per-instruction R2UR).
         if (tm != 0u) __trap();
@@ -468,11 +470,13 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
             const uint32_t zt = tmu + TM_Z0 + 64 * rz1.s;
             const uint64_t xh = umma_desc_k(XK + rx1.s * XK_BYTES), xl = umma_desc_k(XK + rx1.s * XK_BYTES + XH_BYTES);
 #pragma unroll
-            for (int s = 0; s < 8; ++s) mma_ts(zt, tmu + TM_YH + 8 * s, kstep(xh, s, 8192), id_z, s > 0 ? 1u : 0u);
+            for (int s = 0; s < 8; ++s)
+                if (8 * s < kn) mma_ts(zt, tmu + TM_YH + 8 * s, kstep(xh, s, 8192), id_z, s > 0 ? 1u : 0u);
             if (p.z_passes == 3) {
                 // [Yl | Yh] (bf16, TMEM) x [Xh | Xl] (bf16, smem): 128 k' = 8 instructions of K = 16
 #pragma unroll
-                for (int s = 0; s < 8; ++s) mma_ts_f16(zt, tmu + TM_YL + 8 * s, kstep(xl, s, 8192), id_zb, 1u);
+                for (int s = 0; s < 8; ++s)
+                    if (16 * (s & 3) < kn) mma_ts_f16(zt, tmu + TM_YL + 8 * s, kstep(xl, s, 8192), id_zb, 1u);
             }
             tc_commit_elect(bar(B_EMPTY_XK + rx1.s));
             tc_commit_elect(bar(B_Z_FULL + rz1.s));
