@@ -1,33 +1,36 @@
 // Fused data pass on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), K <= 64 (operands zero padded to 64).
 //
-// One persistent CTA per SM walks work items (feature tile of 128 x chunk of samples).  Per
-// 128-feature x 64-sample tile of A (32 KB, streamed once through TMA-staged shared memory):
+// One persistent CTA per SM walks a contiguous, cost-balanced range of 128-feature x 64-sample tiles of A
+// (ItemIter); the maximal runs inside one feature tile are the ITEMS for which the Y operands and the dY
+// accumulator stay resident.  Per tile (32 KB of A, streamed once through a TMA-fed shared-memory ring):
 //
-//   MMA1  Z[j,i]   = sum_k Y[j,k] X[i,k]     A = Y tile in TMEM (hi / lo), B = X tile in smem (K-major)
-//                                            Yh*Xh in TF32 + the two first-order corrections Yl*Xh + Yh*Xl as ONE
-//                                            BF16 contraction over K = 128 ([Yl|Yh] x [Xh|Xl]); FP32 accumulate
-//   epilogue (16 warps, TMEM lane = feature j, so every column parameter is a per-thread
-//            register and every column-gradient sum is a private accumulator):
-//            ColScale/ColShift, noise loss, dL/dz with the NaN mask (src/layers.jl:9-90,
-//            Appendix B of SURVEY.md).  G0 is written back to TMEM in place of Z and, with 128-bit
-//            stores, into shared memory IN PLACE of the A values the same thread just read.
-//   MMA2  dX[i,k]  = sum_j G0[j,i] Y[j,k]    A = G0 in smem read MN-major (M = 64 samples), B = Yh tile
+//   MMA1  Z[j,i]   = sum_k Y[j,k] X[i,k]     A = Y in TMEM, B = X tile in smem (K-major).  Yh*Xh in TF32 plus the
+//                                            two first-order corrections Yl*Xh + Yh*Xl as ONE BF16 contraction over
+//                                            K' = 128 ([Yl|Yh] x [Xh|Xl]); FP32 accumulate in TMEM
+//   epilogue (2 groups of 8 warps on alternating tiles; TMEM lane = feature j, so every column parameter is
+//            a per-thread register and every column-gradient sum a private accumulator):
+//            ColScale/ColShift, noise loss, dL/dz with the NaN mask (src/layers.jl:9-90, SURVEY.md
+//            Appendix B).  dL/dz goes back to TMEM in place of Z and, with 128-bit stores, into shared
+//            memory IN PLACE of the A values the same thread just read.
+//   MMA2  dX[i,k]  = sum_j G[j,i] Ys[j,k]    A = G in smem read MN-major (M = 64 samples), B = Ys = w_j sigma_j Y
 //                                            in smem read MN-major -- no transposed copies exist
-//   MMA3  dY[j,k] += sum_i G0[j,i] X[i,k]    A = G0 in TMEM, B = the same Xh tile read MN-major
+//   MMA3  dY[j,k] += sum_i G[j,i] X[i,k]     A = G in TMEM, B = a second copy of the Xh tile read MN-major
 //
-// Z and dL/dZ never exist in HBM.  dY stays in TMEM across the sample loop of an item; the
-// per-tile dX block is read back from TMEM and reduced into global memory with 128-bit REDs.
-// Operand split: h = rna_tf32(v), l = v - h (exact); gradient contractions use h only
-// (single-pass TF32, round-to-nearest operands); the Z contraction is 3xTF32 unless precision
-// mode 2 asks for plain TF32.
+// Z and dL/dZ never exist in HBM.  dY stays in TMEM across the sample loop of an item; each dX tile is staged
+// in shared memory and leaves as ONE TMA reduce-add (no per-lane REDs).  Operand split: h = rna_tf32(v),
+// l = v - h (exact); the gradient contractions use h only (single-pass TF32, round-to-nearest operands);
+// precision mode 2 drops the BF16 correction of Z.
 //
-// Shared memory (every TMA box is 32 floats = one 128-byte swizzle row wide):
-//   X   3 stages x (Xh 16 KB | Xl 16 KB)   tile [64 samples][64 k] as 2 boxes (32 k x 64 rows)
-//   YS  32 KB   Yh tile [128 features][64 k] as 2 boxes (32 k x 128 rows), written by the epilogue warps
-//   AG  3 stages x 32 KB   A tile as 2 boxes (32 samples x 128 feature rows); becomes G0 in place
-// The same box is a K-major operand when the contraction runs along its 128-byte rows (MMA1) and an
-// MN-major operand when it runs across rows (MMA2, MMA3): 8-row groups are 1024 B apart either way.
-// TMEM (512 columns): Yh 0 | Yl 64 | Z0 128 | Z1 192 | dY 256 | dX0 320 | dX1 384.
+// Warps: 0-15 epilogue | 16 TMA A | 17 MMA issuer (one elected thread) | 18 TMA X operands | 19 dX reduce-add issuer.
+// Shared memory (every box is one 128-byte swizzle row wide):
+//   XK  2 stages x (Xh 16 KB fp32 | Xb 16 KB bf16 [Xh|Xl])   K-major operands of MMA1, 16-byte-atom swizzle
+//   XM  16 KB   Xh tile again, 32-byte-atom swizzle: MN-major operand of MMA3
+//   YS  32 KB   Ys tile [128 features][64 k], 32-byte-atom swizzle, written by the epilogue warps per item
+//   AG  3 stages x 32 KB   A tile as 2 boxes (32 samples x 128 feature rows), 32-byte-atom swizzle; becomes G in place
+//   DXS 16 KB   dX tile staged for the TMA reduce-add (16-byte-atom swizzle)
+// MN-major FP32/TF32 operands exist only in the 32-byte-atom 128B swizzle (UMMA layout type 1), K-major ones
+// only in the 16-byte-atom layouts: hence the two copies of the Xh tile.
+// TMEM (512 columns): Yh 0 | [Yl|Yh] bf16 64 | Z0..Z2 128 | dY 320 | dX0 384 | dX1 448.
 // dX accumulators are M = 64 tiles: sample row r lives in lane (r % 16) + 32 * (r / 16).
 #include <cuda.h>
 #include <cuda_runtime.h>
