@@ -250,6 +250,15 @@ int pmf_comm_destroy(pmf_handle h);
  * per-column sum_i (dl/dz)^2 (MF.batched_column_ssq_grads, src/fit.jl:166) and per-column
  * count of finite entries (MF.column_nonnan, src/fit.jl:140). */
 int pmf_column_stats(pmf_handle h, float* ssq_grads_N, float* nonnan_N);
+/* MF.link_col_sqerr (src/fit.jl:138-139,444-446): per column sum_i (D_ij - forward_ij)^2 over finite
+ * entries, forward = the full layer stack at the current parameters, and MF.column_nonnan (:140,447).
+ * [The link of the non-normal noise models lives in MatFac.jl; identity is used for every column.] */
+int pmf_link_col_sqerr(pmf_handle h, float* sqerr_N, float* nonnan_N);
+/* ba_map(d -> isfinite.(d), theta, data) and ba_map(MF.sqerr_func, theta, model, data)
+ * (src/batch_array.jl:320-334; src/fit.jl:332,355-356,454-456): per batched view v the n_b x N_v
+ * column-major tables of segmented column sums (count of finite entries; squared error in link space).
+ * count / sqerr: arrays of n_views host pointers (an entry or the array itself may be NULL). */
+int pmf_batch_stats(pmf_handle h, int32_t n_views, float* const* count, float* const* sqerr);
 
 /* Test / bench hooks (no reference counterpart). */
 /* kernel kind and precision used by pmf_loss_grad */

@@ -1013,6 +1013,54 @@ class AdaGrad:
         p -= p.dtype.type(self.eta) * g / (np.sqrt(acc) + p.dtype.type(self.epsilon))
 
 
+###############################################################################
+# Staging passes that bracket the hot loop   (src/fit.jl:125-187)
+###############################################################################
+
+
+def link_col_sqerr(m: OracleModel, D: np.ndarray) -> np.ndarray:
+    """MF.link_col_sqerr as used at src/fit.jl:138-139: per column sum_i (D_ij - forward_ij)^2 over finite
+    entries (EXTERNAL; identity link assumed for every noise model)."""
+    Z = forward(m)
+    return np.where(np.isfinite(D), (D - Z) ** 2, 0.0).sum(axis=0)
+
+
+def column_ssq_grads(m: OracleModel, D: np.ndarray) -> np.ndarray:
+    """MF.batched_column_ssq_grads as used at src/fit.jl:166-168: per column sum_i (dl_ij/dz_ij)^2."""
+    Z = forward(m)
+    out = np.zeros(D.shape[1])
+    w = m.noise.weights
+    for cr, dist, th in zip(m.noise.col_ranges, m.noise.dists, m.noise.thresholds):
+        sl = slice(cr.start, cr.stop)
+        _, g = noise_loss_grad(dist, Z[:, sl], D[:, sl], th)
+        out[sl] = ((g * w[sl][None, :]) ** 2).sum(axis=0)
+    return out
+
+
+def init_logsigma(m: OracleModel, D: np.ndarray) -> None:
+    """src/fit.jl:125-148: with X = Y = 0, logsigma = log sqrt(col sq. error / number of finite entries)."""
+    X0, Y0 = m.X, m.Y
+    m.X, m.Y = np.zeros_like(X0), np.zeros_like(Y0)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        col_vars = link_col_sqerr(m, D) / np.isfinite(D).sum(axis=0)
+        m.X, m.Y = X0, Y0
+        m.logsigma = np.log(np.sqrt(col_vars)).astype(m.logsigma.dtype)
+
+
+def reweight_col_losses(m: OracleModel, D: np.ndarray) -> None:
+    """src/fit.jl:151-187: weights = 1 / (sqrt(ssq_grads / M) * exp(logsigma)), non-finite -> 1."""
+    M, N = D.shape
+    m.noise.weights = np.ones(N, dtype=m.noise.weights.dtype)
+    X0, Y0 = m.X, m.Y
+    m.X, m.Y = np.zeros_like(X0), np.zeros_like(Y0)
+    ssq = column_ssq_grads(m, D)
+    m.X, m.Y = X0, Y0
+    with np.errstate(divide="ignore", invalid="ignore"):
+        w = 1.0 / (np.sqrt(ssq / M) * np.exp(m.logsigma))
+    w[~np.isfinite(w)] = 1.0
+    m.noise.weights = w.astype(m.noise.weights.dtype)
+
+
 def mf_fit(m: OracleModel, D, opt: AdaGrad, max_epochs=1000, epoch=1, rel_tol=1e-5, abs_tol=1e-5,
            update_X=False, update_Y=False, update_col_layers=False, capacity=10 ** 8,
            callback=None):

@@ -98,6 +98,8 @@ SIGNATURES = {
                                      C.c_int32, C.c_int32, C.c_float, c_double_p, c_int32_p]),
     "pmf_get_fsard_beta": (C.c_int, [H, c_float_p]),
     "pmf_column_stats": (C.c_int, [H, c_float_p, c_float_p]),
+    "pmf_link_col_sqerr": (C.c_int, [H, c_float_p, c_float_p]),
+    "pmf_batch_stats": (C.c_int, [H, C.c_int32, C.POINTER(c_float_p), C.POINTER(c_float_p)]),
     "pmf_set_loss_grad_kernel": (C.c_int, [H, C.c_int32, C.c_int32]),
     "pmf_set_profiling": (C.c_int, [H, C.c_int32]),
     "pmf_get_profile": (C.c_int, [H, c_int32_p, c_float_p, c_float_p]),

@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(NT, (KG == 1) ? 2 : 1) data_pass_ffma_kernel(D
 #pragma unroll
             for (int c = 0; c < 4; ++c) dYacc[g][a][c] = 0.f;
     float dmu_acc[4] = {0.f, 0.f, 0.f, 0.f}, dls_acc[4] = {0.f, 0.f, 0.f, 0.f};
-    float ssq_acc[4] = {0.f, 0.f, 0.f, 0.f}, cnt_acc[4] = {0.f, 0.f, 0.f, 0.f};
+    float ssq_acc[4] = {0.f, 0.f, 0.f, 0.f}, cnt_acc[4] = {0.f, 0.f, 0.f, 0.f}, sq_acc[4] = {0.f, 0.f, 0.f, 0.f};
     float loss_acc = 0.f;
     double loss_d = 0.0;
 
@@ -157,8 +157,17 @@ __global__ void __launch_bounds__(NT, (KG == 1) ? 2 : 1) data_pass_ffma_kernel(D
                     g *= wv[a];
                     loss_acc += l;
                     if (STATS) {
+                        // statistics pass of the staging code: sum (dl/dz)^2, count of finite entries, squared
+                        // error in link space, and the last two segmented by batch (ba_map, src/batch_array.jl:320)
+                        const float d = aval - z4;
                         ssq_acc[a] += g * g;
                         cnt_acc[a] += 1.f;
+                        sq_acc[a] += d * d;
+                        if (boff[a] >= 0) {
+                            int lj = tj + 16 * a;
+                            atomicAdd(&Bth[lj * nbm + bidx], 1.f);
+                            atomicAdd(&Bld[lj * nbm + bidx], d * d);
+                        }
                     } else {
                         dmu_acc[a] += g;
                         float g1 = g * delta;
@@ -261,23 +270,26 @@ __global__ void __launch_bounds__(NT, (KG == 1) ? 2 : 1) data_pass_ffma_kernel(D
     for (int a = 0; a < 4; ++a) {
         float v0 = STATS ? ssq_acc[a] : dmu_acc[a];
         float v1 = STATS ? cnt_acc[a] : dls_acc[a];
+        float v2 = STATS ? sq_acc[a] : 0.f;
 #pragma unroll
         for (int o = 8; o > 0; o >>= 1) {
             v0 += __shfl_xor_sync(0xffffffffu, v0, o);
             v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+            v2 += __shfl_xor_sync(0xffffffffu, v2, o);
         }
         if (ti == 0 && jok[a]) {
             int j = j0 + tj + 16 * a;
             if (STATS) {
                 atomicAdd(p.col_ssq + j, v0);
                 atomicAdd(p.col_cnt + j, v1);
+                if (p.col_sqerr) atomicAdd(p.col_sqerr + j, v2);
             } else {
                 atomicAdd(p.dmu + j, v0);
                 atomicAdd(p.dlogsigma + j, v1);
             }
         }
     }
-    if (has_batch && !STATS) {
+    if (has_batch) {      // gradients of theta / logdelta, or (statistics pass) per-batch counts / squared errors
         __syncthreads();
         for (int idx = tid; idx < TJ * nbm; idx += NT) {
             int lj = idx / nbm, b = idx - lj * nbm;

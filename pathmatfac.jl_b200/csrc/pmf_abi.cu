@@ -178,7 +178,7 @@ int pmf_destroy(pmf_handle h) {
     dev_free(h->weight); dev_free(h->colinfo); dev_free(h->thresholds); dev_free(h->scalars); dev_free(h->ctrl);
     dev_free(h->vp); dev_free(h->sg); dev_free(h->accvp); dev_free(h->regw); dev_free(h->regc);
     dev_free(h->bcol_off); dev_free(h->bcol_view); dev_free(h->bcol_nb); dev_free(h->batch_of_sample);
-    dev_free(h->hist); dev_free(h->col_ssq); dev_free(h->col_cnt);
+    dev_free(h->hist); dev_free(h->col_ssq); dev_free(h->col_cnt); dev_free(h->col_sqerr);
     for (int s = 0; s < 2; ++s) h->reg[s].free_all();
     if (h->comm) { nccl().CommDestroy(h->comm); h->comm = nullptr; }
     if (h->ctrl_host) cudaFreeHost(h->ctrl_host);
@@ -928,19 +928,61 @@ int pmf_shared_scalar_buffer(pmf_handle h, void** p, int64_t* n) {
     return PMF_OK;
 }
 
-int pmf_column_stats(pmf_handle h, float* ssq, float* nonnan) {
-    CHECK_H(h);
+// One streaming pass over the data with the current parameters (the FP32 tile kernel with a statistics
+// epilogue): per column sum (dl/dz)^2, count of finite entries and squared error in link space; per
+// (batch, column) of every batched view the count and the squared error (left in the batch-gradient tables).
+static int run_stats_pass(pmf_model_s* h) {
     if (ready(h)) return PMF_ERR_STATE;
-    if (!h->col_ssq) { CU(h, dev_alloc(&h->col_ssq, h->Np)); CU(h, dev_alloc(&h->col_cnt, h->Np)); }
+    if (!h->col_ssq) {
+        CU(h, dev_alloc(&h->col_ssq, h->Np)); CU(h, dev_alloc(&h->col_cnt, h->Np)); CU(h, dev_alloc(&h->col_sqerr, h->Np));
+    }
     CU(h, cudaMemsetAsync(h->col_ssq, 0, (size_t)h->Np * 4, h->stream));
     CU(h, cudaMemsetAsync(h->col_cnt, 0, (size_t)h->Np * 4, h->stream));
+    CU(h, cudaMemsetAsync(h->col_sqerr, 0, (size_t)h->Np * 4, h->stream));
+    if (h->nbp > 0) {
+        CU(h, cudaMemsetAsync(h->g_logdelta(), 0, (size_t)h->nbp * 4, h->stream));
+        CU(h, cudaMemsetAsync(h->g_theta(), 0, (size_t)h->nbp * 4, h->stream));
+    }
+    h->grads_clean = false;
     DataPassParams p;
     fill_data_params(h, p, false);
-    p.col_ssq = h->col_ssq; p.col_cnt = h->col_cnt;
+    p.col_ssq = h->col_ssq; p.col_cnt = h->col_cnt; p.col_sqerr = h->col_sqerr;
+    size_t smem = sizeof(float) * ((size_t)128 * (h->Kp + 4) + 64 * 68 + 2 * (size_t)64 * h->nb_max);
+    if (smem > 227 * 1024) return fail(h, PMF_ERR_ARG, "too many batches per view (%d) for K=%d", h->nb_max, h->K);
     CU(h, launch_data_pass_ffma(p, h->stream, h->n_sms));
     CU(h, cudaStreamSynchronize(h->stream));
+    return PMF_OK;
+}
+
+int pmf_column_stats(pmf_handle h, float* ssq, float* nonnan) {
+    CHECK_H(h);
+    int rc = run_stats_pass(h);
+    if (rc != 0) return rc;
     if (ssq) CU(h, cudaMemcpy(ssq, h->col_ssq, (size_t)h->N * 4, cudaMemcpyDeviceToHost));
     if (nonnan) CU(h, cudaMemcpy(nonnan, h->col_cnt, (size_t)h->N * 4, cudaMemcpyDeviceToHost));
+    return PMF_OK;
+}
+
+int pmf_link_col_sqerr(pmf_handle h, float* sqerr, float* nonnan) {
+    CHECK_H(h);
+    int rc = run_stats_pass(h);
+    if (rc != 0) return rc;
+    if (sqerr) CU(h, cudaMemcpy(sqerr, h->col_sqerr, (size_t)h->N * 4, cudaMemcpyDeviceToHost));
+    if (nonnan) CU(h, cudaMemcpy(nonnan, h->col_cnt, (size_t)h->N * 4, cudaMemcpyDeviceToHost));
+    return PMF_OK;
+}
+
+int pmf_batch_stats(pmf_handle h, int32_t n_views, float* const* count, float* const* sqerr) {
+    CHECK_H(h);
+    if (n_views != (int32_t)h->views.size()) return fail(h, PMF_ERR_ARG, "pmf_batch_stats: %d views given, the model has %d", n_views, (int)h->views.size());
+    int rc = run_stats_pass(h);
+    if (rc != 0) return rc;
+    for (int v = 0; v < n_views; ++v) {
+        const BatchView& bv = h->views[v];
+        size_t n = (size_t)(bv.col_stop - bv.col_start) * bv.n_batches;
+        if (count && count[v]) CU(h, cudaMemcpy(count[v], h->g_theta() + bv.offset, n * 4, cudaMemcpyDeviceToHost));
+        if (sqerr && sqerr[v]) CU(h, cudaMemcpy(sqerr[v], h->g_logdelta() + bv.offset, n * 4, cudaMemcpyDeviceToHost));
+    }
     return PMF_OK;
 }
 

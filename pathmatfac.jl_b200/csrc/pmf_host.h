@@ -106,7 +106,7 @@ struct pmf_model_s {
     int hist_cap = 0;
     int cur_epoch = 1;
     int64_t launches = 0;
-    float *col_ssq = nullptr, *col_cnt = nullptr;
+    float *col_ssq = nullptr, *col_cnt = nullptr, *col_sqerr = nullptr;
     int loss_grad_kernel = 0, loss_grad_precision = 0;
     bool profiling = false;
     std::vector<cudaEvent_t> prof_ev;    // pairs (start, stop) per bracketed data pass

@@ -43,6 +43,7 @@ struct DataPassParams {
     // optional per-column statistics pass (pmf_column_stats)
     float* col_ssq;     // [Np] sum_i g^2 or null
     float* col_cnt;     // [Np] count of finite entries or null
+    float* col_sqerr;   // [Np] sum_i (a - z4)^2 over finite entries or null (statistics pass only)
     const int* stop_flag;   // device flag: non-zero => the fit has terminated, do nothing
     int sample_chunks;      // grid.y: number of sample chunks per feature tile
     float ordinal_eps, hinge_margin;

@@ -11,7 +11,7 @@ import numpy as np
 import scipy.sparse as sp
 
 from . import _lib
-from ._lib import (KERNEL_AUTO, TERM_CODES, c_double_p, check, fptr, iptr, pmf_dims, pmf_fit_opts,
+from ._lib import (KERNEL_AUTO, TERM_CODES, c_double_p, c_float_p, check, fptr, iptr, pmf_dims, pmf_fit_opts,
                    pmf_history, pmf_losses)
 from .layers import BatchScale, BatchShift, FrozenLayer, Identity
 from .regularizers import (ARDRegularizer, BatchArrayReg, ColParamReg, CompositeRegularizer,
@@ -362,6 +362,29 @@ class Engine:
         return ssq, cnt
 
 
+    def link_col_sqerr(self):
+        """(sum_i (D_ij - forward_ij)^2 over finite entries, count of finite entries) per column --
+        MF.link_col_sqerr / MF.column_nonnan (src/fit.jl:138-140, :444-447), identity link."""
+        sq = np.empty(self.N, np.float32)
+        cnt = np.empty(self.N, np.float32)
+        self._ck(self.lib.pmf_link_col_sqerr(self.h, fptr(sq), fptr(cnt)))
+        return sq, cnt
+
+    def batch_stats(self):
+        """Per batched view the (n_b, N_v) tables ba_map(isfinite, theta, data) and
+        ba_map(sqerr_func, theta, model, data) (src/batch_array.jl:320-334, src/fit.jl:332,355-356)."""
+        ba = self.model.matfac.col_transform.unwrapped(3).theta if self.n_views else None
+        if ba is None:
+            return [], []
+        shapes = [v.shape for v in ba.values]                      # (n_b, N_v)
+        cnt = [np.empty((nv, nb), np.float32) for nb, nv in shapes]  # device layout: [column][n_b]
+        sq = [np.empty((nv, nb), np.float32) for nb, nv in shapes]
+        pc = (c_float_p * len(cnt))(*[fptr(a) for a in cnt])
+        ps = (c_float_p * len(sq))(*[fptr(a) for a in sq])
+        self._ck(self.lib.pmf_batch_stats(self.h, len(cnt), pc, ps))
+        return [a.T.copy() for a in cnt], [a.T.copy() for a in sq]
+
+
 # ---- device placement (the reference's gpu(model) / cpu(model)) -----------------------------------
 
 def gpu(model, device: int = 0):
@@ -376,6 +399,58 @@ def cpu(model):
         model._engine.close()
         model._engine = None
     return model
+
+
+# ---- staging passes that bracket the hot loop -----------------------------------
+
+def _with_zero_factors(model, fn):
+    """Run ``fn(engine)`` with X and Y temporarily set to zero on the device, as init_logsigma! /
+    reweight_col_losses! do (src/fit.jl:133-136,160-163); the host model is not touched."""
+    transient = model._engine is None
+    eng = Engine(model) if transient else model._engine
+    try:
+        if not transient:
+            eng.push_structure()
+            eng.push_params()
+        mf = model.matfac
+        zx = np.zeros((eng.M, eng.K), np.float32)
+        zy = np.zeros((eng.N, eng.K), np.float32)
+        eng._ck(eng.lib.pmf_set_factors(eng.h, fptr(zx), fptr(zy)))
+        out = fn(eng)
+        if not transient:
+            eng.push_params()          # restore X, Y on the device
+        return out
+    finally:
+        if transient:
+            eng.close()
+
+
+def init_logsigma(model):
+    """``init_logsigma!`` (src/fit.jl:125-148): logsigma_j = log sqrt(mean_i (D_ij - forward_ij)^2) with
+    X = Y = 0, i.e. the spread of each column around its shift; one streaming pass on the device."""
+    sq, cnt = _with_zero_factors(model, lambda eng: eng.link_col_sqerr())
+    with np.errstate(divide="ignore", invalid="ignore"):
+        col_vars = sq / cnt
+        model.matfac.col_transform.unwrapped(0).logsigma[...] = np.log(np.sqrt(col_vars)).astype(np.float32)
+    if model._engine is not None:
+        model._engine.push_params()
+
+
+def reweight_col_losses(model):
+    """``reweight_col_losses!`` (src/fit.jl:151-187): weights = 1 / (rms_i(dl/dz) * sigma_j), rms over ALL M
+    samples (missing entries count as zero gradient, :169-172), non-finite weights -> 1."""
+    nm = model.matfac.noise_model
+    N = model.matfac.Y.shape[1]
+    nm.set_weight(np.ones(N, np.float32))
+    ssq, _ = _with_zero_factors(model, lambda eng: eng.column_stats())
+    M = model.matfac.X.shape[1]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        rms = np.sqrt(ssq / np.float32(M)) * np.exp(model.matfac.col_transform.unwrapped(0).logsigma)
+        w = (1.0 / rms).astype(np.float32)
+    w[~np.isfinite(w)] = 1.0
+    nm.set_weight(w)
+    if model._engine is not None:
+        model._engine.push_structure()
 
 
 # ---- the boundary ----------------------------------------------------------------------------------

@@ -442,3 +442,54 @@ def test_tc_refuses_unsupported_shapes():
             eng.loss_grad(include_reg=False)
     finally:
         eng.close()
+
+
+def test_staging_statistics_passes():
+    """The other O(MN) passes of the staging code: MF.link_col_sqerr / column_nonnan
+    (src/fit.jl:138-140) and ba_map(isfinite) / ba_map(sqerr_func) (src/batch_array.jl:320-334,
+    src/fit.jl:332,355-356), one streaming pass behind the ABI, against the oracle's ba_map."""
+    views = {"methylation": ("normal", 70), "mrnaseq": ("normal", 45)}
+    model, om, D = make_pair(130, views, K=5, seed=81, batch_views=["methylation", "mrnaseq"], n_batches=4, missing=0.3)
+    eng = P.Engine(model)
+    try:
+        sq, cnt = eng.link_col_sqerr()
+        bcnt, bsq = eng.batch_stats()
+    finally:
+        eng.close()
+    Z = O.forward(om)
+    fin = np.isfinite(D)
+    assert np.array_equal(cnt, fin.sum(axis=0).astype(np.float32))
+    assert relerr(sq, np.where(fin, (D - Z) ** 2, 0.0).sum(axis=0)) < TOL
+    ref_cnt = O.ba_map(lambda d: np.isfinite(d).astype(np.float64), om.theta, D)
+    ref_sq = O.ba_map(lambda z, d: np.where(np.isfinite(d), (d - z) ** 2, 0.0), om.theta, Z, D)
+    assert len(bcnt) == len(ref_cnt) == 2
+    for v in range(2):
+        assert np.array_equal(bcnt[v], ref_cnt[v].astype(np.float32))          # bit-exact batch bookkeeping
+        assert relerr(bsq[v], ref_sq[v]) < TOL
+
+
+def test_init_logsigma_and_reweight_col_losses():
+    """init_logsigma! / reweight_col_losses! (src/fit.jl:125-187) through the device statistics pass, then a
+    fit with the resulting weights: same numbers as the oracle's restatement."""
+    views = {"mutation": ("bernoulli", 25), "methylation": ("normal", 60), "counts": ("poisson", 20)}
+    model, om, D = make_pair(140, views, K=5, seed=91, batch_views=["methylation"], n_batches=3, missing=0.3,
+                             lambda_X_l2=1.0)
+    D[:, 30] = np.nan                      # an all-missing column: variance 0/0, weight falls back to 1
+    model.data[:, 30] = np.nan
+    P.init_logsigma(model)
+    O.init_logsigma(om, D)
+    ls, ls_ref = model.matfac.col_transform.unwrapped(0).logsigma, om.logsigma
+    ok = np.isfinite(ls_ref)
+    assert np.array_equal(np.isfinite(ls), ok) and relerr(ls[ok], ls_ref[ok]) < TOL
+    # the reference leaves the non-finite entries in place; give both sides a usable value before going on
+    ls[~ok] = 0.0
+    om.logsigma[~ok] = 0.0
+    P.reweight_col_losses(model)
+    O.reweight_col_losses(om, D)
+    w, w_ref = model.matfac.noise_model.weights(), om.noise.weights
+    assert w[30] == 1.0 and relerr(w, w_ref) < TOL
+    h = P.mf_fit(model, lr=0.2, max_epochs=4, update_X=True, update_Y=True, update_col_layers=True, rel_tol=0,
+                 abs_tol=0, verbosity=0)
+    href = O.mf_fit(om, D, O.AdaGrad(0.2), max_epochs=4, update_X=True, update_Y=True, update_col_layers=True,
+                    rel_tol=0, abs_tol=0)
+    assert np.max(np.abs(np.array(h["loss"]) / np.array(href["loss"]) - 1)) < TOL
