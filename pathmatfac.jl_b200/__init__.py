@@ -8,6 +8,7 @@ from .fit import (AdaGrad, Engine, cpu, gpu, init_logsigma, mf_fit, mf_fit_adapt
 from .layers import (BatchArray, BatchScale, BatchShift, ColScale, ColShift, FrozenLayer,
                      ViewableComposition, construct_model_layers, freeze_layer, unfreeze_layer)
 from .model import CompositeNoise, MatFacModel, PathMatFacModel
+from .transform import transform
 from .regularizers import (ARDRegularizer, BatchArrayReg, ColParamReg, CompositeRegularizer,
                            FeatureSetARDReg, FrozenRegularizer, GroupRegularizer, L2Regularizer,
                            NetworkRegularizer, SelectiveL1Reg, SequenceReg, ZeroReg,

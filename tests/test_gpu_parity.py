@@ -493,3 +493,34 @@ def test_init_logsigma_and_reweight_col_losses():
     href = O.mf_fit(om, D, O.AdaGrad(0.2), max_epochs=4, update_X=True, update_Y=True, update_col_layers=True,
                     rel_tol=0, abs_tol=0)
     assert np.max(np.abs(np.array(h["loss"]) / np.array(href["loss"]) - 1)) < TOL
+
+
+def test_transform_new_samples():
+    """transform (src/transform.jl:6-106): new samples, columns given in another order and only partly
+    present (matched by feature id, NaN-padded), batch layers dropped, X fitted alone through the boundary."""
+    views = {"mutation": ("bernoulli", 30), "methylation": ("normal", 70)}
+    model, om, D = make_pair(120, views, K=6, seed=95, batch_views=["methylation"], n_batches=3, missing=0.2)
+    N = D.shape[1]
+    rng = np.random.default_rng(7)
+    # new data: 40 samples drawn from the model's own forward map, 80 of the 100 features, shuffled
+    M_new = 40
+    Xn = rng.standard_normal((6, M_new))
+    Zn = (Xn.T @ om.Y) * np.exp(om.logsigma)[None, :] + om.mu[None, :]
+    Dn = Zn + 0.1 * rng.standard_normal(Zn.shape)
+    Dn[:, :30] = (rng.random((M_new, 30)) < 1.0 / (1.0 + np.exp(-Zn[:, :30]))).astype(float)
+    keep = rng.permutation(N)[:80]
+    fids = [model.feature_ids[j] for j in keep]
+    new_model = P.transform(model, Dn[:, keep].astype(np.float32), feature_ids=fids, max_epochs=25, lr=0.5,
+                            verbosity=0, rel_tol=0, abs_tol=0)
+    assert new_model.matfac.X.shape == (6, M_new) and new_model.data.shape == (M_new, N)
+    assert np.isnan(new_model.data[:, np.setdiff1d(np.arange(N), keep)]).all()
+    assert np.array_equal(new_model.matfac.Y, model.matfac.Y)                  # Y and the column layers are untouched
+    assert model._engine is None and model.data is not None                    # the fitted model is restored
+    # the oracle's version of the same staging: X = 0, no batch layers, no regularisers, X-only fit
+    Dpad = np.full((M_new, N), np.nan)
+    Dpad[:, keep] = Dn[:, keep].astype(np.float32)
+    on = O.OracleModel(X=np.zeros((6, M_new)), Y=om.Y.copy(), logsigma=om.logsigma.copy(), mu=om.mu.copy(),
+                       logdelta=None, theta=None, noise=om.noise)
+    O.mf_fit_adapt_lr(on, Dpad, lr=0.5, max_epochs=25, update_X=True, rel_tol=0, abs_tol=0)
+    assert relerr(new_model.matfac.X, on.X) < 1e-3
+    assert relerr(new_model.matfac.X, Xn) < 0.5                                 # and it recovers the embedding
