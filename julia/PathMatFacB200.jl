@@ -197,4 +197,41 @@ function mf_fit!(model::PM.PathMatFacModel, h::Handle; opt, max_epochs=1000, epo
                 "data_loss" => losses[2][1:n], "X_reg" => losses[3][1:n], "Y_reg" => losses[4][1:n], "layer_reg" => losses[5][1:n])
 end
 
+# ---- the staging code's other streaming passes (SURVEY 8f rank 1) ------------------------------------
+
+"""`MF.link_col_sqerr` + `MF.column_nonnan` (src/fit.jl:138-140) at the handle's current parameters."""
+function link_col_sqerr(h::Handle, N::Integer)
+    sq = zeros(Float32, N); cnt = zeros(Float32, N)
+    check(h, ccall((:pmf_link_col_sqerr, LIBPMF), Cint, (Handle, Ptr{Float32}, Ptr{Float32}), h, sq, cnt))
+    return sq, cnt
+end
+
+"""`MF.batched_column_ssq_grads` + `MF.column_nonnan` (src/fit.jl:166-168, :140)."""
+function column_stats(h::Handle, N::Integer)
+    ssq = zeros(Float32, N); cnt = zeros(Float32, N)
+    check(h, ccall((:pmf_column_stats, LIBPMF), Cint, (Handle, Ptr{Float32}, Ptr{Float32}), h, ssq, cnt))
+    return ssq, cnt
+end
+
+"""`ba_map(d->isfinite.(d), theta, data)` and `ba_map(MF.sqerr_func, theta, model, data)`
+(src/batch_array.jl:320-334): one n_b x N_v matrix per batched view."""
+function batch_stats(h::Handle, theta::PM.BatchArray)
+    cnt = [zeros(Float32, size(v)) for v in theta.values]; sq = [zeros(Float32, size(v)) for v in theta.values]
+    GC.@preserve cnt sq check(h, ccall((:pmf_batch_stats, LIBPMF), Cint, (Handle, Int32, Ptr{Ptr{Float32}}, Ptr{Ptr{Float32}}),
+                                       h, length(cnt), pointer.(cnt), pointer.(sq)))
+    return cnt, sq
+end
+
+# ---- sample-sharded multi-GPU: one Julia process per GPU (INTEGRATION.md section 3) ---------------------
+
+"""Rank 0 creates the 128-byte NCCL id; broadcast it with MPI.jl / Distributed.jl, then `comm_init!`."""
+function comm_unique_id()
+    id = zeros(UInt8, 128)
+    check(C_NULL, ccall((:pmf_comm_unique_id, LIBPMF), Cint, (Ptr{UInt8},), id))
+    return id
+end
+comm_init!(h::Handle, nranks::Integer, rank::Integer, id::Vector{UInt8}) =
+    check(h, ccall((:pmf_comm_init_rank, LIBPMF), Cint, (Handle, Int32, Int32, Ptr{UInt8}), h, nranks, rank, id))
+comm_destroy!(h::Handle) = check(h, ccall((:pmf_comm_destroy, LIBPMF), Cint, (Handle,), h))
+
 end # module
