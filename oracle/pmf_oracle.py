@@ -1061,6 +1061,57 @@ def reweight_col_losses(m: OracleModel, D: np.ndarray) -> None:
     m.noise.weights = w.astype(m.noise.weights.dtype)
 
 
+def theta_mom(theta_values):
+    """src/fit.jl:297-301."""
+    return ([v.mean(axis=1, keepdims=True) for v in theta_values],
+            [v.var(axis=1, ddof=1, keepdims=True) for v in theta_values])
+
+
+def delta2_mom(delta2_values):
+    """src/fit.jl:303-311."""
+    mean = [v.mean(axis=1, keepdims=True) for v in delta2_values]
+    var = [v.var(axis=1, ddof=1, keepdims=True) for v in delta2_values]
+    alpha = [2.0 + (mm * mm) / (vv + 1e-9) for mm, vv in zip(mean, var)]
+    beta = [mm * (a - 1.0) for mm, a in zip(mean, alpha)]
+    return alpha, beta
+
+
+def theta_delta_em(m: OracleModel, delta2, sigma2, D, update_priors=True, batch_em_max_iter=100, batch_em_rtol=1e-8):
+    """src/fit.jl:326-375 (sqerr_func: squared error in link space, identity link, over finite entries)."""
+    theta = m.theta
+    delta2 = [np.array(d, dtype=np.float64) for d in delta2]
+    theta_lsq = [v.copy() for v in theta.values]
+    batch_sizes = ba_map(lambda d: np.isfinite(d).astype(np.float64), theta, D)
+
+    def nans_to(arrs, val):
+        for a in arrs:
+            a[~np.isfinite(a)] = val
+
+    diffs = []
+    for it in range(batch_em_max_iter):
+        if update_priors or it == 0:
+            theta_mean, theta_var = theta_mom(theta.values)
+            alpha, beta = delta2_mom(delta2)
+        theta_old = [v.copy() for v in theta.values]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            theta.values = [(e * d2 * sigma2[None, cr.start:cr.stop] + tl * bs * vt) / (sigma2[None, cr.start:cr.stop] * d2 + bs * vt)
+                            for e, vt, d2, tl, bs, cr in zip(theta_mean, theta_var, delta2, theta_lsq, batch_sizes, theta.col_ranges)]
+        nans_to(theta.values, 0.0)
+        Z = forward(m)
+        sqerr = ba_map(lambda z, d: np.where(np.isfinite(d), (d - z) ** 2, 0.0), theta, Z, D)
+        nans_to(sqerr, 0.0)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            delta2 = [(b + 0.5 * (sq / sigma2[None, cr.start:cr.stop])) / (a + 0.5 * bs - 1.0)
+                      for a, b, sq, bs, cr in zip(alpha, beta, sqerr, batch_sizes, theta.col_ranges)]
+        nans_to(delta2, 1.0)
+        num = sum(((v - o) ** 2).sum() for v, o in zip(theta.values, theta_old))
+        den = sum((v * v).sum() for v in theta.values)
+        diffs.append(num / den)
+        if diffs[-1] < batch_em_rtol:
+            break
+    return theta.values, delta2, diffs
+
+
 def mf_fit(m: OracleModel, D, opt: AdaGrad, max_epochs=1000, epoch=1, rel_tol=1e-5, abs_tol=1e-5,
            update_X=False, update_Y=False, update_col_layers=False, capacity=10 ** 8,
            callback=None):

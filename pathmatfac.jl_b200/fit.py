@@ -453,6 +453,76 @@ def reweight_col_losses(model):
         model._engine.push_structure()
 
 
+def theta_mom(theta_values):
+    """src/fit.jl:297-301: per-batch mean / (corrected) variance across the view's columns."""
+    return ([v.mean(axis=1, keepdims=True) for v in theta_values],
+            [v.var(axis=1, ddof=1, keepdims=True) for v in theta_values])
+
+
+def delta2_mom(delta2_values):
+    """src/fit.jl:303-311: inverse-gamma (alpha, beta) by the method of moments."""
+    f32 = np.float32
+    mean = [v.mean(axis=1, keepdims=True) for v in delta2_values]
+    var = [v.var(axis=1, ddof=1, keepdims=True) for v in delta2_values]
+    alpha = [f32(2) + (m * m) / (v + f32(1e-9)) for m, v in zip(mean, var)]
+    beta = [m * (a - f32(1)) for m, a in zip(mean, alpha)]
+    return alpha, beta
+
+
+def _nans_to_val(arrs, val):
+    for a in arrs:
+        a[~np.isfinite(a)] = val
+
+
+def theta_delta_em(model, delta2, sigma2, update_priors=True, batch_em_max_iter=100, batch_em_rtol=1e-8):
+    """``theta_delta_em`` (src/fit.jl:326-375): empirical-Bayes EM for the batch shifts theta and the batch
+    scales delta^2.  The two O(MN) quantities of every iteration -- ba_map(isfinite) once and
+    ba_map(sqerr_func) per iteration -- are the device statistics pass (pmf_batch_stats); everything else is
+    n_b x N_v arithmetic.  Returns (theta values, delta2) and leaves theta in the model like the reference."""
+    f32 = np.float32
+    theta = model.matfac.col_transform.unwrapped(3).theta
+    sigma2 = np.asarray(sigma2, dtype=f32)
+    delta2 = [np.asarray(d, dtype=f32).copy() for d in delta2]
+    theta_lsq = [v.astype(f32).copy() for v in theta.values]
+    transient = model._engine is None
+    eng = Engine(model) if transient else model._engine
+    diffs = []
+    try:
+        if not transient:
+            eng.push_structure()
+            eng.push_params()
+        batch_sizes, _ = eng.batch_stats()
+        for it in range(batch_em_max_iter):
+            if update_priors or it == 0:
+                theta_mean, theta_var = theta_mom(theta.values)
+                alpha, beta = delta2_mom(delta2)
+            theta_old = [v.copy() for v in theta.values]
+            with np.errstate(divide="ignore", invalid="ignore"):
+                new_vals = [((e * d2 * sigma2[None, cr.start:cr.stop] + tl * bs * vt)
+                             / (sigma2[None, cr.start:cr.stop] * d2 + bs * vt)).astype(f32)
+                            for e, vt, d2, tl, bs, cr in zip(theta_mean, theta_var, delta2, theta_lsq, batch_sizes,
+                                                             theta.col_ranges)]
+            _nans_to_val(new_vals, f32(0))
+            for v, nv in zip(theta.values, new_vals):
+                v[...] = nv
+            eng.push_params()                                   # the squared errors use the new theta
+            _, sqerr = eng.batch_stats()
+            _nans_to_val(sqerr, f32(0))
+            with np.errstate(divide="ignore", invalid="ignore"):
+                delta2 = [((b + f32(0.5) * (sq / sigma2[None, cr.start:cr.stop])) / (a + f32(0.5) * bs - f32(1))).astype(f32)
+                          for a, b, sq, bs, cr in zip(alpha, beta, sqerr, batch_sizes, theta.col_ranges)]
+            _nans_to_val(delta2, f32(1))
+            num = sum(float(((v - o) ** 2).sum()) for v, o in zip(theta.values, theta_old))
+            den = sum(float((v * v).sum()) for v in theta.values)
+            diffs.append(num / den if den > 0 else float("nan"))
+            if diffs[-1] < batch_em_rtol:
+                break
+    finally:
+        if transient:
+            eng.close()
+    return theta.values, delta2, diffs
+
+
 # ---- the boundary ----------------------------------------------------------------------------------
 
 def mf_fit(model, *, scale_column_losses=False, update_X=False, update_Y=False, update_row_layers=False,

@@ -524,3 +524,20 @@ def test_transform_new_samples():
     O.mf_fit_adapt_lr(on, Dpad, lr=0.5, max_epochs=25, update_X=True, rel_tol=0, abs_tol=0)
     assert relerr(new_model.matfac.X, on.X) < 1e-3
     assert relerr(new_model.matfac.X, Xn) < 0.5                                 # and it recovers the embedding
+
+
+def test_theta_delta_em():
+    """theta_delta_em (src/fit.jl:326-375): the batch-effect EM whose per-iteration O(MN) work is the
+    device's segmented squared-error pass."""
+    views = {"methylation": ("normal", 50), "mrnaseq": ("normal", 35)}
+    model, om, D = make_pair(160, views, K=4, seed=97, batch_views=["methylation", "mrnaseq"], n_batches=4, missing=0.25)
+    rng = np.random.default_rng(5)
+    theta_p = model.matfac.col_transform.unwrapped(3).theta
+    delta2 = [(0.5 + rng.random(v.shape)).astype(np.float32) for v in theta_p.values]
+    sigma2 = np.exp(2.0 * om.logsigma).astype(np.float32)
+    th, d2, diffs = P.theta_delta_em(model, delta2, sigma2, batch_em_max_iter=6, batch_em_rtol=0.0)
+    th_ref, d2_ref, diffs_ref = O.theta_delta_em(om, delta2, sigma2.astype(np.float64), D, batch_em_max_iter=6, batch_em_rtol=0.0)
+    assert len(diffs) == len(diffs_ref) == 6
+    for v in range(2):
+        assert relerr(th[v], th_ref[v]) < 1e-3 and relerr(d2[v], d2_ref[v]) < 1e-3
+    assert abs(diffs[-1] - diffs_ref[-1]) <= 1e-2 * abs(diffs_ref[-1]) + 1e-9
