@@ -1202,7 +1202,7 @@ VIEW_LOGSIGMA_STD = {"mrnaseq": 0.1, "methylation": 0.1, "cna": 0.001, "mutation
 
 
 def simulate_model(M, N_per_view: Dict[str, Tuple[str, int]], K, seed, batch_views: Sequence[str] = (),
-                   n_batches=0, n_conditions=0, missing=0.0, dtype=np.float64, noise=0.1):
+                   n_batches=0, n_conditions=0, missing=0.0, dtype=np.float64, noise=0.1, sort_batches=False):
     """Seeded synthetic inputs following simulate_params!/simulate_data!
     (src/simulate_params.jl:193-255).  ``N_per_view``: view -> (distribution, n cols),
     already listed in the constructor's sorted (distribution, view) order.
@@ -1228,6 +1228,8 @@ def simulate_model(M, N_per_view: Dict[str, Tuple[str, int]], K, seed, batch_vie
     batch_dict = None
     if batch_views:
         batch_dict = {v: [int(b) for b in rng.integers(0, n_batches, size=M)] for v in batch_views}
+        if sort_batches:      # samples grouped by batch, as plate / centre ids of a sorted cohort are
+            batch_dict = {v: sorted(b) for v, b in batch_dict.items()}
         col_ranges = ids_to_ranges(views)
         unq = unique_in_order(views)
 

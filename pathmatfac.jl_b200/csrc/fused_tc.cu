@@ -38,6 +38,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "pmf_epilogue.cuh"
 #include "pmf_internal.h"
 
@@ -270,7 +272,15 @@ struct TcParams {
     long long* trace;  // PMF_TC_TRACE: per-tile clock64 stamps of one CTA (16 events x TRACE_TILES), else null
     int trace_cta;
     int flags;         // PMF_TC_FLAGS: trace filters (16 = only the per-tile G_READY stamp, 32 = only the MMA thread)
+    // batch layers (BATCH instantiation): n_jt counts PASSES = (feature tile, sample order) pairs, see TcBatchDev
+    const int32_t* pass_feat0;   // [n_jt] first feature of the pass' tile
+    const int32_t* pass_order;   // [n_jt] sample order of the pass
+    const int32_t* view_order;   // [n_views] sample order in which the view's batches are contiguous
+    const uint16_t* boq;         // [n_orders][n_views][Mp/4] batch of 4 consecutive positions, 0xFFFF = mixed
+    const uint16_t* bos;         // [n_orders][n_views][Mp]   batch of a position
+    int n_views, n_orders;
 };
+constexpr uint32_t B_MIXED = 0xFFFFu, B_NONE = 0xFFFEu;
 constexpr int TRACE_TILES = 96, TRACE_EV = 32, TRACE_CTAS = 160;   // + per-CTA (start, end) clocks after the stamps
 
 // Work distribution.  The tiles, flattened feature-tile-major ([jt][it]), are cut into gridDim.x equal
@@ -323,7 +333,7 @@ struct Ring {
     __device__ __forceinline__ void next(uint32_t n) { if (++s == n) { s = 0; ph ^= 1u; } }
 };
 
-template <bool DBG>
+template <bool DBG, bool BATCH>
 __global__ void __launch_bounds__(NTHREADS, 1)
 data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUtensorMap tmXl,
                     const __grid_constant__ CUtensorMap tmXm, const __grid_constant__ CUtensorMap tmA,
@@ -407,8 +417,9 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
             };
             for (ItemIter itx(p); itx.next();) {
                 const int it0 = itx.it0, it1 = itx.it1;
+                const int xrow0 = BATCH ? __ldg(p.pass_order + itx.jt) * dp.Mp : 0;   // this order's copy of the X operands
                 for (int it = it0; it < it1; ++it) {
-                    const int i0 = it * BI;
+                    const int i0 = xrow0 + it * BI;
                     mbar_wait(bar(B_EMPTY_XK + rk.s), rk.ph ^ 1);
                     mbar_expect_tx(bar(B_FULL_XK + rk.s), XK_BYTES);
                     const uint32_t dst = XK + rk.s * XK_BYTES;
@@ -434,11 +445,12 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
             uint32_t g = 0;
             for (ItemIter itx(p); itx.next();) {
                 const int it0 = itx.it0, it1 = itx.it1;
+                const int xrow0 = BATCH ? __ldg(p.pass_order + itx.jt) * dp.Mp : 0;   // this order's copy of dX
                 for (int it = it0; it < it1; ++it, ++g) {
                     mbar_wait(bar(B_DXS_FULL), g & 1);
                     if (!(DBG && p.ablate & 16)) {
-                        tma_reduce_add_2d(&tmDX, DXS, 0, it * BI);
-                        if (dp.Kp > 32) tma_reduce_add_2d(&tmDX, DXS + 8192, 32, it * BI);
+                        tma_reduce_add_2d(&tmDX, DXS, 0, xrow0 + it * BI);
+                        if (dp.Kp > 32) tma_reduce_add_2d(&tmDX, DXS + 8192, 32, xrow0 + it * BI);
                     }
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -622,24 +634,35 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
         // Per-item operands of this thread (lane = feature): column constants and its 16-column chunk of
         // the Y row.  They are fetched one item AHEAD, right before the wait for the current item's last
         // contraction, so the two global round trips are off the item-to-item critical path.
-        struct ItemRegs { float logsigma, mu, w; int ci; float4 y[4]; };
+        struct ItemRegs { float logsigma, mu, w; int ci; int boff, bview; float4 y[4]; };
         auto load_item = [&](int jt_, ItemRegs& r) {
-            const int j_ = jt_ * BJ + lrow;
+            const int feat0 = BATCH ? __ldg(p.pass_feat0 + jt_) : jt_ * BJ;
+            const int j_ = feat0 + lrow;
             const int jj_ = j_ < dp.N ? j_ : dp.N - 1;   // padding rows follow the last column (same noise model: no divergence)
             r.logsigma = __ldg(dp.logsigma + jj_);
             r.mu = __ldg(dp.mu + jj_);
             r.w = j_ < dp.N ? __ldg(dp.weight + jj_) : 0.f;
             r.ci = __ldg(dp.colinfo + jj_);
+            if (BATCH) {
+                // offset of the column's block of the batch tables (-1: the column's view has no batch layers)
+                // and the view whose sample tables the column reads.  A column whose view needs another sample
+                // order is all-NaN in this pass (it is served by the tile's other pass): no batch bookkeeping.
+                int bo = j_ < dp.N ? __ldg(dp.bcol_off + jj_) : -1;
+                const int bv = bo >= 0 ? __ldg(dp.bcol_view + jj_) : 0;
+                if (bo >= 0 && __ldg(p.view_order + bv) != __ldg(p.pass_order + jt_)) bo = -1;
+                r.boff = bo;
+                r.bview = bv;
+            }
             // K <= 64: the factor arrays keep their own pitch Kp; columns k >= Kp are zeros here, in the
             // operand scratch (Xh / Xb are 64 / 128 wide and zero padded) and in every TMA box (OOB fill)
-            const float4* yrow = reinterpret_cast<const float4*>(dp.Y + (size_t)(jt_ * BJ + lrow) * dp.Kp) + 4 * c16;
+            const float4* yrow = reinterpret_cast<const float4*>(dp.Y + (size_t)j_ * dp.Kp) + 4 * c16;
 #pragma unroll
             for (int v = 0; v < 4; ++v)
                 r.y[v] = (16 * c16 + 4 * v < dp.Kp) ? __ldg(yrow + v) : make_float4(0.f, 0.f, 0.f, 0.f);
         };
         // L2 prefetch of the same addresses, issued a whole item earlier (the A stream evicts them from L2)
         auto prefetch_item = [&](int jt_) {
-            const int j_ = jt_ * BJ + lrow;
+            const int j_ = (BATCH ? __ldg(p.pass_feat0 + jt_) : jt_ * BJ) + lrow;
             const int jj_ = j_ < dp.N ? j_ : dp.N - 1;   // padding rows follow the last column (same noise model: no divergence)
             if (c16 == 0) {
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(dp.logsigma + jj_));
@@ -648,7 +671,7 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(dp.colinfo + jj_));
             }
             if (16 * c16 < dp.Kp)
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(dp.Y + (size_t)(jt_ * BJ + lrow) * dp.Kp + 16 * c16));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(dp.Y + (size_t)j_ * dp.Kp + 16 * c16));
         };
         ItemRegs cur;
         {
@@ -660,6 +683,8 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
         float4 pend_dy[4];
         float pend_dmu = 0.f, pend_dls = 0.f;
         int pend_j = -1;
+        float pend_dth = 0.f, pend_dld = 0.f;    // BATCH: last batch segment of the previous item
+        int pend_bidx = -1;
         auto store_partials = [&]() {
             if (pend_j >= 0) {
                 float4* dst = reinterpret_cast<float4*>(dp.dY + (size_t)pend_j * dp.Kp + 16 * c16);
@@ -671,10 +696,19 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
             }
             pend_j = -1;
         };
+        // dtheta / dlogdelta of a closed batch segment: issued right AFTER the tile's G_READY arrive (or the next
+        // item's Y_READY arrive), never in front of one
+        auto store_segment = [&]() {
+            if (BATCH && pend_bidx >= 0) {
+                atomicAdd(dp.dtheta + pend_bidx, pend_dth);
+                atomicAdd(dp.dlogdelta + pend_bidx, pend_dld);
+                pend_bidx = -1;
+            }
+        };
 
         for (ItemIter itx(p); itx.next();) {
             const int jt = itx.jt, it0 = itx.it0, it1 = itx.it1;
-            const int j = jt * BJ + lrow;
+            const int j = (BATCH ? __ldg(p.pass_feat0 + jt) : jt * BJ) + lrow;
             const bool jok = j < dp.N;
             // per-thread column constants (lane = feature)
             const float sigma = __expf(cur.logsigma);
@@ -687,6 +721,41 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
             // touches the per-entry path: MMA2 reads Yh scaled by it, the dY tile is scaled at the flush.
             const float gscale = sigma * wj;
             float dmu_acc = 0.f, loss_acc = 0.f;   // unweighted sums over this item (<= a few thousand terms)
+            // Batch layers (src/layers.jl:221-253, src/batch_array.jl:132-212): z4 = z sigma_j delta_bj + mu_j + theta_bj.
+            // The samples of a chunk are the same for every thread of the warp and, in the sample order of this
+            // pass, nearly always share one batch (boq), so the batch parameters are per-thread registers that
+            // change at SEGMENT boundaries only; a segment's sums  sum g  and  sum g z  give dtheta,
+            // dlogdelta = sigma delta sum g z, and its share of dmu and dlogsigma (sum g delta).  delta is folded
+            // into the dloss/dz entries.
+            const int boff = BATCH ? cur.boff : -1;
+            const size_t brow = BATCH ? (size_t)__ldg(p.pass_order + jt) * p.n_views + cur.bview : 0;
+            const uint16_t* const bos_row = BATCH ? p.bos + brow * dp.Mp : nullptr;
+            const uint16_t* const boq_row = BATCH ? p.boq + brow * (dp.Mp >> 2) : nullptr;
+            uint32_t cur_b = B_NONE;               // no batch parameters in force
+            float sd = sigma, mt = muj, dl = 1.f;  // sigma_j delta_bj, mu_j + theta_bj, delta_bj
+            float seg_g = 0.f, seg_gz = 0.f, dls_acc = 0.f;
+            uint32_t pre_b = B_NONE;               // batch whose parameters were fetched ahead (per tile)
+            float pre_ld = 0.f, pre_th = 0.f;
+            auto close_segment = [&]() {
+                if (cur_b != B_NONE) {
+                    store_segment();               // a still older segment (several switches inside one tile)
+                    pend_bidx = boff + (int)cur_b;
+                    pend_dth = seg_g * wj;
+                    pend_dld = seg_gz * sd * wj;
+                }
+                dmu_acc += seg_g;
+                dls_acc = fmaf(seg_g, dl, dls_acc);
+                seg_g = seg_gz = 0.f;
+            };
+            auto enter_segment = [&](uint32_t b_) {
+                close_segment();
+                cur_b = b_;
+                const float ld = b_ == pre_b ? pre_ld : __ldg(dp.logdelta + boff + (int)b_);
+                const float th = b_ == pre_b ? pre_th : __ldg(dp.theta + boff + (int)b_);
+                dl = __expf(ld);
+                sd = sigma * dl;
+                mt = muj + th;
+            };
 
             // ---- Y tile: h = rna_tf32(y), l = y - h -> TMEM (A of MMA1); gscale * y -> shared memory (B of MMA2).
             // The previous item's MMAs have all completed (B_DY_FULL was waited on), so both are free.
@@ -722,29 +791,40 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
                 mbar_arrive(bar(B_Y_READY));
                 if (trp) stamp(g, 21 + 6 * grp);
                 store_partials();
+                store_segment();
                 if (itx.peek_jt() >= 0) prefetch_item(itx.peek_jt());
             }
 
             // per-entry math on 16 consecutive samples: z[] (TMEM columns) in, dloss/dz (TF32-rounded bits) out
-            auto epi16 = [&](uint32_t (&z)[16], const float (&a)[16]) {
+            // entries [OFF, OFF + CNT) of a 16-sample chunk
+            auto epi = [&](auto cnt_c, auto off_c, uint32_t (&z)[16], const float (&a)[16]) {
+                constexpr int CNT = decltype(cnt_c)::value, OFF = decltype(off_c)::value;
                 // dmu_acc / loss_acc collect the unweighted sums; the column weight w_j (a per-thread
                 // constant) is applied at the item flush.
+                auto tally = [&](float gv, uint32_t zraw) -> uint32_t {
+                    if (BATCH) {
+                        seg_g += gv;
+                        seg_gz = fmaf(gv, __uint_as_float(zraw), seg_gz);
+                        return rn_bits(gv * dl);
+                    }
+                    dmu_acc += gv;
+                    return rn_bits(gv);
+                };
                 if (dist == DIST_NORMAL) {
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) {
-                        float d = fmaf(__uint_as_float(z[e]), sigma, muj) - a[e];
+                    for (int e = OFF; e < OFF + CNT; ++e) {
+                        float d = fmaf(__uint_as_float(z[e]), sd, mt) - a[e];
                         d = fabsf(a[e]) < INFINITY ? d : 0.f;        // NaN / Inf => missing (ordered compare)
                         loss_acc = fmaf(d, d, loss_acc);              // (z-a)^2, halved and weighted at flush
-                        dmu_acc += d;
-                        z[e] = rn_bits(d);
+                        z[e] = tally(d, z[e]);
                     }
                 } else if (dist == DIST_BERNOULLI) {
                     // softplus(z) - a z ; sigmoid(z) - a, sharing e = exp(-|z|); a missing entry makes both NaN
                     // and is masked away once at the end
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) {
+                    for (int e = OFF; e < OFF + CNT; ++e) {
                         const uint32_t m = obs_mask(a[e]);
-                        float z4 = fmaf(__uint_as_float(z[e]), sigma, muj);
+                        float z4 = fmaf(__uint_as_float(z[e]), sd, mt);
                         float ex = ex2_fast(fabsf(z4) * -1.4426950408889634f);
                         float w = 1.0f + ex;
                         float r = rcp_fast(w);
@@ -752,37 +832,70 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
                         float l = fmaf(-a[e], z4, fmaf(lg2_fast(w), 0.6931471805599453f, fmaxf(z4, 0.f)));
                         float gv = and_mask(sg - a[e], m);
                         loss_acc = fmaf(2.f, and_mask(l, m), loss_acc);
-                        dmu_acc += gv;
-                        z[e] = rn_bits(gv);
+                        z[e] = tally(gv, z[e]);
                     }
                 } else if (dist == DIST_POISSON) {
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) {
+                    for (int e = OFF; e < OFF + CNT; ++e) {
                         const uint32_t m = obs_mask(a[e]);
-                        float z4 = fmaf(__uint_as_float(z[e]), sigma, muj);
+                        float z4 = fmaf(__uint_as_float(z[e]), sd, mt);
                         float ez = ex2_fast(z4 * 1.4426950408889634f);
                         float gv = and_mask(ez - a[e], m);
                         float l = and_mask(fmaf(-a[e], z4, ez), m);
                         loss_acc = fmaf(2.f, l, loss_acc);
-                        dmu_acc += gv;
-                        z[e] = rn_bits(gv);
+                        z[e] = tally(gv, z[e]);
                     }
                 } else {
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) {
-                        float z4 = fmaf(__uint_as_float(z[e]), sigma, muj);
+                    for (int e = OFF; e < OFF + CNT; ++e) {
+                        float z4 = fmaf(__uint_as_float(z[e]), sd, mt);
                         float2 lg = noise_eval_slow(dist, z4, a[e], th_range, dp.ordinal_eps, dp.hinge_margin);
                         loss_acc = fmaf(2.f, lg.x, loss_acc);        // keep the common 1/2 factor at flush
-                        dmu_acc += lg.y;
-                        z[e] = rn_bits(lg.y);
+                        z[e] = tally(lg.y, z[e]);
                     }
                 }
             };
+            // four positions that lie in several batches (a batch boundary): entry by entry through the generic
+            // noise evaluation, switching segments as the batch id changes
+            auto epi_mixed4 = [&](auto off_c, uint32_t (&z)[16], const float (&a)[16], int i_first) {
+                constexpr int OFF = decltype(off_c)::value;
+#pragma unroll
+                for (int e = OFF; e < OFF + 4; ++e) {
+                    if (i_first + e < dp.M) {
+                        const uint32_t b_ = __ldg(bos_row + i_first + e);
+                        if (b_ != cur_b) enter_segment(b_);
+                    }
+                    const float zr = __uint_as_float(z[e]);
+                    float2 lg = noise_eval_slow(dist, fmaf(zr, sd, mt), a[e], th_range, dp.ordinal_eps, dp.hinge_margin);
+                    loss_acc = fmaf(2.f, lg.x, loss_acc);
+                    seg_g += lg.y;
+                    seg_gz = fmaf(lg.y, zr, seg_gz);
+                    z[e] = rn_bits(lg.y * dl);
+                }
+            };
+            using std::integral_constant;
 
             for (int it = it0; it < it1; ++it, ++g) {
                 if ((g & 1u) != (uint32_t)grp) continue;             // the other group's tile
                 const bool tr = quarter == 0 && h32 == 0 && lane == 0;
                 if (tr) stamp(g, 5);
+                // batches of this thread's eight 4-position groups (16 bits each); the parameters of the first
+                // batch that differs from the one in force are fetched before the waits below
+                uint4 qw = make_uint4(B_NONE * 0x10001u, B_NONE * 0x10001u, B_NONE * 0x10001u, B_NONE * 0x10001u);
+                if (BATCH && boff >= 0) {
+                    qw = __ldg(reinterpret_cast<const uint4*>(boq_row + ((it * BI + 32 * h32) >> 2)));
+                    pre_b = cur_b;
+                    const uint32_t w[4] = {qw.x, qw.y, qw.z, qw.w};
+#pragma unroll
+                    for (int k = 7; k >= 0; --k) {
+                        const uint32_t id = (w[k >> 1] >> (16 * (k & 1))) & 0xffffu;
+                        if (id != cur_b && id != B_MIXED) pre_b = id;
+                    }
+                    if (pre_b != cur_b) {
+                        pre_ld = __ldg(dp.logdelta + boff + (int)pre_b);
+                        pre_th = __ldg(dp.theta + boff + (int)pre_b);
+                    }
+                }
                 mbar_wait(bar(B_Z_FULL + rz.s), rz.ph);
                 if (tr) stamp(g, 6);
                 mbar_wait(bar(B_FULL_A + ra.s), ra.ph);
@@ -811,7 +924,28 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
                         }
                     }
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    if (!(DBG && p.ablate & 8)) epi16(z, a);
+                    if (BATCH) {
+                        const uint32_t w0 = hh == 0 ? qw.x : qw.z, w1 = hh == 0 ? qw.y : qw.w;
+                        const uint32_t id0 = w0 & 0xffffu;
+                        if (w0 == w1 && (w0 >> 16) == id0 && id0 != B_MIXED) {
+                            if (id0 != cur_b) enter_segment(id0);
+                            epi(integral_constant<int, 16>{}, integral_constant<int, 0>{}, z, a);
+                        } else {
+                            const int i_first = it * BI + 32 * h32 + 16 * hh;
+                            auto quad = [&](auto off_c, uint32_t id) {
+                                if (id == B_MIXED) {
+                                    epi_mixed4(off_c, z, a, i_first);
+                                } else {
+                                    if (id != cur_b) enter_segment(id);
+                                    epi(integral_constant<int, 4>{}, off_c, z, a);
+                                }
+                            };
+                            quad(integral_constant<int, 0>{}, w0 & 0xffffu);
+                            quad(integral_constant<int, 4>{}, w0 >> 16);
+                            quad(integral_constant<int, 8>{}, w1 & 0xffffu);
+                            quad(integral_constant<int, 12>{}, w1 >> 16);
+                        }
+                    } else if (!(DBG && p.ablate & 8)) epi(integral_constant<int, 16>{}, integral_constant<int, 0>{}, z, a);
                     // dloss/dz back to TMEM in place of Z (A operand of MMA3) and over the A values this thread
                     // read (MN-major A operand of MMA2): same addresses, 128-bit stores, no transposition
                     TMEM_ST16(zt + 16 * hh, z);
@@ -828,6 +962,7 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
                 tc_fence_before();
                 fence_async_smem();
                 mbar_arrive(bar(B_G_READY + rz.s));
+                store_segment();
                 if (tr) stamp(g, 9);
                 ra.next(SA); ra.next(SA);
                 rz.next(SZ); rz.next(SZ);
@@ -840,7 +975,7 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
             if (trb) stamp(g, 16 + 6 * grp);
             loss_d += (double)(loss_acc * wj);
             ItemRegs nxt;
-            nxt.logsigma = nxt.mu = nxt.w = 0.f; nxt.ci = 0;
+            nxt.logsigma = nxt.mu = nxt.w = 0.f; nxt.ci = 0; nxt.boff = -1; nxt.bview = 0;
 #pragma unroll
             for (int v = 0; v < 4; ++v) nxt.y[v] = make_float4(0.f, 0.f, 0.f, 0.f);
 
@@ -866,14 +1001,20 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
             }
             // dmu_j = sum_i g ; dlogsigma_j = sum_i sigma_j * g  (the reference's ColScale quirk).  The four warps that
             // share a feature row (two groups x two sample halves) each store their own partial.
+            if (BATCH) {
+                close_segment();      // the open segment; its two REDs are deferred like the column sums
+                pend_dls = dls_acc * wj * sigma;
+            } else {
+                pend_dls = dmu_acc * wj * sigma;
+            }
             pend_dmu = dmu_acc * wj;
-            pend_dls = dmu_acc * wj * sigma;
             pend_j = jok ? j : -1;
             if (trb) stamp(g, 18 + 6 * grp);
             cur = nxt;
             ++q;
         }
         store_partials();
+        store_segment();
         // data loss: sum over the epilogue warps, 0.5 factor applied here
         loss_d *= 0.5;
         for (int o = 16; o > 0; o >>= 1) loss_d += __shfl_xor_sync(0xffffffffu, loss_d, o);
@@ -896,12 +1037,13 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
 
 // Operand split of X:  Xh = rna_tf32(X) (FP32 array) and Xb = bf16([Xh | X - Xh]) ([Mp][128] BF16): the TF32
 // operand of every contraction and the BF16 operands of the first-order correction of Z
+// `perm` (or null): output row r holds the split of X row perm[r] (the per-order operand copies of the batch path)
 __global__ void prep_operands_kernel(const float4* __restrict__ X, float4* __restrict__ Xh, uint2* __restrict__ Xb,
-                                     int rows, int K4 /* Kp / 4 */, const int* stop_flag) {
+                                     int rows, int K4 /* Kp / 4 */, const int* stop_flag, const int32_t* __restrict__ perm) {
     if (stop_flag != nullptr && *stop_flag != 0) return;
     const size_t n4 = (size_t)rows * K4;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
-        const float4 v = X[i];
+        const float4 v = perm ? X[(size_t)perm[i / K4] * K4 + (i - (i / K4) * K4)] : X[i];
         float4 h;
         h.x = __uint_as_float(rna_tf32(v.x)); h.y = __uint_as_float(rna_tf32(v.y));
         h.z = __uint_as_float(rna_tf32(v.z)); h.w = __uint_as_float(rna_tf32(v.w));
@@ -910,6 +1052,44 @@ __global__ void prep_operands_kernel(const float4* __restrict__ X, float4* __res
         Xb[row * 32 + c4] = make_uint2(pack_bf16(h.x, h.y), pack_bf16(h.z, h.w));
         Xb[row * 32 + 16 + c4] = make_uint2(pack_bf16(v.x - h.x, v.y - h.y), pack_bf16(v.z - h.z, v.w - h.w));
     }
+}
+
+// dX[i] = sum over the sample orders of the copy's row for sample i; the copies are left zeroed for the next pass
+__global__ void combine_dx_kernel(float4* __restrict__ dXo, const int32_t* __restrict__ pos, float4* __restrict__ dX,
+                                  int n_orders, int Mp, int K4, const int* stop_flag) {
+    if (stop_flag != nullptr && *stop_flag != 0) return;
+    const size_t n4 = (size_t)Mp * K4;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n4; idx += (size_t)gridDim.x * blockDim.x) {
+        const int i = (int)(idx / K4), c = (int)(idx - (size_t)i * K4);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int o = 0; o < n_orders; ++o) {
+            float4* src = dXo + ((size_t)o * Mp + pos[(size_t)o * Mp + i]) * K4 + c;
+            const float4 v = *src;
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            *src = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        dX[idx] = acc;
+    }
+}
+
+// One row of A_tc per block: the pass' feature row with its samples in the pass' order, or NaN when the
+// column belongs to another pass of the same tile
+__global__ void build_a_tc_kernel(const float* __restrict__ A, float* __restrict__ A_tc, int N, int lda, int Mp,
+                                  const int32_t* __restrict__ pass_feat0, const int32_t* __restrict__ pass_order,
+                                  const int32_t* __restrict__ view_order, const int32_t* __restrict__ bcol_view,
+                                  const int32_t* __restrict__ perm) {
+    const int r = blockIdx.x, ps = r >> 7;
+    const int j = pass_feat0[ps] + (r & 127);
+    const int o = pass_order[ps];
+    bool active = j < N;
+    if (active) {
+        const int bv = bcol_view[j];
+        active = bv >= 0 ? view_order[bv] == o : (ps == 0 || pass_feat0[ps - 1] != pass_feat0[ps]);
+    }
+    float* dst = A_tc + (size_t)r * lda;
+    const float* src = A + (size_t)(active ? j : 0) * lda;
+    const int32_t* pr = perm + (size_t)o * Mp;
+    for (int p = threadIdx.x; p < lda; p += blockDim.x) dst[p] = active ? src[pr[p]] : __int_as_float(0x7fc00000);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -961,33 +1141,58 @@ bool make_map(CUtensorMap* m, const float* base, uint64_t cols, uint64_t rows, u
 }  // namespace
 
 bool tc_supported(const DataPassParams& p) {
-    return p.Kp <= KK && p.Kp >= 8 && p.n_batch_views == 0 && p.col_ssq == nullptr;
+    return p.Kp <= KK && p.Kp >= 8 && p.col_ssq == nullptr;
+}
+
+cudaError_t launch_build_a_tc(const DataPassParams& dp, const TcBatchDev& bp, float* A_tc, cudaStream_t s) {
+    build_a_tc_kernel<<<bp.n_pass * 128, 256, 0, s>>>(dp.A, A_tc, dp.N, dp.lda, dp.Mp, bp.pass_feat0, bp.pass_order,
+                                                      bp.view_order, dp.bcol_view, bp.perm);
+    return cudaGetLastError();
 }
 
 // Xh, Xl: [Mp][64] operand scratch owned by the handle; refreshed here when `refresh_split`
-cudaError_t launch_data_pass_tc(const DataPassParams& dp, float* Xh, float* Xl, bool refresh_split, int precision,
-                                cudaStream_t s, int n_sms) {
-    if (!tc_supported(dp)) return cudaErrorInvalidValue;
+cudaError_t launch_data_pass_tc(const DataPassParams& dp_in, float* Xh, float* Xl, bool refresh_split, int precision,
+                                cudaStream_t s, int n_sms, const TcBatchDev* bp, int* n_launches) {
+    if (!tc_supported(dp_in) || (dp_in.n_batch_views > 0) != (bp != nullptr)) return cudaErrorInvalidValue;
+    DataPassParams dp = dp_in;
     cudaError_t e = cudaSuccess;
+    int launched = 0;
+    const bool permuted = bp != nullptr && !bp->direct;
+    int x_rows = dp.Mp;
+    if (permuted) {
+        // per-order copies: operands gathered from the current X on every pass, dX gathered back afterwards
+        Xh = bp->Xh; Xl = bp->Xb;
+        x_rows = bp->n_orders * dp.Mp;
+        refresh_split = true;
+    }
     if (refresh_split) {   // otherwise the previous epoch's update pass wrote Xh / Xl together with X
-        const size_t n4 = (size_t)dp.Mp * dp.Kp / 4;
+        const size_t n4 = (size_t)x_rows * dp.Kp / 4;
         prep_operands_kernel<<<(unsigned)((n4 + 255) / 256 < 1184 ? (n4 + 255) / 256 : 1184), 256, 0, s>>>(
-            reinterpret_cast<const float4*>(dp.X), reinterpret_cast<float4*>(Xh), reinterpret_cast<uint2*>(Xl), dp.Mp,
-            dp.Kp / 4, dp.stop_flag);
+            reinterpret_cast<const float4*>(dp.X), reinterpret_cast<float4*>(Xh), reinterpret_cast<uint2*>(Xl), x_rows,
+            dp.Kp / 4, dp.stop_flag, permuted ? bp->perm : nullptr);
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
+        ++launched;
     }
+    float* dx_target = permuted ? bp->dX : dp.dX;
+    const float* a_src = permuted ? bp->A_tc : dp.A;
+    const int n_pass = bp ? bp->n_pass : (dp.N + BJ - 1) / BJ;
+    if (bp) dp.tc_cost_cum = bp->cost_cum;
 
     CUtensorMap tmXh, tmXl, tmXm, tmA, tmDX;
-    bool ok = make_map(&tmXh, Xh, KK, dp.Mp, KK, 64, false, false) && make_map_bf16(&tmXl, Xl, 2 * KK, dp.Mp, 64) &&
-              make_map(&tmXm, Xh, KK, dp.Mp, KK, 64, false, true) && make_map(&tmA, dp.A, dp.lda, dp.N, dp.lda, 128, true, true) &&
-              make_map(&tmDX, dp.dX, dp.Kp, dp.Mp, dp.Kp, 64, false, false);
+    bool ok = make_map(&tmXh, Xh, KK, x_rows, KK, 64, false, false) && make_map_bf16(&tmXl, Xl, 2 * KK, x_rows, 64) &&
+              make_map(&tmXm, Xh, KK, x_rows, KK, 64, false, true) &&
+              make_map(&tmA, a_src, dp.lda, permuted ? (uint64_t)n_pass * BJ : (uint64_t)dp.N, dp.lda, 128, true, true) &&
+              make_map(&tmDX, dx_target, dp.Kp, x_rows, dp.Kp, 64, false, false);
     if (!ok) return cudaErrorUnknown;
 
     TcParams p;
     p.dp = dp;
-    p.n_jt = (dp.N + BJ - 1) / BJ;
+    p.n_jt = n_pass;
     p.n_it = (dp.M + BI - 1) / BI;
+    p.pass_feat0 = bp ? bp->pass_feat0 : nullptr; p.pass_order = bp ? bp->pass_order : nullptr;
+    p.view_order = bp ? bp->view_order : nullptr; p.boq = bp ? bp->boq : nullptr; p.bos = bp ? bp->bos : nullptr;
+    p.n_views = bp ? bp->n_views : 0; p.n_orders = bp ? bp->n_orders : 1;
     p.z_passes = precision >= 2 ? 1 : 3;
     {
         static const char* ab = getenv("PMF_TC_ABLATE");
@@ -1007,12 +1212,22 @@ cudaError_t launch_data_pass_tc(const DataPassParams& dp, float* Xh, float* Xl, 
         p.trace_cta = tc ? atoi(tc) : 0;
     }
     const bool dbg = p.ablate != 0 || p.trace != nullptr;
-    auto kern = dbg ? data_pass_tc_kernel<true> : data_pass_tc_kernel<false>;
+    const bool batch = bp != nullptr;
+    auto kern = batch ? data_pass_tc_kernel<false, true> : dbg ? data_pass_tc_kernel<true, false> : data_pass_tc_kernel<false, false>;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TOTAL);
     if (e != cudaSuccess) return e;
     const long long n_tiles = (long long)p.n_jt * p.n_it;
     int grid = n_tiles < n_sms ? (int)n_tiles : n_sms;
     kern<<<grid, NTHREADS, SMEM_TOTAL, s>>>(tmXh, tmXl, tmXm, tmA, tmDX, p);
+    ++launched;
+    if (permuted) {
+        const size_t n4 = (size_t)dp.Mp * dp.Kp / 4;
+        combine_dx_kernel<<<(unsigned)((n4 + 255) / 256 < 1184 ? (n4 + 255) / 256 : 1184), 256, 0, s>>>(
+            reinterpret_cast<float4*>(bp->dX), bp->pos, reinterpret_cast<float4*>(dp.dX), bp->n_orders, dp.Mp, dp.Kp / 4,
+            dp.stop_flag);
+        ++launched;
+    }
+    if (n_launches) *n_launches = launched;
     if (trace_path) {      // experiments only: dump the stamps of this launch (synchronises the stream)
         static long long host[TRACE_TILES * TRACE_EV + 2 * TRACE_CTAS];
         cudaStreamSynchronize(s);

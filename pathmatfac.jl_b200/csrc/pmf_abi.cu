@@ -178,6 +178,7 @@ int pmf_destroy(pmf_handle h) {
     dev_free(h->weight); dev_free(h->colinfo); dev_free(h->thresholds); dev_free(h->scalars); dev_free(h->ctrl);
     dev_free(h->vp); dev_free(h->sg); dev_free(h->accvp); dev_free(h->regw); dev_free(h->regc);
     dev_free(h->bcol_off); dev_free(h->bcol_view); dev_free(h->bcol_nb); dev_free(h->batch_of_sample);
+    h->free_tc_plan();
     dev_free(h->hist); dev_free(h->col_ssq); dev_free(h->col_cnt); dev_free(h->col_sqerr);
     for (int s = 0; s < 2; ++s) h->reg[s].free_all();
     if (h->comm) { nccl().CommDestroy(h->comm); h->comm = nullptr; }
@@ -203,6 +204,7 @@ int pmf_set_data(pmf_handle h, const float* A) {
     CU(h, up2d(h->A, h->lda, A, h->M, h->N, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
     h->have_data = true;
+    h->tcb_valid = false;      // A_tc is a permuted copy of A
     return PMF_OK;
 }
 
@@ -264,6 +266,9 @@ int pmf_set_noise(pmf_handle h, int32_t n_ranges, const int32_t* cs, const int32
             w += 30 * (n_present - 1);
             cum[jt + 1] = cum[jt] + w;
         }
+        h->tile_cost_host.resize(n_jt);
+        for (int jt = 0; jt < n_jt; ++jt) h->tile_cost_host[jt] = cum[jt + 1] - cum[jt];
+        h->tcb_valid = false;
         dev_free(h->tc_cost_cum);
         CU(h, dev_alloc(&h->tc_cost_cum, (size_t)n_jt + 1));
         CU(h, cudaMemcpy(h->tc_cost_cum, cum.data(), ((size_t)n_jt + 1) * 4, cudaMemcpyHostToDevice));
@@ -314,6 +319,7 @@ int pmf_set_batch_layout(pmf_handle h, int32_t n_views, const int32_t* cs, const
     CU(h, cudaMemcpy(h->logsigma(), ls.data(), (size_t)h->N * 4, cudaMemcpyHostToDevice));
     CU(h, cudaMemcpy(h->mu(), mu.data(), (size_t)h->N * 4, cudaMemcpyHostToDevice));
     dev_free(h->bcol_off); dev_free(h->bcol_view); dev_free(h->bcol_nb); dev_free(h->batch_of_sample);
+    h->free_tc_plan();
     if (n_views > 0) {
         std::vector<int32_t> coff(h->Np, -1), cview(h->Np, -1), cnb(h->Np, 0);
         for (int v = 0; v < n_views; ++v)
@@ -335,6 +341,7 @@ int pmf_set_batch_layout(pmf_handle h, int32_t n_views, const int32_t* cs, const
         CU(h, cudaMemcpy(h->bcol_view, cview.data(), (size_t)h->Np * 4, cudaMemcpyHostToDevice));
         CU(h, cudaMemcpy(h->bcol_nb, cnb.data(), (size_t)h->Np * 4, cudaMemcpyHostToDevice));
         CU(h, cudaMemcpy(h->batch_of_sample, b.data(), b.size() * 4, cudaMemcpyHostToDevice));
+        h->bos_host.assign(bos, bos + (size_t)n_views * h->M);
     }
     return PMF_OK;
 }
@@ -1035,15 +1042,149 @@ int pmf_model_s::realloc_vectors(int new_nbp) {
     return cudaDeviceSynchronize() == cudaSuccess ? 0 : -1;
 }
 
+// ---- tcgen05 data pass with batch layers: sample orders and passes (TcBatchDev) -----------------------
+void pmf_model_s::free_tc_plan() {
+    for (void* q : tcb_allocs) cudaFree(q);
+    tcb_allocs.clear();
+    tcb = pmf::TcBatchDev{};
+    tcb_valid = false;
+}
+
+int pmf_model_s::build_tc_plan() {
+    free_tc_plan();
+    const int V = (int)views.size();
+    const int n_jt = (N + 127) / 128;
+    if (V == 0 || (int)tile_cost_host.size() != n_jt || bos_host.size() != (size_t)V * M)
+        return fail(this, PMF_ERR_STATE, "batch layout / noise models are not set");
+    for (const BatchView& bv : views)
+        if (bv.n_batches > 65533) return fail(this, PMF_ERR_ARG, "tcgen05 data pass: more than 65533 batches in a view");
+
+    // 1. sample orders.  A view keeps the identity order when its batches are (nearly) contiguous as given;
+    //    otherwise its samples are stably sorted by batch id.  Equal permutations are shared.
+    std::vector<std::vector<int32_t>> perms(1, std::vector<int32_t>(Mp));
+    for (int p = 0; p < Mp; ++p) perms[0][p] = p;
+    std::vector<int32_t> view_order(V, 0);
+    auto mixed_quads = [&](const int32_t* b, const std::vector<int32_t>& perm) {
+        int n = 0;
+        for (int q = 0; 4 * q < M; ++q) {
+            const int hi = std::min(4 * q + 4, M);
+            for (int p = 4 * q + 1; p < hi; ++p)
+                if (b[perm[p]] != b[perm[4 * q]]) { ++n; break; }
+        }
+        return n;
+    };
+    for (int v = 0; v < V; ++v) {
+        const int32_t* b = bos_host.data() + (size_t)v * M;
+        if (mixed_quads(b, perms[0]) <= 2 * views[v].n_batches + 2) continue;
+        std::vector<int32_t> perm(Mp);
+        for (int p = 0; p < Mp; ++p) perm[p] = p;
+        std::stable_sort(perm.begin(), perm.begin() + M, [&](int32_t x, int32_t y) { return b[x] < b[y]; });
+        int o = -1;
+        for (int k = 1; k < (int)perms.size(); ++k)
+            if (perms[k] == perm) { o = k; break; }
+        if (o < 0) { perms.push_back(std::move(perm)); o = (int)perms.size() - 1; }
+        view_order[v] = o;
+    }
+    const int n_orders = (int)perms.size();
+
+    // 2. passes: every feature tile once per order its batched columns need (columns without batch layers
+    //    ride with the tile's first pass)
+    std::vector<int32_t> pass_feat0, pass_order, cost_cum(1, 0);
+    for (int jt = 0; jt < n_jt; ++jt) {
+        std::vector<int> os;
+        for (int v = 0; v < V; ++v)
+            if (views[v].col_start < std::min(N, 128 * jt + 128) && views[v].col_stop > 128 * jt &&
+                std::find(os.begin(), os.end(), view_order[v]) == os.end())
+                os.push_back(view_order[v]);
+        if (os.empty()) os.push_back(0);
+        for (int o : os) {
+            pass_feat0.push_back(128 * jt);
+            pass_order.push_back(o);
+            cost_cum.push_back(cost_cum.back() + tile_cost_host[jt]);
+        }
+    }
+    const int n_pass = (int)pass_feat0.size();
+
+    // 3. batch of every position / 4-position group, per (order, view)
+    const int Mq = Mp / 4;
+    std::vector<uint16_t> bos16((size_t)n_orders * V * Mp), boq((size_t)n_orders * V * Mq);
+    for (int o = 0; o < n_orders; ++o)
+        for (int v = 0; v < V; ++v) {
+            const int32_t* b = bos_host.data() + (size_t)v * M;
+            uint16_t* row = bos16.data() + ((size_t)o * V + v) * Mp;
+            uint16_t* qrow = boq.data() + ((size_t)o * V + v) * Mq;
+            for (int p = 0; p < Mp; ++p) row[p] = (uint16_t)b[perms[o][std::min(p, M - 1)]];   // padding continues the last batch
+            for (int q = 0; q < Mq; ++q) {
+                uint16_t x = row[4 * q];
+                for (int p = 4 * q + 1; p < 4 * q + 4; ++p)
+                    if (row[p] != x) { x = 0xFFFFu; break; }
+                qrow[q] = x;
+            }
+        }
+
+    auto upload = [&](const void* src, size_t bytes, const void** dst) -> bool {
+        void* d = nullptr;
+        if (cudaMalloc(&d, bytes ? bytes : 4) != cudaSuccess) return false;
+        tcb_allocs.push_back(d);
+        if (src && bytes && cudaMemcpy(d, src, bytes, cudaMemcpyHostToDevice) != cudaSuccess) return false;
+        *dst = d;
+        return true;
+    };
+    pmf::TcBatchDev& t = tcb;
+    t.n_orders = n_orders; t.n_pass = n_pass; t.n_views = V;
+    t.direct = n_orders == 1;
+    bool ok = upload(pass_feat0.data(), (size_t)n_pass * 4, (const void**)&t.pass_feat0) &&
+              upload(pass_order.data(), (size_t)n_pass * 4, (const void**)&t.pass_order) &&
+              upload(view_order.data(), (size_t)V * 4, (const void**)&t.view_order) &&
+              upload(cost_cum.data(), ((size_t)n_pass + 1) * 4, (const void**)&t.cost_cum) &&
+              upload(boq.data(), boq.size() * 2, (const void**)&t.boq) &&
+              upload(bos16.data(), bos16.size() * 2, (const void**)&t.bos);
+    if (ok && !t.direct) {
+        std::vector<int32_t> perm_flat((size_t)n_orders * Mp), pos_flat((size_t)n_orders * Mp);
+        for (int o = 0; o < n_orders; ++o)
+            for (int p = 0; p < Mp; ++p) {
+                perm_flat[(size_t)o * Mp + p] = perms[o][p];
+                pos_flat[(size_t)o * Mp + perms[o][p]] = p;
+            }
+        const size_t rows = (size_t)n_orders * Mp;
+        ok = upload(perm_flat.data(), perm_flat.size() * 4, (const void**)&t.perm) &&
+             upload(pos_flat.data(), pos_flat.size() * 4, (const void**)&t.pos) &&
+             upload(nullptr, rows * 64 * 4, (const void**)&t.Xh) && upload(nullptr, rows * 64 * 4, (const void**)&t.Xb) &&
+             upload(nullptr, rows * Kp * 4, (const void**)&t.dX) &&
+             upload(nullptr, (size_t)n_pass * 128 * lda * 4, (const void**)&t.A_tc);
+        if (ok) {
+            // operand scratch is 64 / 128 wide and zero beyond Kp; the dX copies start (and are left) clean
+            ok = cudaMemsetAsync(t.Xh, 0, rows * 64 * 4, stream) == cudaSuccess &&
+                 cudaMemsetAsync(t.Xb, 0, rows * 64 * 4, stream) == cudaSuccess &&
+                 cudaMemsetAsync(t.dX, 0, rows * Kp * 4, stream) == cudaSuccess;
+            pmf::DataPassParams p;
+            std::memset(&p, 0, sizeof p);
+            p.N = N; p.lda = lda; p.Mp = Mp; p.A = A; p.bcol_view = bcol_view;
+            ok = ok && pmf::launch_build_a_tc(p, t, const_cast<float*>(t.A_tc), stream) == cudaSuccess;
+            ++launches;
+        }
+    }
+    if (!ok) {
+        free_tc_plan();
+        return fail(this, PMF_ERR_ALLOC, "device allocation failed (tcgen05 batch plan: %d orders, %d passes)", n_orders, n_pass);
+    }
+    tcb_valid = true;
+    return 0;
+}
+
 int pmf_model_s::run_data_pass(DataPassParams& p, int kind, int precision) {
     const bool tc_ok = tc_supported(p) && cc_major == 10;
     if (kind == PMF_KERNEL_TC && !tc_ok)
-        return fail(this, PMF_ERR_ARG, "tcgen05 data pass needs K <= 64, no batch layers and an sm_100 device");
+        return fail(this, PMF_ERR_ARG, "tcgen05 data pass needs 8 <= K <= 64 and an sm_100 device");
     // AUTO: the tcgen05 path pays off (and its single-pass TF32 gradient contractions average below
     // the 1e-4 parity bar) on large problems; small ones run the exact-FP32 FFMA kernel.
     const bool big = (double)M * (double)N >= 4.0e6 && M >= 1024;
     const bool use_tc = kind == PMF_KERNEL_TC || (kind == PMF_KERNEL_AUTO && tc_ok && auto_tc && big);
     if (use_tc) {
+        if (!views.empty() && !tcb_valid) {
+            int rc = build_tc_plan();
+            if (rc != 0) return rc;
+        }
         if (!Xh) {
             // 64-wide FP32 and 128-wide BF16 operand scratch, zero padded beyond Kp (never written there)
             if (dev_alloc(&Xh, (size_t)Mp * 64) != cudaSuccess || dev_alloc(&Xl, (size_t)Mp * 64) != cudaSuccess ||
@@ -1061,11 +1202,12 @@ int pmf_model_s::run_data_pass(DataPassParams& p, int kind, int precision) {
             cudaEventRecord(t0, stream);
         }
         const bool refresh = !xsplit_valid;
-        cudaError_t e = launch_data_pass_tc(p, Xh, Xl, refresh, precision, stream, n_sms);
+        int n_launched = 0;
+        cudaError_t e = launch_data_pass_tc(p, Xh, Xl, refresh, precision, stream, n_sms, views.empty() ? nullptr : &tcb, &n_launched);
         xsplit_valid = true;     // stays true only while every later change of X goes through run_update_multi
         if (profiling) cudaEventRecord(t1, stream);
         if (e != cudaSuccess) { cuda_failed = true; return fail(this, PMF_ERR_CUDA, "tcgen05 data pass launch: %s", cudaGetErrorString(e)); }
-        launches += refresh ? 2 : 1;
+        launches += n_launched;
         return 0;
     }
     xsplit_valid = false;

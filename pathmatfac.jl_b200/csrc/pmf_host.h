@@ -95,6 +95,15 @@ struct pmf_model_s {
     int nb_max = 0;
     std::vector<BatchView> views;
     int32_t *bcol_off = nullptr, *bcol_view = nullptr, *bcol_nb = nullptr, *batch_of_sample = nullptr;
+    // tcgen05 path with batch layers: sample orders / passes (see TcBatchDev); rebuilt lazily after the data,
+    // the noise models or the batch layout changed
+    std::vector<int32_t> bos_host;           // [n_views][M] batch ids as given
+    std::vector<int32_t> tile_cost_host;     // per 128-feature tile
+    pmf::TcBatchDev tcb{};
+    bool tcb_valid = false;
+    std::vector<void*> tcb_allocs;
+    void free_tc_plan();
+    int build_tc_plan();
     bool layer_reg_present[4] = {false, false, false, false};
     uint32_t frozen_layers = 0, frozen_regs = 0;
     SideReg reg[2];

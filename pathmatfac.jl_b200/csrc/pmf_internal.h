@@ -142,13 +142,40 @@ struct NetworkParams {
 
 // launchers (each defined next to its kernel)
 cudaError_t launch_data_pass_ffma(const DataPassParams& p, cudaStream_t s, int n_sms);
-// tcgen05 path (fused_tc.cu): K <= 64 (operands zero padded to 64), no batch layers.  Xh = rna_tf32(X)
-// ([Mp][64] FP32) and Xl = bf16([Xh | X - Xh]) ([Mp][128] BF16) are scratch operands kept by the update pass
-// (refreshed by the launcher when `refresh_split`).  precision: 0/1 = TF32 + BF16 first-order corrections for
-// Z and TF32 gradients, 2 = TF32 everywhere.
+// tcgen05 path (fused_tc.cu): K <= 64 (operands zero padded to 64).  Xh = rna_tf32(X) ([Mp][64] FP32) and
+// Xl = bf16([Xh | X - Xh]) ([Mp][128] BF16) are scratch operands kept by the update pass (refreshed by the
+// launcher when `refresh_split`).  precision: 0/1 = TF32 + BF16 first-order corrections for Z and TF32
+// gradients, 2 = TF32 everywhere.
+//
+// Batch layers: the epilogue keeps the parameters of ONE batch per thread (column) in registers, so it wants
+// the samples of a batch next to each other.  Views whose batch ids are scattered get their own SAMPLE ORDER
+// (a stable sort by batch id); order 0 is the identity.  A PASS is a (128-feature tile, order) pair: a tile
+// whose columns need several orders is walked once per order, over a copy of A (A_tc) whose rows are permuted
+// to the pass' order and NaN for the columns another pass serves.  Per order there is a copy of the X
+// operands and of the dX accumulator; after the data pass the dX copies are gathered back (combine kernel).
+// When every view is already contiguous (`direct`) there is one order and none of the copies exist.
+struct TcBatchDev {
+    int n_orders, n_pass, n_views;
+    bool direct;
+    const float* A_tc;            // [n_pass * 128][lda]                       (null when direct)
+    const int32_t* perm;          // [n_orders][Mp] position -> sample         (null when direct)
+    const int32_t* pos;           // [n_orders][Mp] sample -> position         (null when direct)
+    float* Xh;                    // [n_orders * Mp][64]                       (null when direct)
+    float* Xb;                    // [n_orders * Mp][128] BF16                 (null when direct)
+    float* dX;                    // [n_orders * Mp][Kp], zero between passes  (null when direct)
+    const int32_t* pass_feat0;    // [n_pass]
+    const int32_t* pass_order;    // [n_pass]
+    const int32_t* view_order;    // [n_views]
+    const int32_t* cost_cum;      // [n_pass + 1]
+    const uint16_t* boq;          // [n_orders][n_views][Mp/4]
+    const uint16_t* bos;          // [n_orders][n_views][Mp]
+};
 bool tc_supported(const DataPassParams& p);
+// `bp`: null for a model without batch layers.  *n_launches receives the number of kernels launched.
 cudaError_t launch_data_pass_tc(const DataPassParams& p, float* Xh, float* Xl, bool refresh_split, int precision,
-                                cudaStream_t s, int n_sms);
+                                cudaStream_t s, int n_sms, const TcBatchDev* bp, int* n_launches);
+// A_tc rows for the plan (fused_tc.cu)
+cudaError_t launch_build_a_tc(const DataPassParams& p, const TcBatchDev& bp, float* A_tc, cudaStream_t s);
 cudaError_t launch_multi_pass(const MultiPassParams& p, cudaStream_t s, int n_sms);
 cudaError_t launch_control(FitControl* ctrl, const double* scalars, double* hist, int hist_cap,
                            int epoch, int max_epochs, double rel_tol, double abs_tol, cudaStream_t s);

@@ -35,7 +35,8 @@ def scale_blocks(blocks, N):
 
 def simulate_problem(M: int, blocks=C2_BLOCKS, K: int = 64, seed: int = 2, missing: float = 0.3,
                      batch_views: Sequence[str] = (), n_batches: int = 0, n_conditions: int = 0,
-                     noise: float = 0.1, data_out: Optional[np.ndarray] = None, model_kwargs=None):
+                     noise: float = 0.1, data_out: Optional[np.ndarray] = None, model_kwargs=None,
+                     sort_batches: bool = False):
     """Build a PathMatFacModel on synthetic data.
 
     Parameters are drawn like simulate_params! (X, Y ~ N(0,1), :7-11; per-view logsigma / mu
@@ -60,6 +61,8 @@ def simulate_problem(M: int, blocks=C2_BLOCKS, K: int = 64, seed: int = 2, missi
     batch_dict = None
     if batch_views:
         batch_dict = {v: [int(b) for b in rng.integers(0, n_batches, size=M)] for v in batch_views}
+        if sort_batches:      # samples grouped by batch in every view (the same sample order works for all)
+            batch_dict = {v: sorted(b) for v, b in batch_dict.items()}
     conditions = None
     if n_conditions or batch_views:
         conditions = list(np.sort(rng.integers(0, max(n_conditions, 1), size=M)))

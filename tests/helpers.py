@@ -15,11 +15,12 @@ def relerr(a, b):
 def make_pair(M, views, K, seed, batch_views=(), n_batches=0, n_conditions=0, missing=0.0,
               lambda_X_l2=None, lambda_Y_l2=1.0, lambda_layer=1.0, feature_graphs=None,
               lambda_Y_selective_l1=None, lambda_Y_graph=None, Y_ard=False, feature_sets=None,
-              feature_ids=None):
+              feature_ids=None, sort_batches=False):
     """Returns (product model, oracle model, D float32).  ``views``: name -> (dist, n cols),
     listed in (distribution, view) sorted order."""
     om, D, meta = O.simulate_model(M, views, K, seed, batch_views=batch_views, n_batches=n_batches,
-                                   n_conditions=n_conditions, missing=missing, dtype=np.float64)
+                                   n_conditions=n_conditions, missing=missing, dtype=np.float64,
+                                   sort_batches=sort_batches)
     D32 = np.asfortranarray(D.astype(np.float32))
     # round parameters to float32 so both paths start from identical numbers
     for name in ("X", "Y", "logsigma", "mu"):

@@ -434,14 +434,54 @@ def test_tc_refuses_unsupported_shapes():
             eng.loss_grad(include_reg=False)
     finally:
         eng.close()
-    model, om, D = make_pair(200, {"methylation": ("normal", 100)}, K=16, seed=71, batch_views=["methylation"], n_batches=3)
+
+
+@pytest.mark.parametrize("sort_batches", [True, False])
+def test_tc_batch_layers(sort_batches):
+    """BatchScale / BatchShift on the tcgen05 path (src/layers.jl:221-253, src/batch_array.jl:132-212): sorted
+    batch ids run the per-segment registers, unsorted ones the entry-by-entry chunks; one view has no batch
+    layers, view boundaries fall inside 128-feature tiles, M is ragged against the 16-sample chunks."""
+    views = {"mutation": ("bernoulli", 150), "methylation": ("normal", 333), "mrnaseq": ("normal", 280),
+             "counts": ("poisson", 190)}
+    model, om, D = make_pair(1203, views, K=24, seed=72, batch_views=["methylation", "mutation", "counts"],
+                             n_batches=9, missing=0.3, lambda_X_l2=1.0, sort_batches=sort_batches)
     eng = P.Engine(model)
     try:
         eng.set_loss_grad_kernel(_lib.KERNEL_TC, 0)
-        with pytest.raises(_lib.PmfError):
-            eng.loss_grad(include_reg=False)
+        got = eng.loss_grad(include_reg=True)
+        eng.set_loss_grad_kernel(_lib.KERNEL_FFMA, 0)
+        ffma = eng.loss_grad(include_reg=True)
     finally:
         eng.close()
+    ref = O.total_loss_grads(om, D)
+    assert abs(got["loss"] - ref["loss"]) <= 1e-5 * abs(ref["loss"])
+    assert relerr(got["dmu"], ref["dmu"]) < 1e-4 and relerr(got["dlogsigma"], ref["dlogsigma"]) < 1e-4
+    assert relerr(got["dY"], ref["dY"]) < 2e-4 and relerr(got["dX"], ref["dX"]) < 2e-4
+    for v in range(len(om.logdelta.values)):
+        assert relerr(got["dtheta"][v], ref["dtheta"][v]) < 1e-4, (v, relerr(got["dtheta"][v], ref["dtheta"][v]))
+        assert relerr(got["dlogdelta"][v], ref["dlogdelta"][v]) < 1e-4, (v, relerr(got["dlogdelta"][v], ref["dlogdelta"][v]))
+        assert relerr(ffma["dtheta"][v], ref["dtheta"][v]) < 1e-5
+
+
+def test_tc_batch_layers_fit_curve():
+    """C3 in miniature through mf_fit with the AUTO kernel (tcgen05 path: M >= 1024, M*N >= 4e6); batch ids are
+    iid per sample and view, so every view gets its own sample order and boundary tiles run two passes.
+    AdaGrad's first steps are sign-like, which amplifies the TF32 rounding of small gradients: 3e-3 on the
+    batch parameters after 6 epochs."""
+    views = {"mutation": ("bernoulli", 600), "methylation": ("normal", 1400), "mrnaseq": ("normal", 1300),
+             "counts": ("poisson", 800)}
+    model, om, D = make_pair(1100, views, K=16, seed=73, batch_views=["methylation", "mrnaseq", "counts"],
+                             n_batches=6, n_conditions=4, missing=0.3, lambda_X_l2=1.0)
+    href = O.mf_fit(om, D, O.AdaGrad(0.1), max_epochs=6, update_X=True, update_Y=True, update_col_layers=True,
+                    rel_tol=0, abs_tol=0)
+    h = P.mf_fit(model, lr=0.1, max_epochs=6, update_X=True, update_Y=True, update_col_layers=True, rel_tol=0,
+                 abs_tol=0, verbosity=0)
+    assert h["epochs"] == href["epochs"]
+    assert np.max(np.abs(np.array(h["loss"]) / np.array(href["loss"]) - 1)) < 1e-4
+    layers = model.matfac.col_transform.layers
+    for v in range(len(om.theta.values)):
+        assert relerr(layers[3].theta.values[v], om.theta.values[v]) < 3e-3
+        assert relerr(layers[1].logdelta.values[v], om.logdelta.values[v]) < 3e-3
 
 
 def test_staging_statistics_passes():
