@@ -855,23 +855,22 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
                     }
                 }
             };
-            // four positions that lie in several batches (a batch boundary): entry by entry through the generic
-            // noise evaluation, switching segments as the batch id changes
+            // four positions that lie in several batches (a batch boundary): entry by entry, switching segments as
+            // the batch id changes
             auto epi_mixed4 = [&](auto off_c, uint32_t (&z)[16], const float (&a)[16], int i_first) {
                 constexpr int OFF = decltype(off_c)::value;
-#pragma unroll
-                for (int e = OFF; e < OFF + 4; ++e) {
-                    if (i_first + e < dp.M) {
-                        const uint32_t b_ = __ldg(bos_row + i_first + e);
+                auto one = [&](auto e_c) {
+                    constexpr int E = decltype(e_c)::value;
+                    if (i_first + E < dp.M) {
+                        const uint32_t b_ = __ldg(bos_row + i_first + E);
                         if (b_ != cur_b) enter_segment(b_);
                     }
-                    const float zr = __uint_as_float(z[e]);
-                    float2 lg = noise_eval_slow(dist, fmaf(zr, sd, mt), a[e], th_range, dp.ordinal_eps, dp.hinge_margin);
-                    loss_acc = fmaf(2.f, lg.x, loss_acc);
-                    seg_g += lg.y;
-                    seg_gz = fmaf(lg.y, zr, seg_gz);
-                    z[e] = rn_bits(lg.y * dl);
-                }
+                    epi(std::integral_constant<int, 1>{}, e_c, z, a);
+                };
+                one(std::integral_constant<int, OFF>{});
+                one(std::integral_constant<int, OFF + 1>{});
+                one(std::integral_constant<int, OFF + 2>{});
+                one(std::integral_constant<int, OFF + 3>{});
             };
             using std::integral_constant;
 

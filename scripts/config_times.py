@@ -43,9 +43,9 @@ def build(name, rng):
     if name == "P25":
         return simulate_problem(10000, blocks=C2_BLOCKS, K=25, seed=2, missing=0.3, model_kwargs=dict(lambda_X_l2=1.0)), \
             "C2 shape at the reference's production latent dimension K=25 (fit_matfac.jl:150)"
-    if name in ("C3", "C3s"):
+    if name in ("C3", "C3s", "C3b1"):
         views = [b[0] for b in C2_BLOCKS]
-        return simulate_problem(10000, blocks=C2_BLOCKS, K=64, seed=3, missing=0.3, batch_views=views, n_batches=40,
+        return simulate_problem(10000, blocks=C2_BLOCKS, K=64, seed=3, missing=0.3, batch_views=views, n_batches=1 if name == "C3b1" else 40,
                                 n_conditions=20, sort_batches=name == "C3s"), \
             "C2 + 40 batches x 4 views of shift/scale + 20 sample conditions (group reg on X)" + \
             ("; samples listed batch by batch" if name == "C3s" else "; batch ids iid per sample and view")

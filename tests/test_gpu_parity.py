@@ -463,6 +463,28 @@ def test_tc_batch_layers(sort_batches):
         assert relerr(ffma["dtheta"][v], ref["dtheta"][v]) < 1e-5
 
 
+def test_tc_batch_plan_follows_new_data():
+    """The permuted copy of A behind the batch path is rebuilt when the data are replaced on a live handle."""
+    views = {"methylation": ("normal", 300), "mrnaseq": ("normal", 200)}
+    model, om, D = make_pair(1100, views, K=16, seed=74, batch_views=["methylation", "mrnaseq"], n_batches=5, missing=0.2)
+    eng = P.Engine(model)
+    try:
+        eng.set_loss_grad_kernel(_lib.KERNEL_TC, 0)
+        first = eng.loss_grad(include_reg=False)
+        D2 = D.copy()
+        D2[:, :300] += 0.5
+        eng.push_data(np.asfortranarray(D2.astype(np.float32)))
+        got = eng.loss_grad(include_reg=False)
+    finally:
+        eng.close()
+    ref = O.data_loss_grads(om, D2)
+    assert abs(first["loss"] - O.data_loss_grads(om, D)["loss"]) <= 1e-5 * abs(first["loss"])
+    assert abs(got["loss"] - ref["loss"]) <= 1e-5 * abs(ref["loss"])
+    assert relerr(got["dmu"], ref["dmu"]) < 1e-4
+    for v in range(2):
+        assert relerr(got["dtheta"][v], ref["dtheta"][v]) < 1e-4
+
+
 def test_tc_batch_layers_fit_curve():
     """C3 in miniature through mf_fit with the AUTO kernel (tcgen05 path: M >= 1024, M*N >= 4e6); batch ids are
     iid per sample and view, so every view gets its own sample order and boundary tiles run two passes.
