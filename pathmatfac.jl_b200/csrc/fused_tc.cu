@@ -38,8 +38,6 @@
 #include <stdio.h>
 #include <stdlib.h>
 
-#include <type_traits>
-
 #include "pmf_epilogue.cuh"
 #include "pmf_internal.h"
 
@@ -276,11 +274,10 @@ struct TcParams {
     const int32_t* pass_feat0;   // [n_jt] first feature of the pass' tile
     const int32_t* pass_order;   // [n_jt] sample order of the pass
     const int32_t* view_order;   // [n_views] sample order in which the view's batches are contiguous
-    const uint16_t* boq;         // [n_orders][n_views][Mp/4] batch of 4 consecutive positions, 0xFFFF = mixed
-    const uint16_t* bos;         // [n_orders][n_views][Mp]   batch of a position
+    const uint16_t* boc;         // [n_views][Mp/16] batch of the 16 positions of a chunk, in the view's own order
     int n_views, n_orders;
 };
-constexpr uint32_t B_MIXED = 0xFFFFu, B_NONE = 0xFFFEu;
+constexpr uint32_t B_NONE = 0xFFFFu;
 constexpr int TRACE_TILES = 96, TRACE_EV = 32, TRACE_CTAS = 160;   // + per-CTA (start, end) clocks after the stamps
 
 // Work distribution.  The tiles, flattened feature-tile-major ([jt][it]), are cut into gridDim.x equal
@@ -722,15 +719,13 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
             const float gscale = sigma * wj;
             float dmu_acc = 0.f, loss_acc = 0.f;   // unweighted sums over this item (<= a few thousand terms)
             // Batch layers (src/layers.jl:221-253, src/batch_array.jl:132-212): z4 = z sigma_j delta_bj + mu_j + theta_bj.
-            // The samples of a chunk are the same for every thread of the warp and, in the sample order of this
-            // pass, nearly always share one batch (boq), so the batch parameters are per-thread registers that
-            // change at SEGMENT boundaries only; a segment's sums  sum g  and  sum g z  give dtheta,
-            // dlogdelta = sigma delta sum g z, and its share of dmu and dlogsigma (sum g delta).  delta is folded
-            // into the dloss/dz entries.
+            // The 16 samples of a chunk are the same for every thread of the warp and, in the sample order of the
+            // column's view, ALWAYS lie in one batch (boc; the orders pad every batch to a multiple of 16
+            // positions).  The batch parameters are therefore per-thread registers that change at SEGMENT
+            // boundaries only; a segment's sums  sum g  and  sum g z  give dtheta, dlogdelta = sigma delta sum g z,
+            // and its share of dmu and dlogsigma (sum g delta).  delta is folded into the dloss/dz entries.
             const int boff = BATCH ? cur.boff : -1;
-            const size_t brow = BATCH ? (size_t)__ldg(p.pass_order + jt) * p.n_views + cur.bview : 0;
-            const uint16_t* const bos_row = BATCH ? p.bos + brow * dp.Mp : nullptr;
-            const uint16_t* const boq_row = BATCH ? p.boq + brow * (dp.Mp >> 2) : nullptr;
+            const uint16_t* const boc_row = BATCH ? p.boc + (size_t)cur.bview * (dp.Mp >> 4) : nullptr;
             uint32_t cur_b = B_NONE;               // no batch parameters in force
             float sd = sigma, mt = muj, dl = 1.f;  // sigma_j delta_bj, mu_j + theta_bj, delta_bj
             float seg_g = 0.f, seg_gz = 0.f, dls_acc = 0.f;
@@ -747,6 +742,21 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
                 dls_acc = fmaf(seg_g, dl, dls_acc);
                 seg_g = seg_gz = 0.f;
             };
+            // batches of this thread's two 16-sample chunks of tile it_ (16 bits each) and the parameters of the first
+            // one that differs from the batch in force: fetched a whole tile ahead, off the critical path
+            uint32_t ids = B_NONE * 0x10001u;
+            auto fetch_ids = [&](int it_) {
+                ids = __ldg(reinterpret_cast<const uint32_t*>(boc_row + ((it_ * BI + 32 * h32) >> 4)));
+                pre_b = (ids & 0xffffu) != cur_b ? (ids & 0xffffu) : (ids >> 16);
+                if (pre_b != cur_b) {
+                    pre_ld = __ldg(dp.logdelta + boff + (int)pre_b);
+                    pre_th = __ldg(dp.theta + boff + (int)pre_b);
+                }
+            };
+            if (BATCH && boff >= 0) {
+                const int it_first = it0 + (int)((g ^ (uint32_t)grp) & 1u);     // this group's first tile of the item
+                if (it_first < it1) fetch_ids(it_first);
+            }
             auto enter_segment = [&](uint32_t b_) {
                 close_segment();
                 cur_b = b_;
@@ -796,9 +806,8 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
             }
 
             // per-entry math on 16 consecutive samples: z[] (TMEM columns) in, dloss/dz (TF32-rounded bits) out
-            // entries [OFF, OFF + CNT) of a 16-sample chunk
-            auto epi = [&](auto cnt_c, auto off_c, uint32_t (&z)[16], const float (&a)[16]) {
-                constexpr int CNT = decltype(cnt_c)::value, OFF = decltype(off_c)::value;
+            // per-entry math on 16 consecutive samples: z[] (TMEM columns) in, dloss/dz (TF32-rounded bits) out
+            auto epi16 = [&](uint32_t (&z)[16], const float (&a)[16]) {
                 // dmu_acc / loss_acc collect the unweighted sums; the column weight w_j (a per-thread
                 // constant) is applied at the item flush.
                 auto tally = [&](float gv, uint32_t zraw) -> uint32_t {
@@ -812,7 +821,7 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
                 };
                 if (dist == DIST_NORMAL) {
 #pragma unroll
-                    for (int e = OFF; e < OFF + CNT; ++e) {
+                    for (int e = 0; e < 16; ++e) {
                         float d = fmaf(__uint_as_float(z[e]), sd, mt) - a[e];
                         d = fabsf(a[e]) < INFINITY ? d : 0.f;        // NaN / Inf => missing (ordered compare)
                         loss_acc = fmaf(d, d, loss_acc);              // (z-a)^2, halved and weighted at flush
@@ -822,7 +831,7 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
                     // softplus(z) - a z ; sigmoid(z) - a, sharing e = exp(-|z|); a missing entry makes both NaN
                     // and is masked away once at the end
 #pragma unroll
-                    for (int e = OFF; e < OFF + CNT; ++e) {
+                    for (int e = 0; e < 16; ++e) {
                         const uint32_t m = obs_mask(a[e]);
                         float z4 = fmaf(__uint_as_float(z[e]), sd, mt);
                         float ex = ex2_fast(fabsf(z4) * -1.4426950408889634f);
@@ -836,7 +845,7 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
                     }
                 } else if (dist == DIST_POISSON) {
 #pragma unroll
-                    for (int e = OFF; e < OFF + CNT; ++e) {
+                    for (int e = 0; e < 16; ++e) {
                         const uint32_t m = obs_mask(a[e]);
                         float z4 = fmaf(__uint_as_float(z[e]), sd, mt);
                         float ez = ex2_fast(z4 * 1.4426950408889634f);
@@ -847,7 +856,7 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
                     }
                 } else {
 #pragma unroll
-                    for (int e = OFF; e < OFF + CNT; ++e) {
+                    for (int e = 0; e < 16; ++e) {
                         float z4 = fmaf(__uint_as_float(z[e]), sd, mt);
                         float2 lg = noise_eval_slow(dist, z4, a[e], th_range, dp.ordinal_eps, dp.hinge_margin);
                         loss_acc = fmaf(2.f, lg.x, loss_acc);        // keep the common 1/2 factor at flush
@@ -855,46 +864,12 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
                     }
                 }
             };
-            // four positions that lie in several batches (a batch boundary): entry by entry, switching segments as
-            // the batch id changes
-            auto epi_mixed4 = [&](auto off_c, uint32_t (&z)[16], const float (&a)[16], int i_first) {
-                constexpr int OFF = decltype(off_c)::value;
-                auto one = [&](auto e_c) {
-                    constexpr int E = decltype(e_c)::value;
-                    if (i_first + E < dp.M) {
-                        const uint32_t b_ = __ldg(bos_row + i_first + E);
-                        if (b_ != cur_b) enter_segment(b_);
-                    }
-                    epi(std::integral_constant<int, 1>{}, e_c, z, a);
-                };
-                one(std::integral_constant<int, OFF>{});
-                one(std::integral_constant<int, OFF + 1>{});
-                one(std::integral_constant<int, OFF + 2>{});
-                one(std::integral_constant<int, OFF + 3>{});
-            };
-            using std::integral_constant;
+
 
             for (int it = it0; it < it1; ++it, ++g) {
                 if ((g & 1u) != (uint32_t)grp) continue;             // the other group's tile
                 const bool tr = quarter == 0 && h32 == 0 && lane == 0;
                 if (tr) stamp(g, 5);
-                // batches of this thread's eight 4-position groups (16 bits each); the parameters of the first
-                // batch that differs from the one in force are fetched before the waits below
-                uint4 qw = make_uint4(B_NONE * 0x10001u, B_NONE * 0x10001u, B_NONE * 0x10001u, B_NONE * 0x10001u);
-                if (BATCH && boff >= 0) {
-                    qw = __ldg(reinterpret_cast<const uint4*>(boq_row + ((it * BI + 32 * h32) >> 2)));
-                    pre_b = cur_b;
-                    const uint32_t w[4] = {qw.x, qw.y, qw.z, qw.w};
-#pragma unroll
-                    for (int k = 7; k >= 0; --k) {
-                        const uint32_t id = (w[k >> 1] >> (16 * (k & 1))) & 0xffffu;
-                        if (id != cur_b && id != B_MIXED) pre_b = id;
-                    }
-                    if (pre_b != cur_b) {
-                        pre_ld = __ldg(dp.logdelta + boff + (int)pre_b);
-                        pre_th = __ldg(dp.theta + boff + (int)pre_b);
-                    }
-                }
                 mbar_wait(bar(B_Z_FULL + rz.s), rz.ph);
                 if (tr) stamp(g, 6);
                 mbar_wait(bar(B_FULL_A + ra.s), ra.ph);
@@ -924,27 +899,10 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
                     }
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                     if (BATCH) {
-                        const uint32_t w0 = hh == 0 ? qw.x : qw.z, w1 = hh == 0 ? qw.y : qw.w;
-                        const uint32_t id0 = w0 & 0xffffu;
-                        if (w0 == w1 && (w0 >> 16) == id0 && id0 != B_MIXED) {
-                            if (id0 != cur_b) enter_segment(id0);
-                            epi(integral_constant<int, 16>{}, integral_constant<int, 0>{}, z, a);
-                        } else {
-                            const int i_first = it * BI + 32 * h32 + 16 * hh;
-                            auto quad = [&](auto off_c, uint32_t id) {
-                                if (id == B_MIXED) {
-                                    epi_mixed4(off_c, z, a, i_first);
-                                } else {
-                                    if (id != cur_b) enter_segment(id);
-                                    epi(integral_constant<int, 4>{}, off_c, z, a);
-                                }
-                            };
-                            quad(integral_constant<int, 0>{}, w0 & 0xffffu);
-                            quad(integral_constant<int, 4>{}, w0 >> 16);
-                            quad(integral_constant<int, 8>{}, w1 & 0xffffu);
-                            quad(integral_constant<int, 12>{}, w1 >> 16);
-                        }
-                    } else if (!(DBG && p.ablate & 8)) epi(integral_constant<int, 16>{}, integral_constant<int, 0>{}, z, a);
+                        const uint32_t id = hh == 0 ? (ids & 0xffffu) : (ids >> 16);
+                        if (id != cur_b) enter_segment(id);
+                    }
+                    if (!(DBG && p.ablate & 8)) epi16(z, a);
                     // dloss/dz back to TMEM in place of Z (A operand of MMA3) and over the A values this thread
                     // read (MN-major A operand of MMA2): same addresses, 128-bit stores, no transposition
                     TMEM_ST16(zt + 16 * hh, z);
@@ -962,6 +920,7 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
                 fence_async_smem();
                 mbar_arrive(bar(B_G_READY + rz.s));
                 store_segment();
+                if (BATCH && boff >= 0 && it + 2 < it1) fetch_ids(it + 2);
                 if (tr) stamp(g, 9);
                 ra.next(SA); ra.next(SA);
                 rz.next(SZ); rz.next(SZ);
@@ -1042,7 +1001,13 @@ __global__ void prep_operands_kernel(const float4* __restrict__ X, float4* __res
     if (stop_flag != nullptr && *stop_flag != 0) return;
     const size_t n4 = (size_t)rows * K4;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
-        const float4 v = perm ? X[(size_t)perm[i / K4] * K4 + (i - (i / K4) * K4)] : X[i];
+        float4 v;
+        if (perm) {
+            const int src = perm[i / K4];            // -1: padding position of the order
+            v = src >= 0 ? X[(size_t)src * K4 + (i - (i / K4) * K4)] : make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+            v = X[i];
+        }
         float4 h;
         h.x = __uint_as_float(rna_tf32(v.x)); h.y = __uint_as_float(rna_tf32(v.y));
         h.z = __uint_as_float(rna_tf32(v.z)); h.w = __uint_as_float(rna_tf32(v.w));
@@ -1055,14 +1020,14 @@ __global__ void prep_operands_kernel(const float4* __restrict__ X, float4* __res
 
 // dX[i] = sum over the sample orders of the copy's row for sample i; the copies are left zeroed for the next pass
 __global__ void combine_dx_kernel(float4* __restrict__ dXo, const int32_t* __restrict__ pos, float4* __restrict__ dX,
-                                  int n_orders, int Mp, int K4, const int* stop_flag) {
+                                  int n_orders, int M, int n_pos, int K4, const int* stop_flag) {
     if (stop_flag != nullptr && *stop_flag != 0) return;
-    const size_t n4 = (size_t)Mp * K4;
+    const size_t n4 = (size_t)M * K4;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n4; idx += (size_t)gridDim.x * blockDim.x) {
         const int i = (int)(idx / K4), c = (int)(idx - (size_t)i * K4);
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int o = 0; o < n_orders; ++o) {
-            float4* src = dXo + ((size_t)o * Mp + pos[(size_t)o * Mp + i]) * K4 + c;
+            float4* src = dXo + ((size_t)o * n_pos + pos[(size_t)o * M + i]) * K4 + c;
             const float4 v = *src;
             acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
             *src = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1073,7 +1038,7 @@ __global__ void combine_dx_kernel(float4* __restrict__ dXo, const int32_t* __res
 
 // One row of A_tc per block: the pass' feature row with its samples in the pass' order, or NaN when the
 // column belongs to another pass of the same tile
-__global__ void build_a_tc_kernel(const float* __restrict__ A, float* __restrict__ A_tc, int N, int lda, int Mp,
+__global__ void build_a_tc_kernel(const float* __restrict__ A, float* __restrict__ A_tc, int N, int lda, int n_pos,
                                   const int32_t* __restrict__ pass_feat0, const int32_t* __restrict__ pass_order,
                                   const int32_t* __restrict__ view_order, const int32_t* __restrict__ bcol_view,
                                   const int32_t* __restrict__ perm) {
@@ -1085,10 +1050,13 @@ __global__ void build_a_tc_kernel(const float* __restrict__ A, float* __restrict
         const int bv = bcol_view[j];
         active = bv >= 0 ? view_order[bv] == o : (ps == 0 || pass_feat0[ps - 1] != pass_feat0[ps]);
     }
-    float* dst = A_tc + (size_t)r * lda;
+    float* dst = A_tc + (size_t)r * n_pos;
     const float* src = A + (size_t)(active ? j : 0) * lda;
-    const int32_t* pr = perm + (size_t)o * Mp;
-    for (int p = threadIdx.x; p < lda; p += blockDim.x) dst[p] = active ? src[pr[p]] : __int_as_float(0x7fc00000);
+    const int32_t* pr = perm + (size_t)o * n_pos;
+    for (int p = threadIdx.x; p < n_pos; p += blockDim.x) {
+        const int i = pr[p];
+        dst[p] = active && i >= 0 ? src[i] : __int_as_float(0x7fc00000);
+    }
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -1144,7 +1112,7 @@ bool tc_supported(const DataPassParams& p) {
 }
 
 cudaError_t launch_build_a_tc(const DataPassParams& dp, const TcBatchDev& bp, float* A_tc, cudaStream_t s) {
-    build_a_tc_kernel<<<bp.n_pass * 128, 256, 0, s>>>(dp.A, A_tc, dp.N, dp.lda, dp.Mp, bp.pass_feat0, bp.pass_order,
+    build_a_tc_kernel<<<bp.n_pass * 128, 256, 0, s>>>(dp.A, A_tc, dp.N, dp.lda, bp.n_pos, bp.pass_feat0, bp.pass_order,
                                                       bp.view_order, dp.bcol_view, bp.perm);
     return cudaGetLastError();
 }
@@ -1158,11 +1126,15 @@ cudaError_t launch_data_pass_tc(const DataPassParams& dp_in, float* Xh, float* X
     int launched = 0;
     const bool permuted = bp != nullptr && !bp->direct;
     int x_rows = dp.Mp;
+    const int M_real = dp.M;
     if (permuted) {
-        // per-order copies: operands gathered from the current X on every pass, dX gathered back afterwards
+        // per-order copies: operands gathered from the current X on every pass, dX gathered back afterwards.
+        // The kernel sees a problem of n_pos sample POSITIONS (batches padded to multiples of 16).
         Xh = bp->Xh; Xl = bp->Xb;
-        x_rows = bp->n_orders * dp.Mp;
+        x_rows = bp->n_orders * bp->n_pos;
         refresh_split = true;
+        dp.Mp = dp.lda = bp->n_pos;
+        dp.M = bp->n_used;
     }
     if (refresh_split) {   // otherwise the previous epoch's update pass wrote Xh / Xl together with X
         const size_t n4 = (size_t)x_rows * dp.Kp / 4;
@@ -1190,7 +1162,7 @@ cudaError_t launch_data_pass_tc(const DataPassParams& dp_in, float* Xh, float* X
     p.n_jt = n_pass;
     p.n_it = (dp.M + BI - 1) / BI;
     p.pass_feat0 = bp ? bp->pass_feat0 : nullptr; p.pass_order = bp ? bp->pass_order : nullptr;
-    p.view_order = bp ? bp->view_order : nullptr; p.boq = bp ? bp->boq : nullptr; p.bos = bp ? bp->bos : nullptr;
+    p.view_order = bp ? bp->view_order : nullptr; p.boc = bp ? bp->boc : nullptr;
     p.n_views = bp ? bp->n_views : 0; p.n_orders = bp ? bp->n_orders : 1;
     p.z_passes = precision >= 2 ? 1 : 3;
     {
@@ -1220,10 +1192,10 @@ cudaError_t launch_data_pass_tc(const DataPassParams& dp_in, float* Xh, float* X
     kern<<<grid, NTHREADS, SMEM_TOTAL, s>>>(tmXh, tmXl, tmXm, tmA, tmDX, p);
     ++launched;
     if (permuted) {
-        const size_t n4 = (size_t)dp.Mp * dp.Kp / 4;
+        const size_t n4 = (size_t)M_real * dp.Kp / 4;
         combine_dx_kernel<<<(unsigned)((n4 + 255) / 256 < 1184 ? (n4 + 255) / 256 : 1184), 256, 0, s>>>(
-            reinterpret_cast<float4*>(bp->dX), bp->pos, reinterpret_cast<float4*>(dp.dX), bp->n_orders, dp.Mp, dp.Kp / 4,
-            dp.stop_flag);
+            reinterpret_cast<float4*>(bp->dX), bp->pos, reinterpret_cast<float4*>(dp_in.dX), bp->n_orders, M_real, bp->n_pos,
+            dp.Kp / 4, dp.stop_flag);
         ++launched;
     }
     if (n_launches) *n_launches = launched;

@@ -1059,26 +1059,27 @@ int pmf_model_s::build_tc_plan() {
     for (const BatchView& bv : views)
         if (bv.n_batches > 65533) return fail(this, PMF_ERR_ARG, "tcgen05 data pass: more than 65533 batches in a view");
 
-    // 1. sample orders.  A view keeps the identity order when its batches are (nearly) contiguous as given;
-    //    otherwise its samples are stably sorted by batch id.  Equal permutations are shared.
-    std::vector<std::vector<int32_t>> perms(1, std::vector<int32_t>(Mp));
-    for (int p = 0; p < Mp; ++p) perms[0][p] = p;
+    // 1. sample orders (position -> sample, -1 = padding).  A view keeps the identity order when every 16-sample
+    //    chunk lies in one batch as given; otherwise its samples are stably sorted by batch id and every batch is
+    //    padded to a multiple of 16 positions.  Equal orders are shared between views.
+    std::vector<std::vector<int32_t>> perms(1, std::vector<int32_t>(M));
+    for (int p = 0; p < M; ++p) perms[0][p] = p;
     std::vector<int32_t> view_order(V, 0);
-    auto mixed_quads = [&](const int32_t* b, const std::vector<int32_t>& perm) {
-        int n = 0;
-        for (int q = 0; 4 * q < M; ++q) {
-            const int hi = std::min(4 * q + 4, M);
-            for (int p = 4 * q + 1; p < hi; ++p)
-                if (b[perm[p]] != b[perm[4 * q]]) { ++n; break; }
-        }
-        return n;
-    };
     for (int v = 0; v < V; ++v) {
         const int32_t* b = bos_host.data() + (size_t)v * M;
-        if (mixed_quads(b, perms[0]) <= 2 * views[v].n_batches + 2) continue;
-        std::vector<int32_t> perm(Mp);
-        for (int p = 0; p < Mp; ++p) perm[p] = p;
-        std::stable_sort(perm.begin(), perm.begin() + M, [&](int32_t x, int32_t y) { return b[x] < b[y]; });
+        bool uniform = true;
+        for (int p = 1; p < M && uniform; ++p) uniform = (p & 15) == 0 || b[p] == b[p - 1];
+        if (uniform) continue;
+        std::vector<int32_t> idx(M);
+        for (int p = 0; p < M; ++p) idx[p] = p;
+        std::stable_sort(idx.begin(), idx.end(), [&](int32_t x, int32_t y) { return b[x] < b[y]; });
+        std::vector<int32_t> perm;
+        perm.reserve((size_t)M + 16 * (size_t)views[v].n_batches);
+        for (int k = 0; k < M; ++k) {
+            if (k > 0 && b[idx[k]] != b[idx[k - 1]])
+                while (perm.size() & 15) perm.push_back(-1);
+            perm.push_back(idx[k]);
+        }
         int o = -1;
         for (int k = 1; k < (int)perms.size(); ++k)
             if (perms[k] == perm) { o = k; break; }
@@ -1086,6 +1087,10 @@ int pmf_model_s::build_tc_plan() {
         view_order[v] = o;
     }
     const int n_orders = (int)perms.size();
+    size_t n_used = 0;
+    for (const auto& pm : perms) n_used = std::max(n_used, pm.size());
+    const int n_pos = n_orders == 1 ? Mp : round_up((int)n_used, 128);
+    for (auto& pm : perms) pm.resize(n_pos, -1);
 
     // 2. passes: every feature tile once per order its batched columns need (columns without batch layers
     //    ride with the tile's first pass)
@@ -1105,22 +1110,19 @@ int pmf_model_s::build_tc_plan() {
     }
     const int n_pass = (int)pass_feat0.size();
 
-    // 3. batch of every position / 4-position group, per (order, view)
-    const int Mq = Mp / 4;
-    std::vector<uint16_t> bos16((size_t)n_orders * V * Mp), boq((size_t)n_orders * V * Mq);
-    for (int o = 0; o < n_orders; ++o)
-        for (int v = 0; v < V; ++v) {
-            const int32_t* b = bos_host.data() + (size_t)v * M;
-            uint16_t* row = bos16.data() + ((size_t)o * V + v) * Mp;
-            uint16_t* qrow = boq.data() + ((size_t)o * V + v) * Mq;
-            for (int p = 0; p < Mp; ++p) row[p] = (uint16_t)b[perms[o][std::min(p, M - 1)]];   // padding continues the last batch
-            for (int q = 0; q < Mq; ++q) {
-                uint16_t x = row[4 * q];
-                for (int p = 4 * q + 1; p < 4 * q + 4; ++p)
-                    if (row[p] != x) { x = 0xFFFFu; break; }
-                qrow[q] = x;
-            }
+    // 3. batch of every 16-position chunk of a view, in the view's order (a chunk of padding only continues
+    //    the batch before it, so that it never triggers a switch)
+    const int n_chunks = n_pos / 16;
+    std::vector<uint16_t> boc((size_t)V * n_chunks);
+    for (int v = 0; v < V; ++v) {
+        const int32_t* b = bos_host.data() + (size_t)v * M;
+        const std::vector<int32_t>& pm = perms[view_order[v]];
+        uint16_t last = 0;
+        for (int c = 0; c < n_chunks; ++c) {
+            if (pm[16 * c] >= 0) last = (uint16_t)b[pm[16 * c]];      // a chunk's first position is never padding unless all are
+            boc[(size_t)v * n_chunks + c] = last;
         }
+    }
 
     auto upload = [&](const void* src, size_t bytes, const void** dst) -> bool {
         void* d = nullptr;
@@ -1132,26 +1134,26 @@ int pmf_model_s::build_tc_plan() {
     };
     pmf::TcBatchDev& t = tcb;
     t.n_orders = n_orders; t.n_pass = n_pass; t.n_views = V;
+    t.n_pos = n_pos; t.n_used = n_orders == 1 ? M : (int)n_used;
     t.direct = n_orders == 1;
     bool ok = upload(pass_feat0.data(), (size_t)n_pass * 4, (const void**)&t.pass_feat0) &&
               upload(pass_order.data(), (size_t)n_pass * 4, (const void**)&t.pass_order) &&
               upload(view_order.data(), (size_t)V * 4, (const void**)&t.view_order) &&
               upload(cost_cum.data(), ((size_t)n_pass + 1) * 4, (const void**)&t.cost_cum) &&
-              upload(boq.data(), boq.size() * 2, (const void**)&t.boq) &&
-              upload(bos16.data(), bos16.size() * 2, (const void**)&t.bos);
+              upload(boc.data(), boc.size() * 2, (const void**)&t.boc);
     if (ok && !t.direct) {
-        std::vector<int32_t> perm_flat((size_t)n_orders * Mp), pos_flat((size_t)n_orders * Mp);
+        std::vector<int32_t> perm_flat((size_t)n_orders * n_pos), pos_flat((size_t)n_orders * M);
         for (int o = 0; o < n_orders; ++o)
-            for (int p = 0; p < Mp; ++p) {
-                perm_flat[(size_t)o * Mp + p] = perms[o][p];
-                pos_flat[(size_t)o * Mp + perms[o][p]] = p;
+            for (int p = 0; p < n_pos; ++p) {
+                perm_flat[(size_t)o * n_pos + p] = perms[o][p];
+                if (perms[o][p] >= 0) pos_flat[(size_t)o * M + perms[o][p]] = p;
             }
-        const size_t rows = (size_t)n_orders * Mp;
+        const size_t rows = (size_t)n_orders * n_pos;
         ok = upload(perm_flat.data(), perm_flat.size() * 4, (const void**)&t.perm) &&
              upload(pos_flat.data(), pos_flat.size() * 4, (const void**)&t.pos) &&
              upload(nullptr, rows * 64 * 4, (const void**)&t.Xh) && upload(nullptr, rows * 64 * 4, (const void**)&t.Xb) &&
              upload(nullptr, rows * Kp * 4, (const void**)&t.dX) &&
-             upload(nullptr, (size_t)n_pass * 128 * lda * 4, (const void**)&t.A_tc);
+             upload(nullptr, (size_t)n_pass * 128 * n_pos * 4, (const void**)&t.A_tc);
         if (ok) {
             // operand scratch is 64 / 128 wide and zero beyond Kp; the dX copies start (and are left) clean
             ok = cudaMemsetAsync(t.Xh, 0, rows * 64 * 4, stream) == cudaSuccess &&

@@ -147,28 +147,31 @@ cudaError_t launch_data_pass_ffma(const DataPassParams& p, cudaStream_t s, int n
 // launcher when `refresh_split`).  precision: 0/1 = TF32 + BF16 first-order corrections for Z and TF32
 // gradients, 2 = TF32 everywhere.
 //
-// Batch layers: the epilogue keeps the parameters of ONE batch per thread (column) in registers, so it wants
-// the samples of a batch next to each other.  Views whose batch ids are scattered get their own SAMPLE ORDER
-// (a stable sort by batch id); order 0 is the identity.  A PASS is a (128-feature tile, order) pair: a tile
-// whose columns need several orders is walked once per order, over a copy of A (A_tc) whose rows are permuted
-// to the pass' order and NaN for the columns another pass serves.  Per order there is a copy of the X
-// operands and of the dX accumulator; after the data pass the dX copies are gathered back (combine kernel).
-// When every view is already contiguous (`direct`) there is one order and none of the copies exist.
+// Batch layers: the epilogue keeps the parameters of ONE batch per thread (column) in registers and switches
+// them between 16-sample chunks, so it wants every chunk to lie in one batch.  A view whose batch ids do not
+// come that way gets its own SAMPLE ORDER: samples stably sorted by batch id, every batch padded to a multiple
+// of 16 positions (padding positions hold no sample: A is NaN there).  Order 0 is the identity.  A PASS is a
+// (128-feature tile, order) pair: a tile whose columns need several orders is walked once per order, over a
+// copy of A (A_tc) whose rows are laid out in the pass' order and are NaN for the columns another pass serves.
+// Per order there is a copy of the X operands and of the dX accumulator; after the data pass the dX copies are
+// gathered back (combine kernel).  When every view is chunk-uniform as given (`direct`) there is one order and
+// none of the copies exist.
 struct TcBatchDev {
     int n_orders, n_pass, n_views;
+    int n_pos;                    // sample positions per order (multiple of 128; = Mp when direct)
+    int n_used;                   // positions in use: max over the orders (= M when direct)
     bool direct;
-    const float* A_tc;            // [n_pass * 128][lda]                       (null when direct)
-    const int32_t* perm;          // [n_orders][Mp] position -> sample         (null when direct)
-    const int32_t* pos;           // [n_orders][Mp] sample -> position         (null when direct)
-    float* Xh;                    // [n_orders * Mp][64]                       (null when direct)
-    float* Xb;                    // [n_orders * Mp][128] BF16                 (null when direct)
-    float* dX;                    // [n_orders * Mp][Kp], zero between passes  (null when direct)
+    const float* A_tc;            // [n_pass * 128][n_pos]                     (null when direct)
+    const int32_t* perm;          // [n_orders][n_pos] position -> sample, -1  (null when direct)
+    const int32_t* pos;           // [n_orders][M]     sample -> position      (null when direct)
+    float* Xh;                    // [n_orders * n_pos][64]                    (null when direct)
+    float* Xb;                    // [n_orders * n_pos][128] BF16              (null when direct)
+    float* dX;                    // [n_orders * n_pos][Kp], zero between passes (null when direct)
     const int32_t* pass_feat0;    // [n_pass]
     const int32_t* pass_order;    // [n_pass]
     const int32_t* view_order;    // [n_views]
     const int32_t* cost_cum;      // [n_pass + 1]
-    const uint16_t* boq;          // [n_orders][n_views][Mp/4]
-    const uint16_t* bos;          // [n_orders][n_views][Mp]
+    const uint16_t* boc;          // [n_views][n_pos/16] batch of a chunk in the view's order
 };
 bool tc_supported(const DataPassParams& p);
 // `bp`: null for a model without batch layers.  *n_launches receives the number of kernels launched.
