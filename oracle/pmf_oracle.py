@@ -1037,6 +1037,27 @@ def column_ssq_grads(m: OracleModel, D: np.ndarray) -> np.ndarray:
     return out
 
 
+def compute_M_estimates(m: OracleModel, D: np.ndarray, lr=0.1, max_epochs=500, rel_tol=1e-5, abs_tol=1e-3):
+    """``MF.compute_M_estimates`` as ``init_mu!`` calls it (src/fit.jl:82-104) [EXTERNAL, INFERRED; parity
+    unpinned]: per column, the shift minimising the column's noise-model loss.  Restated as the full-batch
+    AdaGrad loop of ``mf_fit`` on a model reduced to its ColShift layer (Z = 0, sigma = 1, no batch layers,
+    no penalties), started at mu = 0.  Returns (M_estimates, history)."""
+    K, M = m.X.shape
+    N = m.Y.shape[1]
+    mm = OracleModel(X=np.zeros((K, M)), Y=np.zeros((K, N)), logsigma=np.zeros(N), mu=np.zeros(N),
+                     logdelta=None, theta=None, noise=m.noise)
+    mm.frozen = [True, True, False, True]
+    h = mf_fit(mm, D, AdaGrad(lr), max_epochs=max_epochs, rel_tol=rel_tol, abs_tol=abs_tol, update_col_layers=True)
+    return mm.mu, h
+
+
+def init_mu(m: OracleModel, D: np.ndarray, lr_mu=0.1, max_epochs=500):
+    """``init_mu!`` (src/fit.jl:82-104): mu <- M-estimates (rel_tol 1e-5, abs_tol 1e-3 as hard-coded there)."""
+    est, h = compute_M_estimates(m, D, lr=lr_mu, max_epochs=max_epochs)
+    m.mu = est.astype(m.mu.dtype)
+    return h
+
+
 def init_logsigma(m: OracleModel, D: np.ndarray) -> None:
     """src/fit.jl:125-148: with X = Y = 0, logsigma = log sqrt(col sq. error / number of finite entries)."""
     X0, Y0 = m.X, m.Y

@@ -4,8 +4,8 @@ Holds the CUDA kernels + C ABI (``csrc/``, built into ``libpmf.so``) and the hos
 mirror of the reference interface for that path (``PathMatFacModel``, ``mf_fit``,
 ``mf_fit_adapt_lr``).  Import it as ``pathmatfac_b200`` (the directory name carries a dot;
 ``pathmatfac_b200.py`` at the repo root is the import alias)."""
-from .fit import (AdaGrad, Engine, cpu, gpu, init_logsigma, mf_fit, mf_fit_adapt_lr, reweight_col_losses,
-                  theta_delta_em)
+from .fit import (AdaGrad, Engine, compute_M_estimates, cpu, gpu, init_logsigma, init_mu, mf_fit, mf_fit_adapt_lr,
+                  reweight_col_losses, theta_delta_em)
 from .layers import (BatchArray, BatchScale, BatchShift, ColScale, ColShift, FrozenLayer,
                      ViewableComposition, construct_model_layers, freeze_layer, unfreeze_layer)
 from .model import CompositeNoise, MatFacModel, PathMatFacModel

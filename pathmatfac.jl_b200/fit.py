@@ -425,6 +425,55 @@ def _with_zero_factors(model, fn):
             eng.close()
 
 
+def compute_M_estimates(model, lr=0.1, max_epochs=500, rel_tol=1e-5, abs_tol=1e-3, device=0):
+    """``MF.compute_M_estimates`` as ``init_mu!`` calls it (src/fit.jl:88-92): per column, the shift that
+    minimises the column's noise-model loss.  It is the fit loop on a model reduced to its ColShift layer:
+    X = Y = 0, sigma = 1, batch parameters zero, every other layer and every penalty frozen, mu started at 0
+    -- the same fused data pass, 2 bytes of parameter traffic per column.  Returns (M_estimates, history);
+    the host model is not touched."""
+    transient = model._engine is None
+    eng = Engine(model, device=device) if transient else model._engine
+    try:
+        if not transient:
+            eng.push_structure()
+        zx = np.zeros((eng.M, eng.K), np.float32)
+        zy = np.zeros((eng.N, eng.K), np.float32)
+        zn = np.zeros(eng.N, np.float32)
+        eng._ck(eng.lib.pmf_set_factors(eng.h, fptr(zx), fptr(zy)))
+        eng._ck(eng.lib.pmf_set_col_params(eng.h, fptr(zn), fptr(zn)))
+        ld, th = eng._batch_arrays()
+        for v in range(eng.n_views):
+            z = np.zeros((ld if ld is not None else th).values[v].shape[::-1], np.float32)
+            eng._ck(eng.lib.pmf_set_batch_values(eng.h, v, fptr(z), fptr(z)))
+        eng._ck(eng.lib.pmf_set_frozen(eng.h, 0b1011, 0xFFFFFFFF))     # only ColShift (slot 3 of 4) trains
+        eng.reset_opt_state(1e-8)
+        o = eng.make_opts(max_epochs=int(max_epochs), epoch=1, lr=float(lr), adagrad_eps=1e-8, rel_tol=float(rel_tol),
+                          abs_tol=float(abs_tol), update_X=0, update_Y=0, update_col_layers=1)
+        h = eng.fit(o)
+        est = np.empty(eng.N, np.float32)
+        eng._ck(eng.lib.pmf_get_col_params(eng.h, None, fptr(est)))
+        if not transient:
+            eng.push_structure()       # frozen masks, penalties
+            eng.push_params()
+            eng.reset_opt_state(1e-8)
+        return est, h
+    finally:
+        if transient:
+            eng.close()
+
+
+def init_mu(model, lr_mu=0.1, max_epochs=500, history=None, **kwargs):
+    """``init_mu!`` (src/fit.jl:82-104)."""
+    est, h = compute_M_estimates(model, lr=lr_mu, max_epochs=max_epochs, **kwargs)
+    if history is not None:
+        h["name"] = "init_mu"
+        history.append(h)
+    model.matfac.col_transform.unwrapped(2).mu[...] = est
+    if model._engine is not None:
+        model._engine.push_params()
+    return h
+
+
 def init_logsigma(model):
     """``init_logsigma!`` (src/fit.jl:125-148): logsigma_j = log sqrt(mean_i (D_ij - forward_ij)^2) with
     X = Y = 0, i.e. the spread of each column around its shift; one streaming pass on the device."""

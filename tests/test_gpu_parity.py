@@ -557,6 +557,33 @@ def test_init_logsigma_and_reweight_col_losses():
     assert np.max(np.abs(np.array(h["loss"]) / np.array(href["loss"]) - 1)) < TOL
 
 
+def test_init_mu_m_estimates():
+    """init_mu! (src/fit.jl:82-104): mu <- the per-column shift minimising the column's noise-model loss,
+    found by the fit loop on the model reduced to its ColShift layer.  Checked against the oracle's
+    restatement (same epochs, loss curve, estimates) and against the closed forms: the column mean for
+    normal columns, logit / log of the mean for bernoulli / poisson columns once converged."""
+    views = {"mutation": ("bernoulli", 40), "methylation": ("normal", 60), "counts": ("poisson", 30)}
+    model, om, D = make_pair(300, views, K=4, seed=93, batch_views=["methylation"], n_batches=3, missing=0.2)
+    est_ref, href = O.compute_M_estimates(om, D, lr=0.1, max_epochs=300)
+    mu_before = model.matfac.col_transform.layers[2].mu.copy()
+    est, h = P.compute_M_estimates(model, lr=0.1, max_epochs=300)
+    assert np.array_equal(model.matfac.col_transform.layers[2].mu, mu_before)       # host model untouched
+    assert h["epochs"] == href["epochs"] and h["term_code"] == href["term_code"]
+    # the total changes sign on the way down (poisson / bernoulli terms): compare on the scale of its terms
+    assert np.max(np.abs(np.array(h["loss"]) - np.array(href["loss"]))) < 1e-5 * abs(href["loss"][0])
+    assert relerr(est, est_ref) < 1e-3
+    P.init_mu(model, lr_mu=0.1, max_epochs=300)
+    assert np.array_equal(model.matfac.col_transform.layers[2].mu, est)
+    # long run: the M-estimates of the three noise models in closed form
+    est, _ = P.compute_M_estimates(model, lr=0.5, max_epochs=3000, rel_tol=0.0, abs_tol=0.0)
+    with np.errstate(invalid="ignore"):
+        m = np.nanmean(D, axis=0)
+    assert np.allclose(est[40:100], m[40:100], atol=2e-3)
+    ok = (m[:40] > 0.02) & (m[:40] < 0.98)
+    assert np.allclose(est[:40][ok], np.log(m[:40][ok] / (1 - m[:40][ok])), atol=2e-2)
+    assert np.allclose(est[100:], np.log(m[100:]), atol=2e-2)
+
+
 def test_transform_new_samples():
     """transform (src/transform.jl:6-106): new samples, columns given in another order and only partly
     present (matched by feature id, NaN-padded), batch layers dropped, X fitted alone through the boundary."""
