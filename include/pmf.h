@@ -68,6 +68,11 @@ typedef struct {
 /* size(model.data), size(model.matfac.X,1)  (src/model.jl:46, src/fit.jl:142). */
 int pmf_create(const pmf_dims* dims, pmf_handle* out);
 int pmf_destroy(pmf_handle h);
+/* A destroyed handle parks its data buffer (>= 64 MB; at most two are kept per process) for the next
+ * pmf_create of the same size on the same device: mf_fit! on a host-resident model creates and destroys a
+ * handle per call (src/fit.jl:9-38 with the model moved by gpu()/cpu() around it), and cudaMalloc / cudaFree of
+ * a gigabyte would otherwise dominate short fits.  This call returns the parked memory to the driver. */
+int pmf_release_cached_memory(void);
 const char* pmf_last_error(pmf_handle h);
 /* Library / build identification ("libpmf <ver> sm_100a"). */
 const char* pmf_version(void);

@@ -58,6 +58,7 @@ function to_device(model::PM.PathMatFacModel; device::Integer=0)
 end
 
 release(h::Handle) = ccall((:pmf_destroy, LIBPMF), Cint, (Handle,), h)
+release_cached_memory() = ccall((:pmf_release_cached_memory, LIBPMF), Cint, ())
 
 function push_params!(h::Handle, model)
     mf = model.matfac

@@ -53,6 +53,7 @@ H = C.c_void_p
 SIGNATURES = {
     "pmf_create": (C.c_int, [C.POINTER(pmf_dims), C.POINTER(H)]),
     "pmf_destroy": (C.c_int, [H]),
+    "pmf_release_cached_memory": (C.c_int, []),
     "pmf_last_error": (C.c_char_p, [H]),
     "pmf_version": (C.c_char_p, []),
     "pmf_set_stream": (C.c_int, [H, C.c_void_p]),

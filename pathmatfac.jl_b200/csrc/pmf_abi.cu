@@ -11,6 +11,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -61,6 +62,74 @@ template <class T>
 static void dev_free(T*& p) {
     if (p) cudaFree((void*)p);
     p = nullptr;
+}
+
+// The data buffer (and its permuted copy on the batch path) is by far the largest allocation of a handle, and
+// cudaMalloc / cudaFree of a gigabyte cost 10-200 ms depending on the driver's mood.  Callers that create a
+// handle per fit (mf_fit on a host-resident model) would pay that on every call, so a destroyed handle parks its
+// big buffers here and the next pmf_create of the same size on the same device takes them over.  At most
+// kPoolSlots buffers are parked; pmf_release_cached_memory() frees them.
+namespace {
+struct ParkedBuf { int dev; size_t bytes; void* p; };
+constexpr size_t kPoolMinBytes = 64u << 20;
+constexpr int kPoolSlots = 2;
+std::mutex g_pool_mu;
+std::vector<ParkedBuf> g_pool;
+}  // namespace
+
+static cudaError_t big_alloc(float** p, size_t n_floats, int dev) {
+    const size_t bytes = n_floats * sizeof(float);
+    *p = nullptr;
+    if (bytes == 0) return cudaSuccess;
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        for (size_t k = 0; k < g_pool.size(); ++k)
+            if (g_pool[k].dev == dev && g_pool[k].bytes == bytes) {
+                *p = static_cast<float*>(g_pool[k].p);
+                g_pool.erase(g_pool.begin() + k);
+                return cudaSuccess;
+            }
+    }
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(p), bytes);
+    if (e != cudaSuccess) {      // out of memory: give the parked buffers back and retry once
+        pmf_release_cached_memory();
+        cudaGetLastError();
+        e = cudaMalloc(reinterpret_cast<void**>(p), bytes);
+    }
+    return e;
+}
+// the caller has synchronised the device: no work can still touch the buffer
+static void big_free(float*& p, size_t n_floats, int dev) {
+    if (!p) return;
+    const size_t bytes = n_floats * sizeof(float);
+    void* victim = p;
+    p = nullptr;
+    if (bytes >= kPoolMinBytes) {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        g_pool.push_back(ParkedBuf{dev, bytes, victim});
+        victim = nullptr;
+        if ((int)g_pool.size() > kPoolSlots) {
+            victim = g_pool.front().p;
+            g_pool.erase(g_pool.begin());
+        }
+    }
+    if (victim) cudaFree(victim);
+}
+
+int pmf_release_cached_memory(void) {
+    std::vector<ParkedBuf> drop;
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        drop.swap(g_pool);
+    }
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (const ParkedBuf& b : drop) {
+        cudaSetDevice(b.dev);
+        cudaFree(b.p);
+    }
+    cudaSetDevice(cur);
+    return PMF_OK;
 }
 
 // host [rows][w] (pitch w) -> device [rows][wd] (pitch wd)
@@ -144,7 +213,7 @@ int pmf_create(const pmf_dims* d, pmf_handle* out) {
     cudaEventCreate(&h->ev1);
     const size_t xk = (size_t)h->Mp * h->Kp, yk = (size_t)h->Np * h->Kp;
     bool ok = true;
-    ok &= dev_alloc(&h->A, (size_t)h->N * h->lda) == cudaSuccess;
+    ok &= big_alloc(&h->A, (size_t)h->N * h->lda, d->device) == cudaSuccess;
     ok &= dev_alloc(&h->X, xk) == cudaSuccess && dev_alloc(&h->dX, xk) == cudaSuccess && dev_alloc(&h->accX, xk) == cudaSuccess;
     ok &= dev_alloc(&h->Y, yk) == cudaSuccess && dev_alloc(&h->accY, yk) == cudaSuccess;
     ok &= dev_alloc(&h->weight, h->Np) == cudaSuccess && dev_alloc(&h->colinfo, h->Np) == cudaSuccess;
@@ -173,7 +242,8 @@ int pmf_destroy(pmf_handle h) {
     if (!h) return PMF_OK;
     cudaSetDevice(h->dims.device);
     cudaDeviceSynchronize();
-    dev_free(h->A); dev_free(h->X); dev_free(h->dX); dev_free(h->accX); dev_free(h->Y); dev_free(h->accY);
+    big_free(h->A, (size_t)h->N * h->lda, h->dims.device);
+    dev_free(h->X); dev_free(h->dX); dev_free(h->accX); dev_free(h->Y); dev_free(h->accY);
     dev_free(h->Xl); dev_free(h->Xh); dev_free(h->tc_cost_cum);
     dev_free(h->weight); dev_free(h->colinfo); dev_free(h->thresholds); dev_free(h->scalars); dev_free(h->ctrl);
     dev_free(h->vp); dev_free(h->sg); dev_free(h->accvp); dev_free(h->regw); dev_free(h->regc);
@@ -1044,6 +1114,11 @@ int pmf_model_s::realloc_vectors(int new_nbp) {
 
 // ---- tcgen05 data pass with batch layers: sample orders and passes (TcBatchDev) -----------------------
 void pmf_model_s::free_tc_plan() {
+    if (tcb.A_tc) {
+        cudaStreamSynchronize(stream);       // the buffer is parked for reuse, not freed: nothing may still read it
+        float* a = const_cast<float*>(tcb.A_tc);
+        big_free(a, (size_t)tcb.n_pass * 128 * tcb.n_pos, dims.device);
+    }
     for (void* q : tcb_allocs) cudaFree(q);
     tcb_allocs.clear();
     tcb = pmf::TcBatchDev{};
@@ -1152,8 +1227,12 @@ int pmf_model_s::build_tc_plan() {
         ok = upload(perm_flat.data(), perm_flat.size() * 4, (const void**)&t.perm) &&
              upload(pos_flat.data(), pos_flat.size() * 4, (const void**)&t.pos) &&
              upload(nullptr, rows * 64 * 4, (const void**)&t.Xh) && upload(nullptr, rows * 64 * 4, (const void**)&t.Xb) &&
-             upload(nullptr, rows * Kp * 4, (const void**)&t.dX) &&
-             upload(nullptr, (size_t)n_pass * 128 * n_pos * 4, (const void**)&t.A_tc);
+             upload(nullptr, rows * Kp * 4, (const void**)&t.dX);
+        if (ok) {
+            float* a = nullptr;
+            ok = big_alloc(&a, (size_t)n_pass * 128 * n_pos, dims.device) == cudaSuccess;
+            t.A_tc = a;
+        }
         if (ok) {
             // operand scratch is 64 / 128 wide and zero beyond Kp; the dX copies start (and are left) clean
             ok = cudaMemsetAsync(t.Xh, 0, rows * 64 * 4, stream) == cudaSuccess &&
