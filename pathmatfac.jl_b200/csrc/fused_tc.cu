@@ -365,9 +365,11 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
     if (threadIdx.x == 0) {
         for (int b = 0; b < B_COUNT; ++b) {
             uint32_t cnt = 1u;
-            if (b == B_Y_READY || b == B_DY_EMPTY) cnt = 32u * NEPI;                       // every epilogue thread
+            // Epilogue warps arrive ONCE PER WARP (lane 0, after the lanes' fences and a __syncwarp): an arrive is
+            // an atomic on the barrier word, and 256 of them per barrier and tile serialise in the shared-memory unit
+            if (b == B_Y_READY || b == B_DY_EMPTY) cnt = NEPI;                             // every epilogue warp
             if ((b >= B_G_READY && b < B_G_READY + SZ) || b == B_DX_EMPTY || b == B_DX_EMPTY + 1 || b == B_DXS_FULL)
-                cnt = 16u * NEPI;                                                         // one epilogue group
+                cnt = NEPI / 2;                                                           // one epilogue group
             mbar_init(bar(b), cnt);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -445,6 +447,7 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
                 const int xrow0 = BATCH ? __ldg(p.pass_order + itx.jt) * dp.Mp : 0;   // this order's copy of dX
                 for (int it = it0; it < it1; ++it, ++g) {
                     mbar_wait(bar(B_DXS_FULL), g & 1);
+                    stamp(g, 31);
                     if (!(DBG && p.ablate & 16)) {
                         tma_reduce_add_2d(&tmDX, DXS, 0, xrow0 + it * BI);
                         if (dp.Kp > 32) tma_reduce_add_2d(&tmDX, DXS + 8192, 32, xrow0 + it * BI);
@@ -607,12 +610,15 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
             TMEM_LD16(tm + lane_addr + TM_DX0 + 64 * b + 32 * h32 + 16, r1);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             tc_fence_before();
-            mbar_arrive_relaxed(bar(B_DX_EMPTY + b));
+            __syncwarp();
+            if (lane == 0) mbar_arrive_relaxed(bar(B_DX_EMPTY + b));
+            if (tr) stamp(gg, 28);
             {
                 const uint32_t n_other = grp == 0 ? (gg >> 1) : ((gg + 1) >> 1), n_own = gg >> 1;   // flushes before tile gg
                 mbar_wait(bar(B_DXS_DONE + (grp ^ 1)), (n_other - 1u) & 1u);     // n == 0: parity 1 passes on a fresh barrier
                 mbar_wait(bar(B_DXS_DONE + grp), (n_own - 1u) & 1u);
             }
+            if (tr) stamp(gg, 29);
             if (lane < 16 && !(DBG && p.ablate & 16)) {
                 const int r = 16 * quarter + lane;                       // sample row of the tile
                 uint8_t* row = dxs_ptr + h32 * 8192 + r * 128;
@@ -623,7 +629,9 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
                 }
             }
             fence_async_smem();
-            mbar_arrive(bar(B_DXS_FULL));
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar(B_DXS_FULL));
+            if (tr) stamp(gg, 30);
         };
         int pend_i0 = -1;          // sample offset of this group's tile whose dX is still in TMEM
         uint32_t pend_g = 0;
@@ -798,7 +806,8 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
                 tc_fence_before();
                 fence_async_smem();
                 if (trp) stamp(g, 20 + 6 * grp);
-                mbar_arrive(bar(B_Y_READY));
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar(B_Y_READY));
                 if (trp) stamp(g, 21 + 6 * grp);
                 store_partials();
                 store_segment();
@@ -918,7 +927,8 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 tc_fence_before();
                 fence_async_smem();
-                mbar_arrive(bar(B_G_READY + rz.s));
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar(B_G_READY + rz.s));
                 store_segment();
                 if (BATCH && boff >= 0 && it + 2 < it1) fetch_ids(it + 2);
                 if (tr) stamp(g, 9);
@@ -946,7 +956,8 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
                 TMEM_LD16(tm + lane_addr + TM_DY + 16 * c16, r);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 tc_fence_before();
-                mbar_arrive_relaxed(bar(B_DY_EMPTY));
+                __syncwarp();
+                if (lane == 0) mbar_arrive_relaxed(bar(B_DY_EMPTY));
                 // next item's operands: issued after the last arrive of this item so that no fence waits on them
                 if (itx.peek_jt() >= 0) load_item(itx.peek_jt(), nxt);
                 // The results stay in registers and are reduced into global memory AFTER the next item's Y

@@ -33,3 +33,13 @@ for g in range(1, a.shape[0]):
     if a[g, 17] > 0 or a[g, 23] > 0:
         print(f" tile {g}: " + " | ".join(f"{grp}:" + ",".join(f"{n}={a[g, 16 + 6 * k + i] - t0 if a[g, 16 + 6 * k + i] > 0 else -1}" for i, n in enumerate(names)) for k, grp in enumerate("AB")),
               f"| MMA Y_READY->M1_issue(g)={a[g, 1] - t0}")
+
+# finer stamps of the dX flush (events 28..31): TMEM read done, staging buffer free, staged + arrived, issuer woke up
+if a.shape[1] >= 32 and (a[lo:hi, 28] > 0).all():
+    print("dX flush of tile g (cycles after DXFULL_seen):")
+    for name, ev in [("TMEM read + DX_EMPTY arrive", 28), ("staging buffer free (DXS_DONE x2)", 29), ("staged, DXS_FULL arrive", 30),
+                     ("issuer saw DXS_FULL", 31), ("TMA read of staging done", 12)]:
+        v = d[:, ev] - d[:, 11]
+        print(f"  {name:38s} mean {v.mean():9.1f}  min {v.min():7d}  max {v.max():7d}")
+    v = d[2:, 5] - d[:-2, 30]
+    print(f"  {'epi_top(g+2) - staged(g-2..)':38s} (next tile of the group starts) see rows")
