@@ -73,6 +73,21 @@ int pmf_destroy(pmf_handle h);
  * handle per call (src/fit.jl:9-38 with the model moved by gpu()/cpu() around it), and cudaMalloc / cudaFree of
  * a gigabyte would otherwise dominate short fits.  This call returns the parked memory to the driver. */
 int pmf_release_cached_memory(void);
+
+/* Host-side preview of how the tcgen05 data pass lays out a model with batch layers (no device work, no handle;
+ * the same planner every handle runs).  BatchArray (src/batch_array.jl:5-15, 47-79) puts no order on the
+ * samples of a batch; the kernel wants every 16-sample chunk inside one batch, so a view that does not come
+ * that way gets a SAMPLE ORDER (samples stably sorted by batch id, every batch padded to a multiple of 16
+ * positions; order 0 = identity), and every 128-column tile is walked once per order its views need (a PASS).
+ *   bos:         [n_views][M] batch of each sample, 0-based
+ *   view_order:  [n_views] order of each view                       (may be NULL)
+ *   perm:        [n_orders][n_pos] position -> sample, -1 = padding (may be NULL; capacity in elements)
+ *   pass_feat0 / pass_order: [n_pass] first column and order of each pass (may be NULL)
+ *   chunk_batch: [n_views][n_pos / 16] batch of each chunk in the view's own order (may be NULL) */
+int pmf_plan_batch_orders(int32_t M, int32_t N, int32_t n_views, const int32_t* col_start, const int32_t* col_stop,
+                          const int32_t* n_batches, const int32_t* bos, int32_t* n_orders, int32_t* n_pass,
+                          int32_t* n_pos, int32_t* view_order, int32_t* perm, int64_t perm_cap, int32_t* pass_feat0,
+                          int32_t* pass_order, int32_t pass_cap, uint16_t* chunk_batch, int64_t chunk_cap);
 const char* pmf_last_error(pmf_handle h);
 /* Library / build identification ("libpmf <ver> sm_100a"). */
 const char* pmf_version(void);

@@ -54,6 +54,9 @@ SIGNATURES = {
     "pmf_create": (C.c_int, [C.POINTER(pmf_dims), C.POINTER(H)]),
     "pmf_destroy": (C.c_int, [H]),
     "pmf_release_cached_memory": (C.c_int, []),
+    "pmf_plan_batch_orders": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, c_int32_p, c_int32_p, c_int32_p, c_int32_p,
+                                        c_int32_p, c_int32_p, c_int32_p, c_int32_p, c_int32_p, C.c_int64, c_int32_p,
+                                        c_int32_p, C.c_int32, C.POINTER(C.c_uint16), C.c_int64]),
     "pmf_last_error": (C.c_char_p, [H]),
     "pmf_version": (C.c_char_p, []),
     "pmf_set_stream": (C.c_int, [H, C.c_void_p]),

@@ -1125,15 +1125,18 @@ void pmf_model_s::free_tc_plan() {
     tcb_valid = false;
 }
 
-int pmf_model_s::build_tc_plan() {
-    free_tc_plan();
+// Host-side planning of the batch path (pure bookkeeping, no device work): sample orders, passes, chunk batches.
+struct TcBatchPlanHost {
+    int n_orders = 1, n_pass = 0, n_pos = 0, n_used = 0;
+    std::vector<std::vector<int32_t>> perms;         // [n_orders][n_pos] position -> sample, -1 = padding
+    std::vector<int32_t> view_order, pass_feat0, pass_order, cost_cum;
+    std::vector<uint16_t> boc;                       // [n_views][n_pos / 16]
+};
+
+static void plan_tc_batches(int M, int Mp, int N, const std::vector<BatchView>& views, const std::vector<int32_t>& bos_host,
+                            const std::vector<int32_t>& tile_cost_host, TcBatchPlanHost& out) {
     const int V = (int)views.size();
     const int n_jt = (N + 127) / 128;
-    if (V == 0 || (int)tile_cost_host.size() != n_jt || bos_host.size() != (size_t)V * M)
-        return fail(this, PMF_ERR_STATE, "batch layout / noise models are not set");
-    for (const BatchView& bv : views)
-        if (bv.n_batches > 65533) return fail(this, PMF_ERR_ARG, "tcgen05 data pass: more than 65533 batches in a view");
-
     // 1. sample orders (position -> sample, -1 = padding).  A view keeps the identity order when every 16-sample
     //    chunk lies in one batch as given; otherwise its samples are stably sorted by batch id and every batch is
     //    padded to a multiple of 16 positions.  Equal orders are shared between views.
@@ -1199,6 +1202,72 @@ int pmf_model_s::build_tc_plan() {
         }
     }
 
+    out.n_orders = n_orders; out.n_pass = n_pass; out.n_pos = n_pos;
+    out.n_used = n_orders == 1 ? M : (int)n_used;
+    out.perms = std::move(perms);
+    out.view_order = std::move(view_order);
+    out.pass_feat0 = std::move(pass_feat0);
+    out.pass_order = std::move(pass_order);
+    out.cost_cum = std::move(cost_cum);
+    out.boc = std::move(boc);
+}
+
+int pmf_plan_batch_orders(int32_t M, int32_t N, int32_t n_views, const int32_t* cs, const int32_t* ce, const int32_t* nb,
+                          const int32_t* bos, int32_t* n_orders, int32_t* n_pass, int32_t* n_pos, int32_t* view_order,
+                          int32_t* perm, int64_t perm_cap, int32_t* pass_feat0, int32_t* pass_order, int32_t pass_cap,
+                          uint16_t* chunk_batch, int64_t chunk_cap) {
+    if (M <= 0 || N <= 0 || n_views <= 0 || !cs || !ce || !nb || !bos || !n_orders || !n_pass || !n_pos)
+        return fail(nullptr, PMF_ERR_ARG, "bad arguments");
+    std::vector<BatchView> views;
+    int prev_end = 0;
+    for (int v = 0; v < n_views; ++v) {
+        if (cs[v] < prev_end || ce[v] > N || cs[v] >= ce[v] || nb[v] <= 0 || nb[v] > 65533)
+            return fail(nullptr, PMF_ERR_ARG, "batch view %d: bad column range or batch count", v);
+        prev_end = ce[v];
+        views.push_back(BatchView{cs[v], ce[v], nb[v], 0});
+        for (int i = 0; i < M; ++i)
+            if (bos[(size_t)v * M + i] < 0 || bos[(size_t)v * M + i] >= nb[v])
+                return fail(nullptr, PMF_ERR_ARG, "batch_of_sample[%d][%d] out of range", v, i);
+    }
+    std::vector<int32_t> b(bos, bos + (size_t)n_views * M), cost((N + 127) / 128, 1);
+    TcBatchPlanHost pl;
+    plan_tc_batches(M, round_up(M, 128), N, views, b, cost, pl);
+    *n_orders = pl.n_orders; *n_pass = pl.n_pass; *n_pos = pl.n_pos;
+    if (view_order) std::copy(pl.view_order.begin(), pl.view_order.end(), view_order);
+    if (perm) {
+        if (perm_cap < (int64_t)pl.n_orders * pl.n_pos) return fail(nullptr, PMF_ERR_ARG, "perm buffer too small");
+        for (int o = 0; o < pl.n_orders; ++o) std::copy(pl.perms[o].begin(), pl.perms[o].end(), perm + (size_t)o * pl.n_pos);
+    }
+    if (pass_feat0 || pass_order) {
+        if (pass_cap < pl.n_pass) return fail(nullptr, PMF_ERR_ARG, "pass buffers too small");
+        if (pass_feat0) std::copy(pl.pass_feat0.begin(), pl.pass_feat0.end(), pass_feat0);
+        if (pass_order) std::copy(pl.pass_order.begin(), pl.pass_order.end(), pass_order);
+    }
+    if (chunk_batch) {
+        if (chunk_cap < (int64_t)pl.boc.size()) return fail(nullptr, PMF_ERR_ARG, "chunk buffer too small");
+        std::copy(pl.boc.begin(), pl.boc.end(), chunk_batch);
+    }
+    return PMF_OK;
+}
+
+int pmf_model_s::build_tc_plan() {
+    free_tc_plan();
+    const int V = (int)views.size();
+    const int n_jt = (N + 127) / 128;
+    if (V == 0 || (int)tile_cost_host.size() != n_jt || bos_host.size() != (size_t)V * M)
+        return fail(this, PMF_ERR_STATE, "batch layout / noise models are not set");
+    for (const BatchView& bv : views)
+        if (bv.n_batches > 65533) return fail(this, PMF_ERR_ARG, "tcgen05 data pass: more than 65533 batches in a view");
+
+    TcBatchPlanHost pl;
+    plan_tc_batches(M, Mp, N, views, bos_host, tile_cost_host, pl);
+    const int n_orders = pl.n_orders, n_pass = pl.n_pass, n_pos = pl.n_pos;
+    const size_t n_used = (size_t)pl.n_used;
+    const std::vector<std::vector<int32_t>>& perms = pl.perms;
+    const std::vector<int32_t>&view_order = pl.view_order, &pass_feat0 = pl.pass_feat0, &pass_order = pl.pass_order,
+                              &cost_cum = pl.cost_cum;
+    const std::vector<uint16_t>& boc = pl.boc;
+
     auto upload = [&](const void* src, size_t bytes, const void** dst) -> bool {
         void* d = nullptr;
         if (cudaMalloc(&d, bytes ? bytes : 4) != cudaSuccess) return false;
@@ -1209,7 +1278,7 @@ int pmf_model_s::build_tc_plan() {
     };
     pmf::TcBatchDev& t = tcb;
     t.n_orders = n_orders; t.n_pass = n_pass; t.n_views = V;
-    t.n_pos = n_pos; t.n_used = n_orders == 1 ? M : (int)n_used;
+    t.n_pos = n_pos; t.n_used = (int)n_used;
     t.direct = n_orders == 1;
     bool ok = upload(pass_feat0.data(), (size_t)n_pass * 4, (const void**)&t.pass_feat0) &&
               upload(pass_order.data(), (size_t)n_pass * 4, (const void**)&t.pass_order) &&

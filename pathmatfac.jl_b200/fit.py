@@ -401,6 +401,37 @@ def cpu(model):
     return model
 
 
+def plan_batch_orders(M, N, col_ranges, n_batches, batch_of_sample) -> Dict:
+    """Host-side preview of the batch-layer layout of the tcgen05 data pass (``pmf_plan_batch_orders``; no device
+    needed): sample orders, passes and per-chunk batches.  ``col_ranges``: [(start, stop)] 0-based per batched
+    view, ``batch_of_sample``: [n_views][M] int."""
+    lib = _lib.load()
+    V = len(col_ranges)
+    cs = np.array([r[0] for r in col_ranges], np.int32)
+    ce = np.array([r[1] for r in col_ranges], np.int32)
+    nb = np.asarray(n_batches, np.int32)
+    bos = np.ascontiguousarray(np.asarray(batch_of_sample, np.int32).reshape(V, M))
+    n = (C.c_int32 * 3)()
+    p0, p1, p2 = (C.cast(C.byref(n, 4 * k), _lib.c_int32_p) for k in range(3))
+
+    def call(*bufs):
+        rc = lib.pmf_plan_batch_orders(M, N, V, iptr(cs), iptr(ce), iptr(nb), iptr(bos), p0, p1, p2, *bufs)
+        if rc != 0:
+            msg = lib.pmf_last_error(None)
+            raise _lib.PmfError(msg.decode() if msg else f"pmf_plan_batch_orders failed ({rc})")
+    call(None, None, 0, None, None, 0, None, 0)
+    n_orders, n_pass, n_pos = int(n[0]), int(n[1]), int(n[2])
+    view_order = np.zeros(V, np.int32)
+    perm = np.zeros((n_orders, n_pos), np.int32)
+    pass_feat0 = np.zeros(n_pass, np.int32)
+    pass_order = np.zeros(n_pass, np.int32)
+    chunk_batch = np.zeros((V, n_pos // 16), np.uint16)
+    call(iptr(view_order), iptr(perm), perm.size, iptr(pass_feat0), iptr(pass_order), n_pass,
+         chunk_batch.ctypes.data_as(C.POINTER(C.c_uint16)), chunk_batch.size)
+    return {"n_orders": n_orders, "n_pass": n_pass, "n_pos": n_pos, "view_order": view_order, "perm": perm,
+            "pass_feat0": pass_feat0, "pass_order": pass_order, "chunk_batch": chunk_batch}
+
+
 # ---- staging passes that bracket the hot loop (SURVEY 8f rank 1) -----------------------------------
 
 def _with_zero_factors(model, fn):

@@ -177,3 +177,65 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".h", ".cuh")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def _check_plan(M, N, ranges, nb, bos):
+    from pathmatfac_b200.fit import plan_batch_orders
+    pl = plan_batch_orders(M, N, ranges, nb, bos)
+    V = len(ranges)
+    n_pos, perm = pl["n_pos"], pl["perm"]
+    assert n_pos % 128 == 0 and perm.shape == (pl["n_orders"], n_pos)
+    # every order lists every sample exactly once; order 0 is the identity
+    for o in range(pl["n_orders"]):
+        real = perm[o][perm[o] >= 0]
+        assert np.array_equal(np.sort(real), np.arange(M))
+    assert np.array_equal(perm[0][:M], np.arange(M))
+    for v in range(V):
+        pm = perm[pl["view_order"][v]]
+        b = np.asarray(bos[v])
+        cb = pl["chunk_batch"][v]
+        for c in range(n_pos // 16):
+            idx = pm[16 * c:16 * c + 16]
+            idx = idx[idx >= 0]
+            # the kernel's invariant: the samples of a chunk share one batch, and the table names it
+            assert np.all(b[idx] == cb[c]), (v, c)
+        # stable inside a batch: samples keep their relative order
+        if pl["view_order"][v] != 0:
+            real = pm[pm >= 0]
+            assert np.array_equal(b[real], np.sort(b, kind="stable"))
+            for k in np.unique(b):
+                assert np.all(np.diff(real[b[real] == k]) > 0)
+    # passes: every 128-column tile appears once per order its batched views need; unbatched-only tiles once
+    n_jt = (N + 127) // 128
+    for jt in range(n_jt):
+        need = {int(pl["view_order"][v]) for v, (s, e) in enumerate(ranges) if s < min(N, 128 * jt + 128) and e > 128 * jt}
+        got = [int(o) for f, o in zip(pl["pass_feat0"], pl["pass_order"]) if f == 128 * jt]
+        assert sorted(got) == sorted(need or {0}) and len(got) == len(set(got))
+    assert np.all(np.diff(pl["pass_feat0"]) >= 0)
+    return pl
+
+
+def test_batch_order_planner_bookkeeping():
+    """Bit-exact bookkeeping of the batch path's host planner (pmf_plan_batch_orders): orders are
+    permutations with every batch padded to 16-position chunks, chunk tables name the batch of every chunk,
+    passes cover every (tile, order) pair once.  No device needed."""
+    rng = np.random.default_rng(5)
+    M, N = 1203, 900
+    ranges = [(0, 150), (150, 483), (600, 900)]                      # view boundaries inside tiles, a gap without batches
+    nb = [9, 4, 40]
+    bos = [rng.integers(0, k, size=M) for k in nb]
+    bos[1] = np.sort(bos[1])                                         # contiguous, but not aligned to 16: still its own order
+    pl = _check_plan(M, N, ranges, nb, bos)
+    assert pl["n_orders"] == 4 and len(set(pl["view_order"])) == 3 and 0 not in pl["view_order"]
+    # two views with the same batch assignment share one order
+    pl = _check_plan(M, N, ranges, [9, 9, 40], [bos[0], bos[0], bos[2]])
+    assert pl["n_orders"] == 3 and pl["view_order"][0] == pl["view_order"][1]
+    # batches that already fill whole 16-sample chunks: identity order, no permuted copies
+    aligned = np.repeat(np.arange(8), 160)[:M]
+    pl = _check_plan(M, N, [(0, 900)], [8], [aligned])
+    assert pl["n_orders"] == 1 and pl["n_pass"] == (N + 127) // 128 and pl["n_pos"] == 1280
+    # a single batch, a batch with one sample, M smaller than a chunk
+    _check_plan(7, 130, [(0, 130)], [3], [np.array([2, 0, 0, 1, 0, 2, 2])])
+    _check_plan(300, 40, [(5, 40)], [2], [np.r_[np.zeros(299, int), 1]])
+    with pytest.raises(_lib.PmfError):
+        _check_plan(10, 10, [(0, 10)], [2], [np.full(10, 2)])         # batch id out of range
