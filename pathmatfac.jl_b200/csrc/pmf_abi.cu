@@ -1323,9 +1323,11 @@ int pmf_model_s::build_tc_plan() {
 }
 
 int pmf_model_s::run_data_pass(DataPassParams& p, int kind, int precision) {
-    const bool tc_ok = tc_supported(p) && cc_major == 10;
+    bool batches_ok = true;                    // chunk tables hold 16-bit batch ids
+    for (const BatchView& bv : views) batches_ok &= bv.n_batches <= 65533;
+    const bool tc_ok = tc_supported(p) && cc_major == 10 && batches_ok;
     if (kind == PMF_KERNEL_TC && !tc_ok)
-        return fail(this, PMF_ERR_ARG, "tcgen05 data pass needs 8 <= K <= 64 and an sm_100 device");
+        return fail(this, PMF_ERR_ARG, "tcgen05 data pass needs 8 <= K <= 64, at most 65533 batches per view and an sm_100 device");
     // AUTO: the tcgen05 path pays off (and its single-pass TF32 gradient contractions average below
     // the 1e-4 parity bar) on large problems; small ones run the exact-FP32 FFMA kernel.
     const bool big = (double)M * (double)N >= 4.0e6 && M >= 1024;
