@@ -1037,6 +1037,120 @@ def column_ssq_grads(m: OracleModel, D: np.ndarray) -> np.ndarray:
     return out
 
 
+###############################################################################
+# Between hot-loop calls: empirical-Bayes re-weighting, factor re-ordering, post-processing
+# (reference: src/regularizers.jl reweight_eb! / reorder_reg! methods, src/fit.jl:504-555)
+###############################################################################
+
+def reweight_eb(reg, x, mixture_p=1.0):
+    """``reweight_eb!``.  x: K x n matrix, vector, BatchArray, or the list of the four layer parameters
+    [logsigma, logdelta, mu, theta] for the layer SequenceReg (a plain list of regs here)."""
+    if isinstance(reg, ZeroReg):                                            # regularizers.jl:941
+        return
+    if isinstance(reg, L2Regularizer):                                      # :39-51  (largest singular value)^2
+        X = np.atleast_2d(np.asarray(x, float))
+        reg.weights = np.full(len(reg.weights), mixture_p / np.linalg.svd(X, compute_uv=False)[0] ** 2)
+    elif isinstance(reg, SelectiveL1Reg):                                   # :149-159
+        sel = reg.l1_idx * np.asarray(x, float)
+        var_x = (sel ** 2).mean(axis=1) - sel.mean(axis=1) ** 2
+        with np.errstate(divide="ignore", invalid="ignore"):
+            w = mixture_p * np.sqrt(2.0 / var_x)
+        w[~np.isfinite(w)] = 1.0
+        reg.weight = w
+    elif isinstance(reg, NetworkRegularizer):                               # :313-328
+        row_precs = mixture_p / np.var(np.asarray(x, float), axis=1, ddof=1)
+        for k, ratio in enumerate(row_precs / reg.cur_weights):
+            reg.AA[k] = reg.AA[k] * ratio
+            reg.AB[k] = reg.AB[k] * ratio
+            reg.BB[k] = reg.BB[k] * ratio
+        reg.cur_weights = row_precs
+    elif isinstance(reg, GroupRegularizer):                                 # :406-420
+        X = np.asarray(x, float)
+        reg.group_weights = [np.full(X.shape[0], mixture_p / np.linalg.svd(X[:, r.start:r.stop], compute_uv=False)[0] ** 2)
+                             for r in reg.group_idx]
+    elif isinstance(reg, ColParamReg):                                      # :490-497
+        v = np.asarray(x, float)
+        reg.centers = [float(np.mean(v[r.start:r.stop])) for r in reg.col_ranges]
+        reg.weights = [float(mixture_p * np.float32(1e-1 + 0.5) / (np.float32(1e-1) + np.float32(0.5) * np.var(v[r.start:r.stop], ddof=1)))
+                       for r in reg.col_ranges]
+    elif isinstance(reg, ARDRegularizer):                                   # :588-609
+        reg.alpha = [0.001] * len(reg.alpha)
+        reg.beta = [0.001] * len(reg.beta)
+    elif isinstance(reg, CompositeRegularizer):                             # :634-638
+        for r, p in zip(reg.regularizers, reg.mixture_p):
+            reweight_eb(r, x, mixture_p=p * mixture_p)
+    elif isinstance(reg, BatchArrayReg):                                    # :818-840
+        reg.centers = [v.mean(axis=1) for v in x.values]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            reg.weights = [mixture_p / np.var(v, axis=1, ddof=1) for v in x.values]
+        for w, cr in zip(reg.weights, x.col_ranges):
+            w[~np.isfinite(w)] = 1.0 + 0.5 * len(cr)
+    elif isinstance(reg, list):                                             # SequenceReg, :928-932
+        for r, param in zip(reg, x):
+            reweight_eb(r, param, mixture_p=mixture_p)
+    else:
+        raise TypeError(type(reg).__name__)
+
+
+def reorder_reg(reg, perm):
+    """``reorder_reg!`` methods (regularizers.jl:5,53,161,330,449,645; featureset_ard.jl:68); perm 0-based."""
+    perm = list(perm)
+    if isinstance(reg, L2Regularizer):
+        reg.weights = reg.weights[perm]
+    elif isinstance(reg, SelectiveL1Reg):
+        reg.l1_idx = reg.l1_idx[perm, :]
+    elif isinstance(reg, NetworkRegularizer):
+        reg.AA = [reg.AA[k] for k in perm]
+        reg.AB = [reg.AB[k] for k in perm]
+        reg.BB = [reg.BB[k] for k in perm]
+        reg.x_virtual = [reg.x_virtual[k] for k in perm]
+        reg.cur_weights = reg.cur_weights[perm]
+    elif isinstance(reg, GroupRegularizer):
+        reg.group_weights = [w[perm] for w in reg.group_weights]
+    elif isinstance(reg, CompositeRegularizer):
+        for r in reg.regularizers:
+            reorder_reg(r, perm)
+    elif isinstance(reg, FeatureSetARDReg):
+        reg.beta = reg.beta[perm, :]
+        reg.A = [A[:, perm] for A in reg.A]
+        for opt in reg.A_opts:
+            opt.ssq_grad = opt.ssq_grad[:, perm]
+            opt.lam = opt.lam[perm]
+
+
+def whiten(m: OracleModel, feature_views) -> None:
+    """``whiten!`` (src/fit.jl:504-528)."""
+    x_rms = np.sqrt(np.mean(m.X * m.X, axis=1, keepdims=True))
+    m.X = m.X / x_rms
+    m.Y = m.Y * x_rms
+    for cr in ids_to_ranges(list(feature_views)):
+        y_rms_max = np.sqrt(np.mean(m.Y[:, cr.start:cr.stop] ** 2, axis=1)).max()
+        if y_rms_max > 0:
+            m.Y[:, cr.start:cr.stop] /= y_rms_max
+            m.logsigma[cr.start:cr.stop] += math.log(y_rms_max)
+        else:
+            m.Y[:, cr.start:cr.stop] = 0.0
+            m.logsigma[cr.start:cr.stop] = np.float32(-1e9)
+
+
+def rotate_by_svd(m: OracleModel) -> None:
+    """``rotate_by_svd!`` (src/fit.jl:531-544)."""
+    U, s, Vt = np.linalg.svd(m.Y, full_matrices=False)
+    m.Y = s[:, None] * Vt
+    m.X = (m.X.T @ U).T
+
+
+def reorder_by_importance(m: OracleModel):
+    """``reorder_by_importance!`` (src/fit.jl:547-555): sortperm(Y_ssq, rev=true) is stable."""
+    y_ssq = np.sum(m.Y * m.Y, axis=1)
+    idx = sorted(range(len(y_ssq)), key=lambda k: -y_ssq[k])
+    m.X = m.X[idx, :]
+    m.Y = m.Y[idx, :]
+    reorder_reg(m.Y_reg, idx)
+    reorder_reg(m.X_reg, idx)
+    return idx
+
+
 def compute_M_estimates(m: OracleModel, D: np.ndarray, lr=0.1, max_epochs=500, rel_tol=1e-5, abs_tol=1e-3):
     """``MF.compute_M_estimates`` as ``init_mu!`` calls it (src/fit.jl:82-104) [EXTERNAL, INFERRED; parity
     unpinned]: per column, the shift minimising the column's noise-model loss.  Restated as the full-batch

@@ -61,3 +61,21 @@ def make_pair(M, views, K, seed, batch_views=(), n_batches=0, n_conditions=0, mi
         regs[3] = O.BatchArrayReg(om.theta, weight=lambda_layer)
     om.layer_regs = regs
     return model, om, D.astype(np.float32).astype(np.float64)
+
+
+def random_graphs(N, K, rng, n_virtual=6, n_edges=60):
+    """Per-factor edge lists over features 1..N with a few virtual nodes (signed edges), as the model constructor
+    takes them (``feature_graphs``)."""
+    graphs = []
+    for k in range(K):
+        el = []
+        for _ in range(n_edges):
+            a, b = rng.integers(1, N + 1, size=2)
+            if a != b:
+                el.append([int(a), int(b), float(rng.choice([-1.0, 1.0]))])
+        for v in range(n_virtual):
+            for _ in range(3):
+                el.append([int(rng.integers(1, N + 1)), f"virt{k}_{v}", 1.0])
+        el.append([f"virt{k}_0", f"virt{k}_1", -1.0])
+        graphs.append(el)
+    return graphs

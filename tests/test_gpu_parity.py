@@ -7,7 +7,7 @@ import pytest
 import pathmatfac_b200 as P
 from pathmatfac_b200 import _lib
 from oracle import pmf_oracle as O
-from tests.helpers import make_pair, relerr
+from tests.helpers import make_pair, random_graphs as _graphs, relerr
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-4
@@ -67,22 +67,6 @@ def test_empty_and_all_missing_columns():
     # an all-missing column gets no data gradient: only the penalty's pullback remains
     assert relerr(got["dY"][:, 5], O._value_grad(om.Y_reg, om.Y)[1][:, 5]) < 1e-6
     assert got["dmu"][5] == pytest.approx(om.layer_regs[2].grad(om.mu)[5], rel=1e-5, abs=1e-7)
-
-
-def _graphs(N, K, rng, n_virtual=6, n_edges=60):
-    graphs = []
-    for k in range(K):
-        el = []
-        for _ in range(n_edges):
-            a, b = rng.integers(1, N + 1, size=2)
-            if a != b:
-                el.append([int(a), int(b), float(rng.choice([-1.0, 1.0]))])
-        for v in range(n_virtual):
-            for _ in range(3):
-                el.append([int(rng.integers(1, N + 1)), f"virt{k}_{v}", 1.0])
-        el.append([f"virt{k}_0", f"virt{k}_1", -1.0])
-        graphs.append(el)
-    return graphs
 
 
 def test_network_and_selective_l1_regularisers():

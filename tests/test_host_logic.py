@@ -239,3 +239,106 @@ def test_batch_order_planner_bookkeeping():
     _check_plan(300, 40, [(5, 40)], [2], [np.r_[np.zeros(299, int), 1]])
     with pytest.raises(_lib.PmfError):
         _check_plan(10, 10, [(0, 10)], [2], [np.full(10, 2)])         # batch id out of range
+
+
+def _pair_with_regs(seed=11):
+    from tests.helpers import make_pair, random_graphs as _graphs
+    rng = np.random.default_rng(seed)
+    views = {"mutation": ("bernoulli", 30), "methylation": ("normal", 50), "counts": ("poisson", 25)}
+    K, N = 5, 105
+    g = _graphs(N, K, rng)
+    model, om, D = make_pair(90, views, K=K, seed=seed, batch_views=["methylation", "counts"], n_batches=4,
+                             n_conditions=3, missing=0.2, lambda_X_l2=0.7, feature_graphs=g,
+                             lambda_Y_selective_l1=0.3, lambda_Y_graph=0.9)
+    return model, om, D
+
+
+def test_reweight_eb_matches_the_restatement():
+    """reweight_eb! (src/regularizers.jl) on every regulariser the model constructor can produce: the mirror's
+    float32 objects against the oracle's float64 restatement, plus the closed forms."""
+    model, om, D = _pair_with_regs()
+    mf = model.matfac
+    P.reweight_eb(mf.X_reg, mf.X)
+    O.reweight_eb(om.X_reg, om.X)
+    P.reweight_eb(mf.Y_reg, mf.Y)
+    O.reweight_eb(om.Y_reg, om.Y)
+    # X: slots (L2, Group by condition, Zero) with mixture 1/2 each
+    l2, grp = mf.X_reg.regularizers[0], mf.X_reg.regularizers[1]
+    assert np.allclose(l2.weights, om.X_reg.regularizers[0].weights, rtol=1e-4)
+    assert np.allclose(l2.weights, 0.5 / np.linalg.norm(om.X, 2) ** 2, rtol=1e-4)
+    for w, wref, r in zip(grp.group_weights, om.X_reg.regularizers[1].group_weights, grp.group_idx):
+        assert np.allclose(w, wref, rtol=1e-4)
+        assert np.allclose(w, 0.5 / np.linalg.norm(om.X[:, r.start:r.stop], 2) ** 2, rtol=1e-4)
+    # Y: slots (Group by view, SelectiveL1, Network), mixture 1/3 each
+    gy, sl1, net = mf.Y_reg.regularizers
+    ogy, osl1, onet = om.Y_reg.regularizers
+    for w, wref in zip(gy.group_weights, ogy.group_weights):
+        assert np.allclose(w, wref, rtol=1e-4)
+    assert np.allclose(sl1.weight, osl1.weight, rtol=1e-4)
+    assert np.allclose(net.cur_weights, onet.cur_weights, rtol=1e-4)
+    assert np.allclose(net.cur_weights, (1 / 3) / np.var(om.Y, axis=1, ddof=1), rtol=1e-4)
+    for k in range(len(net.AA)):
+        for a, b in ((net.AA, onet.AA), (net.AB, onet.AB), (net.BB, onet.BB)):
+            assert np.allclose(a[k].toarray(), b[k].toarray(), rtol=2e-4, atol=1e-7)
+    # layer regularisers: ColParamReg on logsigma / mu, BatchArrayReg on logdelta / theta
+    P.reweight_eb(mf.col_transform_reg, mf.col_transform)
+    O.reweight_eb(om.layer_regs, [om.logsigma, om.logdelta, om.mu, om.theta])
+    for slot in (0, 2):
+        assert np.allclose(mf.col_transform_reg.regs[slot].weights, om.layer_regs[slot].weights, rtol=1e-4)
+        assert np.allclose(mf.col_transform_reg.regs[slot].centers, om.layer_regs[slot].centers, rtol=1e-4, atol=1e-6)
+    for slot in (1, 3):
+        for w, wref in zip(mf.col_transform_reg.regs[slot].weights, om.layer_regs[slot].weights):
+            assert np.allclose(w, wref, rtol=2e-4)
+    mu_reg = mf.col_transform_reg.regs[2]
+    r0 = mu_reg.col_ranges[0]
+    assert np.isclose(mu_reg.weights[0], 0.6 / (0.1 + 0.5 * np.var(om.mu[r0.start:r0.stop], ddof=1)), rtol=1e-4)
+    # ARD: fixed hyper-parameters; a frozen layer has no method
+    ard = P.ARDRegularizer(model.feature_views)
+    P.reweight_eb(ard, mf.Y)
+    assert ard.alpha == [0.001] * 3 and ard.beta == [0.001] * 3
+    P.freeze_layer(mf.col_transform, 1)
+    with pytest.raises(TypeError):
+        P.reweight_eb(mf.col_transform_reg, mf.col_transform)
+
+
+def test_whiten_rotate_reorder_keep_the_fit():
+    """whiten! / rotate_by_svd! / reorder_by_importance! (src/fit.jl:504-555) re-parametrise the factors without
+    changing the fitted link-space prediction; the mirror agrees with the oracle's restatement."""
+    model, om, D = _pair_with_regs(seed=12)
+    mf = model.matfac
+    z_before = O.forward(om)
+
+    def check(tol=2e-4):
+        assert np.allclose(mf.X, om.X, rtol=tol, atol=tol) and np.allclose(mf.Y, om.Y, rtol=tol, atol=tol)
+        assert np.allclose(mf.col_transform.layers[0].logsigma, om.logsigma, rtol=tol, atol=tol)
+        assert np.allclose(O.forward(om), z_before, rtol=1e-8, atol=1e-8)
+
+    P.whiten(model)
+    O.whiten(om, model.feature_views)
+    check()
+    assert np.allclose(np.sqrt(np.mean(mf.X ** 2, axis=1)), 1, rtol=1e-5)
+    for cr in util.ids_to_ranges(list(model.feature_views)):
+        assert np.isclose(np.sqrt(np.mean(mf.Y[:, cr.start:cr.stop] ** 2, axis=1)).max(), 1, rtol=1e-5)
+    P.rotate_by_svd(model)
+    O.rotate_by_svd(om)
+    # singular vectors are defined up to a sign per factor: align before comparing
+    sgn = np.sign(np.sum(mf.Y * om.Y, axis=1))
+    om.X, om.Y = om.X * sgn[:, None], om.Y * sgn[:, None]
+    check(tol=1e-3)
+    gram = mf.Y @ mf.Y.T
+    assert np.allclose(gram - np.diag(np.diag(gram)), 0, atol=1e-3 * np.abs(gram).max())
+    # shuffle the factors, then sort them back by importance
+    shuffle = np.random.default_rng(3).permutation(mf.Y.shape[0])
+    for obj in (mf, om):
+        obj.X, obj.Y = obj.X[shuffle].copy(), obj.Y[shuffle].copy()
+    w_before = mf.X_reg.regularizers[0].weights.copy()
+    w_before[:] = np.arange(len(w_before))
+    mf.X_reg.regularizers[0].weights[...] = w_before
+    om.X_reg.regularizers[0].weights = w_before.astype(float)
+    idx = P.reorder_by_importance(model)
+    idx_ref = O.reorder_by_importance(om)
+    assert list(idx) == list(idx_ref)
+    assert np.all(np.diff(np.sum(mf.Y ** 2, axis=1)) <= 0)
+    assert np.array_equal(mf.X_reg.regularizers[0].weights, w_before[idx])
+    assert np.array_equal(om.X_reg.regularizers[0].weights, w_before[idx])
+    check(tol=1e-3)
