@@ -29,6 +29,13 @@ def _jl(a):
     return np.ascontiguousarray(np.asarray(a, dtype=np.float32).T)
 
 
+def _jl_out(a):
+    """Writable [cols][rows] float32 view of a column-major (rows, cols) array -- a download can land in the
+    array's own memory -- or None when the array is not laid out that way."""
+    t = a.T
+    return t if (a.dtype == np.float32 and t.flags["C_CONTIGUOUS"] and t.flags["WRITEABLE"]) else None
+
+
 class AdaGrad:
     """Flux.Optimise.AdaGrad(lr) as built by construct_optimizer (src/fit.jl:41-43).  The
     accumulators live on the device (libpmf handle); a new AdaGrad object means fresh state,
@@ -257,11 +264,14 @@ class Engine:
     def pull_params(self):
         """Write the fitted parameters back into the host model (in place)."""
         mf = self.model.matfac
-        X = np.empty((self.M, self.K), np.float32)
-        Y = np.empty((self.N, self.K), np.float32)
+        x_own, y_own = _jl_out(mf.X[:, self.rows.start:self.rows.stop]), _jl_out(mf.Y)
+        X = x_own if x_own is not None else np.empty((self.M, self.K), np.float32)
+        Y = y_own if y_own is not None else np.empty((self.N, self.K), np.float32)
         self._ck(self.lib.pmf_get_factors(self.h, fptr(X), fptr(Y)))
-        mf.X[:, self.rows.start:self.rows.stop] = X.T
-        mf.Y[...] = Y.T
+        if x_own is None:
+            mf.X[:, self.rows.start:self.rows.stop] = X.T
+        if y_own is None:
+            mf.Y[...] = Y.T
         ls = np.empty(self.N, np.float32)
         mu = np.empty(self.N, np.float32)
         self._ck(self.lib.pmf_get_col_params(self.h, fptr(ls), fptr(mu)))

@@ -49,8 +49,10 @@ class MatFacModel:
         rng = np.random.default_rng(0) if rng is None else rng
         # MatFac.jl's random init is external and unreproducible; callers that need parity set
         # X and Y explicitly
-        self.X = (rng.standard_normal((K, M)) * 0.01).astype(np.float32)
-        self.Y = (rng.standard_normal((K, N)) * 0.01).astype(np.float32)
+        # column-major like the reference's K x M / K x N Julia arrays: the device layout ([M][K], [N][K]) is then
+        # the arrays' own memory and uploads / downloads need no transposed copy
+        self.X = np.asfortranarray((rng.standard_normal((K, M)) * 0.01).astype(np.float32))
+        self.Y = np.asfortranarray((rng.standard_normal((K, N)) * 0.01).astype(np.float32))
         self.col_transform = col_transform
         self.X_reg = X_reg
         self.Y_reg = Y_reg

@@ -62,7 +62,7 @@ def transform(model, D, feature_ids=None, sample_ids=None, verbosity=1, print_pr
     mf.Y_reg = ZeroReg()                                   # Y is not updated: drop its regulariser
     set_layer(mf.col_transform, 2, Identity())             # batch effects are ignored on new data
     set_layer(mf.col_transform, 4, Identity())
-    mf.X = np.zeros((K, M_new), dtype=np.float32)
+    mf.X = np.zeros((K, M_new), dtype=np.float32, order="F")
     mf.X_reg = ZeroReg()
     new_model.sample_ids = sample_ids
     new_model.sample_conditions = None
