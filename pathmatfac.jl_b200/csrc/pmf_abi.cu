@@ -203,10 +203,9 @@ int pmf_create(const pmf_dims* d, pmf_handle* out) {
         delete h;
         return fail(nullptr, PMF_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
     }
-    cudaDeviceProp prop;
-    cudaGetDeviceProperties(&prop, d->device);
-    h->n_sms = prop.multiProcessorCount;
-    h->cc_major = prop.major;
+    // two attribute queries, not cudaGetDeviceProperties (which fills ~100 fields and costs milliseconds per handle)
+    cudaDeviceGetAttribute(&h->n_sms, cudaDevAttrMultiProcessorCount, d->device);
+    cudaDeviceGetAttribute(&h->cc_major, cudaDevAttrComputeCapabilityMajor, d->device);
     cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
     h->stream = h->own_stream;
     cudaEventCreate(&h->ev0);
