@@ -335,9 +335,14 @@ int pmf_set_noise(pmf_handle h, int32_t n_ranges, const int32_t* cs, const int32
             w += 30 * (n_present - 1);
             cum[jt + 1] = cum[jt] + w;
         }
-        h->tile_cost_host.resize(n_jt);
-        for (int jt = 0; jt < n_jt; ++jt) h->tile_cost_host[jt] = cum[jt + 1] - cum[jt];
-        h->tcb_valid = false;
+        // the batch-path plan depends on the noise models only through these costs: a call that merely refreshes
+        // the column weights (every mf_fit! on a resident model) keeps it
+        std::vector<int32_t> cost(n_jt);
+        for (int jt = 0; jt < n_jt; ++jt) cost[jt] = cum[jt + 1] - cum[jt];
+        if (cost != h->tile_cost_host) {
+            h->tile_cost_host.swap(cost);
+            h->tcb_valid = false;
+        }
         dev_free(h->tc_cost_cum);
         CU(h, dev_alloc(&h->tc_cost_cum, (size_t)n_jt + 1));
         CU(h, cudaMemcpy(h->tc_cost_cum, cum.data(), ((size_t)n_jt + 1) * 4, cudaMemcpyHostToDevice));
