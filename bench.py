@@ -187,6 +187,11 @@ def cpu_iterations(model, sample_rows, steps, warmup):
     return sum(ts) / len(ts)
 
 
+def workload_name(M, N, K):
+    return (f"C2 (BASELINE configs[1]): {M}x{N} K={K}, bernoulli/normal/normal/poisson views, "
+            f"{int(C2['missing'] * 100)}% missing, L2 on X, per-view L2 on Y, column-layer regs")
+
+
 def run_reference(args):
     """`--impl reference`: the reference's CPU implementation of the path.  Julia and MatFac.jl
     are not available in this image, so this times the CPU restatement (the oracle,
@@ -207,7 +212,9 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": steps, "warmup": warm, "ms_per_step": sec * scale * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"C2 {args.M}x{args.N} K={args.K} mixed bernoulli/normal/poisson 30% missing",
+            "config": {"workload": workload_name(args.M, args.N, args.K), "per_rank_samples": args.M,
+                       "parallelism": "host CPU, all cores (NumPy / BLAS threads)",
+                       "value_definition": "C2-equivalent iterations/sec",
                        "note": "Julia/MatFac.jl unavailable: CPU restatement of the reference algorithm (oracle)"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{Ms} of {args.M} samples x all {args.N} features, {steps} timed iterations, "
@@ -393,9 +400,7 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": sec_per_step * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"C2 (BASELINE configs[1]): {M}x{N} K={K}, bernoulli/normal/normal/poisson views, "
-                                   f"{int(C2['missing'] * 100)}% missing, L2 on X, per-view L2 on Y, column-layer regs",
-                       "per_rank_samples": M, "parallelism": f"sample-sharded x{world}" if world > 1 else "single GPU",
+            "config": {"workload": workload_name(M, N, K), "per_rank_samples": M, "parallelism": f"sample-sharded x{world}" if world > 1 else "single GPU",
                        "kernel": args.kernel, "precision": args.precision,
                        "l2_flush": "inputs (1.2 GB of A per step) exceed the 126 MB L2",
                        "value_definition": "C2-equivalent iterations/sec = n_gpus / seconds per step"},
