@@ -363,3 +363,22 @@ def test_fit_loop_contract():
     assert last < first
     for a, b in zip(hist[:-1], hist[1:]):
         assert a["term_code"] == "loss_increase" and np.isclose(b["lr"], a["lr"] * 0.5)
+
+
+def test_m_estimates_closed_forms():
+    """compute_M_estimates (src/fit.jl:88-92, restated): the shift that minimises a column's noise-model loss has a
+    closed form for the three exponential-family models -- mean, logit(mean), log(mean) of the observed entries --
+    and the restated AdaGrad loop converges to it."""
+    om, D, meta = O.simulate_model(200, {"mutation": ("bernoulli", 20), "methylation": ("normal", 30), "counts": ("poisson", 15)},
+                                   3, 41, batch_views=["methylation"], n_batches=3, missing=0.2)
+    mu_before = om.mu.copy()
+    est, h = O.compute_M_estimates(om, D, lr=0.5, max_epochs=3000, rel_tol=0.0, abs_tol=0.0)
+    assert np.array_equal(om.mu, mu_before)                     # the model itself is untouched
+    m = np.nanmean(D, axis=0)
+    assert np.allclose(est[20:50], m[20:50], atol=1e-6)
+    ok = (m[:20] > 0.02) & (m[:20] < 0.98)
+    assert np.allclose(est[:20][ok], np.log(m[:20][ok] / (1 - m[:20][ok])), atol=1e-4)
+    assert np.allclose(est[50:], np.log(m[50:]), atol=1e-6)
+    assert h["loss"][-1] <= h["loss"][0]
+    O.init_mu(om, D, lr_mu=0.5, max_epochs=50)
+    assert not np.array_equal(om.mu, mu_before)
