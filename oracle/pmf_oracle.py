@@ -1118,6 +1118,23 @@ def reorder_reg(reg, perm):
             opt.lam = opt.lam[perm]
 
 
+def init_ordinal_thresholds(m: OracleModel, D: np.ndarray) -> None:
+    """``init_ordinal_thresholds!`` (src/fit.jl:222-246) with ``rec_set_thresholds`` (:190-219) and ``inv_logistic``
+    (src/util.jl:8-10).  ``p_vec[2:1-end]`` in the reference is an empty range, so only the outermost pair of level
+    probabilities is ever used -- which is all a three-level model has."""
+    def inv_logistic(x):
+        return math.log(0.5 + 0.99 * (x / (1.0 - x) - 0.5))
+    for r, dist, th in zip(m.noise.col_ranges, m.noise.dists, m.noise.thresholds):
+        if dist != "ordinal3":
+            continue
+        levels = len(th) - 1
+        block = D[:, r.start:r.stop]
+        p = np.array([float(np.sum(block == k)) + 1.0 for k in range(1, levels + 1)])
+        p /= p.sum()
+        if len(p) >= 2:
+            th[1:-1] = [inv_logistic(p[0]), inv_logistic(1.0 - p[-1])]
+
+
 def whiten(m: OracleModel, feature_views) -> None:
     """``whiten!`` (src/fit.jl:504-528)."""
     x_rms = np.sqrt(np.mean(m.X * m.X, axis=1, keepdims=True))

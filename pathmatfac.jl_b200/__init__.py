@@ -10,7 +10,8 @@ from .layers import (BatchArray, BatchScale, BatchShift, ColScale, ColShift, Fro
                      ViewableComposition, construct_model_layers, freeze_layer, unfreeze_layer)
 from .model import CompositeNoise, MatFacModel, PathMatFacModel
 from .transform import transform
-from .postfit import reorder_by_importance, reorder_reg, reweight_eb, rotate_by_svd, whiten
+from .postfit import (init_ordinal_thresholds, reorder_by_importance, reorder_reg, reweight_eb, rotate_by_svd,
+                      whiten)
 from .regularizers import (ARDRegularizer, BatchArrayReg, ColParamReg, CompositeRegularizer,
                            FeatureSetARDReg, FrozenRegularizer, GroupRegularizer, L2Regularizer,
                            NetworkRegularizer, SelectiveL1Reg, SequenceReg, ZeroReg,

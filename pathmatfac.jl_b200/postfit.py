@@ -171,3 +171,37 @@ def reorder_by_importance(model):
     reorder_reg(mf.X_reg, idx)
     _resync(model)
     return idx
+
+
+def inv_logistic(x):
+    """src/util.jl:8-10 (the reference's damped logit)."""
+    x = f32(x)
+    return f32(np.log(f32(0.5) + f32(0.99) * (x / (f32(1) - x) - f32(0.5))))
+
+
+def rec_set_thresholds(p_vec, l_p, r_p):
+    """src/fit.jl:190-219.  The reference drops ALL remaining probabilities after the first step
+    (``p_vec[2:1-end]`` is an empty range), so the result has two thresholds -- exactly what its only ordinal
+    model, three levels, needs."""
+    if len(p_vec) < 2:
+        return []
+    l_p = f32(l_p) + f32(p_vec[0])
+    r_p = f32(r_p) + f32(p_vec[-1])
+    return [inv_logistic(l_p)] + rec_set_thresholds([], l_p, r_p) + [inv_logistic(f32(1) - r_p)]
+
+
+def init_ordinal_thresholds(model):
+    """``init_ordinal_thresholds!`` (src/fit.jl:222-246): interior thresholds of every OrdinalNoise range from the
+    add-one-smoothed level frequencies of its columns."""
+    nm = model.matfac.noise_model
+    for n, cr in zip(nm.noises, nm.col_ranges):
+        if n.dist != "ordinal3":                       # isa(n, MF.OrdinalNoise); the squared-hinge variant is left alone
+            continue
+        levels = len(n.ext_thresholds) - 1
+        block = model.data[:, cr.start:cr.stop]
+        p = np.array([np.sum(block == f32(k)) + 1 for k in range(1, levels + 1)], dtype=f32)
+        p /= p.sum()
+        n.ext_thresholds[1:-1] = rec_set_thresholds(list(p), 0.0, 0.0)
+    if model._engine is not None:
+        model._engine.push_structure()
+

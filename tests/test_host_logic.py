@@ -342,3 +342,27 @@ def test_whiten_rotate_reorder_keep_the_fit():
     assert np.array_equal(mf.X_reg.regularizers[0].weights, w_before[idx])
     assert np.array_equal(om.X_reg.regularizers[0].weights, w_before[idx])
     check(tol=1e-3)
+
+
+def test_init_ordinal_thresholds():
+    """init_ordinal_thresholds! (src/fit.jl:190-246): add-one-smoothed level frequencies -> the reference's damped
+    logits; only OrdinalNoise ranges are touched; mirror and oracle agree."""
+    from tests.helpers import make_pair
+    views = {"mrnaseq": ("normal", 12), "cna": ("ordinal3", 20), "methylation": ("ordinal_sq_hinge3", 9)}
+    model, om, D = make_pair(80, views, K=3, seed=17, missing=0.25)
+    nm = model.matfac.noise_model
+    before = [None if n.ext_thresholds is None else n.ext_thresholds.copy() for n in nm.noises]
+    P.init_ordinal_thresholds(model)
+    O.init_ordinal_thresholds(om, D)
+    dists = [n.dist for n in nm.noises]
+    i3, ih = dists.index("ordinal3"), dists.index("ordinal_sq_hinge3")
+    assert np.array_equal(nm.noises[ih].ext_thresholds, before[ih])                 # not an OrdinalNoise
+    th = nm.noises[i3].ext_thresholds
+    assert th[0] == -np.inf and th[-1] == np.inf and th[1] < th[2]
+    assert np.allclose(th[1:-1], om.noise.thresholds[om.noise.dists.index("ordinal3")][1:-1], rtol=1e-5)
+    cr = nm.col_ranges[i3]
+    block = D[:, cr.start:cr.stop]
+    cnt = np.array([np.sum(block == k) + 1 for k in (1, 2, 3)], float)
+    p = cnt / cnt.sum()
+    logit = lambda x: np.log(0.5 + 0.99 * (x / (1 - x) - 0.5))
+    assert np.allclose(th[1:-1], [logit(p[0]), logit(1 - p[2])], rtol=1e-5)
