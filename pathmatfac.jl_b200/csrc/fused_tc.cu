@@ -11,7 +11,9 @@
 //            a per-thread register and every column-gradient sum a private accumulator):
 //            ColScale/ColShift, noise loss, dL/dz with the NaN mask (src/layers.jl:9-90, SURVEY.md
 //            Appendix B).  dL/dz goes back to TMEM in place of Z and, with 128-bit stores, into shared
-//            memory IN PLACE of the A values the same thread just read.
+//            memory IN PLACE of the A values the same thread just read.  BATCH instantiation: BatchScale /
+//            BatchShift too (src/layers.jl:95-214) -- the batch parameters are per-thread registers that change
+//            between 16-sample chunks, over sample orders / passes planned on the host (TcBatchDev).
 //   MMA2  dX[i,k]  = sum_j G[j,i] Ys[j,k]    A = G in smem read MN-major (M = 64 samples), B = Ys = w_j sigma_j Y
 //                                            in smem read MN-major -- no transposed copies exist
 //   MMA3  dY[j,k] += sum_i G[j,i] X[i,k]     A = G in TMEM, B = a second copy of the Xh tile read MN-major
@@ -385,7 +387,7 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
 
     if (warp == W_TMA_A || warp == W_TMA_X) {
         // ================================ TMA producers ===========================================
-        // Warp 0 streams the A tiles (HBM); warp 2 feeds both X operand buffers (L2): the K-major pair
+        // Warp W_TMA_A streams the A tiles (HBM); warp W_TMA_X feeds both X operand buffers (L2): the K-major pair
         // (Xh | Xl) of tile t, then the MN-major Xh copy of tile t-2 -- the order in which MMA1 (two tiles
         // ahead) and MMA3 consume them, so neither load waits behind a buffer that is released later.
         if (lane == 0 && warp == W_TMA_A) {
@@ -722,7 +724,7 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
             const int ci = cur.ci;
             const int dist = ci & 0xff;
             const float* th_range = dp.thresholds + 4 * (ci >> 8);
-            // G0 = (w_j sigma_j) * dloss/dz4 (no batch layers on this path).  The per-feature factor never
+            // G0 = (w_j sigma_j) * dloss/dz4 (times delta_bj with batch layers, folded into the entries).  The per-feature factor never
             // touches the per-entry path: MMA2 reads Yh scaled by it, the dY tile is scaled at the flush.
             const float gscale = sigma * wj;
             float dmu_acc = 0.f, loss_acc = 0.f;   // unweighted sums over this item (<= a few thousand terms)
