@@ -366,3 +366,32 @@ def test_init_ordinal_thresholds():
     p = cnt / cnt.sum()
     logit = lambda x: np.log(0.5 + 0.99 * (x / (1 - x) - 0.5))
     assert np.allclose(th[1:-1], [logit(p[0]), logit(1 - p[2])], rtol=1e-5)
+
+
+def test_batch_order_planner_random_layouts():
+    """Property check of the planner over random layouts (sizes, view ranges with gaps, batch counts, sorted /
+    unsorted / duplicated batch assignments): the invariants of ``_check_plan`` hold for every one."""
+    rng = np.random.default_rng(2024)
+    for trial in range(40):
+        M = int(rng.integers(1, 700))
+        N = int(rng.integers(1, 1200))
+        n_views = int(rng.integers(1, 5))
+        cuts = np.sort(rng.choice(np.arange(N + 1), size=min(2 * n_views, N + 1), replace=False))
+        ranges = [(int(cuts[2 * v]), int(cuts[2 * v + 1])) for v in range(len(cuts) // 2) if cuts[2 * v] < cuts[2 * v + 1]]
+        if not ranges:
+            continue
+        nb, bos = [], []
+        for v in range(len(ranges)):
+            k = int(rng.integers(1, 12))
+            b = rng.integers(0, k, size=M)
+            style = rng.integers(0, 4)
+            if style == 1:
+                b = np.sort(b)
+            elif style == 2 and bos:
+                b, k = bos[-1].copy(), nb[-1]                       # same assignment as the previous view
+            elif style == 3:
+                b = np.repeat(np.arange(k), 16 * (M // (16 * k) + 1))[:M]   # aligned to the 16-sample chunks
+            nb.append(k)
+            bos.append(b)
+        pl = _check_plan(M, N, ranges, nb, bos)
+        assert pl["n_orders"] <= len(ranges) + 1 and pl["n_pass"] >= (N + 127) // 128
