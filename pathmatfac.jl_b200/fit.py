@@ -60,6 +60,7 @@ class Engine:
         self.rows = range(0, M_all) if rows is None else rows
         self.M, self.N, self.K = len(self.rows), N, K
         self.h = C.c_void_p()
+        self.device = device
         dims = pmf_dims(self.M, N, K, device)
         rc = self.lib.pmf_create(C.byref(dims), C.byref(self.h))
         if rc != 0:
