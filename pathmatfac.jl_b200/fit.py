@@ -651,8 +651,10 @@ def mf_fit(model, *, scale_column_losses=False, update_X=False, update_Y=False, 
         h["lr"] = opt.eta
         if verbosity > 1:
             print(f"{print_prefix}mf_fit: epochs={h['epochs']} term={h['term_code']} loss={h['loss'][-1] if h['loss'] else None}")
+        # The host copy of the parameters is current after every fit, resident model or not: the steps between fits
+        # (reweight_eb!, whiten!, the statistics passes' save / restore of X and Y) work on it.
+        eng.pull_params()
         if transient:
-            eng.pull_params()
             opt._owner = None
         h["h2d_bytes"], h["d2h_bytes"] = eng.h2d_bytes, eng.d2h_bytes
         return h

@@ -144,13 +144,16 @@ def init_batch_effects(model, max_epochs=5000, lr_regress=0.25, lr_mu=0.1, lr_th
         N = orig.Y.shape[1]
         sur.X = np.asfortranarray(cond.T.copy())
         sur.Y = np.zeros((k_cond, N), dtype=f32, order="F")
-        sur.X_reg = ZeroReg()                     # X is data here; its K no longer matches the original penalty
+        # X is data here and K is the number of conditions: the original factor penalties (K-sized weight vectors) do
+        # not apply to the stand-in.  The reference drops Y_reg after init_mu! (whose M-estimation ignores penalties).
+        sur.X_reg = ZeroReg()
+        sur.Y_reg = ZeroReg()
         model.matfac = sur
 
         backend.init_mu(model, lr_mu=lr_mu, max_epochs=max_epochs, history=history)
         orig.col_transform.unwrapped(2).mu[...] = sur.col_transform.unwrapped(2).mu
 
-        sur.Y_reg = ZeroReg()                                                        # regress on the conditions
+        # regress every column on the conditions (no penalty)
         backend.mf_fit_adapt_lr(model, max_epochs=max_epochs, lr=lr_regress, min_lr=0.05, update_X=False, update_Y=True,
                                 update_col_layers=False, history=history)
         _note(history, "regress_against_sample_conditions")
@@ -176,8 +179,9 @@ def init_batch_effects(model, max_epochs=5000, lr_regress=0.25, lr_mu=0.1, lr_th
 
         theta_values = theta.values
         if batch_method in ("EM", "EB"):
-            theta_values, delta2 = backend.theta_delta_em(model, delta2, col_vars, update_priors=batch_method == "EM",
-                                                          batch_em_max_iter=batch_em_max_iter, batch_em_rtol=batch_em_rtol)
+            res = backend.theta_delta_em(model, delta2, col_vars, update_priors=batch_method == "EM",
+                                         batch_em_max_iter=batch_em_max_iter, batch_em_rtol=batch_em_rtol)
+            theta_values, delta2 = res[0], res[1]              # (theta, delta^2[, relative changes per iteration])
     finally:
         model.matfac = orig
     ct = orig.col_transform
