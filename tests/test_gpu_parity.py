@@ -1,6 +1,8 @@
 """Parity of the CUDA path (through the host mirror and the C ABI) against the CPU oracle.
 Tolerance: north_star asks for per-iteration loss and gradients within 1e-4 relative in FP32;
 gradients are compared norm-wise (||g - g_ref|| / ||g_ref||), losses relatively."""
+import os
+
 import numpy as np
 import pytest
 
@@ -614,3 +616,28 @@ def test_theta_delta_em():
     for v in range(2):
         assert relerr(th[v], th_ref[v]) < 1e-3 and relerr(d2[v], d2_ref[v]) < 1e-3
     assert abs(diffs[-1] - diffs_ref[-1]) <= 1e-2 * abs(diffs_ref[-1]) + 1e-9
+
+
+@pytest.mark.skipif(os.environ.get("PMF_TEST_STAGING", "0") in ("", "0"),
+                    reason="the stage functions have only run on the CPU so far (tests/test_staging_cpu.py); opt in with PMF_TEST_STAGING=1")
+def test_staging_fit_on_device():
+    """fit! (staging.py) end to end on the device backend: same orchestration as tests/test_staging_cpu.py, the calls
+    served by libpmf.  Checks the post-conditions of the procedure and that the fitted model explains the data about as
+    well as the CPU run of the same procedure on a twin model."""
+    from pathmatfac_b200 import staging as S
+    from tests import oracle_backend as OB
+    views = {"methylation": ("normal", 60), "mrnaseq": ("normal", 50)}
+    kw = dict(K=4, seed=36, batch_views=["methylation"], n_batches=3, n_conditions=2, missing=0.1, lambda_X_l2=1.0)
+    model, om, D = make_pair(150, views, **kw)
+    twin, _, _ = make_pair(150, views, **kw)
+    hist = S.fit(model, lr=0.2, max_epochs=30, keep_history=True)
+    S.fit(twin, lr=0.2, max_epochs=30, backend=OB.BACKEND)
+    mf = model.matfac
+    assert model._engine is None
+    assert np.allclose(np.sqrt(np.mean(mf.X ** 2, axis=1)), 1, rtol=1e-3)
+    assert np.all(np.diff(np.sum(mf.Y ** 2, axis=1)) <= 1e-5)
+    assert all(np.all(np.isfinite(v)) for v in mf.col_transform.layers[3].theta.values)
+    assert [h["name"] for h in hist if h.get("name") in ("start", "finish")] == ["start", "finish"]
+    loss = lambda m: O.data_loss_grads(OB.to_oracle(m)[0], D, want_grads=False)["loss"]
+    assert loss(model) <= 1.2 * loss(twin)
+
