@@ -258,7 +258,6 @@ def fit_non_ard(model, fit_reg_weight="EB", lambda_max=None, n_lambda=8, lambda_
     if fit_reg_weight == "EB":
         basic_fit_reg_weight_eb(model, backend=backend, **kwargs)
     else:
-        kwargs.pop("svd_rotate", None)
         basic_fit(model, fit_mu=True, fit_logsigma=True, reweight_losses=True, fit_batch=_has_batch_layers(model),
                   fit_factors=True, backend=backend, **kwargs)
 
@@ -316,14 +315,16 @@ def fit(model, lr=1.0, fit_reg_weight="EB", n_lambda=8, lambda_max=None, lambda_
         mf = model.matfac
         common = dict(history=hist, rel_tol=rel_tol, abs_tol=abs_tol, svd_rotate=svd_rotate, max_epochs=max_epochs,
                       backend=backend, **kwargs)
+        # `lr` reaches only the feature-set branch and the joint adjustment: fit! names it as a keyword of its own
+        # and does not hand it to fit_ard! / fit_non_ard!, which therefore run at their default of 1.0 (:962-1001)
         if isinstance(mf.Y_reg, ARDRegularizer):
-            fit_ard(model, lr=lr, **common)
+            fit_ard(model, **common)
         elif isinstance(mf.Y_reg, FeatureSetARDReg):
             fit_feature_set_ard(model, lr=lr, fsard_max_iter=fsard_max_iter, fsard_max_A_iter=fsard_max_A_iter,
                                 fsard_term_rtol=fsard_term_rtol, **common)
         else:
             fit_non_ard(model, fit_reg_weight=fit_reg_weight, lambda_max=lambda_max, n_lambda=n_lambda,
-                        lambda_min_frac=lambda_min_frac, lr=lr, **common)
+                        lambda_min_frac=lambda_min_frac, **common)
         if fit_joint:                                               # let the fitted parameters share information
             ct = mf.col_transform
             freeze_layer(ct, [1, 2, 3])
