@@ -106,7 +106,9 @@ def init_factors(model, lr=1.0, max_epochs=1000, init_factors_method="adagrad", 
 
 def construct_minimal_regularizer(model):
     """``construct_minimal_regularizer`` (src/regularizers.jl:750-774): one L2 group per noise model, weighted by
-    K, the mean sigma^2 of the group's columns and the density of its data."""
+    K, the mean sigma^2 of the group's columns and the density of its data.  ``MF.batched_column_nanvar`` lives in
+    MatFac.jl (not in the tree); taken as the corrected variance over the finite entries, like the reference's own
+    ``nanvar`` (src/util.jl:38-40)."""
     mf = model.matfac
     K, M = mf.X.shape
     nm = mf.noise_model
