@@ -255,7 +255,8 @@ def main():
     if world > 1:   # replicated parameters must be identical on every rank
         import torch.distributed as dist
         for arr in (model.matfac.Y, model.matfac.col_transform.layers[0].logsigma, model.matfac.col_transform.layers[2].mu):
-            t = torch.from_numpy(arr).cuda()
+            # Y is column-major on the host (model.py); NCCL broadcasts contiguous tensors only
+            t = torch.from_numpy(np.ascontiguousarray(arr)).cuda()
             dist.broadcast(t, 0)
             arr[...] = t.cpu().numpy()
     X0, Y0 = model.matfac.X.copy(), model.matfac.Y.copy()

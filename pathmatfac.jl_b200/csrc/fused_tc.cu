@@ -411,9 +411,13 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
             int pend[2] = {-1, -1};       // sample offsets of the last two tiles whose MN-major copy is still due
             auto load_xm = [&](int i0) {
                 mbar_wait(bar(B_EMPTY_XM + rm.s), rm.ph ^ 1);
-                mbar_expect_tx(bar(B_FULL_XM + rm.s), XM_BYTES);
-                for (int kb = 0; kb < 2; ++kb)
-                    tma_load_2d(XM + rm.s * XM_BYTES + kb * 8192, &tmXm, bar(B_FULL_XM + rm.s), 32 * kb, i0);
+                if (DBG && (p.ablate & 128)) {       // experiment: no L2 -> shared-memory traffic for the MN-major copy
+                    mbar_arrive(bar(B_FULL_XM + rm.s));
+                } else {
+                    mbar_expect_tx(bar(B_FULL_XM + rm.s), XM_BYTES);
+                    for (int kb = 0; kb < 2; ++kb)
+                        tma_load_2d(XM + rm.s * XM_BYTES + kb * 8192, &tmXm, bar(B_FULL_XM + rm.s), 32 * kb, i0);
+                }
                 rm.next(SXM);
             };
             for (ItemIter itx(p); itx.next();) {
@@ -422,11 +426,15 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
                 for (int it = it0; it < it1; ++it) {
                     const int i0 = xrow0 + it * BI;
                     mbar_wait(bar(B_EMPTY_XK + rk.s), rk.ph ^ 1);
-                    mbar_expect_tx(bar(B_FULL_XK + rk.s), XK_BYTES);
-                    const uint32_t dst = XK + rk.s * XK_BYTES;
-                    for (int kb = 0; kb < 2; ++kb) {
-                        tma_load_2d(dst + kb * 8192, &tmXh, bar(B_FULL_XK + rk.s), 32 * kb, i0);
-                        tma_load_2d(dst + XH_BYTES + kb * 8192, &tmXl, bar(B_FULL_XK + rk.s), 64 * kb, i0);   // bf16 [Xh | Xl]
+                    if (DBG && (p.ablate & 64)) {    // experiment: no L2 -> shared-memory traffic for the K-major pair
+                        mbar_arrive(bar(B_FULL_XK + rk.s));
+                    } else {
+                        mbar_expect_tx(bar(B_FULL_XK + rk.s), XK_BYTES);
+                        const uint32_t dst = XK + rk.s * XK_BYTES;
+                        for (int kb = 0; kb < 2; ++kb) {
+                            tma_load_2d(dst + kb * 8192, &tmXh, bar(B_FULL_XK + rk.s), 32 * kb, i0);
+                            tma_load_2d(dst + XH_BYTES + kb * 8192, &tmXl, bar(B_FULL_XK + rk.s), 64 * kb, i0);   // bf16 [Xh | Xl]
+                        }
                     }
                     rk.next(SXK);
                     if (pend[0] >= 0) load_xm(pend[0]);

@@ -370,6 +370,19 @@ int pmf_set_batch_layout(pmf_handle h, int32_t n_views, const int32_t* cs, const
                          const int32_t* bos) {
     CHECK_H(h);
     if (n_views < 0 || (n_views > 0 && (!cs || !ce || !nb || !bos))) return fail(h, PMF_ERR_ARG, "bad batch layout");
+    // An unchanged layout is a no-op: the batch parameters, their AdaGrad accumulators, the layer penalties and the
+    // tcgen05 batch plan all survive.  Callers re-send the structure before every fit (mf_fit! on a resident model,
+    // reweight_col_losses!, the LR-halving restarts of mf_fit_adapt_lr!, src/fit.jl:46-75), where the reference keeps
+    // parameters and optimiser state.
+    if (h->layout_set && n_views == (int)h->views.size()) {
+        bool same = true;
+        for (int v = 0; v < n_views && same; ++v)
+            same = h->views[v].col_start == cs[v] && h->views[v].col_stop == ce[v] && h->views[v].n_batches == nb[v];
+        if (same && n_views > 0)
+            same = h->bos_host.size() == (size_t)n_views * h->M &&
+                   std::memcmp(h->bos_host.data(), bos, h->bos_host.size() * sizeof(int32_t)) == 0;
+        if (same) return PMF_OK;
+    }
     CU(h, cudaStreamSynchronize(h->stream));
     // keep logsigma / mu across the re-allocation
     std::vector<float> ls(h->N), mu(h->N);
@@ -416,7 +429,10 @@ int pmf_set_batch_layout(pmf_handle h, int32_t n_views, const int32_t* cs, const
         CU(h, cudaMemcpy(h->bcol_nb, cnb.data(), (size_t)h->Np * 4, cudaMemcpyHostToDevice));
         CU(h, cudaMemcpy(h->batch_of_sample, b.data(), b.size() * 4, cudaMemcpyHostToDevice));
         h->bos_host.assign(bos, bos + (size_t)n_views * h->M);
+    } else {
+        h->bos_host.clear();
     }
+    h->layout_set = true;
     return PMF_OK;
 }
 
@@ -1441,7 +1457,8 @@ int pmf_model_s::run_reg_multi(bool x_side, bool y_side, bool vectors, const int
         vec_segments(this, segs);
         for (const VecSeg& sgm : segs) {
             const unsigned bit = 1u << (sgm.slot - 1);
-            if (sgm.n <= 0 || !layer_reg_present[sgm.slot - 1] || (frozen_regs & bit)) continue;
+            // a frozen layer's ColParamReg / BatchArrayReg evaluates to 0 in the reference (src/regularizers.jl:509, :867)
+            if (sgm.n <= 0 || !layer_reg_present[sgm.slot - 1] || ((frozen_regs | frozen_layers) & bit)) continue;
             VectorUpdateParams& q = mp.v[mp.nv++];
             q.n = sgm.n; q.p = vp + sgm.off; q.grad = sg + (size_t)Np * Kp + sgm.off; q.acc = accvp + sgm.off;
             q.stop_flag = stop;

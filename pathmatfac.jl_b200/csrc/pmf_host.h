@@ -71,6 +71,7 @@ struct pmf_model_s {
     std::string err;
     bool cuda_failed = false;
     bool have_data = false, have_noise = false;
+    bool layout_set = false;                 // pmf_set_batch_layout has run (an identical layout is then a no-op)
 
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;

@@ -32,31 +32,19 @@ def shard_plan(M: int, world: int) -> List[range]:
     return [shard_rows(M, r, world) for r in range(world)]
 
 
-class _DeviceBuffer:
-    """Expose a raw device pointer to torch through __cuda_array_interface__."""
-
-    def __init__(self, ptr: int, n: int, typestr: str):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
-
-
 class ShardedFit:
-    """Drives pmf_fit_start / pmf_epoch_begin / all-reduce / pmf_epoch_end on one rank."""
+    """Drives pmf_fit_start / pmf_epoch_begin / all-reduce / pmf_epoch_end on one rank.  The engine supplies
+    ``shared_buffers()`` (torch tensors aliasing the handle's shared gradient buffer and its rank-local loss
+    scalars) and ``use_torch_stream()`` (so that the collective is ordered with the kernels); the CPU tests drive
+    the same sequence through a stub engine over gloo."""
 
     def __init__(self, engine, group=None):
-        import torch
         import torch.distributed as dist
-        self.torch, self.dist = torch, dist
+        self.dist = dist
         self.eng = engine
         self.group = group
-        lib, h = engine.lib, engine.h
-        p, n = C.c_void_p(), C.c_int64()
-        engine._ck(lib.pmf_shared_grad_buffer(h, C.byref(p), C.byref(n)))
-        dev = torch.device("cuda", torch.cuda.current_device())
-        self.grads = torch.as_tensor(_DeviceBuffer(p.value, n.value, "<f4"), device=dev)
-        engine._ck(lib.pmf_shared_scalar_buffer(h, C.byref(p), C.byref(n)))
-        self.scalars = torch.as_tensor(_DeviceBuffer(p.value, n.value, "<f8"), device=dev)
-        # run the library on torch's current stream so the collective is ordered with the kernels
-        engine.set_stream(torch.cuda.current_stream().cuda_stream)
+        self.grads, self.scalars = engine.shared_buffers()
+        engine.use_torch_stream()
 
     def fit(self, opts) -> Dict:
         eng, lib = self.eng, self.eng.lib

@@ -20,6 +20,10 @@ from .regularizers import (ARDRegularizer, BatchArrayReg, ColParamReg, Composite
 from .util import DIST_CODE
 
 
+_REG_TYPES = (ARDRegularizer, BatchArrayReg, ColParamReg, CompositeRegularizer, FeatureSetARDReg, FrozenRegularizer,
+              GroupRegularizer, L2Regularizer, NetworkRegularizer, SelectiveL1Reg, ZeroReg)
+
+
 def _f32(a, order="C"):
     return np.ascontiguousarray(a, dtype=np.float32) if order == "C" else np.asfortranarray(a, dtype=np.float32)
 
@@ -34,6 +38,30 @@ def _jl_out(a):
     array's own memory -- or None when the array is not laid out that way."""
     t = a.T
     return t if (a.dtype == np.float32 and t.flags["C_CONTIGUOUS"] and t.flags["WRITEABLE"]) else None
+
+
+def recognise_closure(r, K):
+    """The stage functions of the reference install anonymous functions as regularisers: ``X -> 0.5f0*sum(X.*X)``
+    (src/fit.jl:686), ``0.05 * sum(x.^2)``-style quadratic closures (:266-267) and the zero closures ``X -> 0f0`` /
+    ``y -> 0`` / ``x -> 0.0`` (:415, :769, src/transform.jl:61,70).  A closure has no structure to marshal, so it is
+    identified by evaluating it on probes: identically zero -> no penalty; 0.5 w sum(x^2) with one scalar w -> an
+    L2Regularizer with uniform weight w.  Anything else is an ERROR -- a penalty must never be dropped silently.
+    Returns None (zero) or the uniform L2 weight."""
+    rng = np.random.default_rng(12345)
+    probes = [np.ones((K, 3), np.float32), rng.standard_normal((K, 5)).astype(np.float32),
+              (3.0 * rng.standard_normal((K, 2))).astype(np.float32)]
+    try:
+        vals = [float(r(p)) for p in probes]
+    except Exception as e:  # noqa: BLE001
+        raise _lib.PmfError(f"regulariser closure could not be evaluated on a K x n probe: {e!r}")
+    if all(v == 0.0 for v in vals):
+        return None
+    ssq = [float((p.astype(np.float64) ** 2).sum()) for p in probes]
+    w = vals[0] / (0.5 * ssq[0])
+    if w > 0 and all(abs(v - 0.5 * w * q) <= 1e-4 * abs(0.5 * w * q) for v, q in zip(vals, ssq)):
+        return w
+    raise _lib.PmfError("unsupported regulariser closure: only `x -> 0` and `x -> 0.5*w*sum(x.*x)` (the closures "
+                        "src/fit.jl installs) can be moved to the device; use a regulariser object instead")
 
 
 class AdaGrad:
@@ -91,6 +119,28 @@ class Engine:
 
     def set_stream(self, cuda_stream_ptr: int):
         self._ck(self.lib.pmf_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
+
+    # -- host-driven exchange step (dist.ShardedFit) -----------------------------------------------
+    def shared_buffers(self):
+        """(gradients, scalars): torch tensors that alias the handle's shared gradient buffer
+        [dY | dlogsigma | dmu | dlogdelta | dtheta] (float32) and its two rank-local loss scalars (float64)."""
+        import torch
+
+        class _DeviceBuffer:   # raw device pointer -> torch through __cuda_array_interface__
+            def __init__(self, ptr, n, typestr):
+                self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+        dev = torch.device("cuda", self.device)
+        p, n = C.c_void_p(), C.c_int64()
+        self._ck(self.lib.pmf_shared_grad_buffer(self.h, C.byref(p), C.byref(n)))
+        grads = torch.as_tensor(_DeviceBuffer(p.value, n.value, "<f4"), device=dev)
+        self._ck(self.lib.pmf_shared_scalar_buffer(self.h, C.byref(p), C.byref(n)))
+        scalars = torch.as_tensor(_DeviceBuffer(p.value, n.value, "<f8"), device=dev)
+        return grads, scalars
+
+    def use_torch_stream(self):
+        """Run the library on torch's current stream of the handle's device."""
+        import torch
+        self.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
 
     # -- uploads ---------------------------------------------------------------------------
     def push_data(self, D):
@@ -192,7 +242,12 @@ class Engine:
         lo = self.rows.start if which == 0 else 0
 
         def install(r, p):
-            if r is None or isinstance(r, ZeroReg) or callable(r) or p == 0.0:
+            if r is None or isinstance(r, ZeroReg) or p == 0.0:
+                return
+            if callable(r) and not isinstance(r, _REG_TYPES):
+                w = recognise_closure(r, self.K)       # raises on anything but the reference's own closures
+                if w is not None:
+                    self._ck(lib.pmf_set_reg_l2(h, which, fptr(np.full(self.K, w, np.float32)), p))
                 return
             if isinstance(r, L2Regularizer):
                 self._ck(lib.pmf_set_reg_l2(h, which, fptr(_f32(r.weights)), p))

@@ -395,3 +395,17 @@ def test_batch_order_planner_random_layouts():
             bos.append(b)
         pl = _check_plan(M, N, ranges, nb, bos)
         assert pl["n_orders"] <= len(ranges) + 1 and pl["n_pass"] >= (N + 127) // 128
+
+
+def test_closure_regularisers_are_recognised_or_refused():
+    """The anonymous regularisers src/fit.jl installs (:266-267, :415, :686, :769; src/transform.jl:61,70) are
+    identified by probing; any other closure is an error, never a silently dropped penalty."""
+    from pathmatfac_b200 import _lib
+    from pathmatfac_b200.fit import recognise_closure
+    assert recognise_closure(lambda X: np.float32(0.5) * np.sum(X * X), 6) == pytest.approx(1.0)
+    assert recognise_closure(lambda X: 0.05 * np.sum(X ** 2), 9) == pytest.approx(0.1)
+    assert recognise_closure(lambda X: 0.0, 4) is None
+    assert recognise_closure(lambda y: 0, 4) is None
+    for bad in (lambda X: np.sum(np.abs(X)), lambda X: 0.5 * np.sum(X * X) + 1.0, lambda X: np.sum(X ** 4), lambda X: X[99, 0]):
+        with pytest.raises(_lib.PmfError):
+            recognise_closure(bad, 5)
