@@ -5,7 +5,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["pmf_abi.cu", "fused_ffma.cu", "reg_update.cu", "fsard.cu", "fused_tc.cu"]
+SOURCES = ["pmf_abi.cu", "fused_ffma.cu", "reg_update.cu", "fsard.cu", "fused_tc.cu", "wide_tc.cu"]
 OUT = os.path.join(HERE, "libpmf.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-ldl",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -23,9 +23,11 @@ def build(force=False, verbose=False):
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
     if not force and not _stale():
         return OUT
-    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + srcs
+    tmp = OUT + ".tmp"       # link into a temporary name: a snapshot of the tree never sees a half-written library
+    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + srcs
     print(" ".join(cmd), file=sys.stderr)
     subprocess.check_call(cmd, cwd=CSRC)
+    os.replace(tmp, OUT)
     return OUT
 
 

@@ -244,6 +244,9 @@ int pmf_destroy(pmf_handle h) {
     big_free(h->A, (size_t)h->N * h->lda, h->dims.device);
     dev_free(h->X); dev_free(h->dX); dev_free(h->accX); dev_free(h->Y); dev_free(h->accY);
     dev_free(h->Xl); dev_free(h->Xh); dev_free(h->tc_cost_cum);
+    big_free(h->wide.G, (size_t)h->N * h->lda, h->dims.device);
+    dev_free(h->wide.Xh); dev_free(h->wide.Yh);
+    { float* q = static_cast<float*>(h->wide.Xb); dev_free(q); q = static_cast<float*>(h->wide.Yb); dev_free(q); h->wide.Xb = h->wide.Yb = nullptr; }
     dev_free(h->weight); dev_free(h->colinfo); dev_free(h->thresholds); dev_free(h->scalars); dev_free(h->ctrl);
     dev_free(h->vp); dev_free(h->sg); dev_free(h->accvp); dev_free(h->regw); dev_free(h->regc);
     dev_free(h->bcol_off); dev_free(h->bcol_view); dev_free(h->bcol_nb); dev_free(h->batch_of_sample);
@@ -1346,11 +1349,41 @@ int pmf_model_s::run_data_pass(DataPassParams& p, int kind, int precision) {
     bool batches_ok = true;                    // chunk tables hold 16-bit batch ids
     for (const BatchView& bv : views) batches_ok &= bv.n_batches <= 65533;
     const bool tc_ok = tc_supported(p) && cc_major == 10 && batches_ok;
-    if (kind == PMF_KERNEL_TC && !tc_ok)
-        return fail(this, PMF_ERR_ARG, "tcgen05 data pass needs 8 <= K <= 64, at most 65533 batches per view and an sm_100 device");
+    const bool wide_ok = wide_supported(p) && cc_major == 10;
+    if (kind == PMF_KERNEL_TC && !tc_ok && !wide_ok)
+        return fail(this, PMF_ERR_ARG, "tcgen05 data pass needs an sm_100 device and 8 <= K <= 64 (at most 65533 batches per "
+                                       "view) or 64 < K <= 256 without batch layers");
     // AUTO: the tcgen05 path pays off (and its single-pass TF32 gradient contractions average below
     // the 1e-4 parity bar) on large problems; small ones run the exact-FP32 FFMA kernel.
     const bool big = (double)M * (double)N >= 4.0e6 && M >= 1024;
+    if (wide_ok && (kind == PMF_KERNEL_TC || (kind == PMF_KERNEL_AUTO && auto_tc && big))) {
+        if (!wide.G) {
+            const size_t nx = wide_scratch_floats(Mp, Kp), ny = wide_scratch_floats(Np, Kp);
+            float *xb = nullptr, *yb = nullptr;
+            if (big_alloc(&wide.G, (size_t)N * lda, dims.device) != cudaSuccess || dev_alloc(&wide.Xh, nx) != cudaSuccess ||
+                dev_alloc(&xb, nx) != cudaSuccess || dev_alloc(&wide.Yh, ny) != cudaSuccess || dev_alloc(&yb, ny) != cudaSuccess)
+                return fail(this, PMF_ERR_ALLOC, "device allocation failed (K > 64 tensor-core path needs a second %.2f GB matrix)",
+                            (double)N * lda * 4e-9);
+            wide.Xb = xb; wide.Yb = yb;
+            // G' rows are written for every column j < N and every sample position i < lda; nothing else is ever read
+        }
+        cudaEvent_t t0 = nullptr, t1 = nullptr;
+        if (profiling) {
+            if (prof_used + 2 > prof_ev.size()) {
+                for (int i = 0; i < 2; ++i) { cudaEvent_t ev; cudaEventCreate(&ev); prof_ev.push_back(ev); }
+            }
+            t0 = prof_ev[prof_used]; t1 = prof_ev[prof_used + 1];
+            prof_used += 2;
+            cudaEventRecord(t0, stream);
+        }
+        int n_launched = 0;
+        cudaError_t e = launch_data_pass_wide(p, wide, precision, stream, n_sms, &n_launched);
+        if (profiling) cudaEventRecord(t1, stream);
+        if (e != cudaSuccess) { cuda_failed = true; return fail(this, PMF_ERR_CUDA, "tcgen05 (K > 64) data pass launch: %s", cudaGetErrorString(e)); }
+        launches += n_launched;
+        xsplit_valid = false;
+        return 0;
+    }
     const bool use_tc = kind == PMF_KERNEL_TC || (kind == PMF_KERNEL_AUTO && tc_ok && auto_tc && big);
     if (use_tc) {
         if (!views.empty() && !tcb_valid) {

@@ -81,6 +81,7 @@ struct pmf_model_s {
     float *X = nullptr, *dX = nullptr, *accX = nullptr;
     float *Y = nullptr, *accY = nullptr;
     float *Xh = nullptr, *Xl = nullptr;   // TF32 operand split of X for the tcgen05 path (lazy)
+    pmf::WideScratch wide{};              // K > 64 tensor-core path: operand scratch + the G' matrix (lazy)
     bool xsplit_valid = false;            // Xh / Xl match X (written by the update pass); else the launcher refreshes them
     bool grads_clean = false;             // dX, sg and the loss scalars were cleared by the previous epoch's update pass
     bool auto_tc = true;                     // PMF_KERNEL_AUTO picks the tcgen05 path when it applies

@@ -173,6 +173,18 @@ struct TcBatchDev {
     const int32_t* cost_cum;      // [n_pass + 1]
     const uint16_t* boc;          // [n_views][n_pos/16] batch of a chunk in the view's order
 };
+// 64 < K <= 256 (wide_tc.cu): operand scratch of the three-kernel tensor-core pass.  Kq = roundup(Kp, 32).
+struct WideScratch {
+    float* Xh;     // [Mp][Kq]   rna_tf32(X)
+    void* Xb;      // [Mp][2 Kq] BF16, per 32-factor slab [Xh | Xl]
+    float* Yh;     // [Np][Kq]
+    void* Yb;      // [Np][2 Kq] BF16, per slab [Yl | Yh]
+    float* G;      // [N][lda]   w_j sigma_j dloss/dz
+};
+bool wide_supported(const DataPassParams& p);
+size_t wide_scratch_floats(int rows_pad, int Kp);      // floats of Xh / Xb (each) for `rows_pad` rows
+cudaError_t launch_data_pass_wide(const DataPassParams& p, const WideScratch& ws, int precision, cudaStream_t s, int n_sms,
+                                  int* n_launches);
 bool tc_supported(const DataPassParams& p);
 // `bp`: null for a model without batch layers.  *n_launches receives the number of kernels launched.
 cudaError_t launch_data_pass_tc(const DataPassParams& p, float* Xh, float* Xl, bool refresh_split, int precision,

@@ -1,0 +1,580 @@
+// Data pass for 64 < K <= 256 on the 5th-generation tensor cores (tcgen05 + TMEM + TMA).
+//
+// K is the number of pathway factors (src/model.jl:122, K = length(feature_graphs)); at K = 128 / 256 the three
+// contractions of the pass (Z = X'Y, dX = Y G', dY = X G) are tensor-bound and the operand
+// tiles of a single fused tile pipeline (fused_tc.cu) no longer fit TMEM / shared memory.  The pass is therefore three
+// GEMM-shaped kernels around ONE M x N scratch matrix G' (4 HBM bytes per entry written once, read twice):
+//
+//   zlink_kernel      Z[j,i] = sum_k Y[j,k] X[i,k] as TF32 (Yh Xh) + one BF16 contraction over 2K for the first-order
+//                     corrections Yl Xh + Yh Xl (3xTF32-equivalent, see fused_tc.cu); K-loop over 32-wide slabs, both
+//                     operands K-major through a TMA-fed ring; accumulator tile 128 features x 256 samples in TMEM,
+//                     double buffered.  Epilogue (16 warps, lane = feature): ColScale / ColShift, noise-model loss and
+//                     dloss/dz with the NaN mask (src/layers.jl:9-90), column sums for dmu / dlogsigma, the data read
+//                     straight from global memory with 256-bit loads (its tile was prefetched to L2 by TMA when the
+//                     tile's K-loop started) and G' = w_j sigma_j dloss/dz stored with 256-bit stores.
+//   grad_gemm_kernel  <A_MN = false>  dY[j,:] += sum_i G'[j,i] Xh[i,:]   A = G' tile K-major, B = Xh rows MN-major
+//                     <A_MN = true >  dX[i,:] += sum_j G'[j,i] Yh[j,:]   A = G' tile MN-major (no transposition), B = Yh
+//                     two 128-row output tiles x K columns accumulate in TMEM over a contiguous range of 32-deep
+//                     contraction steps; the accumulators leave once per item as 128-bit REDs.
+//
+// Operand scratch (prep_wide_kernel, every epoch): Ph = rna_tf32(P) [rows][Kq] FP32 and Pb [rows][2 Kq] BF16, per
+// 32-factor slab [Pl | Ph] for Y (the A operand) and [Ph | Pl] for X (the B operand), Kq = roundup(K, 32), zero padded.
+// Single-pass TF32 with round-to-nearest operands for the two gradient contractions (as in fused_tc.cu).
+// Batch shift / scale layers are not served here (the FP32 kernel runs those models when K > 64).
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include "pmf_epilogue.cuh"
+#include "pmf_internal.h"
+#include "tc_common.cuh"
+
+namespace pmf {
+
+namespace {
+
+using namespace tcx;
+
+// ---- work distribution --------------------------------------------------------------------------------------
+// Units (outer, inner), flattened outer-major, are cut into gridDim.x contiguous ranges of equal cost; a range is
+// walked as ITEMS = maximal runs inside one outer index (per-item state: column constants, accumulators).
+// `cum`: cumulative cost per outer index ([n_outer + 1]) or null for uniform cost.
+struct RangeIter {
+    long long t, t_end;
+    int n_inner, outer, in0, in1;
+    static __device__ __forceinline__ long long cut(const int32_t* cum, int n_outer, int n_inner, unsigned num, unsigned den) {
+        const long long total = (long long)n_outer * n_inner;
+        if (num >= den) return total;
+        if (cum == nullptr) return total * num / den;
+        const long long W = (long long)cum[n_outer] * n_inner;
+        const long long x = W * num / den;
+        int lo = 0, hi = n_outer;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if ((long long)cum[mid] * n_inner <= x) lo = mid; else hi = mid;
+        }
+        const long long w = cum[lo + 1] - cum[lo];
+        long long in = (x - (long long)cum[lo] * n_inner) / (w > 0 ? w : 1);
+        if (in > n_inner) in = n_inner;
+        return (long long)lo * n_inner + in;
+    }
+    __device__ __forceinline__ RangeIter(const int32_t* cum, int n_outer, int n_inner_) {
+        t = cut(cum, n_outer, n_inner_, blockIdx.x, gridDim.x);
+        t_end = cut(cum, n_outer, n_inner_, blockIdx.x + 1, gridDim.x);
+        n_inner = n_inner_;
+        outer = in0 = in1 = 0;
+    }
+    __device__ __forceinline__ bool next() {
+        if (t >= t_end) return false;
+        outer = (int)(t / n_inner);
+        in0 = (int)(t - (long long)outer * n_inner);
+        const long long len = min((long long)(n_inner - in0), t_end - t);
+        in1 = in0 + (int)len;
+        t += len;
+        return true;
+    }
+};
+
+struct Ring {
+    uint32_t s = 0, ph = 0;
+    __device__ __forceinline__ void next(uint32_t n) { if (++s == n) { s = 0; ph ^= 1u; } }
+};
+
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], 16-bit operands (kind::f16; here BF16 x BF16 -> F32, K = 16 per instruction)
+__device__ __forceinline__ void mma_ss_f16(uint32_t d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+// 256-bit global accesses: one full 32-byte sector per lane (a lane walks its own feature row of the data)
+__device__ __forceinline__ void ldg256(const float* p, float (&r)[16], int o) {
+    asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r[o]), "=f"(r[o + 1]), "=f"(r[o + 2]), "=f"(r[o + 3]), "=f"(r[o + 4]), "=f"(r[o + 5]), "=f"(r[o + 6]), "=f"(r[o + 7])
+                 : "l"(p));
+}
+__device__ __forceinline__ void stg256(float* p, const uint32_t (&r)[16], int o) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"l"(p), "r"(r[o]), "r"(r[o + 1]), "r"(r[o + 2]), "r"(r[o + 3]), "r"(r[o + 4]), "r"(r[o + 5]), "r"(r[o + 6]), "r"(r[o + 7])
+                 : "memory");
+}
+
+__device__ __noinline__ float2 noise_eval_slow_w(int dist, float z, float a, const float* __restrict__ th_range,
+                                                  float ord_eps, float margin) {
+    if (!is_observed(a)) return make_float2(0.f, 0.f);
+    const float4 th4 = __ldg(reinterpret_cast<const float4*>(th_range));
+    const float th[4] = {th4.x, th4.y, th4.z, th4.w};
+    float l, g;
+    noise_eval(dist, z, a, th, ord_eps, margin, l, g);
+    return make_float2(l, g);
+}
+
+// ================================================================================================================
+// zlink: Z contraction + link epilogue
+// ================================================================================================================
+constexpr int ZBJ = 128, ZBI = 256, ZS = 2;
+constexpr uint32_t Z_YH = 16384, Z_YB = 16384, Z_XH = 32768, Z_XB = 32768;
+constexpr uint32_t Z_OFF_YB = Z_YH, Z_OFF_XH = Z_YH + Z_YB, Z_OFF_XB = Z_YH + Z_YB + Z_XH;
+constexpr uint32_t Z_STAGE = Z_YH + Z_YB + Z_XH + Z_XB;                      // 96 KB per 32-factor slab
+constexpr int Z_NEPI = 16, Z_W_TMA = Z_NEPI, Z_W_MMA = Z_NEPI + 1, Z_NTHREADS = 32 * (Z_NEPI + 2);
+constexpr uint32_t Z_SMEM = ZS * Z_STAGE + 1024 + 256;
+enum ZBar { ZB_FULL = 0, ZB_EMPTY = ZB_FULL + ZS, ZB_ZFULL = ZB_EMPTY + ZS, ZB_ZEMPTY = ZB_ZFULL + 2, ZB_COUNT = ZB_ZEMPTY + 2 };
+
+struct WideParams {
+    DataPassParams dp;
+    float* G;            // [N][lda] scratch: w_j sigma_j dloss/dz, TF32-rounded; exactly 0 at missing entries
+    int n_jt, n_it;      // 128-feature tiles, 256-sample tiles
+    int nks;             // 32-factor slabs = Kq / 32
+    int corr;            // 1: BF16 first-order corrections of Z (precision 0 / 1), 0: plain TF32 (precision 2)
+};
+
+__global__ void __launch_bounds__(Z_NTHREADS, 1)
+zlink_kernel(const __grid_constant__ CUtensorMap tmYh, const __grid_constant__ CUtensorMap tmYb,
+             const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUtensorMap tmXb,
+             const __grid_constant__ CUtensorMap tmA, const WideParams p) {
+    const DataPassParams& dp = p.dp;
+    if (dp.stop_flag != nullptr && *dp.stop_flag != 0) return;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t BARS = base + ZS * Z_STAGE;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + ZS * Z_STAGE + 8 * ZB_COUNT);
+    __shared__ double red_smem[Z_NEPI];
+    auto bar = [&](int b) { return BARS + 8u * (uint32_t)b; };
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int b = 0; b < ZB_COUNT; ++b) mbar_init(bar(b), (b >= ZB_ZEMPTY) ? (uint32_t)Z_NEPI : 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == Z_W_MMA) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tm = *tmem_slot;
+
+    if (warp == Z_W_TMA) {
+        if (lane == 0) {
+            Ring r;
+            const uint32_t bytes = p.corr ? Z_STAGE : (Z_YH + Z_XH);
+            for (RangeIter itx(dp.tc_cost_cum, p.n_jt, p.n_it); itx.next();) {
+                const int j0 = itx.outer * ZBJ;
+                for (int it = itx.in0; it < itx.in1; ++it) {
+                    const int i0 = it * ZBI;
+                    // the data tile of this accumulator: on its way to L2 while the K-loop runs
+                    for (int q = 0; q < 4; ++q)
+                        if (i0 + 64 * q < dp.lda) tma_prefetch_2d(&tmA, i0 + 64 * q, j0);
+                    for (int ks = 0; ks < p.nks; ++ks, r.next(ZS)) {
+                        mbar_wait(bar(ZB_EMPTY + r.s), r.ph ^ 1);
+                        mbar_expect_tx(bar(ZB_FULL + r.s), bytes);
+                        const uint32_t st = base + r.s * Z_STAGE;
+                        tma_load_2d(st, &tmYh, bar(ZB_FULL + r.s), 32 * ks, j0);
+                        tma_load_2d(st + Z_OFF_XH, &tmXh, bar(ZB_FULL + r.s), 32 * ks, i0);
+                        if (p.corr) {
+                            tma_load_2d(st + Z_OFF_YB, &tmYb, bar(ZB_FULL + r.s), 64 * ks, j0);
+                            tma_load_2d(st + Z_OFF_XB, &tmXb, bar(ZB_FULL + r.s), 64 * ks, i0);
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == Z_W_MMA) {
+        if (elect_one()) {
+            const uint32_t id_z = umma_idesc(ZBJ, ZBI, false, false);                       // TF32, both K-major
+            const uint32_t id_zb = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(ZBI >> 3) << 17) | ((uint32_t)(ZBJ >> 4) << 24);   // BF16
+            Ring r;
+            uint32_t tcount = 0;
+            for (RangeIter itx(dp.tc_cost_cum, p.n_jt, p.n_it); itx.next();) {
+                for (int it = itx.in0; it < itx.in1; ++it, ++tcount) {
+                    const uint32_t b = tcount & 1u, ph = (tcount >> 1) & 1u;
+                    mbar_wait(bar(ZB_ZEMPTY + b), ph ^ 1u);
+                    tc_fence_after();
+                    const uint32_t zt = tm + ZBI * b;
+                    for (int ks = 0; ks < p.nks; ++ks, r.next(ZS)) {
+                        mbar_wait(bar(ZB_FULL + r.s), r.ph);
+                        tc_fence_after();
+                        const uint32_t st = base + r.s * Z_STAGE;
+                        const uint64_t yh = umma_desc_k(st), xh = umma_desc_k(st + Z_OFF_XH);
+#pragma unroll
+                        for (int s = 0; s < 4; ++s)
+                            mma_ss(zt, yh + (uint64_t)(2 * s), xh + (uint64_t)(2 * s), id_z, (ks > 0 || s > 0) ? 1u : 0u);
+                        if (p.corr) {
+                            const uint64_t yb = umma_desc_k(st + Z_OFF_YB), xb = umma_desc_k(st + Z_OFF_XB);
+#pragma unroll
+                            for (int s = 0; s < 4; ++s) mma_ss_f16(zt, yb + (uint64_t)(2 * s), xb + (uint64_t)(2 * s), id_zb, 1u);
+                        }
+                        tc_commit(bar(ZB_EMPTY + r.s));
+                    }
+                    tc_commit(bar(ZB_ZFULL + b));
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ================================ epilogue warps ===========================================
+        // warp = (TMEM lane quarter, 64-sample chunk of the 256-sample tile); lane = feature row
+        const int quarter = warp & 3, c64 = warp >> 2;
+        const int lrow = 32 * quarter + lane;
+        const uint32_t lane_addr = ((uint32_t)(32 * quarter)) << 16;
+        double loss_d = 0.0;
+        uint32_t tcount = 0;
+        for (RangeIter itx(dp.tc_cost_cum, p.n_jt, p.n_it); itx.next();) {
+            const int j = itx.outer * ZBJ + lrow;
+            const bool jok = j < dp.N;
+            const int jj = jok ? j : dp.N - 1;           // padding rows follow the last column (same branch, no stores)
+            const float sigma = __expf(__ldg(dp.logsigma + jj));
+            const float muj = __ldg(dp.mu + jj);
+            const float wj = jok ? __ldg(dp.weight + jj) : 0.f;
+            const int ci = __ldg(dp.colinfo + jj);
+            const int dist = ci & 0xff;
+            const float* th_range = dp.thresholds + 4 * (ci >> 8);
+            const float gscale = sigma * wj;
+            float dmu_acc = 0.f, loss_acc = 0.f;
+            const float* arow = dp.A + (size_t)jj * dp.lda;
+            float* grow = p.G + (size_t)jj * dp.lda;
+            for (int it = itx.in0; it < itx.in1; ++it, ++tcount) {
+                const uint32_t b = tcount & 1u, ph = (tcount >> 1) & 1u;
+                const int ib = it * ZBI + 64 * c64;
+                mbar_wait(bar(ZB_ZFULL + b), ph);
+                tc_fence_after();
+                const uint32_t zt = tm + lane_addr + ZBI * b + 64 * c64;
+#pragma unroll 1
+                for (int hh = 0; hh < 4; ++hh) {
+                    const int i = ib + 16 * hh;
+                    if (i >= dp.lda) break;               // warp-uniform: lda is a multiple of 32
+                    uint32_t z[16];
+                    float a[16];
+                    TMEM_LD16(zt + 16 * hh, z);
+                    if (jok) {
+                        ldg256(arow + i, a, 0);
+                        ldg256(arow + i + 8, a, 8);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) a[e] = __int_as_float(0x7fc00000);
+                    }
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (dist == DIST_NORMAL) {
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) {
+                            float d = fmaf(__uint_as_float(z[e]), sigma, muj) - a[e];
+                            d = fabsf(a[e]) < INFINITY ? d : 0.f;
+                            loss_acc = fmaf(d, d, loss_acc);
+                            dmu_acc += d;
+                            z[e] = rn_bits(d * gscale);
+                        }
+                    } else if (dist == DIST_BERNOULLI) {
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) {
+                            const uint32_t m = obs_mask(a[e]);
+                            float z4 = fmaf(__uint_as_float(z[e]), sigma, muj);
+                            float ex = ex2_fast(fabsf(z4) * -1.4426950408889634f);
+                            float w = 1.0f + ex;
+                            float r = rcp_fast(w);
+                            float sg = z4 >= 0.f ? r : ex * r;
+                            float l = fmaf(-a[e], z4, fmaf(lg2_fast(w), 0.6931471805599453f, fmaxf(z4, 0.f)));
+                            float gv = and_mask(sg - a[e], m);
+                            loss_acc = fmaf(2.f, and_mask(l, m), loss_acc);
+                            dmu_acc += gv;
+                            z[e] = rn_bits(gv * gscale);
+                        }
+                    } else if (dist == DIST_POISSON) {
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) {
+                            const uint32_t m = obs_mask(a[e]);
+                            float z4 = fmaf(__uint_as_float(z[e]), sigma, muj);
+                            float ez = ex2_fast(z4 * 1.4426950408889634f);
+                            float gv = and_mask(ez - a[e], m);
+                            float l = and_mask(fmaf(-a[e], z4, ez), m);
+                            loss_acc = fmaf(2.f, l, loss_acc);
+                            dmu_acc += gv;
+                            z[e] = rn_bits(gv * gscale);
+                        }
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) {
+                            float z4 = fmaf(__uint_as_float(z[e]), sigma, muj);
+                            float2 lg = noise_eval_slow_w(dist, z4, a[e], th_range, dp.ordinal_eps, dp.hinge_margin);
+                            loss_acc = fmaf(2.f, lg.x, loss_acc);
+                            dmu_acc += lg.y;
+                            z[e] = rn_bits(lg.y * gscale);
+                        }
+                    }
+                    if (jok) {
+                        stg256(grow + i, z, 0);
+                        stg256(grow + i + 8, z, 8);
+                    }
+                }
+                // every TMEM read of this warp has completed (wait::ld above): the accumulator may be overwritten
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_relaxed(bar(ZB_ZEMPTY + b));
+            }
+            loss_d += (double)(loss_acc * wj);
+            // dmu_j = w_j sum_i g ; dlogsigma_j = sigma_j w_j sum_i g (the reference's ColScale quirk, src/layers.jl:39-44)
+            if (jok) {
+                atomicAdd(dp.dmu + j, dmu_acc * wj);
+                atomicAdd(dp.dlogsigma + j, dmu_acc * wj * sigma);
+            }
+        }
+        loss_d *= 0.5;
+        for (int o = 16; o > 0; o >>= 1) loss_d += __shfl_xor_sync(0xffffffffu, loss_d, o);
+        if (lane == 0) red_smem[warp] = loss_d;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < Z_NEPI; ++w) t += red_smem[w];
+        atomicAdd(dp.scalars + SC_DATA, t);
+    }
+    if (warp == Z_W_MMA) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"(512u) : "memory");
+    }
+}
+
+// ================================================================================================================
+// gradient contractions
+// ================================================================================================================
+constexpr int GS = 3;                                  // ring stages
+constexpr uint32_t G_A = 32768, G_B = 32768, G_STAGE = G_A + G_B;
+constexpr int G_NEPI = 4, G_W_TMA = G_NEPI, G_W_MMA = G_NEPI + 1, G_NTHREADS = 32 * (G_NEPI + 2);
+constexpr uint32_t G_SMEM = GS * G_STAGE + 1024 + 256;
+enum GBar { GB_FULL = 0, GB_EMPTY = GB_FULL + GS, GB_ACC_FULL = GB_EMPTY + GS, GB_ACC_EMPTY, GB_COUNT };
+
+struct GradParams {
+    float* out;          // [rows_pad][Kp] accumulated with REDs
+    int rows_pad;        // rows of `out` (multiple of 128)
+    int Kp, Kc, nkb;     // row pitch, accumulator width (multiple of 16), 32-column boxes of the B operand
+    int n_groups;        // 256-row output groups
+    int n_steps;         // 32-deep contraction steps
+    const int* stop_flag;
+};
+
+template <bool A_MN>
+__global__ void __launch_bounds__(G_NTHREADS, 1)
+grad_gemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmB, const GradParams p) {
+    if (p.stop_flag != nullptr && *p.stop_flag != 0) return;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t BARS = base + GS * G_STAGE;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + GS * G_STAGE + 8 * GB_COUNT);
+    auto bar = [&](int b) { return BARS + 8u * (uint32_t)b; };
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int b = 0; b < GB_COUNT; ++b) mbar_init(bar(b), b == GB_ACC_EMPTY ? (uint32_t)G_NEPI : 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == G_W_MMA) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tm = *tmem_slot;
+
+    if (warp == G_W_TMA) {
+        if (lane == 0) {
+            Ring r;
+            const uint32_t bytes = G_A + (uint32_t)p.nkb * 4096u;
+            for (RangeIter itx(nullptr, p.n_groups, p.n_steps); itx.next();) {
+                const int r0 = itx.outer * 256;
+                for (int c = itx.in0; c < itx.in1; ++c, r.next(GS)) {
+                    const int c0 = 32 * c;
+                    mbar_wait(bar(GB_EMPTY + r.s), r.ph ^ 1);
+                    mbar_expect_tx(bar(GB_FULL + r.s), bytes);
+                    const uint32_t st = base + r.s * G_STAGE;
+                    if (!A_MN) {
+                        // G' rows r0 .. (features), 32 samples: K-major A tiles (contraction = samples, contiguous)
+                        for (int t = 0; t < 2; ++t) tma_load_2d(st + t * 16384, &tmG, bar(GB_FULL + r.s), c0, r0 + 128 * t);
+                    } else {
+                        // 32 feature rows x 128 samples per tile as four 32-sample boxes: MN-major A tiles
+                        for (int t = 0; t < 2; ++t)
+                            for (int q = 0; q < 4; ++q)
+                                tma_load_2d(st + t * 16384 + q * 4096, &tmG, bar(GB_FULL + r.s), r0 + 128 * t + 32 * q, c0);
+                    }
+                    for (int kb = 0; kb < p.nkb; ++kb) tma_load_2d(st + G_A + kb * 4096, &tmB, bar(GB_FULL + r.s), 32 * kb, c0);
+                }
+            }
+        }
+    } else if (warp == G_W_MMA) {
+        if (elect_one()) {
+            const uint32_t idesc = umma_idesc(128, p.Kc, A_MN, true);
+            Ring r;
+            uint32_t q = 0;
+            for (RangeIter itx(nullptr, p.n_groups, p.n_steps); itx.next(); ++q) {
+                mbar_wait(bar(GB_ACC_EMPTY), (q & 1u) ^ 1u);
+                tc_fence_after();
+                for (int c = itx.in0; c < itx.in1; ++c, r.next(GS)) {
+                    mbar_wait(bar(GB_FULL + r.s), r.ph);
+                    tc_fence_after();
+                    const uint32_t st = base + r.s * G_STAGE;
+                    const uint64_t bd = umma_desc_mn(st + G_A, 4096u);
+                    const uint32_t acc = c > itx.in0 ? 1u : 0u;
+#pragma unroll
+                    for (int t = 0; t < 2; ++t) {
+                        const uint64_t ad = A_MN ? umma_desc_mn(st + t * 16384, 4096u) : umma_desc_k(st + t * 16384);
+#pragma unroll
+                        for (int s = 0; s < 4; ++s)
+                            mma_ss(tm + (uint32_t)(t * p.Kc), ad + (uint64_t)(A_MN ? 64 * s : 2 * s), bd + (uint64_t)(64 * s), idesc,
+                                   s > 0 ? 1u : acc);
+                    }
+                    tc_commit(bar(GB_EMPTY + r.s));
+                }
+                tc_commit(bar(GB_ACC_FULL));
+            }
+        }
+        __syncwarp();
+    } else {
+        const int quarter = warp & 3;
+        const uint32_t lane_addr = ((uint32_t)(32 * quarter)) << 16;
+        uint32_t q = 0;
+        for (RangeIter itx(nullptr, p.n_groups, p.n_steps); itx.next(); ++q) {
+            mbar_wait(bar(GB_ACC_FULL), q & 1u);
+            tc_fence_after();
+            for (int t = 0; t < 2; ++t) {
+                const int row = itx.outer * 256 + 128 * t + 32 * quarter + lane;
+                float* dst = p.out + (size_t)row * p.Kp;
+                for (int c16 = 0; 16 * c16 < p.Kc; ++c16) {
+                    uint32_t v[16];
+                    TMEM_LD16(tm + lane_addr + (uint32_t)(t * p.Kc + 16 * c16), v);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (row < p.rows_pad) {
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            if (16 * c16 + 4 * u < p.Kp)
+                                atomicAdd(reinterpret_cast<float4*>(dst + 16 * c16 + 4 * u),
+                                          make_float4(__uint_as_float(v[4 * u]), __uint_as_float(v[4 * u + 1]),
+                                                      __uint_as_float(v[4 * u + 2]), __uint_as_float(v[4 * u + 3])));
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_relaxed(bar(GB_ACC_EMPTY));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == G_W_MMA) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"(512u) : "memory");
+    }
+}
+
+// Operand split of a factor matrix P [rows][Kp] for the wide path (see the file header).  One thread per 4 factors.
+__global__ void prep_wide_kernel(const float* __restrict__ P, float* __restrict__ Ph, uint2* __restrict__ Pb, int rows, int Kp,
+                                 int Kq, int a_side, const int* stop_flag) {
+    if (stop_flag != nullptr && *stop_flag != 0) return;
+    const int q4 = Kq >> 2;
+    const size_t n4 = (size_t)rows * q4;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n4; idx += (size_t)gridDim.x * blockDim.x) {
+        const size_t row = idx / q4;
+        const int k = 4 * (int)(idx - row * q4);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k < Kp) v = *reinterpret_cast<const float4*>(P + row * Kp + k);
+        float4 h;
+        h.x = __uint_as_float(rna_tf32(v.x)); h.y = __uint_as_float(rna_tf32(v.y));
+        h.z = __uint_as_float(rna_tf32(v.z)); h.w = __uint_as_float(rna_tf32(v.w));
+        *reinterpret_cast<float4*>(Ph + row * Kq + k) = h;
+        const uint2 hb = make_uint2(pack_bf16(h.x, h.y), pack_bf16(h.z, h.w));
+        const uint2 lb = make_uint2(pack_bf16(v.x - h.x, v.y - h.y), pack_bf16(v.z - h.z, v.w - h.w));
+        // BF16 row of 2 Kq: slab s = k / 32 occupies elements 64 s .. 64 s + 63 as two 32-element halves
+        const size_t e0 = row * (size_t)(2 * Kq) + (size_t)(64 * (k >> 5) + (k & 31));     // element index of the first half
+        uint2* first = Pb + (e0 >> 2);
+        uint2* second = Pb + ((e0 + 32) >> 2);
+        if (a_side) { *first = lb; *second = hb; }      // Y: [Yl | Yh]
+        else { *first = hb; *second = lb; }             // X: [Xh | Xl]
+    }
+}
+
+}  // namespace
+
+bool wide_supported(const DataPassParams& p) {
+    return p.Kp > 64 && p.Kp <= 256 && p.n_batch_views == 0 && p.col_ssq == nullptr;
+}
+
+size_t wide_scratch_floats(int rows_pad, int Kp) { return (size_t)rows_pad * (size_t)((Kp + 31) / 32 * 32); }
+
+cudaError_t launch_data_pass_wide(const DataPassParams& dp, const WideScratch& ws, int precision, cudaStream_t s, int n_sms,
+                                  int* n_launches) {
+    if (!wide_supported(dp)) return cudaErrorInvalidValue;
+    const int Kq = (dp.Kp + 31) / 32 * 32;
+    const int Kc = (dp.Kp + 15) / 16 * 16;
+    int launched = 0;
+    // 1. operand split of X and Y
+    {
+        const size_t nx = (size_t)dp.Mp * (Kq >> 2), ny = (size_t)dp.Np * (Kq >> 2);
+        auto blocks = [](size_t n) { size_t b = (n + 255) / 256; return (unsigned)(b < 1184 ? (b ? b : 1) : 1184); };
+        prep_wide_kernel<<<blocks(nx), 256, 0, s>>>(dp.X, ws.Xh, reinterpret_cast<uint2*>(ws.Xb), dp.Mp, dp.Kp, Kq, 0, dp.stop_flag);
+        prep_wide_kernel<<<blocks(ny), 256, 0, s>>>(dp.Y, ws.Yh, reinterpret_cast<uint2*>(ws.Yb), dp.Np, dp.Kp, Kq, 1, dp.stop_flag);
+        launched += 2;
+    }
+    const CUtensorMapDataType F32 = CU_TENSOR_MAP_DATA_TYPE_FLOAT32, BF16 = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    const CUtensorMapSwizzle SW = CU_TENSOR_MAP_SWIZZLE_128B, SWA = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+    // 2. Z + link
+    {
+        CUtensorMap tmYh, tmYb, tmXh, tmXb, tmA;
+        bool ok = encode_map_2d(&tmYh, F32, ws.Yh, Kq, dp.Np, (uint64_t)Kq * 4, 32, ZBJ, SW) &&
+                  encode_map_2d(&tmYb, BF16, ws.Yb, 2 * (uint64_t)Kq, dp.Np, (uint64_t)Kq * 4, 64, ZBJ, SW) &&
+                  encode_map_2d(&tmXh, F32, ws.Xh, Kq, dp.Mp, (uint64_t)Kq * 4, 32, ZBI, SW) &&
+                  encode_map_2d(&tmXb, BF16, ws.Xb, 2 * (uint64_t)Kq, dp.Mp, (uint64_t)Kq * 4, 64, ZBI, SW) &&
+                  encode_map_2d(&tmA, F32, dp.A, dp.lda, dp.N, (uint64_t)dp.lda * 4, 64, ZBJ, CU_TENSOR_MAP_SWIZZLE_NONE);
+        if (!ok) return cudaErrorUnknown;
+        WideParams p;
+        p.dp = dp;
+        p.G = ws.G;
+        p.n_jt = (dp.N + ZBJ - 1) / ZBJ;
+        p.n_it = (dp.M + ZBI - 1) / ZBI;
+        p.nks = Kq / 32;
+        p.corr = precision >= 2 ? 0 : 1;
+        cudaError_t e = cudaFuncSetAttribute(zlink_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Z_SMEM);
+        if (e != cudaSuccess) return e;
+        const long long n_tiles = (long long)p.n_jt * p.n_it;
+        const int grid = n_tiles < n_sms ? (int)n_tiles : n_sms;
+        zlink_kernel<<<grid, Z_NTHREADS, Z_SMEM, s>>>(tmYh, tmYb, tmXh, tmXb, tmA, p);
+        ++launched;
+    }
+    // 3. the two gradient contractions over G'
+    {
+        CUtensorMap tmGk, tmGm, tmX, tmY;
+        bool ok = encode_map_2d(&tmGk, F32, ws.G, dp.lda, dp.N, (uint64_t)dp.lda * 4, 32, 128, SW) &&
+                  encode_map_2d(&tmGm, F32, ws.G, dp.lda, dp.N, (uint64_t)dp.lda * 4, 32, 32, SWA) &&
+                  encode_map_2d(&tmX, F32, ws.Xh, Kq, dp.Mp, (uint64_t)Kq * 4, 32, 32, SWA) &&
+                  encode_map_2d(&tmY, F32, ws.Yh, Kq, dp.Np, (uint64_t)Kq * 4, 32, 32, SWA);
+        if (!ok) return cudaErrorUnknown;
+        GradParams g;
+        g.Kp = dp.Kp; g.Kc = Kc; g.nkb = (Kc + 31) / 32; g.stop_flag = dp.stop_flag;
+        cudaError_t e = cudaFuncSetAttribute(grad_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(grad_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM);
+        if (e != cudaSuccess) return e;
+        auto grid_of = [&](const GradParams& q) {
+            const long long units = (long long)q.n_groups * q.n_steps;
+            return units < n_sms ? (int)units : n_sms;
+        };
+        // dY[j,:] += sum_i G'[j,i] Xh[i,:]
+        g.out = dp.dY; g.rows_pad = dp.Np; g.n_groups = (dp.N + 255) / 256; g.n_steps = (dp.M + 31) / 32;
+        grad_gemm_kernel<false><<<grid_of(g), G_NTHREADS, G_SMEM, s>>>(tmGk, tmX, g);
+        // dX[i,:] += sum_j G'[j,i] Yh[j,:]
+        g.out = dp.dX; g.rows_pad = dp.Mp; g.n_groups = (dp.M + 255) / 256; g.n_steps = (dp.N + 31) / 32;
+        grad_gemm_kernel<true><<<grid_of(g), G_NTHREADS, G_SMEM, s>>>(tmGm, tmY, g);
+        launched += 2;
+    }
+    if (n_launches) *n_launches = launched;
+    return cudaGetLastError();
+}
+
+}  // namespace pmf

@@ -412,8 +412,8 @@ def test_tc_small_latent_dimension(K):
 
 def test_tc_refuses_unsupported_shapes():
     """PMF_KERNEL_TC on a model the tcgen05 kernel does not cover is an error, never a silent fallback."""
-    model, om, D = make_pair(200, {"methylation": ("normal", 100)}, K=72, seed=70)
-    eng = P.Engine(model)
+    model, om, D = make_pair(200, {"methylation": ("normal", 100)}, K=72, seed=70, batch_views=["methylation"], n_batches=2)
+    eng = P.Engine(model)      # K > 64 WITH batch layers: neither tensor-core path covers it
     try:
         eng.set_loss_grad_kernel(_lib.KERNEL_TC, 0)
         with pytest.raises(_lib.PmfError):

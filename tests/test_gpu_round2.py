@@ -85,3 +85,90 @@ def test_frozen_layer_drops_its_penalty():
                  verbosity=0)
     assert relerr(h["loss"], href["loss"]) < TOL
     assert relerr(h["layer_reg"], [c["layer_reg"] for c in href["components"]]) < TOL
+
+
+# ---- K > 64 (BASELINE configs[3], configs[4]: K = 256 / K = 128 pathway factors, src/model.jl:122) ----------------
+def _wide_views():
+    # (distribution, view) sorted: bernoulli < normal < ordinal3 < poisson
+    return {"mutation": ("bernoulli", 90), "methylation": ("normal", 170), "cna": ("ordinal3", 50), "counts": ("poisson", 75)}
+
+
+@pytest.mark.parametrize("K", [72, 128, 256])
+def test_wide_k_ffma_against_oracle(K):
+    """The FP32 kernel at K > 64 (the on-device reference of the tensor-core path and the kernel of batch-layer models
+    there) against the oracle."""
+    model, om, D = make_pair(310, _wide_views(), K=K, seed=300 + K, missing=0.3, lambda_X_l2=1.0)
+    eng = P.Engine(model)
+    try:
+        eng.set_loss_grad_kernel(_lib.KERNEL_FFMA, 0)
+        got = eng.loss_grad(include_reg=True)
+    finally:
+        eng.close()
+    ref = O.total_loss_grads(om, D)
+    assert abs(got["loss"] - ref["loss"]) <= 1e-5 * abs(ref["loss"])
+    for k in ("dX", "dY", "dmu", "dlogsigma"):
+        assert relerr(got[k], ref[k]) < TOL, (k, relerr(got[k], ref[k]))
+
+
+@pytest.mark.parametrize("K,M", [(72, 310), (128, 523), (200, 257), (256, 300)])
+def test_wide_k_tensor_core_against_oracle(K, M):
+    """wide_tc.cu (Z + link kernel, the two gradient contractions over G') against the oracle: ragged M / N against the
+    256-sample and 128-feature tiles, four noise models, 30% missing.  Loss and column gradients to FP32 level
+    (TF32 + BF16 first-order corrections of Z); dX / dY are single-pass TF32 contractions: 3e-4 at this size."""
+    model, om, D = make_pair(M, _wide_views(), K=K, seed=310 + K, missing=0.3, lambda_X_l2=1.0)
+    eng = P.Engine(model)
+    try:
+        eng.set_loss_grad_kernel(_lib.KERNEL_TC, 0)
+        got = eng.loss_grad(include_reg=True)
+        eng.set_loss_grad_kernel(_lib.KERNEL_TC, 0)
+        again = eng.loss_grad(include_reg=True)          # second pass over the same handle (scratch reuse)
+    finally:
+        eng.close()
+    ref = O.total_loss_grads(om, D)
+    assert got["dX"].shape == (K, M) and got["dY"].shape == (K, 385)
+    assert abs(got["loss"] - ref["loss"]) <= 1e-5 * abs(ref["loss"]), (got["loss"], ref["loss"])
+    assert relerr(got["dmu"], ref["dmu"]) < TOL and relerr(got["dlogsigma"], ref["dlogsigma"]) < TOL
+    assert relerr(got["dY"], ref["dY"]) < 3e-4 and relerr(got["dX"], ref["dX"]) < 3e-4, (relerr(got["dY"], ref["dY"]), relerr(got["dX"], ref["dX"]))
+    assert relerr(again["dY"], got["dY"]) < 1e-5 and abs(again["loss"] - got["loss"]) <= 1e-9 * abs(got["loss"])
+
+
+@pytest.mark.parametrize("K", [128, 256])
+def test_wide_k_tensor_core_midsize_and_fit(K):
+    """2 000 x 3 000: the tensor-core path against the FP32 kernel on the same handle (every CTA range crosses feature
+    tiles and item boundaries), then a short fit through AUTO against the oracle's loss curve."""
+    views = {"mutation": ("bernoulli", 700), "methylation": ("normal", 1500), "counts": ("poisson", 800)}
+    model, om, D = make_pair(2000, views, K=K, seed=330 + K, missing=0.3, lambda_X_l2=1.0)
+    eng = P.Engine(model)
+    try:
+        eng.set_loss_grad_kernel(_lib.KERNEL_FFMA, 0)
+        ref = eng.loss_grad(include_reg=True)
+        eng.set_loss_grad_kernel(_lib.KERNEL_TC, 0)
+        got = eng.loss_grad(include_reg=True)
+    finally:
+        eng.close()
+    assert abs(got["loss"] - ref["loss"]) <= 2e-6 * abs(ref["loss"])
+    assert relerr(got["dmu"], ref["dmu"]) < 2e-5 and relerr(got["dlogsigma"], ref["dlogsigma"]) < 2e-5
+    assert relerr(got["dY"], ref["dY"]) < 2e-4 and relerr(got["dX"], ref["dX"]) < 2e-4, (relerr(got["dY"], ref["dY"]), relerr(got["dX"], ref["dX"]))
+    h = P.mf_fit(model, lr=0.05, max_epochs=4, update_X=True, update_Y=True, update_col_layers=True, rel_tol=0, abs_tol=0,
+                 verbosity=0, kernel=_lib.KERNEL_AUTO)
+    href = O.mf_fit(om, D, O.AdaGrad(0.05), max_epochs=4, update_X=True, update_Y=True, update_col_layers=True, rel_tol=0,
+                    abs_tol=0)
+    assert np.max(np.abs(np.array(h["loss"]) / np.array(href["loss"]) - 1)) < 1e-4
+
+
+def test_wide_k_with_batch_layers_runs_fp32_kernel():
+    """K > 64 with batch layers is not served by the tensor-core kernels: AUTO runs the FP32 kernel (parity with the
+    oracle), an explicit PMF_KERNEL_TC is an error, never a silent fallback."""
+    model, om, D = make_pair(200, {"methylation": ("normal", 130)}, K=72, seed=350, batch_views=["methylation"], n_batches=3,
+                             missing=0.2, lambda_X_l2=1.0)
+    eng = P.Engine(model)
+    try:
+        eng.set_loss_grad_kernel(_lib.KERNEL_AUTO, 0)
+        got = eng.loss_grad(include_reg=True)
+        ref = O.total_loss_grads(om, D)
+        assert relerr(got["dY"], ref["dY"]) < TOL and relerr(got["dtheta"][0], ref["dtheta"][0]) < TOL
+        eng.set_loss_grad_kernel(_lib.KERNEL_TC, 0)
+        with pytest.raises(_lib.PmfError):
+            eng.loss_grad(include_reg=False)
+    finally:
+        eng.close()
