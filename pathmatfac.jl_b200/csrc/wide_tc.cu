@@ -82,9 +82,6 @@ struct Ring {
     __device__ __forceinline__ void next(uint32_t n) { if (++s == n) { s = 0; ph ^= 1u; } }
 };
 
-__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
-    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
-}
 // D[tmem] (+)= A[smem] * B[smem], 16-bit operands (kind::f16; here BF16 x BF16 -> F32, K = 16 per instruction)
 __device__ __forceinline__ void mma_ss_f16(uint32_t d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
     asm volatile(
@@ -92,16 +89,10 @@ __device__ __forceinline__ void mma_ss_f16(uint32_t d, uint64_t adesc, uint64_t 
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
-// 256-bit global accesses: one full 32-byte sector per lane (a lane walks its own feature row of the data)
-__device__ __forceinline__ void ldg256(const float* p, float (&r)[16], int o) {
-    asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=f"(r[o]), "=f"(r[o + 1]), "=f"(r[o + 2]), "=f"(r[o + 3]), "=f"(r[o + 4]), "=f"(r[o + 5]), "=f"(r[o + 6]), "=f"(r[o + 7])
-                 : "l"(p));
-}
-__device__ __forceinline__ void stg256(float* p, const uint32_t (&r)[16], int o) {
-    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
-                 ::"l"(p), "r"(r[o]), "r"(r[o + 1]), "r"(r[o + 2]), "r"(r[o + 3]), "r"(r[o + 4]), "r"(r[o + 5]), "r"(r[o + 6]), "r"(r[o + 7])
-                 : "memory");
+// shared -> global tile store (bulk async-group completion); out-of-bounds parts of the box are clipped
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
 }
 
 __device__ __noinline__ float2 noise_eval_slow_w(int dist, float z, float a, const float* __restrict__ th_range,
@@ -117,40 +108,57 @@ __device__ __noinline__ float2 noise_eval_slow_w(int dist, float z, float a, con
 // ================================================================================================================
 // zlink: Z contraction + link epilogue
 // ================================================================================================================
-constexpr int ZBJ = 128, ZBI = 256, ZS = 2;
-constexpr uint32_t Z_YH = 16384, Z_YB = 16384, Z_XH = 32768, Z_XB = 32768;
+// Tile = 128 features x 128 samples, accumulators in TMEM (4 x 128 columns: the K-loop runs up to three tiles ahead
+// of the epilogue).  The data take the TMA path in and out: a tile's 128 x 128 block of A arrives as two 64-sample
+// sub-tiles (two 32-sample boxes each, NaN fill beyond the matrix) in a 3-deep shared-memory ring, the 16 epilogue
+// warps turn a sub-tile into G' IN PLACE (128-bit accesses, conflict free under the 128-byte swizzle) and a TMA store
+// returns it.  Measured on B200 at 10 000 x 50 000, K = 128: per-lane 256-bit global loads / stores of the same data
+// (a lane per feature row, 32-byte sectors 40 KB apart) cost 0.77 ms on top of the 0.55 ms K-loop; the bulk path
+// moves the same bytes at HBM speed behind the tensor work.
+constexpr int ZBJ = 128, ZBI = 128, ZS = 2, ZSZ = 4, ZSA = 3;
+constexpr uint32_t Z_YH = 16384, Z_YB = 16384, Z_XH = 16384, Z_XB = 16384;
 constexpr uint32_t Z_OFF_YB = Z_YH, Z_OFF_XH = Z_YH + Z_YB, Z_OFF_XB = Z_YH + Z_YB + Z_XH;
-constexpr uint32_t Z_STAGE = Z_YH + Z_YB + Z_XH + Z_XB;                      // 96 KB per 32-factor slab
-constexpr int Z_NEPI = 16, Z_W_TMA = Z_NEPI, Z_W_MMA = Z_NEPI + 1, Z_NTHREADS = 32 * (Z_NEPI + 2);
-constexpr uint32_t Z_SMEM = ZS * Z_STAGE + 1024 + 256;
-enum ZBar { ZB_FULL = 0, ZB_EMPTY = ZB_FULL + ZS, ZB_ZFULL = ZB_EMPTY + ZS, ZB_ZEMPTY = ZB_ZFULL + 2, ZB_COUNT = ZB_ZEMPTY + 2 };
+constexpr uint32_t Z_STAGE = Z_YH + Z_YB + Z_XH + Z_XB;                      // 64 KB per 32-factor slab
+constexpr uint32_t Z_AG = 32768;                                            // 128 features x 64 samples of A / G'
+constexpr int Z_NEPI = 16, Z_W_TMA = Z_NEPI, Z_W_MMA = Z_NEPI + 1, Z_W_TMA_A = Z_NEPI + 2, Z_W_GST = Z_NEPI + 3,
+              Z_NTHREADS = 32 * (Z_NEPI + 4);
+constexpr uint32_t Z_SMEM_DATA = ZS * Z_STAGE + ZSA * Z_AG;
+constexpr uint32_t Z_SMEM = Z_SMEM_DATA + 1024 + 256;
+enum ZBar { ZB_FULL = 0, ZB_EMPTY = ZB_FULL + ZS, ZB_ZFULL = ZB_EMPTY + ZS, ZB_ZEMPTY = ZB_ZFULL + ZSZ,
+            ZB_AG_FULL = ZB_ZEMPTY + ZSZ, ZB_AG_EMPTY = ZB_AG_FULL + ZSA, ZB_G_READY = ZB_AG_EMPTY + ZSA,
+            ZB_COUNT = ZB_G_READY + ZSA };
 
 struct WideParams {
     DataPassParams dp;
-    float* G;            // [N][lda] scratch: w_j sigma_j dloss/dz, TF32-rounded; exactly 0 at missing entries
-    int n_jt, n_it;      // 128-feature tiles, 256-sample tiles
+    int n_jt, n_it;      // 128-feature tiles, 128-sample tiles
     int nks;             // 32-factor slabs = Kq / 32
     int corr;            // 1: BF16 first-order corrections of Z (precision 0 / 1), 0: plain TF32 (precision 2)
+    int flags;           // PMF_WIDE_FLAGS experiments (results wrong): 1 no data loads, 2 no G' stores
 };
 
 __global__ void __launch_bounds__(Z_NTHREADS, 1)
 zlink_kernel(const __grid_constant__ CUtensorMap tmYh, const __grid_constant__ CUtensorMap tmYb,
              const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUtensorMap tmXb,
-             const __grid_constant__ CUtensorMap tmA, const WideParams p) {
+             const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmG, const WideParams p) {
     const DataPassParams& dp = p.dp;
     if (dp.stop_flag != nullptr && *dp.stop_flag != 0) return;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
-    const uint32_t BARS = base + ZS * Z_STAGE;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + ZS * Z_STAGE + 8 * ZB_COUNT);
+    const uint32_t AG = base + ZS * Z_STAGE;
+    uint8_t* ag_ptr0 = gbase + ZS * Z_STAGE;
+    const uint32_t BARS = base + Z_SMEM_DATA;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + Z_SMEM_DATA + 8 * ZB_COUNT);
     __shared__ double red_smem[Z_NEPI];
     auto bar = [&](int b) { return BARS + 8u * (uint32_t)b; };
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
-        for (int b = 0; b < ZB_COUNT; ++b) mbar_init(bar(b), (b >= ZB_ZEMPTY) ? (uint32_t)Z_NEPI : 1u);
+        for (int b = 0; b < ZB_COUNT; ++b) {
+            const bool per_warp = (b >= ZB_ZEMPTY && b < ZB_ZEMPTY + ZSZ) || (b >= ZB_G_READY && b < ZB_G_READY + ZSA);
+            mbar_init(bar(b), per_warp ? (uint32_t)Z_NEPI : 1u);     // one arrive per epilogue warp
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == Z_W_MMA) {
@@ -163,6 +171,7 @@ zlink_kernel(const __grid_constant__ CUtensorMap tmYh, const __grid_constant__ C
     const uint32_t tm = *tmem_slot;
 
     if (warp == Z_W_TMA) {
+        // ================================ operand producer (L2) ====================================
         if (lane == 0) {
             Ring r;
             const uint32_t bytes = p.corr ? Z_STAGE : (Z_YH + Z_XH);
@@ -170,9 +179,6 @@ zlink_kernel(const __grid_constant__ CUtensorMap tmYh, const __grid_constant__ C
                 const int j0 = itx.outer * ZBJ;
                 for (int it = itx.in0; it < itx.in1; ++it) {
                     const int i0 = it * ZBI;
-                    // the data tile of this accumulator: on its way to L2 while the K-loop runs
-                    for (int q = 0; q < 4; ++q)
-                        if (i0 + 64 * q < dp.lda) tma_prefetch_2d(&tmA, i0 + 64 * q, j0);
                     for (int ks = 0; ks < p.nks; ++ks, r.next(ZS)) {
                         mbar_wait(bar(ZB_EMPTY + r.s), r.ph ^ 1);
                         mbar_expect_tx(bar(ZB_FULL + r.s), bytes);
@@ -187,18 +193,62 @@ zlink_kernel(const __grid_constant__ CUtensorMap tmYh, const __grid_constant__ C
                 }
             }
         }
+    } else if (warp == Z_W_TMA_A) {
+        // ================================ data producer (HBM stream) ===============================
+        if (lane == 0) {
+            Ring r;
+            for (RangeIter itx(dp.tc_cost_cum, p.n_jt, p.n_it); itx.next();) {
+                const int j0 = itx.outer * ZBJ;
+                for (int it = itx.in0; it < itx.in1; ++it) {
+                    for (int h = 0; h < 2; ++h, r.next(ZSA)) {
+                        const int i0 = it * ZBI + 64 * h;
+                        mbar_wait(bar(ZB_AG_EMPTY + r.s), r.ph ^ 1);
+                        if (p.flags & 1) { mbar_arrive(bar(ZB_AG_FULL + r.s)); continue; }
+                        mbar_expect_tx(bar(ZB_AG_FULL + r.s), Z_AG);
+                        for (int q = 0; q < 2; ++q)
+                            tma_load_2d(AG + r.s * Z_AG + q * 16384, &tmA, bar(ZB_AG_FULL + r.s), i0 + 32 * q, j0);
+                    }
+                }
+            }
+        }
+    } else if (warp == Z_W_GST) {
+        // ================================ G' store issuer ==========================================
+        // One TMA store per 32-sample box; a buffer returns to the data producer once the store engine has READ it.
+        // One store group stays in flight: buffer u - 1 is released after the stores of u have been issued.
+        if (lane == 0) {
+            Ring r;
+            int prev = -1;
+            for (RangeIter itx(dp.tc_cost_cum, p.n_jt, p.n_it); itx.next();) {
+                const int j0 = itx.outer * ZBJ;
+                for (int it = itx.in0; it < itx.in1; ++it) {
+                    for (int h = 0; h < 2; ++h, r.next(ZSA)) {
+                        const int i0 = it * ZBI + 64 * h;
+                        mbar_wait(bar(ZB_G_READY + r.s), r.ph);
+                        if (!(p.flags & 2)) {
+                            for (int q = 0; q < 2; ++q)
+                                if (i0 + 32 * q < dp.lda) tma_store_2d(&tmG, AG + r.s * Z_AG + q * 16384, i0 + 32 * q, j0);
+                        }
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                        if (prev >= 0) mbar_arrive(bar(ZB_AG_EMPTY + prev));
+                        prev = (int)r.s;
+                    }
+                }
+            }
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            if (prev >= 0) mbar_arrive(bar(ZB_AG_EMPTY + prev));
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");       // every store has been performed
+        }
     } else if (warp == Z_W_MMA) {
         if (elect_one()) {
             const uint32_t id_z = umma_idesc(ZBJ, ZBI, false, false);                       // TF32, both K-major
             const uint32_t id_zb = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(ZBI >> 3) << 17) | ((uint32_t)(ZBJ >> 4) << 24);   // BF16
-            Ring r;
-            uint32_t tcount = 0;
+            Ring r, rz;
             for (RangeIter itx(dp.tc_cost_cum, p.n_jt, p.n_it); itx.next();) {
-                for (int it = itx.in0; it < itx.in1; ++it, ++tcount) {
-                    const uint32_t b = tcount & 1u, ph = (tcount >> 1) & 1u;
-                    mbar_wait(bar(ZB_ZEMPTY + b), ph ^ 1u);
+                for (int it = itx.in0; it < itx.in1; ++it, rz.next(ZSZ)) {
+                    mbar_wait(bar(ZB_ZEMPTY + rz.s), rz.ph ^ 1u);
                     tc_fence_after();
-                    const uint32_t zt = tm + ZBI * b;
+                    const uint32_t zt = tm + ZBI * rz.s;
                     for (int ks = 0; ks < p.nks; ++ks, r.next(ZS)) {
                         mbar_wait(bar(ZB_FULL + r.s), r.ph);
                         tc_fence_after();
@@ -214,23 +264,27 @@ zlink_kernel(const __grid_constant__ CUtensorMap tmYh, const __grid_constant__ C
                         }
                         tc_commit(bar(ZB_EMPTY + r.s));
                     }
-                    tc_commit(bar(ZB_ZFULL + b));
+                    tc_commit(bar(ZB_ZFULL + rz.s));
                 }
             }
         }
         __syncwarp();
     } else {
         // ================================ epilogue warps ===========================================
-        // warp = (TMEM lane quarter, 64-sample chunk of the 256-sample tile); lane = feature row
-        const int quarter = warp & 3, c64 = warp >> 2;
+        // warp = (TMEM lane quarter, 16-sample chunk of the 64-sample sub-tile); lane = feature row
+        const int quarter = warp & 3, c16 = warp >> 2;
         const int lrow = 32 * quarter + lane;
         const uint32_t lane_addr = ((uint32_t)(32 * quarter)) << 16;
+        // this thread's 64 bytes of its row in box (c16 >> 1): logical 16-byte chunks 4 (c16 & 1) .. + 3 of the 128-byte
+        // row, physical chunk = logical ^ (row & 7)  (128-byte swizzle)
+        const uint32_t row_off = (uint32_t)(c16 >> 1) * 16384u + (uint32_t)lrow * 128u;
+        auto chunk_off = [&](int v) { return row_off + (uint32_t)(((4 * (c16 & 1) + v) ^ (lrow & 7)) << 4); };
         double loss_d = 0.0;
-        uint32_t tcount = 0;
+        Ring ra, rz;
         for (RangeIter itx(dp.tc_cost_cum, p.n_jt, p.n_it); itx.next();) {
             const int j = itx.outer * ZBJ + lrow;
             const bool jok = j < dp.N;
-            const int jj = jok ? j : dp.N - 1;           // padding rows follow the last column (same branch, no stores)
+            const int jj = jok ? j : dp.N - 1;           // padding rows follow the last column (same branch; their data are NaN)
             const float sigma = __expf(__ldg(dp.logsigma + jj));
             const float muj = __ldg(dp.mu + jj);
             const float wj = jok ? __ldg(dp.weight + jj) : 0.f;
@@ -239,29 +293,28 @@ zlink_kernel(const __grid_constant__ CUtensorMap tmYh, const __grid_constant__ C
             const float* th_range = dp.thresholds + 4 * (ci >> 8);
             const float gscale = sigma * wj;
             float dmu_acc = 0.f, loss_acc = 0.f;
-            const float* arow = dp.A + (size_t)jj * dp.lda;
-            float* grow = p.G + (size_t)jj * dp.lda;
-            for (int it = itx.in0; it < itx.in1; ++it, ++tcount) {
-                const uint32_t b = tcount & 1u, ph = (tcount >> 1) & 1u;
-                const int ib = it * ZBI + 64 * c64;
-                mbar_wait(bar(ZB_ZFULL + b), ph);
+            for (int it = itx.in0; it < itx.in1; ++it, rz.next(ZSZ)) {
+                mbar_wait(bar(ZB_ZFULL + rz.s), rz.ph);
                 tc_fence_after();
-                const uint32_t zt = tm + lane_addr + ZBI * b + 64 * c64;
 #pragma unroll 1
-                for (int hh = 0; hh < 4; ++hh) {
-                    const int i = ib + 16 * hh;
-                    if (i >= dp.lda) break;               // warp-uniform: lda is a multiple of 32
+                for (int h = 0; h < 2; ++h, ra.next(ZSA)) {
                     uint32_t z[16];
                     float a[16];
-                    TMEM_LD16(zt + 16 * hh, z);
-                    if (jok) {
-                        ldg256(arow + i, a, 0);
-                        ldg256(arow + i + 8, a, 8);
-                    } else {
+                    TMEM_LD16(tm + lane_addr + ZBI * rz.s + 64 * h + 16 * c16, z);
+                    mbar_wait(bar(ZB_AG_FULL + ra.s), ra.ph);
+                    uint8_t* abox = ag_ptr0 + ra.s * Z_AG;
 #pragma unroll
-                        for (int e = 0; e < 16; ++e) a[e] = __int_as_float(0x7fc00000);
+                    for (int v = 0; v < 4; ++v) {
+                        const float4 a4 = *reinterpret_cast<const float4*>(abox + chunk_off(v));
+                        a[4 * v] = a4.x; a[4 * v + 1] = a4.y; a[4 * v + 2] = a4.z; a[4 * v + 3] = a4.w;
                     }
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (h == 1) {
+                        // both halves of the accumulator have been read by this warp: the K-loop may reuse it
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_relaxed(bar(ZB_ZEMPTY + rz.s));
+                    }
                     if (dist == DIST_NORMAL) {
 #pragma unroll
                         for (int e = 0; e < 16; ++e) {
@@ -308,15 +361,14 @@ zlink_kernel(const __grid_constant__ CUtensorMap tmYh, const __grid_constant__ C
                             z[e] = rn_bits(lg.y * gscale);
                         }
                     }
-                    if (jok) {
-                        stg256(grow + i, z, 0);
-                        stg256(grow + i + 8, z, 8);
-                    }
+                    // G' over the data values this thread just read (same addresses), then hand the buffer to the store
+#pragma unroll
+                    for (int v = 0; v < 4; ++v)
+                        *reinterpret_cast<uint4*>(abox + chunk_off(v)) = make_uint4(z[4 * v], z[4 * v + 1], z[4 * v + 2], z[4 * v + 3]);
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar(ZB_G_READY + ra.s));
                 }
-                // every TMEM read of this warp has completed (wait::ld above): the accumulator may be overwritten
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_relaxed(bar(ZB_ZEMPTY + b));
             }
             loss_d += (double)(loss_acc * wj);
             // dmu_j = w_j sum_i g ; dlogsigma_j = sigma_j w_j sum_i g (the reference's ColScale quirk, src/layers.jl:39-44)
@@ -521,31 +573,35 @@ cudaError_t launch_data_pass_wide(const DataPassParams& dp, const WideScratch& w
         auto blocks = [](size_t n) { size_t b = (n + 255) / 256; return (unsigned)(b < 1184 ? (b ? b : 1) : 1184); };
         prep_wide_kernel<<<blocks(nx), 256, 0, s>>>(dp.X, ws.Xh, reinterpret_cast<uint2*>(ws.Xb), dp.Mp, dp.Kp, Kq, 0, dp.stop_flag);
         prep_wide_kernel<<<blocks(ny), 256, 0, s>>>(dp.Y, ws.Yh, reinterpret_cast<uint2*>(ws.Yb), dp.Np, dp.Kp, Kq, 1, dp.stop_flag);
+        const cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
         launched += 2;
     }
     const CUtensorMapDataType F32 = CU_TENSOR_MAP_DATA_TYPE_FLOAT32, BF16 = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
     const CUtensorMapSwizzle SW = CU_TENSOR_MAP_SWIZZLE_128B, SWA = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
     // 2. Z + link
     {
-        CUtensorMap tmYh, tmYb, tmXh, tmXb, tmA;
+        CUtensorMap tmYh, tmYb, tmXh, tmXb, tmA, tmG;
         bool ok = encode_map_2d(&tmYh, F32, ws.Yh, Kq, dp.Np, (uint64_t)Kq * 4, 32, ZBJ, SW) &&
                   encode_map_2d(&tmYb, BF16, ws.Yb, 2 * (uint64_t)Kq, dp.Np, (uint64_t)Kq * 4, 64, ZBJ, SW) &&
                   encode_map_2d(&tmXh, F32, ws.Xh, Kq, dp.Mp, (uint64_t)Kq * 4, 32, ZBI, SW) &&
                   encode_map_2d(&tmXb, BF16, ws.Xb, 2 * (uint64_t)Kq, dp.Mp, (uint64_t)Kq * 4, 64, ZBI, SW) &&
-                  encode_map_2d(&tmA, F32, dp.A, dp.lda, dp.N, (uint64_t)dp.lda * 4, 64, ZBJ, CU_TENSOR_MAP_SWIZZLE_NONE);
+                  encode_map_2d(&tmA, F32, dp.A, dp.lda, dp.N, (uint64_t)dp.lda * 4, 32, ZBJ, SW, /*nan_fill=*/true) &&
+                  encode_map_2d(&tmG, F32, ws.G, dp.lda, dp.N, (uint64_t)dp.lda * 4, 32, ZBJ, SW);
         if (!ok) return cudaErrorUnknown;
         WideParams p;
         p.dp = dp;
-        p.G = ws.G;
         p.n_jt = (dp.N + ZBJ - 1) / ZBJ;
         p.n_it = (dp.M + ZBI - 1) / ZBI;
         p.nks = Kq / 32;
         p.corr = precision >= 2 ? 0 : 1;
+        { const char* f = getenv("PMF_WIDE_FLAGS"); p.flags = f ? atoi(f) : 0; }
         cudaError_t e = cudaFuncSetAttribute(zlink_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Z_SMEM);
         if (e != cudaSuccess) return e;
         const long long n_tiles = (long long)p.n_jt * p.n_it;
         const int grid = n_tiles < n_sms ? (int)n_tiles : n_sms;
-        zlink_kernel<<<grid, Z_NTHREADS, Z_SMEM, s>>>(tmYh, tmYb, tmXh, tmXb, tmA, p);
+        zlink_kernel<<<grid, Z_NTHREADS, Z_SMEM, s>>>(tmYh, tmYb, tmXh, tmXb, tmA, tmG, p);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
         ++launched;
     }
     // 3. the two gradient contractions over G'
@@ -568,6 +624,7 @@ cudaError_t launch_data_pass_wide(const DataPassParams& dp, const WideScratch& w
         // dY[j,:] += sum_i G'[j,i] Xh[i,:]
         g.out = dp.dY; g.rows_pad = dp.Np; g.n_groups = (dp.N + 255) / 256; g.n_steps = (dp.M + 31) / 32;
         grad_gemm_kernel<false><<<grid_of(g), G_NTHREADS, G_SMEM, s>>>(tmGk, tmX, g);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
         // dX[i,:] += sum_j G'[j,i] Yh[j,:]
         g.out = dp.dX; g.rows_pad = dp.Mp; g.n_groups = (dp.M + 255) / 256; g.n_steps = (dp.N + 31) / 32;
         grad_gemm_kernel<true><<<grid_of(g), G_NTHREADS, G_SMEM, s>>>(tmGm, tmY, g);
