@@ -286,8 +286,9 @@ def main():
         sampler.start()
     eng.set_profiling(True)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    stream = torch.cuda.current_stream()
-    eng.set_stream(stream.cuda_stream)      # the library (kernels + its ncclAllReduce) runs on the timed stream
+    # the library (kernels + its ncclAllReduce) runs on a dedicated torch stream and the events are recorded on that
+    # stream (the legacy default stream has handle 0, which pmf_set_stream reads as "the handle's own stream")
+    stream = eng.torch_stream()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()

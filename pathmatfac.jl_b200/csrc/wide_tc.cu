@@ -5,20 +5,23 @@
 // tiles of a single fused tile pipeline (fused_tc.cu) no longer fit TMEM / shared memory.  The pass is therefore three
 // GEMM-shaped kernels around ONE M x N scratch matrix G' (4 HBM bytes per entry written once, read twice):
 //
-//   zlink_kernel      Z[j,i] = sum_k Y[j,k] X[i,k] as TF32 (Yh Xh) + one BF16 contraction over 2K for the first-order
-//                     corrections Yl Xh + Yh Xl (3xTF32-equivalent, see fused_tc.cu); K-loop over 32-wide slabs, both
-//                     operands K-major through a TMA-fed ring; accumulator tile 128 features x 256 samples in TMEM,
-//                     double buffered.  Epilogue (16 warps, lane = feature): ColScale / ColShift, noise-model loss and
-//                     dloss/dz with the NaN mask (src/layers.jl:9-90), column sums for dmu / dlogsigma, the data read
-//                     straight from global memory with 256-bit loads (its tile was prefetched to L2 by TMA when the
-//                     tile's K-loop started) and G' = w_j sigma_j dloss/dz stored with 256-bit stores.
+//   zlink_kernel      Z[j,i] = sum_k Y[j,k] X[i,k] from a two-term BF16 split of both operands, h = bf16(v),
+//                     l = bf16(v - h): Yh Xh + Yh Xl + Yl Xh, three BF16 contractions with FP32 accumulation in TMEM
+//                     (operand error 2^-17; measured |dZ| = 4e-6 rms(Z), against 7e-7 for the TF32 + BF16-correction
+//                     form of fused_tc.cu -- at half the operand bytes per factor and 3/4 of its tensor time, which
+//                     matters here because the K-loop re-streams both operands from L2 for every tile and the L2 -> SM
+//                     fabric, not the tensor pipe, bounds it).  K-loop over 64-wide slabs, operands K-major through a
+//                     TMA-fed ring; accumulator tile 128 features x 128 samples, four of them in TMEM.  Epilogue (16
+//                     warps, lane = feature): ColScale / ColShift, noise-model loss and dloss/dz with the NaN mask
+//                     (src/layers.jl:9-90), column sums for dmu / dlogsigma; the data tile comes in and
+//                     G' = w_j sigma_j dloss/dz goes out through shared memory by TMA.
 //   grad_gemm_kernel  <A_MN = false>  dY[j,:] += sum_i G'[j,i] Xh[i,:]   A = G' tile K-major, B = Xh rows MN-major
 //                     <A_MN = true >  dX[i,:] += sum_j G'[j,i] Yh[j,:]   A = G' tile MN-major (no transposition), B = Yh
 //                     two 128-row output tiles x K columns accumulate in TMEM over a contiguous range of 32-deep
 //                     contraction steps; the accumulators leave once per item as 128-bit REDs.
 //
-// Operand scratch (prep_wide_kernel, every epoch): Ph = rna_tf32(P) [rows][Kq] FP32 and Pb [rows][2 Kq] BF16, per
-// 32-factor slab [Pl | Ph] for Y (the A operand) and [Ph | Pl] for X (the B operand), Kq = roundup(K, 32), zero padded.
+// Operand scratch (prep_wide_kernel, every epoch): Ph = rna_tf32(P) [rows][Kq] FP32 (gradient contractions) and two BF16
+// planes Pb = [bf16(P) | bf16(P - bf16(P))], each [rows][Kq] (Z contraction); Kq = roundup(K, 64), zero padded.
 // Single-pass TF32 with round-to-nearest operands for the two gradient contractions (as in fused_tc.cu).
 // Batch shift / scale layers are not served here (the FP32 kernel runs those models when K > 64).
 #include <cuda.h>
@@ -118,7 +121,7 @@ __device__ __noinline__ float2 noise_eval_slow_w(int dist, float z, float a, con
 constexpr int ZBJ = 128, ZBI = 128, ZS = 2, ZSZ = 4, ZSA = 3;
 constexpr uint32_t Z_YH = 16384, Z_YB = 16384, Z_XH = 16384, Z_XB = 16384;
 constexpr uint32_t Z_OFF_YB = Z_YH, Z_OFF_XH = Z_YH + Z_YB, Z_OFF_XB = Z_YH + Z_YB + Z_XH;
-constexpr uint32_t Z_STAGE = Z_YH + Z_YB + Z_XH + Z_XB;                      // 64 KB per 32-factor slab
+constexpr uint32_t Z_STAGE = Z_YH + Z_YB + Z_XH + Z_XB;                      // 64 KB per 64-factor slab: Yh | Yl | Xh | Xl (BF16)
 constexpr uint32_t Z_AG = 32768;                                            // 128 features x 64 samples of A / G'
 constexpr int Z_NEPI = 16, Z_W_TMA = Z_NEPI, Z_W_MMA = Z_NEPI + 1, Z_W_TMA_A = Z_NEPI + 2, Z_W_GST = Z_NEPI + 3,
               Z_NTHREADS = 32 * (Z_NEPI + 4);
@@ -131,8 +134,7 @@ enum ZBar { ZB_FULL = 0, ZB_EMPTY = ZB_FULL + ZS, ZB_ZFULL = ZB_EMPTY + ZS, ZB_Z
 struct WideParams {
     DataPassParams dp;
     int n_jt, n_it;      // 128-feature tiles, 128-sample tiles
-    int nks;             // 32-factor slabs = Kq / 32
-    int corr;            // 1: BF16 first-order corrections of Z (precision 0 / 1), 0: plain TF32 (precision 2)
+    int nks;             // 64-factor slabs = Kq / 64
     int flags;           // PMF_WIDE_FLAGS experiments (results wrong): 1 no data loads, 2 no G' stores
 };
 
@@ -174,21 +176,18 @@ zlink_kernel(const __grid_constant__ CUtensorMap tmYh, const __grid_constant__ C
         // ================================ operand producer (L2) ====================================
         if (lane == 0) {
             Ring r;
-            const uint32_t bytes = p.corr ? Z_STAGE : (Z_YH + Z_XH);
             for (RangeIter itx(dp.tc_cost_cum, p.n_jt, p.n_it); itx.next();) {
                 const int j0 = itx.outer * ZBJ;
                 for (int it = itx.in0; it < itx.in1; ++it) {
                     const int i0 = it * ZBI;
                     for (int ks = 0; ks < p.nks; ++ks, r.next(ZS)) {
                         mbar_wait(bar(ZB_EMPTY + r.s), r.ph ^ 1);
-                        mbar_expect_tx(bar(ZB_FULL + r.s), bytes);
+                        mbar_expect_tx(bar(ZB_FULL + r.s), Z_STAGE);
                         const uint32_t st = base + r.s * Z_STAGE;
-                        tma_load_2d(st, &tmYh, bar(ZB_FULL + r.s), 32 * ks, j0);
-                        tma_load_2d(st + Z_OFF_XH, &tmXh, bar(ZB_FULL + r.s), 32 * ks, i0);
-                        if (p.corr) {
-                            tma_load_2d(st + Z_OFF_YB, &tmYb, bar(ZB_FULL + r.s), 64 * ks, j0);
-                            tma_load_2d(st + Z_OFF_XB, &tmXb, bar(ZB_FULL + r.s), 64 * ks, i0);
-                        }
+                        tma_load_2d(st, &tmYh, bar(ZB_FULL + r.s), 64 * ks, j0);
+                        tma_load_2d(st + Z_OFF_XH, &tmXh, bar(ZB_FULL + r.s), 64 * ks, i0);
+                        tma_load_2d(st + Z_OFF_YB, &tmYb, bar(ZB_FULL + r.s), 64 * ks, j0);
+                        tma_load_2d(st + Z_OFF_XB, &tmXb, bar(ZB_FULL + r.s), 64 * ks, i0);
                     }
                 }
             }
@@ -241,8 +240,8 @@ zlink_kernel(const __grid_constant__ CUtensorMap tmYh, const __grid_constant__ C
         }
     } else if (warp == Z_W_MMA) {
         if (elect_one()) {
-            const uint32_t id_z = umma_idesc(ZBJ, ZBI, false, false);                       // TF32, both K-major
-            const uint32_t id_zb = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(ZBI >> 3) << 17) | ((uint32_t)(ZBJ >> 4) << 24);   // BF16
+            // BF16 x BF16 -> F32 (kind::f16), both operands K-major, K = 16 per instruction
+            const uint32_t id_zb = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(ZBI >> 3) << 17) | ((uint32_t)(ZBJ >> 4) << 24);
             Ring r, rz;
             for (RangeIter itx(dp.tc_cost_cum, p.n_jt, p.n_it); itx.next();) {
                 for (int it = itx.in0; it < itx.in1; ++it, rz.next(ZSZ)) {
@@ -253,15 +252,17 @@ zlink_kernel(const __grid_constant__ CUtensorMap tmYh, const __grid_constant__ C
                         mbar_wait(bar(ZB_FULL + r.s), r.ph);
                         tc_fence_after();
                         const uint32_t st = base + r.s * Z_STAGE;
-                        const uint64_t yh = umma_desc_k(st), xh = umma_desc_k(st + Z_OFF_XH);
+                        const uint64_t yh = umma_desc_k(st), yl = umma_desc_k(st + Z_OFF_YB);
+                        const uint64_t xh = umma_desc_k(st + Z_OFF_XH), xl = umma_desc_k(st + Z_OFF_XB);
 #pragma unroll
-                        for (int s = 0; s < 4; ++s)
-                            mma_ss(zt, yh + (uint64_t)(2 * s), xh + (uint64_t)(2 * s), id_z, (ks > 0 || s > 0) ? 1u : 0u);
-                        if (p.corr) {
-                            const uint64_t yb = umma_desc_k(st + Z_OFF_YB), xb = umma_desc_k(st + Z_OFF_XB);
+                        for (int s = 0; s < 4; ++s)       // Yh Xh
+                            mma_ss_f16(zt, yh + (uint64_t)(2 * s), xh + (uint64_t)(2 * s), id_zb, (ks > 0 || s > 0) ? 1u : 0u);
 #pragma unroll
-                            for (int s = 0; s < 4; ++s) mma_ss_f16(zt, yb + (uint64_t)(2 * s), xb + (uint64_t)(2 * s), id_zb, 1u);
-                        }
+                        for (int s = 0; s < 4; ++s)       // Yh Xl
+                            mma_ss_f16(zt, yh + (uint64_t)(2 * s), xl + (uint64_t)(2 * s), id_zb, 1u);
+#pragma unroll
+                        for (int s = 0; s < 4; ++s)       // Yl Xh
+                            mma_ss_f16(zt, yl + (uint64_t)(2 * s), xh + (uint64_t)(2 * s), id_zb, 1u);
                         tc_commit(bar(ZB_EMPTY + r.s));
                     }
                     tc_commit(bar(ZB_ZFULL + rz.s));
@@ -529,7 +530,7 @@ grad_gemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant_
 
 // Operand split of a factor matrix P [rows][Kp] for the wide path (see the file header).  One thread per 4 factors.
 __global__ void prep_wide_kernel(const float* __restrict__ P, float* __restrict__ Ph, uint2* __restrict__ Pb, int rows, int Kp,
-                                 int Kq, int a_side, const int* stop_flag) {
+                                 int Kq, const int* stop_flag) {
     if (stop_flag != nullptr && *stop_flag != 0) return;
     const int q4 = Kq >> 2;
     const size_t n4 = (size_t)rows * q4;
@@ -542,14 +543,13 @@ __global__ void prep_wide_kernel(const float* __restrict__ P, float* __restrict_
         h.x = __uint_as_float(rna_tf32(v.x)); h.y = __uint_as_float(rna_tf32(v.y));
         h.z = __uint_as_float(rna_tf32(v.z)); h.w = __uint_as_float(rna_tf32(v.w));
         *reinterpret_cast<float4*>(Ph + row * Kq + k) = h;
-        const uint2 hb = make_uint2(pack_bf16(h.x, h.y), pack_bf16(h.z, h.w));
-        const uint2 lb = make_uint2(pack_bf16(v.x - h.x, v.y - h.y), pack_bf16(v.z - h.z, v.w - h.w));
-        // BF16 row of 2 Kq: slab s = k / 32 occupies elements 64 s .. 64 s + 63 as two 32-element halves
-        const size_t e0 = row * (size_t)(2 * Kq) + (size_t)(64 * (k >> 5) + (k & 31));     // element index of the first half
-        uint2* first = Pb + (e0 >> 2);
-        uint2* second = Pb + ((e0 + 32) >> 2);
-        if (a_side) { *first = lb; *second = hb; }      // Y: [Yl | Yh]
-        else { *first = hb; *second = lb; }             // X: [Xh | Xl]
+        // two-term BF16 split: b = bf16(v) (round to nearest), l = bf16(v - b)
+        const uint2 hb = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+        const float bx = __uint_as_float(hb.x << 16), by = __uint_as_float(hb.x & 0xffff0000u);
+        const float bz = __uint_as_float(hb.y << 16), bw = __uint_as_float(hb.y & 0xffff0000u);
+        const uint2 lb = make_uint2(pack_bf16(v.x - bx, v.y - by), pack_bf16(v.z - bz, v.w - bw));
+        Pb[idx] = hb;                               // plane 0: [rows][Kq] BF16
+        Pb[n4 + idx] = lb;                          // plane 1
     }
 }
 
@@ -559,20 +559,20 @@ bool wide_supported(const DataPassParams& p) {
     return p.Kp > 64 && p.Kp <= 256 && p.n_batch_views == 0 && p.col_ssq == nullptr;
 }
 
-size_t wide_scratch_floats(int rows_pad, int Kp) { return (size_t)rows_pad * (size_t)((Kp + 31) / 32 * 32); }
+size_t wide_scratch_floats(int rows_pad, int Kp) { return (size_t)rows_pad * (size_t)((Kp + 63) / 64 * 64); }
 
 cudaError_t launch_data_pass_wide(const DataPassParams& dp, const WideScratch& ws, int precision, cudaStream_t s, int n_sms,
                                   int* n_launches) {
     if (!wide_supported(dp)) return cudaErrorInvalidValue;
-    const int Kq = (dp.Kp + 31) / 32 * 32;
+    const int Kq = (dp.Kp + 63) / 64 * 64;
     const int Kc = (dp.Kp + 15) / 16 * 16;
     int launched = 0;
     // 1. operand split of X and Y
     {
         const size_t nx = (size_t)dp.Mp * (Kq >> 2), ny = (size_t)dp.Np * (Kq >> 2);
         auto blocks = [](size_t n) { size_t b = (n + 255) / 256; return (unsigned)(b < 1184 ? (b ? b : 1) : 1184); };
-        prep_wide_kernel<<<blocks(nx), 256, 0, s>>>(dp.X, ws.Xh, reinterpret_cast<uint2*>(ws.Xb), dp.Mp, dp.Kp, Kq, 0, dp.stop_flag);
-        prep_wide_kernel<<<blocks(ny), 256, 0, s>>>(dp.Y, ws.Yh, reinterpret_cast<uint2*>(ws.Yb), dp.Np, dp.Kp, Kq, 1, dp.stop_flag);
+        prep_wide_kernel<<<blocks(nx), 256, 0, s>>>(dp.X, ws.Xh, reinterpret_cast<uint2*>(ws.Xb), dp.Mp, dp.Kp, Kq, dp.stop_flag);
+        prep_wide_kernel<<<blocks(ny), 256, 0, s>>>(dp.Y, ws.Yh, reinterpret_cast<uint2*>(ws.Yb), dp.Np, dp.Kp, Kq, dp.stop_flag);
         const cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
         launched += 2;
@@ -582,10 +582,13 @@ cudaError_t launch_data_pass_wide(const DataPassParams& dp, const WideScratch& w
     // 2. Z + link
     {
         CUtensorMap tmYh, tmYb, tmXh, tmXb, tmA, tmG;
-        bool ok = encode_map_2d(&tmYh, F32, ws.Yh, Kq, dp.Np, (uint64_t)Kq * 4, 32, ZBJ, SW) &&
-                  encode_map_2d(&tmYb, BF16, ws.Yb, 2 * (uint64_t)Kq, dp.Np, (uint64_t)Kq * 4, 64, ZBJ, SW) &&
-                  encode_map_2d(&tmXh, F32, ws.Xh, Kq, dp.Mp, (uint64_t)Kq * 4, 32, ZBI, SW) &&
-                  encode_map_2d(&tmXb, BF16, ws.Xb, 2 * (uint64_t)Kq, dp.Mp, (uint64_t)Kq * 4, 64, ZBI, SW) &&
+        // BF16 planes: hi at the base, lo one plane (rows x Kq elements) further
+        const uint16_t* yb = static_cast<const uint16_t*>(ws.Yb);
+        const uint16_t* xb = static_cast<const uint16_t*>(ws.Xb);
+        bool ok = encode_map_2d(&tmYh, BF16, yb, Kq, dp.Np, (uint64_t)Kq * 2, 64, ZBJ, SW) &&
+                  encode_map_2d(&tmYb, BF16, yb + (size_t)dp.Np * Kq, Kq, dp.Np, (uint64_t)Kq * 2, 64, ZBJ, SW) &&
+                  encode_map_2d(&tmXh, BF16, xb, Kq, dp.Mp, (uint64_t)Kq * 2, 64, ZBI, SW) &&
+                  encode_map_2d(&tmXb, BF16, xb + (size_t)dp.Mp * Kq, Kq, dp.Mp, (uint64_t)Kq * 2, 64, ZBI, SW) &&
                   encode_map_2d(&tmA, F32, dp.A, dp.lda, dp.N, (uint64_t)dp.lda * 4, 32, ZBJ, SW, /*nan_fill=*/true) &&
                   encode_map_2d(&tmG, F32, ws.G, dp.lda, dp.N, (uint64_t)dp.lda * 4, 32, ZBJ, SW);
         if (!ok) return cudaErrorUnknown;
@@ -593,8 +596,7 @@ cudaError_t launch_data_pass_wide(const DataPassParams& dp, const WideScratch& w
         p.dp = dp;
         p.n_jt = (dp.N + ZBJ - 1) / ZBJ;
         p.n_it = (dp.M + ZBI - 1) / ZBI;
-        p.nks = Kq / 32;
-        p.corr = precision >= 2 ? 0 : 1;
+        p.nks = Kq / 64;
         { const char* f = getenv("PMF_WIDE_FLAGS"); p.flags = f ? atoi(f) : 0; }
         cudaError_t e = cudaFuncSetAttribute(zlink_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Z_SMEM);
         if (e != cudaSuccess) return e;

@@ -35,8 +35,9 @@ def shard_plan(M: int, world: int) -> List[range]:
 class ShardedFit:
     """Drives pmf_fit_start / pmf_epoch_begin / all-reduce / pmf_epoch_end on one rank.  The engine supplies
     ``shared_buffers()`` (torch tensors aliasing the handle's shared gradient buffer and its rank-local loss
-    scalars) and ``use_torch_stream()`` (so that the collective is ordered with the kernels); the CPU tests drive
-    the same sequence through a stub engine over gloo."""
+    scalars) and ``torch_stream()`` (the stream the library runs on, made current around the loop so that every
+    collective is ordered with the kernels; None on a CPU engine); the CPU tests drive the same sequence through a
+    stub engine over gloo."""
 
     def __init__(self, engine, group=None):
         import torch.distributed as dist
@@ -44,9 +45,16 @@ class ShardedFit:
         self.eng = engine
         self.group = group
         self.grads, self.scalars = engine.shared_buffers()
-        engine.use_torch_stream()
+        self.stream = engine.torch_stream()
 
     def fit(self, opts) -> Dict:
+        if self.stream is None:
+            return self._fit(opts)
+        import torch
+        with torch.cuda.stream(self.stream):
+            return self._fit(opts)
+
+    def _fit(self, opts) -> Dict:
         eng, lib = self.eng, self.eng.lib
         eng._ck(lib.pmf_fit_start(eng.h, C.byref(opts)))
         check = opts.check_every if opts.check_every > 0 else 8

@@ -137,10 +137,16 @@ class Engine:
         scalars = torch.as_tensor(_DeviceBuffer(p.value, n.value, "<f8"), device=dev)
         return grads, scalars
 
-    def use_torch_stream(self):
-        """Run the library on torch's current stream of the handle's device."""
+    def torch_stream(self):
+        """A torch stream of the handle's device that the library runs on from now on, to be made current around
+        every collective (``with torch.cuda.stream(s)``): torch.distributed orders a collective against the CURRENT
+        stream.  The legacy default stream (handle 0) cannot be used -- ``pmf_set_stream(h, NULL)`` selects the handle's
+        own non-blocking stream, which torch knows nothing about -- so a dedicated stream is created."""
         import torch
-        self.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+        s = torch.cuda.Stream(device=self.device)
+        self.set_stream(s.cuda_stream)
+        self._torch_stream = s          # keep it alive as long as the handle uses it
+        return s
 
     # -- uploads ---------------------------------------------------------------------------
     def push_data(self, D):

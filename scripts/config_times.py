@@ -86,11 +86,11 @@ def main():
         eng.fit(eng.make_opts(epoch=1, max_epochs=3, **common))
         eng.set_profiling(True)
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        eng.set_stream(torch.cuda.current_stream().cuda_stream)
+        stream = eng.torch_stream()
         torch.cuda.synchronize()
-        ev0.record()
+        ev0.record(stream)
         h = eng.fit(eng.make_opts(epoch=4, max_epochs=3 + args.steps, **common))
-        ev1.record()
+        ev1.record(stream)
         torch.cuda.synchronize()
         ms = ev0.elapsed_time(ev1) / args.steps
         n, dp_ms, dp_min = eng.get_profile()

@@ -173,8 +173,9 @@ class _StubEngine:
     def shared_buffers(self):
         return self._g, self._s
 
-    def use_torch_stream(self):
+    def torch_stream(self):
         self.stream_calls += 1
+        return None
 
     def _ck(self, rc):
         assert rc == 0
