@@ -191,6 +191,11 @@ typedef struct {
 int pmf_loss_grad(pmf_handle h, int32_t include_reg, pmf_losses* out, float* dX, float* dY,
                   float* dlogsigma, float* dmu);
 int pmf_get_batch_grads(pmf_handle h, int32_t view, float* dlogdelta, float* dtheta);
+/* d loss / d(t1, t2) of every noise range after pmf_loss_grad ([n_ranges][2]; zero for non-ordinal ranges) and the
+ * current extended thresholds [n_ranges][4] (after a fit with update_noise_models: the trained values, which the
+ * caller writes back into noise.ext_thresholds; src/fit.jl:228-242, src/impute.jl:15-24). */
+int pmf_get_threshold_grads(pmf_handle h, int32_t n_ranges, float* dthr);
+int pmf_get_thresholds(pmf_handle h, int32_t n_ranges, float* thresholds);
 
 typedef struct {
     /* kwargs of mf_fit! / MF.fit! (src/fit.jl:9-36, 923-939) */
@@ -201,11 +206,26 @@ typedef struct {
     double  rel_tol, abs_tol;
     int32_t update_X, update_Y, update_col_layers;
     int32_t kernel;              /* pmf_kernel_kind                                    */
-    int32_t precision;           /* TC kernel: 0 = 3xTF32 everywhere (FP32 parity),
-                                    1 = 3xTF32 for Z, TF32 for dX/dY, 2 = TF32         */
+    int32_t precision;           /* tensor-core kernels only (PMF_KERNEL_FFMA is exact FP32 throughout):
+                                    0, 1 (identical): Z = X'Y at FP32 level -- K <= 64: TF32 product + BF16
+                                       first-order corrections; K > 64: two-term BF16 split, three
+                                       contractions -- so loss and column / batch gradients agree with FP32
+                                       to ~1e-6; the contractions dX = Y G', dY = X G are single-pass TF32
+                                       with round-to-nearest operands (FP32 accumulation): ~1-2e-4 relative
+                                       on small problems, 3-4e-5 at 10 000 x 30 000.  PMF_KERNEL_AUTO
+                                       therefore picks these kernels for large problems only.
+                                    2: plain TF32 for Z as well (K <= 64; ignored for K > 64)            */
     int32_t check_every;         /* epochs launched between host checks of the stop flag */
     int32_t no_terminate;        /* bench hook: run every epoch up to max_epochs, never stop on
                                     a tolerance / loss-increase test (losses still recorded) */
+    int32_t update_noise_models; /* src/fit.jl:14 (true in every call of the reference): train the interior
+                                    thresholds of the ordinal noise models with the same optimiser
+                                    (the trainable noise parameters are INFERRED); no effect
+                                    on models without ordinal columns.  Default 1.                     */
+    int32_t alternating;         /* SURVEY App. D1, the unknown epoch order of MF.fit!: 0 (default) = one pass,
+                                    simultaneous step of every parameter; 1 = column-side step (Y, layers,
+                                    thresholds) from the first pass, then the row-side step (X) from a second
+                                    pass at the new column-side parameters (pmf_fit only)              */
 } pmf_fit_opts;
 
 typedef struct {

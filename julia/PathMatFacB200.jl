@@ -1,6 +1,10 @@
 # PathMatFacB200.jl -- Julia shim that drops libpmf (include/pmf.h) in for the fit-loop hot path
-# of PathMatFac.jl.  It overrides ONLY `PathMatFac.mf_fit!` (src/fit.jl:9-38); the staging code
-# (`fit!`, `mf_fit_adapt_lr!`, `basic_fit!`, ... src/fit.jl) keeps running in Julia unchanged.
+# of PathMatFac.jl.  `using PathMatFacB200` REDEFINES the method the reference itself calls,
+# `PathMatFac.mf_fit!(model::PathMatFacModel; kwargs...)` (src/fit.jl:9-38; its only caller is
+# `mf_fit_adapt_lr!`, src/fit.jl:58), so the staging code (`fit!`, `mf_fit_adapt_lr!`, `basic_fit!`, ...,
+# `transform`) keeps running in Julia unchanged and every inner fit lands on the GPU.  A model is bound to a
+# device handle with `to_device(model)` (the `gpu(model)` of fit_matfac.jl:325-340); a model without a handle
+# gets a transient one for the duration of the call.  There is no CPU fallback.
 #
 # WRITE-ONLY in this repository: the build image has no Julia runtime, so this file is exercised
 # only indirectly -- the Python mirror (pathmatfac.jl_b200/fit.py) drives the very same C ABI
@@ -25,6 +29,7 @@ mutable struct PmfFitOpts            # mirrors pmf_fit_opts
     rel_tol::Float64; abs_tol::Float64
     update_X::Int32; update_Y::Int32; update_col_layers::Int32
     kernel::Int32; precision::Int32; check_every::Int32; no_terminate::Int32
+    update_noise_models::Int32; alternating::Int32
 end
 
 mutable struct PmfHistory            # mirrors pmf_history
@@ -47,17 +52,36 @@ unwrap_reg(r) = isa(r, PM.FrozenRegularizer) ? r.reg : r
 f32(a) = convert(Array{Float32}, a)
 i32(a) = convert(Vector{Int32}, a)
 
-"""gpu(model) equivalent (fit_matfac.jl:325-340): create the handle and upload the data once."""
-function to_device(model::PM.PathMatFacModel; device::Integer=0)
+# model => handle.  Keyed by object identity: the stage functions mutate the model in place and pass the same
+# object down to mf_fit! (src/fit.jl:58), which looks its handle up here.
+const HANDLES = IdDict{PM.PathMatFacModel,Handle}()
+
+function create_handle(model::PM.PathMatFacModel, device::Integer)
     M, N = size(model.data); K = size(model.matfac.X, 1)
     h = Ref{Handle}(C_NULL)
     check(C_NULL, ccall((:pmf_create, LIBPMF), Cint, (Ref{PmfDims}, Ref{Handle}), PmfDims(M, N, K, device), h))
     A = f32(model.data)                                    # M x N column-major, NaN = missing
     check(h[], ccall((:pmf_set_data, LIBPMF), Cint, (Handle, Ptr{Float32}), h[], A))
+    push_layout!(h[], model)                               # once per handle: it re-allocates the batch tables
     return h[]
 end
 
-release(h::Handle) = ccall((:pmf_destroy, LIBPMF), Cint, (Handle,), h)
+"""gpu(model) equivalent (fit_matfac.jl:325-340): create the handle, upload the data once, bind it to the model."""
+function to_device(model::PM.PathMatFacModel; device::Integer=0)
+    haskey(HANDLES, model) && return HANDLES[model]
+    HANDLES[model] = create_handle(model, device)
+end
+
+"""cpu(model) equivalent: the host model is current after every fit, so this only frees the device side."""
+function release(model::PM.PathMatFacModel)
+    h = pop!(HANDLES, model, C_NULL)
+    h == C_NULL || release(h)
+    return model
+end
+function release(h::Handle)
+    for (opt, hs) in OPT_OWNERS; filter!(x -> x != h, hs); end
+    ccall((:pmf_destroy, LIBPMF), Cint, (Handle,), h)
+end
 release_cached_memory() = ccall((:pmf_release_cached_memory, LIBPMF), Cint, ())
 
 function push_params!(h::Handle, model)
@@ -68,6 +92,20 @@ function push_params!(h::Handle, model)
                    f32(unwrap(layers[1]).logsigma), f32(unwrap(layers[3]).mu)))
     if isa(unwrap(layers[2]), PM.BatchScale)
         ld = unwrap(layers[2]).logdelta; th = unwrap(layers[4]).theta
+        for v in 1:length(ld.values)
+            check(h, ccall((:pmf_set_batch_values, LIBPMF), Cint, (Handle, Int32, Ptr{Float32}, Ptr{Float32}),
+                           h, v - 1, f32(ld.values[v]), f32(th.values[v])))
+        end
+    end
+end
+
+# Batch layout (views, batch counts, batch of every sample): structure, not values.  Sent when the handle is created;
+# sending an identical layout again is a no-op in the library (parameters, AdaGrad accumulators and the tensor-core
+# batch plan survive), a different one re-allocates the batch tables.
+function push_layout!(h::Handle, model)
+    layers = model.matfac.col_transform.layers
+    if isa(unwrap(layers[2]), PM.BatchScale)
+        ld = unwrap(layers[2]).logdelta
         nv = length(ld.col_ranges); M = size(model.data, 1)
         cs = i32([r.start - 1 for r in ld.col_ranges]); ce = i32([r.stop for r in ld.col_ranges])
         nb = i32([size(v, 1) for v in ld.values])
@@ -78,10 +116,6 @@ function push_params!(h::Handle, model)
         end
         check(h, ccall((:pmf_set_batch_layout, LIBPMF), Cint, (Handle, Int32, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}),
                        h, nv, cs, ce, nb, bos))
-        for v in 1:nv
-            check(h, ccall((:pmf_set_batch_values, LIBPMF), Cint, (Handle, Int32, Ptr{Float32}, Ptr{Float32}),
-                           h, v - 1, f32(ld.values[v]), f32(th.values[v])))
-        end
     else
         check(h, ccall((:pmf_set_batch_layout, LIBPMF), Cint, (Handle, Int32, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}),
                        h, 0, C_NULL, C_NULL, C_NULL, C_NULL))
@@ -105,7 +139,27 @@ function pull_params!(h::Handle, model)
             ld.values[v] .= a; th.values[v] .= b
         end
     end
+    # interior ordinal thresholds, trained when update_noise_models (src/fit.jl:14)
+    nm = mf.noise_model
+    if any(hasproperty(n, :ext_thresholds) for n in nm.noises)
+        th4 = zeros(Float32, 4, length(nm.noises))
+        check(h, ccall((:pmf_get_thresholds, LIBPMF), Cint, (Handle, Int32, Ptr{Float32}), h, length(nm.noises), th4))
+        for (i, n) in enumerate(nm.noises); hasproperty(n, :ext_thresholds) && (n.ext_thresholds[2:3] .= th4[2:3, i]); end
+    end
 end
+
+function recognise_closure(r::Function, K::Integer)
+    probes = (ones(Float32, K, 3), Float32.(reshape(sin.(1:5K), K, 5)), 3f0 .* Float32.(reshape(cos.(1:2K), K, 2)))
+    vals = [Float64(r(P)) for P in probes]
+    all(==(0.0), vals) && return nothing
+    ssq = [sum(Float64.(P) .^ 2) for P in probes]
+    w = vals[1] / (0.5 * ssq[1])
+    (w > 0 && all(abs(v - 0.5 * w * q) <= 1e-4 * abs(0.5 * w * q) for (v, q) in zip(vals, ssq))) && return w
+    error("PathMatFacB200: unsupported regulariser closure (only `x -> 0` and `x -> 0.5*w*sum(x.*x)`, the closures ",
+          "src/fit.jl installs, can be moved to the device); use a regulariser object")
+end
+
+const model_K = Ref{Any}(zeros(Float32, 1, 1))     # X of the model being marshalled (size(., 1) = K), set by push_regs!
 
 # one regulariser object -> ABI calls; `which` 0 = X_reg, 1 = Y_reg; p = mixture weight
 function install_reg!(h::Handle, which::Integer, r, p::Real)
@@ -136,7 +190,15 @@ function install_reg!(h::Handle, which::Integer, r, p::Real)
                         Ptr{Int32}, Ptr{Int32}, Ptr{Float32}, Ptr{Float32}, Float32, Float32, Float32, Int32),
                        h, which, nv, aa[1], aa[2], aa[3], ab[1], ab[2], ab[3], bb[1], bb[2], bb[3], xv, p, 0f0, 0f0, 0))
     elseif isa(r, Function)
-        # `x->0` closures installed by the stages (src/fit.jl:415,769): nothing to install
+        # The stages install anonymous functions: `X -> 0.5f0*sum(X.*X)` (src/fit.jl:686, the DEFAULT fit! path),
+        # `0.05 .* sum(x.^2)`-style quadratics (:266-267) and the zero closures `X -> 0f0` / `y -> 0` / `x -> 0.0`
+        # (:415, :769, src/transform.jl:61,70).  A closure has no fields to marshal, so it is identified by probing:
+        # identically zero -> nothing to install; 0.5 w sum(x^2) with one scalar w -> L2 with uniform weight w.
+        # Anything else is an error: a penalty is never dropped silently.
+        K = size(model_K[], 1)
+        w = recognise_closure(r, K)
+        w === nothing || check(h, ccall((:pmf_set_reg_l2, LIBPMF), Cint, (Handle, Int32, Ptr{Float32}, Float32),
+                                        h, which, fill(Float32(w), K), p))
     else
         error("PathMatFacB200: unsupported regulariser ", typeof(r))
     end
@@ -144,6 +206,7 @@ end
 
 function push_regs!(h::Handle, model)
     mf = model.matfac
+    model_K[] = mf.X
     for (which, reg) in ((0, mf.X_reg), (1, mf.Y_reg))
         check(h, ccall((:pmf_clear_reg, LIBPMF), Cint, (Handle, Int32), h, which))
         if isa(reg, PM.CompositeRegularizer)
@@ -178,24 +241,44 @@ function push_regs!(h::Handle, model)
                    h, length(cs), cs, ce, dc, th, w))
 end
 
-const OPT_OWNER = IdDict{Any,Handle}()   # a fresh Flux AdaGrad object => fresh accumulators (src/fit.jl:55)
+# A fresh Flux AdaGrad object means fresh accumulators (src/fit.jl:55); the same object across the LR-halving
+# restarts of mf_fit_adapt_lr! keeps them (:55-64).  Per optimiser the handles whose accumulators belong to it.
+const OPT_OWNERS = IdDict{Any,Vector{Handle}}()
 
-"""Replacement for `PathMatFac.mf_fit!` (src/fit.jl:9-38) on a device-resident model."""
-function mf_fit!(model::PM.PathMatFacModel, h::Handle; opt, max_epochs=1000, epoch=1, update_X=false, update_Y=false,
-                 update_col_layers=false, rel_tol=1e-5, abs_tol=1e-5, kwargs...)
-    push_params!(h, model); push_regs!(h, model)
-    if get(OPT_OWNER, opt, C_NULL) != h
-        check(h, ccall((:pmf_reset_opt_state, LIBPMF), Cint, (Handle, Float32), h, opt.epsilon)); OPT_OWNER[opt] = h
+"""
+The method the reference calls (src/fit.jl:58: `mf_fit!(model; opt=opt, capacity=..., max_epochs=..., epoch=...,
+keep_history=true, kwargs...)`), same keyword surface as src/fit.jl:9-21.  `capacity` is accepted and ignored (the
+fused pass never materialises Z), `scale_column_losses=true` is refused (never used by the reference).
+"""
+function PM.mf_fit!(model::PM.PathMatFacModel; scale_column_losses=false, update_X=false, update_Y=false,
+                    update_row_layers=false, update_col_layers=false, update_noise_models=true,
+                    reg_relative_weighting=false, update_X_reg=false, update_Y_reg=false,
+                    update_row_layers_reg=false, update_col_layers_reg=false, keep_history=true,
+                    opt=PM.construct_optimizer(model, 1.0), max_epochs=1000, epoch=1, rel_tol=1e-5, abs_tol=1e-5,
+                    capacity=nothing, verbosity=1, print_prefix="", alternating=false, device=0, kwargs...)
+    scale_column_losses && error("PathMatFacB200: scale_column_losses=true is not implemented (unused by the reference)")
+    transient = !haskey(HANDLES, model)
+    h = transient ? create_handle(model, device) : HANDLES[model]
+    try
+        push_params!(h, model); push_regs!(h, model)
+        owners = get!(OPT_OWNERS, opt, Handle[])
+        if !(h in owners)
+            check(h, ccall((:pmf_reset_opt_state, LIBPMF), Cint, (Handle, Float32), h, opt.epsilon)); push!(owners, h)
+        end
+        cap = max(1, max_epochs - epoch + 1)
+        losses = [zeros(Float64, cap) for _ in 1:5]
+        hist = PmfHistory(0, 0, 0, cap, pointer.(losses)..., 0f0, 0)
+        opts = PmfFitOpts(max_epochs, epoch, opt.eta, opt.epsilon, rel_tol, abs_tol, update_X, update_Y, update_col_layers,
+                          0, 0, 8, 0, update_noise_models, alternating)
+        GC.@preserve losses check(h, ccall((:pmf_fit, LIBPMF), Cint, (Handle, Ref{PmfFitOpts}, Ref{PmfHistory}), h, opts, hist))
+        pull_params!(h, model)
+        n = hist.n_recorded
+        return Dict("term_code" => TERM_CODES[hist.term_code + 1], "epochs" => Int(hist.epochs), "loss" => losses[1][1:n],
+                    "data_loss" => losses[2][1:n], "X_reg" => losses[3][1:n], "Y_reg" => losses[4][1:n],
+                    "layer_reg" => losses[5][1:n])
+    finally
+        transient && release(h)
     end
-    cap = max(1, max_epochs - epoch + 1)
-    losses = [zeros(Float64, cap) for _ in 1:5]
-    hist = PmfHistory(0, 0, 0, cap, pointer.(losses)..., 0f0, 0)
-    opts = PmfFitOpts(max_epochs, epoch, opt.eta, opt.epsilon, rel_tol, abs_tol, update_X, update_Y, update_col_layers, 0, 0, 8, 0)
-    GC.@preserve losses check(h, ccall((:pmf_fit, LIBPMF), Cint, (Handle, Ref{PmfFitOpts}, Ref{PmfHistory}), h, opts, hist))
-    pull_params!(h, model)
-    n = hist.n_recorded
-    return Dict("term_code" => TERM_CODES[hist.term_code + 1], "epochs" => Int(hist.epochs), "loss" => losses[1][1:n],
-                "data_loss" => losses[2][1:n], "X_reg" => losses[3][1:n], "Y_reg" => losses[4][1:n], "layer_reg" => losses[5][1:n])
 end
 
 # ---- the staging code's other streaming passes (SURVEY 8f rank 1) ------------------------------------

@@ -389,6 +389,37 @@ def noise_loss_grad(dist: str, z, a, thresholds=None):
     return np.where(mask, l, 0.0), np.where(mask, g, 0.0)
 
 
+def noise_threshold_grads(dist: str, z, a, thresholds):
+    """Per-entry derivatives of the ordinal losses with respect to the two INTERIOR thresholds t1, t2
+    (``ext_thresholds`` = [-inf, t1, t2, +inf]; the outer two are fixed, src/fit.jl:228-242).  With lo = t[c-1],
+    hi = t[c] for category c:  ordinal3  l = -log(s(hi-z) - s(lo-z) + eps):  dl/dhi = -s'(hi-z)/p, dl/dlo = s'(lo-z)/p;
+    ordinal_sq_hinge3  l = max(0, lo-z+m)^2 + max(0, z-hi+m)^2:  dl/dlo = 2 hl, dl/dhi = -2 hr.
+    Returns (d/dt1, d/dt2) arrays shaped like z; zero at missing entries.  SURVEY App. D7: which noise parameters
+    MatFac.jl trains is INFERRED -- thresholds are the only ones the reference ever touches."""
+    mask = np.isfinite(a)
+    a0 = np.where(mask, a, 1.0)
+    cat = a0.astype(np.int64)
+    t = np.asarray(thresholds, dtype=z.dtype)
+    lo, hi = t[cat - 1], t[cat]
+    if dist == "ordinal3":
+        sr, sl = _sigmoid(hi - z), _sigmoid(lo - z)
+        p = sr - sl + z.dtype.type(ORDINAL_EPS)
+        dhi = -sr * (1.0 - sr) / p
+        dlo = sl * (1.0 - sl) / p
+    elif dist == "ordinal_sq_hinge3":
+        m = z.dtype.type(SQ_HINGE_MARGIN)
+        with np.errstate(invalid="ignore"):
+            hl = np.where(np.isfinite(lo), np.maximum(0.0, lo - z + m), 0.0)
+            hr = np.where(np.isfinite(hi), np.maximum(0.0, z - hi + m), 0.0)
+        dlo, dhi = 2.0 * hl, -2.0 * hr
+    else:
+        raise ValueError(dist)
+    # category c touches thresholds c-1 (as lo) and c (as hi); interior ones are indices 1 and 2
+    g1 = np.where(cat == 2, dlo, 0.0) + np.where(cat == 1, dhi, 0.0)
+    g2 = np.where(cat == 3, dlo, 0.0) + np.where(cat == 2, dhi, 0.0)
+    return np.where(mask, g1, 0.0), np.where(mask, g2, 0.0)
+
+
 @dataclass
 class NoiseModel:
     """CompositeNoise stand-in: contiguous column ranges, one distribution each,
@@ -882,7 +913,8 @@ def data_loss_grads(m: OracleModel, D: np.ndarray, capacity: int = 10 ** 8, want
         out.update(dX=np.zeros_like(m.X), dY=np.zeros_like(m.Y), dlogsigma=np.zeros(N, dt),
                    dmu=np.zeros(N, dt),
                    dlogdelta=[np.zeros_like(v) for v in m.logdelta.values] if m.logdelta is not None else None,
-                   dtheta=[np.zeros_like(v) for v in m.theta.values] if m.theta is not None else None)
+                   dtheta=[np.zeros_like(v) for v in m.theta.values] if m.theta is not None else None,
+                   dthresholds=np.zeros((len(m.noise.dists), 2), np.float64))
     sigma = np.exp(m.logsigma)
     block = max(1, capacity // N)
     for r0 in range(0, M, block):
@@ -910,6 +942,11 @@ def data_loss_grads(m: OracleModel, D: np.ndarray, capacity: int = 10 ** 8, want
             w = m.noise.weights[sl].astype(dt)[None, :]
             out["loss"] += float(np.sum(w * l, dtype=np.float64))
             G[:, sl] = w * g
+            if want_grads and dist.startswith("ordinal"):
+                g1, g2 = noise_threshold_grads(dist, z4[:, sl], Dv[:, sl], th)
+                r = m.noise.dists.index(dist)
+                out["dthresholds"][r, 0] += float(np.sum(w * g1, dtype=np.float64))
+                out["dthresholds"][r, 1] += float(np.sum(w * g2, dtype=np.float64))
         if not want_grads:
             continue
         # BatchShift pullback (batch_array.jl:132-150)
@@ -1264,10 +1301,40 @@ def theta_delta_em(m: OracleModel, delta2, sigma2, D, update_priors=True, batch_
     return theta.values, delta2, diffs
 
 
+def _apply_updates(m, opt, out, update_X, update_Y, update_col_layers, update_noise_models):
+    if update_X:
+        opt.apply("X", m.X, out["dX"])
+    if update_Y:
+        opt.apply("Y", m.Y, out["dY"])
+    if update_col_layers:
+        if not m.frozen[0]:
+            opt.apply("logsigma", m.logsigma, out["dlogsigma"])
+        if not m.frozen[2]:
+            opt.apply("mu", m.mu, out["dmu"])
+        if m.logdelta is not None and not m.frozen[1]:
+            for v, (p, g) in enumerate(zip(m.logdelta.values, out["dlogdelta"])):
+                opt.apply(f"logdelta{v}", p, g)
+        if m.theta is not None and not m.frozen[3]:
+            for v, (p, g) in enumerate(zip(m.theta.values, out["dtheta"])):
+                opt.apply(f"theta{v}", p, g)
+    if update_noise_models:
+        # D7: the interior ordinal thresholds are the trainable noise-model parameters
+        for r, th in enumerate(m.noise.thresholds):
+            if th is not None:
+                inner = th[1:3].copy()
+                opt.apply(f"thresholds{r}", inner, out["dthresholds"][r].astype(inner.dtype))
+                th[1:3] = inner
+
+
 def mf_fit(m: OracleModel, D, opt: AdaGrad, max_epochs=1000, epoch=1, rel_tol=1e-5, abs_tol=1e-5,
            update_X=False, update_Y=False, update_col_layers=False, capacity=10 ** 8,
-           callback=None):
+           callback=None, update_noise_models=False, alternating=False):
     """One ``MF.fit!`` call as wrapped by ``mf_fit!`` (src/fit.jl:9-38).
+
+    ``update_noise_models`` (src/fit.jl:14, true in every call of the reference; D7): train the interior ordinal
+    thresholds with the same optimiser.  ``alternating`` (D1): instead of one simultaneous step from one pass, the
+    epoch takes the column-side step (Y, column / batch layers, thresholds) from the first pass and the row-side step
+    (X) from a SECOND pass at the new column-side parameters; the recorded loss is the first pass'.
 
     Assumed semantics (SURVEY App. D): D1 simultaneous gradients from one pass;
     D2 the loss of epoch t is the one evaluated in that epoch's gradient pass
@@ -1301,21 +1368,13 @@ def mf_fit(m: OracleModel, D, opt: AdaGrad, max_epochs=1000, epoch=1, rel_tol=1e
                 h["term_code"] = "rel_tol"
                 break
         prev = loss
-        if update_X:
-            opt.apply("X", m.X, out["dX"])
-        if update_Y:
-            opt.apply("Y", m.Y, out["dY"])
-        if update_col_layers:
-            if not m.frozen[0]:
-                opt.apply("logsigma", m.logsigma, out["dlogsigma"])
-            if not m.frozen[2]:
-                opt.apply("mu", m.mu, out["dmu"])
-            if m.logdelta is not None and not m.frozen[1]:
-                for v, (p, g) in enumerate(zip(m.logdelta.values, out["dlogdelta"])):
-                    opt.apply(f"logdelta{v}", p, g)
-            if m.theta is not None and not m.frozen[3]:
-                for v, (p, g) in enumerate(zip(m.theta.values, out["dtheta"])):
-                    opt.apply(f"theta{v}", p, g)
+        if alternating:
+            _apply_updates(m, opt, out, False, update_Y, update_col_layers, update_noise_models)
+            if update_X:
+                out2 = total_loss_grads(m, D, capacity)
+                _apply_updates(m, opt, out2, True, False, False, False)
+        else:
+            _apply_updates(m, opt, out, update_X, update_Y, update_col_layers, update_noise_models)
         epoch += 1
     return h
 

@@ -35,7 +35,7 @@ class pmf_fit_opts(C.Structure):
                 ("adagrad_eps", C.c_float), ("rel_tol", C.c_double), ("abs_tol", C.c_double),
                 ("update_X", C.c_int32), ("update_Y", C.c_int32), ("update_col_layers", C.c_int32),
                 ("kernel", C.c_int32), ("precision", C.c_int32), ("check_every", C.c_int32),
-                ("no_terminate", C.c_int32)]
+                ("no_terminate", C.c_int32), ("update_noise_models", C.c_int32), ("alternating", C.c_int32)]
 
 
 class pmf_history(C.Structure):
@@ -89,6 +89,8 @@ SIGNATURES = {
     "pmf_set_opt_state": (C.c_int, [H, C.c_int32, C.c_int32, c_float_p]),
     "pmf_loss_grad": (C.c_int, [H, C.c_int32, C.POINTER(pmf_losses), c_float_p, c_float_p, c_float_p, c_float_p]),
     "pmf_get_batch_grads": (C.c_int, [H, C.c_int32, c_float_p, c_float_p]),
+    "pmf_get_threshold_grads": (C.c_int, [H, C.c_int32, c_float_p]),
+    "pmf_get_thresholds": (C.c_int, [H, C.c_int32, c_float_p]),
     "pmf_default_fit_opts": (None, [C.POINTER(pmf_fit_opts)]),
     "pmf_fit": (C.c_int, [H, C.POINTER(pmf_fit_opts), C.POINTER(pmf_history)]),
     "pmf_epoch_begin": (C.c_int, [H, C.POINTER(pmf_fit_opts)]),

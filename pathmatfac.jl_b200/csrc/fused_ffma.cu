@@ -87,6 +87,7 @@ __global__ void __launch_bounds__(NT, (KG == 1) ? 2 : 1) data_pass_ffma_kernel(D
     float ssq_acc[4] = {0.f, 0.f, 0.f, 0.f}, cnt_acc[4] = {0.f, 0.f, 0.f, 0.f}, sq_acc[4] = {0.f, 0.f, 0.f, 0.f};
     float loss_acc = 0.f;
     double loss_d = 0.0;
+    float thr_acc[4][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};   // interior ordinal thresholds (p.dthr)
 
     for (int it = it_begin; it < it_end; ++it) {
         const int i0 = it * TI;
@@ -153,6 +154,12 @@ __global__ void __launch_bounds__(NT, (KG == 1) ? 2 : 1) data_pass_ffma_kernel(D
                     float z4 = z2 + muv[a] + th;
                     float l, g;
                     noise_eval(dist[a], z4, aval, thp[a], p.ordinal_eps, p.hinge_margin, l, g);
+                    if (!STATS && p.dthr != nullptr && is_ordinal(dist[a])) {
+                        float t1, t2;
+                        noise_threshold_grads(dist[a], z4, aval, thp[a], p.ordinal_eps, p.hinge_margin, t1, t2);
+                        thr_acc[a][0] = fmaf(wv[a], t1, thr_acc[a][0]);
+                        thr_acc[a][1] = fmaf(wv[a], t2, thr_acc[a][1]);
+                    }
                     l *= wv[a];
                     g *= wv[a];
                     loss_acc += l;
@@ -287,6 +294,14 @@ __global__ void __launch_bounds__(NT, (KG == 1) ? 2 : 1) data_pass_ffma_kernel(D
                 atomicAdd(p.dmu + j, v0);
                 atomicAdd(p.dlogsigma + j, v1);
             }
+        }
+    }
+    if (!STATS && p.dthr != nullptr) {
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const int range = (int)((thp[a] - p.thresholds) >> 2);
+            if (thr_acc[a][0] != 0.f) atomicAdd(p.dthr + 2 * range, thr_acc[a][0]);
+            if (thr_acc[a][1] != 0.f) atomicAdd(p.dthr + 2 * range + 1, thr_acc[a][1]);
         }
     }
     if (has_batch) {      // gradients of theta / logdelta, or (statistics pass) per-batch counts / squared errors

@@ -87,6 +87,16 @@ __device__ __noinline__ float2 noise_eval_slow(int dist, float z, float a, const
     return make_float2(l, g);
 }
 
+__device__ __noinline__ float2 threshold_grads_slow(int dist, float z, float a, const float* __restrict__ th_range,
+                                                    float ord_eps, float margin) {
+    if (!is_observed(a)) return make_float2(0.f, 0.f);
+    const float4 th4 = __ldg(reinterpret_cast<const float4*>(th_range));
+    const float th[4] = {th4.x, th4.y, th4.z, th4.w};
+    float g1, g2;
+    noise_threshold_grads(dist, z, a, th, ord_eps, margin, g1, g2);
+    return make_float2(g1, g2);
+}
+
 struct TcParams {
     DataPassParams dp;
     int n_jt, n_it;
@@ -155,7 +165,9 @@ struct Ring {
     __device__ __forceinline__ void next(uint32_t n) { if (++s == n) { s = 0; ph ^= 1u; } }
 };
 
-template <bool DBG, bool BATCH>
+// THR: also accumulate the gradients of the interior ordinal thresholds (update_noise_models on a model with ordinal
+// columns).  A separate instantiation: the production kernel carries none of that code.
+template <bool DBG, bool BATCH, bool THR>
 __global__ void __launch_bounds__(NTHREADS, 1)
 data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUtensorMap tmXl,
                     const __grid_constant__ CUtensorMap tmXm, const __grid_constant__ CUtensorMap tmA,
@@ -697,13 +709,22 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
                         z[e] = tally(gv, z[e]);
                     }
                 } else {
+                    // interior-threshold gradients of the ordinal models (update_noise_models): summed over the chunk
+                    // here, so that nothing of it is live outside this rare branch
+                    float t1s = 0.f, t2s = 0.f;
 #pragma unroll
                     for (int e = 0; e < 16; ++e) {
                         float z4 = fmaf(__uint_as_float(z[e]), sd, mt);
                         float2 lg = noise_eval_slow(dist, z4, a[e], th_range, dp.ordinal_eps, dp.hinge_margin);
+                        if (THR && dp.dthr != nullptr && is_ordinal(dist)) {
+                            float2 tg = threshold_grads_slow(dist, z4, a[e], th_range, dp.ordinal_eps, dp.hinge_margin);
+                            t1s += tg.x; t2s += tg.y;
+                        }
                         loss_acc = fmaf(2.f, lg.x, loss_acc);        // keep the common 1/2 factor at flush
                         z[e] = tally(lg.y, z[e]);
                     }
+                    if (THR && dp.dthr != nullptr && is_ordinal(dist))
+                        add_threshold_grads(dp.dthr, ci >> 8, t1s * wj, t2s * wj);
                 }
             };
 
@@ -1028,7 +1049,10 @@ cudaError_t launch_data_pass_tc(const DataPassParams& dp_in, float* Xh, float* X
     }
     const bool dbg = p.ablate != 0 || p.trace != nullptr;
     const bool batch = bp != nullptr;
-    auto kern = batch ? data_pass_tc_kernel<false, true> : dbg ? data_pass_tc_kernel<true, false> : data_pass_tc_kernel<false, false>;
+    const bool thr = dp.dthr != nullptr;
+    auto kern = batch ? (thr ? data_pass_tc_kernel<false, true, true> : data_pass_tc_kernel<false, true, false>)
+                : dbg ? data_pass_tc_kernel<true, false, false>
+                      : (thr ? data_pass_tc_kernel<false, false, true> : data_pass_tc_kernel<false, false, false>);
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TOTAL);
     if (e != cudaSuccess) return e;
     const long long n_tiles = (long long)p.n_jt * p.n_it;

@@ -217,7 +217,7 @@ int pmf_create(const pmf_dims* d, pmf_handle* out) {
     ok &= dev_alloc(&h->Y, yk) == cudaSuccess && dev_alloc(&h->accY, yk) == cudaSuccess;
     ok &= dev_alloc(&h->weight, h->Np) == cudaSuccess && dev_alloc(&h->colinfo, h->Np) == cudaSuccess;
     ok &= dev_alloc(&h->scalars, SC_COUNT) == cudaSuccess && dev_alloc(&h->ctrl, 1) == cudaSuccess;
-    ok &= dev_alloc(&h->thresholds, 4) == cudaSuccess;
+    ok &= dev_alloc(&h->thresholds, 4) == cudaSuccess && dev_alloc(&h->acc_thr, 2 * PMF_MAX_RANGES) == cudaSuccess;
     if (!ok) {
         pmf_destroy(h);
         return fail(nullptr, PMF_ERR_ALLOC, "device allocation failed (A needs %.2f GB)", (double)h->N * h->lda * 4e-9);
@@ -247,7 +247,7 @@ int pmf_destroy(pmf_handle h) {
     big_free(h->wide.G, (size_t)h->N * h->lda, h->dims.device);
     dev_free(h->wide.Xh); dev_free(h->wide.Yh);
     { float* q = static_cast<float*>(h->wide.Xb); dev_free(q); q = static_cast<float*>(h->wide.Yb); dev_free(q); h->wide.Xb = h->wide.Yb = nullptr; }
-    dev_free(h->weight); dev_free(h->colinfo); dev_free(h->thresholds); dev_free(h->scalars); dev_free(h->ctrl);
+    dev_free(h->weight); dev_free(h->colinfo); dev_free(h->thresholds); dev_free(h->acc_thr); dev_free(h->scalars); dev_free(h->ctrl);
     dev_free(h->vp); dev_free(h->sg); dev_free(h->accvp); dev_free(h->regw); dev_free(h->regc);
     dev_free(h->bcol_off); dev_free(h->bcol_view); dev_free(h->bcol_nb); dev_free(h->batch_of_sample);
     h->free_tc_plan();
@@ -301,6 +301,7 @@ int pmf_set_noise(pmf_handle h, int32_t n_ranges, const int32_t* cs, const int32
                   const float* thresholds, const float* weight) {
     CHECK_H(h);
     if (n_ranges <= 0 || !cs || !ce || !dist) return fail(h, PMF_ERR_ARG, "bad noise ranges");
+    if (n_ranges > PMF_MAX_RANGES) return fail(h, PMF_ERR_ARG, "more than %d noise ranges", PMF_MAX_RANGES);
     std::vector<int32_t> ci(h->Np, 0);
     std::vector<char> seen(h->N, 0);
     for (int r = 0; r < n_ranges; ++r) {
@@ -350,7 +351,18 @@ int pmf_set_noise(pmf_handle h, int32_t n_ranges, const int32_t* cs, const int32
         CU(h, dev_alloc(&h->tc_cost_cum, (size_t)n_jt + 1));
         CU(h, cudaMemcpy(h->tc_cost_cum, cum.data(), ((size_t)n_jt + 1) * 4, cudaMemcpyHostToDevice));
     }
+    h->n_ranges = n_ranges;
+    h->has_ordinal = false;
+    for (int r = 0; r < n_ranges; ++r) h->has_ordinal |= (dist[r] == 3 || dist[r] == 5) && ce[r] > cs[r];
     h->have_noise = true;
+    return PMF_OK;
+}
+
+int pmf_get_thresholds(pmf_handle h, int32_t n_ranges, float* thresholds) {
+    CHECK_H(h);
+    if (!thresholds || n_ranges != h->n_ranges) return fail(h, PMF_ERR_ARG, "pmf_get_thresholds: %d ranges given, the model has %d", n_ranges, h->n_ranges);
+    CU(h, cudaStreamSynchronize(h->stream));
+    CU(h, cudaMemcpy(thresholds, h->thresholds, (size_t)4 * n_ranges * 4, cudaMemcpyDeviceToHost));
     return PMF_OK;
 }
 
@@ -724,6 +736,7 @@ int pmf_reset_opt_state(pmf_handle h, float eps) {
     fill_kernel<<<296, 256, 0, h->stream>>>(h->accX, (size_t)h->Mp * h->Kp, eps);
     fill_kernel<<<296, 256, 0, h->stream>>>(h->accY, (size_t)h->Np * h->Kp, eps);
     fill_kernel<<<296, 256, 0, h->stream>>>(h->accvp, h->vp_len(), eps);
+    fill_kernel<<<1, 128, 0, h->stream>>>(h->acc_thr, 2 * PMF_MAX_RANGES, eps);
     CU(h, cudaGetLastError());
     CU(h, cudaStreamSynchronize(h->stream));
     return PMF_OK;
@@ -770,6 +783,8 @@ void pmf_default_fit_opts(pmf_fit_opts* o) {
     o->max_epochs = 1000; o->epoch = 1; o->lr = 1.0f; o->adagrad_eps = 1e-8f;
     o->rel_tol = 1e-5; o->abs_tol = 1e-5;       // src/fit.jl:934-935
     o->kernel = PMF_KERNEL_AUTO; o->precision = 0; o->check_every = 8; o->no_terminate = 0;
+    o->update_noise_models = 1;                  // src/fit.jl:14: true in every call of the reference
+    o->alternating = 0;                          // one pass, simultaneous step
 }
 
 static int ready(pmf_model_s* h) {
@@ -809,6 +824,7 @@ static int phase_begin(pmf_model_s* h, const pmf_fit_opts* o, bool use_stop, boo
     h->grads_clean = false;
     DataPassParams p;
     fill_data_params(h, p, use_stop);
+    if (h->has_ordinal && (o == nullptr || o->update_noise_models)) p.dthr = h->g_thr();
     int kind = o ? o->kernel : PMF_KERNEL_AUTO;
     int rc = h->run_data_pass(p, kind, o ? o->precision : 0);
     if (rc != 0) return rc;
@@ -829,9 +845,11 @@ static int phase_reg_shared(pmf_model_s* h, bool use_stop, bool with_x) {
     return h->run_reg_multi(with_x, true, true, stop);
 }
 
-static int phase_update(pmf_model_s* h, const pmf_fit_opts* o) {
-    return h->run_update_multi(o->update_X != 0, o->update_Y != 0, o->update_col_layers != 0, o->lr, o->adagrad_eps,
-                               &h->ctrl->stop);
+// which: 0 = every enabled parameter, 1 = column side only (Y, layers, thresholds), 2 = row side only (X)
+static int phase_update(pmf_model_s* h, const pmf_fit_opts* o, int which = 0) {
+    return h->run_update_multi(o->update_X != 0 && which != 1, o->update_Y != 0 && which != 2,
+                               o->update_col_layers != 0 && which != 2, o->update_noise_models != 0 && which != 2, o->lr,
+                               o->adagrad_eps, &h->ctrl->stop);
 }
 
 int pmf_loss_grad(pmf_handle h, int32_t include_reg, pmf_losses* out, float* dX, float* dY, float* dls, float* dmu) {
@@ -856,6 +874,14 @@ int pmf_loss_grad(pmf_handle h, int32_t include_reg, pmf_losses* out, float* dX,
     CU(h, cudaStreamSynchronize(h->stream));
     if (dls) CU(h, cudaMemcpy(dls, h->g_logsigma(), (size_t)h->N * 4, cudaMemcpyDeviceToHost));
     if (dmu) CU(h, cudaMemcpy(dmu, h->g_mu(), (size_t)h->N * 4, cudaMemcpyDeviceToHost));
+    return PMF_OK;
+}
+
+int pmf_get_threshold_grads(pmf_handle h, int32_t n_ranges, float* dthr) {
+    CHECK_H(h);
+    if (!dthr || n_ranges != h->n_ranges) return fail(h, PMF_ERR_ARG, "pmf_get_threshold_grads: %d ranges given, the model has %d", n_ranges, h->n_ranges);
+    CU(h, cudaStreamSynchronize(h->stream));
+    CU(h, cudaMemcpy(dthr, h->g_thr(), (size_t)2 * n_ranges * 4, cudaMemcpyDeviceToHost));
     return PMF_OK;
 }
 
@@ -890,6 +916,7 @@ int pmf_epoch_begin(pmf_handle h, const pmf_fit_opts* o) {
 int pmf_epoch_end(pmf_handle h, const pmf_fit_opts* o) {
     CHECK_H(h);
     if (!o) return fail(h, PMF_ERR_ARG, "null options");
+    if (o->alternating) return fail(h, PMF_ERR_ARG, "alternating steps are only available through pmf_fit");
     int rc = phase_reg_shared(h, true, false);
     if (rc != 0) return rc;
     CU(h, launch_control(h->ctrl, h->scalars, h->hist, h->hist_cap, h->cur_epoch, o->no_terminate ? -1 : o->max_epochs, o->rel_tol, o->abs_tol, h->stream));
@@ -944,7 +971,18 @@ int pmf_fit(pmf_handle h, const pmf_fit_opts* o, pmf_history* out) {
         if ((rc = phase_reg_shared(h, true, !sharded)) != 0) return rc;
         CU(h, launch_control(h->ctrl, h->scalars, h->hist, h->hist_cap, h->cur_epoch, o->no_terminate ? -1 : o->max_epochs, o->rel_tol, o->abs_tol, h->stream));
         h->launches++;
-        if ((rc = phase_update(h, o)) != 0) return rc;
+        if (o->alternating) {
+            // SURVEY App. D1, the other reading of MF.fit!: column-side step from this pass, then the row-side step from
+            // a SECOND pass at the new column-side parameters (no history record, no termination test of its own; a
+            // stop raised above makes every kernel of the second half return at once)
+            if ((rc = phase_update(h, o, 1)) != 0) return rc;
+            if (o->update_X) {
+                if ((rc = phase_begin(h, o, true, sharded)) != 0) return rc;
+                if (!sharded && (rc = h->run_network_reg(0, &h->ctrl->stop)) != 0) return rc;
+                if (!sharded && (rc = h->run_reg_multi(true, false, false, &h->ctrl->stop)) != 0) return rc;
+                if ((rc = phase_update(h, o, 2)) != 0) return rc;
+            }
+        } else if ((rc = phase_update(h, o)) != 0) return rc;
         h->cur_epoch++;
         if (++since >= check && e < o->max_epochs) {
             since = 0;
@@ -1510,7 +1548,7 @@ int pmf_model_s::run_reg_multi(bool x_side, bool y_side, bool vectors, const int
 // AdaGrad step of every enabled parameter array in ONE launch.  The same pass clears the gradient
 // buffers and the loss scalars for the next epoch and, for X, writes the TF32 operand split of the
 // updated values, so the next epoch starts directly with the data pass.
-int pmf_model_s::run_update_multi(bool upd_X, bool upd_Y, bool upd_layers, float lr, float eps, const int* stop) {
+int pmf_model_s::run_update_multi(bool upd_X, bool upd_Y, bool upd_layers, bool upd_noise, float lr, float eps, const int* stop) {
     MultiPassParams mp;
     std::memset(&mp, 0, sizeof mp);
     {
@@ -1538,6 +1576,10 @@ int pmf_model_s::run_update_multi(bool upd_X, bool upd_Y, bool upd_layers, float
         q.zero_buf = sg + (size_t)Np * Kp + sgm.off;
     }
     mp.zero_scalars = scalars;
+    if (has_ordinal) {
+        mp.thr = thresholds; mp.thr_grad = g_thr(); mp.thr_acc = acc_thr; mp.thr_ranges = n_ranges;
+        mp.thr_update = upd_noise ? 1 : 0; mp.thr_lr = lr; mp.thr_eps = eps;
+    }
     cudaError_t e = launch_multi_pass(mp, stream, n_sms);
     if (e != cudaSuccess) { cuda_failed = true; return fail(this, PMF_ERR_CUDA, "update pass launch: %s", cudaGetErrorString(e)); }
     launches++;

@@ -66,6 +66,49 @@ __device__ __forceinline__ void noise_eval(int dist, float z, float a, const flo
     }
 }
 
+// Derivatives of the two ordinal losses with respect to the INTERIOR thresholds t1 = th[1], t2 = th[2] (the outer two
+// are -inf / +inf and fixed, src/fit.jl:228-242) at a finite datum a; MF.fit!'s update_noise_models (src/fit.jl:14,
+// SURVEY App. D7) trains exactly these.  Category c has lo = th[c-1], hi = th[c].
+__device__ __forceinline__ void noise_threshold_grads(int dist, float z, float a, const float* __restrict__ th, float ord_eps,
+                                                      float margin, float& g1, float& g2) {
+    int c = (int)a;
+    c = c < 1 ? 1 : (c > 3 ? 3 : c);
+    const float lo = th[c - 1], hi = th[c];
+    float dlo, dhi;
+    if (dist == DIST_ORDINAL3) {
+        const float sr = sigmoidf_(hi - z), sl = sigmoidf_(lo - z);
+        const float p = sr - sl + ord_eps;
+        dhi = -sr * (1.0f - sr) / p;
+        dlo = sl * (1.0f - sl) / p;
+    } else {   // DIST_ORD_SQ_HINGE3
+        const float hl = (c > 1) ? fmaxf(0.f, lo - z + margin) : 0.f;
+        const float hr = (c < 3) ? fmaxf(0.f, z - hi + margin) : 0.f;
+        dlo = 2.0f * hl;
+        dhi = -2.0f * hr;
+    }
+    g1 = (c == 2 ? dlo : 0.f) + (c == 1 ? dhi : 0.f);
+    g2 = (c == 3 ? dlo : 0.f) + (c == 2 ? dhi : 0.f);
+}
+__device__ __forceinline__ bool is_ordinal(int dist) { return dist == DIST_ORDINAL3 || dist == DIST_ORD_SQ_HINGE3; }
+
+// Sum of one (d/dt1, d/dt2) pair per calling lane into dthr[2 * range + {0, 1}].  Called from a branch only the lanes
+// with an ordinal column take: when the whole warp is there and works on one noise range (32 consecutive features: the
+// normal case) the pairs are reduced with shuffles and leave as two atomics, otherwise every lane adds its own.
+__device__ __forceinline__ void add_threshold_grads(float* __restrict__ dthr, int range, float g1, float g2) {
+    const unsigned m = __activemask();
+    bool uniform = false;
+    if (m == 0xffffffffu) uniform = __all_sync(m, range == __shfl_sync(m, range, 0));
+    if (uniform) {
+        for (int o = 16; o > 0; o >>= 1) {
+            g1 += __shfl_xor_sync(0xffffffffu, g1, o);
+            g2 += __shfl_xor_sync(0xffffffffu, g2, o);
+        }
+        if ((threadIdx.x & 31) != 0) return;
+    }
+    if (g1 != 0.f) atomicAdd(dthr + 2 * range, g1);
+    if (g2 != 0.f) atomicAdd(dthr + 2 * range + 1, g2);
+}
+
 __device__ __forceinline__ bool is_observed(float a) {
     // missing data is NaN-encoded; non-finite values never contribute (bit test, immune to
     // fast-math comparisons)

@@ -90,6 +90,9 @@ struct pmf_model_s {
     int32_t* colinfo = nullptr;
     int32_t* tc_cost_cum = nullptr;          // cumulative per-feature-tile cost of the tcgen05 data pass (n_jt + 1)
     float* thresholds = nullptr;
+    float* acc_thr = nullptr;                // AdaGrad accumulators of the interior ordinal thresholds [PMF_MAX_RANGES][2]
+    int n_ranges = 0;
+    bool has_ordinal = false;
     // vector parameters  vp = [logsigma Np | mu Np | logdelta nbp | theta nbp]
     // shared gradients   sg = [dY Np*Kp | dlogsigma Np | dmu Np | dlogdelta nbp | dtheta nbp]
     float *vp = nullptr, *sg = nullptr, *accvp = nullptr, *regw = nullptr, *regc = nullptr;
@@ -129,7 +132,9 @@ struct pmf_model_s {
     int exchange_gradients();   // all-reduce of sg and of the rank-local loss scalars on `stream`
 
     size_t vp_len() const { return 2 * (size_t)Np + 2 * (size_t)nbp; }
-    size_t sg_len() const { return (size_t)Np * Kp + vp_len(); }
+    // shared gradients: [dY | dlogsigma | dmu | dlogdelta | dtheta | interior ordinal thresholds (2 per noise range)]
+    size_t sg_len() const { return (size_t)Np * Kp + vp_len() + 2 * (size_t)pmf::PMF_MAX_RANGES; }
+    float* g_thr() { return sg + (size_t)Np * Kp + vp_len(); }
     float* logsigma() { return vp; }
     float* mu() { return vp + Np; }
     float* logdelta() { return vp + 2 * (size_t)Np; }
@@ -145,5 +150,5 @@ struct pmf_model_s {
     void fill_factor_params(int which, pmf::FactorUpdateParams& q);
     int run_network_reg(int which, const int* stop);
     int run_reg_multi(bool x_side, bool y_side, bool vectors, const int* stop);
-    int run_update_multi(bool upd_X, bool upd_Y, bool upd_layers, float lr, float eps, const int* stop);
+    int run_update_multi(bool upd_X, bool upd_Y, bool upd_layers, bool upd_noise, float lr, float eps, const int* stop);
 };

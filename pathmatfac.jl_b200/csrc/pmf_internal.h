@@ -39,6 +39,7 @@ struct DataPassParams {
     float* dmu;         // [Np]
     float* dlogdelta;   // batch table layout
     float* dtheta;
+    float* dthr;        // [n_ranges][2] gradients of the interior ordinal thresholds, or null (thresholds not trained)
     double* scalars;    // SC_* ; data loss accumulated into scalars[SC_DATA]
     // optional per-column statistics pass (pmf_column_stats)
     float* col_ssq;     // [Np] sum_i g^2 or null
@@ -78,6 +79,8 @@ struct FactorUpdateParams {
     int n_pad;
 };
 
+constexpr int PMF_MAX_RANGES = 64;     // noise ranges whose thresholds can be trained (tail of the shared gradient buffer)
+
 // 1-D parameters (logsigma | mu | logdelta | theta) with optional quadratic penalty.
 struct VectorUpdateParams {
     int n;
@@ -103,6 +106,13 @@ struct MultiPassParams {
     FactorUpdateParams f[2];
     VectorUpdateParams v[4];
     double* zero_scalars;       // SC_COUNT doubles cleared by block 0 after the pass (next epoch's accumulators), or null
+    // interior ordinal thresholds (update pass only): th [n_ranges][4], gradients / accumulators [n_ranges][2]
+    float* thr;
+    float* thr_grad;
+    float* thr_acc;
+    int thr_ranges;             // 0: nothing to do
+    int thr_update;             // AdaGrad step (else only the gradients are cleared)
+    float thr_lr, thr_eps;
 };
 
 struct FitControl {

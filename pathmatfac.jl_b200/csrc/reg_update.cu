@@ -136,9 +136,20 @@ __global__ void __launch_bounds__(UT) multi_pass_kernel(const __grid_constant__ 
             vector_pass(mp.v[i], vb, nvb, red_smem);
             __syncthreads();
         }
-        if (vb == 0 && mp.zero_scalars != nullptr && threadIdx.x < SC_COUNT) {
-            const int* stop = mp.nv > 0 ? mp.v[0].stop_flag : (mp.nf > 0 ? mp.f[0].stop_flag : nullptr);
-            if (stop == nullptr || *stop == 0) mp.zero_scalars[threadIdx.x] = 0.0;
+        const int* stop = mp.nv > 0 ? mp.v[0].stop_flag : (mp.nf > 0 ? mp.f[0].stop_flag : nullptr);
+        const bool live = stop == nullptr || *stop == 0;
+        if (vb == 0 && mp.zero_scalars != nullptr && threadIdx.x < SC_COUNT && live) mp.zero_scalars[threadIdx.x] = 0.0;
+        // interior ordinal thresholds t1, t2 of every noise range (update_noise_models, src/fit.jl:14): AdaGrad step on
+        // the gradients the data pass left behind (zero for the non-ordinal ranges), then clear them
+        if (vb == 0 && mp.thr_ranges > 0 && (int)threadIdx.x < 2 * mp.thr_ranges && live) {
+            const int t = threadIdx.x;
+            const float g = mp.thr_grad[t];
+            if (mp.thr_update && g != 0.f) {
+                const float a = mp.thr_acc[t] + g * g;
+                mp.thr_acc[t] = a;
+                mp.thr[4 * (t >> 1) + 1 + (t & 1)] -= mp.thr_lr * g / (sqrtf(a) + mp.thr_eps);
+            }
+            mp.thr_grad[t] = 0.f;
         }
     }
 }

@@ -108,6 +108,16 @@ __device__ __noinline__ float2 noise_eval_slow_w(int dist, float z, float a, con
     return make_float2(l, g);
 }
 
+__device__ __noinline__ float2 threshold_grads_slow_w(int dist, float z, float a, const float* __restrict__ th_range,
+                                                      float ord_eps, float margin) {
+    if (!is_observed(a)) return make_float2(0.f, 0.f);
+    const float4 th4 = __ldg(reinterpret_cast<const float4*>(th_range));
+    const float th[4] = {th4.x, th4.y, th4.z, th4.w};
+    float g1, g2;
+    noise_threshold_grads(dist, z, a, th, ord_eps, margin, g1, g2);
+    return make_float2(g1, g2);
+}
+
 // ================================================================================================================
 // zlink: Z contraction + link epilogue
 // ================================================================================================================
@@ -353,14 +363,21 @@ zlink_kernel(const __grid_constant__ CUtensorMap tmYh, const __grid_constant__ C
                             z[e] = rn_bits(gv * gscale);
                         }
                     } else {
+                        float t1s = 0.f, t2s = 0.f;      // interior-threshold gradients (update_noise_models)
 #pragma unroll
                         for (int e = 0; e < 16; ++e) {
                             float z4 = fmaf(__uint_as_float(z[e]), sigma, muj);
                             float2 lg = noise_eval_slow_w(dist, z4, a[e], th_range, dp.ordinal_eps, dp.hinge_margin);
+                            if (dp.dthr != nullptr && is_ordinal(dist)) {
+                                float2 tg = threshold_grads_slow_w(dist, z4, a[e], th_range, dp.ordinal_eps, dp.hinge_margin);
+                                t1s += tg.x; t2s += tg.y;
+                            }
                             loss_acc = fmaf(2.f, lg.x, loss_acc);
                             dmu_acc += lg.y;
                             z[e] = rn_bits(lg.y * gscale);
                         }
+                        if (dp.dthr != nullptr && is_ordinal(dist))
+                            add_threshold_grads(dp.dthr, ci >> 8, t1s * wj, t2s * wj);
                     }
                     // G' over the data values this thread just read (same addresses), then hand the buffer to the store
 #pragma unroll

@@ -351,6 +351,14 @@ class Engine:
             if th is not None:
                 th.values[v][...] = b.T
         self.d2h_bytes += X.nbytes + Y.nbytes + 8 * self.N
+        # ordinal thresholds (trained when update_noise_models; src/fit.jl:14)
+        nm = mf.noise_model
+        if any(n.ext_thresholds is not None for n in nm.noises):
+            th4 = np.empty((len(nm.noises), 4), np.float32)
+            self._ck(self.lib.pmf_get_thresholds(self.h, len(nm.noises), fptr(th4)))
+            for n, row in zip(nm.noises, th4):
+                if n.ext_thresholds is not None:
+                    n.ext_thresholds[1:3] = row[1:3]
         for reg in (mf.X_reg, mf.Y_reg):
             nets = [reg] if isinstance(reg, NetworkRegularizer) else (
                 [r for r in reg.regularizers if isinstance(r, NetworkRegularizer)]
@@ -390,6 +398,10 @@ class Engine:
             self._ck(self.lib.pmf_get_batch_grads(self.h, v, fptr(a), fptr(b)))
             res["dlogdelta"].append(a.T.copy())
             res["dtheta"].append(b.T.copy())
+        nr = len(self.model.matfac.noise_model.col_ranges)
+        dthr = np.zeros((nr, 2), np.float32)
+        self._ck(self.lib.pmf_get_threshold_grads(self.h, nr, fptr(dthr)))
+        res["dthresholds"] = dthr
         return res
 
     def reset_opt_state(self, epsilon=1e-8):
@@ -682,13 +694,15 @@ def mf_fit(model, *, scale_column_losses=False, update_X=False, update_Y=False, 
            update_X_reg=False, update_Y_reg=False, update_row_layers_reg=False, update_col_layers_reg=False,
            keep_history=True, opt: Optional[AdaGrad] = None, lr=1.0, max_epochs=1000, epoch=1,
            rel_tol=1e-5, abs_tol=1e-5, capacity=None, verbosity=1, print_prefix="", print_iter=10,
-           kernel=KERNEL_AUTO, precision=0, check_every=8, device=0, **kwargs) -> Dict:
+           kernel=KERNEL_AUTO, precision=0, check_every=8, device=0, alternating=False, **kwargs) -> Dict:
     """``mf_fit!`` (src/fit.jl:9-38): one ``MF.fit!`` call on the model.
 
     Same keyword surface and defaults.  ``capacity`` is accepted and ignored (the fused pass
-    never materialises Z).  ``update_noise_models`` only concerns ordinal thresholds, which this
-    build keeps fixed.  A model that is not device-resident (``gpu(model)`` not called) is
-    uploaded, fitted and written back within the call -- the end-to-end path."""
+    never materialises Z).  ``update_noise_models`` (true by default, as in every call of the reference) trains
+    the interior thresholds of the ordinal noise models.  ``alternating`` selects the other
+    reading of MatFac.jl's epoch (App. D1): column-side step, then the row-side step from a second pass.  A model
+    that is not device-resident (``gpu(model)`` not called) is uploaded, fitted and written back within the call --
+    the end-to-end path."""
     if scale_column_losses:
         raise NotImplementedError("scale_column_losses=true is never used by the reference (src/fit.jl:9)")
     transient = model._engine is None
@@ -706,7 +720,8 @@ def mf_fit(model, *, scale_column_losses=False, update_X=False, update_Y=False, 
                           adagrad_eps=float(opt.epsilon), rel_tol=float(rel_tol), abs_tol=float(abs_tol),
                           update_X=int(update_X), update_Y=int(update_Y),
                           update_col_layers=int(update_col_layers), kernel=int(kernel),
-                          precision=int(precision), check_every=int(check_every))
+                          precision=int(precision), check_every=int(check_every),
+                          update_noise_models=int(bool(update_noise_models)), alternating=int(bool(alternating)))
         h = eng.fit(o)
         h["time"] = time.time() - t0
         h["lr"] = opt.eta

@@ -172,3 +172,70 @@ def test_wide_k_with_batch_layers_runs_fp32_kernel():
             eng.loss_grad(include_reg=False)
     finally:
         eng.close()
+
+
+# ---- MatFac.jl unknowns as explicit options ---------------------------------------------
+ORD_VIEWS = {"mutation": ("bernoulli_sq_hinge", 40), "cna": ("ordinal3", 60), "methylation": ("ordinal_sq_hinge3", 45)}
+
+
+@pytest.mark.parametrize("kernel,M,K", [(_lib.KERNEL_FFMA, 150, 6), (_lib.KERNEL_TC, 700, 16), (_lib.KERNEL_TC, 300, 72)])
+def test_ordinal_threshold_gradients(kernel, M, K):
+    """d loss / d(t1, t2) of the ordinal noise models (update_noise_models, src/fit.jl:14) on every kernel against the
+    oracle (whose values are finite-difference checked on the CPU, tests/test_oracle_golden.py)."""
+    model, om, D = make_pair(M, ORD_VIEWS, K=K, seed=400 + K, missing=0.15, lambda_X_l2=1.0)
+    eng = P.Engine(model)
+    try:
+        eng.set_loss_grad_kernel(kernel, 0)
+        got = eng.loss_grad(include_reg=True)
+    finally:
+        eng.close()
+    ref = O.total_loss_grads(om, D)
+    assert got["dthresholds"].shape == (3, 2)
+    assert np.all(got["dthresholds"][0] == 0)                    # bernoulli_sq_hinge has no thresholds
+    assert relerr(got["dthresholds"][1:], ref["dthresholds"][1:]) < TOL
+    assert abs(got["loss"] - ref["loss"]) <= TOL * abs(ref["loss"])
+
+
+def test_fit_trains_ordinal_thresholds():
+    model, om, D = make_pair(160, ORD_VIEWS, K=5, seed=410, missing=0.1, lambda_X_l2=1.0)
+    th0 = [None if n.ext_thresholds is None else n.ext_thresholds.copy() for n in model.matfac.noise_model.noises]
+    kw = dict(max_epochs=12, update_X=True, update_Y=True, update_col_layers=True, rel_tol=0, abs_tol=0)
+    # thresholds fixed: nothing moves
+    import copy
+    m_fixed = copy.deepcopy(model)
+    h_fixed = P.mf_fit(m_fixed, lr=0.25, update_noise_models=False, verbosity=0, kernel=_lib.KERNEL_FFMA, **kw)
+    for n, t in zip(m_fixed.matfac.noise_model.noises, th0):
+        assert t is None or np.array_equal(n.ext_thresholds, t)
+    om_fixed = copy.deepcopy(om)
+    href_fixed = O.mf_fit(om_fixed, D, O.AdaGrad(0.25), update_noise_models=False, **kw)
+    assert relerr(h_fixed["loss"], href_fixed["loss"]) < TOL
+    # thresholds trained (the reference's default)
+    h = P.mf_fit(model, lr=0.25, verbosity=0, kernel=_lib.KERNEL_FFMA, **kw)
+    href = O.mf_fit(om, D, O.AdaGrad(0.25), update_noise_models=True, **kw)
+    assert relerr(h["loss"], href["loss"]) < TOL
+    assert h["loss"][-1] < h_fixed["loss"][-1]
+    for n, t, t_ref in zip(model.matfac.noise_model.noises, th0, om.noise.thresholds):
+        if t is None:
+            continue
+        assert np.isneginf(n.ext_thresholds[0]) and np.isposinf(n.ext_thresholds[3])
+        assert not np.array_equal(n.ext_thresholds[1:3], t[1:3])
+        assert np.allclose(n.ext_thresholds[1:3], t_ref[1:3], rtol=1e-3, atol=1e-4)
+
+
+@pytest.mark.parametrize("kernel,M,N", [(_lib.KERNEL_FFMA, 130, 90), (_lib.KERNEL_TC, 900, 600)])
+def test_alternating_epochs(kernel, M, N):
+    """`alternating` = column-side step, then the row-side step from a second pass at the new Y.  Same
+    loss curve and parameters as the oracle's alternating loop; a different curve from the simultaneous step."""
+    views = {"mutation": ("bernoulli", N // 3), "methylation": ("normal", N - N // 3)}
+    model, om, D = make_pair(M, views, K=8, seed=420, missing=0.2, lambda_X_l2=1.0, batch_views=["methylation"], n_batches=3)
+    import copy
+    model_s = copy.deepcopy(model)
+    kw = dict(max_epochs=8, update_X=True, update_Y=True, update_col_layers=True, rel_tol=0, abs_tol=0)
+    h = P.mf_fit(model, lr=0.25, alternating=True, verbosity=0, kernel=kernel, **kw)
+    href = O.mf_fit(om, D, O.AdaGrad(0.25), alternating=True, **kw)
+    tol = TOL if kernel == _lib.KERNEL_FFMA else 3 * TOL
+    assert np.max(np.abs(np.array(h["loss"]) / np.array(href["loss"]) - 1)) < tol
+    assert relerr(model.matfac.X, om.X) < 30 * tol and relerr(model.matfac.Y, om.Y) < 30 * tol
+    h_s = P.mf_fit(model_s, lr=0.25, alternating=False, verbosity=0, kernel=kernel, **kw)
+    assert abs(h_s["loss"][3] / h["loss"][3] - 1) > 1e-3
+    assert h["kernel_launches"] > h_s["kernel_launches"]

@@ -382,3 +382,36 @@ def test_m_estimates_closed_forms():
     assert h["loss"][-1] <= h["loss"][0]
     O.init_mu(om, D, lr_mu=0.5, max_epochs=50)
     assert not np.array_equal(om.mu, mu_before)
+
+
+def test_ordinal_threshold_gradients_finite_differences():
+    """d loss / d(t1, t2) of both ordinal noise models (update_noise_models, src/fit.jl:14) against
+    central differences of the oracle's own loss."""
+    m, D, meta = O.simulate_model(60, {"cna": ("ordinal3", 30), "methylation": ("ordinal_sq_hinge3", 25)}, K=3, seed=4, missing=0.1)
+    g = O.data_loss_grads(m, D)
+    for r in range(2):
+        for c in range(2):
+            eps = 1e-6
+            th = m.noise.thresholds[r]
+            th[1 + c] += eps
+            lp = O.data_loss_grads(m, D, want_grads=False)["loss"]
+            th[1 + c] -= 2 * eps
+            lm = O.data_loss_grads(m, D, want_grads=False)["loss"]
+            th[1 + c] += eps
+            assert abs(g["dthresholds"][r, c] - (lp - lm) / (2 * eps)) <= 1e-6 * abs(g["dthresholds"][r, c]) + 1e-6
+
+
+def test_alternating_and_threshold_training_are_options_of_the_oracle():
+    m, D, meta = O.simulate_model(50, {"methylation": ("normal", 25), "cna": ("ordinal3", 20)}, K=3, seed=5)
+    import copy
+    kw = dict(max_epochs=5, update_X=True, update_Y=True, update_col_layers=True, rel_tol=0, abs_tol=0)
+    runs = {}
+    for name, opts in (("plain", {}), ("thr", dict(update_noise_models=True)), ("alt", dict(alternating=True))):
+        mm = copy.deepcopy(m)
+        h = O.mf_fit(mm, D, O.AdaGrad(0.2), **kw, **opts)
+        runs[name] = (h["loss"], mm)
+    assert runs["plain"][0][0] == runs["thr"][0][0] == runs["alt"][0][0]          # same first loss
+    assert runs["plain"][0][-1] != runs["thr"][0][-1] and runs["plain"][0][-1] != runs["alt"][0][-1]
+    assert np.array_equal(runs["plain"][1].noise.thresholds[1], m.noise.thresholds[1])
+    assert not np.array_equal(runs["thr"][1].noise.thresholds[1][1:3], m.noise.thresholds[1][1:3])
+    assert np.isinf(runs["thr"][1].noise.thresholds[1][[0, 3]]).all()
