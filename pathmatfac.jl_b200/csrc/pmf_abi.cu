@@ -216,7 +216,8 @@ int pmf_create(const pmf_dims* d, pmf_handle* out) {
     ok &= dev_alloc(&h->X, xk) == cudaSuccess && dev_alloc(&h->dX, xk) == cudaSuccess && dev_alloc(&h->accX, xk) == cudaSuccess;
     ok &= dev_alloc(&h->Y, yk) == cudaSuccess && dev_alloc(&h->accY, yk) == cudaSuccess;
     ok &= dev_alloc(&h->weight, h->Np) == cudaSuccess && dev_alloc(&h->colinfo, h->Np) == cudaSuccess;
-    ok &= dev_alloc(&h->scalars, SC_COUNT) == cudaSuccess && dev_alloc(&h->ctrl, 1) == cudaSuccess;
+    ok &= dev_alloc(&h->scalars_base, 4 * SC_COUNT) == cudaSuccess && dev_alloc(&h->ctrl_base, 2) == cudaSuccess;
+    h->scalars = h->scalars_base; h->ctrl = h->ctrl_base;
     ok &= dev_alloc(&h->thresholds, 4) == cudaSuccess && dev_alloc(&h->acc_thr, 2 * PMF_MAX_RANGES) == cudaSuccess;
     if (!ok) {
         pmf_destroy(h);
@@ -225,7 +226,8 @@ int pmf_create(const pmf_dims* d, pmf_handle* out) {
     cudaMemset(h->X, 0, xk * 4); cudaMemset(h->Y, 0, yk * 4);
     cudaMemset(h->colinfo, 0, (size_t)h->Np * 4);
     cudaMemset(h->thresholds, 0, 16);
-    cudaMemset(h->ctrl, 0, sizeof(FitControl));
+    cudaMemset(h->ctrl_base, 0, 2 * sizeof(FitControl));
+    cudaMemset(h->scalars_base, 0, 4 * SC_COUNT * sizeof(double));
     std::vector<float> ones(h->Np, 1.f);
     cudaMemcpy(h->weight, ones.data(), (size_t)h->Np * 4, cudaMemcpyHostToDevice);
     cudaMallocHost((void**)&h->ctrl_host, sizeof(FitControl));
@@ -247,7 +249,8 @@ int pmf_destroy(pmf_handle h) {
     big_free(h->wide.G, (size_t)h->N * h->lda, h->dims.device);
     dev_free(h->wide.Xh); dev_free(h->wide.Yh);
     { float* q = static_cast<float*>(h->wide.Xb); dev_free(q); q = static_cast<float*>(h->wide.Yb); dev_free(q); h->wide.Xb = h->wide.Yb = nullptr; }
-    dev_free(h->weight); dev_free(h->colinfo); dev_free(h->thresholds); dev_free(h->acc_thr); dev_free(h->scalars); dev_free(h->ctrl);
+    dev_free(h->weight); dev_free(h->colinfo); dev_free(h->thresholds); dev_free(h->acc_thr); dev_free(h->scalars_base); dev_free(h->ctrl_base);
+    h->scalars = nullptr; h->ctrl = nullptr;
     dev_free(h->vp); dev_free(h->sg); dev_free(h->accvp); dev_free(h->regw); dev_free(h->regc);
     dev_free(h->bcol_off); dev_free(h->bcol_view); dev_free(h->bcol_nb); dev_free(h->batch_of_sample);
     h->free_tc_plan();
@@ -900,6 +903,7 @@ int pmf_fit_start(pmf_handle h, const pmf_fit_opts* o) {
     std::memset(&c, 0, sizeof c);
     c.term_code = PMF_TERM_MAX_EPOCHS;
     c.epochs = o->epoch;
+    h->scalars = h->scalars_base; h->ctrl = h->ctrl_base;
     CU(h, cudaMemcpyAsync(h->ctrl, &c, sizeof c, cudaMemcpyHostToDevice, h->stream));
     h->cur_epoch = o->epoch;
     h->launches = 0;
@@ -955,6 +959,53 @@ int pmf_fit_poll(pmf_handle h, pmf_history* out, int32_t* stopped) {
     return PMF_OK;
 }
 
+// The epoch loop with one fused pass per epoch after the data pass (reg_update.cu: fused_epoch_kernel).  Loss scalars
+// rotate through a ring of three buffers (this epoch / next epoch, whose penalty values this epoch's pass produces at
+// the updated parameters / the one after, cleared meanwhile), the control state through two.
+static int fit_loop_fused(pmf_model_s* h, const pmf_fit_opts* o) {
+    cudaStream_t s = h->stream;
+    const bool sharded = h->comm != nullptr && h->comm_ranks > 1;
+    const int check = o->check_every > 0 ? o->check_every : 8;
+    int rc;
+    CU(h, cudaMemsetAsync(h->scalars_base, 0, 4 * SC_COUNT * sizeof(double), s));
+    if (!h->grads_clean) {
+        CU(h, cudaMemsetAsync(h->dX, 0, (size_t)h->Mp * h->Kp * 4, s));
+        CU(h, cudaMemsetAsync(h->sg, 0, h->sg_len() * 4, s));
+    }
+    h->scalars = h->scalars_base; h->ctrl = h->ctrl_base;
+    if ((rc = h->run_penalty_values(o)) != 0) return rc;           // penalties of the first epoch
+    int since = 0;
+    for (int e = o->epoch; e <= o->max_epochs; ++e) {
+        const int i = e - o->epoch;
+        FitControl* cin = h->ctrl_base + (i & 1);
+        FitControl* cout = h->ctrl_base + ((i + 1) & 1);
+        h->scalars = h->scalars_base + (size_t)(i % 3) * SC_COUNT;
+        h->ctrl = cin;
+        h->grads_clean = true;          // cleared above / by the previous epoch's pass; the scalars ring is managed here
+        if ((rc = phase_begin(h, o, true, false)) != 0) return rc;
+        if ((rc = h->run_network_reg(0, &cin->stop)) != 0) return rc;      // rank-local: before the exchange
+        if (sharded && (rc = h->exchange_gradients()) != 0) return rc;
+        if ((rc = h->run_network_reg(1, &cin->stop)) != 0) return rc;
+        FusedControl fc;
+        fc.cin = cin; fc.cout = cout; fc.sc = h->scalars;
+        fc.sc_zero = h->scalars_base + (size_t)((i + 2) % 3) * SC_COUNT;
+        fc.hist = h->hist; fc.hist_cap = h->hist_cap; fc.epoch = h->cur_epoch;
+        fc.max_epochs = o->no_terminate ? -1 : o->max_epochs; fc.rel_tol = o->rel_tol; fc.abs_tol = o->abs_tol;
+        h->scalars = h->scalars_base + (size_t)((i + 1) % 3) * SC_COUNT;    // the pass adds the NEXT epoch's penalty values
+        if ((rc = h->run_fused_epoch(o, fc)) != 0) return rc;
+        h->ctrl = cout;
+        h->cur_epoch++;
+        if (++since >= check && e < o->max_epochs) {
+            since = 0;
+            CU(h, cudaMemcpyAsync(h->ctrl_host, cout, sizeof(FitControl), cudaMemcpyDeviceToHost, s));
+            CU(h, cudaStreamSynchronize(s));
+            if (h->ctrl_host->stop) break;
+        }
+    }
+    h->scalars = h->scalars_base;
+    return 0;
+}
+
 int pmf_fit(pmf_handle h, const pmf_fit_opts* o, pmf_history* out) {
     CHECK_H(h);
     int rc = pmf_fit_start(h, o);
@@ -962,6 +1013,9 @@ int pmf_fit(pmf_handle h, const pmf_fit_opts* o, pmf_history* out) {
     const int check = o->check_every > 0 ? o->check_every : 8;
     CU(h, cudaEventRecord(h->ev0, h->stream));
     int since = 0;
+    if (!o->alternating) {
+        if ((rc = fit_loop_fused(h, o)) != 0) return rc;
+    } else
     for (int e = o->epoch; e <= o->max_epochs; ++e) {
         // Sharded: X-side penalties are rank-local sums and go before the exchange.  Single GPU: every
         // penalty of the epoch is one launch, after the data pass.
@@ -971,7 +1025,7 @@ int pmf_fit(pmf_handle h, const pmf_fit_opts* o, pmf_history* out) {
         if ((rc = phase_reg_shared(h, true, !sharded)) != 0) return rc;
         CU(h, launch_control(h->ctrl, h->scalars, h->hist, h->hist_cap, h->cur_epoch, o->no_terminate ? -1 : o->max_epochs, o->rel_tol, o->abs_tol, h->stream));
         h->launches++;
-        if (o->alternating) {
+        {
             // SURVEY App. D1, the other reading of MF.fit!: column-side step from this pass, then the row-side step from
             // a SECOND pass at the new column-side parameters (no history record, no termination test of its own; a
             // stop raised above makes every kernel of the second half return at once)
@@ -982,7 +1036,7 @@ int pmf_fit(pmf_handle h, const pmf_fit_opts* o, pmf_history* out) {
                 if (!sharded && (rc = h->run_reg_multi(true, false, false, &h->ctrl->stop)) != 0) return rc;
                 if ((rc = phase_update(h, o, 2)) != 0) return rc;
             }
-        } else if ((rc = phase_update(h, o)) != 0) return rc;
+        }
         h->cur_epoch++;
         if (++since >= check && e < o->max_epochs) {
             since = 0;
@@ -1044,7 +1098,8 @@ int pmf_model_s::exchange_gradients() {
     NcclApi& a = nccl();
     int rc = a.GroupStart();
     if (rc == 0) rc = a.AllReduce(sg, sg, sg_len(), NCCL_FLOAT32, NCCL_SUM, comm, stream);
-    if (rc == 0) rc = a.AllReduce(scalars, scalars, SC_COUNT, NCCL_FLOAT64, NCCL_SUM, comm, stream);
+    // SC_DATA and SC_XREG are rank-local partial sums; the other scalars are replicated and must not be summed
+    if (rc == 0) rc = a.AllReduce(scalars, scalars, 2, NCCL_FLOAT64, NCCL_SUM, comm, stream);
     int rc2 = a.GroupEnd();
     if (rc == 0) rc = rc2;
     if (rc != 0) { cuda_failed = true; return fail(this, PMF_ERR_CUDA, "ncclAllReduce: %s", a.GetErrorString ? a.GetErrorString(rc) : "?"); }
@@ -1587,3 +1642,78 @@ int pmf_model_s::run_update_multi(bool upd_X, bool upd_Y, bool upd_layers, bool 
     return 0;
 }
 
+
+// ---- fused epoch pass (pmf_fit) --------------------------------------------------------------------------------
+// Every elementwise penalty and every AdaGrad step of the epoch as ONE MultiPassParams: the segments of run_reg_multi
+// and run_update_multi merged.  Penalty values are taken at the UPDATED parameters and added into `scalars` (which the
+// caller has pointed at the next epoch's buffer).  values_only: no gradients touched, no update, values at the
+// current parameters (the penalties of a fit's first epoch).
+void pmf_model_s::fill_epoch_pass(MultiPassParams& mp, const pmf_fit_opts* o, bool values_only) {
+    std::memset(&mp, 0, sizeof mp);
+    const bool upd[2] = {o->update_X != 0, o->update_Y != 0};
+    for (int which = 0; which < 2; ++which) {
+        FactorUpdateParams& q = mp.f[mp.nf++];
+        fill_factor_params(which, q);
+        SideReg& r = reg[which];
+        q.l2_w = r.l2_w; q.group_id = r.group_id; q.group_w = r.group_w;
+        q.l1_mask = r.l1_mask; q.l1_w = r.l1_w;
+        q.ard_alpha = r.ard_alpha; q.ard_beta_row = r.ard_beta_row; q.ard_beta_full = r.ard_beta_full;
+        q.loss_out = r.any_elementwise() ? scalars + (which == 0 ? SC_XREG : SC_YREG) : nullptr;
+        q.loss_after = 1;
+        q.lr = o->lr; q.eps = o->adagrad_eps;
+        if (!values_only) {
+            q.do_update = upd[which] ? 1 : 0;
+            q.zero_buf = which == 0 ? dX : g_Y(); q.n_pad = which == 0 ? Mp : Np;
+            if (which == 0 && Xh && xsplit_valid) { q.Ph = Xh; q.Pl = Xl; }
+        }
+    }
+    VecSeg segs[4];
+    vec_segments(this, segs);
+    for (const VecSeg& sgm : segs) {
+        if (sgm.n <= 0) continue;
+        const unsigned bit = 1u << (sgm.slot - 1);
+        // a frozen layer's (or frozen regulariser's) penalty evaluates to 0 (src/regularizers.jl:508-510, :887, :950-1004)
+        const bool reg_on = layer_reg_present[sgm.slot - 1] && !((frozen_regs | frozen_layers) & bit);
+        if (values_only && !reg_on) continue;
+        VectorUpdateParams& q = mp.v[mp.nv++];
+        q.n = sgm.n; q.p = vp + sgm.off; q.grad = sg + (size_t)Np * Kp + sgm.off; q.acc = accvp + sgm.off;
+        q.reg_w = regw + sgm.off; q.reg_c = regc + sgm.off; q.reg_active = reg_on ? 1 : 0;
+        q.loss_out = reg_on ? scalars + SC_LAYERREG : nullptr;
+        q.loss_after = 1;
+        q.lr = o->lr; q.eps = o->adagrad_eps;
+        if (!values_only) {
+            q.do_update = (o->update_col_layers && !(frozen_layers & bit)) ? 1 : 0;
+            q.zero_buf = sg + (size_t)Np * Kp + sgm.off;
+        }
+    }
+    if (!values_only && has_ordinal) {
+        mp.thr = thresholds; mp.thr_grad = g_thr(); mp.thr_acc = acc_thr; mp.thr_ranges = n_ranges;
+        mp.thr_update = o->update_noise_models ? 1 : 0; mp.thr_lr = o->lr; mp.thr_eps = o->adagrad_eps;
+    }
+}
+
+int pmf_model_s::run_penalty_values(const pmf_fit_opts* o) {
+    MultiPassParams mp;
+    fill_epoch_pass(mp, o, true);
+    // only segments that carry a penalty
+    MultiPassParams pr;
+    std::memset(&pr, 0, sizeof pr);
+    for (int i = 0; i < mp.nf; ++i)
+        if (mp.f[i].loss_out) pr.f[pr.nf++] = mp.f[i];
+    for (int i = 0; i < mp.nv; ++i) pr.v[pr.nv++] = mp.v[i];
+    if (pr.nf == 0 && pr.nv == 0) return 0;
+    cudaError_t e = launch_multi_pass(pr, stream, n_sms);
+    if (e != cudaSuccess) { cuda_failed = true; return fail(this, PMF_ERR_CUDA, "penalty value pass launch: %s", cudaGetErrorString(e)); }
+    launches++;
+    return 0;
+}
+
+int pmf_model_s::run_fused_epoch(const pmf_fit_opts* o, const FusedControl& fc) {
+    MultiPassParams mp;
+    fill_epoch_pass(mp, o, false);
+    cudaError_t e = launch_fused_epoch_pass(mp, fc, stream, n_sms);
+    if (e != cudaSuccess) { cuda_failed = true; return fail(this, PMF_ERR_CUDA, "epoch pass launch: %s", cudaGetErrorString(e)); }
+    launches++;
+    grads_clean = true;
+    return 0;
+}

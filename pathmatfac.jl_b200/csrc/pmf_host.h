@@ -113,6 +113,11 @@ struct pmf_model_s {
     uint32_t frozen_layers = 0, frozen_regs = 0;
     SideReg reg[2];
 
+    // Loss scalars and fit-control state.  `scalars` / `ctrl` point at the CURRENT buffers: the fused epoch loop of
+    // pmf_fit rotates them through scalars_base (3 x SC_COUNT ring + 1 spare) and ctrl_base (2), everything else uses
+    // the first of each.
+    double* scalars_base = nullptr;
+    pmf::FitControl* ctrl_base = nullptr;
     double* scalars = nullptr;
     pmf::FitControl* ctrl = nullptr;
     pmf::FitControl* ctrl_host = nullptr;   // pinned
@@ -129,7 +134,6 @@ struct pmf_model_s {
     // sample-sharded multi-GPU: NCCL communicator (opaque; loaded with dlopen) or null
     void* comm = nullptr;
     int comm_ranks = 1;
-    int exchange_gradients();   // all-reduce of sg and of the rank-local loss scalars on `stream`
 
     size_t vp_len() const { return 2 * (size_t)Np + 2 * (size_t)nbp; }
     // shared gradients: [dY | dlogsigma | dmu | dlogdelta | dtheta | interior ordinal thresholds (2 per noise range)]
@@ -151,4 +155,10 @@ struct pmf_model_s {
     int run_network_reg(int which, const int* stop);
     int run_reg_multi(bool x_side, bool y_side, bool vectors, const int* stop);
     int run_update_multi(bool upd_X, bool upd_Y, bool upd_layers, bool upd_noise, float lr, float eps, const int* stop);
+    // the fused epoch pass of pmf_fit (termination test + penalties + update in one launch); values_only: just the
+    // penalty values at the current parameters into `scalars` (first epoch of a fit)
+    void fill_epoch_pass(pmf::MultiPassParams& mp, const pmf_fit_opts* o, bool values_only);
+    int run_penalty_values(const pmf_fit_opts* o);
+    int run_fused_epoch(const pmf_fit_opts* o, const pmf::FusedControl& fc);
+    int exchange_gradients();   // all-reduce of sg and of the rank-local loss scalars on `stream`
 };

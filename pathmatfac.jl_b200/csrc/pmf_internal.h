@@ -70,6 +70,7 @@ struct FactorUpdateParams {
     const float* ard_beta_full; // [n][Kp] or null
     double* loss_out;           // scalar accumulated (pre-update value of the penalty)
     int do_update;
+    int loss_after;             // fused epoch pass: the penalty VALUE is taken at the updated parameters (next epoch's loss)
     float lr, eps;
     const int* stop_flag;
     // optional by-products of the update pass
@@ -93,6 +94,7 @@ struct VectorUpdateParams {
     double* loss_out;
     int reg_active;             // 0 when the slot's regulariser is frozen / absent
     int do_update;
+    int loss_after;             // as in FactorUpdateParams
     float lr, eps;
     const int* stop_flag;
     float* zero_buf;            // gradient segment to clear once consumed, or null
@@ -113,6 +115,21 @@ struct MultiPassParams {
     int thr_ranges;             // 0: nothing to do
     int thr_update;             // AdaGrad step (else only the gradients are cleared)
     float thr_lr, thr_eps;
+};
+
+// Fused epoch pass (pmf_fit): termination test + penalties + AdaGrad step in ONE launch.  Every block evaluates the
+// test from the epoch's loss scalars and the control state of the PREVIOUS epoch (read-only during the launch: state
+// and scalars are ring buffers), block 0 writes the next state and the history record.
+struct FitControl;
+struct FusedControl {
+    const FitControl* cin;    // state left by the previous epoch
+    FitControl* cout;         // state for the next epoch
+    const double* sc;         // this epoch's loss scalars (data loss from the data pass, penalties from the previous
+                              //   epoch's pass, which evaluated them at the updated parameters)
+    double* sc_zero;          // the scalars of the epoch after next: cleared here
+    double* hist;
+    int hist_cap, epoch, max_epochs;
+    double rel_tol, abs_tol;
 };
 
 struct FitControl {
@@ -202,6 +219,7 @@ cudaError_t launch_data_pass_tc(const DataPassParams& p, float* Xh, float* Xl, b
 // A_tc rows for the plan (fused_tc.cu)
 cudaError_t launch_build_a_tc(const DataPassParams& p, const TcBatchDev& bp, float* A_tc, cudaStream_t s);
 cudaError_t launch_multi_pass(const MultiPassParams& p, cudaStream_t s, int n_sms);
+cudaError_t launch_fused_epoch_pass(const MultiPassParams& p, const FusedControl& fc, cudaStream_t s, int n_sms);
 cudaError_t launch_control(FitControl* ctrl, const double* scalars, double* hist, int hist_cap,
                            int epoch, int max_epochs, double rel_tol, double abs_tol, cudaStream_t s);
 cudaError_t launch_network_reg(const NetworkParams& p, cudaStream_t s);

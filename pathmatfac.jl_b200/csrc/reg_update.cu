@@ -44,29 +44,33 @@ __device__ __forceinline__ void factor_pass(const FactorUpdateParams& q, int bid
         const int gid = q.group_id ? q.group_id[row] : -1;
         const float al = q.ard_alpha ? q.ard_alpha[row] : 0.f;
         const float brow = q.ard_beta_row ? q.ard_beta_row[row] : 1.f;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        // value and pullback of every elementwise penalty at x (factor k = 4 c4 + c of this row)
+        auto penalty = [&](int c, float x, float& l, float& g) {
             const int k = 4 * c4 + c;
-            const float x = pa[c];
             float w = 0.f;
             if (q.l2_w) w += q.l2_w[k];
             if (gid >= 0) w += q.group_w[(size_t)gid * q.Kp + k];
-            float g = ga[c] + w * x;
-            loss += 0.5f * w * x * x;
+            g = w * x;
+            l = 0.5f * w * x * x;
             if (q.l1_mask && q.l1_mask[off + c]) {
                 float w1 = q.l1_w[k];
-                loss += w1 * fabsf(x);
+                l += w1 * fabsf(x);
                 g += w1 * (x > 0.f ? 1.f : (x < 0.f ? -1.f : 0.f));
             }
             if (q.ard_alpha && k < q.K) {
                 float beta = q.ard_beta_full ? q.ard_beta_full[off + c] : brow;
                 float b = 1.f + (0.5f / beta) * x * x;
-                loss += (0.5f + al) * logf(b);
+                l += (0.5f + al) * logf(b);
                 g += (al + 0.5f) * x / (b * beta);
             }
-            ga[c] = g;
+        };
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            float l, g;
+            penalty(c, pa[c], l, g);
+            ga[c] += g;
+            if (!q.loss_after) loss += l;
         }
-        lsum += (double)loss;
         if (q.grad_out) *reinterpret_cast<float4*>(q.grad_out + off) = make_float4(ga[0], ga[1], ga[2], ga[3]);
         if (q.do_update) {
             float4 av = *reinterpret_cast<const float4*>(q.acc + off);
@@ -79,6 +83,15 @@ __device__ __forceinline__ void factor_pass(const FactorUpdateParams& q, int bid
             *reinterpret_cast<float4*>(q.acc + off) = make_float4(aa[0], aa[1], aa[2], aa[3]);
             *reinterpret_cast<float4*>(q.P + off) = make_float4(pa[0], pa[1], pa[2], pa[3]);
         }
+        if (q.loss_after && q.loss_out) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                float l, g;
+                penalty(c, pa[c], l, g);
+                loss += l;
+            }
+        }
+        lsum += (double)loss;
         if (q.Ph) {   // operand split of the (updated) parameters for the next tcgen05 data pass (Kp <= 64):
             float h[4];   // Ph = rna_tf32(P) as FP32 [n][64], Pl = bf16([Ph | P - Ph]) as [n][128] BF16, zero padded
 #pragma unroll
@@ -106,17 +119,22 @@ __device__ __forceinline__ void vector_pass(const VectorUpdateParams& q, int bid
     for (int idx = bid * blockDim.x + threadIdx.x; idx < q.n; idx += nblk * blockDim.x) {
         float x = q.p[idx];
         float g = q.grad[idx];
-        if (q.reg_active && q.reg_w) {
-            float w = q.reg_w[idx], d = x - q.reg_c[idx];
+        const bool reg = q.reg_active && q.reg_w;
+        float w = 0.f, cen = 0.f;
+        if (reg) {
+            w = q.reg_w[idx]; cen = q.reg_c[idx];
+            const float d = x - cen;
             g += w * d;
-            lsum += (double)(0.5f * w * d * d);
+            if (!q.loss_after) lsum += (double)(0.5f * w * d * d);
         }
         if (q.grad_out) q.grad_out[idx] = g;
         if (q.do_update) {
             float a = q.acc[idx] + g * g;
             q.acc[idx] = a;
-            q.p[idx] = x - q.lr * g / (sqrtf(a) + q.eps);
+            x -= q.lr * g / (sqrtf(a) + q.eps);
+            q.p[idx] = x;
         }
+        if (reg && q.loss_after) { const float d = x - cen; lsum += (double)(0.5f * w * d * d); }
         if (q.zero_buf) q.zero_buf[idx] = 0.f;
     }
     double tot = block_reduce_sum_double(lsum, red_smem);
@@ -125,8 +143,7 @@ __device__ __forceinline__ void vector_pass(const VectorUpdateParams& q, int bid
 
 // Segments share the grid: factor segment s owns blocks [fb[s], fb[s+1]); the vector segments share the
 // last `vblocks` blocks one after the other (they are tiny).
-__global__ void __launch_bounds__(UT) multi_pass_kernel(const __grid_constant__ MultiPassParams mp, int fb1, int fb2) {
-    __shared__ double red_smem[UT / 32];
+__device__ __forceinline__ void multi_pass_body(const MultiPassParams& mp, int fb1, int fb2, double* red_smem) {
     const int b = blockIdx.x;
     if (mp.nf > 0 && b < fb1) factor_pass(mp.f[0], b, fb1, red_smem);
     else if (mp.nf > 1 && b < fb2) factor_pass(mp.f[1], b - fb1, fb2 - fb1, red_smem);
@@ -152,6 +169,66 @@ __global__ void __launch_bounds__(UT) multi_pass_kernel(const __grid_constant__ 
             mp.thr_grad[t] = 0.f;
         }
     }
+}
+
+__global__ void __launch_bounds__(UT) multi_pass_kernel(const __grid_constant__ MultiPassParams mp, int fb1, int fb2) {
+    __shared__ double red_smem[UT / 32];
+    multi_pass_body(mp, fb1, fb2, red_smem);
+}
+
+// The termination test of MF.fit! (same rules as control_kernel below) on the loss of this epoch
+// against the previous one.  Returns the term code (>= 0: stop) or -1.
+__device__ __forceinline__ int termination_test(const FitControl& c, double total, int max_epochs, double rel_tol, double abs_tol) {
+    if (max_epochs < 0) return -1;                        // bench hook (no_terminate): record the loss, never stop
+    if (!isfinite(total)) return 4;                       // nonfinite
+    if (c.have_prev) {
+        const double d = c.prev_loss - total;
+        if (d < 0) return 3;                              // loss_increase
+        if (fabs(d) < abs_tol) return 1;                  // abs_tol
+        if (fabs(d / total) < rel_tol) return 2;          // rel_tol
+    }
+    return -1;
+}
+
+// Fused epoch pass: termination test, then (unless it fired) every elementwise penalty pullback + AdaGrad step, the
+// penalty VALUES at the updated parameters (they belong to the next epoch's loss), gradient clearing and the operand
+// split of X -- what used to be the penalty pass, the one-thread control launch and the update pass.
+__global__ void __launch_bounds__(UT) fused_epoch_kernel(const __grid_constant__ MultiPassParams mp,
+                                                         const __grid_constant__ FusedControl fc, int fb1, int fb2) {
+    __shared__ double red_smem[UT / 32];
+    __shared__ int s_stop;
+    if (threadIdx.x == 0) {
+        const FitControl c = *fc.cin;
+        int stop = c.stop;
+        if (!stop) {
+            const double total = fc.sc[SC_DATA] + fc.sc[SC_XREG] + fc.sc[SC_YREG] + fc.sc[SC_LAYERREG];
+            const int code = termination_test(c, total, fc.max_epochs, fc.rel_tol, fc.abs_tol);
+            stop = code >= 0;
+            if (blockIdx.x == 0) {
+                FitControl n = c;
+                const int r = c.n_recorded;
+                if (r < fc.hist_cap) {
+                    fc.hist[5 * r + 0] = total;
+                    fc.hist[5 * r + 1] = fc.sc[SC_DATA];
+                    fc.hist[5 * r + 2] = fc.sc[SC_XREG];
+                    fc.hist[5 * r + 3] = fc.sc[SC_YREG];
+                    fc.hist[5 * r + 4] = fc.sc[SC_LAYERREG];
+                }
+                n.n_recorded = r + 1;
+                n.epochs = fc.epoch;
+                if (stop) { n.stop = 1; n.term_code = code; }
+                else { n.prev_loss = total; n.have_prev = 1; }
+                *fc.cout = n;
+            }
+        } else if (blockIdx.x == 0) {
+            *fc.cout = c;
+        }
+        s_stop = stop;
+    }
+    __syncthreads();
+    if (blockIdx.x == 0 && threadIdx.x < SC_COUNT) fc.sc_zero[threadIdx.x] = 0.0;
+    if (s_stop) return;
+    multi_pass_body(mp, fb1, fb2, red_smem);
 }
 
 // Termination test of MF.fit!, evaluated on the device so the epoch loop
@@ -312,23 +389,36 @@ __global__ void __launch_bounds__(NTH) network_reg_kernel(NetworkParams q) {
 
 }  // namespace
 
-cudaError_t launch_multi_pass(const MultiPassParams& mp, cudaStream_t s, int n_sms) {
+static void multi_pass_grid(const MultiPassParams& mp, int n_sms, int& fb1, int& fb2, int& grid) {
     auto fblocks = [&](const FactorUpdateParams& q) {
         size_t total4 = (size_t)(q.zero_buf ? q.n_pad : q.n) * (q.Kp >> 2);
         long long b = (long long)((total4 + UT - 1) / UT);
         const long long cap = (long long)n_sms * 6;
         return (int)(b > cap ? cap : (b < 1 ? 1 : b));
     };
-    int fb1 = mp.nf > 0 ? fblocks(mp.f[0]) : 0;
-    int fb2 = fb1 + (mp.nf > 1 ? fblocks(mp.f[1]) : 0);
+    fb1 = mp.nf > 0 ? fblocks(mp.f[0]) : 0;
+    fb2 = fb1 + (mp.nf > 1 ? fblocks(mp.f[1]) : 0);
     int nmax = 0;
     for (int i = 0; i < mp.nv; ++i) nmax = mp.v[i].n > nmax ? mp.v[i].n : nmax;
-    int vblocks = (mp.nv > 0 || mp.zero_scalars) ? (nmax + UT - 1) / UT : 0;
+    int vblocks = (mp.nv > 0 || mp.zero_scalars || mp.thr_ranges > 0) ? (nmax + UT - 1) / UT : 0;
     if (vblocks > n_sms) vblocks = n_sms;
-    if ((mp.nv > 0 || mp.zero_scalars) && vblocks < 1) vblocks = 1;
-    const int grid = fb2 + vblocks;
+    if ((mp.nv > 0 || mp.zero_scalars || mp.thr_ranges > 0) && vblocks < 1) vblocks = 1;
+    grid = fb2 + vblocks;
+}
+
+cudaError_t launch_multi_pass(const MultiPassParams& mp, cudaStream_t s, int n_sms) {
+    int fb1, fb2, grid;
+    multi_pass_grid(mp, n_sms, fb1, fb2, grid);
     if (grid <= 0) return cudaSuccess;
     multi_pass_kernel<<<grid, UT, 0, s>>>(mp, fb1, fb2);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fused_epoch_pass(const MultiPassParams& mp, const FusedControl& fc, cudaStream_t s, int n_sms) {
+    int fb1, fb2, grid;
+    multi_pass_grid(mp, n_sms, fb1, fb2, grid);
+    if (grid <= 0) grid = 1;
+    fused_epoch_kernel<<<grid, UT, 0, s>>>(mp, fc, fb1, fb2);
     return cudaGetLastError();
 }
 
