@@ -676,6 +676,10 @@ int pmf_set_reg_network(pmf_handle h, int32_t which, const int32_t* nv, const in
     CU(h, cudaMemset(net.u, 0, (size_t)std::max<int64_t>(vt, 1) * 4));
     if (xv && vt > 0) CU(h, cudaMemcpy(net.u, xv, (size_t)vt * 4, cudaMemcpyHostToDevice));
     net.nv_total = vt;
+    net.nv_max = 0;
+    for (int k = 0; k < K; ++k) net.nv_max = std::max(net.nv_max, (int)nv[k]);
+    net.ld = round_up(n, 32);
+    CU(h, dev_alloc(&net.yt, (size_t)K * net.ld)); CU(h, dev_alloc(&net.gt, (size_t)K * net.ld));
     net.p = p;
     const float deps = std::sqrt(1.1920929e-7f);
     net.rtol = rtol > 0 ? rtol : deps;
@@ -1545,11 +1549,12 @@ int pmf_model_s::run_network_reg(int which, const int* stop) {
     auto cv = [](const DevCsr& d) { CsrBlock b{d.rowptr, d.col, d.val, d.rowptr_base, d.nnz_base}; return b; };
     q.AA = cv(r.net.AA); q.AB = cv(r.net.AB); q.BB = cv(r.net.BB); q.ABt = cv(r.net.ABt);
     q.nv = r.net.nv; q.virt_base = r.net.virt_base; q.u = r.net.u; q.work = r.net.work; q.nv_total = r.net.nv_total;
+    q.yt = r.net.yt; q.gt = r.net.gt; q.ld = r.net.ld;
     q.p = r.net.p; q.rtol = r.net.rtol; q.atol = r.net.atol; q.itmax = r.net.itmax;
     q.loss_out = scalars + (which == 0 ? SC_XREG : SC_YREG); q.stop_flag = stop;
-    cudaError_t e = launch_network_reg(q, stream);
+    cudaError_t e = launch_network_reg(q, stream, n_sms, r.net.nv_max);
     if (e != cudaSuccess) { cuda_failed = true; return fail(this, PMF_ERR_CUDA, "network reg launch: %s", cudaGetErrorString(e)); }
-    launches++;
+    launches += r.net.nv_max > 0 ? 4 : 3;
     return 0;
 }
 

@@ -33,13 +33,16 @@ struct DevNetwork {
     int64_t* virt_base = nullptr;
     float* u = nullptr;
     float* work = nullptr;
+    float* yt = nullptr;      // [K][ld] transposed factor matrix / per-factor gradient (scratch of the pass)
+    float* gt = nullptr;
+    int ld = 0, nv_max = 0;
     int64_t nv_total = 0;
     float p = 1.f, rtol = 0.f, atol = 0.f;
     int itmax = 0;
     void free_all() {
         AA.free_all(); AB.free_all(); BB.free_all(); ABt.free_all();
-        cudaFree(nv); cudaFree(virt_base); cudaFree(u); cudaFree(work);
-        nv = nullptr; virt_base = nullptr; u = work = nullptr;
+        cudaFree(nv); cudaFree(virt_base); cudaFree(u); cudaFree(work); cudaFree(yt); cudaFree(gt);
+        nv = nullptr; virt_base = nullptr; u = work = yt = gt = nullptr;
         present = false; nv_total = 0;
     }
 };

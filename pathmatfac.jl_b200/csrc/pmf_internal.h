@@ -157,6 +157,9 @@ struct NetworkParams {
     CsrBlock AA, AB, BB, ABt;  // ABt: CSR of AB^T (nv rows)
     const int32_t* nv;       // [K]
     const int64_t* virt_base;    // [K] offset into the virtual-node vectors
+    float* yt;               // [K][ld] transposed copy of P (scratch)
+    float* gt;               // [K][ld] AA y + AB u per factor (scratch)
+    int ld;
     float* u;                // x_virtual (sign-flipped convention of the reference)
     float* work;             // 4 * sum(nv) scratch: r, pvec, Ap, rhs
     int64_t nv_total;
@@ -222,6 +225,7 @@ cudaError_t launch_multi_pass(const MultiPassParams& p, cudaStream_t s, int n_sm
 cudaError_t launch_fused_epoch_pass(const MultiPassParams& p, const FusedControl& fc, cudaStream_t s, int n_sms);
 cudaError_t launch_control(FitControl* ctrl, const double* scalars, double* hist, int hist_cap,
                            int epoch, int max_epochs, double rel_tol, double abs_tol, cudaStream_t s);
-cudaError_t launch_network_reg(const NetworkParams& p, cudaStream_t s);
+// four launches (transpose in, virtual-node solves, rows, transpose-add); nv_max = max virtual nodes over the factors
+cudaError_t launch_network_reg(const NetworkParams& p, cudaStream_t s, int n_sms, int nv_max);
 
 }  // namespace pmf

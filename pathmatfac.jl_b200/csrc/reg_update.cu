@@ -267,14 +267,22 @@ __global__ void control_kernel(FitControl* c, const double* sc, double* hist, in
 }
 
 // ---------------------------------------------------------------------------------------------
-// Graph-Laplacian regulariser.  One CTA per latent factor k (the K Laplacians are independent,
-// src/regularizers.jl:169-183).  For its factor the CTA
-//   rhs  = AB_k' y_k                      (CSR of AB_k^T, sub-warp per row)
-//   u    = -cg(BB_k, rhs, warm start)     (Krylov.cg semantics, src/regularizers.jl:284)
-//   grad = AA_k y_k + AB_k u              (:285-299)      loss = .5 y'AAy + y'ABu + .5 u'BBu
-// with every vector of the solve living in L2-resident global scratch.
+// Graph-Laplacian regulariser (NetworkRegularizer, src/regularizers.jl:169-306): K independent Laplacians, one per
+// latent factor, each split into observed x observed (AA), observed x virtual (AB) and virtual x virtual (BB) blocks.
+//   rhs  = AB_k' y_k ;  u_k = -cg(BB_k, rhs, warm start)   (Krylov.cg semantics, :256,284; stored sign-flipped)
+//   grad = AA_k y_k + AB_k u_k                              (:285-299)    loss = .5 y'AAy + y'ABu + .5 u'BBu
+// The factor matrix is [n][Kp] (a factor's vector is a stride-Kp column), so the pass works on a TRANSPOSED copy
+// Yt [K][ld]: a factor's vector is contiguous, thread j of a block owns row j of the factor's CSR blocks (the graphs
+// have a handful of entries per row: the diagonal plus the node's edges), its loads of rowptr / diagonal / yt and its
+// store of the gradient are coalesced and the off-diagonal gathers stay inside the factor's 4 n bytes.  Four launches:
+//   transpose_in   Y -> Yt                                        (tiled through shared memory)
+//   virtual        per factor one CTA: rhs, warm-started CG on BB with every vector in shared memory (nv <= NV_SMEM,
+//                  else in global scratch), u, 0.5 u'BBu
+//   rows           grid (row chunks, K): AA y + AB u -> Gt, 0.5 y'AAy + y'ABu
+//   transpose_add  grad += p Gt'
 // ---------------------------------------------------------------------------------------------
-constexpr int NTH = 512;
+constexpr int NTH = 256;
+constexpr int NV_SMEM = 8192;       // virtual nodes per factor whose CG vectors fit shared memory (5 x 4 x nv bytes)
 
 __device__ __forceinline__ float block_sum(float v, float* sm) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -293,97 +301,149 @@ __device__ __forceinline__ float block_sum(float v, float* sm) {
     return t;
 }
 
-// y = M x for a CSR segment; x gathered through (ptr, stride)
+// one CSR row times a contiguous vector
 __device__ __forceinline__ float csr_row_dot(const int32_t* __restrict__ rp, const int32_t* __restrict__ col,
-                                             const float* __restrict__ val, int row,
-                                             const float* __restrict__ x, int xstride) {
+                                             const float* __restrict__ val, int row, const float* __restrict__ x) {
     float s = 0.f;
-    for (int e = rp[row]; e < rp[row + 1]; ++e) s = fmaf(val[e], x[(size_t)col[e] * xstride], s);
+    for (int e = rp[row]; e < rp[row + 1]; ++e) s = fmaf(val[e], x[col[e]], s);
     return s;
 }
 
-__global__ void __launch_bounds__(NTH) network_reg_kernel(NetworkParams q) {
+// out[k][j] = in[j][k]  (in: [rows][Kp], out: [K][ld]); 32 x 32 tiles
+__global__ void transpose_in_kernel(const float* __restrict__ in, float* __restrict__ out, int rows, int Kp, int K, int ld,
+                                    const int* stop_flag) {
+    if (stop_flag != nullptr && *stop_flag != 0) return;
+    __shared__ float tile[32][33];
+    const int j0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int j = j0 + r, k = k0 + threadIdx.x;
+        tile[r][threadIdx.x] = (j < rows && k < K) ? in[(size_t)j * Kp + k] : 0.f;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int k = k0 + r, j = j0 + threadIdx.x;
+        if (k < K && j < rows) out[(size_t)k * ld + j] = tile[threadIdx.x][r];
+    }
+}
+
+// grad[j][k] += p * gt[k][j]
+__global__ void transpose_add_kernel(const float* __restrict__ gt, float* __restrict__ grad, int rows, int Kp, int K, int ld,
+                                     float p, const int* stop_flag) {
+    if (stop_flag != nullptr && *stop_flag != 0) return;
+    __shared__ float tile[32][33];
+    const int j0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int k = k0 + r, j = j0 + threadIdx.x;
+        tile[r][threadIdx.x] = (k < K && j < rows) ? gt[(size_t)k * ld + j] : 0.f;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int j = j0 + r, k = k0 + threadIdx.x;
+        if (j < rows && k < K) grad[(size_t)j * Kp + k] += p * tile[threadIdx.x][r];
+    }
+}
+
+__global__ void __launch_bounds__(NTH) network_virtual_kernel(NetworkParams q) {
     if (q.stop_flag != nullptr && *q.stop_flag != 0) return;
+    extern __shared__ float dyn[];
     __shared__ float sm[NTH / 32];
     const int k = blockIdx.x;
-    const int n = q.n, nv = q.nv[k];
-    const float* y = q.P + k;                 // y_k[j] = P[j*Kp + k]
-    const int ys = q.Kp;
-    const int32_t* aa_rp = q.AA.rowptr + q.AA.rowptr_base[k];
-    const int32_t* aa_c = q.AA.col + q.AA.nnz_base[k];
-    const float* aa_v = q.AA.val + q.AA.nnz_base[k];
-    const int32_t* ab_rp = q.AB.rowptr + q.AB.rowptr_base[k];
-    const int32_t* ab_c = q.AB.col + q.AB.nnz_base[k];
-    const float* ab_v = q.AB.val + q.AB.nnz_base[k];
+    const int nv = q.nv[k];
+    if (nv <= 0) return;
+    const float* y = q.yt + (size_t)k * q.ld;
     const int32_t* abt_rp = q.ABt.rowptr + q.ABt.rowptr_base[k];
     const int32_t* abt_c = q.ABt.col + q.ABt.nnz_base[k];
     const float* abt_v = q.ABt.val + q.ABt.nnz_base[k];
     const int32_t* bb_rp = q.BB.rowptr + q.BB.rowptr_base[k];
     const int32_t* bb_c = q.BB.col + q.BB.nnz_base[k];
     const float* bb_v = q.BB.val + q.BB.nnz_base[k];
-    float* u = q.u + q.virt_base[k];
-    float* r = q.work + q.virt_base[k];
-    float* pv = q.work + q.nv_total + q.virt_base[k];
-    float* Ap = q.work + 2 * q.nv_total + q.virt_base[k];
-    float* rhs = q.work + 3 * q.nv_total + q.virt_base[k];
+    float* ug = q.u + q.virt_base[k];
+    const bool in_smem = nv <= NV_SMEM;
+    float* u = in_smem ? dyn : ug;
+    float* r = in_smem ? dyn + nv : q.work + q.virt_base[k];
+    float* pv = in_smem ? dyn + 2 * nv : q.work + q.nv_total + q.virt_base[k];
+    float* Ap = in_smem ? dyn + 3 * nv : q.work + 2 * q.nv_total + q.virt_base[k];
+    float* rhs = in_smem ? dyn + 4 * nv : q.work + 3 * q.nv_total + q.virt_base[k];
 
-    if (nv > 0) {
-        // rhs = AB' y ; x0 = stored (sign-flipped) vector, reference quirk (vi)
-        for (int v = threadIdx.x; v < nv; v += NTH) rhs[v] = csr_row_dot(abt_rp, abt_c, abt_v, v, y, ys);
-        __syncthreads();
-        float rr = 0.f;
+    // rhs = AB' y ; x0 = stored (sign-flipped) vector, reference quirk (vi)
+    for (int v = threadIdx.x; v < nv; v += NTH) {
+        rhs[v] = csr_row_dot(abt_rp, abt_c, abt_v, v, y);
+        if (in_smem) u[v] = ug[v];
+    }
+    __syncthreads();
+    float rr = 0.f;
+    for (int v = threadIdx.x; v < nv; v += NTH) {
+        float res = rhs[v] - csr_row_dot(bb_rp, bb_c, bb_v, v, u);
+        r[v] = res;
+        pv[v] = res;
+        rr += res * res;
+    }
+    float gamma = block_sum(rr, sm);
+    float rnorm = sqrtf(gamma);
+    const float tol = q.atol + q.rtol * rnorm;
+    const int itmax = q.itmax > 0 ? q.itmax : 2 * nv;
+    int it = 0;
+    while (rnorm > tol && it < itmax) {
+        float pap = 0.f;
         for (int v = threadIdx.x; v < nv; v += NTH) {
-            float res = rhs[v] - csr_row_dot(bb_rp, bb_c, bb_v, v, u, 1);
+            float a = csr_row_dot(bb_rp, bb_c, bb_v, v, pv);
+            Ap[v] = a;
+            pap += pv[v] * a;
+        }
+        pap = block_sum(pap, sm);
+        if (!(pap > 0.f)) break;
+        float alpha = gamma / pap;
+        float rr2 = 0.f;
+        for (int v = threadIdx.x; v < nv; v += NTH) {
+            u[v] += alpha * pv[v];
+            float res = r[v] - alpha * Ap[v];
             r[v] = res;
-            pv[v] = res;
-            rr += res * res;
+            rr2 += res * res;
         }
-        float gamma = block_sum(rr, sm);
-        float rnorm = sqrtf(gamma);
-        const float tol = q.atol + q.rtol * rnorm;
-        const int itmax = q.itmax > 0 ? q.itmax : 2 * nv;
-        int it = 0;
-        while (rnorm > tol && it < itmax) {
-            float pap = 0.f;
-            for (int v = threadIdx.x; v < nv; v += NTH) {
-                float a = csr_row_dot(bb_rp, bb_c, bb_v, v, pv, 1);
-                Ap[v] = a;
-                pap += pv[v] * a;
-            }
-            pap = block_sum(pap, sm);
-            if (!(pap > 0.f)) break;
-            float alpha = gamma / pap;
-            float rr2 = 0.f;
-            for (int v = threadIdx.x; v < nv; v += NTH) {
-                u[v] += alpha * pv[v];
-                float res = r[v] - alpha * Ap[v];
-                r[v] = res;
-                rr2 += res * res;
-            }
-            float gnext = block_sum(rr2, sm);
-            float beta = gnext / gamma;
-            gamma = gnext;
-            rnorm = sqrtf(gamma);
-            for (int v = threadIdx.x; v < nv; v += NTH) pv[v] = r[v] + beta * pv[v];
-            __syncthreads();
-            ++it;
-        }
-        // x_virtual = -cg(...)
-        for (int v = threadIdx.x; v < nv; v += NTH) u[v] = -u[v];
+        float gnext = block_sum(rr2, sm);
+        float beta = gnext / gamma;
+        gamma = gnext;
+        rnorm = sqrtf(gamma);
+        for (int v = threadIdx.x; v < nv; v += NTH) pv[v] = r[v] + beta * pv[v];
         __syncthreads();
+        ++it;
     }
-    // gradient and loss
-    float l1 = 0.f, l2 = 0.f;
-    for (int j = threadIdx.x; j < n; j += NTH) {
-        float yj = y[(size_t)j * ys];
-        float xaa = csr_row_dot(aa_rp, aa_c, aa_v, j, y, ys);
-        float abu = nv > 0 ? csr_row_dot(ab_rp, ab_c, ab_v, j, u, 1) : 0.f;
+    // x_virtual = -cg(...)
+    for (int v = threadIdx.x; v < nv; v += NTH) u[v] = -u[v];
+    __syncthreads();
+    float l2 = 0.f;
+    for (int v = threadIdx.x; v < nv; v += NTH) {
+        l2 += 0.5f * u[v] * csr_row_dot(bb_rp, bb_c, bb_v, v, u);
+        if (in_smem) ug[v] = u[v];
+    }
+    float tot = block_sum(l2, sm);
+    if (threadIdx.x == 0 && tot != 0.f) atomicAdd(q.loss_out, (double)(q.p * tot));
+}
+
+__global__ void __launch_bounds__(NTH) network_rows_kernel(NetworkParams q) {
+    if (q.stop_flag != nullptr && *q.stop_flag != 0) return;
+    __shared__ float sm[NTH / 32];
+    const int k = blockIdx.y;
+    const int nv = q.nv[k];
+    const float* y = q.yt + (size_t)k * q.ld;
+    float* g = q.gt + (size_t)k * q.ld;
+    const int32_t* aa_rp = q.AA.rowptr + q.AA.rowptr_base[k];
+    const int32_t* aa_c = q.AA.col + q.AA.nnz_base[k];
+    const float* aa_v = q.AA.val + q.AA.nnz_base[k];
+    const int32_t* ab_rp = q.AB.rowptr + q.AB.rowptr_base[k];
+    const int32_t* ab_c = q.AB.col + q.AB.nnz_base[k];
+    const float* ab_v = q.AB.val + q.AB.nnz_base[k];
+    const float* u = q.u + q.virt_base[k];
+    float l1 = 0.f;
+    for (int j = blockIdx.x * NTH + threadIdx.x; j < q.n; j += gridDim.x * NTH) {
+        const float yj = y[j];
+        const float xaa = csr_row_dot(aa_rp, aa_c, aa_v, j, y);
+        const float abu = nv > 0 ? csr_row_dot(ab_rp, ab_c, ab_v, j, u) : 0.f;
         l1 += 0.5f * xaa * yj + yj * abu;
-        q.grad[(size_t)j * q.Kp + k] += q.p * (xaa + abu);
+        g[j] = xaa + abu;
     }
-    for (int v = threadIdx.x; v < nv; v += NTH) l2 += 0.5f * u[v] * csr_row_dot(bb_rp, bb_c, bb_v, v, u, 1);
-    float tot = block_sum(l1 + l2, sm);
-    if (threadIdx.x == 0) atomicAdd(q.loss_out, (double)(q.p * tot));
+    float tot = block_sum(l1, sm);
+    if (threadIdx.x == 0 && tot != 0.f) atomicAdd(q.loss_out, (double)(q.p * tot));
 }
 
 
@@ -428,8 +488,21 @@ cudaError_t launch_control(FitControl* ctrl, const double* scalars, double* hist
     return cudaGetLastError();
 }
 
-cudaError_t launch_network_reg(const NetworkParams& p, cudaStream_t s) {
-    network_reg_kernel<<<p.K, NTH, 0, s>>>(p);
+cudaError_t launch_network_reg(const NetworkParams& p, cudaStream_t s, int n_sms, int nv_max) {
+    const dim3 tb(32, 8), tg((p.n + 31) / 32, (p.K + 31) / 32);
+    transpose_in_kernel<<<tg, tb, 0, s>>>(p.P, p.yt, p.n, p.Kp, p.K, p.ld, p.stop_flag);
+    if (nv_max > 0) {
+        const size_t smem = nv_max <= NV_SMEM ? (size_t)5 * nv_max * sizeof(float) : 0;
+        cudaError_t e = cudaFuncSetAttribute(network_virtual_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        network_virtual_kernel<<<p.K, NTH, smem, s>>>(p);
+    }
+    // one row per thread: the pass is a chain of dependent loads per row (rowptr -> column / value -> gather), so it
+    // wants as many rows in flight as the SMs hold
+    const int chunks = (p.n + NTH - 1) / NTH;
+    (void)n_sms;
+    network_rows_kernel<<<dim3(chunks, p.K), NTH, 0, s>>>(p);
+    transpose_add_kernel<<<tg, tb, 0, s>>>(p.gt, p.grad, p.n, p.Kp, p.K, p.ld, p.p, p.stop_flag);
     return cudaGetLastError();
 }
 

@@ -6,7 +6,7 @@ import pytest
 import pathmatfac_b200 as P
 from pathmatfac_b200 import _lib
 from oracle import pmf_oracle as O
-from tests.helpers import make_pair, relerr
+from tests.helpers import make_pair, random_graphs as _graphs, relerr
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-4
@@ -239,3 +239,28 @@ def test_alternating_epochs(kernel, M, N):
     h_s = P.mf_fit(model_s, lr=0.25, alternating=False, verbosity=0, kernel=kernel, **kw)
     assert abs(h_s["loss"][3] / h["loss"][3] - 1) > 1e-3
     assert h["kernel_launches"] > h_s["kernel_launches"]
+
+
+def test_network_regulariser_at_a_3000_feature_cut():
+    """NetworkRegularizer (src/regularizers.jl:169-306) on a 3 000-feature cut of the C4 shape: K = 24 per-factor graphs
+    with ~800 signed edges and 80 virtual nodes each (virtual-node CG in shared memory), selective L1 beside it; value
+    and pullback against the oracle, then a warm-started second evaluation (x_virtual carried over, reference quirk vi)."""
+    rng = np.random.default_rng(77)
+    N, K = 3000, 24
+    graphs = _graphs(N, K, rng, n_virtual=80, n_edges=800)
+    model, om, D = make_pair(120, {"mrnaseq": ("normal", N)}, K=K, seed=430, feature_graphs=graphs,
+                             lambda_Y_selective_l1=0.5, lambda_Y_graph=1.0)
+    for r in model.matfac.Y_reg.regularizers:
+        if isinstance(r, P.NetworkRegularizer):
+            r.cg_rtol, r.cg_atol = 1e-7, 1e-10
+    eng = P.Engine(model)
+    try:
+        got = eng.loss_grad(include_reg=True)
+        again = eng.loss_grad(include_reg=True)
+    finally:
+        eng.close()
+    ref = O.total_loss_grads(om, D)
+    assert abs(got["components"]["Y_reg"] - ref["components"]["Y_reg"]) <= TOL * abs(ref["components"]["Y_reg"])
+    assert relerr(got["dY"], ref["dY"]) < TOL
+    assert abs(again["components"]["Y_reg"] - got["components"]["Y_reg"]) <= 1e-5 * abs(got["components"]["Y_reg"])
+    assert relerr(again["dY"], got["dY"]) < 1e-5
