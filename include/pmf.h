@@ -308,6 +308,10 @@ int pmf_set_loss_grad_kernel(pmf_handle h, int32_t kernel, int32_t precision);
  * mean / min duration in milliseconds. */
 int pmf_set_profiling(pmf_handle h, int32_t enable);
 int pmf_get_profile(pmf_handle h, int32_t* n_launches, float* mean_ms, float* min_ms);
+/* With PMF_GUARD=1 in the environment (read at the first allocation) every device buffer of the library carries a
+ * 1 KiB guard zone on each side; this verifies them all: number of live buffers and of corrupted guard bytes.
+ * Returns PMF_ERR_STATE when guards are not enabled. */
+int pmf_check_guards(int64_t* n_buffers, int64_t* n_corrupt_bytes);
 
 #ifdef __cplusplus
 }

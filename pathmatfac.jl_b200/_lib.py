@@ -91,6 +91,7 @@ SIGNATURES = {
     "pmf_get_batch_grads": (C.c_int, [H, C.c_int32, c_float_p, c_float_p]),
     "pmf_get_threshold_grads": (C.c_int, [H, C.c_int32, c_float_p]),
     "pmf_get_thresholds": (C.c_int, [H, C.c_int32, c_float_p]),
+    "pmf_check_guards": (C.c_int, [C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "pmf_default_fit_opts": (None, [C.POINTER(pmf_fit_opts)]),
     "pmf_fit": (C.c_int, [H, C.POINTER(pmf_fit_opts), C.POINTER(pmf_history)]),
     "pmf_epoch_begin": (C.c_int, [H, C.POINTER(pmf_fit_opts)]),

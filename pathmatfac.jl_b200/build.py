@@ -5,7 +5,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["pmf_abi.cu", "fused_ffma.cu", "reg_update.cu", "fsard.cu", "fused_tc.cu", "wide_tc.cu"]
+SOURCES = ["pmf_abi.cu", "fused_ffma.cu", "reg_update.cu", "fsard.cu", "fused_tc.cu", "wide_tc.cu", "guard.cu"]
 OUT = os.path.join(HERE, "libpmf.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-ldl",
               "-Xcompiler", "-fPIC", "-shared"]

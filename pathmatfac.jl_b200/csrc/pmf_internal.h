@@ -5,6 +5,12 @@
 
 namespace pmf {
 
+// guard.cu: every device allocation of the library goes through these (guard zones when PMF_GUARD=1, else plain
+// cudaMalloc / cudaFree).  The macros below route the remaining direct calls of the translation units that include
+// this header.
+cudaError_t guarded_malloc(void** p, size_t bytes);
+cudaError_t guarded_free(void* p);
+
 // Number of double scalars in the shared scalar buffer.
 enum { SC_DATA = 0, SC_XREG = 1, SC_YREG = 2, SC_LAYERREG = 3, SC_COUNT = 8 };
 
@@ -229,3 +235,8 @@ cudaError_t launch_control(FitControl* ctrl, const double* scalars, double* hist
 cudaError_t launch_network_reg(const NetworkParams& p, cudaStream_t s, int n_sms, int nv_max);
 
 }  // namespace pmf
+
+#ifndef PMF_NO_GUARD_MACROS
+#define cudaMalloc(p, n) ::pmf::guarded_malloc(reinterpret_cast<void**>(p), (n))
+#define cudaFree(p) ::pmf::guarded_free((void*)(p))
+#endif

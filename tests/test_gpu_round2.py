@@ -264,3 +264,18 @@ def test_network_regulariser_at_a_3000_feature_cut():
     assert relerr(got["dY"], ref["dY"]) < TOL
     assert abs(again["components"]["Y_reg"] - got["components"]["Y_reg"]) <= 1e-5 * abs(got["components"]["Y_reg"])
     assert relerr(again["dY"], got["dY"]) < 1e-5
+
+
+def test_guard_zones_stay_intact():
+    """Own memcheck (compute-sanitizer is closed on this pool): with PMF_GUARD=1 every device buffer of the library has
+    1 KiB guard zones; after loss / gradient passes of every kernel family at ragged shapes, statistics passes and fit
+    epochs no guard byte may have changed (scripts/sanitize_case.py)."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PMF_GUARD="1")
+    r = subprocess.run([sys.executable, os.path.join(root, "scripts", "sanitize_case.py")], env=env, capture_output=True,
+                       text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    lines = [l for l in r.stdout.splitlines() if "guards" in l]
+    assert len(lines) == 5 and all("corrupt bytes 0" in l for l in lines), r.stdout
+    assert all(" buffers, " in l and int(l.split("guards ")[1].split(" buffers")[0]) > 20 for l in lines)
