@@ -19,6 +19,7 @@ import sys
 import threading
 import time
 
+os.environ.setdefault("NCCL_DEBUG", "WARN")     # rank 0 prints ONE JSON line: keep NCCL's version banner off stdout
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
@@ -142,7 +143,7 @@ class ClockSampler(threading.Thread):
                     self._sample_smi()
             except Exception:
                 pass
-            time.sleep(0.002 if self.nv is not None else 0.1)
+            time.sleep(0.0004 if self.nv is not None else 0.1)
 
     def summary(self):
         self.stop_flag = True
@@ -187,6 +188,15 @@ def cpu_iterations(model, sample_rows, steps, warmup):
     return sum(ts) / len(ts)
 
 
+CPU_BLOCK = 2000        # samples of the bounded CPU sample: ~1.4 s per oracle iteration at N = 30 000, K = 64
+
+
+def cpu_block(M, n_iters):
+    """Samples per CPU iteration so that `n_iters` iterations stay near 30-40 s of CPU work."""
+    ms = CPU_BLOCK if n_iters <= 25 else max(250, int(CPU_BLOCK * 25 / n_iters))
+    return min(M, ms)
+
+
 def workload_name(M, N, K):
     return (f"C2 (BASELINE configs[1]): {M}x{N} K={K}, bernoulli/normal/normal/poisson views, "
             f"{int(C2['missing'] * 100)}% missing, L2 on X, per-view L2 on Y, column-layer regs")
@@ -201,11 +211,12 @@ def run_reference(args):
         return
     from pathmatfac_b200.simulate import C2_BLOCKS, scale_blocks, simulate_problem
     cores = os.cpu_count() or 1
-    Ms = min(args.M, 500)
+    # the same steps / warm-up as the repo arm; every step is one full oracle iteration (loss, all gradients, penalties,
+    # AdaGrad) on a bounded block of the workload's samples x ALL its features, the time scaled to the full sample count
+    steps, warm = max(1, args.steps), max(0, args.warmup)
+    Ms = cpu_block(args.M, steps + warm)
     model = simulate_problem(Ms, blocks=scale_blocks(C2_BLOCKS, args.N), K=args.K, seed=2, missing=C2["missing"],
                              model_kwargs=dict(lambda_X_l2=1.0))
-    steps = max(1, min(args.steps, 5))
-    warm = max(1, min(args.warmup, 1))
     sec = cpu_iterations(model, range(0, Ms), steps, warm)
     scale = args.M / Ms
     value = 1.0 / (sec * scale)
@@ -217,8 +228,8 @@ def run_reference(args):
                        "value_definition": "C2-equivalent iterations/sec",
                        "note": "Julia/MatFac.jl unavailable: CPU restatement of the reference algorithm (oracle)"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{Ms} of {args.M} samples x all {args.N} features, {steps} timed iterations, "
-                                       f"time scaled x{scale:.0f}"},
+                             "sample": f"{Ms} of {args.M} samples x all {args.N} features per step, {steps} timed + {warm} warm-up "
+                                       f"iterations ({sec * (steps + warm):.0f} s of CPU work), time per step scaled x{scale:g}"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -364,11 +375,11 @@ def main():
     e2e = e2e_sharded
     eng.close()
     if not args.no_e2e and world == 1:
-        # two identical calls, the faster one is reported: the first one on a fresh process also pays one-time
-        # driver costs (first large cudaMalloc / cudaFree of the 1.2 GB data buffer) that vary by a factor of
-        # ten between boxes and are not part of the path
-        dt, he, dts = None, None, []
-        for _ in range(2):
+        # three identical calls, the MEDIAN is reported (every call's time is listed): the first call of a fresh process
+        # also pays one-time driver costs (first cudaMalloc / cudaFree of the 1.2 GB data buffer) that vary by a factor of
+        # ten between boxes
+        runs = []
+        for _ in range(3):
             model.matfac.X[...] = X0
             model.matfac.Y[...] = Y0
             torch.cuda.synchronize()
@@ -377,27 +388,28 @@ def main():
                              kernel=kernel, precision=args.precision, rel_tol=-1.0, abs_tol=-1.0, verbosity=0, device=local,
                              check_every=1 << 20)
             torch.cuda.synchronize()
-            dt_try = time.perf_counter() - t0
-            dts.append(dt_try)
-            if dt is None or dt_try < dt:
-                dt, he = dt_try, h_try
+            runs.append((time.perf_counter() - t0, h_try))
+        dts = [r[0] for r in runs]
+        dt, he = sorted(runs, key=lambda r: r[0])[1]
         e2e = {"value": he["epochs"] / dt, "unit": UNIT,
                "h2d_bytes_per_step": he["h2d_bytes"] / max(he["epochs"], 1),
                "d2h_bytes_per_step": he["d2h_bytes"] / max(he["epochs"], 1),
                "call": f"mf_fit(model; max_epochs={args.steps}) on a host-resident model: create handle, H2D of "
                        f"data (pinned) + parameters, {he['epochs']} epochs, D2H of parameters + history; "
-                       f"faster of two identical calls",
+                       f"median of three identical calls",
                "epochs_run": he["epochs"], "seconds": dt, "seconds_each_call": dts}
 
     # ---- CPU baseline beside it (bounded sample, rank 0) -----------------------------------------------
     cpu = None
     if not args.no_cpu:
-        Ms = 250
-        sec = cpu_iterations(model, range(0, Ms), 2, 1)
+        n_it, n_warm = 8, 1
+        Ms = cpu_block(M, n_it + n_warm)
+        sec = cpu_iterations(model, range(0, Ms), n_it, n_warm)
         scale = M / Ms
         cpu = {"value": 1.0 / (sec * scale), "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-               "sample": f"first {Ms} of {M} samples x all {N} features, 2 timed iterations of the NumPy restatement "
-                         f"(float32, BLAS threads = all cores), time scaled x{scale:.0f}"}
+               "sample": f"first {Ms} of {M} samples x all {N} features, {n_it} timed + {n_warm} warm-up iterations of the NumPy "
+                         f"restatement ({sec * (n_it + n_warm):.0f} s of CPU work; float32, BLAS threads = all cores), time per "
+                         f"step scaled x{scale:g}"}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": sec_per_step * 1e3, "higher_is_better": True, "scaling": "weak",

@@ -471,9 +471,13 @@ class Engine:
 
 # ---- device placement (the reference's gpu(model) / cpu(model)) -----------------------------------
 
-def gpu(model, device: int = 0):
+def gpu(model, device: Optional[int] = None):
+    """``gpu(model)``.  The device ordinal is remembered on the model (``model._device``): the transient handles of the
+    staging passes (statistics, M-estimates, EM) are created on the same GPU."""
+    if device is not None:
+        model._device = int(device)
     if model._engine is None:
-        model._engine = Engine(model, device=device)
+        model._engine = Engine(model, device=getattr(model, "_device", 0))
     return model
 
 
@@ -522,7 +526,7 @@ def _with_zero_factors(model, fn):
     """Run ``fn(engine)`` with X and Y temporarily set to zero on the device, as init_logsigma! /
     reweight_col_losses! do (src/fit.jl:133-136,160-163); the host model is not touched."""
     transient = model._engine is None
-    eng = Engine(model) if transient else model._engine
+    eng = Engine(model, device=getattr(model, "_device", 0)) if transient else model._engine
     try:
         if not transient:
             eng.push_structure()
@@ -540,14 +544,14 @@ def _with_zero_factors(model, fn):
             eng.close()
 
 
-def compute_M_estimates(model, lr=0.1, max_epochs=500, rel_tol=1e-5, abs_tol=1e-3, device=0):
+def compute_M_estimates(model, lr=0.1, max_epochs=500, rel_tol=1e-5, abs_tol=1e-3, device=None):
     """``MF.compute_M_estimates`` as ``init_mu!`` calls it (src/fit.jl:88-92): per column, the shift that
     minimises the column's noise-model loss.  It is the fit loop on a model reduced to its ColShift layer:
     X = Y = 0, sigma = 1, batch parameters zero, every other layer and every penalty frozen, mu started at 0
     -- the same fused data pass, 2 bytes of parameter traffic per column.  Returns (M_estimates, history);
     the host model is not touched."""
     transient = model._engine is None
-    eng = Engine(model, device=device) if transient else model._engine
+    eng = Engine(model, device=device if device is not None else getattr(model, "_device", 0)) if transient else model._engine
     try:
         if not transient:
             eng.push_structure()
@@ -649,7 +653,7 @@ def theta_delta_em(model, delta2, sigma2, update_priors=True, batch_em_max_iter=
     delta2 = [np.asarray(d, dtype=f32).copy() for d in delta2]
     theta_lsq = [v.astype(f32).copy() for v in theta.values]
     transient = model._engine is None
-    eng = Engine(model) if transient else model._engine
+    eng = Engine(model, device=getattr(model, "_device", 0)) if transient else model._engine
     diffs = []
     try:
         if not transient:
@@ -694,7 +698,7 @@ def mf_fit(model, *, scale_column_losses=False, update_X=False, update_Y=False, 
            update_X_reg=False, update_Y_reg=False, update_row_layers_reg=False, update_col_layers_reg=False,
            keep_history=True, opt: Optional[AdaGrad] = None, lr=1.0, max_epochs=1000, epoch=1,
            rel_tol=1e-5, abs_tol=1e-5, capacity=None, verbosity=1, print_prefix="", print_iter=10,
-           kernel=KERNEL_AUTO, precision=0, check_every=8, device=0, alternating=False, **kwargs) -> Dict:
+           kernel=KERNEL_AUTO, precision=0, check_every=8, device=None, alternating=False, **kwargs) -> Dict:
     """``mf_fit!`` (src/fit.jl:9-38): one ``MF.fit!`` call on the model.
 
     Same keyword surface and defaults.  ``capacity`` is accepted and ignored (the fused pass
@@ -706,7 +710,7 @@ def mf_fit(model, *, scale_column_losses=False, update_X=False, update_Y=False, 
     if scale_column_losses:
         raise NotImplementedError("scale_column_losses=true is never used by the reference (src/fit.jl:9)")
     transient = model._engine is None
-    eng = Engine(model, device=device) if transient else model._engine
+    eng = Engine(model, device=device if device is not None else getattr(model, "_device", 0)) if transient else model._engine
     try:
         if not transient:
             eng.push_regs()      # stages swap regularisers / freeze layers between calls
@@ -745,7 +749,7 @@ def mf_fit_adapt_lr(model, *, lr=1.0, min_lr=0.001, max_epochs=1000, history=Non
     (AdaGrad state kept) and resume at h["epochs"]; stop below ``min_lr``."""
     made_resident = model._engine is None
     if made_resident:
-        gpu(model, device=kwargs.get("device", 0))
+        gpu(model, device=kwargs.get("device"))
     try:
         opt = AdaGrad(lr)
         epoch = 1

@@ -116,3 +116,124 @@ def simulate_problem(M: int, blocks=C2_BLOCKS, K: int = 64, seed: int = 2, missi
             mf.col_transform.layers[1].logdelta.values[i][...] = gen_batch[v][0] * f32(0.5)
             mf.col_transform.layers[3].theta.values[i][...] = gen_batch[v][1] * f32(0.5)
     return model
+
+
+# ---- factor simulators of the ARD priors (src/simulate_params.jl:14-79) -------------------------------------------
+
+def simulate_factor_ard(K: int, N: int, rng, ard_alpha=1.01, ard_beta=0.01) -> np.ndarray:
+    """simulate_params!(X, ::ARDRegularizer) (src/simulate_params.jl:14-21): tau ~ Gamma(shape alpha, scale 1/beta) per
+    entry, X = randn / sqrt(tau)."""
+    tau = rng.gamma(shape=ard_alpha, scale=1.0 / ard_beta, size=(K, N))
+    return (rng.standard_normal((K, N)) / np.sqrt(tau)).astype(np.float32)
+
+
+def corrupt_S(S, S_add_corruption: float, S_rem_corruption: float, rng) -> np.ndarray:
+    """corrupt_S (src/simulate_params.jl:24-43): per feature set remove round(rem * |set|) members, add
+    round(add * |set|) non-members, renormalise the row to 1 / sqrt(|corrupted set|).  Dense L x N float32 result."""
+    S_new = np.asarray(S.todense() if hasattr(S, "todense") else S, dtype=np.float32).copy()
+    L, N = S_new.shape
+    for l in range(L):
+        cur = np.flatnonzero(S_new[l] != 0)
+        comp = np.flatnonzero(S_new[l] == 0)
+        rm_n = int(round(S_rem_corruption * len(cur)))
+        add_n = int(round(len(cur) * S_add_corruption))
+        to_remove = rng.choice(cur, size=rm_n, replace=False) if rm_n else np.zeros(0, np.int64)
+        to_add = rng.choice(comp, size=min(add_n, len(comp)), replace=False) if add_n else np.zeros(0, np.int64)
+        corrupted = np.union1d(np.setdiff1d(cur, to_remove), to_add)
+        S_new[l, :] = 0
+        if len(corrupted):
+            S_new[l, corrupted] = 1.0 / np.sqrt(len(corrupted))
+    return S_new
+
+
+def simulate_factor_fsard(Y: np.ndarray, reg, rng, ard_alpha=1.01, beta0=0.001, S_add_corruption=0.1,
+                          S_rem_corruption=0.1) -> None:
+    """simulate_params!(Y, ::FeatureSetARDReg) (src/simulate_params.jl:45-79), in place on Y (K x N) and on the
+    regulariser's A / S: per view one random feature set per factor (A[l, k] = |5 randn|), the sets corrupted, Y small
+    (randn / sqrt(tau), tau ~ Gamma(alpha, 1 / beta0)) outside the assigned sets and +-1 inside them."""
+    import scipy.sparse as sp
+    for v, (cr, A, S) in enumerate(zip(reg.col_ranges, reg.A, reg.S)):
+        Yv = Y[:, cr.start:cr.stop]
+        K, N = Yv.shape
+        L = S.shape[0]
+        A[...] = 0
+        for k in range(K):
+            A[int(rng.integers(0, L)), k] = abs(rng.standard_normal() * 5.0)
+        S_new = corrupt_S(S, S_add_corruption, S_rem_corruption, rng)
+        reg.S[v] = sp.csr_matrix(S_new, dtype=np.float32)
+        tau = rng.gamma(shape=ard_alpha, scale=1.0 / beta0, size=(K, N))
+        beta = A.T @ S_new
+        Yv[...] = (rng.standard_normal((K, N)) / np.sqrt(tau)) * (beta == 0)
+        Yv += (beta > 0) * rng.choice([-1.0, 1.0], size=(K, N))
+
+
+def add_missingness(data: np.ndarray, view_cols: Dict[str, slice], batch_of_sample: Dict[str, Sequence], rng,
+                    missingness=0.1) -> None:
+    """add_missingness! of the study's simulator (analyses/scripts/julia/simulate_matfac.jl:106-130): per batched view
+    whole rows go missing, batch by batch in random batch order, until round(M * missingness) rows are gone (the last
+    batch touched loses a random subset of its rows).  ``data`` is modified in place (NaN = missing)."""
+    M = data.shape[0]
+    for view, cols in view_cols.items():
+        if view not in batch_of_sample:
+            continue
+        b = np.asarray(batch_of_sample[view])
+        to_remove = int(round(M * missingness))
+        unq = list(dict.fromkeys(b.tolist()))
+        for ub in [unq[i] for i in rng.permutation(len(unq))]:
+            rows = np.flatnonzero(b == ub)
+            n_rem = min(len(rows), to_remove)
+            if n_rem < len(rows):
+                rows = rng.choice(rows, size=n_rem, replace=False)
+            data[rows, cols] = np.nan
+            to_remove -= n_rem
+
+
+# ---- flat binary export: the same bytes for a Julia run of the reference (SURVEY.md 8d) --------------------------------
+
+def export_problem(model, directory: str) -> str:
+    """Write the inputs of a fit as raw little-endian arrays plus a text manifest (one line per array: name, element
+    type, rows, cols; Julia column-major order, so ``read!(io, Matrix{T}(undef, rows, cols))`` restores each one).
+    ``julia/load_exported_problem.jl`` rebuilds the PathMatFacModel from it.  Returns the manifest path."""
+    import os
+    os.makedirs(directory, exist_ok=True)
+    mf = model.matfac
+    ct = mf.col_transform
+    arrays = {"data": np.asarray(model.data, np.float32), "X": np.asarray(mf.X, np.float32), "Y": np.asarray(mf.Y, np.float32),
+              "logsigma": np.asarray(ct.unwrapped(0).logsigma, np.float32)[:, None],
+              "mu": np.asarray(ct.unwrapped(2).mu, np.float32)[:, None],
+              "col_weights": mf.noise_model.weights()[:, None]}
+    from .layers import BatchShift
+    l4 = ct.unwrapped(3)
+    if isinstance(l4, BatchShift):
+        ld, th = ct.unwrapped(1).logdelta, l4.theta
+        for v, name in enumerate(th.col_range_ids):
+            arrays[f"batch_of_sample__{name}"] = (np.asarray(th.batch_index[v], np.int32) + 1)[:, None]    # 1-based for Julia
+            arrays[f"theta__{name}"] = np.asarray(th.values[v], np.float32)
+            arrays[f"logdelta__{name}"] = np.asarray(ld.values[v], np.float32)
+    lines = []
+    for name, a in arrays.items():
+        a = np.asfortranarray(a)
+        with open(os.path.join(directory, name + ".bin"), "wb") as f:
+            f.write(a.tobytes(order="F"))
+        lines.append(f"{name} {'Float32' if a.dtype == np.float32 else 'Int32'} {a.shape[0]} {a.shape[1]}")
+    with open(os.path.join(directory, "feature_views.txt"), "w") as f:
+        f.write("\n".join(str(v) for v in model.feature_views) + "\n")
+    with open(os.path.join(directory, "feature_distributions.txt"), "w") as f:
+        f.write("\n".join(str(d) for d in model.feature_distributions) + "\n")
+    with open(os.path.join(directory, "sample_conditions.txt"), "w") as f:
+        f.write("\n".join(str(c) for c in (model.sample_conditions if model.sample_conditions is not None else [])) + "\n")
+    manifest = os.path.join(directory, "manifest.txt")
+    with open(manifest, "w") as f:
+        f.write("\n".join(lines) + "\n")
+    return manifest
+
+
+def import_problem_arrays(directory: str) -> Dict[str, np.ndarray]:
+    """Read back what export_problem wrote (round-trip check of the format)."""
+    import os
+    out = {}
+    for line in open(os.path.join(directory, "manifest.txt")):
+        name, ty, r, c = line.split()
+        dt = np.float32 if ty == "Float32" else np.int32
+        out[name] = np.fromfile(os.path.join(directory, name + ".bin"), dtype=dt).reshape((int(r), int(c)), order="F")
+    return out

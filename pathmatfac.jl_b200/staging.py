@@ -34,7 +34,7 @@ def _device_link_col_sqerr(model):
         model._engine.push_structure()
         model._engine.push_params()
         return model._engine.link_col_sqerr()
-    eng = _fit.Engine(model)
+    eng = _fit.Engine(model, device=getattr(model, "_device", 0))
     try:
         return eng.link_col_sqerr()
     finally:
@@ -47,7 +47,7 @@ def _device_batch_stats(model):
         model._engine.push_structure()
         model._engine.push_params()
         return model._engine.batch_stats()
-    eng = _fit.Engine(model)
+    eng = _fit.Engine(model, device=getattr(model, "_device", 0))
     try:
         return eng.batch_stats()
     finally:

@@ -618,8 +618,6 @@ def test_theta_delta_em():
     assert abs(diffs[-1] - diffs_ref[-1]) <= 1e-2 * abs(diffs_ref[-1]) + 1e-9
 
 
-@pytest.mark.skipif(os.environ.get("PMF_TEST_STAGING", "0") in ("", "0"),
-                    reason="the stage functions have only run on the CPU so far (tests/test_staging_cpu.py); opt in with PMF_TEST_STAGING=1")
 def test_staging_fit_on_device():
     """fit! (staging.py) end to end on the device backend: same orchestration as tests/test_staging_cpu.py, the calls
     served by libpmf.  Checks the post-conditions of the procedure and that the fitted model explains the data about as

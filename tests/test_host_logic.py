@@ -409,3 +409,57 @@ def test_closure_regularisers_are_recognised_or_refused():
     for bad in (lambda X: np.sum(np.abs(X)), lambda X: 0.5 * np.sum(X * X) + 1.0, lambda X: np.sum(X ** 4), lambda X: X[99, 0]):
         with pytest.raises(_lib.PmfError):
             recognise_closure(bad, 5)
+
+
+def test_ard_and_fsard_factor_simulators():
+    """src/simulate_params.jl:14-79: ARD factors are randn / sqrt(tau) with tau ~ Gamma(alpha, 1/beta); the FSARD
+    simulator assigns one feature set per factor, corrupts the sets and sets the members to +-1."""
+    from pathmatfac_b200 import simulate as S
+    from pathmatfac_b200.regularizers import construct_featureset_ard
+    rng = np.random.default_rng(0)
+    X = S.simulate_factor_ard(6, 4000, rng, ard_alpha=3.0, ard_beta=2.0)
+    # E[1/tau] = beta / (alpha - 1) for tau ~ Gamma(shape alpha, rate beta)
+    assert X.shape == (6, 4000) and abs(X.var() - 2.0 / (3.0 - 1.0)) < 0.1
+    N, K = 60, 4
+    feature_ids = list(range(1, N + 1))
+    sets = {"mrnaseq": [list(range(1, 21)), list(range(15, 41)), list(range(30, 61))]}
+    reg = construct_featureset_ard(K, feature_ids, ["mrnaseq"] * N, sets)
+    S0 = np.asarray(reg.S[0].todense())
+    assert np.allclose((S0 != 0).sum(1), [20, 26, 31]) and np.allclose((S0 ** 2).sum(1), 1.0, atol=1e-6)
+    Y = np.zeros((K, N), np.float32)
+    S.simulate_factor_fsard(Y, reg, rng)
+    A, S1 = reg.A[0], np.asarray(reg.S[0].todense())
+    assert ((A != 0).sum(0) == 1).all()                               # one set per factor
+    assert np.allclose((S1 ** 2).sum(1), 1.0, atol=1e-5)              # corrupted rows renormalised
+    sizes = (S1 != 0).sum(1)
+    assert all(abs(int(s) - n) <= 1 for s, n in zip(sizes, [20, 26, 31]))   # -10% +10% of the set size
+    inside = (A.T @ S1) > 0
+    assert np.all(np.abs(np.abs(Y[inside]) - 1.0) < 1e-6) and np.median(np.abs(Y[~inside])) < 0.1   # Gamma(1.01, 1/beta0): heavy tail
+
+
+def test_row_block_missingness_and_binary_export(tmp_path):
+    """analyses/scripts/julia/simulate_matfac.jl:106-130 (whole rows of a view go missing, batch by batch) and the
+    flat-binary export a Julia run of the reference can load (julia/load_exported_problem.jl): exact round trip."""
+    from pathmatfac_b200 import simulate as S
+    blocks = (("methylation", "normal", 30), ("mrnaseq", "normal", 20))
+    model = S.simulate_problem(80, blocks=blocks, K=3, seed=9, missing=0.0, batch_views=["methylation", "mrnaseq"], n_batches=4)
+    rng = np.random.default_rng(1)
+    cols = {"methylation": slice(0, 30), "mrnaseq": slice(30, 50)}
+    bos = {v: model.matfac.col_transform.unwrapped(3).theta.batch_index[i] for i, v in enumerate(["methylation", "mrnaseq"])}
+    S.add_missingness(model.data, cols, bos, rng, missingness=0.25)
+    for v, sl in cols.items():
+        miss = np.isnan(model.data[:, sl])
+        assert np.all(miss.all(axis=1) | (~miss).all(axis=1))          # rows of a view are missing as a whole
+        assert miss.all(axis=1).sum() == 20                            # round(M * missingness)
+        # whole batches first: at most one batch is partially removed
+        b = np.asarray(bos[v])
+        partial = [u for u in np.unique(b) if 0 < miss.all(axis=1)[b == u].sum() < (b == u).sum()]
+        assert len(partial) <= 1
+    man = S.export_problem(model, str(tmp_path / "exp"))
+    back = S.import_problem_arrays(str(tmp_path / "exp"))
+    assert np.array_equal(back["data"], model.data, equal_nan=True)
+    assert np.array_equal(back["X"], model.matfac.X) and np.array_equal(back["Y"], model.matfac.Y)
+    assert np.array_equal(back["theta__mrnaseq"], model.matfac.col_transform.unwrapped(3).theta.values[1])
+    assert np.array_equal(back["batch_of_sample__methylation"][:, 0] - 1, bos["methylation"])
+    assert open(tmp_path / "exp" / "feature_views.txt").read().split() == list(model.feature_views)
+    assert os.path.getsize(tmp_path / "exp" / "data.bin") == 80 * 50 * 4 and os.path.exists(man)
