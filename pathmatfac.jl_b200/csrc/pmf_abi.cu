@@ -1450,9 +1450,15 @@ int pmf_model_s::run_data_pass(DataPassParams& p, int kind, int precision) {
     if (kind == PMF_KERNEL_TC && !tc_ok && !wide_ok)
         return fail(this, PMF_ERR_ARG, "tcgen05 data pass needs an sm_100 device and 8 <= K <= 64 (at most 65533 batches per "
                                        "view) or 64 < K <= 256 without batch layers");
-    // AUTO: the tcgen05 path pays off (and its single-pass TF32 gradient contractions average below
-    // the 1e-4 parity bar) on large problems; small ones run the exact-FP32 FFMA kernel.
-    const bool big = (double)M * (double)N >= 4.0e6 && M >= 1024;
+    // AUTO: the tensor-core kernels take a problem when it is large enough for their single-pass TF32 gradient
+    // contractions to stay below the 1e-4 parity bar; smaller ones run the exact-FP32 kernel.  Measured against the
+    // FP32 kernel (scripts/tc_precision_vs_size.py, profiles/r2_tc_precision_vs_size.jsonl; freshly initialised
+    // model): K = 64: 8.8e-5 at 2 000 x 3 000, 6e-5 at 4 000 x 6 000, 3-4e-5 at 10 000 x 30 000; K = 128: 1.2e-4 at
+    // 2 000 x 3 000, 8.8e-5 at 4 000 x 6 000; K = 256: 1.2e-4 at 4 000 x 6 000, 6-8e-5 at 10 000 x 30 000 -- the error
+    // goes with K / sqrt(M N), hence the K^2 in the size rule.  (Near a fitted model the gradients shrink and the
+    // rounding noise does not: 5-7e-5 at the C2 shape after 30 epochs.)
+    const double kscale = std::max(1.0, Kp / 64.0);
+    const bool big = (double)M * (double)N >= 6.0e6 * kscale * kscale && std::min(M, N) >= 2000;
     if (wide_ok && (kind == PMF_KERNEL_TC || (kind == PMF_KERNEL_AUTO && auto_tc && big))) {
         if (!wide.G) {
             const size_t nx = wide_scratch_floats(Mp, Kp), ny = wide_scratch_floats(Np, Kp);

@@ -230,7 +230,10 @@ def test_abi_error_paths():
 # Z is contracted in 3xTF32 (FP32-equivalent: loss and column gradients match to ~1e-6); dX / dY use a
 # single TF32 pass with round-to-nearest operands, whose rounding noise averages out with the number
 # of terms: ~2e-4 at a few hundred samples, ~1e-4 at 1000, 3-4e-5 at the 10k x 30k benchmark shape.
-# PMF_KERNEL_AUTO therefore only selects this path for large problems (M >= 1024, M*N >= 4e6).
+# PMF_KERNEL_AUTO therefore only selects this path where the measured error is below 1e-4
+# (M*N >= 6e6 (K/64)^2, min(M, N) >= 2000; profiles/r2_tc_precision_vs_size.jsonl,
+# tests/test_gpu_round2.py::test_auto_eligible_sizes_meet_the_gradient_tolerance); the tests below request
+# the kernel explicitly at smaller, cheaper-to-check sizes and allow for the larger noise there.
 
 def _tc_views(n):
     return {"mutation": ("bernoulli", n // 6), "methylation": ("normal", n // 3), "mrnaseq": ("normal", n // 3),
@@ -275,11 +278,11 @@ def test_tc_ragged_edges_and_all_missing():
 
 
 def test_tc_fit_curve_auto_kernel():
-    model, om, D = make_pair(1300, _tc_views(3200), K=64, seed=33, missing=0.3, lambda_X_l2=1.0)
+    model, om, D = make_pair(2100, _tc_views(3000), K=64, seed=33, missing=0.3, lambda_X_l2=1.0)
     href = O.mf_fit(om, D, O.AdaGrad(0.1), max_epochs=8, update_X=True, update_Y=True, update_col_layers=True,
                     rel_tol=0, abs_tol=0)
     h = P.mf_fit(model, lr=0.1, max_epochs=8, update_X=True, update_Y=True, update_col_layers=True, rel_tol=0,
-                 abs_tol=0, verbosity=0)          # AUTO -> tcgen05 path (M >= 1024, M*N >= 4e6, K = 64)
+                 abs_tol=0, verbosity=0)          # AUTO -> tcgen05 path (min(M, N) >= 2000, M*N >= 6e6, K = 64)
     assert h["epochs"] == href["epochs"] and h["term_code"] == href["term_code"]
     assert np.max(np.abs(np.array(h["loss"]) / np.array(href["loss"]) - 1)) < 1e-4
     assert relerr(model.matfac.Y, om.Y) < 1e-3 and relerr(model.matfac.X, om.X) < 1e-3

@@ -279,3 +279,62 @@ def test_guard_zones_stay_intact():
     lines = [l for l in r.stdout.splitlines() if "guards" in l]
     assert len(lines) == 5 and all("corrupt bytes 0" in l for l in lines), r.stdout
     assert all(" buffers, " in l and int(l.split("guards ")[1].split(" buffers")[0]) > 20 for l in lines)
+
+
+def test_c3_full_size_five_batched_views_tc_against_fp32_kernel():
+    """BASELINE configs[2] at full size: 10 000 x 30 000, K = 64, FIVE batched assays x 40 batches (batch ids iid per
+    sample and view: five sample orders, ten passes' worth of A_tc), 20 sample conditions.  The tcgen05 batch path
+    against the FP32 kernel on the same handle: batch gradients and column gradients to 1e-4, loss to 1e-6."""
+    from pathmatfac_b200.simulate import simulate_problem
+    blocks = (("mutation", "bernoulli", 5000), ("cna", "normal", 5000), ("methylation", "normal", 7500),
+              ("mrnaseq", "normal", 7500), ("counts", "poisson", 5000))
+    model = simulate_problem(10000, blocks=blocks, K=64, seed=3, missing=0.3, batch_views=[b[0] for b in blocks], n_batches=40,
+                             n_conditions=20)
+    eng = P.Engine(model)
+    try:
+        eng.set_loss_grad_kernel(_lib.KERNEL_FFMA, 0)
+        ref = eng.loss_grad(include_reg=True)
+        eng.set_loss_grad_kernel(_lib.KERNEL_TC, 0)
+        got = eng.loss_grad(include_reg=True)
+    finally:
+        eng.close()
+    assert len(got["dtheta"]) == 5
+    assert abs(got["loss"] - ref["loss"]) <= 1e-6 * abs(ref["loss"])
+    for v in range(5):
+        assert relerr(got["dtheta"][v], ref["dtheta"][v]) < TOL, (v, relerr(got["dtheta"][v], ref["dtheta"][v]))
+        assert relerr(got["dlogdelta"][v], ref["dlogdelta"][v]) < TOL, (v, relerr(got["dlogdelta"][v], ref["dlogdelta"][v]))
+    assert relerr(got["dmu"], ref["dmu"]) < TOL and relerr(got["dlogsigma"], ref["dlogsigma"]) < TOL
+    assert relerr(got["dY"], ref["dY"]) < TOL and relerr(got["dX"], ref["dX"]) < TOL
+
+
+@pytest.mark.parametrize("M,N,K", [(2000, 3000, 64), (4000, 6000, 128)])
+def test_auto_eligible_sizes_meet_the_gradient_tolerance(M, N, K):
+    """north_star: loss and gradients within 1e-4 of the reference's FP32 fit.  At the smallest sizes PMF_KERNEL_AUTO
+    hands to the tensor-core kernels (M N >= 6e6 (K/64)^2, min(M, N) >= 2000) every gradient is within 1e-4 of the
+    ORACLE; one notch below the threshold AUTO stays on the FP32 kernel."""
+    nb, nn = N // 6, N // 3
+    views = {"mutation": ("bernoulli", nb), "methylation": ("normal", nn), "mrnaseq": ("normal", nn), "counts": ("poisson", N - nb - 2 * nn)}
+    model, om, D = make_pair(M, views, K=K, seed=440 + K, missing=0.3, lambda_X_l2=1.0)
+    eng = P.Engine(model)
+    try:
+        eng.set_loss_grad_kernel(_lib.KERNEL_AUTO, 0)
+        got = eng.loss_grad(include_reg=True)
+        eng.set_loss_grad_kernel(_lib.KERNEL_FFMA, 0)
+        ffma = eng.loss_grad(include_reg=True)
+    finally:
+        eng.close()
+    ref = O.total_loss_grads(om, D)
+    assert abs(got["loss"] - ref["loss"]) <= 1e-5 * abs(ref["loss"])
+    for k in ("dX", "dY", "dmu", "dlogsigma"):
+        assert relerr(got[k], ref[k]) < TOL, (k, relerr(got[k], ref[k]))
+    assert relerr(got["dY"], ffma["dY"]) > 1e-5          # AUTO did run the TF32 contractions here ...
+    small, _, _ = make_pair(1990, views, K=K, seed=441 + K, missing=0.3, lambda_X_l2=1.0)
+    eng = P.Engine(small)
+    try:
+        eng.set_loss_grad_kernel(_lib.KERNEL_AUTO, 0)
+        a = eng.loss_grad(include_reg=False)
+        eng.set_loss_grad_kernel(_lib.KERNEL_FFMA, 0)
+        b = eng.loss_grad(include_reg=False)
+    finally:
+        eng.close()
+    assert relerr(a["dY"], b["dY"]) < 2e-6               # ... and the FP32 kernel below the threshold
