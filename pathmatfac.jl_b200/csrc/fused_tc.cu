@@ -4,9 +4,10 @@
 // (ItemIter); the maximal runs inside one feature tile are the ITEMS for which the Y operands and the dY
 // accumulator stay resident.  Per tile (32 KB of A, streamed once through a TMA-fed shared-memory ring):
 //
-//   MMA1  Z[j,i]   = sum_k Y[j,k] X[i,k]     A = Y in TMEM, B = X tile in smem (K-major).  Yh*Xh in TF32 plus the
-//                                            two first-order corrections Yl*Xh + Yh*Xl as ONE BF16 contraction over
-//                                            K' = 128 ([Yl|Yh] x [Xh|Xl]); FP32 accumulate in TMEM
+//   MMA1  Z[j,i]   = sum_k Y[j,k] X[i,k]     A = Y in TMEM, B = X tile in smem (K-major).  Two-term BF16 split of both
+//                                            operands (v = h + l, h = bf16(v), l = bf16(v - h)): Yh*Xh + Yl*Xh + Yh*Xl
+//                                            as ONE BF16 contraction over K' = 192 (12 instructions of K = 16; the
+//                                            dropped terms are 2^-17 of a product); FP32 accumulate in TMEM
 //   epilogue (2 groups of 8 warps on alternating tiles; TMEM lane = feature j, so every column parameter is
 //            a per-thread register and every column-gradient sum a private accumulator):
 //            ColScale/ColShift, noise loss, dL/dz with the NaN mask (src/layers.jl:9-90, SURVEY.md
@@ -19,20 +20,21 @@
 //   MMA3  dY[j,k] += sum_i G[j,i] X[i,k]     A = G in TMEM, B = a second copy of the Xh tile read MN-major
 //
 // Z and dL/dZ never exist in HBM.  dY stays in TMEM across the sample loop of an item; each dX tile is staged
-// in shared memory and leaves as ONE TMA reduce-add (no per-lane REDs).  Operand split: h = rna_tf32(v),
-// l = v - h (exact); the gradient contractions use h only (single-pass TF32, round-to-nearest operands);
-// precision mode 2 drops the BF16 correction of Z.
+// in shared memory by four drain warps and leaves as ONE TMA reduce-add (no per-lane REDs), two of them in
+// flight.  The gradient contractions use rna_tf32 operands (single-pass TF32); precision mode 2 keeps only the
+// leading BF16 term of Z (experiments).
 //
-// Warps: 0-15 epilogue | 16 TMA A | 17 MMA issuer (one elected thread) | 18 TMA X operands | 19 dX reduce-add issuer.
+// Warps: 0-15 epilogue | 16 TMA A | 17 MMA issuer (one elected thread) | 18 TMA X operands | 19 dX reduce-add
+// issuer | 20-23 dX drain (TMEM -> staging buffer), one per TMEM lane quarter.  24 warps start with 80 registers;
+// setmaxnreg then gives the epilogue warpgroups REGS_EPI and leaves the two small warpgroups REGS_SMALL.
 // Shared memory (every box is one 128-byte swizzle row wide):
-//   XK  2 stages x (Xh 16 KB fp32 | Xb 16 KB bf16 [Xh|Xl])   K-major operands of MMA1, 16-byte-atom swizzle
-//   XM  16 KB   Xh tile again, 32-byte-atom swizzle: MN-major operand of MMA3
+//   XK  3 stages x 16 KB   Xb tile: bf16 [Xh | Xl] of 64 samples, K-major operand of MMA1, 16-byte-atom swizzle
+//   XM  16 KB   rna_tf32(X) tile, 32-byte-atom swizzle: MN-major operand of MMA3
 //   YS  32 KB   Ys tile [128 features][64 k], 32-byte-atom swizzle, written by the epilogue warps per item
 //   AG  3 stages x 32 KB   A tile as 2 boxes (32 samples x 128 feature rows), 32-byte-atom swizzle; becomes G in place
-//   DXS 16 KB   dX tile staged for the TMA reduce-add (16-byte-atom swizzle)
-// MN-major FP32/TF32 operands exist only in the 32-byte-atom 128B swizzle (UMMA layout type 1), K-major ones
-// only in the 16-byte-atom layouts: hence the two copies of the Xh tile.
-// TMEM (512 columns): Yh 0 | [Yl|Yh] bf16 64 | Z0..Z2 128 | dY 320 | dX0 384 | dX1 448.
+//   DXS 2 x 16 KB   dX tiles staged for the TMA reduce-add (16-byte-atom swizzle)
+// MN-major FP32/TF32 operands exist only in the 32-byte-atom 128B swizzle (UMMA layout type 1).
+// TMEM (512 columns): [Yh|Yl] bf16 0 | Z0..Z3 64 | dY 320 | dX0 384 | dX1 448.
 // dX accumulators are M = 64 tiles: sample row r lives in lane (r % 16) + 32 * (r / 16).
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -53,25 +55,38 @@ constexpr int NEPI = 16;                  // epilogue warps: 2 groups x (TMEM la
 // Warp roles.  The epilogue warps come FIRST: the SM's issue arbiter favours the highest warp id on a
 // scheduler, so the four single-thread role warps sit at the top and are never starved by the 16 epilogue
 // warps they share schedulers with (a starved MMA thread idles the tensor pipe).
-constexpr int W_TMA_A = NEPI, W_MMA = NEPI + 1, W_TMA_X = NEPI + 2, W_DXRED = NEPI + 3;
+constexpr int W_TMA_A = NEPI, W_MMA = NEPI + 1, W_TMA_X = NEPI + 2, W_MMA1 = NEPI + 3;
+// Four more warps, one per TMEM lane quarter, do nothing but move finished dX tiles from TMEM into the staging
+// buffers of the TMA reduce-add: off the epilogue warps, whose per-tile cycle sets the pace of the kernel.
+constexpr int W_DRAIN0 = NEPI + 4, NDRAIN = 4;
 constexpr int NPRE = 4;
-constexpr int NTHREADS = 32 * (NPRE + NEPI);
+constexpr int NTHREADS = 32 * (NPRE + NEPI + NDRAIN);
+// 24 warps are launched with 80 registers each (65536 / 768 rounded down to the allocation unit); setmaxnreg moves
+// registers inside that allocation: 512 x REGS_EPI + 256 x REGS_SMALL <= 768 x 80.
+constexpr int REGS_EPI = 88, REGS_SMALL = 64;
 // Pipeline depths.  The X operands come from L2 and are re-loaded while the tensor pipe works on the other
 // contractions of the neighbouring tiles, so one stage each suffices; the A/G ring is the HBM stream and
 // stays occupied from the TMA issue until MMA2 has consumed G0, so it gets every byte that is left.
-constexpr int SXK = 2, SXM = 1, SA = 3;
-static_assert(SXK >= 2, "the merged X producer loads XK(t) before XM(t-2): with one XK stage it deadlocks at item boundaries");
-constexpr int SZ = 3;                     // Z / G0 accumulators in TMEM
-constexpr uint32_t XH_BYTES = 16384, XK_BYTES = 32768 /* Xh | Xl */, XM_BYTES = 16384, YS_BYTES = 32768, AG_BYTES = 32768,
+constexpr int SXK = 3, SXM = 1, SA = 3;
+constexpr int SZ = 4;                     // Z / G0 accumulators in TMEM
+constexpr int LA = SZ - 1;                // MMA1 runs LA tiles ahead of MMA2 / MMA3
+// The merged X producer loads XK(t) before XM(t - LA), and MMA1 never runs ahead across an item boundary: the last
+// MMA3 of an item needs XM(last), which is issued after XK(last + LA), which needs the stage MMA1(last + LA - SXK) frees.
+static_assert(SXK >= LA, "with fewer XK stages than the MMA1 look-ahead the X producer deadlocks at item boundaries");
+constexpr int SDX = 2;                    // dX staging buffers (TMA reduce-adds in flight)
+constexpr uint32_t XK_BYTES = 16384 /* bf16 [Xh | Xl] */, XM_BYTES = 16384, YS_BYTES = 32768, AG_BYTES = 32768,
                    DXS_BYTES = 16384 /* dX tile staged for the TMA reduce-add */;
-constexpr uint32_t SMEM_DATA = SXK * XK_BYTES + SXM * XM_BYTES + YS_BYTES + SA * AG_BYTES + DXS_BYTES;
-constexpr uint32_t SMEM_TOTAL = SMEM_DATA + 1024 /*align slack*/ + 256 /*barriers*/;
-constexpr uint32_t TM_YH = 0, TM_YL = 64, TM_Z0 = 128, TM_DY = 320, TM_DX0 = 384;   // Z_b = Z0+64b, dX1 = dX0+64
+constexpr uint32_t SMEM_DATA = SXK * XK_BYTES + SXM * XM_BYTES + YS_BYTES + SA * AG_BYTES + SDX * DXS_BYTES;
+constexpr uint32_t SMEM_TOTAL = SMEM_DATA + 1024 /*align slack*/ + 512 /*barriers*/;
+static_assert(SMEM_TOTAL <= 232448, "shared memory budget of one CTA");
+constexpr uint32_t TM_YB = 0, TM_Z0 = 64, TM_DY = 320, TM_DX0 = 384;   // [Yh|Yl] bf16 pairs; Z_b = Z0+64b, dX1 = dX0+64
+static_assert(TM_Z0 + 64 * SZ <= TM_DY, "TMEM map");
 
 enum Bar { B_FULL_XK = 0, B_EMPTY_XK = B_FULL_XK + SXK, B_FULL_XM = B_EMPTY_XK + SXK, B_EMPTY_XM = B_FULL_XM + SXM,
            B_FULL_A = B_EMPTY_XM + SXM, B_EMPTY_AG = B_FULL_A + SA, B_Z_FULL = B_EMPTY_AG + SA, B_G_READY = B_Z_FULL + SZ,
            B_DX_FULL = B_G_READY + SZ, B_DX_EMPTY = B_DX_FULL + 2, B_Y_READY = B_DX_EMPTY + 2, B_DY_FULL, B_DY_EMPTY,
-           B_DXS_FULL, B_DXS_DONE /* one per group */, B_COUNT = B_DXS_DONE + 2 };
+           B_DXS_FULL, B_DXS_DONE = B_DXS_FULL + SDX, B_Z_EMPTY = B_DXS_DONE + SDX, B_COUNT = B_Z_EMPTY + SZ };
+static_assert(8 * B_COUNT + 8 <= 512, "barrier area");
 
 using namespace tcx;
 
@@ -169,8 +184,8 @@ struct Ring {
 // columns).  A separate instantiation: the production kernel carries none of that code.
 template <bool DBG, bool BATCH, bool THR>
 __global__ void __launch_bounds__(NTHREADS, 1)
-data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUtensorMap tmXl,
-                    const __grid_constant__ CUtensorMap tmXm, const __grid_constant__ CUtensorMap tmA,
+data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXb, const __grid_constant__ CUtensorMap tmXm,
+                    const __grid_constant__ CUtensorMap tmA,
                     const __grid_constant__ CUtensorMap tmDX, const TcParams p) {
     const DataPassParams& dp = p.dp;
     if (dp.stop_flag != nullptr && *dp.stop_flag != 0) return;
@@ -188,13 +203,15 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
     // event stamp of CTA 0 (timeline experiments; the branch is CTA-uniform)
     auto stamp = [&](uint32_t gg, int ev) {
         if (DBG && p.trace != nullptr && blockIdx.x == (unsigned)p.trace_cta && gg < (uint32_t)TRACE_TILES &&
-            (!(p.flags & 16) || ev == 9) && (!(p.flags & 32) || ev == 1 || ev == 2 || ev == 3 || ev == 4 || ev >= 13))
+            (!(p.flags & 16) || ev == 9) && (!(p.flags & 32) || ev == 1 || ev == 2 || ev == 3 || ev == 4 || ev >= 13) &&
+            (!(p.flags & 64) || (ev >= 5 && ev <= 9) || (ev >= 16 && ev <= 21)) &&
+            (!(p.flags & 128) || ev == 0 || (ev >= 5 && ev <= 9)))
             p.trace[gg * TRACE_EV + ev] = clock64();
     };
 
     // warp index through a shuffle: the compiler then treats role branches as warp-uniform and keeps
     // MMA descriptors / barrier addresses in uniform registers
-    if (DBG && p.trace != nullptr && threadIdx.x == 0 && blockIdx.x < (unsigned)TRACE_CTAS)
+    if (p.trace != nullptr && threadIdx.x == 0 && blockIdx.x < (unsigned)TRACE_CTAS)     // CTA-uniform; also in production (PMF_TC_CTATIMES)
         p.trace[TRACE_TILES * TRACE_EV + 2 * blockIdx.x] = (long long)globaltimer_ns();
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
@@ -205,8 +222,8 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
             // Epilogue warps arrive ONCE PER WARP (lane 0, after the lanes' fences and a __syncwarp): an arrive is
             // an atomic on the barrier word, and 256 of them per barrier and tile serialise in the shared-memory unit
             if (b == B_Y_READY || b == B_DY_EMPTY) cnt = NEPI;                             // every epilogue warp
-            if ((b >= B_G_READY && b < B_G_READY + SZ) || b == B_DX_EMPTY || b == B_DX_EMPTY + 1 || b == B_DXS_FULL)
-                cnt = NEPI / 2;                                                           // one epilogue group
+            if (b >= B_G_READY && b < B_G_READY + SZ) cnt = NEPI / 2;                      // one epilogue group
+            if (b == B_DX_EMPTY || b == B_DX_EMPTY + 1 || (b >= B_DXS_FULL && b < B_DXS_FULL + SDX)) cnt = NDRAIN;   // the drain warps
             mbar_init(bar(b), cnt);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -220,7 +237,12 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
     tc_fence_after();
     const uint32_t tm = *tmem_slot;
 
-    if (warp == W_TMA_A || warp == W_TMA_X) {
+    // Register re-allocation: ONE setmaxnreg for the two small warpgroups (warps 16-23) and one for the four epilogue
+    // warpgroups -- every warp of a warpgroup executes the same instruction -- each dominating the code of its roles.
+    if (warp >= NEPI) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_SMALL));
+    if (warp < NEPI) {
+        // (epilogue: the last branch)
+    } else if (warp == W_TMA_A || warp == W_TMA_X) {
         // ================================ TMA producers ===========================================
         // Warp W_TMA_A streams the A tiles (HBM); warp W_TMA_X feeds both X operand buffers (L2): the K-major pair
         // (Xh | Xl) of tile t, then the MN-major Xh copy of tile t-2 -- the order in which MMA1 (two tiles
@@ -238,12 +260,22 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
                     mbar_expect_tx(bar(B_FULL_A + r.s), AG_BYTES);
                     for (int iq = 0; iq < 2; ++iq)
                         tma_load_2d(AG + r.s * AG_BYTES + iq * 16384, &tmA, bar(B_FULL_A + r.s),
-                                    (DBG && p.ablate & 32) ? 32 * iq : i0 + 32 * iq, (DBG && p.ablate & 32) ? 0 : j0);
+                                    (DBG && (p.ablate & 32)) ? 32 * iq : i0 + 32 * iq, (DBG && (p.ablate & 32)) ? 0 : j0);
+                    // The load of a tile can only be issued when its ring stage is free, about 1.5 tile periods before
+                    // the epilogue wants it: the HBM latency would sit inside the stage's cycle.  An L2 prefetch a few
+                    // tiles further ahead costs no stage and turns that latency into an L2 hit.
+                    const int pf = DBG ? (p.flags >> 8) & 15 : 0;
+                    if (pf && it + pf < it1) {
+                        tma_prefetch_2d(&tmA, i0 + 64 * pf, j0);
+                        tma_prefetch_2d(&tmA, i0 + 64 * pf + 32, j0);
+                    }
                 }
             }
         } else if (lane == 0) {
             Ring rk, rm;
-            int pend[2] = {-1, -1};       // sample offsets of the last two tiles whose MN-major copy is still due
+            int pend[LA];                 // sample offsets of the last LA tiles whose MN-major copy is still due
+#pragma unroll
+            for (int k = 0; k < LA; ++k) pend[k] = -1;
             auto load_xm = [&](int i0) {
                 mbar_wait(bar(B_EMPTY_XM + rm.s), rm.ph ^ 1);
                 if (DBG && (p.ablate & 128)) {       // experiment: no L2 -> shared-memory traffic for the MN-major copy
@@ -266,53 +298,102 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
                     } else {
                         mbar_expect_tx(bar(B_FULL_XK + rk.s), XK_BYTES);
                         const uint32_t dst = XK + rk.s * XK_BYTES;
-                        for (int kb = 0; kb < 2; ++kb) {
-                            tma_load_2d(dst + kb * 8192, &tmXh, bar(B_FULL_XK + rk.s), 32 * kb, i0);
-                            tma_load_2d(dst + XH_BYTES + kb * 8192, &tmXl, bar(B_FULL_XK + rk.s), 64 * kb, i0);   // bf16 [Xh | Xl]
-                        }
+                        for (int kb = 0; kb < 2; ++kb)
+                            tma_load_2d(dst + kb * 8192, &tmXb, bar(B_FULL_XK + rk.s), 64 * kb, i0);   // bf16 Xh | Xl
                     }
                     rk.next(SXK);
                     if (pend[0] >= 0) load_xm(pend[0]);
-                    pend[0] = pend[1];
-                    pend[1] = i0;
+#pragma unroll
+                    for (int k = 0; k + 1 < LA; ++k) pend[k] = pend[k + 1];
+                    pend[LA - 1] = i0;
                 }
             }
-            if (pend[0] >= 0) load_xm(pend[0]);
-            if (pend[1] >= 0) load_xm(pend[1]);
+#pragma unroll
+            for (int k = 0; k < LA; ++k)
+                if (pend[k] >= 0) load_xm(pend[k]);
         }
-    } else if (warp == W_DXRED) {
-        // ================================ dX reduce-add issuer =====================================
-        // The epilogue groups stage each dX tile in shared memory; this thread turns it into ONE TMA
-        // reduce-add per 32-column box and waits for the engine to have read the staging buffer, so no
-        // epilogue warp ever blocks on the memory system.
-        if (lane == 0) {
-            uint32_t g = 0;
-            for (ItemIter itx(p); itx.next();) {
-                const int it0 = itx.it0, it1 = itx.it1;
-                const int xrow0 = BATCH ? __ldg(p.pass_order + itx.jt) * dp.Mp : 0;   // this order's copy of dX
-                for (int it = it0; it < it1; ++it, ++g) {
-                    mbar_wait(bar(B_DXS_FULL), g & 1);
-                    stamp(g, 31);
-                    if (!(DBG && p.ablate & 16)) {
-                        tma_reduce_add_2d(&tmDX, DXS, 0, xrow0 + it * BI);
-                        if (dp.Kp > 32) tma_reduce_add_2d(&tmDX, DXS + 8192, 32, xrow0 + it * BI);
-                    }
-                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                    mbar_arrive(bar(B_DXS_DONE + (g & 1)));
-                    stamp(g, 12);
-                }
-            }
-            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // every reduce-add has been performed
-        }
-    } else if (warp == W_MMA) {
+    } else if (warp == W_MMA1) {
       if (elect_one()) {
-        // ================================ MMA issuer ===============================================
-        // One elected thread runs the whole role: barrier waits, tcgen05.mma, tcgen05.commit.
-        const uint32_t id_z = umma_idesc(128, 64, false, false);   // Z  = Y(tmem) * Xh' : B K-major
+        // ================================ MMA issuer 1: Z = Y X' =====================================
+        // tcgen05.mma is accepted at the rate the tensor pipe executes it (the queue holds one or two instructions),
+        // so every cycle an issuing thread spends in a barrier wait is a cycle the pipe idles.  The contractions
+        // are therefore issued by TWO threads: this one runs MMA1 up to SZ tiles ahead, the other one MMA2 / MMA3;
+        // while one of them waits, the instructions of the other keep the pipe busy.  The order the single
+        // in-order thread used to provide -- MMA3 of tile t - SZ has read G out of the Z buffer that MMA1 of tile
+        // t overwrites -- is now the barrier Z_EMPTY.
         // BF16 x BF16 -> F32 (kind::f16): c_format F32, a_format = b_format = BF16, both K-major
         const uint32_t id_zb = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-        // K < 64: the contraction of MMA1 stops at Kp and the gradient tiles are only Kp columns wide
+        const int kn = dp.Kp;                                       // multiple of 8, <= 64
+        if (tm != 0u) __trap();
+        const uint32_t tmu = 0u;
+        auto kstep = [](uint64_t d0, int s, uint32_t atom) { return d0 + (uint64_t)((((s >> 2) * atom) + (s & 3) * 32) >> 4); };
+        uint32_t q = 0, g1 = 0;
+        Ring rx1, rz1;         // XK stage / Z buffer of the next MMA1
+        // This thread runs tiles ahead of everything else, so it also issues the TMA reduce-adds of the staged dX
+        // tiles, RLAG tiles behind its own MMA1 (by then the drain warps have staged that tile): two bulk groups in
+        // flight, the staging buffer of a tile is handed back once the engine has read it.  Pending reduce-adds
+        // are flushed at the end of an item -- the drain of the item's last tiles needs the buffers back before
+        // the item can complete, and this thread is about to block on the next item's Y operands.
+        constexpr int RLAG = 5;
+        uint32_t gr = 0;       // next tile whose dX is to be reduced
+        auto reduce_tile = [&](int it_r, int xrow0) {
+            const uint32_t sb = gr & 1u;
+            mbar_wait(bar(B_DXS_FULL + sb), (gr >> 1) & 1);
+            stamp(gr, 31);
+            if (!(DBG && (p.ablate & 16))) {
+                tma_reduce_add_2d(&tmDX, DXS + sb * DXS_BYTES, 0, xrow0 + it_r * BI);
+                if (dp.Kp > 32) tma_reduce_add_2d(&tmDX, DXS + sb * DXS_BYTES + 8192, 32, xrow0 + it_r * BI);
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            if (gr > 0) mbar_arrive(bar(B_DXS_DONE + (sb ^ 1u)));     // tile gr - 1 has been read
+            stamp(gr, 12);
+            ++gr;
+        };
+        for (ItemIter itx(p); itx.next();) {
+            const int it0 = itx.it0, it1 = itx.it1;
+            const int xrow0 = BATCH ? __ldg(p.pass_order + itx.jt) * dp.Mp : 0;   // this order's copy of dX
+            mbar_wait(bar(B_Y_READY), q & 1);
+            int it_r = it0;
+            for (int it = it0; it < it1; ++it, ++g1) {
+                stamp(g1, 13);
+                mbar_wait(bar(B_Z_EMPTY + rz1.s), rz1.ph ^ 1);
+                mbar_wait(bar(B_FULL_XK + rx1.s), rx1.ph);
+                tc_fence_after();
+                stamp(g1, 1);
+                const uint32_t zt = tmu + TM_Z0 + 64 * rz1.s;
+                // Xb tile: box 0 = Xh (64 bf16 = 128 bytes per sample row), box 1 = Xl; a k-step of 16 is 32 bytes
+                const uint64_t xb = umma_desc_k(XK + rx1.s * XK_BYTES);
+#pragma unroll
+                for (int s = 0; s < 4; ++s)       // Yh * Xh
+                    if (16 * s < kn) mma_ts_f16(zt, tmu + TM_YB + 8 * s, kstep(xb, s, 8192), id_zb, s > 0 ? 1u : 0u);
+                if (p.z_passes == 3) {
+#pragma unroll
+                    for (int s = 0; s < 4; ++s)   // Yl * Xh
+                        if (16 * s < kn) mma_ts_f16(zt, tmu + TM_YB + 32 + 8 * s, kstep(xb, s, 8192), id_zb, 1u);
+#pragma unroll
+                    for (int s = 0; s < 4; ++s)   // Yh * Xl
+                        if (16 * s < kn) mma_ts_f16(zt, tmu + TM_YB + 8 * s, kstep(xb, 4 + s, 8192), id_zb, 1u);
+                }
+                tc_commit_elect(bar(B_EMPTY_XK + rx1.s));
+                tc_commit_elect(bar(B_Z_FULL + rz1.s));
+                stamp(g1, 14);
+                rx1.next(SXK);
+                rz1.next(SZ);
+                if (it - it_r >= RLAG) reduce_tile(it_r++, xrow0);
+            }
+            while (it_r < it1) reduce_tile(it_r++, xrow0);
+            ++q;
+        }
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        if (gr > 0) mbar_arrive(bar(B_DXS_DONE + ((gr - 1u) & 1u)));
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // every reduce-add has been performed
+      }
+      __syncwarp();
+    } else if (warp == W_MMA) {
+      if (elect_one()) {
+        // ================================ MMA issuer 2: dX, dY ======================================
+        // K < 64: the gradient tiles are only Kp columns wide
         const int kn = dp.Kp;                                       // multiple of 8, <= 64
         const uint32_t id_dx = umma_idesc(64, kn, true, true);     // dX = G0'(smem, MN) * Yh(smem, MN)
         const uint32_t id_dy = umma_idesc(128, kn, false, true);   // dY = G0(tmem) * Xh(smem, MN)
@@ -320,64 +401,17 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
         // keeps every tcgen05.mma operand in uniform registers (no per-instruction R2UR).
         if (tm != 0u) __trap();
         const uint32_t tmu = 0u;
-        // k-step s of a K-major operand whose 32-wide K-atoms (boxes) are `atom` bytes apart
-        auto kstep = [](uint64_t d0, int s, uint32_t atom) { return d0 + (uint64_t)((((s >> 2) * atom) + (s & 3) * 32) >> 4); };
-        uint32_t g = 0, q = 0, g1 = 0;
-        Ring rx1, rz1;         // XK stage / Z buffer of the next MMA1
+        uint32_t g = 0, q = 0;
         Ring rx3, ra, rz;      // XM stage of the next MMA3, A/G stage of the next MMA2, Z buffer of the next MMA2/3
-        auto issue_mma1_nowait = [&]() {
-            ++g1;
-            const uint32_t zt = tmu + TM_Z0 + 64 * rz1.s;
-            const uint64_t xh = umma_desc_k(XK + rx1.s * XK_BYTES), xl = umma_desc_k(XK + rx1.s * XK_BYTES + XH_BYTES);
-#pragma unroll
-            for (int s = 0; s < 8; ++s)
-                if (8 * s < kn) mma_ts(zt, tmu + TM_YH + 8 * s, kstep(xh, s, 8192), id_z, s > 0 ? 1u : 0u);
-            if (p.z_passes == 3) {
-                // [Yl | Yh] (bf16, TMEM) x [Xh | Xl] (bf16, smem): 128 k' = 8 instructions of K = 16
-#pragma unroll
-                for (int s = 0; s < 8; ++s)
-                    if (16 * (s & 3) < kn) mma_ts_f16(zt, tmu + TM_YL + 8 * s, kstep(xl, s, 8192), id_zb, 1u);
-            }
-            tc_commit_elect(bar(B_EMPTY_XK + rx1.s));
-            tc_commit_elect(bar(B_Z_FULL + rz1.s));
-            stamp(g1 - 1, 14);
-            rx1.next(SXK);
-            rz1.next(SZ);
-        };
-        auto issue_mma1 = [&]() {
-            stamp(g1, 13);
-            mbar_wait(bar(B_FULL_XK + rx1.s), rx1.ph);
-            tc_fence_after();
-            stamp(g1, 1);
-            issue_mma1_nowait();
-        };
         for (ItemIter itx(p); itx.next();) {
             const int it0 = itx.it0, it1 = itx.it1;
             mbar_wait(bar(B_Y_READY), q & 1);
             mbar_wait(bar(B_DY_EMPTY), (q & 1) ^ 1);
-            tc_fence_after();
-            // MMA1 runs two tiles ahead of the epilogue (three Z accumulators), never across an item boundary
-            issue_mma1();
-            if (it0 + 1 < it1) issue_mma1();
             for (int it = it0; it < it1; ++it, ++g) {
-                // In steady state the MMA thread is the pacing role and every barrier of the iteration has
-                // already completed when it gets here: one batched probe replaces four serial waits (each a
-                // shared-memory round trip during which the tensor queue drains); a barrier that is still
-                // open is waited for where the old code did, MMA1 of tile g+2 going first to fill the wait.
                 const uint32_t b = g & 1, ph = (g >> 1) & 1;
-                const bool m1 = it + 2 < it1;
-                const uint32_t ok = mbar_probe4(bar(B_FULL_XK + rx1.s), rx1.ph, bar(B_G_READY + rz.s), rz.ph,
-                                                bar(B_DX_EMPTY + b), ph ^ 1, bar(B_FULL_XM + rx3.s), rx3.ph);
-                if (m1) {
-                    stamp(g1, 13);
-                    if (!(ok & 1u)) mbar_wait(bar(B_FULL_XK + rx1.s), rx1.ph);
-                    tc_fence_after();
-                    stamp(g1, 1);
-                    issue_mma1_nowait();
-                }
-                if (!(ok & 2u)) mbar_wait(bar(B_G_READY + rz.s), rz.ph);
+                mbar_wait(bar(B_G_READY + rz.s), rz.ph);
                 stamp(g, 2);
-                if (!(ok & 4u)) mbar_wait(bar(B_DX_EMPTY + b), ph ^ 1);
+                mbar_wait(bar(B_DX_EMPTY + b), ph ^ 1);
                 tc_fence_after();
                 stamp(g, 3);
                 {
@@ -386,7 +420,7 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
                     const uint32_t dxt = tmu + TM_DX0 + 64 * b;
 #pragma unroll
                     for (int s = 0; s < 16; ++s) {
-                        if ((DBG && p.ablate & 1) && s > 0) break;
+                        if (DBG && (p.ablate & 1) && s > 0) break;
                         mma_ss(dxt, gd + (uint64_t)(s * 64), yd + (uint64_t)(s * 64), id_dx, s > 0 ? 1u : 0u);
                     }
                     tc_commit_elect(bar(B_EMPTY_AG + ra.s));
@@ -395,17 +429,19 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
                 }
                 {
                     // MMA3: dY += G0 * Xh  (MN-major copy of the Xh tile)
-                    if (!(ok & 8u)) { mbar_wait(bar(B_FULL_XM + rx3.s), rx3.ph); tc_fence_after(); }
+                    mbar_wait(bar(B_FULL_XM + rx3.s), rx3.ph);
+                    tc_fence_after();
                     stamp(g, 4);
                     const uint32_t ga = tmu + TM_Z0 + 64 * rz.s;
                     const uint64_t xd = umma_desc_mn(XM + rx3.s * XM_BYTES, 8192u);
                     const uint32_t first = it > it0 ? 1u : 0u;
 #pragma unroll
                     for (int s = 0; s < 8; ++s) {
-                        if ((DBG && p.ablate & 2) && s > 0) break;
+                        if (DBG && (p.ablate & 2) && s > 0) break;
                         mma_ts(tmu + TM_DY, ga + 8 * s, xd + (uint64_t)(s * 64), id_dy, s > 0 ? 1u : first);
                     }
                     tc_commit_elect(bar(B_EMPTY_XM + rx3.s));
+                    tc_commit_elect(bar(B_Z_EMPTY + rz.s));
                     stamp(g, 15);
                     rx3.next(SXM);
                     rz.next(SZ);
@@ -416,8 +452,72 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
         }
       }
       __syncwarp();
-    } else {
+    } else if (warp >= W_DRAIN0) {
+        // ================================ dX drain warps ===========================================
+        // dX tile of EVERY tile: TMEM -> registers -> one of the two swizzled staging buffers, from where the MMA1
+        // thread issues a TMA reduce-add into global dX (the L2 does the additions on full lines; no per-lane REDs
+        // through the LSU), two of them in flight.  M = 64 accumulator: sample row r sits in lane (r % 16) +
+        // 32 * (r / 16), so warp q of the four holds rows 16q .. 16q + 15 in the first 16 lanes of its quarter:
+        // ONE tcgen05.ld of shape 16x256b.x8 brings the warp's 16 x 64 block in, spread over all 32 threads
+        // (thread t: rows t/4 and t/4 + 8, columns 8j + 2(t%4), +1 of every 8-column atom j).
+        const int quarter = warp & 3;
+        const uint32_t lane_addr = ((uint32_t)(32 * quarter)) << 16;
+        const int ra_ = 16 * quarter + (lane >> 2), rb_ = ra_ + 8;   // sample rows of the tile held by this thread
+        const uint32_t cw = (uint32_t)(lane & 3) * 8u;                // byte offset of its column pair inside a 32-byte group
+        const bool tr = warp == W_DRAIN0 && lane == 0;
+        uint32_t g = 0;
+        for (ItemIter itx(p); itx.next();) {
+            const int it0 = itx.it0, it1 = itx.it1;
+            for (int it = it0; it < it1; ++it, ++g) {
+                const uint32_t b = g & 1;
+                uint8_t* const buf = dxs_ptr + b * DXS_BYTES;
+                // experiment (PMF_TC_FLAGS bits 8..11 = distance in tiles): L2 prefetch of a later A tile through the LSU
+                if (!BATCH) {
+                    const int pf = (p.flags >> 8) & 15;
+                    if (pf && it + pf < it1) {
+                        const int jrow = itx.jt * BJ + 32 * quarter + lane;
+                        if (jrow < dp.N) {
+                            const float* pa = dp.A + (size_t)jrow * dp.lda + (size_t)(it + pf) * BI;
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(pa));
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(pa + 32));
+                        }
+                    }
+                }
+                if (tr) stamp(g, 10);
+                mbar_wait(bar(B_DX_FULL + b), (g >> 1) & 1);
+                tc_fence_after();
+                if (tr) stamp(g, 11);
+                uint32_t r0[32];
+                TMEM_LD_16x256b_x8(tm + lane_addr + TM_DX0 + 64 * b, r0);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                // the accumulator has been read: MMA2 of tile g + 2 may overwrite it
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_relaxed(bar(B_DX_EMPTY + b));
+                if (tr) stamp(g, 28);
+                // the reduce-add of tile g - 2 has read this staging buffer (first use: parity 1 passes on a fresh barrier)
+                mbar_wait(bar(B_DXS_DONE + b), ((g >> 1) - 1u) & 1u);
+                if (tr) stamp(g, 29);
+                if (!(DBG && (p.ablate & 16))) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        // columns 8j + 2(t%4), +1: box j / 4, 16-byte chunk 2 (j % 4) + (t % 4) / 2 of the 128-byte row
+                        const uint32_t c = 2u * (j & 3) + ((lane & 3) >> 1);
+                        uint8_t* const bx = buf + (j >> 2) * 8192;
+                        *reinterpret_cast<uint2*>(bx + ra_ * 128 + ((c ^ (ra_ & 7)) << 4) + (cw & 8u)) = make_uint2(r0[4 * j], r0[4 * j + 1]);
+                        *reinterpret_cast<uint2*>(bx + rb_ * 128 + ((c ^ (rb_ & 7)) << 4) + (cw & 8u)) = make_uint2(r0[4 * j + 2], r0[4 * j + 3]);
+                    }
+                }
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar(B_DXS_FULL + b));
+                if (tr) stamp(g, 30);
+            }
+        }
+    }
+    if (warp < NEPI) {
         // ================================ epilogue warps ===========================================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_EPI));
         // Two groups of 8 warps work on alternating tiles, so that the load / compute / store-drain
         // phases of one tile overlap those of the next.  Inside a tile a warp owns (TMEM lane quarter,
         // 32-sample half): TMEM lanes 32*quarter.., columns 32*h32.. = one row of A box h32 per thread.
@@ -437,49 +537,6 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
         Ring ra, rz;
         if (grp == 1) { ra.next(SA); rz.next(SZ); }
         double loss_d = 0.0;
-        // dX tile of one of this group's tiles: TMEM -> registers -> swizzled staging buffer, from where warp 4
-        // issues a TMA reduce-add into global dX (the L2 does the additions on full lines; no per-lane REDs
-        // through the LSU).
-        // M = 64 accumulator: sample row r sits in lane (r%16) + 32*(r/16).  The staging buffer is shared by the
-        // two groups: flush(g) waits until the TMA reads of flush(g-1) (other group) and flush(g-2) (own group,
-        // whose issuing thread may lag behind) are over.  Each group counts its flushes on its own barrier.
-        auto dx_out = [&](uint32_t gg, int i0) {
-            const uint32_t b = gg & 1;
-            const bool tr = quarter == 0 && h32 == 0 && lane == 0;
-            if (tr) stamp(gg, 10);
-            mbar_wait(bar(B_DX_FULL + b), (gg >> 1) & 1);
-            tc_fence_after();
-            if (tr) stamp(gg, 11);
-            uint32_t r0[16], r1[16];
-            TMEM_LD16(tm + lane_addr + TM_DX0 + 64 * b + 32 * h32, r0);
-            TMEM_LD16(tm + lane_addr + TM_DX0 + 64 * b + 32 * h32 + 16, r1);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_relaxed(bar(B_DX_EMPTY + b));
-            if (tr) stamp(gg, 28);
-            {
-                const uint32_t n_other = grp == 0 ? (gg >> 1) : ((gg + 1) >> 1), n_own = gg >> 1;   // flushes before tile gg
-                mbar_wait(bar(B_DXS_DONE + (grp ^ 1)), (n_other - 1u) & 1u);     // n == 0: parity 1 passes on a fresh barrier
-                mbar_wait(bar(B_DXS_DONE + grp), (n_own - 1u) & 1u);
-            }
-            if (tr) stamp(gg, 29);
-            if (lane < 16 && !(DBG && p.ablate & 16)) {
-                const int r = 16 * quarter + lane;                       // sample row of the tile
-                uint8_t* row = dxs_ptr + h32 * 8192 + r * 128;
-#pragma unroll
-                for (int v = 0; v < 4; ++v) {
-                    *reinterpret_cast<uint4*>(row + ((v ^ (r & 7)) << 4)) = make_uint4(r0[4 * v], r0[4 * v + 1], r0[4 * v + 2], r0[4 * v + 3]);
-                    *reinterpret_cast<uint4*>(row + (((4 + v) ^ (r & 7)) << 4)) = make_uint4(r1[4 * v], r1[4 * v + 1], r1[4 * v + 2], r1[4 * v + 3]);
-                }
-            }
-            fence_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar(B_DXS_FULL));
-            if (tr) stamp(gg, 30);
-        };
-        int pend_i0 = -1;          // sample offset of this group's tile whose dX is still in TMEM
-        uint32_t pend_g = 0;
 
         // Per-item operands of this thread (lane = feature): column constants and its 16-column chunk of
         // the Y row.  They are fetched one item AHEAD, right before the wait for the current item's last
@@ -623,37 +680,29 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
             // ---- Y tile: h = rna_tf32(y), l = y - h -> TMEM (A of MMA1); gscale * y -> shared memory (B of MMA2).
             // The previous item's MMAs have all completed (B_DY_FULL was waited on), so both are free.
             {
-                uint32_t hi[16], lob[8], hib[8];      // Yh (tf32), packed bf16 pairs of Yl and of Yh
+                uint32_t lob[8], hib[8];      // packed bf16 pairs of Yh = bf16(y) and of Yl = bf16(y - Yh)
 #pragma unroll
                 for (int v = 0; v < 4; ++v) {
                     const float4 y4 = cur.y[v];
-                    float ys[4] = {y4.x, y4.y, y4.z, y4.w};
-                    float ls[4];
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        uint32_t hb = rna_tf32(ys[c]);
-                        hi[4 * v + c] = hb;
-                        ls[c] = ys[c] - __uint_as_float(hb);
-                    }
-                    lob[2 * v] = pack_bf16(ls[0], ls[1]);
-                    lob[2 * v + 1] = pack_bf16(ls[2], ls[3]);
-                    hib[2 * v] = pack_bf16(__uint_as_float(hi[4 * v]), __uint_as_float(hi[4 * v + 1]));
-                    hib[2 * v + 1] = pack_bf16(__uint_as_float(hi[4 * v + 2]), __uint_as_float(hi[4 * v + 3]));
+                    const uint32_t h01 = pack_bf16(y4.x, y4.y), h23 = pack_bf16(y4.z, y4.w);
+                    hib[2 * v] = h01;
+                    hib[2 * v + 1] = h23;
+                    lob[2 * v] = pack_bf16(y4.x - __uint_as_float(h01 << 16), y4.y - __uint_as_float(h01 & 0xffff0000u));
+                    lob[2 * v + 1] = pack_bf16(y4.z - __uint_as_float(h23 << 16), y4.w - __uint_as_float(h23 & 0xffff0000u));
                     *reinterpret_cast<uint4*>(ys_ptr + (uint32_t)(c16 >> 1) * 16384u + chunk_off(4 * (c16 & 1) + v)) =
                         make_uint4(rna_tf32(gscale * y4.x), rna_tf32(gscale * y4.y), rna_tf32(gscale * y4.z), rna_tf32(gscale * y4.w));
                 }
                 const bool trp = quarter == 0 && h32 == 0 && lane == 0;
-                if (trp) stamp(g, 19 + 6 * grp);
-                TMEM_ST16(tm + lane_addr + TM_YH + 16 * c16, hi);
-                TMEM_ST8(tm + lane_addr + TM_YL + 8 * c16, lob);          // k' = 0..63  : Yl (pairs with Xh)
-                TMEM_ST8(tm + lane_addr + TM_YL + 32 + 8 * c16, hib);     // k' = 64..127: Yh (pairs with Xl)
+                if (trp && !(p.flags & 64)) stamp(g, 19 + 6 * grp);
+                TMEM_ST8(tm + lane_addr + TM_YB + 8 * c16, hib);          // Yh: 16 k of this warp = 8 columns of bf16 pairs
+                TMEM_ST8(tm + lane_addr + TM_YB + 32 + 8 * c16, lob);     // Yl
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 tc_fence_before();
                 fence_async_smem();
-                if (trp) stamp(g, 20 + 6 * grp);
+                if (trp && !(p.flags & 64)) stamp(g, 20 + 6 * grp);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar(B_Y_READY));
-                if (trp) stamp(g, 21 + 6 * grp);
+                if (trp && !(p.flags & 64)) stamp(g, 21 + 6 * grp);
                 store_partials();
                 store_segment();
                 if (itx.peek_jt() >= 0) prefetch_item(itx.peek_jt());
@@ -761,11 +810,13 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
                         }
                     }
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (tr && (p.flags & 64)) stamp(g, 16 + 3 * hh);
                     if (BATCH) {
                         const uint32_t id = hh == 0 ? (ids & 0xffffu) : (ids >> 16);
                         if (id != cur_b) enter_segment(id);
                     }
-                    if (!(DBG && p.ablate & 8)) epi16(z, a);
+                    if (!(DBG && (p.ablate & 8))) epi16(z, a);
+                    if (tr && (p.flags & 64)) stamp(g, 17 + 3 * hh);
                     // dloss/dz back to TMEM in place of Z (A operand of MMA3) and over the A values this thread
                     // read (MN-major A operand of MMA2): same addresses, 128-bit stores, no transposition
                     TMEM_ST16(zt + 16 * hh, z);
@@ -776,6 +827,7 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
                             make_uint4(swapped ? z[4 * w] : z[4 * v], swapped ? z[4 * w + 1] : z[4 * v + 1],
                                        swapped ? z[4 * w + 2] : z[4 * v + 2], swapped ? z[4 * w + 3] : z[4 * v + 3]);
                     }
+                    if (tr && (p.flags & 64)) stamp(g, 18 + 3 * hh);
                 }
                 if (tr) stamp(g, 8);
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
@@ -788,13 +840,9 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
                 if (tr) stamp(g, 9);
                 ra.next(SA); ra.next(SA);
                 rz.next(SZ); rz.next(SZ);
-                if (pend_i0 >= 0) dx_out(pend_g, pend_i0);
-                pend_g = g; pend_i0 = it * BI;
             }
-            // every dX tile of the item leaves TMEM before the item's accumulators are flushed
-            if (pend_i0 >= 0) { dx_out(pend_g, pend_i0); pend_i0 = -1; }
             const bool trb = quarter == 0 && h32 == 0 && lane == 0;
-            if (trb) stamp(g, 16 + 6 * grp);
+            if (trb && !(p.flags & 64)) stamp(g, 16 + 6 * grp);
             loss_d += (double)(loss_acc * wj);
             ItemRegs nxt;
             nxt.logsigma = nxt.mu = nxt.w = 0.f; nxt.ci = 0; nxt.boff = -1; nxt.bview = 0;
@@ -804,7 +852,7 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
             // ---- item epilogue: dY tile out of TMEM, column sums --------------------------------------
             mbar_wait(bar(B_DY_FULL), q & 1);
             tc_fence_after();
-            if (trb) stamp(g, 17 + 6 * grp);
+            if (trb && !(p.flags & 64)) stamp(g, 17 + 6 * grp);
             {
                 uint32_t r[16];
                 TMEM_LD16(tm + lane_addr + TM_DY + 16 * c16, r);
@@ -832,7 +880,7 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
             }
             pend_dmu = dmu_acc * wj;
             pend_j = jok ? j : -1;
-            if (trb) stamp(g, 18 + 6 * grp);
+            if (trb && !(p.flags & 64)) stamp(g, 18 + 6 * grp);
             cur = nxt;
             ++q;
         }
@@ -845,7 +893,7 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
     }
     tc_fence_before();
     __syncthreads();
-    if (DBG && p.trace != nullptr && threadIdx.x == 0 && blockIdx.x < (unsigned)TRACE_CTAS)
+    if (p.trace != nullptr && threadIdx.x == 0 && blockIdx.x < (unsigned)TRACE_CTAS)
         p.trace[TRACE_TILES * TRACE_EV + 2 * blockIdx.x + 1] = (long long)globaltimer_ns();
     if (threadIdx.x == 0) {
         double t = 0.0;
@@ -858,8 +906,8 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_const
     }
 }
 
-// Operand split of X:  Xh = rna_tf32(X) (FP32 array) and Xb = bf16([Xh | X - Xh]) ([Mp][128] BF16): the TF32
-// operand of every contraction and the BF16 operands of the first-order correction of Z
+// Operand split of X:  Xh = rna_tf32(X) (FP32 array: TF32 operand of the gradient contraction dY) and the two-term
+// BF16 split Xb = [bf16(X) | bf16(X - bf16(X))] ([Mp][128] BF16: operands of the Z contraction)
 // `perm` (or null): output row r holds the split of X row perm[r] (the per-order operand copies of the batch path)
 __global__ void prep_operands_kernel(const float4* __restrict__ X, float4* __restrict__ Xh, uint2* __restrict__ Xb,
                                      int rows, int K4 /* Kp / 4 */, const int* stop_flag, const int32_t* __restrict__ perm) {
@@ -878,8 +926,10 @@ __global__ void prep_operands_kernel(const float4* __restrict__ X, float4* __res
         h.z = __uint_as_float(rna_tf32(v.z)); h.w = __uint_as_float(rna_tf32(v.w));
         const size_t row = i / K4, c4 = i - row * K4;
         Xh[row * 16 + c4] = h;                             // 16 float4 per 64-wide scratch row
-        Xb[row * 32 + c4] = make_uint2(pack_bf16(h.x, h.y), pack_bf16(h.z, h.w));
-        Xb[row * 32 + 16 + c4] = make_uint2(pack_bf16(v.x - h.x, v.y - h.y), pack_bf16(v.z - h.z, v.w - h.w));
+        const uint32_t b01 = pack_bf16(v.x, v.y), b23 = pack_bf16(v.z, v.w);
+        Xb[row * 32 + c4] = make_uint2(b01, b23);
+        Xb[row * 32 + 16 + c4] = make_uint2(pack_bf16(v.x - __uint_as_float(b01 << 16), v.y - __uint_as_float(b01 & 0xffff0000u)),
+                                            pack_bf16(v.z - __uint_as_float(b23 << 16), v.w - __uint_as_float(b23 & 0xffff0000u)));
     }
 }
 
@@ -1015,9 +1065,8 @@ cudaError_t launch_data_pass_tc(const DataPassParams& dp_in, float* Xh, float* X
     const int n_pass = bp ? bp->n_pass : (dp.N + BJ - 1) / BJ;
     if (bp) dp.tc_cost_cum = bp->cost_cum;
 
-    CUtensorMap tmXh, tmXl, tmXm, tmA, tmDX;
-    bool ok = make_map(&tmXh, Xh, KK, x_rows, KK, 64, false, false) && make_map_bf16(&tmXl, Xl, 2 * KK, x_rows, 64) &&
-              make_map(&tmXm, Xh, KK, x_rows, KK, 64, false, true) &&
+    CUtensorMap tmXb, tmXm, tmA, tmDX;
+    bool ok = make_map_bf16(&tmXb, Xl, 2 * KK, x_rows, 64) && make_map(&tmXm, Xh, KK, x_rows, KK, 64, false, true) &&
               make_map(&tmA, a_src, dp.lda, permuted ? (uint64_t)n_pass * BJ : (uint64_t)dp.N, dp.lda, 128, true, true) &&
               make_map(&tmDX, dx_target, dp.Kp, x_rows, dp.Kp, 64, false, false);
     if (!ok) return cudaErrorUnknown;
@@ -1038,7 +1087,8 @@ cudaError_t launch_data_pass_tc(const DataPassParams& dp_in, float* Xh, float* X
     static const char* fl = getenv("PMF_TC_FLAGS");
     p.flags = fl ? atoi(fl) : 0;
     p.trace = nullptr;
-    static const char* trace_path = getenv("PMF_TC_TRACE");
+    static const char* cta_times_path = getenv("PMF_TC_CTATIMES");   // per-CTA (start, end) clocks only, production kernel
+    static const char* trace_path = getenv("PMF_TC_TRACE") ? getenv("PMF_TC_TRACE") : cta_times_path;
     static long long* trace_dev = nullptr;
     if (trace_path) {
         if (!trace_dev) cudaMalloc(&trace_dev, sizeof(long long) * (TRACE_TILES * TRACE_EV + 2 * TRACE_CTAS));
@@ -1047,7 +1097,7 @@ cudaError_t launch_data_pass_tc(const DataPassParams& dp_in, float* Xh, float* X
         const char* tc = getenv("PMF_TC_TRACE_CTA");
         p.trace_cta = tc ? atoi(tc) : 0;
     }
-    const bool dbg = p.ablate != 0 || p.trace != nullptr;
+    const bool dbg = p.ablate != 0 || (p.trace != nullptr && !cta_times_path);
     const bool batch = bp != nullptr;
     const bool thr = dp.dthr != nullptr;
     auto kern = batch ? (thr ? data_pass_tc_kernel<false, true, true> : data_pass_tc_kernel<false, true, false>)
@@ -1057,7 +1107,7 @@ cudaError_t launch_data_pass_tc(const DataPassParams& dp_in, float* Xh, float* X
     if (e != cudaSuccess) return e;
     const long long n_tiles = (long long)p.n_jt * p.n_it;
     int grid = n_tiles < n_sms ? (int)n_tiles : n_sms;
-    kern<<<grid, NTHREADS, SMEM_TOTAL, s>>>(tmXh, tmXl, tmXm, tmA, tmDX, p);
+    kern<<<grid, NTHREADS, SMEM_TOTAL, s>>>(tmXb, tmXm, tmA, tmDX, p);
     ++launched;
     if (permuted) {
         const size_t n4 = (size_t)M_real * dp.Kp / 4;

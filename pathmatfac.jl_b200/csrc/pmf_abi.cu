@@ -326,10 +326,11 @@ int pmf_set_noise(pmf_handle h, int32_t n_ranges, const int32_t* cs, const int32
     CU(h, cudaMemcpy(h->colinfo, ci.data(), (size_t)h->Np * 4, cudaMemcpyHostToDevice));
     if (weight) CU(h, cudaMemcpy(h->weight, weight, (size_t)h->N * 4, cudaMemcpyHostToDevice));
     {
-        // Relative cost of one tile of the tcgen05 data pass per 128-feature tile (measured: all-normal
-        // 0.367 ms, all-bernoulli 0.452 ms, all-poisson 0.39 ms at the C2 shape), cumulated so that the
-        // kernel can cut the tile list into ranges of equal COST, not equal count.
-        static const int kCost[6] = {100, 129, 104, 200, 130, 200};
+        // Relative cost of one tile of the tcgen05 data pass per 128-feature tile (measured at the C2 shape: all-normal
+        // 0.326 ms, all-bernoulli 0.431 ms, all-poisson 0.341 ms; inside the C2 mix the per-CTA clocks put a bernoulli
+        // tile at 1.4 and a poisson tile at 1.07 normal tiles), cumulated so that the kernel can cut the tile list into
+        // ranges of equal COST, not equal count.
+        static const int kCost[6] = {100, 140, 107, 200, 130, 200};
         const int n_jt = (h->N + 127) / 128;
         std::vector<int32_t> cum(n_jt + 1, 0);
         for (int jt = 0; jt < n_jt; ++jt) {

@@ -93,13 +93,15 @@ __device__ __forceinline__ void factor_pass(const FactorUpdateParams& q, int bid
         }
         lsum += (double)loss;
         if (q.Ph) {   // operand split of the (updated) parameters for the next tcgen05 data pass (Kp <= 64):
-            float h[4];   // Ph = rna_tf32(P) as FP32 [n][64], Pl = bf16([Ph | P - Ph]) as [n][128] BF16, zero padded
+            float h[4];   // Ph = rna_tf32(P) as FP32 [n][64]; Pl = two-term BF16 split [bf16(P) | bf16(P - bf16(P))] as [n][128] BF16, zero padded
 #pragma unroll
             for (int c = 0; c < 4; ++c) h[c] = tf32_rna(pa[c]);
             *reinterpret_cast<float4*>(q.Ph + (size_t)row * 64 + 4 * c4) = make_float4(h[0], h[1], h[2], h[3]);
             uint2* pb = reinterpret_cast<uint2*>(q.Pl) + (size_t)row * 32 + c4;
-            pb[0] = make_uint2(bf16x2(h[0], h[1]), bf16x2(h[2], h[3]));
-            pb[16] = make_uint2(bf16x2(pa[0] - h[0], pa[1] - h[1]), bf16x2(pa[2] - h[2], pa[3] - h[3]));
+            const uint32_t b01 = bf16x2(pa[0], pa[1]), b23 = bf16x2(pa[2], pa[3]);
+            pb[0] = make_uint2(b01, b23);
+            pb[16] = make_uint2(bf16x2(pa[0] - __uint_as_float(b01 << 16), pa[1] - __uint_as_float(b01 & 0xffff0000u)),
+                                bf16x2(pa[2] - __uint_as_float(b23 << 16), pa[3] - __uint_as_float(b23 & 0xffff0000u)));
         }
         if (q.zero_buf) *reinterpret_cast<float4*>(q.zero_buf + off) = make_float4(0.f, 0.f, 0.f, 0.f);
     }

@@ -62,6 +62,10 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
+// L2 prefetch of a tile (no shared-memory destination, no completion tracking)
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
+}
 // shared -> global tile, element-wise f32 add performed by the memory system (bulk async-group completion)
 __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
     asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
@@ -126,6 +130,19 @@ __host__ __device__ constexpr uint32_t umma_idesc(int M, int N, bool a_mn, bool 
 
 #define TMEM_LD32(taddr, r)                                                                                       \
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                        \
+                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,"  \
+                 "%26,%27,%28,%29,%30,%31}, [%32];"                                                               \
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),  \
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),        \
+                   "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]),      \
+                   "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]),      \
+                   "=r"(r[29]), "=r"(r[30]), "=r"(r[31])                                                          \
+                 : "r"(taddr))
+// 16 lanes x 256 bits, 8 times along the columns: a 16 x 64 block of 32-bit words spread over the 32 threads of the warp
+// (thread t: rows t/4 and t/4 + 8; per 8-column atom j the registers r[4j], r[4j+1] = row t/4, columns 8j + 2(t%4), +1
+// and r[4j+2], r[4j+3] = row t/4 + 8, same columns)
+#define TMEM_LD_16x256b_x8(taddr, r)                                                                              \
+    asm volatile("tcgen05.ld.sync.aligned.16x256b.x8.b32 "                                                        \
                  "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,"  \
                  "%26,%27,%28,%29,%30,%31}, [%32];"                                                               \
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),  \
