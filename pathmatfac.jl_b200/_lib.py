@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpmf.so")
+LIB_PATH = os.environ.get("PMF_LIB") or os.path.join(_HERE, "libpmf.so")   # PMF_LIB: A/B runs of experiment builds
 
 c_int32_p = C.POINTER(C.c_int32)
 c_float_p = C.POINTER(C.c_float)

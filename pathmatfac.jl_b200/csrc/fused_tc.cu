@@ -67,13 +67,17 @@ constexpr int REGS_EPI = 88, REGS_SMALL = 64;
 // Pipeline depths.  The X operands come from L2 and are re-loaded while the tensor pipe works on the other
 // contractions of the neighbouring tiles, so one stage each suffices; the A/G ring is the HBM stream and
 // stays occupied from the TMA issue until MMA2 has consumed G0, so it gets every byte that is left.
-constexpr int SXK = 3, SXM = 1, SA = 3;
-constexpr int SZ = 4;                     // Z / G0 accumulators in TMEM
+#ifndef PMF_SA
+#define PMF_SA 3
+#endif
+constexpr int SA = PMF_SA;
+constexpr int SXK = SA == 4 ? 2 : 3, SXM = 1;
+constexpr int SZ = SA == 4 ? 3 : 4;       // Z / G0 accumulators in TMEM
 constexpr int LA = SZ - 1;                // MMA1 runs LA tiles ahead of MMA2 / MMA3
 // The merged X producer loads XK(t) before XM(t - LA), and MMA1 never runs ahead across an item boundary: the last
 // MMA3 of an item needs XM(last), which is issued after XK(last + LA), which needs the stage MMA1(last + LA - SXK) frees.
 static_assert(SXK >= LA, "with fewer XK stages than the MMA1 look-ahead the X producer deadlocks at item boundaries");
-constexpr int SDX = 2;                    // dX staging buffers (TMA reduce-adds in flight)
+constexpr int SDX = SA == 4 ? 1 : 2;      // dX staging buffers (TMA reduce-adds in flight)
 constexpr uint32_t XK_BYTES = 16384 /* bf16 [Xh | Xl] */, XM_BYTES = 16384, YS_BYTES = 32768, AG_BYTES = 32768,
                    DXS_BYTES = 16384 /* dX tile staged for the TMA reduce-add */;
 constexpr uint32_t SMEM_DATA = SXK * XK_BYTES + SXM * XM_BYTES + YS_BYTES + SA * AG_BYTES + SDX * DXS_BYTES;
@@ -140,21 +144,24 @@ constexpr int TRACE_TILES = 96, TRACE_EV = 32, TRACE_CTAS = 160;   // + per-CTA 
 struct ItemIter {
     int t, t_end, n_it;
     int jt, it0, it1;
-    // tile index at cost position  frac = num / den  of the whole pass
+    // tile index at cost position  frac = num / den  of the whole pass.  A feature tile costs its tiles plus the
+    // pipeline drain / refill at its boundary (CB, in the units of tc_cost_cum: a normal tile = 100).
+    static constexpr long long CB = 500;
     static __device__ __forceinline__ int cut(const TcParams& p, unsigned num, unsigned den) {
         const int32_t* cum = p.dp.tc_cost_cum;
         if (num >= den) return p.n_jt * p.n_it;
-        const long long W = (long long)cum[p.n_jt] * p.n_it;        // total cost in (cost x tile) units
-        const long long x = W * num / den;
-        int lo = 0, hi = p.n_jt;                                    // feature tile with cum[jt]*n_it <= x < cum[jt+1]*n_it
+        auto upto = [&](int jt) { return (long long)cum[jt] * p.n_it + CB * jt; };   // cost of the feature tiles before jt
+        const long long x = upto(p.n_jt) * num / den;
+        int lo = 0, hi = p.n_jt;                                    // feature tile with upto(jt) <= x < upto(jt + 1)
         while (hi - lo > 1) {
             const int mid = (lo + hi) >> 1;
-            if ((long long)cum[mid] * p.n_it <= x) lo = mid; else hi = mid;
+            if (upto(mid) <= x) lo = mid; else hi = mid;
         }
         const long long w = cum[lo + 1] - cum[lo];
-        int it = (int)((x - (long long)cum[lo] * p.n_it) / (w > 0 ? w : 1));
+        long long it = (x - upto(lo) - CB) / (w > 0 ? w : 1);
+        if (it < 0) it = 0;
         if (it > p.n_it) it = p.n_it;
-        return lo * p.n_it + it;
+        return lo * p.n_it + (int)it;
     }
     __device__ __forceinline__ explicit ItemIter(const TcParams& p) {
         t = cut(p, blockIdx.x, gridDim.x);
@@ -334,19 +341,24 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXb, const __grid_const
         // flight, the staging buffer of a tile is handed back once the engine has read it.  Pending reduce-adds
         // are flushed at the end of an item -- the drain of the item's last tiles needs the buffers back before
         // the item can complete, and this thread is about to block on the next item's Y operands.
-        constexpr int RLAG = 5;
+        constexpr int RLAG = SDX == 2 ? 5 : 3;
         uint32_t gr = 0;       // next tile whose dX is to be reduced
         auto reduce_tile = [&](int it_r, int xrow0) {
-            const uint32_t sb = gr & 1u;
-            mbar_wait(bar(B_DXS_FULL + sb), (gr >> 1) & 1);
+            const uint32_t sb = gr % SDX;
+            mbar_wait(bar(B_DXS_FULL + sb), (gr / SDX) & 1);
             stamp(gr, 31);
             if (!(DBG && (p.ablate & 16))) {
                 tma_reduce_add_2d(&tmDX, DXS + sb * DXS_BYTES, 0, xrow0 + it_r * BI);
                 if (dp.Kp > 32) tma_reduce_add_2d(&tmDX, DXS + sb * DXS_BYTES + 8192, 32, xrow0 + it_r * BI);
             }
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-            if (gr > 0) mbar_arrive(bar(B_DXS_DONE + (sb ^ 1u)));     // tile gr - 1 has been read
+            if (SDX == 2) {
+                asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                if (gr > 0) mbar_arrive(bar(B_DXS_DONE + (sb ^ 1u)));     // tile gr - 1 has been read
+            } else {
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                mbar_arrive(bar(B_DXS_DONE));
+            }
             stamp(gr, 12);
             ++gr;
         };
@@ -386,7 +398,7 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXb, const __grid_const
             ++q;
         }
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        if (gr > 0) mbar_arrive(bar(B_DXS_DONE + ((gr - 1u) & 1u)));
+        if (SDX == 2 && gr > 0) mbar_arrive(bar(B_DXS_DONE + ((gr - 1u) & 1u)));
         asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // every reduce-add has been performed
       }
       __syncwarp();
@@ -469,8 +481,9 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXb, const __grid_const
         for (ItemIter itx(p); itx.next();) {
             const int it0 = itx.it0, it1 = itx.it1;
             for (int it = it0; it < it1; ++it, ++g) {
-                const uint32_t b = g & 1;
-                uint8_t* const buf = dxs_ptr + b * DXS_BYTES;
+                const uint32_t b = g & 1;                  // dX accumulator
+                const uint32_t sb = g % SDX;               // staging buffer
+                uint8_t* const buf = dxs_ptr + sb * DXS_BYTES;
                 // experiment (PMF_TC_FLAGS bits 8..11 = distance in tiles): L2 prefetch of a later A tile through the LSU
                 if (!BATCH) {
                     const int pf = (p.flags >> 8) & 15;
@@ -496,7 +509,7 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXb, const __grid_const
                 if (lane == 0) mbar_arrive_relaxed(bar(B_DX_EMPTY + b));
                 if (tr) stamp(g, 28);
                 // the reduce-add of tile g - 2 has read this staging buffer (first use: parity 1 passes on a fresh barrier)
-                mbar_wait(bar(B_DXS_DONE + b), ((g >> 1) - 1u) & 1u);
+                mbar_wait(bar(B_DXS_DONE + sb), ((g / SDX) - 1u) & 1u);
                 if (tr) stamp(g, 29);
                 if (!(DBG && (p.ablate & 16))) {
 #pragma unroll
@@ -510,7 +523,7 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXb, const __grid_const
                 }
                 fence_async_smem();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar(B_DXS_FULL + b));
+                if (lane == 0) mbar_arrive(bar(B_DXS_FULL + sb));
                 if (tr) stamp(g, 30);
             }
         }

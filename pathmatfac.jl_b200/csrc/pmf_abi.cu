@@ -330,7 +330,7 @@ int pmf_set_noise(pmf_handle h, int32_t n_ranges, const int32_t* cs, const int32
         // 0.326 ms, all-bernoulli 0.431 ms, all-poisson 0.341 ms; inside the C2 mix the per-CTA clocks put a bernoulli
         // tile at 1.4 and a poisson tile at 1.07 normal tiles), cumulated so that the kernel can cut the tile list into
         // ranges of equal COST, not equal count.
-        static const int kCost[6] = {100, 140, 107, 200, 130, 200};
+        static const int kCost[6] = {100, 146, 106, 200, 130, 200};
         const int n_jt = (h->N + 127) / 128;
         std::vector<int32_t> cum(n_jt + 1, 0);
         for (int jt = 0; jt < n_jt; ++jt) {

@@ -468,7 +468,19 @@ static void multi_pass_grid(const MultiPassParams& mp, int n_sms, int& fb1, int&
     grid = fb2 + vblocks;
 }
 
+// The fused data pass runs with the SM's whole L1 / shared-memory array carved out as shared memory; a kernel that
+// prefers another split in between makes the SMs switch the carve-out twice per epoch (each switch drains the SM).
+// The elementwise passes stream their operands once, so they give the L1 up.
+static void prefer_max_shared_carveout() {
+    static bool done = false;
+    if (done || getenv("PMF_NO_CARVEOUT_HINT")) return;
+    done = true;
+    cudaFuncSetAttribute(multi_pass_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(fused_epoch_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+
 cudaError_t launch_multi_pass(const MultiPassParams& mp, cudaStream_t s, int n_sms) {
+    prefer_max_shared_carveout();
     int fb1, fb2, grid;
     multi_pass_grid(mp, n_sms, fb1, fb2, grid);
     if (grid <= 0) return cudaSuccess;
@@ -478,6 +490,7 @@ cudaError_t launch_multi_pass(const MultiPassParams& mp, cudaStream_t s, int n_s
 
 cudaError_t launch_fused_epoch_pass(const MultiPassParams& mp, const FusedControl& fc, cudaStream_t s, int n_sms) {
     int fb1, fb2, grid;
+    prefer_max_shared_carveout();
     multi_pass_grid(mp, n_sms, fb1, fb2, grid);
     if (grid <= 0) grid = 1;
     fused_epoch_kernel<<<grid, UT, 0, s>>>(mp, fc, fb1, fb2);
