@@ -463,3 +463,35 @@ def test_row_block_missingness_and_binary_export(tmp_path):
     assert np.array_equal(back["batch_of_sample__methylation"][:, 0] - 1, bos["methylation"])
     assert open(tmp_path / "exp" / "feature_views.txt").read().split() == list(model.feature_views)
     assert os.path.getsize(tmp_path / "exp" / "data.bin") == 80 * 50 * 4 and os.path.exists(man)
+
+
+def test_save_load_model_round_trip(tmp_path):
+    """src/model_io.jl:9-19: whole-model save with `data` dropped unless save_data; load gives the model back.  The flat
+    export carries the dataset names of bson_to_hdf.jl:18-71."""
+    rng = np.random.default_rng(3)
+    M, N = 12, 9
+    D = rng.standard_normal((M, N)).astype(np.float32)
+    views = ["a"] * 4 + ["b"] * 5
+    batch = {"a": [1] * 6 + [2] * 6}
+    model = P.PathMatFacModel(D.copy(), K=3, feature_views=views, batch_dict=batch,
+                              sample_conditions=["c1"] * 6 + ["c2"] * 6, lambda_X_l2=1.0)
+    model.matfac.X[...] = rng.standard_normal(model.matfac.X.shape)
+    f = tmp_path / "model.bin"
+    P.save_model(model, f)
+    assert model.data is not None                       # the caller's model keeps its data
+    m2 = P.load_model(f)
+    assert m2.data is None and m2._engine is None
+    assert np.array_equal(m2.matfac.X, model.matfac.X) and np.array_equal(m2.matfac.Y, model.matfac.Y)
+    assert m2.feature_views == model.feature_views and np.array_equal(m2.data_idx, model.data_idx)
+    P.save_model(model, f, save_data=True)
+    assert np.array_equal(P.load_model(f).data, model.data)
+    arr = P.model_arrays(model)
+    for k in ("X", "Y", "logsigma", "mu", "feature_ids", "sample_ids", "data_idx", "logdelta/values_1", "theta/values_1"):
+        assert k in arr, k
+    assert arr["X"].shape == (3, M) and arr["logdelta/values_1"].shape[1] == 4
+    P.write_model_arrays(tmp_path / "arrays.npz", model)
+    z = np.load(tmp_path / "arrays.npz")
+    assert np.array_equal(z["theta__values_1"], arr["theta/values_1"])
+    with pytest.raises(ValueError):
+        (tmp_path / "junk.bin").write_bytes(__import__("pickle").dumps({"format": "other"}))
+        P.load_model(tmp_path / "junk.bin")
