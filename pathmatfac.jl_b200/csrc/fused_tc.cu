@@ -721,9 +721,9 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXb, const __grid_const
                 if (itx.peek_jt() >= 0) prefetch_item(itx.peek_jt());
             }
 
-            // per-entry math on 16 consecutive samples: z[] (TMEM columns) in, dloss/dz (TF32-rounded bits) out
-            // per-entry math on 16 consecutive samples: z[] (TMEM columns) in, dloss/dz (TF32-rounded bits) out
-            auto epi16 = [&](uint32_t (&z)[16], const float (&a)[16]) {
+            // per-entry math on EPC consecutive samples: z[] (TMEM columns) in, dloss/dz (TF32-rounded bits) out
+            constexpr int EPC = 8;
+            auto epi8 = [&](uint32_t (&z)[EPC], const float (&a)[EPC]) {
                 // dmu_acc / loss_acc collect the unweighted sums; the column weight w_j (a per-thread
                 // constant) is applied at the item flush.
                 auto tally = [&](float gv, uint32_t zraw) -> uint32_t {
@@ -737,7 +737,7 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXb, const __grid_const
                 };
                 if (dist == DIST_NORMAL) {
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) {
+                    for (int e = 0; e < EPC; ++e) {
                         float d = fmaf(__uint_as_float(z[e]), sd, mt) - a[e];
                         d = fabsf(a[e]) < INFINITY ? d : 0.f;        // NaN / Inf => missing (ordered compare)
                         loss_acc = fmaf(d, d, loss_acc);              // (z-a)^2, halved and weighted at flush
@@ -747,7 +747,7 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXb, const __grid_const
                     // softplus(z) - a z ; sigmoid(z) - a, sharing e = exp(-|z|); a missing entry makes both NaN
                     // and is masked away once at the end
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) {
+                    for (int e = 0; e < EPC; ++e) {
                         const uint32_t m = obs_mask(a[e]);
                         float z4 = fmaf(__uint_as_float(z[e]), sd, mt);
                         float ex = ex2_fast(fabsf(z4) * -1.4426950408889634f);
@@ -761,7 +761,7 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXb, const __grid_const
                     }
                 } else if (dist == DIST_POISSON) {
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) {
+                    for (int e = 0; e < EPC; ++e) {
                         const uint32_t m = obs_mask(a[e]);
                         float z4 = fmaf(__uint_as_float(z[e]), sd, mt);
                         float ez = ex2_fast(z4 * 1.4426950408889634f);
@@ -775,7 +775,7 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXb, const __grid_const
                     // here, so that nothing of it is live outside this rare branch
                     float t1s = 0.f, t2s = 0.f;
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) {
+                    for (int e = 0; e < EPC; ++e) {
                         float z4 = fmaf(__uint_as_float(z[e]), sd, mt);
                         float2 lg = noise_eval_slow(dist, z4, a[e], th_range, dp.ordinal_eps, dp.hinge_margin);
                         if (THR && dp.dthr != nullptr && is_ordinal(dist)) {
@@ -802,45 +802,52 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXb, const __grid_const
                 if (tr) stamp(g, 7);
                 const uint32_t zt = tm + lane_addr + TM_Z0 + 64 * rz.s + 32 * h32;
                 uint8_t* abox = ag_ptr0 + ra.s * AG_BYTES + tile_box;
-#pragma unroll 1
-                for (int hh = 0; hh < 2; ++hh) {
-                    uint32_t z[16];
-                    float a[16];
-                    TMEM_LD16(zt + 16 * hh, z);
-                    // The 32-byte-atom swizzle leaves rows r and r+4 of a quarter-warp phase in the same banks.
-                    // Lanes 4..7 of every 8 therefore take the two 16-byte halves of a 32-byte pair in the
-                    // opposite order (address ^ 16): conflict-free 128-bit accesses, undone by register selects.
-                    {
-                        float4 raw[4];
+                // The thread's 32 samples go through in four chunks of 8, software pipelined: the TMEM and shared-memory
+                // loads of chunk c + 1 are issued before the math of chunk c, so their latency (TMEM read port, shared-
+                // memory contention with the tensor core and TMA) is off the tile's critical path.
+                // The 32-byte-atom swizzle leaves rows r and r+4 of a quarter-warp phase in the same banks.  Lanes 4..7
+                // of every 8 therefore take the two 16-byte halves of a 32-byte pair in the opposite order
+                // (address ^ 16): conflict-free 128-bit accesses, undone by register selects.
+                uint32_t zb[2][EPC];
+                float4 rawb[2][2];
+                auto load_chunk = [&](int c, uint32_t (&zc)[EPC], float4 (&rc)[2]) {
+                    TMEM_LD8(zt + EPC * c, zc);
 #pragma unroll
-                        for (int v = 0; v < 4; ++v)
-                            raw[v] = *reinterpret_cast<const float4*>(abox + (chunk_off(4 * hh + v) ^ half_swap));
+                    for (int v = 0; v < 2; ++v)
+                        rc[v] = *reinterpret_cast<const float4*>(abox + (chunk_off(2 * c + v) ^ half_swap));
+                };
+                load_chunk(0, zb[0], rawb[0]);
 #pragma unroll
-                        for (int v = 0; v < 4; ++v) {
-                            const float4 a4 = make_float4(swapped ? raw[v ^ 1].x : raw[v].x, swapped ? raw[v ^ 1].y : raw[v].y,
-                                                          swapped ? raw[v ^ 1].z : raw[v].z, swapped ? raw[v ^ 1].w : raw[v].w);
-                            a[4 * v] = a4.x; a[4 * v + 1] = a4.y; a[4 * v + 2] = a4.z; a[4 * v + 3] = a4.w;
-                        }
-                    }
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t (&z)[EPC] = zb[c & 1];
+                    float4 (&raw)[2] = rawb[c & 1];
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    if (tr && (p.flags & 64)) stamp(g, 16 + 3 * hh);
-                    if (BATCH) {
-                        const uint32_t id = hh == 0 ? (ids & 0xffffu) : (ids >> 16);
+                    if (c < 3) load_chunk(c + 1, zb[(c + 1) & 1], rawb[(c + 1) & 1]);
+                    float a[EPC];
+#pragma unroll
+                    for (int v = 0; v < 2; ++v) {
+                        const float4 a4 = make_float4(swapped ? raw[v ^ 1].x : raw[v].x, swapped ? raw[v ^ 1].y : raw[v].y,
+                                                      swapped ? raw[v ^ 1].z : raw[v].z, swapped ? raw[v ^ 1].w : raw[v].w);
+                        a[4 * v] = a4.x; a[4 * v + 1] = a4.y; a[4 * v + 2] = a4.z; a[4 * v + 3] = a4.w;
+                    }
+                    if (tr && (p.flags & 64) && (c & 1) == 0) stamp(g, 16 + 3 * (c >> 1));
+                    if (BATCH && (c & 1) == 0) {
+                        const uint32_t id = c == 0 ? (ids & 0xffffu) : (ids >> 16);
                         if (id != cur_b) enter_segment(id);
                     }
-                    if (!(DBG && (p.ablate & 8))) epi16(z, a);
-                    if (tr && (p.flags & 64)) stamp(g, 17 + 3 * hh);
+                    if (!(DBG && (p.ablate & 8))) epi8(z, a);
+                    if (tr && (p.flags & 64) && (c & 1) == 1) stamp(g, 17 + 3 * (c >> 1));
                     // dloss/dz back to TMEM in place of Z (A operand of MMA3) and over the A values this thread
                     // read (MN-major A operand of MMA2): same addresses, 128-bit stores, no transposition
-                    TMEM_ST16(zt + 16 * hh, z);
+                    TMEM_ST8(zt + EPC * c, z);
 #pragma unroll
-                    for (int v = 0; v < 4; ++v) {
+                    for (int v = 0; v < 2; ++v) {
                         const int w = v ^ 1;
-                        *reinterpret_cast<uint4*>(abox + (chunk_off(4 * hh + v) ^ half_swap)) =
+                        *reinterpret_cast<uint4*>(abox + (chunk_off(2 * c + v) ^ half_swap)) =
                             make_uint4(swapped ? z[4 * w] : z[4 * v], swapped ? z[4 * w + 1] : z[4 * v + 1],
                                        swapped ? z[4 * w + 2] : z[4 * v + 2], swapped ? z[4 * w + 3] : z[4 * v + 3]);
                     }
-                    if (tr && (p.flags & 64)) stamp(g, 18 + 3 * hh);
+                    if (tr && (p.flags & 64) && (c & 1) == 1) stamp(g, 18 + 3 * (c >> 1));
                 }
                 if (tr) stamp(g, 8);
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");

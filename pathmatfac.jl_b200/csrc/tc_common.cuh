@@ -166,6 +166,10 @@ __host__ __device__ constexpr uint32_t umma_idesc(int M, int N, bool a_mn, bool 
                  ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]),        \
                  "r"(r[7]) : "memory")
 
+#define TMEM_LD8(taddr, r)                                                                                        \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"                          \
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])   \
+                 : "r"(taddr))
 #define TMEM_LD16(taddr, r)                                                                                       \
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "                                                        \
                  "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"                                  \
