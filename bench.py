@@ -47,8 +47,11 @@ def parse():
 def ncu_traffic():
     """DRAM bytes (read + write) per launch of the fused data pass, from the committed `ncu --set full`
     capture of the same kernel on the same workload (profiles/); None when no capture is committed."""
-    path = os.path.join(ROOT, "profiles", "r1_tc_final_ncu_summary.csv")
-    if not os.path.exists(path):
+    for name in ("r2_c2_tc_final_ncu_summary.csv", "r1_tc_final_ncu_summary.csv"):     # newest capture first
+        path = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(path):
+            break
+    else:
         return None, None
     rd = wr = None
     for line in open(path):
@@ -59,7 +62,7 @@ def ncu_traffic():
             wr = float(f[2]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[f[1]]
     if rd is None or wr is None:
         return None, None
-    return rd + wr, "profiles/r1_tc_final_ncu_summary.csv (ncu --set full, one launch at the C2 shape)"
+    return rd + wr, f"profiles/{name} (ncu --set full, one launch at the C2 shape)"
 
 
 def peaks():
