@@ -722,7 +722,8 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXb, const __grid_const
             }
 
             // per-entry math on EPC consecutive samples: z[] (TMEM columns) in, dloss/dz (TF32-rounded bits) out
-            constexpr int EPC = 8;
+            // (BATCH: 16 -- a chunk never straddles a batch segment, and the pipelined form below measured slower there)
+            constexpr int EPC = BATCH ? 16 : 8;
             auto epi8 = [&](uint32_t (&z)[EPC], const float (&a)[EPC]) {
                 // dmu_acc / loss_acc collect the unweighted sums; the column weight w_j (a per-thread
                 // constant) is applied at the item flush.
@@ -802,6 +803,48 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXb, const __grid_const
                 if (tr) stamp(g, 7);
                 const uint32_t zt = tm + lane_addr + TM_Z0 + 64 * rz.s + 32 * h32;
                 uint8_t* abox = ag_ptr0 + ra.s * AG_BYTES + tile_box;
+                if constexpr (BATCH) {
+#pragma unroll 1
+                for (int hh = 0; hh < 2; ++hh) {
+                    uint32_t z[16];
+                    float a[16];
+                    TMEM_LD16(zt + 16 * hh, z);
+                    // The 32-byte-atom swizzle leaves rows r and r+4 of a quarter-warp phase in the same banks.
+                    // Lanes 4..7 of every 8 therefore take the two 16-byte halves of a 32-byte pair in the
+                    // opposite order (address ^ 16): conflict-free 128-bit accesses, undone by register selects.
+                    {
+                        float4 raw[4];
+#pragma unroll
+                        for (int v = 0; v < 4; ++v)
+                            raw[v] = *reinterpret_cast<const float4*>(abox + (chunk_off(4 * hh + v) ^ half_swap));
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) {
+                            const float4 a4 = make_float4(swapped ? raw[v ^ 1].x : raw[v].x, swapped ? raw[v ^ 1].y : raw[v].y,
+                                                          swapped ? raw[v ^ 1].z : raw[v].z, swapped ? raw[v ^ 1].w : raw[v].w);
+                            a[4 * v] = a4.x; a[4 * v + 1] = a4.y; a[4 * v + 2] = a4.z; a[4 * v + 3] = a4.w;
+                        }
+                    }
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (tr && (p.flags & 64)) stamp(g, 16 + 3 * hh);
+                    if (BATCH) {
+                        const uint32_t id = hh == 0 ? (ids & 0xffffu) : (ids >> 16);
+                        if (id != cur_b) enter_segment(id);
+                    }
+                    if (!(DBG && (p.ablate & 8))) epi8(z, a);
+                    if (tr && (p.flags & 64)) stamp(g, 17 + 3 * hh);
+                    // dloss/dz back to TMEM in place of Z (A operand of MMA3) and over the A values this thread
+                    // read (MN-major A operand of MMA2): same addresses, 128-bit stores, no transposition
+                    TMEM_ST16(zt + 16 * hh, z);
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) {
+                        const int w = v ^ 1;
+                        *reinterpret_cast<uint4*>(abox + (chunk_off(4 * hh + v) ^ half_swap)) =
+                            make_uint4(swapped ? z[4 * w] : z[4 * v], swapped ? z[4 * w + 1] : z[4 * v + 1],
+                                       swapped ? z[4 * w + 2] : z[4 * v + 2], swapped ? z[4 * w + 3] : z[4 * v + 3]);
+                    }
+                    if (tr && (p.flags & 64)) stamp(g, 18 + 3 * hh);
+                }
+                } else {
                 // The thread's 32 samples go through in four chunks of 8, software pipelined: the TMEM and shared-memory
                 // loads of chunk c + 1 are issued before the math of chunk c, so their latency (TMEM read port, shared-
                 // memory contention with the tensor core and TMA) is off the tile's critical path.
@@ -848,6 +891,7 @@ data_pass_tc_kernel(const __grid_constant__ CUtensorMap tmXb, const __grid_const
                                        swapped ? z[4 * w + 2] : z[4 * v + 2], swapped ? z[4 * w + 3] : z[4 * v + 3]);
                     }
                     if (tr && (p.flags & 64) && (c & 1) == 1) stamp(g, 18 + 3 * (c >> 1));
+                }
                 }
                 if (tr) stamp(g, 8);
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
