@@ -404,7 +404,7 @@ def main():
 
     # ---- CPU baseline beside it (bounded sample, rank 0) -----------------------------------------------
     cpu = None
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:         # reported at N = 1 only (the other ranks would idle at the barrier meanwhile)
         n_it, n_warm = 8, 1
         Ms = cpu_block(M, n_it + n_warm)
         sec = cpu_iterations(model, range(0, Ms), n_it, n_warm)

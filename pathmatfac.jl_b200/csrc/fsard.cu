@@ -187,25 +187,25 @@ extern "C" int pmf_fsard_update_A(pmf_handle h, int32_t col_start, int32_t col_s
         cudaFree(d_A); cudaFree(d_Abest); cudaFree(d_ssq); cudaFree(d_G); cudaFree(d_lam); cudaFree(d_c);
     };
     if (!ok) { cleanup(); return bad(PMF_ERR_ALLOC, "device allocation failed"); }
-    cudaMemcpy(d_srp, S_rp, (size_t)(L + 1) * 4, cudaMemcpyHostToDevice);
-    cudaMemcpy(d_trp, t_rp.data(), (size_t)(Nv + 1) * 4, cudaMemcpyHostToDevice);
+    cudaMemcpyAsync(d_srp, S_rp, (size_t)(L + 1) * 4, cudaMemcpyHostToDevice, s);
+    cudaMemcpyAsync(d_trp, t_rp.data(), (size_t)(Nv + 1) * 4, cudaMemcpyHostToDevice, s);
     if (nnz > 0) {
-        cudaMemcpy(d_scol, S_col, (size_t)nnz * 4, cudaMemcpyHostToDevice);
-        cudaMemcpy(d_sval, S_val, (size_t)nnz * 4, cudaMemcpyHostToDevice);
-        cudaMemcpy(d_tcol, t_col.data(), (size_t)nnz * 4, cudaMemcpyHostToDevice);
-        cudaMemcpy(d_tval, t_val.data(), (size_t)nnz * 4, cudaMemcpyHostToDevice);
+        cudaMemcpyAsync(d_scol, S_col, (size_t)nnz * 4, cudaMemcpyHostToDevice, s);
+        cudaMemcpyAsync(d_sval, S_val, (size_t)nnz * 4, cudaMemcpyHostToDevice, s);
+        cudaMemcpyAsync(d_tcol, t_col.data(), (size_t)nnz * 4, cudaMemcpyHostToDevice, s);
+        cudaMemcpyAsync(d_tval, t_val.data(), (size_t)nnz * 4, cudaMemcpyHostToDevice, s);
     }
     // A is zeroed first like update_A! (featureset_ard.jl:286); ssq_grad is the optimiser's state
-    cudaMemset(d_A, 0, (size_t)L * Kp * 4);
-    cudaMemset(d_Abest, 0, (size_t)L * Kp * 4);
-    cudaMemset(d_ssq, 0, (size_t)L * Kp * 4);
-    cudaMemcpy2D(d_ssq, (size_t)Kp * 4, ssq_host, (size_t)K * 4, (size_t)K * 4, L, cudaMemcpyHostToDevice);
+    cudaMemsetAsync(d_A, 0, (size_t)L * Kp * 4, s);
+    cudaMemsetAsync(d_Abest, 0, (size_t)L * Kp * 4, s);
+    cudaMemsetAsync(d_ssq, 0, (size_t)L * Kp * 4, s);
+    cudaMemcpy2DAsync(d_ssq, (size_t)Kp * 4, ssq_host, (size_t)K * 4, (size_t)K * 4, L, cudaMemcpyHostToDevice, s);
     std::vector<float> lam(Kp, 0.f);
     std::memcpy(lam.data(), lambda_K, (size_t)K * 4);
-    cudaMemcpy(d_lam, lam.data(), (size_t)Kp * 4, cudaMemcpyHostToDevice);
+    cudaMemcpyAsync(d_lam, lam.data(), (size_t)Kp * 4, cudaMemcpyHostToDevice, s);
     FsCtrl c0;
     std::memset(&c0, 0, sizeof c0);
-    cudaMemcpy(d_c, &c0, sizeof c0, cudaMemcpyHostToDevice);
+    cudaMemcpyAsync(d_c, &c0, sizeof c0, cudaMemcpyHostToDevice, s);
 
     const float beta0 = alpha0 - 1.0f;
     const float* Yv = h->Y + (size_t)col_start * Kp;
@@ -239,7 +239,7 @@ extern "C" int pmf_fsard_update_A(pmf_handle h, int32_t col_start, int32_t col_s
     // A .= A_best ; beta[:, cr] = beta0 (v0 + A'S)   (featureset_ard.jl:272, :292)
     c0 = hc;
     c0.stop = 0; c0.cur_smooth = 0.0;
-    cudaMemcpy(d_c, &c0, sizeof c0, cudaMemcpyHostToDevice);
+    cudaMemcpyAsync(d_c, &c0, sizeof c0, cudaMemcpyHostToDevice, s);
     fs_beta_kernel<<<gb, FT, 0, s>>>(Nv, K, Kp, d_trp, d_tcol, d_tval, d_Abest, Yv, alpha, beta0, v0, beta_out, d_G, d_c, 0);
     h->launches += 1;
     cudaMemcpy2DAsync(A_host, (size_t)K * 4, d_Abest, (size_t)Kp * 4, (size_t)K * 4, L, cudaMemcpyDeviceToHost, s);

@@ -50,6 +50,14 @@ static int fail(pmf_model_s* h, int code, const char* fmt, ...) {
         }                                                                       \
     } while (0)
 
+// Every host <-> device copy of the ABI runs on the handle's stream and completes before the call returns: the
+// stream is non-blocking, so the legacy-stream cudaMemcpy / cudaMemset would not be ordered against its kernels
+// (a pageable H2D cudaMemcpy may return before its DMA has landed).
+static cudaError_t copy_sync(cudaStream_t s, void* dst, const void* src, size_t bytes, cudaMemcpyKind kind) {
+    cudaError_t e = cudaMemcpyAsync(dst, src, bytes, kind, s);
+    return e != cudaSuccess ? e : cudaStreamSynchronize(s);
+}
+
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
 template <class T>
@@ -223,13 +231,13 @@ int pmf_create(const pmf_dims* d, pmf_handle* out) {
         pmf_destroy(h);
         return fail(nullptr, PMF_ERR_ALLOC, "device allocation failed (A needs %.2f GB)", (double)h->N * h->lda * 4e-9);
     }
-    cudaMemset(h->X, 0, xk * 4); cudaMemset(h->Y, 0, yk * 4);
-    cudaMemset(h->colinfo, 0, (size_t)h->Np * 4);
-    cudaMemset(h->thresholds, 0, 16);
-    cudaMemset(h->ctrl_base, 0, 2 * sizeof(FitControl));
-    cudaMemset(h->scalars_base, 0, 4 * SC_COUNT * sizeof(double));
+    cudaMemsetAsync(h->X, 0, xk * 4, h->stream); cudaMemsetAsync(h->Y, 0, yk * 4, h->stream);
+    cudaMemsetAsync(h->colinfo, 0, (size_t)h->Np * 4, h->stream);
+    cudaMemsetAsync(h->thresholds, 0, 16, h->stream);
+    cudaMemsetAsync(h->ctrl_base, 0, 2 * sizeof(FitControl), h->stream);
+    cudaMemsetAsync(h->scalars_base, 0, 4 * SC_COUNT * sizeof(double), h->stream);
     std::vector<float> ones(h->Np, 1.f);
-    cudaMemcpy(h->weight, ones.data(), (size_t)h->Np * 4, cudaMemcpyHostToDevice);
+    copy_sync(h->stream, h->weight, ones.data(), (size_t)h->Np * 4, cudaMemcpyHostToDevice);
     cudaMallocHost((void**)&h->ctrl_host, sizeof(FitControl));
     int rc = h->realloc_vectors(0);   // no batch views yet
     if (rc != 0) { pmf_destroy(h); return fail(nullptr, PMF_ERR_ALLOC, "device allocation failed"); }
@@ -322,9 +330,9 @@ int pmf_set_noise(pmf_handle h, int32_t n_ranges, const int32_t* cs, const int32
     CU(h, dev_alloc(&h->thresholds, (size_t)4 * n_ranges));
     std::vector<float> th(4 * (size_t)n_ranges, 0.f);
     if (thresholds) std::memcpy(th.data(), thresholds, th.size() * 4);
-    CU(h, cudaMemcpy(h->thresholds, th.data(), th.size() * 4, cudaMemcpyHostToDevice));
-    CU(h, cudaMemcpy(h->colinfo, ci.data(), (size_t)h->Np * 4, cudaMemcpyHostToDevice));
-    if (weight) CU(h, cudaMemcpy(h->weight, weight, (size_t)h->N * 4, cudaMemcpyHostToDevice));
+    CU(h, copy_sync(h->stream, h->thresholds, th.data(), th.size() * 4, cudaMemcpyHostToDevice));
+    CU(h, copy_sync(h->stream, h->colinfo, ci.data(), (size_t)h->Np * 4, cudaMemcpyHostToDevice));
+    if (weight) CU(h, copy_sync(h->stream, h->weight, weight, (size_t)h->N * 4, cudaMemcpyHostToDevice));
     {
         // Relative cost of one tile of the tcgen05 data pass per 128-feature tile (measured at the C2 shape: all-normal
         // 0.326 ms, all-bernoulli 0.431 ms, all-poisson 0.341 ms; inside the C2 mix the per-CTA clocks put a bernoulli
@@ -353,7 +361,7 @@ int pmf_set_noise(pmf_handle h, int32_t n_ranges, const int32_t* cs, const int32
         }
         dev_free(h->tc_cost_cum);
         CU(h, dev_alloc(&h->tc_cost_cum, (size_t)n_jt + 1));
-        CU(h, cudaMemcpy(h->tc_cost_cum, cum.data(), ((size_t)n_jt + 1) * 4, cudaMemcpyHostToDevice));
+        CU(h, copy_sync(h->stream, h->tc_cost_cum, cum.data(), ((size_t)n_jt + 1) * 4, cudaMemcpyHostToDevice));
     }
     h->n_ranges = n_ranges;
     h->has_ordinal = false;
@@ -366,22 +374,22 @@ int pmf_get_thresholds(pmf_handle h, int32_t n_ranges, float* thresholds) {
     CHECK_H(h);
     if (!thresholds || n_ranges != h->n_ranges) return fail(h, PMF_ERR_ARG, "pmf_get_thresholds: %d ranges given, the model has %d", n_ranges, h->n_ranges);
     CU(h, cudaStreamSynchronize(h->stream));
-    CU(h, cudaMemcpy(thresholds, h->thresholds, (size_t)4 * n_ranges * 4, cudaMemcpyDeviceToHost));
+    CU(h, copy_sync(h->stream, thresholds, h->thresholds, (size_t)4 * n_ranges * 4, cudaMemcpyDeviceToHost));
     return PMF_OK;
 }
 
 int pmf_set_col_params(pmf_handle h, const float* logsigma, const float* mu) {
     CHECK_H(h);
-    if (logsigma) CU(h, cudaMemcpy(h->logsigma(), logsigma, (size_t)h->N * 4, cudaMemcpyHostToDevice));
-    if (mu) CU(h, cudaMemcpy(h->mu(), mu, (size_t)h->N * 4, cudaMemcpyHostToDevice));
+    if (logsigma) CU(h, copy_sync(h->stream, h->logsigma(), logsigma, (size_t)h->N * 4, cudaMemcpyHostToDevice));
+    if (mu) CU(h, copy_sync(h->stream, h->mu(), mu, (size_t)h->N * 4, cudaMemcpyHostToDevice));
     return PMF_OK;
 }
 
 int pmf_get_col_params(pmf_handle h, float* logsigma, float* mu) {
     CHECK_H(h);
     CU(h, cudaStreamSynchronize(h->stream));
-    if (logsigma) CU(h, cudaMemcpy(logsigma, h->logsigma(), (size_t)h->N * 4, cudaMemcpyDeviceToHost));
-    if (mu) CU(h, cudaMemcpy(mu, h->mu(), (size_t)h->N * 4, cudaMemcpyDeviceToHost));
+    if (logsigma) CU(h, copy_sync(h->stream, logsigma, h->logsigma(), (size_t)h->N * 4, cudaMemcpyDeviceToHost));
+    if (mu) CU(h, copy_sync(h->stream, mu, h->mu(), (size_t)h->N * 4, cudaMemcpyDeviceToHost));
     return PMF_OK;
 }
 
@@ -405,8 +413,8 @@ int pmf_set_batch_layout(pmf_handle h, int32_t n_views, const int32_t* cs, const
     CU(h, cudaStreamSynchronize(h->stream));
     // keep logsigma / mu across the re-allocation
     std::vector<float> ls(h->N), mu(h->N);
-    CU(h, cudaMemcpy(ls.data(), h->logsigma(), (size_t)h->N * 4, cudaMemcpyDeviceToHost));
-    CU(h, cudaMemcpy(mu.data(), h->mu(), (size_t)h->N * 4, cudaMemcpyDeviceToHost));
+    CU(h, copy_sync(h->stream, ls.data(), h->logsigma(), (size_t)h->N * 4, cudaMemcpyDeviceToHost));
+    CU(h, copy_sync(h->stream, mu.data(), h->mu(), (size_t)h->N * 4, cudaMemcpyDeviceToHost));
     h->views.clear();
     int64_t off = 0;
     int prev_end = 0, nb_max = 0;
@@ -422,8 +430,8 @@ int pmf_set_batch_layout(pmf_handle h, int32_t n_views, const int32_t* cs, const
     if (off > (int64_t)INT32_MAX) return fail(h, PMF_ERR_ARG, "batch table too large");
     h->nb_max = nb_max;
     if (h->realloc_vectors((int)off) != 0) return fail(h, PMF_ERR_ALLOC, "device allocation failed");
-    CU(h, cudaMemcpy(h->logsigma(), ls.data(), (size_t)h->N * 4, cudaMemcpyHostToDevice));
-    CU(h, cudaMemcpy(h->mu(), mu.data(), (size_t)h->N * 4, cudaMemcpyHostToDevice));
+    CU(h, copy_sync(h->stream, h->logsigma(), ls.data(), (size_t)h->N * 4, cudaMemcpyHostToDevice));
+    CU(h, copy_sync(h->stream, h->mu(), mu.data(), (size_t)h->N * 4, cudaMemcpyHostToDevice));
     dev_free(h->bcol_off); dev_free(h->bcol_view); dev_free(h->bcol_nb); dev_free(h->batch_of_sample);
     h->free_tc_plan();
     if (n_views > 0) {
@@ -443,10 +451,10 @@ int pmf_set_batch_layout(pmf_handle h, int32_t n_views, const int32_t* cs, const
             }
         CU(h, dev_alloc(&h->bcol_off, h->Np)); CU(h, dev_alloc(&h->bcol_view, h->Np)); CU(h, dev_alloc(&h->bcol_nb, h->Np));
         CU(h, dev_alloc(&h->batch_of_sample, b.size()));
-        CU(h, cudaMemcpy(h->bcol_off, coff.data(), (size_t)h->Np * 4, cudaMemcpyHostToDevice));
-        CU(h, cudaMemcpy(h->bcol_view, cview.data(), (size_t)h->Np * 4, cudaMemcpyHostToDevice));
-        CU(h, cudaMemcpy(h->bcol_nb, cnb.data(), (size_t)h->Np * 4, cudaMemcpyHostToDevice));
-        CU(h, cudaMemcpy(h->batch_of_sample, b.data(), b.size() * 4, cudaMemcpyHostToDevice));
+        CU(h, copy_sync(h->stream, h->bcol_off, coff.data(), (size_t)h->Np * 4, cudaMemcpyHostToDevice));
+        CU(h, copy_sync(h->stream, h->bcol_view, cview.data(), (size_t)h->Np * 4, cudaMemcpyHostToDevice));
+        CU(h, copy_sync(h->stream, h->bcol_nb, cnb.data(), (size_t)h->Np * 4, cudaMemcpyHostToDevice));
+        CU(h, copy_sync(h->stream, h->batch_of_sample, b.data(), b.size() * 4, cudaMemcpyHostToDevice));
         h->bos_host.assign(bos, bos + (size_t)n_views * h->M);
     } else {
         h->bos_host.clear();
@@ -465,8 +473,8 @@ int pmf_set_batch_values(pmf_handle h, int32_t v, const float* logdelta, const f
     if (check_view(h, v)) return PMF_ERR_ARG;
     const BatchView& bv = h->views[v];
     size_t n = (size_t)(bv.col_stop - bv.col_start) * bv.n_batches;
-    if (logdelta) CU(h, cudaMemcpy(h->logdelta() + bv.offset, logdelta, n * 4, cudaMemcpyHostToDevice));
-    if (theta) CU(h, cudaMemcpy(h->theta() + bv.offset, theta, n * 4, cudaMemcpyHostToDevice));
+    if (logdelta) CU(h, copy_sync(h->stream, h->logdelta() + bv.offset, logdelta, n * 4, cudaMemcpyHostToDevice));
+    if (theta) CU(h, copy_sync(h->stream, h->theta() + bv.offset, theta, n * 4, cudaMemcpyHostToDevice));
     return PMF_OK;
 }
 
@@ -476,8 +484,8 @@ int pmf_get_batch_values(pmf_handle h, int32_t v, float* logdelta, float* theta)
     CU(h, cudaStreamSynchronize(h->stream));
     const BatchView& bv = h->views[v];
     size_t n = (size_t)(bv.col_stop - bv.col_start) * bv.n_batches;
-    if (logdelta) CU(h, cudaMemcpy(logdelta, h->logdelta() + bv.offset, n * 4, cudaMemcpyDeviceToHost));
-    if (theta) CU(h, cudaMemcpy(theta, h->theta() + bv.offset, n * 4, cudaMemcpyDeviceToHost));
+    if (logdelta) CU(h, copy_sync(h->stream, logdelta, h->logdelta() + bv.offset, n * 4, cudaMemcpyDeviceToHost));
+    if (theta) CU(h, copy_sync(h->stream, theta, h->theta() + bv.offset, n * 4, cudaMemcpyDeviceToHost));
     return PMF_OK;
 }
 
@@ -487,8 +495,8 @@ int pmf_get_batch_grads(pmf_handle h, int32_t v, float* dlogdelta, float* dtheta
     CU(h, cudaStreamSynchronize(h->stream));
     const BatchView& bv = h->views[v];
     size_t n = (size_t)(bv.col_stop - bv.col_start) * bv.n_batches;
-    if (dlogdelta) CU(h, cudaMemcpy(dlogdelta, h->g_logdelta() + bv.offset, n * 4, cudaMemcpyDeviceToHost));
-    if (dtheta) CU(h, cudaMemcpy(dtheta, h->g_theta() + bv.offset, n * 4, cudaMemcpyDeviceToHost));
+    if (dlogdelta) CU(h, copy_sync(h->stream, dlogdelta, h->g_logdelta() + bv.offset, n * 4, cudaMemcpyDeviceToHost));
+    if (dtheta) CU(h, copy_sync(h->stream, dtheta, h->g_theta() + bv.offset, n * 4, cudaMemcpyDeviceToHost));
     return PMF_OK;
 }
 
@@ -523,7 +531,7 @@ int pmf_set_reg_l2(pmf_handle h, int32_t which, const float* w, float p) {
     dev_free(r.l2_w);
     auto o = pad_scale(w, h->K, h->Kp, p);
     CU(h, dev_alloc(&r.l2_w, h->Kp));
-    CU(h, cudaMemcpy(r.l2_w, o.data(), (size_t)h->Kp * 4, cudaMemcpyHostToDevice));
+    CU(h, copy_sync(h->stream, r.l2_w, o.data(), (size_t)h->Kp * 4, cudaMemcpyHostToDevice));
     return PMF_OK;
 }
 
@@ -542,8 +550,8 @@ int pmf_set_reg_group(pmf_handle h, int32_t which, int32_t ng, const int32_t* st
     SideReg& r = h->reg[which];
     dev_free(r.group_id); dev_free(r.group_w);
     CU(h, dev_alloc(&r.group_id, n)); CU(h, dev_alloc(&r.group_w, gw.size()));
-    CU(h, cudaMemcpy(r.group_id, gid.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
-    CU(h, cudaMemcpy(r.group_w, gw.data(), gw.size() * 4, cudaMemcpyHostToDevice));
+    CU(h, copy_sync(h->stream, r.group_id, gid.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
+    CU(h, copy_sync(h->stream, r.group_w, gw.data(), gw.size() * 4, cudaMemcpyHostToDevice));
     return PMF_OK;
 }
 
@@ -558,8 +566,8 @@ int pmf_set_reg_sel_l1(pmf_handle h, int32_t which, const uint8_t* idx, const fl
     dev_free(r.l1_mask); dev_free(r.l1_w);
     auto o = pad_scale(w, h->K, h->Kp, p);
     CU(h, dev_alloc(&r.l1_mask, m.size())); CU(h, dev_alloc(&r.l1_w, h->Kp));
-    CU(h, cudaMemcpy(r.l1_mask, m.data(), m.size(), cudaMemcpyHostToDevice));
-    CU(h, cudaMemcpy(r.l1_w, o.data(), (size_t)h->Kp * 4, cudaMemcpyHostToDevice));
+    CU(h, copy_sync(h->stream, r.l1_mask, m.data(), m.size(), cudaMemcpyHostToDevice));
+    CU(h, copy_sync(h->stream, r.l1_w, o.data(), (size_t)h->Kp * 4, cudaMemcpyHostToDevice));
     return PMF_OK;
 }
 
@@ -577,8 +585,8 @@ int pmf_set_reg_ard(pmf_handle h, int32_t which, int32_t nr, const int32_t* st, 
     SideReg& r = h->reg[which];
     dev_free(r.ard_alpha); dev_free(r.ard_beta_row); dev_free(r.ard_beta_full);
     CU(h, dev_alloc(&r.ard_alpha, n)); CU(h, dev_alloc(&r.ard_beta_row, n));
-    CU(h, cudaMemcpy(r.ard_alpha, a.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
-    CU(h, cudaMemcpy(r.ard_beta_row, b.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
+    CU(h, copy_sync(h->stream, r.ard_alpha, a.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
+    CU(h, copy_sync(h->stream, r.ard_beta_row, b.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
     return PMF_OK;
 }
 
@@ -590,9 +598,9 @@ int pmf_set_reg_fsard(pmf_handle h, int32_t which, const float* alpha, const flo
     SideReg& r = h->reg[which];
     dev_free(r.ard_alpha); dev_free(r.ard_beta_row); dev_free(r.ard_beta_full);
     CU(h, dev_alloc(&r.ard_alpha, n)); CU(h, dev_alloc(&r.ard_beta_full, (size_t)npad * h->Kp));
-    CU(h, cudaMemcpy(r.ard_alpha, alpha, (size_t)n * 4, cudaMemcpyHostToDevice));
+    CU(h, copy_sync(h->stream, r.ard_alpha, alpha, (size_t)n * 4, cudaMemcpyHostToDevice));
     std::vector<float> ones((size_t)npad * h->Kp, 1.f);
-    CU(h, cudaMemcpy(r.ard_beta_full, ones.data(), ones.size() * 4, cudaMemcpyHostToDevice));
+    CU(h, copy_sync(h->stream, r.ard_beta_full, ones.data(), ones.size() * 4, cudaMemcpyHostToDevice));
     CU(h, up2d(r.ard_beta_full, h->Kp, beta, h->K, n, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
     return PMF_OK;
@@ -608,7 +616,7 @@ int pmf_get_fsard_beta(pmf_handle h, float* beta) {
 }
 
 // builds the device copy of K concatenated CSR matrices
-static cudaError_t upload_csr(DevCsr& d, int K, const std::vector<int64_t>& rp_base, const std::vector<int64_t>& nnz_base,
+static cudaError_t upload_csr(cudaStream_t s, DevCsr& d, int K, const std::vector<int64_t>& rp_base, const std::vector<int64_t>& nnz_base,
                               const int32_t* rowptr, int64_t rp_total, const int32_t* col, const float* val, int64_t nnz_total) {
     cudaError_t e;
     if ((e = dev_alloc(&d.rowptr, (size_t)rp_total)) != cudaSuccess) return e;
@@ -616,13 +624,13 @@ static cudaError_t upload_csr(DevCsr& d, int K, const std::vector<int64_t>& rp_b
     if ((e = dev_alloc(&d.val, (size_t)std::max<int64_t>(nnz_total, 1))) != cudaSuccess) return e;
     if ((e = dev_alloc(&d.rowptr_base, K)) != cudaSuccess) return e;
     if ((e = dev_alloc(&d.nnz_base, K)) != cudaSuccess) return e;
-    cudaMemcpy(d.rowptr, rowptr, (size_t)rp_total * 4, cudaMemcpyHostToDevice);
+    copy_sync(s, d.rowptr, rowptr, (size_t)rp_total * 4, cudaMemcpyHostToDevice);
     if (nnz_total > 0) {
-        cudaMemcpy(d.col, col, (size_t)nnz_total * 4, cudaMemcpyHostToDevice);
-        cudaMemcpy(d.val, val, (size_t)nnz_total * 4, cudaMemcpyHostToDevice);
+        copy_sync(s, d.col, col, (size_t)nnz_total * 4, cudaMemcpyHostToDevice);
+        copy_sync(s, d.val, val, (size_t)nnz_total * 4, cudaMemcpyHostToDevice);
     }
-    cudaMemcpy(d.rowptr_base, rp_base.data(), (size_t)K * 8, cudaMemcpyHostToDevice);
-    return cudaMemcpy(d.nnz_base, nnz_base.data(), (size_t)K * 8, cudaMemcpyHostToDevice);
+    copy_sync(s, d.rowptr_base, rp_base.data(), (size_t)K * 8, cudaMemcpyHostToDevice);
+    return copy_sync(s, d.nnz_base, nnz_base.data(), (size_t)K * 8, cudaMemcpyHostToDevice);
 }
 
 int pmf_set_reg_network(pmf_handle h, int32_t which, const int32_t* nv, const int32_t* aa_rp, const int32_t* aa_c,
@@ -666,16 +674,16 @@ int pmf_set_reg_network(pmf_handle h, int32_t which, const int32_t* nv, const in
                 abt_v[ab_nb[k] + pos] = v[e];
             }
     }
-    CU(h, upload_csr(net.AA, K, aa_rb, aa_nb, aa_rp, aa_rt, aa_c, aa_v, aa_nt));
-    CU(h, upload_csr(net.AB, K, ab_rb, ab_nb, ab_rp, ab_rt, ab_c, ab_v, ab_nt));
-    CU(h, upload_csr(net.BB, K, bb_rb, bb_nb, bb_rp, bb_rt, bb_c, bb_v, bb_nt));
-    CU(h, upload_csr(net.ABt, K, bb_rb, ab_nb, abt_rp.data(), bb_rt, abt_c.data(), abt_v.data(), ab_nt));
+    CU(h, upload_csr(h->stream, net.AA, K, aa_rb, aa_nb, aa_rp, aa_rt, aa_c, aa_v, aa_nt));
+    CU(h, upload_csr(h->stream, net.AB, K, ab_rb, ab_nb, ab_rp, ab_rt, ab_c, ab_v, ab_nt));
+    CU(h, upload_csr(h->stream, net.BB, K, bb_rb, bb_nb, bb_rp, bb_rt, bb_c, bb_v, bb_nt));
+    CU(h, upload_csr(h->stream, net.ABt, K, bb_rb, ab_nb, abt_rp.data(), bb_rt, abt_c.data(), abt_v.data(), ab_nt));
     CU(h, dev_alloc(&net.nv, K)); CU(h, dev_alloc(&net.virt_base, K));
-    CU(h, cudaMemcpy(net.nv, nv, (size_t)K * 4, cudaMemcpyHostToDevice));
-    CU(h, cudaMemcpy(net.virt_base, vb.data(), (size_t)K * 8, cudaMemcpyHostToDevice));
+    CU(h, copy_sync(h->stream, net.nv, nv, (size_t)K * 4, cudaMemcpyHostToDevice));
+    CU(h, copy_sync(h->stream, net.virt_base, vb.data(), (size_t)K * 8, cudaMemcpyHostToDevice));
     CU(h, dev_alloc(&net.u, (size_t)std::max<int64_t>(vt, 1))); CU(h, dev_alloc(&net.work, (size_t)std::max<int64_t>(4 * vt, 1)));
-    CU(h, cudaMemset(net.u, 0, (size_t)std::max<int64_t>(vt, 1) * 4));
-    if (xv && vt > 0) CU(h, cudaMemcpy(net.u, xv, (size_t)vt * 4, cudaMemcpyHostToDevice));
+    CU(h, cudaMemsetAsync(net.u, 0, (size_t)std::max<int64_t>(vt, 1) * 4, h->stream));
+    if (xv && vt > 0) CU(h, copy_sync(h->stream, net.u, xv, (size_t)vt * 4, cudaMemcpyHostToDevice));
     net.nv_total = vt;
     net.nv_max = 0;
     for (int k = 0; k < K; ++k) net.nv_max = std::max(net.nv_max, (int)nv[k]);
@@ -695,7 +703,7 @@ int pmf_get_network_virtual(pmf_handle h, int32_t which, float* xv) {
     if (which < 0 || which > 1 || !h->reg[which].net.present) return fail(h, PMF_ERR_STATE, "no network regulariser");
     CU(h, cudaStreamSynchronize(h->stream));
     DevNetwork& net = h->reg[which].net;
-    if (net.nv_total > 0) CU(h, cudaMemcpy(xv, net.u, (size_t)net.nv_total * 4, cudaMemcpyDeviceToHost));
+    if (net.nv_total > 0) CU(h, copy_sync(h->stream, xv, net.u, (size_t)net.nv_total * 4, cudaMemcpyDeviceToHost));
     return PMF_OK;
 }
 
@@ -705,9 +713,9 @@ int pmf_set_layer_reg_col(pmf_handle h, int32_t slot, const float* w, const floa
     size_t off = slot == 1 ? 0 : (size_t)h->Np;
     h->layer_reg_present[slot - 1] = (w != nullptr);
     if (!w) return PMF_OK;
-    CU(h, cudaMemcpy(h->regw + off, w, (size_t)h->N * 4, cudaMemcpyHostToDevice));
-    if (c) CU(h, cudaMemcpy(h->regc + off, c, (size_t)h->N * 4, cudaMemcpyHostToDevice));
-    else CU(h, cudaMemset(h->regc + off, 0, (size_t)h->N * 4));
+    CU(h, copy_sync(h->stream, h->regw + off, w, (size_t)h->N * 4, cudaMemcpyHostToDevice));
+    if (c) CU(h, copy_sync(h->stream, h->regc + off, c, (size_t)h->N * 4, cudaMemcpyHostToDevice));
+    else CU(h, cudaMemsetAsync(h->regc + off, 0, (size_t)h->N * 4, h->stream));
     return PMF_OK;
 }
 
@@ -729,8 +737,8 @@ int pmf_set_layer_reg_batch(pmf_handle h, int32_t slot, const float* w, const fl
         src += bv.n_batches;
     }
     size_t off = 2 * (size_t)h->Np + (slot == 2 ? 0 : (size_t)h->nbp);
-    CU(h, cudaMemcpy(h->regw + off, ew.data(), ew.size() * 4, cudaMemcpyHostToDevice));
-    CU(h, cudaMemcpy(h->regc + off, ec.data(), ec.size() * 4, cudaMemcpyHostToDevice));
+    CU(h, copy_sync(h->stream, h->regw + off, ew.data(), ew.size() * 4, cudaMemcpyHostToDevice));
+    CU(h, copy_sync(h->stream, h->regc + off, ec.data(), ec.size() * 4, cudaMemcpyHostToDevice));
     return PMF_OK;
 }
 
@@ -872,7 +880,7 @@ int pmf_loss_grad(pmf_handle h, int32_t include_reg, pmf_losses* out, float* dX,
     if (include_reg && (rc = phase_reg_shared(h, false, false)) != 0) return rc;
     CU(h, cudaStreamSynchronize(h->stream));
     double sc[SC_COUNT];
-    CU(h, cudaMemcpy(sc, h->scalars, sizeof sc, cudaMemcpyDeviceToHost));
+    CU(h, copy_sync(h->stream, sc, h->scalars, sizeof sc, cudaMemcpyDeviceToHost));
     if (out) {
         out->data = sc[SC_DATA]; out->x_reg = sc[SC_XREG]; out->y_reg = sc[SC_YREG]; out->layer_reg = sc[SC_LAYERREG];
         out->total = sc[SC_DATA] + sc[SC_XREG] + sc[SC_YREG] + sc[SC_LAYERREG];
@@ -880,8 +888,8 @@ int pmf_loss_grad(pmf_handle h, int32_t include_reg, pmf_losses* out, float* dX,
     if (dX) CU(h, down2d(dX, h->K, h->dX, h->Kp, h->M, h->stream));
     if (dY) CU(h, down2d(dY, h->K, h->g_Y(), h->Kp, h->N, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
-    if (dls) CU(h, cudaMemcpy(dls, h->g_logsigma(), (size_t)h->N * 4, cudaMemcpyDeviceToHost));
-    if (dmu) CU(h, cudaMemcpy(dmu, h->g_mu(), (size_t)h->N * 4, cudaMemcpyDeviceToHost));
+    if (dls) CU(h, copy_sync(h->stream, dls, h->g_logsigma(), (size_t)h->N * 4, cudaMemcpyDeviceToHost));
+    if (dmu) CU(h, copy_sync(h->stream, dmu, h->g_mu(), (size_t)h->N * 4, cudaMemcpyDeviceToHost));
     return PMF_OK;
 }
 
@@ -889,7 +897,7 @@ int pmf_get_threshold_grads(pmf_handle h, int32_t n_ranges, float* dthr) {
     CHECK_H(h);
     if (!dthr || n_ranges != h->n_ranges) return fail(h, PMF_ERR_ARG, "pmf_get_threshold_grads: %d ranges given, the model has %d", n_ranges, h->n_ranges);
     CU(h, cudaStreamSynchronize(h->stream));
-    CU(h, cudaMemcpy(dthr, h->g_thr(), (size_t)2 * n_ranges * 4, cudaMemcpyDeviceToHost));
+    CU(h, copy_sync(h->stream, dthr, h->g_thr(), (size_t)2 * n_ranges * 4, cudaMemcpyDeviceToHost));
     return PMF_OK;
 }
 
@@ -950,7 +958,7 @@ int pmf_fit_poll(pmf_handle h, pmf_history* out, int32_t* stopped) {
         out->n_recorded = n;
         if (n > 0) {
             std::vector<double> hst((size_t)5 * n);
-            CU(h, cudaMemcpy(hst.data(), h->hist, hst.size() * 8, cudaMemcpyDeviceToHost));
+            CU(h, copy_sync(h->stream, hst.data(), h->hist, hst.size() * 8, cudaMemcpyDeviceToHost));
             for (int i = 0; i < n; ++i) {
                 if (out->loss_total) out->loss_total[i] = hst[5 * i + 0];
                 if (out->loss_data) out->loss_data[i] = hst[5 * i + 1];
@@ -1156,8 +1164,8 @@ int pmf_column_stats(pmf_handle h, float* ssq, float* nonnan) {
     CHECK_H(h);
     int rc = run_stats_pass(h);
     if (rc != 0) return rc;
-    if (ssq) CU(h, cudaMemcpy(ssq, h->col_ssq, (size_t)h->N * 4, cudaMemcpyDeviceToHost));
-    if (nonnan) CU(h, cudaMemcpy(nonnan, h->col_cnt, (size_t)h->N * 4, cudaMemcpyDeviceToHost));
+    if (ssq) CU(h, copy_sync(h->stream, ssq, h->col_ssq, (size_t)h->N * 4, cudaMemcpyDeviceToHost));
+    if (nonnan) CU(h, copy_sync(h->stream, nonnan, h->col_cnt, (size_t)h->N * 4, cudaMemcpyDeviceToHost));
     return PMF_OK;
 }
 
@@ -1165,8 +1173,8 @@ int pmf_link_col_sqerr(pmf_handle h, float* sqerr, float* nonnan) {
     CHECK_H(h);
     int rc = run_stats_pass(h);
     if (rc != 0) return rc;
-    if (sqerr) CU(h, cudaMemcpy(sqerr, h->col_sqerr, (size_t)h->N * 4, cudaMemcpyDeviceToHost));
-    if (nonnan) CU(h, cudaMemcpy(nonnan, h->col_cnt, (size_t)h->N * 4, cudaMemcpyDeviceToHost));
+    if (sqerr) CU(h, copy_sync(h->stream, sqerr, h->col_sqerr, (size_t)h->N * 4, cudaMemcpyDeviceToHost));
+    if (nonnan) CU(h, copy_sync(h->stream, nonnan, h->col_cnt, (size_t)h->N * 4, cudaMemcpyDeviceToHost));
     return PMF_OK;
 }
 
@@ -1178,8 +1186,8 @@ int pmf_batch_stats(pmf_handle h, int32_t n_views, float* const* count, float* c
     for (int v = 0; v < n_views; ++v) {
         const BatchView& bv = h->views[v];
         size_t n = (size_t)(bv.col_stop - bv.col_start) * bv.n_batches;
-        if (count && count[v]) CU(h, cudaMemcpy(count[v], h->g_theta() + bv.offset, n * 4, cudaMemcpyDeviceToHost));
-        if (sqerr && sqerr[v]) CU(h, cudaMemcpy(sqerr[v], h->g_logdelta() + bv.offset, n * 4, cudaMemcpyDeviceToHost));
+        if (count && count[v]) CU(h, copy_sync(h->stream, count[v], h->g_theta() + bv.offset, n * 4, cudaMemcpyDeviceToHost));
+        if (sqerr && sqerr[v]) CU(h, copy_sync(h->stream, sqerr[v], h->g_logdelta() + bv.offset, n * 4, cudaMemcpyDeviceToHost));
     }
     return PMF_OK;
 }
@@ -1228,7 +1236,7 @@ int pmf_model_s::realloc_vectors(int new_nbp) {
     if (dev_alloc(&vp, nv) != cudaSuccess || dev_alloc(&sg, ng) != cudaSuccess || dev_alloc(&accvp, nv) != cudaSuccess ||
         dev_alloc(&regw, nv) != cudaSuccess || dev_alloc(&regc, nv) != cudaSuccess)
         return -1;
-    cudaMemset(vp, 0, nv * 4); cudaMemset(sg, 0, ng * 4); cudaMemset(regw, 0, nv * 4); cudaMemset(regc, 0, nv * 4);
+    cudaMemsetAsync(vp, 0, nv * 4, stream); cudaMemsetAsync(sg, 0, ng * 4, stream); cudaMemsetAsync(regw, 0, nv * 4, stream); cudaMemsetAsync(regc, 0, nv * 4, stream);
     fill_kernel<<<64, 256>>>(accvp, nv, 1e-8f);
     return cudaDeviceSynchronize() == cudaSuccess ? 0 : -1;
 }
@@ -1393,7 +1401,7 @@ int pmf_model_s::build_tc_plan() {
         void* d = nullptr;
         if (cudaMalloc(&d, bytes ? bytes : 4) != cudaSuccess) return false;
         tcb_allocs.push_back(d);
-        if (src && bytes && cudaMemcpy(d, src, bytes, cudaMemcpyHostToDevice) != cudaSuccess) return false;
+        if (src && bytes && copy_sync(stream, d, src, bytes, cudaMemcpyHostToDevice) != cudaSuccess) return false;
         *dst = d;
         return true;
     };
