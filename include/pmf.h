@@ -53,9 +53,12 @@ typedef enum {
 
 /* Which hand-written kernel computes the data pass. */
 typedef enum {
-    PMF_KERNEL_AUTO = 0,   /* tcgen05 path when the shape supports it, else FFMA */
+    PMF_KERNEL_AUTO = 0,   /* tcgen05 kernels when the shape supports them AND the problem is large enough
+                              for their TF32 gradient contractions to stay within 1e-4 (pmf_fit_opts.precision),
+                              else FFMA */
     PMF_KERNEL_FFMA = 1,   /* FP32 CUDA-core tile kernel (exact FP32 products)   */
-    PMF_KERNEL_TC = 2      /* tcgen05/TMEM tile kernel (TF32 / 3xTF32 products)  */
+    PMF_KERNEL_TC = 2      /* tcgen05/TMEM kernels (split-BF16 Z, TF32 gradients); an error on shapes they do
+                              not support, never a silent fallback */
 } pmf_kernel_kind;
 
 typedef struct {
@@ -207,14 +210,18 @@ typedef struct {
     int32_t update_X, update_Y, update_col_layers;
     int32_t kernel;              /* pmf_kernel_kind                                    */
     int32_t precision;           /* tensor-core kernels only (PMF_KERNEL_FFMA is exact FP32 throughout):
-                                    0, 1 (identical): Z = X'Y at FP32 level -- K <= 64: TF32 product + BF16
-                                       first-order corrections; K > 64: two-term BF16 split, three
-                                       contractions -- so loss and column / batch gradients agree with FP32
-                                       to ~1e-6; the contractions dX = Y G', dY = X G are single-pass TF32
-                                       with round-to-nearest operands (FP32 accumulation): ~1-2e-4 relative
-                                       on small problems, 3-4e-5 at 10 000 x 30 000.  PMF_KERNEL_AUTO
-                                       therefore picks these kernels for large problems only.
-                                    2: plain TF32 for Z as well (K <= 64; ignored for K > 64)            */
+                                    0, 1 (identical): Z = X'Y at FP32 level -- a two-term BF16 split of both
+                                       operands (v = h + l, h = bf16(v), l = bf16(v - h)) and the three
+                                       contractions Yh Xh + Yl Xh + Yh Xl with FP32 accumulation (dropped
+                                       term: 2^-17 of a product), for K <= 64 and K > 64 alike -- so loss and
+                                       column / batch gradients agree with FP32 to ~1e-6; the contractions
+                                       dX = Y G', dY = X G are single-pass TF32 with round-to-nearest
+                                       operands (FP32 accumulation): ~1-2e-4 relative on small problems,
+                                       3-4e-5 at 10 000 x 30 000.  PMF_KERNEL_AUTO therefore picks these
+                                       kernels only from M N >= 6e6 (K/64)^2, min(M, N) >= 2000, where the
+                                       measured gradient error is below 1e-4.
+                                    2: experiments -- only the leading term Yh Xh of Z (K <= 64; ignored
+                                       for K > 64)                                                       */
     int32_t check_every;         /* epochs launched between host checks of the stop flag */
     int32_t no_terminate;        /* bench hook: run every epoch up to max_epochs, never stop on
                                     a tolerance / loss-increase test (losses still recorded) */

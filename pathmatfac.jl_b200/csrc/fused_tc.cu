@@ -119,7 +119,7 @@ __device__ __noinline__ float2 threshold_grads_slow(int dist, float z, float a, 
 struct TcParams {
     DataPassParams dp;
     int n_jt, n_it;
-    int z_passes;      // 3 = 3xTF32 for the Z contraction, 1 = plain TF32
+    int z_passes;      // 3 = Yh Xh + Yl Xh + Yh Xl (split-BF16 Z at FP32 level), 1 = the leading term Yh Xh only
     int ablate;        // PMF_TC_ABLATE (performance experiments only; results are wrong when non-zero)
     long long* trace;  // PMF_TC_TRACE: per-tile clock64 stamps of one CTA (16 events x TRACE_TILES), else null
     int trace_cta;

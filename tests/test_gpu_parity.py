@@ -475,8 +475,9 @@ def test_tc_batch_plan_follows_new_data():
 
 
 def test_tc_batch_layers_fit_curve():
-    """C3 in miniature through mf_fit with the AUTO kernel (tcgen05 path: M >= 1024, M*N >= 4e6); batch ids are
-    iid per sample and view, so every view gets its own sample order and boundary tiles run two passes.
+    """C3 in miniature through mf_fit on the tcgen05 path (requested explicitly: PMF_KERNEL_AUTO keeps a problem of
+    this size on the FP32 kernel); batch ids are iid per sample and view, so every view gets its own sample order and
+    boundary tiles run two passes.
     AdaGrad's first steps are sign-like, which amplifies the TF32 rounding of small gradients: 3e-3 on the
     batch parameters after 6 epochs."""
     views = {"mutation": ("bernoulli", 600), "methylation": ("normal", 1400), "mrnaseq": ("normal", 1300),
@@ -486,7 +487,7 @@ def test_tc_batch_layers_fit_curve():
     href = O.mf_fit(om, D, O.AdaGrad(0.1), max_epochs=6, update_X=True, update_Y=True, update_col_layers=True,
                     rel_tol=0, abs_tol=0)
     h = P.mf_fit(model, lr=0.1, max_epochs=6, update_X=True, update_Y=True, update_col_layers=True, rel_tol=0,
-                 abs_tol=0, verbosity=0)
+                 abs_tol=0, verbosity=0, kernel=_lib.KERNEL_TC)
     assert h["epochs"] == href["epochs"]
     assert np.max(np.abs(np.array(h["loss"]) / np.array(href["loss"]) - 1)) < 1e-4
     layers = model.matfac.col_transform.layers
