@@ -41,6 +41,9 @@ def parse():
     ap.add_argument("--K", type=int, default=C2["K"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--kernel-events", default="same", choices=["same", "separate"],
+                    help="same: the per-launch CUDA events of the fused data pass are recorded inside the timed region; "
+                         "separate: the timed region runs without them and a second region of the same K steps records them")
     return ap.parse_args()
 
 
@@ -298,25 +301,35 @@ def main():
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
-    eng.set_profiling(True)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     # the library (kernels + its ncclAllReduce) runs on a dedicated torch stream and the events are recorded on that
     # stream (the legacy default stream has handle 0, which pmf_set_stream reads as "the handle's own stream")
     stream = eng.torch_stream()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
+
+    def timed_region(first, last, kernel_events):
+        """`last - first + 1` steps bracketed by synchronize + barrier on both sides; device time, max over ranks."""
+        eng.set_profiling(kernel_events)
         torch.cuda.synchronize()
-    ev0.record(stream)
-    h = run_epochs(args.warmup + 1, args.warmup + args.steps)
-    ev1.record(stream)
-    torch.cuda.synchronize()
-    ms = ev0.elapsed_time(ev1)
-    if world > 1:
-        t = torch.tensor([ms], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-        dist.barrier()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+        ev0.record(stream)
+        hh = run_epochs(first, last)
+        ev1.record(stream)
+        torch.cuda.synchronize()
+        t_ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([t_ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            t_ms = float(t.item())
+            dist.barrier()
+        return hh, t_ms
+
+    separate = args.kernel_events == "separate"
+    h, ms = timed_region(args.warmup + 1, args.warmup + args.steps, not separate)
+    ms_events = ms
+    if separate:    # the same K steps again, with the per-launch events of the fused data pass
+        _, ms_events = timed_region(args.warmup + args.steps + 1, args.warmup + 2 * args.steps, True)
     clocks = sampler.summary() if sampler else None
     n_prof, dp_mean_ms, dp_min_ms = eng.get_profile()
     eng.set_profiling(False)
@@ -372,17 +385,20 @@ def main():
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "traffic_source": traffic_src, "kernel": "fused data pass", "kernel_ms": dp_mean_ms, "kernel_min_ms": dp_min_ms,
                 "launches_timed": n_prof, "algorithmic_bytes": alg_bytes, "peak_source": peak_src,
-                "kernel_share_of_step": dp_mean_ms / (sec_per_step * 1e3)}
+                "kernel_share_of_step": dp_mean_ms / (ms_events / args.steps),
+                "events": "recorded inside the timed region" if not separate else
+                          f"recorded over a second region of the same {args.steps} steps ({ms_events / args.steps:.4f} ms/step with them)"}
 
     # ---- end to end through the reference-facing call with host buffers ---------------------------
     e2e = e2e_sharded
     eng.close()
     if not args.no_e2e and world == 1:
-        # three identical calls, the MEDIAN is reported (every call's time is listed): the first call of a fresh process
-        # also pays one-time driver costs (first cudaMalloc / cudaFree of the 1.2 GB data buffer) that vary by a factor of
-        # ten between boxes
+        # five identical calls, the MEDIAN is reported (every call's time is listed): the first call of a fresh process
+        # also pays one-time driver costs (first cudaMalloc of the 1.2 GB data buffer and of the handle's other blocks;
+        # later calls take them from the library's caches), and single calls have been seen to stall for hundreds of
+        # milliseconds inside the driver
         runs = []
-        for _ in range(3):
+        for _ in range(5):
             model.matfac.X[...] = X0
             model.matfac.Y[...] = Y0
             torch.cuda.synchronize()
@@ -393,13 +409,13 @@ def main():
             torch.cuda.synchronize()
             runs.append((time.perf_counter() - t0, h_try))
         dts = [r[0] for r in runs]
-        dt, he = sorted(runs, key=lambda r: r[0])[1]
+        dt, he = sorted(runs, key=lambda r: r[0])[len(runs) // 2]
         e2e = {"value": he["epochs"] / dt, "unit": UNIT,
                "h2d_bytes_per_step": he["h2d_bytes"] / max(he["epochs"], 1),
                "d2h_bytes_per_step": he["d2h_bytes"] / max(he["epochs"], 1),
                "call": f"mf_fit(model; max_epochs={args.steps}) on a host-resident model: create handle, H2D of "
                        f"data (pinned) + parameters, {he['epochs']} epochs, D2H of parameters + history; "
-                       f"median of three identical calls",
+                       f"median of five identical calls",
                "epochs_run": he["epochs"], "seconds": dt, "seconds_each_call": dts}
 
     # ---- CPU baseline beside it (bounded sample, rank 0) -----------------------------------------------

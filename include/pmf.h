@@ -71,10 +71,12 @@ typedef struct {
 /* size(model.data), size(model.matfac.X,1)  (src/model.jl:46, src/fit.jl:142). */
 int pmf_create(const pmf_dims* dims, pmf_handle* out);
 int pmf_destroy(pmf_handle h);
-/* A destroyed handle parks its data buffer (>= 64 MB; at most two are kept per process) for the next
- * pmf_create of the same size on the same device: mf_fit! on a host-resident model creates and destroys a
- * handle per call (src/fit.jl:9-38 with the model moved by gpu()/cpu() around it), and cudaMalloc / cudaFree of
- * a gigabyte would otherwise dominate short fits.  This call returns the parked memory to the driver. */
+/* mf_fit! on a host-resident model creates and destroys a handle per call (src/fit.jl:9-38 with the model moved
+ * by gpu()/cpu() around it), and cudaMalloc / cudaFree would otherwise dominate short fits.  A destroyed handle
+ * therefore parks its data buffer (>= 64 MB; at most two are kept per process) for the next pmf_create of the same
+ * size on the same device, and every smaller device block the library frees is kept in a size-keyed cache (at most
+ * 1 GB per process; handed out zero-filled; PMF_ALLOC_CACHE=0 in the environment disables it).  This call returns
+ * all of that memory to the driver. */
 int pmf_release_cached_memory(void);
 
 /* Host-side preview of how the tcgen05 data pass lays out a model with batch layers (no device work, no handle;

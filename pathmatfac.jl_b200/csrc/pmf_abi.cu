@@ -83,7 +83,33 @@ constexpr size_t kPoolMinBytes = 64u << 20;
 constexpr int kPoolSlots = 2;
 std::mutex g_pool_mu;
 std::vector<ParkedBuf> g_pool;
+// the pinned control block of a handle (cudaMallocHost / cudaFreeHost page-lock and unlock: ~0.1-1 ms each)
+std::mutex g_ctrl_pool_mu;
+std::vector<void*> g_ctrl_pool;
 }  // namespace
+
+static cudaError_t ctrl_host_alloc(FitControl** p) {
+    {
+        std::lock_guard<std::mutex> lk(g_ctrl_pool_mu);
+        if (!g_ctrl_pool.empty()) {
+            *p = static_cast<FitControl*>(g_ctrl_pool.back());
+            g_ctrl_pool.pop_back();
+            std::memset(*p, 0, sizeof(FitControl));
+            return cudaSuccess;
+        }
+    }
+    // portable: one pinned block serves the handles of every device of the process
+    cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(p), sizeof(FitControl), cudaHostAllocPortable);
+    if (e == cudaSuccess) std::memset(*p, 0, sizeof(FitControl));
+    return e;
+}
+static void ctrl_host_free(FitControl*& p) {
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(g_ctrl_pool_mu);
+    if (g_ctrl_pool.size() < 16) g_ctrl_pool.push_back(p);
+    else cudaFreeHost(p);
+    p = nullptr;
+}
 
 static cudaError_t big_alloc(float** p, size_t n_floats, int dev) {
     const size_t bytes = n_floats * sizeof(float);
@@ -137,6 +163,12 @@ int pmf_release_cached_memory(void) {
         cudaFree(b.p);
     }
     cudaSetDevice(cur);
+    pmf::release_alloc_cache();         // the small blocks parked by the allocator (guard.cu)
+    {
+        std::lock_guard<std::mutex> lk(g_ctrl_pool_mu);
+        for (void* q : g_ctrl_pool) cudaFreeHost(q);
+        g_ctrl_pool.clear();
+    }
     return PMF_OK;
 }
 
@@ -238,7 +270,7 @@ int pmf_create(const pmf_dims* d, pmf_handle* out) {
     cudaMemsetAsync(h->scalars_base, 0, 4 * SC_COUNT * sizeof(double), h->stream);
     std::vector<float> ones(h->Np, 1.f);
     copy_sync(h->stream, h->weight, ones.data(), (size_t)h->Np * 4, cudaMemcpyHostToDevice);
-    cudaMallocHost((void**)&h->ctrl_host, sizeof(FitControl));
+    if (ctrl_host_alloc(&h->ctrl_host) != cudaSuccess) { pmf_destroy(h); return fail(nullptr, PMF_ERR_ALLOC, "pinned host allocation failed"); }
     int rc = h->realloc_vectors(0);   // no batch views yet
     if (rc != 0) { pmf_destroy(h); return fail(nullptr, PMF_ERR_ALLOC, "device allocation failed"); }
     pmf_reset_opt_state(h, 1e-8f);
@@ -265,7 +297,7 @@ int pmf_destroy(pmf_handle h) {
     dev_free(h->hist); dev_free(h->col_ssq); dev_free(h->col_cnt); dev_free(h->col_sqerr);
     for (int s = 0; s < 2; ++s) h->reg[s].free_all();
     if (h->comm) { nccl().CommDestroy(h->comm); h->comm = nullptr; }
-    if (h->ctrl_host) cudaFreeHost(h->ctrl_host);
+    ctrl_host_free(h->ctrl_host);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);

@@ -5,11 +5,12 @@
 
 namespace pmf {
 
-// guard.cu: every device allocation of the library goes through these (guard zones when PMF_GUARD=1, else plain
-// cudaMalloc / cudaFree).  The macros below route the remaining direct calls of the translation units that include
-// this header.
+// guard.cu: every device allocation of the library goes through these (a size-keyed cache of freed blocks; guard
+// zones instead when PMF_GUARD=1).  The macros below route the remaining direct calls of the translation units that
+// include this header.
 cudaError_t guarded_malloc(void** p, size_t bytes);
 cudaError_t guarded_free(void* p);
+void release_alloc_cache();      // every parked block back to the driver (pmf_release_cached_memory)
 
 // Number of double scalars in the shared scalar buffer.
 enum { SC_DATA = 0, SC_XREG = 1, SC_YREG = 2, SC_LAYERREG = 3, SC_COUNT = 8 };

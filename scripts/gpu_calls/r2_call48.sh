@@ -9,3 +9,5 @@ timeout -s KILL 150 python bench.py --steps 20 --warmup 5 > gpurun_out/r2c48_ben
 cut -c1-400 gpurun_out/r2c48_bench.json; tail -2 gpurun_out/r2c48_bench.err
 timeout -s KILL 90 python scripts/measure_tolerances.py > gpurun_out/r2c48_tolerances.jsonl 2> gpurun_out/r2c48_tolerances.err
 cat gpurun_out/r2c48_tolerances.jsonl | cut -c1-600; tail -2 gpurun_out/r2c48_tolerances.err
+timeout -s KILL 90 python bench.py --steps 20 --warmup 5 --no-cpu --no-e2e --kernel-events separate > gpurun_out/r2c48_bench_separate.json 2> gpurun_out/r2c48_bench_separate.err
+cut -c1-200 gpurun_out/r2c48_bench_separate.json; tail -2 gpurun_out/r2c48_bench_separate.err

@@ -1,0 +1,46 @@
+"""bench.py's driver contract, as far as it can be checked without a GPU: the reference arm prints ONE JSON line with
+the keys the driver reads, and the repo arm refuses to run without a CUDA device (there is no CPU path to time)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(args, env=None, timeout=300):
+    e = dict(os.environ)
+    e.update(env or {})
+    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py")] + args, cwd=ROOT, capture_output=True, text=True,
+                          timeout=timeout, env=e)
+
+
+def test_reference_arm_prints_one_json_line_with_the_contract_keys():
+    r = _run(["--impl", "reference", "--steps", "2", "--warmup", "1", "--M", "300", "--N", "400", "--K", "8"])
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["higher_is_better"] is True and d["unit"] == "iter/s"
+    assert d["steps"] == 2 and d["warmup"] == 1 and d["value"] > 0 and d["ms_per_step"] > 0
+    assert abs(d["value"] * d["ms_per_step"] / 1e3 - 1.0) < 1e-9           # iterations/sec <-> ms per step
+    assert d["e2e"] == {"value": d["value"], "unit": "iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "samples" in cb["sample"]
+    assert d["config"]["workload"].startswith("C2") and "model" not in d["config"]
+
+
+def test_reference_arm_runs_on_rank_0_only():
+    r = _run(["--impl", "reference", "--steps", "1", "--warmup", "0", "--M", "200", "--N", "300", "--K", "8"],
+             env={"RANK": "1", "LOCAL_RANK": "1", "WORLD_SIZE": "2"})
+    assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_repo_arm_needs_a_cuda_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    r = _run(["--steps", "1", "--warmup", "0", "--M", "256", "--N", "256", "--K", "8", "--no-cpu", "--no-e2e"])
+    assert r.returncode != 0 and "CUDA device" in (r.stderr + r.stdout)

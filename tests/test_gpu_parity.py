@@ -109,10 +109,13 @@ def test_fsard_regulariser_and_update_A():
     finally:
         P.cpu(model)
     ref = O.update_A(om.Y_reg, om.Y.astype(np.float32), max_epochs=150, term_iter=20, atol=1e-5)
+    # measured on B200 (scripts/measure_tolerances.py, profiles/r2_tolerances.jsonl): best loss within 1.4e-7, A within
+    # 1.2e-7, beta within 4.4e-8 of the oracle after 20 as well as after 150 ISTA epochs
     for (bl, ep), (rbl, rep), A, Ar in zip(res, ref, model.matfac.Y_reg.A, om.Y_reg.A):
-        assert abs(bl - rbl) <= 1e-4 * abs(rbl) + 1e-3
-        assert relerr(A, Ar) < 5e-3
-    assert relerr(model.matfac.Y_reg.beta, om.Y_reg.beta) < 5e-3
+        assert ep == rep
+        assert abs(bl - rbl) <= 1e-5 * abs(rbl)
+        assert relerr(A, Ar) < 1e-5
+    assert relerr(model.matfac.Y_reg.beta, om.Y_reg.beta) < 1e-5
 
 
 def test_fit_loss_curve_and_parameters():
@@ -132,9 +135,10 @@ def test_fit_loss_curve_and_parameters():
     assert len(h["loss"]) == len(href["loss"])
     assert relerr(h["loss"], href["loss"]) < TOL
     assert np.max(np.abs(np.array(h["loss"]) / np.array(href["loss"]) - 1)) < 5 * TOL
-    assert relerr(model.matfac.X, om.X) < 1e-3 and relerr(model.matfac.Y, om.Y) < 1e-3
-    assert relerr(model.matfac.col_transform.layers[2].mu, om.mu) < 1e-3
-    assert relerr(model.matfac.col_transform.layers[3].theta.values[0], om.theta.values[0]) < 1e-3
+    # fitted parameters after 25 epochs: 1-2e-6 measured (profiles/r2_tolerances.jsonl)
+    assert relerr(model.matfac.X, om.X) < 5e-5 and relerr(model.matfac.Y, om.Y) < 5e-5
+    assert relerr(model.matfac.col_transform.layers[2].mu, om.mu) < 5e-5
+    assert relerr(model.matfac.col_transform.layers[3].theta.values[0], om.theta.values[0]) < 5e-5
 
 
 def test_frozen_layers_and_flags():
@@ -478,8 +482,8 @@ def test_tc_batch_layers_fit_curve():
     """C3 in miniature through mf_fit on the tcgen05 path (requested explicitly: PMF_KERNEL_AUTO keeps a problem of
     this size on the FP32 kernel); batch ids are iid per sample and view, so every view gets its own sample order and
     boundary tiles run two passes.
-    AdaGrad's first steps are sign-like, which amplifies the TF32 rounding of small gradients: 3e-3 on the
-    batch parameters after 6 epochs."""
+    AdaGrad's first steps are sign-like, which amplifies the TF32 rounding of small gradients: 5e-5 measured on the
+    batch parameters after 6 epochs (profiles/r2_tolerances.jsonl; the FP32 kernel: 1e-7), asserted at 5e-4."""
     views = {"mutation": ("bernoulli", 600), "methylation": ("normal", 1400), "mrnaseq": ("normal", 1300),
              "counts": ("poisson", 800)}
     model, om, D = make_pair(1100, views, K=16, seed=73, batch_views=["methylation", "mrnaseq", "counts"],
@@ -492,8 +496,8 @@ def test_tc_batch_layers_fit_curve():
     assert np.max(np.abs(np.array(h["loss"]) / np.array(href["loss"]) - 1)) < 1e-4
     layers = model.matfac.col_transform.layers
     for v in range(len(om.theta.values)):
-        assert relerr(layers[3].theta.values[v], om.theta.values[v]) < 3e-3
-        assert relerr(layers[1].logdelta.values[v], om.logdelta.values[v]) < 3e-3
+        assert relerr(layers[3].theta.values[v], om.theta.values[v]) < 5e-4
+        assert relerr(layers[1].logdelta.values[v], om.logdelta.values[v]) < 5e-4
 
 
 def test_staging_statistics_passes():
