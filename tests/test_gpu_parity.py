@@ -482,8 +482,9 @@ def test_tc_batch_layers_fit_curve():
     """C3 in miniature through mf_fit on the tcgen05 path (requested explicitly: PMF_KERNEL_AUTO keeps a problem of
     this size on the FP32 kernel); batch ids are iid per sample and view, so every view gets its own sample order and
     boundary tiles run two passes.
-    AdaGrad's first steps are sign-like, which amplifies the TF32 rounding of small gradients: 5e-5 measured on the
-    batch parameters after 6 epochs (profiles/r2_tolerances.jsonl; the FP32 kernel: 1e-7), asserted at 5e-4."""
+    AdaGrad's first steps are sign-like, which amplifies the TF32 rounding of small gradients into the batch
+    parameters: after 6 epochs 1e-3 on theta of the first view with these inputs, 5e-5 with 25 % instead of 30 %
+    missing entries (profiles/r2_tolerances.jsonl; the FP32 kernel: 1e-7 on both).  Asserted at 3e-3."""
     views = {"mutation": ("bernoulli", 600), "methylation": ("normal", 1400), "mrnaseq": ("normal", 1300),
              "counts": ("poisson", 800)}
     model, om, D = make_pair(1100, views, K=16, seed=73, batch_views=["methylation", "mrnaseq", "counts"],
@@ -495,9 +496,10 @@ def test_tc_batch_layers_fit_curve():
     assert h["epochs"] == href["epochs"]
     assert np.max(np.abs(np.array(h["loss"]) / np.array(href["loss"]) - 1)) < 1e-4
     layers = model.matfac.col_transform.layers
-    for v in range(len(om.theta.values)):
-        assert relerr(layers[3].theta.values[v], om.theta.values[v]) < 5e-4
-        assert relerr(layers[1].logdelta.values[v], om.logdelta.values[v]) < 5e-4
+    errs = [(relerr(layers[3].theta.values[v], om.theta.values[v]), relerr(layers[1].logdelta.values[v], om.logdelta.values[v]))
+            for v in range(len(om.theta.values))]
+    print("batch-parameter differences (theta, logdelta) per view:", errs)
+    assert max(max(e) for e in errs) < 3e-3, errs
 
 
 def test_staging_statistics_passes():
