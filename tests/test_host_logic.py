@@ -132,6 +132,78 @@ def test_model_constructor_mirrors_reference():
     assert isinstance(m.matfac.X_reg, P.L2Regularizer)
 
 
+def test_model_constructor_reference_testsets():
+    """The reference's own constructor testsets (test/runtests.jl:939-1084) against the mirror: same inputs (M = 20,
+    N = 30, K = 4, star graphs through one virtual node, 2 views x 4 row batches), same structural assertions.  The two
+    value assertions (`Y_reg(Y) == 0.5*3.14*sum(Y.^2)`, `X_reg(X) == 0.5*3.14*sum(X.*X)`, :998, :1033) are evaluated on
+    the oracle's regularisers built from the same arguments (the mirror's objects carry data, the device evaluates
+    them; tests/test_gpu_parity.py compares the device values with the oracle's)."""
+    M, N, K = 20, 30, 4
+    rng = np.random.default_rng(5)
+    Z = (rng.standard_normal((M, K)) @ rng.standard_normal((K, N))).astype(np.float32)
+    sample_ids = [f"sample_{i}" for i in range(1, M + 1)]
+    sample_conditions = ["condition_1"] * (M // 2) + ["condition_2"] * (M // 2)
+    sample_graphs = [[[s, "z", 1] for s in sample_ids] for _ in range(K)]
+    feature_ids = [f"x_{i}" for i in range(1, N + 1)]
+    feature_views = [1] * (N // 2) + [2] * (N // 2)
+    batch_dict = {j: [f"rowbatch{i}" for i in range(1, 5) for _ in range(M // 4)] for j in (1, 2)}
+    feature_graphs = [[[f, "y", 1] for f in feature_ids] for _ in range(K)]
+
+    # "Default constructor" (:965-975)
+    m = P.PathMatFacModel(Z.copy())
+    assert m.matfac.X.shape == (10, M) and m.matfac.Y.shape == (10, N)
+    assert list(m.sample_ids) == list(range(1, M + 1)) and list(m.feature_ids) == list(range(1, N + 1))
+    # "Batch effect model constructor" (:977-986)
+    m = P.PathMatFacModel(Z.copy(), K=K, sample_conditions=sample_conditions, feature_views=feature_views, batch_dict=batch_dict)
+    assert m.matfac.X.shape == (K, M) and m.matfac.Y.shape == (K, N)
+    assert [type(l) for l in m.matfac.col_transform.layers] == [P.ColScale, P.BatchScale, P.ColShift, P.BatchShift]
+    # "Y-regularized model constructor" (:988-1024)
+    m = P.PathMatFacModel(Z.copy(), feature_ids=feature_ids, feature_graphs=feature_graphs, lambda_Y_graph=1.0)
+    assert m.matfac.Y.shape == (K, N) and len(m.matfac.col_transform.layers) == 4     # K = number of graphs (src/model.jl:122)
+    assert len(m.matfac.X_reg.regularizers) == 3 and len(m.matfac.Y_reg.regularizers) == 3
+    assert isinstance(m.matfac.Y_reg.regularizers[2], P.NetworkRegularizer)
+    m = P.PathMatFacModel(Z.copy(), K=7, lambda_Y_l2=3.14)
+    assert m.matfac.Y.shape == (7, N) and len(m.matfac.X_reg.regularizers) == 3 and len(m.matfac.Y_reg.regularizers) == 3
+    assert isinstance(m.matfac.Y_reg.regularizers[0], P.GroupRegularizer)
+    Y = m.matfac.Y.astype(np.float64)
+    oy = O.construct_Y_reg(7, N, list(range(1, N + 1)), [1] * N, None, None, 3.14, None, None, False, False, None,
+                           np.float32(1.001), np.float32(0.8))
+    assert O._value_grad(oy, Y)[0] == pytest.approx(0.5 * 3.14 * np.sum(Y ** 2), rel=1e-6)
+    assert m.matfac.Y_reg.mixture_p == tuple(oy.mixture_p)
+    m = P.PathMatFacModel(Z.copy(), feature_ids=feature_ids, feature_graphs=feature_graphs, lambda_Y_selective_l1=1.0)
+    assert m.matfac.Y.shape == (K, N) and isinstance(m.matfac.Y_reg.regularizers[1], P.SelectiveL1Reg)
+    m = P.PathMatFacModel(Z.copy(), feature_ids=feature_ids, feature_graphs=feature_graphs, lambda_Y_graph=1.0,
+                          lambda_Y_selective_l1=1.0)
+    assert isinstance(m.matfac.Y_reg.regularizers[1], P.SelectiveL1Reg) and isinstance(m.matfac.Y_reg.regularizers[2], P.NetworkRegularizer)
+    # "X-regularized model constructor" (:1026-1061)
+    m = P.PathMatFacModel(Z.copy(), K=8, lambda_X_l2=3.14)
+    assert m.matfac.X.shape == (8, M) and isinstance(m.matfac.X_reg.regularizers[0], P.L2Regularizer)
+    X = m.matfac.X.astype(np.float64)
+    ox = O.construct_X_reg(8, M, list(range(1, M + 1)), None, None, 3.14, 1.0, 1.0, False, False)
+    assert O._value_grad(ox, X)[0] == pytest.approx(0.5 * 3.14 * np.sum(X * X), rel=1e-6)
+    m = P.PathMatFacModel(Z.copy(), K=6, sample_conditions=sample_conditions, lambda_X_condition=3.14)
+    assert m.matfac.X.shape == (6, M) and isinstance(m.matfac.X_reg.regularizers[1], P.GroupRegularizer)
+    m = P.PathMatFacModel(Z.copy(), sample_ids=sample_ids, sample_graphs=sample_graphs)
+    assert m.matfac.X.shape == (K, M) and isinstance(m.matfac.X_reg.regularizers[2], P.NetworkRegularizer)
+    assert np.all(np.asarray(m.matfac.X_reg.regularizers[2].cur_weights) == 1.0)
+    m = P.PathMatFacModel(Z.copy(), sample_ids=sample_ids, sample_conditions=sample_conditions, sample_graphs=sample_graphs,
+                          lambda_X_graph=1.234, lambda_X_condition=5.678)
+    xr = m.matfac.X_reg.regularizers
+    assert isinstance(xr[1], P.GroupRegularizer) and isinstance(xr[2], P.NetworkRegularizer)
+    assert all(np.allclose(w, np.full(K, 5.678)) for w in xr[1].group_weights)
+    assert np.allclose(xr[2].cur_weights, 1.234)
+    # "Full-featured model constructor" (:1063-1084)
+    m = P.PathMatFacModel(Z.copy(), sample_ids=sample_ids, sample_conditions=sample_conditions, sample_graphs=sample_graphs,
+                          lambda_X_graph=1.234, lambda_X_condition=5.678, feature_ids=feature_ids, feature_views=feature_views,
+                          feature_graphs=feature_graphs, batch_dict=batch_dict, lambda_Y_graph=1.0, lambda_Y_selective_l1=1.0)
+    xr, yr = m.matfac.X_reg.regularizers, m.matfac.Y_reg.regularizers
+    assert m.matfac.X.shape == (K, M) and m.matfac.Y.shape == (K, N) and len(m.matfac.col_transform.layers) == 4
+    assert len(xr) == 3 and isinstance(xr[1], P.GroupRegularizer) and isinstance(xr[2], P.NetworkRegularizer)
+    assert all(np.allclose(w, np.full(K, 5.678)) for w in xr[1].group_weights) and np.allclose(xr[2].cur_weights, 1.234)
+    assert len(yr) == 3 and isinstance(yr[1], P.SelectiveL1Reg) and isinstance(yr[2], P.NetworkRegularizer)
+    assert np.all(np.asarray(yr[1].weight) == 1.0) and np.all(np.asarray(yr[2].cur_weights) == 1.0)
+
+
 def test_freeze_helpers():
     m = P.PathMatFacModel(np.zeros((6, 4), np.float32), K=2, feature_views=[1, 1, 2, 2],
                           sample_conditions=[0] * 6, batch_dict={1: [0, 0, 0, 1, 1, 1]})
