@@ -10,7 +10,9 @@ from .layers import (BatchArray, BatchScale, BatchShift, ColScale, ColShift, Fro
                      ViewableComposition, construct_model_layers, freeze_layer, unfreeze_layer)
 from .model import CompositeNoise, MatFacModel, PathMatFacModel
 from .transform import transform
-from .model_io import load_model, model_arrays, save_model, write_model_arrays
+from .model_io import (load_batches, load_model, load_omic_data, model_arrays, read_model_hdf, save_model, save_omic_data,
+                       save_transformed, write_model_arrays, write_model_to_hdf)
+from . import h5lite
 from . import staging      # fit!, basic_fit!, init_batch_effects!, ... (kept in their namespace: `fit` is also a submodule)
 from .postfit import (init_ordinal_thresholds, reorder_by_importance, reorder_reg, reweight_eb, rotate_by_svd,
                       whiten)
