@@ -46,27 +46,28 @@ def test_repo_arm_needs_a_cuda_device():
     assert r.returncode != 0 and "CUDA device" in (r.stderr + r.stdout)
 
 
-def test_repo_arm_control_flow_at_two_ranks_on_cpu(tmp_path):
-    """bench.py --gpus 2 launched exactly as the driver launches it (torch.distributed.run, 127.0.0.1), with the CUDA
+@pytest.mark.parametrize("n", [2, 4])
+def test_repo_arm_control_flow_at_two_ranks_on_cpu(tmp_path, n):
+    """bench.py --gpus N launched exactly as the driver launches it (torch.distributed.run, 127.0.0.1), with the CUDA
     pieces replaced by stand-ins (tests/bench_dryrun_worker.py): rendezvous, parameter broadcast, barriers, max over
     ranks, the end-to-end leg and the ONE JSON line of rank 0."""
     import socket
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-           "--master-port", str(port), os.path.join(ROOT, "tests", "bench_dryrun_worker.py"), "--gpus", "2", "--steps", "4",
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(ROOT, "tests", "bench_dryrun_worker.py"), "--gpus", str(n), "--steps", "4",
            "--warmup", "3", "--M", "96", "--N", "128", "--K", "8"]
     r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1, r.stdout
     d = json.loads(lines[0])
-    assert d["n_gpus"] == 2 and d["steps"] == 4 and d["warmup"] == 3 and d["scaling"] == "weak"
-    assert d["value"] == pytest.approx(2 / (d["ms_per_step"] / 1e3)) and d["gpu_launches"] == 9
-    assert d["config"]["parallelism"] == "sample-sharded x2" and d["config"]["per_rank_samples"] == 96
+    assert d["n_gpus"] == n and d["steps"] == 4 and d["warmup"] == 3 and d["scaling"] == "weak"
+    assert d["value"] == pytest.approx(n / (d["ms_per_step"] / 1e3)) and d["gpu_launches"] == 9
+    assert d["config"]["parallelism"] == f"sample-sharded x{n}" and d["config"]["per_rank_samples"] == 96
     e = d["e2e"]
     assert e["epochs_run"] == 4 and len(e["seconds_each_call"]) == 3 and e["seconds"] == sorted(e["seconds_each_call"])[1]
-    assert e["value"] == pytest.approx(2 * 4 / e["seconds"]) and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0
+    assert e["value"] == pytest.approx(n * 4 / e["seconds"]) and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0
     assert d["roofline"]["launches_timed"] == 4 and d["cpu_baseline"] is None      # CPU baseline at N = 1 only
     assert d["loss_first_last"][1] < d["loss_first_last"][0]

@@ -1,4 +1,4 @@
-"""World-size-2 gloo test (CPU) of the sample-sharded decomposition: each rank owns a
+"""World-size-2 and -4 gloo tests (CPU) of the sample-sharded decomposition: each rank owns a
 contiguous block of samples, computes its shard's loss and gradients (here with the CPU oracle,
 since there is no GPU), all-reduces the SHARED buffer [dY | dlogsigma | dmu | dtheta | dlogdelta]
 and the two rank-local loss scalars, then applies the identical AdaGrad update.  The result must
@@ -74,8 +74,8 @@ def test_shard_plan_is_a_partition():
 
 
 @pytest.mark.timeout(180)
-def test_two_rank_sharded_step_equals_full_batch():
-    world = 2
+@pytest.mark.parametrize("world", [2, 4])           # 37 samples: uneven shards at both sizes (18 + 19; 9 + 9 + 9 + 10)
+def test_two_rank_sharded_step_equals_full_batch(world):
     mgr = mp.Manager()
     out = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
@@ -205,11 +205,12 @@ def _sharded_worker(rank, world, port, out, epochs):
 
 
 @pytest.mark.timeout(300)
-def test_sharded_fit_class_over_gloo_matches_full_batch_fit():
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_fit_class_over_gloo_matches_full_batch_fit(world):
     """dist.ShardedFit (the product's host-driven exchange loop) on two gloo ranks, each over a stub engine that
     serves the ABI calls with the oracle on its row shard, against the single-process full-batch oracle fit: same
     loss curve, same term code, replicated parameters identical on both ranks, X equal to the matching columns."""
-    world, epochs = 2, 7
+    epochs = 7
     mgr = mp.Manager()
     out = mgr.dict()
     mp.spawn(_sharded_worker, args=(world, _free_port(), out, epochs), nprocs=world, join=True)
@@ -217,12 +218,13 @@ def test_sharded_fit_class_over_gloo_matches_full_batch_fit():
     _no_layer_regs(m)
     href = O.mf_fit(m, D, O.AdaGrad(0.25), max_epochs=epochs, rel_tol=1e-12, abs_tol=1e-12, update_X=True, update_Y=True,
                     update_col_layers=True)
-    r0, r1 = out[0], out[1]
-    for r in (r0, r1):
+    ranks = [out[r] for r in range(world)]
+    for r in ranks:
         assert r["stream_calls"] == 1
         assert r["h"]["term_code"] == href["term_code"] and r["h"]["epochs"] == href["epochs"]
         assert np.allclose(r["h"]["loss"], href["loss"], rtol=1e-10)
         assert np.allclose(r["Y"], m.Y, rtol=1e-9, atol=1e-11) and np.allclose(r["mu"], m.mu, rtol=1e-9, atol=1e-11)
         assert np.allclose(r["theta"], m.theta.values[0], rtol=1e-9, atol=1e-11)
         assert np.allclose(r["X"], m.X[:, r["rows"][0]:r["rows"][1]], rtol=1e-9, atol=1e-11)
-    assert np.array_equal(r0["Y"], r1["Y"])          # replicas never diverge
+    assert all(np.array_equal(ranks[0]["Y"], r["Y"]) for r in ranks[1:])          # replicas never diverge
+    assert [r["rows"] for r in ranks] == [(p.start, p.stop) for p in shard_plan(D.shape[0], world)]
