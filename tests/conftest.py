@@ -22,6 +22,12 @@ def _has_gpu():
 
 def pytest_collection_modifyitems(config, items):
     if _has_gpu():
+        # safety net: a deadlocked kernel must end the run, not hold the box.  The thread method of pytest-timeout
+        # ends the process even when the main thread is blocked inside a CUDA call (SIGALRM would never be served).
+        if config.pluginmanager.hasplugin("timeout"):
+            for item in items:
+                if "gpu" in item.keywords and item.get_closest_marker("timeout") is None:
+                    item.add_marker(pytest.mark.timeout(1200, method="thread"))
         return
     skip = pytest.mark.skip(reason="no CUDA device")
     for item in items:
