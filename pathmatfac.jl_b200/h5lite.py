@@ -121,7 +121,7 @@ class Dataset:
                 addr, sz = struct.unpack_from("<QQ", b, 2)
                 if addr == UNDEF:
                     return bytes(n)                         # never written: fill value 0
-                return f.at(addr, sz)
+                return f.view(addr, sz)                     # no copy: a data matrix can be gigabytes
             if cls == 2:
                 rank = b[2]
                 bt = struct.unpack_from("<Q", b, 3)[0]
@@ -138,7 +138,7 @@ class Dataset:
             dims = struct.unpack_from(f"<{rank}I", b, off)
             off += 4 * rank
             if cls == 1:
-                return f.at(addr, n) if addr != UNDEF else bytes(n)
+                return f.view(addr, n) if addr != UNDEF else bytes(n)
             if cls == 2:
                 return self._read_chunked(addr, dims[:-1] if len(dims) == len(self.shape) + 1 else dims, n)
             sz = struct.unpack_from("<I", b, off)[0]
@@ -288,6 +288,12 @@ class File(Group):
         if a + n > len(self.buf):
             raise H5Error(f"address {addr} + {n} bytes runs past the end of the file")
         return self.buf[a:a + n]
+
+    def view(self, addr: int, n: int) -> memoryview:
+        a = self.base + addr
+        if a + n > len(self.buf):
+            raise H5Error(f"address {addr} + {n} bytes runs past the end of the file")
+        return memoryview(self.buf)[a:a + n]
 
     def read(self, name: str, julia: bool = True):
         obj = self[name]
