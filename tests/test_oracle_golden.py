@@ -415,3 +415,34 @@ def test_alternating_and_threshold_training_are_options_of_the_oracle():
     assert np.array_equal(runs["plain"][1].noise.thresholds[1], m.noise.thresholds[1])
     assert not np.array_equal(runs["thr"][1].noise.thresholds[1][1:3], m.noise.thresholds[1][1:3])
     assert np.isinf(runs["thr"][1].noise.thresholds[1][[0, 3]]).all()
+
+
+def test_pinning_tool_identifies_the_epoch_order(tmp_path):
+    """oracle/pin_against_julia.py end to end with a stand-in for the Julia run: the "reference outputs" are written by
+    the oracle with `alternating=True`; the tool must rebuild the same model from the exported files, single out that
+    option combination and reject the other one.  (What it will do with julia/run_reference_fit.jl's real outputs.)"""
+    import pathmatfac_b200 as P
+    from pathmatfac_b200.simulate import export_problem
+    from oracle import pin_against_julia as pin
+    from tests.helpers import make_pair
+    views = {"mutation": ("bernoulli", 12), "methylation": ("normal", 20), "mrnaseq": ("normal", 18)}
+    model, om, D = make_pair(40, views, K=4, seed=11, batch_views=["methylation"], n_batches=3, n_conditions=2, missing=0.2)
+    d = str(tmp_path / "exp")
+    export_problem(model, d)
+    m0, D0 = pin.oracle_model_from_export(d, 4)
+    assert np.array_equal(np.isnan(D0), np.isnan(D)) and np.allclose(np.nan_to_num(D0), np.nan_to_num(D))
+    ref = O.total_loss_grads(om, D)                     # the rebuilt model is the model the pair was made from
+    got = O.total_loss_grads(m0, D0)
+    assert abs(got["loss"] - ref["loss"]) <= 1e-9 * abs(ref["loss"]) and np.allclose(got["dY"], ref["dY"], rtol=1e-9, atol=1e-12)
+    # stand-in for step 2: "the reference" alternates
+    O.mf_fit(m0, D0, O.AdaGrad(0.05), max_epochs=4, rel_tol=0.0, abs_tol=0.0, update_X=True, update_Y=True,
+             update_col_layers=True, alternating=True)
+    for k, v in pin.oracle_outputs(m0).items():
+        name = "ref_" + k.replace("/", "__") + ".bin"
+        np.asfortranarray(v.astype(np.float32)).tofile(os.path.join(d, name)) if v.ndim < 2 else \
+            open(os.path.join(d, name), "wb").write(np.asfortranarray(v.astype(np.float32)).tobytes(order="F"))
+    rows, match = pin.pin(d, 4, 0.05, 4)
+    assert match == {"alternating": True, "update_noise_models": False}
+    assert rows[0][2] < 1e-6 and rows[1][0]["alternating"] is False and rows[1][2] > 1e-4
+    assert pin.main([d, "--K", "4", "--lr", "0.05", "--epochs", "4"]) == 0
+    assert pin.main([d, "--K", "4", "--lr", "0.05", "--epochs", "3"]) == 1      # a different run does not match
