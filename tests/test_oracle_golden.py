@@ -446,3 +446,75 @@ def test_pinning_tool_identifies_the_epoch_order(tmp_path):
     assert rows[0][2] < 1e-6 and rows[1][0]["alternating"] is False and rows[1][2] > 1e-4
     assert pin.main([d, "--K", "4", "--lr", "0.05", "--epochs", "4"]) == 0
     assert pin.main([d, "--K", "4", "--lr", "0.05", "--epochs", "3"]) == 1      # a different run does not match
+
+
+def _fd_grad(f, X, idxs, eps=1e-6):
+    out = []
+    for idx in idxs:
+        old = X[idx]
+        X[idx] = old + eps
+        lp = f(X)
+        X[idx] = old - eps
+        lm = f(X)
+        X[idx] = old
+        out.append((lp - lm) / (2 * eps))
+    return np.array(out)
+
+
+def test_every_rrule_of_the_oracle_is_the_derivative_of_its_value():
+    """The reference writes its pullbacks by hand (src/regularizers.jl, src/featureset_ard.jl:141-150); apart from the
+    documented ColScale quirk each one is the true derivative of the value it comes with.  Central differences in
+    float64 on every regulariser the constructor can produce -- including the NetworkRegularizer, whose gradient
+    AA y + AB u is the derivative of the Schur-complement loss only because u minimises it (src/regularizers.jl:279-299)
+    -- and on all six noise models (MatFac.jl, restated: Appendix B)."""
+    rng = np.random.default_rng(17)
+    K, N = 3, 11
+    Y = rng.standard_normal((K, N))
+    idxs = [(0, 0), (1, 4), (2, 10), (0, 7)]
+    views = ["a"] * 4 + ["b"] * 7
+    fids = [f"f{j}" for j in range(N)]
+    edgelists = [[[fids[0], fids[1], 1.0], [fids[1], fids[2], -1.0], [fids[2], "virt", 1.0], ["virt", fids[5], 1.0],
+                  [fids[6], fids[7], 1.0]] for _ in range(K)]
+    fs = O.FeatureSetARDReg(K, views, [np.abs(rng.standard_normal((2, 4))), np.abs(rng.standard_normal((3, 7)))],
+                            [["s1", "s2"], ["t1", "t2", "t3"]], dtype=np.float64)
+    fs.beta = 0.5 + rng.random((K, N))
+    fs.alpha = 1.0 + rng.random(N)
+    regs = {
+        "l2": O.L2Regularizer(K, 0.8),
+        "group": O.GroupRegularizer(views, weight=0.7, K=K),
+        "selective_l1": O.SelectiveL1Reg(fids, edgelists, weight=0.3),
+        "network": O.NetworkRegularizer(fids, edgelists, epsilon=0.1, weight=1.3),
+        "ard": O.ARDRegularizer(views, alpha=1.001, beta=0.4),
+        "fsard": fs,
+    }
+    regs["composite"] = O.CompositeRegularizer([regs["l2"], regs["network"], regs["selective_l1"]], [0.5, 0.25, 0.25])
+    for name, r in regs.items():
+        g = r.grad(Y.copy())
+        fd = _fd_grad(lambda Z: r.value(Z), Y.copy(), idxs)
+        assert np.allclose([g[i] for i in idxs], fd, rtol=2e-5, atol=1e-7), (name, [g[i] for i in idxs], fd)
+    # layer penalties: per-view quadratics around a centre
+    v = rng.standard_normal(N)
+    cp = O.ColParamReg(views, weight=0.8, center=0.3)
+    assert np.allclose(cp.grad(v.copy())[[0, 5, 10]], _fd_grad(lambda z: cp.value(z), v.copy(), [0, 5, 10]), rtol=1e-5, atol=1e-8)
+    # noise models: d loss / dz per entry, missing entries contribute nothing
+    z = rng.standard_normal((6, 5)) * 1.5
+    thr = np.array([-np.inf, -0.7, 0.9, np.inf])
+    data = {"normal": rng.standard_normal((6, 5)), "bernoulli": (rng.random((6, 5)) < 0.5).astype(float),
+            "poisson": rng.poisson(2.0, (6, 5)).astype(float), "bernoulli_sq_hinge": (rng.random((6, 5)) < 0.5).astype(float),
+            "ordinal3": rng.integers(1, 4, (6, 5)).astype(float), "ordinal_sq_hinge3": rng.integers(1, 4, (6, 5)).astype(float)}
+    for dist, a in data.items():
+        a[1, 2] = np.nan
+        l, g = O.noise_loss_grad(dist, z, a, thr)
+        assert l[1, 2] == 0.0 and g[1, 2] == 0.0
+        eps = 1e-6
+        lp, _ = O.noise_loss_grad(dist, z + eps, a, thr)
+        lm, _ = O.noise_loss_grad(dist, z - eps, a, thr)
+        assert np.allclose(g, (lp - lm) / (2 * eps), rtol=1e-5, atol=1e-6), dist
+        if dist.startswith("ordinal"):                       # and the interior thresholds (D7)
+            g1, g2 = O.noise_threshold_grads(dist, z, a, thr)
+            for j, gj in ((1, g1), (2, g2)):
+                tp, tm = thr.copy(), thr.copy()
+                tp[j] += eps
+                tm[j] -= eps
+                fdj = (O.noise_loss_grad(dist, z, a, tp)[0] - O.noise_loss_grad(dist, z, a, tm)[0]) / (2 * eps)
+                assert np.allclose(gj, fdj, rtol=1e-5, atol=1e-6), (dist, j)
