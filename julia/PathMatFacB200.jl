@@ -109,7 +109,7 @@ function push_layout!(h::Handle, model)
         nv = length(ld.col_ranges); M = size(model.data, 1)
         cs = i32([r.start - 1 for r in ld.col_ranges]); ce = i32([r.stop for r in ld.col_ranges])
         nb = i32([size(v, 1) for v in ld.values])
-        bos = Matrix{Int32}(undef, M, nv)                  # column v = batch ordinal (0-based) of every sample
+        bos = fill(Int32(-1), M, nv)                       # column v = batch ordinal (0-based) of every sample; -1 = none
         for v in 1:nv
             I, J, _ = findnz(sparse(ld.row_batches[v]))
             bos[I, v] .= Int32.(J .- 1)
