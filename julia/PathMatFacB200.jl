@@ -109,7 +109,8 @@ function push_layout!(h::Handle, model)
         nv = length(ld.col_ranges); M = size(model.data, 1)
         cs = i32([r.start - 1 for r in ld.col_ranges]); ce = i32([r.stop for r in ld.col_ranges])
         nb = i32([size(v, 1) for v in ld.values])
-        bos = fill(Int32(-1), M, nv)                       # column v = batch ordinal (0-based) of every sample; -1 = none
+        bos = fill(Int32(-1), M, nv)                       # column v = batch ordinal (0-based) of every sample; a row of
+                                                           # row_batches[v] without a nonzero stays -1, which the library refuses
         for v in 1:nv
             I, J, _ = findnz(sparse(ld.row_batches[v]))
             bos[I, v] .= Int32.(J .- 1)
