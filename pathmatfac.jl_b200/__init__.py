@@ -13,6 +13,7 @@ from .transform import transform
 from .model_io import (load_batches, load_model, load_omic_data, model_arrays, read_model_hdf, save_model, save_omic_data,
                        save_transformed, write_model_arrays, write_model_to_hdf)
 from . import h5lite
+from .prep_pathways import prep_pathway_featuresets, prep_pathway_graphs
 from . import staging      # fit!, basic_fit!, init_batch_effects!, ... (kept in their namespace: `fit` is also a submodule)
 from .postfit import (init_ordinal_thresholds, reorder_by_importance, reorder_reg, reweight_eb, rotate_by_svd,
                       whiten)
