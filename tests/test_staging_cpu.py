@@ -124,3 +124,39 @@ def test_fit_ard_and_featureset_ard_paths():
     first_update = names.index("update_A")
     assert [d["Y_reg"] for n, d in OB.CALLS[:first_update] if n == "mf_fit_adapt_lr"] == ["GroupRegularizer", "ARDRegularizer"]
     assert [d["Y_reg"] for n, d in OB.CALLS[first_update:] if n == "mf_fit_adapt_lr"] == ["FeatureSetARDReg"]
+
+
+def test_reference_fit_tests_featureset_ard_fit_cpu():
+    """The reference's own integration test, the one ``fit_tests`` still runs (test/runtests.jl:1134-1171, 1321-1346:
+    "Featureset ARD fit CPU"), transcribed: 40 x 60, K = 4, two views x four row batches, five feature sets per view,
+    ``Y_fsard`` with ``fsard_v0 = 0.5``, then ``fit!(model; lr=0.05, max_epochs=1000, rel_tol=1e-5, abs_tol=1e-5, fsard_term_rtol=1e-3,
+    fsard_max_iter=10, fsard_max_A_iter=500)`` and its three assertions: X changed, Y changed, the batch scales changed.
+    Every device-touching call is served by the oracle (tests/oracle_backend.py), the staging is the product's."""
+    M, N, K = 40, 60, 4
+    rng = np.random.default_rng(1134)
+    Z = (rng.standard_normal((K, M)).T @ rng.standard_normal((K, N))).astype(np.float32)
+    sample_ids = [f"sample_{i}" for i in range(1, M + 1)]
+    sample_conditions = ["condition_1"] * (M // 2) + ["condition_2"] * (M // 2)
+    feature_ids = [f"x_{i}" for i in range(1, N + 1)]
+    feature_views = [1] * (N // 2) + [2] * (N // 2)
+    batch_dict = {j: [f"rowbatch{i}" for i in range(1, 5) for _ in range(M // 4)] for j in (1, 2)}
+    blocks = [[range(1, 6), range(6, 11), range(11, 16), range(16, 21), range(21, 31)],
+              [range(31, 36), range(36, 41), range(41, 46), range(46, 51), range(51, 61)]]
+    feature_sets = {v + 1: [{f"x_{i}" for i in s} for s in blk] for v, blk in enumerate(blocks)}
+    model = P.PathMatFacModel(Z, K=4, sample_ids=sample_ids, sample_conditions=sample_conditions, feature_views=feature_views,
+                              feature_ids=feature_ids, batch_dict=batch_dict, feature_sets_dict=feature_sets, Y_fsard=True,
+                              fsard_v0=0.5, rng=np.random.default_rng(7))
+    assert isinstance(model.matfac.Y_reg, P.FeatureSetARDReg) and model.matfac.Y_reg.v0 == np.float32(0.5)
+    assert [S_.shape for S_ in model.matfac.Y_reg.S] == [(5, 30), (5, 30)]
+    X_start, Y_start = model.matfac.X.copy(), model.matfac.Y.copy()
+    logdelta_start = [v.copy() for v in model.matfac.col_transform.layers[1].logdelta.values]
+    OB.CALLS.clear()
+    S.fit(model, lr=0.05, max_epochs=1000, rel_tol=1e-5, abs_tol=1e-5, fsard_term_rtol=1e-3, fsard_max_iter=10,
+          fsard_max_A_iter=500, backend=OB.BACKEND)
+    assert not np.allclose(model.matfac.X, X_start)                                            # :1340
+    assert not np.allclose(model.matfac.Y, Y_start)                                            # :1341
+    assert not all(np.allclose(a, b) for a, b in zip(logdelta_start, model.matfac.col_transform.layers[1].logdelta.values))
+    names = _names()
+    assert "theta_delta_em" in names or "init_batch_effects" in names or any("batch" in n for n in names), names
+    assert names.count("update_A") >= 1 and all(np.isfinite(model.matfac.Y).ravel())
+    assert np.all(model.matfac.Y_reg.beta > 0)
