@@ -567,3 +567,18 @@ def test_save_load_model_round_trip(tmp_path):
     with pytest.raises(ValueError):
         (tmp_path / "junk.bin").write_bytes(__import__("pickle").dumps({"format": "other"}))
         P.load_model(tmp_path / "junk.bin")
+
+
+def test_nccl_is_found_without_a_gpu():
+    """The exchange step loads NCCL with dlopen on the first pmf_comm_* call; ncclGetUniqueId needs no device, so the
+    lookup (torch's bundled libnccl.so.2 when torch is imported first, else the system one) is checked here."""
+    import ctypes as C
+    import torch  # noqa: F401  (the order bench.py and the tests import in)
+    from pathmatfac_b200 import _lib
+    lib = _lib.load()
+    a, b = (C.c_uint8 * 128)(), (C.c_uint8 * 128)()
+    assert lib.pmf_comm_unique_id(a) == 0 and lib.pmf_comm_unique_id(b) == 0
+    assert any(bytes(a)) and bytes(a) != bytes(b)
+    assert lib.pmf_comm_unique_id(None) != 0                      # null buffer: an error code, not a crash
+    mapped = {l.split()[-1] for l in open("/proc/self/maps") if "libnccl" in l}
+    assert len(mapped) == 1, mapped                                # one NCCL in the process, not two
