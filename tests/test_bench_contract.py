@@ -25,7 +25,11 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["higher_is_better"] is True and d["unit"] == "iter/s"
     assert d["steps"] == 2 and d["warmup"] == 1 and d["value"] > 0 and d["ms_per_step"] > 0
-    assert abs(d["value"] * d["ms_per_step"] / 1e3 - 1.0) < 1e-9           # iterations/sec <-> ms per step
+    # ms_per_step is the arm's own (bounded) step, so that steps x ms_per_step is its real timed region; value is in the
+    # metric's unit (scaled to the workload's full sample count)
+    assert abs(d["value"] * d["ms_per_full_step_extrapolated"] / 1e3 - 1.0) < 1e-9
+    assert d["ms_per_step"] <= d["ms_per_full_step_extrapolated"] * (1 + 1e-12)
+    assert d["steps"] * d["ms_per_step"] / 1e3 < 60                        # what the driver checks against its own clock
     assert d["e2e"] == {"value": d["value"], "unit": "iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "samples" in cb["sample"]
@@ -70,4 +74,12 @@ def test_repo_arm_control_flow_at_two_ranks_on_cpu(tmp_path, n):
     assert e["epochs_run"] == 4 and len(e["seconds_each_call"]) == 3 and e["seconds"] == sorted(e["seconds_each_call"])[1]
     assert e["value"] == pytest.approx(n * 4 / e["seconds"]) and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0
     assert d["roofline"]["launches_timed"] == 4 and d["cpu_baseline"] is None      # CPU baseline at N = 1 only
+    # the reference arm, launched with the same arguments, prints the SAME `config` (the driver compares them)
+    ref = _run(["--impl", "reference", "--gpus", str(n), "--steps", "4", "--warmup", "3", "--M", "96", "--N", "128", "--K", "8"],
+               env={"RANK": "0", "LOCAL_RANK": "0", "WORLD_SIZE": str(n)})
+    assert ref.returncode == 0, ref.stderr[-2000:]
+    rd = json.loads(ref.stdout.strip().splitlines()[-1])
+    assert rd["config"] == d["config"] and rd["metric"] == d["metric"] and rd["unit"] == d["unit"]
+    assert rd["steps"] == d["steps"] and rd["warmup"] == d["warmup"] and rd["higher_is_better"] == d["higher_is_better"]
+    assert rd["n_gpus"] == d["n_gpus"] and "kernel" in d["arm"] and "note" in rd["arm"]
     assert d["loss_first_last"][1] < d["loss_first_last"][0]
