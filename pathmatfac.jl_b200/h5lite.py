@@ -559,7 +559,7 @@ class Writer:
         space = struct.pack("<BBBBI", 1, len(shape), 0, 0, 0) + b"".join(struct.pack("<Q", d) for d in shape)
         msgs = [_message(0x0001, space),
                 _message(0x0003, tmsg, flags=1),                                     # constant
-                _message(0x0005, struct.pack("<BBBBI", 2, 2, 2, 1, 0)),              # fill value v2: late allocation, written if set, the default value
+                _message(0x0005, struct.pack("<BBBBI", 2, 2, 2, 1, 0), flags=1),     # fill value v2: late allocation, written if set, the default value
                 _message(0x0008, struct.pack("<BBQQ", 3, 1, daddr, len(raw)))]       # layout v3, contiguous
         return self._alloc(_object_header(msgs))
 

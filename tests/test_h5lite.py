@@ -50,6 +50,17 @@ def test_writer_emits_the_messages_libhdf5_wrote():
     g = h5lite.File(w.tobytes())
     mine = dict((t, b) for t, b in g._messages(g._members["testdouble"]) if t in (1, 3))
     assert mine[1] == msgs[1] and mine[3][:20] == msgs[3][:20]
+
+    def flags(file, addr):                                   # message type -> flag byte, first header block
+        hsize = struct.unpack_from("<I", file.at(addr, 16), 8)[0]
+        blk, off, out = file.at(addr + 16, hsize), 0, {}
+        while off + 8 <= hsize:
+            t, sz, fl = struct.unpack_from("<HHB", blk, off)
+            out.setdefault(t, fl)
+            off += 8 + sz
+        return out
+    theirs, ours = flags(f, f._members["testdouble"]), flags(g, g._members["testdouble"])
+    assert all(ours[t] == theirs[t] for t in (1, 3, 5))      # dataspace 0, datatype and fill value "constant"
     assert np.array_equal(g.read("testdouble"), f.read("testdouble"))
     # the local heap of the anchor: the empty string at offset 0, names null-terminated and 8-aligned, the free list
     # closed by a block whose "next" is 1 -- the conventions the writer follows
