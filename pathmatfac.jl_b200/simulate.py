@@ -237,3 +237,16 @@ def import_problem_arrays(directory: str) -> Dict[str, np.ndarray]:
         dt = np.float32 if ty == "Float32" else np.int32
         out[name] = np.fromfile(os.path.join(directory, name + ".bin"), dtype=dt).reshape((int(r), int(c)), order="F")
     return out
+
+
+def export_problem_hdf(model, path: str, barcodes=None, barcode_features=None) -> str:
+    """The same inputs in the study's own HDF5 layout (``omic_data/{data, feature_assays, feature_genes, instances,
+    instance_groups}`` [+ ``barcodes/*``], analyses/scripts/julia/script_util.jl:165-180), so that the reference's
+    driver script fit_matfac.jl -- not only a custom loader -- can read a simulated problem (``load_omic_data``,
+    fit_matfac.jl:60-82): views become the assays, feature ids the genes, sample conditions the instance groups."""
+    from .model_io import save_omic_data
+    M = np.asarray(model.data).shape[0]
+    groups = model.sample_conditions if model.sample_conditions is not None else ["all"] * M
+    return save_omic_data(path, [str(v) for v in model.feature_views], [str(f) for f in model.feature_ids],
+                          [str(x) for x in model.sample_ids], [str(g) for g in groups], np.asarray(model.data),
+                          barcodes=barcodes, barcode_features=barcode_features)

@@ -388,3 +388,17 @@ def test_omic_hdf_layout_round_trip(tmp_path):
     assert f.visit() == ["X", "instance_groups", "instances", "target"]
     assert np.array_equal(f.read("X"), model.matfac.X) and list(f.read("instances")) == sid
     assert np.array_equal(f.read("target"), np.arange(M) % 2)
+
+
+def test_simulated_problem_in_the_studys_input_layout(tmp_path):
+    """simulate.export_problem_hdf -> the file fit_matfac.jl's load_omic_data reads (fit_matfac.jl:60-82)."""
+    from pathmatfac_b200.simulate import export_problem_hdf, simulate_problem
+    blocks = [("mutation", "bernoulli", 6), ("methylation", "normal", 10), ("mrnaseq", "normal", 8)]
+    model = simulate_problem(30, blocks=blocks, K=3, seed=5, missing=0.2)
+    path = export_problem_hdf(model, str(tmp_path / "omic.hdf"))
+    walk_structure(open(path, "rb").read())
+    D, sid, cond, genes, assays = P.load_omic_data(path, ["methylation", "mrnaseq"])
+    keep = [j for j, v in enumerate(model.feature_views) if v in ("methylation", "mrnaseq")]
+    assert assays == [model.feature_views[j] for j in keep] and genes == [str(model.feature_ids[j]) for j in keep]
+    assert np.array_equal(D, np.asarray(model.data)[:, keep], equal_nan=True) and np.isnan(D).any()
+    assert sid == [str(x) for x in model.sample_ids] and len(cond) == 30
