@@ -1,0 +1,181 @@
+"""What ``fit.Engine`` hands to the C ABI, checked on CPU against a recording stand-in for libpmf: array layouts (the
+reference's column-major K x M / K x N / M x N arrays as [M][K] / [N][K] / [N][M] buffers), 0-based half-open ranges, the
+frozen masks, mixture weights, closure regularisers -- and the ROW-SHARD logic of the sample-sharded multi-GPU path
+(``rows=``): a rank's X columns, its rows of the data and of the batch index, the condition groups clipped to its block,
+the refusal of a sample-coupling penalty.  The GPU suite exercises the same code against the real library; this file
+makes the N > 1 marshalling fail on CPU when it breaks."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import pathmatfac_b200 as P
+from pathmatfac_b200 import _lib, fit as F
+
+
+class RecordingLib:
+    """Every entry point returns 0 and records (name, args); pointer arguments are kept as ctypes pointers and decoded
+    by the test with the sizes the header documents."""
+
+    def __init__(self):
+        self.calls = []
+
+    def __getattr__(self, name):
+        if not name.startswith("pmf_"):
+            raise AttributeError(name)
+
+        def fn(*args):
+            self.calls.append((name, args))
+            if name == "pmf_last_error":
+                return b""
+            if name == "pmf_default_fit_opts":
+                return None
+            return 0
+        return fn
+
+    def of(self, name):
+        return [a for n, a in self.calls if n == name]
+
+
+def arr(ptr, n, dtype=np.float32):
+    if ptr is None:
+        return None
+    return np.ctypeslib.as_array(ptr, shape=(n,)).astype(dtype).copy()
+
+
+@pytest.fixture
+def lib(monkeypatch):
+    rec = RecordingLib()
+    monkeypatch.setattr(_lib, "load", lambda: rec)
+    monkeypatch.setattr(F._lib, "load", lambda: rec)
+    return rec
+
+
+def _model(M=20, K=3, **kw):
+    rng = np.random.default_rng(0)
+    views = ["methylation"] * 5 + ["mrnaseq"] * 4 + ["mutation"] * 3
+    dists = ["normal"] * 9 + ["bernoulli"] * 3
+    D = rng.standard_normal((M, 12)).astype(np.float32)
+    D[3, 4] = np.nan
+    cond = ["c1"] * 8 + ["c2"] * 7 + ["c3"] * (M - 15)
+    batch = {"methylation": [f"b{(i * 7) % 3}" for i in range(M)], "mrnaseq": [f"p{i % 2}" for i in range(M)]}
+    model = P.PathMatFacModel(D, K=K, feature_views=views, feature_distributions=dists, sample_conditions=cond,
+                              batch_dict=batch, **kw)
+    mf = model.matfac
+    mf.X[...] = rng.standard_normal(mf.X.shape)
+    mf.Y[...] = rng.standard_normal(mf.Y.shape)
+    ct = mf.col_transform
+    ct.layers[0].logsigma[...] = rng.standard_normal(12)
+    ct.layers[2].mu[...] = rng.standard_normal(12)
+    for v in ct.layers[1].logdelta.values + ct.layers[3].theta.values:
+        v[...] = rng.standard_normal(v.shape)
+    return model
+
+
+def test_full_model_layouts_ranges_and_masks(lib):
+    model = _model(lambda_X_l2=0.5)
+    M, N, K = 20, 12, 3
+    P.freeze_layer(model.matfac.col_transform, [2, 4])
+    eng = P.Engine(model)
+    dims = lib.of("pmf_create")[0][0]._obj
+    assert (dims.M, dims.N, dims.K, dims.device) == (M, N, K, 0)
+    # data: the reference's column-major M x N = [N][M]; NaN stays NaN
+    (h, p), = lib.of("pmf_set_data")
+    A = arr(p, N * M).reshape(N, M)
+    assert np.array_equal(A, np.asarray(model.data).T, equal_nan=True) and np.isnan(A).sum() == 1
+    # factors: K x M / K x N column-major = [M][K] / [N][K]
+    (h, px, py), = lib.of("pmf_set_factors")
+    assert np.array_equal(arr(px, M * K).reshape(M, K), model.matfac.X.T)
+    assert np.array_equal(arr(py, N * K).reshape(N, K), model.matfac.Y.T)
+    # noise ranges: sorted (distribution, view) blocks, 0-based half-open; one code per range
+    h, nr, cs, ce, dc, th, w = lib.of("pmf_set_noise")[0]
+    assert nr == 2 and list(arr(cs, 2, np.int32)) == [0, 3] and list(arr(ce, 2, np.int32)) == [3, 12]
+    assert list(arr(dc, 2, np.int32)) == [1, 0] and np.array_equal(arr(w, N), np.ones(N, np.float32))   # bernoulli, normal
+    assert model.feature_distributions[:3] == ["bernoulli"] * 3                    # the constructor sorted the columns
+    # batch layout: two batched views after the bernoulli block, batch ordinals in first-appearance order
+    h, nv, bcs, bce, nb, bos = lib.of("pmf_set_batch_layout")[0]
+    assert nv == 2 and list(arr(bcs, 2, np.int32)) == [3, 8] and list(arr(bce, 2, np.int32)) == [8, 12]
+    assert list(arr(nb, 2, np.int32)) == [3, 2]
+    B = arr(bos, 2 * M, np.int32).reshape(2, M)
+    ld = model.matfac.col_transform.unwrapped(1).logdelta
+    assert np.array_equal(B[0], ld.batch_index[0]) and np.array_equal(B[1], ld.batch_index[1])
+    assert list(B[0][:4]) == [0, 1, 2, 0] and list(B[1][:4]) == [0, 1, 0, 1]
+    # batch values: n_b x N_v column-major = [N_v][n_b]
+    vals = lib.of("pmf_set_batch_values")
+    assert [a[1] for a in vals] == [0, 1]
+    assert np.array_equal(arr(vals[0][2], 15).reshape(5, 3), ld.values[0].T)
+    th_ba = model.matfac.col_transform.unwrapped(3).theta
+    assert np.array_equal(arr(vals[1][3], 8).reshape(4, 2), th_ba.values[1].T)
+    # frozen masks: bit s-1 per slot s; layers 2 and 4 frozen
+    h, fl, fr = lib.of("pmf_set_frozen")[0]
+    assert fl == 0b1010 and fr == 0
+    # X penalty: with conditions AND lambda_X_l2 the constructor mixes L2 and the condition groups half and half
+    l2 = [a for a in lib.of("pmf_set_reg_l2") if a[1] == 0]
+    grp = [a for a in lib.of("pmf_set_reg_group") if a[1] == 0]
+    assert len(l2) >= 1 and len(grp) >= 1
+    assert l2[0][3] == pytest.approx(0.5) and grp[0][6] == pytest.approx(0.5)      # mixture weights (regularizers.jl:655-689)
+    assert np.allclose(arr(l2[0][2], K), 0.5)
+    ng = grp[0][2]
+    assert ng == 3 and list(arr(grp[0][3], 3, np.int32)) == [0, 8, 15] and list(arr(grp[0][4], 3, np.int32)) == [8, 15, 20]
+    eng.close()
+
+
+def test_row_shard_marshalling(lib):
+    """rank 1 of 3 on 20 samples owns rows 6..12: its X columns, its rows of the data and of the batch index, the
+    condition groups clipped to the block (c1 = 0..8 -> [0, 2), c2 = 8..15 -> [2, 7) in local coordinates)."""
+    from pathmatfac_b200.dist import shard_rows
+    model = _model()
+    rows = shard_rows(20, 1, 3)
+    assert (rows.start, rows.stop) == (6, 13)
+    eng = P.Engine(model, rows=rows)
+    Ms, N, K = 7, 12, 3
+    dims = lib.of("pmf_create")[0][0]._obj
+    assert (dims.M, dims.N, dims.K) == (Ms, N, K)
+    A = arr(lib.of("pmf_set_data")[0][1], N * Ms).reshape(N, Ms)
+    assert np.array_equal(A, np.asarray(model.data)[6:13].T, equal_nan=True)
+    (h, px, py), = lib.of("pmf_set_factors")
+    assert np.array_equal(arr(px, Ms * K).reshape(Ms, K), model.matfac.X[:, 6:13].T)
+    assert np.array_equal(arr(py, N * K).reshape(N, K), model.matfac.Y.T)                 # Y is replicated
+    h, nv, bcs, bce, nb, bos = lib.of("pmf_set_batch_layout")[0]
+    B = arr(bos, 2 * Ms, np.int32).reshape(2, Ms)
+    ld = model.matfac.col_transform.unwrapped(1).logdelta
+    assert np.array_equal(B[0], ld.batch_index[0][6:13]) and np.array_equal(B[1], ld.batch_index[1][6:13])
+    assert list(arr(nb, 2, np.int32)) == [3, 2]                                           # batch tables stay whole
+    grp = [a for a in lib.of("pmf_set_reg_group") if a[1] == 0][0]
+    assert grp[2] == 2 and list(arr(grp[3], 2, np.int32)) == [0, 2] and list(arr(grp[4], 2, np.int32)) == [2, 7]
+    # downloads land in the rank's columns only
+    lib.calls.clear()
+    before = model.matfac.X.copy()
+    eng.pull_params()
+    (h, px, py), = lib.of("pmf_get_factors")
+    assert np.array_equal(model.matfac.X[:, :6], before[:, :6]) and np.array_equal(model.matfac.X[:, 13:], before[:, 13:])
+    eng.close()
+
+
+def test_sample_coupling_penalty_is_refused_on_a_shard(lib):
+    """a NetworkRegularizer on X (sample_graphs) couples samples -- replicas only."""
+    rng = np.random.default_rng(1)
+    M, N, K = 12, 6, 2
+    sids = [f"s{i}" for i in range(M)]
+    graphs = [[[sids[i], sids[i + 1], 1.0] for i in range(M - 1)] for _ in range(K)]
+    model = P.PathMatFacModel(rng.standard_normal((M, N)).astype(np.float32), sample_ids=sids, sample_graphs=graphs,
+                              lambda_X_graph=1.0)
+    P.Engine(model).close()                                   # the whole problem on one handle: fine
+    assert any(a[1] == 0 for a in lib.of("pmf_set_reg_network"))
+    with pytest.raises(_lib.PmfError, match="not shardable"):
+        P.Engine(model, rows=range(0, 6))
+
+
+def test_closure_and_composite_regularisers(lib):
+    model = _model()
+    K = 3
+    model.matfac.X_reg = lambda X: 0.5 * np.float32(0.3) * float((X * X).sum())        # src/fit.jl:686-style closure
+    model.matfac.Y_reg = lambda Y: 0.0                                                   # the zero closures
+    eng = P.Engine(model)
+    l2 = lib.of("pmf_set_reg_l2")
+    assert [a[1] for a in l2] == [0] and np.allclose(arr(l2[0][2], K), 0.3, rtol=1e-5) and l2[0][3] == 1.0
+    assert [a[1] for a in lib.of("pmf_clear_reg")] == [0, 1]
+    model.matfac.X_reg = lambda X: float(np.abs(X).sum())                                # not one of the reference's
+    with pytest.raises(_lib.PmfError, match="unsupported regulariser closure"):
+        eng.push_regs()
+    eng.close()
