@@ -179,3 +179,61 @@ def test_closure_and_composite_regularisers(lib):
     with pytest.raises(_lib.PmfError, match="unsupported regulariser closure"):
         eng.push_regs()
     eng.close()
+
+
+class ScriptedLib(RecordingLib):
+    """RecordingLib whose pmf_fit plays a script of (term_code, last epoch) results."""
+
+    def __init__(self, script):
+        super().__init__()
+        self.script = list(script)
+        self.fits = []
+
+    def __getattr__(self, name):
+        base = super().__getattr__(name)
+        if name != "pmf_fit":
+            return base
+
+        def fit(h, opts, hist):
+            o, hh = opts._obj, hist._obj
+            term, last = self.script.pop(0)
+            self.fits.append(dict(epoch=o.epoch, max_epochs=o.max_epochs, lr=o.lr, update_X=o.update_X, update_Y=o.update_Y,
+                                  update_col_layers=o.update_col_layers, update_noise_models=o.update_noise_models,
+                                  rel_tol=o.rel_tol))
+            n = min(last - o.epoch + 1, hh.capacity)
+            for i in range(n):
+                hh.loss_total[i] = 100.0 - (o.epoch + i)
+            hh.term_code, hh.epochs, hh.n_recorded, hh.kernel_launches = term, last, n, 2 * n
+            return base(h, opts, hist)
+        return fit
+
+
+def test_restart_policy_of_mf_fit_adapt_lr(monkeypatch):
+    """src/fit.jl:46-75 in the mirror, on CPU: "loss_increase" halves eta and resumes AT the epoch that raised it with
+    the SAME optimiser (accumulators reset once, when the optimiser first meets the handle); any other code ends the
+    loop; so does eta < min_lr.  The GPU suite checks the same against the real library (test_lr_halving_restart_policy)."""
+    LOSS_INCREASE, MAX_EPOCHS, REL_TOL = 3, 0, 2
+    rec = ScriptedLib([(LOSS_INCREASE, 7), (LOSS_INCREASE, 12), (REL_TOL, 30)])
+    monkeypatch.setattr(_lib, "load", lambda: rec)
+    model = _model()
+    hs = P.mf_fit_adapt_lr(model, lr=0.8, min_lr=0.01, max_epochs=50, update_X=True, update_Y=True, verbosity=0, rel_tol=1e-7)
+    assert [h["term_code"] for h in hs] == ["loss_increase", "loss_increase", "rel_tol"]
+    assert [f["epoch"] for f in rec.fits] == [1, 7, 12] and all(f["max_epochs"] == 50 for f in rec.fits)
+    assert np.allclose([f["lr"] for f in rec.fits], [0.8, 0.4, 0.2])
+    assert all(f["update_X"] == 1 and f["update_Y"] == 1 and f["update_col_layers"] == 0 for f in rec.fits)
+    assert all(f["update_noise_models"] == 1 and f["rel_tol"] == 1e-7 for f in rec.fits)       # src/fit.jl:14 default
+    assert len(rec.of("pmf_reset_opt_state")) == 1                  # AdaGrad state survives the restarts (:55-64)
+    assert [h["name"] for h in hs] == ["mf_fit_lr=0.8", "mf_fit_lr=0.4", "mf_fit_lr=0.2"] and hs[0]["epochs"] == 7
+    assert hs[1]["loss"] == [100.0 - e for e in range(7, 13)]
+    assert model._engine is None                                    # the residency taken for the call was released
+    # eta below min_lr ends the loop even though the last call asked for a restart
+    rec2 = ScriptedLib([(LOSS_INCREASE, 3), (LOSS_INCREASE, 4), (LOSS_INCREASE, 5)])
+    monkeypatch.setattr(_lib, "load", lambda: rec2)
+    hs = P.mf_fit_adapt_lr(_model(), lr=0.1, min_lr=0.04, max_epochs=50, update_Y=True, verbosity=0)
+    assert len(hs) == 2 and np.allclose([f["lr"] for f in rec2.fits], [0.1, 0.05])
+    # a history list handed in is appended to (src/fit.jl:61)
+    rec3 = ScriptedLib([(MAX_EPOCHS, 9)])
+    monkeypatch.setattr(_lib, "load", lambda: rec3)
+    hist = [{"name": "earlier"}]
+    P.mf_fit_adapt_lr(_model(), lr=1.0, max_epochs=9, update_X=True, verbosity=0, history=hist)
+    assert [h["name"] for h in hist] == ["earlier", "mf_fit_lr=1.0"] and hist[1]["term_code"] == "max_epochs"
