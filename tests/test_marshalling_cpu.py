@@ -237,3 +237,39 @@ def test_restart_policy_of_mf_fit_adapt_lr(monkeypatch):
     hist = [{"name": "earlier"}]
     P.mf_fit_adapt_lr(_model(), lr=1.0, max_epochs=9, update_X=True, verbosity=0, history=hist)
     assert [h["name"] for h in hist] == ["earlier", "mf_fit_lr=1.0"] and hist[1]["term_code"] == "max_epochs"
+
+
+def test_transform_host_logic(monkeypatch):
+    """src/transform.jl:6-106 in the mirror, on CPU: new columns are matched to the training features by id (unmatched
+    training columns become NaN = missing, unknown new columns are dropped), batch layers and factor penalties are dropped,
+    the column layers and their penalties frozen, X starts at zero and is the only thing fitted; the training model keeps
+    its data.  (GPU: test_transform_new_samples.)"""
+    rec = ScriptedLib([(2, 17)])
+    monkeypatch.setattr(_lib, "load", lambda: rec)
+    model = _model(lambda_X_l2=1.0)
+    N, K = 12, 3
+    ids = [f"f{j}" for j in range(N)]
+    model.feature_ids = list(ids)
+    rng = np.random.default_rng(5)
+    new_ids = [f"f{j}" for j in range(5, 15)]                       # f5..f11 known, f12..f14 unknown
+    D_new = rng.standard_normal((6, 10)).astype(np.float32)
+    data_before = np.asarray(model.data).copy()
+    res = P.transform(model, D_new, feature_ids=new_ids, verbosity=0, lr=0.05, max_epochs=40)
+    assert np.array_equal(np.asarray(model.data), data_before, equal_nan=True) and model._engine is None
+    assert res.matfac.X.shape == (K, 6) and res.matfac.Y.shape == (K, N) and res.sample_ids == [1, 2, 3, 4, 5, 6]
+    dims = rec.of("pmf_create")[0][0]._obj
+    assert (dims.M, dims.N, dims.K) == (6, N, K)
+    A = arr(rec.of("pmf_set_data")[0][1], N * 6).reshape(N, 6).T          # back to samples x features
+    assert np.isnan(A[:, :5]).all() and np.array_equal(A[:, 5:], D_new[:, :7])
+    px = rec.of("pmf_set_factors")[0][1]
+    assert not arr(px, 6 * K).any()                                        # X = 0
+    assert rec.of("pmf_set_batch_layout")[0][1] == 0                       # batch effects are ignored on new data
+    assert not rec.of("pmf_set_reg_l2") and not rec.of("pmf_set_reg_group")        # X_reg, Y_reg dropped
+    masks = rec.of("pmf_set_frozen")[-1]
+    # column layers and their penalties frozen (slots 2 and 4 are identities here: nothing to freeze on the device)
+    assert masks[1] & 0b0101 == 0b0101 and masks[2] & 0b0101 == 0b0101
+    (f,) = rec.fits
+    assert (f["update_X"], f["update_Y"], f["update_col_layers"]) == (1, 0, 0) and f["max_epochs"] == 40
+    assert f["lr"] == pytest.approx(0.05)
+    with pytest.raises(AssertionError, match="Provide `feature_ids`"):
+        P.transform(model, D_new, verbosity=0)                             # 10 columns against 12, no ids
