@@ -273,3 +273,58 @@ def test_transform_host_logic(monkeypatch):
     assert f["lr"] == pytest.approx(0.05)
     with pytest.raises(AssertionError, match="Provide `feature_ids`"):
         P.transform(model, D_new, verbosity=0)                             # 10 columns against 12, no ids
+
+
+def test_graph_selective_l1_and_fsard_marshalling(lib):
+    """The Y-side regularisers with structure: the K per-factor Laplacians as concatenated CSR blocks AA / AB / BB (each
+    block's row pointer starts at 0), the selective-L1 mask as [N][K] bytes, the FSARD beta as [N][K] -- rebuilt here
+    from what the ABI received and compared with the objects (src/regularizers.jl:187-240, 106-163;
+    src/featureset_ard.jl:19-65)."""
+    import scipy.sparse as sp
+    from tests.helpers import random_graphs
+    rng = np.random.default_rng(3)
+    M, N, K = 10, 14, 3
+    graphs = random_graphs(N, K, rng, n_virtual=2, n_edges=12)
+    D = rng.standard_normal((M, N)).astype(np.float32)
+    model = P.PathMatFacModel(D, feature_graphs=graphs, lambda_Y_graph=0.7, lambda_Y_selective_l1=0.2, lambda_Y_l2=None)
+    regs = {type(r).__name__: (r, p) for r, p in zip(model.matfac.Y_reg.regularizers, model.matfac.Y_reg.mixture_p)}
+    net, p_net = regs["NetworkRegularizer"]
+    sel, p_sel = regs["SelectiveL1Reg"]
+    eng = P.Engine(model)
+    a = [c for c in lib.of("pmf_set_reg_network") if c[1] == 1][0]
+    nv = arr(a[2], K, np.int32)
+    assert list(nv) == [b.shape[0] for b in net.BB] and a[13] == pytest.approx(float(p_net))
+
+    def blocks(rp_ptr, ci_ptr, va_ptr, rows, cols):
+        out, rp_off, nz_off = [], 0, 0
+        for k in range(K):
+            rp = arr(rp_ptr, rp_off + rows[k] + 1, np.int32)[rp_off:]
+            assert rp[0] == 0
+            nnz = int(rp[-1])
+            ci = arr(ci_ptr, nz_off + nnz, np.int32)[nz_off:] if nnz else np.zeros(0, np.int32)
+            va = arr(va_ptr, nz_off + nnz)[nz_off:] if nnz else np.zeros(0, np.float32)
+            out.append(sp.csr_matrix((va, ci, rp), shape=(rows[k], cols[k])))
+            rp_off += rows[k] + 1
+            nz_off += nnz
+        return out
+    for got, ref in ((blocks(a[3], a[4], a[5], [N] * K, [N] * K), net.AA), (blocks(a[6], a[7], a[8], [N] * K, list(nv)), net.AB),
+                     (blocks(a[9], a[10], a[11], list(nv), list(nv)), net.BB)):
+        for g, r in zip(got, ref):
+            assert np.allclose(g.toarray(), np.asarray(r.todense(), dtype=np.float32))
+    s = [c for c in lib.of("pmf_set_reg_sel_l1") if c[1] == 1][0]
+    mask = np.ctypeslib.as_array(s[2], shape=(N * K,)).reshape(N, K)
+    assert np.array_equal(mask.T.astype(bool), np.asarray(sel.l1_idx, dtype=bool)) and s[4] == pytest.approx(float(p_sel))
+    assert mask.any() and not mask.all()
+    eng.close()
+    # feature-set ARD: alpha (N), beta K x N column-major = [N][K]
+    fids = [f"g{j}" for j in range(N)]
+    views = ["a"] * 6 + ["b"] * 8
+    fsets = {"a": [fids[0:3], fids[2:6]], "b": [fids[6:10], fids[9:14]]}
+    model = P.PathMatFacModel(D.copy(), K=K, feature_ids=fids, feature_views=views, feature_sets_dict=fsets, Y_fsard=True)
+    reg = model.matfac.Y_reg
+    reg.beta[...] = 0.5 + rng.random(reg.beta.shape).astype(np.float32)
+    reg.alpha[...] = 1.0 + rng.random(N).astype(np.float32)
+    lib.calls.clear()
+    P.Engine(model).close()
+    f = [c for c in lib.of("pmf_set_reg_fsard") if c[1] == 1][0]
+    assert np.array_equal(arr(f[2], N), reg.alpha) and np.array_equal(arr(f[3], N * K).reshape(N, K), reg.beta.T)
