@@ -246,6 +246,12 @@ int pmf_create(const pmf_dims* d, pmf_handle* out) {
     // two attribute queries, not cudaGetDeviceProperties (which fills ~100 fields and costs milliseconds per handle)
     cudaDeviceGetAttribute(&h->n_sms, cudaDevAttrMultiProcessorCount, d->device);
     cudaDeviceGetAttribute(&h->cc_major, cudaDevAttrComputeCapabilityMajor, d->device);
+    if (h->cc_major != 10) {
+        // the library holds sm_100a code only: say so here instead of failing at the first kernel launch
+        const int cc = h->cc_major;
+        delete h;
+        return fail(nullptr, PMF_ERR_CUDA, "device %d has compute capability %d.x: libpmf is built for sm_100a (B200) only", d->device, cc);
+    }
     cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
     h->stream = h->own_stream;
     cudaEventCreate(&h->ev0);

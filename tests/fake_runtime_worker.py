@@ -1,0 +1,249 @@
+"""Worker of tests/test_abi_on_fake_runtime.py: a fresh interpreter (no torch, hence no real libcudart in the process)
+loads the host-only libcudart stand-in (tests/cuda_stub/fake_cudart), then the REAL libpmf built with `-cudart shared`
+(argv), and drives it through the Python mirror exactly as on a GPU box.  Prints one JSON object."""
+import ctypes as C
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+fake = C.CDLL(sys.argv[1], mode=C.RTLD_GLOBAL)
+os.environ["PMF_LIB"] = sys.argv[2]
+
+import numpy as np  # noqa: E402
+
+import pathmatfac_b200 as P  # noqa: E402
+from pathmatfac_b200 import _lib  # noqa: E402
+
+assert "torch" not in sys.modules
+lib = _lib.load()
+OUT = {}
+
+
+def launches(clear=True):
+    name, dims, sm = C.create_string_buffer(512), (C.c_uint * 6)(), C.c_size_t()
+    out = []
+    for i in range(fake.fake_launch_count()):
+        fake.fake_launch(i, name, 512, dims, C.byref(sm))
+        out.append({"name": name.value.decode(), "grid": list(dims)[:3], "block": list(dims)[3:], "smem": sm.value})
+    if clear:
+        fake.fake_clear_launches()
+    return out
+
+
+def maps():
+    v = (C.c_longlong * 10)()
+    out = []
+    for i in range(fake.fake_map_count()):
+        fake.fake_map(i, v)
+        out.append(dict(zip(("dtype", "rank", "swizzle", "oob", "rc", "dim0", "dim1", "box0", "box1", "stride0"), list(v))))
+    return out
+
+
+def counters():
+    v = (C.c_long * 10)()
+    fake.fake_counters(v)
+    return dict(zip(("mallocs", "frees", "live_blocks", "live_bytes", "host_allocs", "host_frees", "streams", "events",
+                     "bad_frees", "oob_copies"), list(v)))
+
+
+def short(names):
+    """Kernel names without namespaces / hashes / parameter lists: 'data_pass_tc_kernel<0,1,0>'."""
+    import re
+    import subprocess
+    dem = subprocess.run(["c++filt"], input="\n".join(names), capture_output=True, text=True).stdout.splitlines()
+    out = []
+    for d in dem:
+        d = re.sub(r"^void ", "", d)
+        d = d.replace("(anonymous namespace)::", "").replace("(bool)", "")
+        d = re.sub(r"\(.*$", "", d)
+        d = d.replace("pmf::", "").replace("false", "0").replace("true", "1").replace(" ", "")
+        out.append(d)
+    return out
+
+
+def model_(M, N, K, batch_views=0, ordinal=False, seed=0, **kw):
+    rng = np.random.default_rng(seed)
+    nv = max(batch_views, 2)
+    cuts = np.linspace(0, N, nv + 1).astype(int)
+    views = [f"v{i}" for i in range(nv) for _ in range(cuts[i + 1] - cuts[i])]
+    dists = ["normal"] * N
+    if ordinal:
+        dists = ["normal"] * (N - 6) + ["ordinal3"] * 6
+        views = views[:N - 6] + ["zord"] * 6
+    D = rng.standard_normal((M, N)).astype(np.float32)
+    if ordinal:
+        D[:, N - 6:] = rng.integers(1, 4, (M, 6))
+    D[rng.random((M, N)) < 0.1] = np.nan
+    batch = {f"v{i}": [f"b{int(b)}" for b in rng.integers(0, 3 + i, M)] for i in range(batch_views)} or None
+    cond = ["c"] * M if batch else None
+    m = P.PathMatFacModel(D, K=K, feature_views=views, feature_distributions=dists, sample_conditions=cond, batch_dict=batch, **kw)
+    mf = m.matfac
+    mf.X[...] = rng.standard_normal(mf.X.shape)
+    mf.Y[...] = rng.standard_normal(mf.Y.shape)
+    ct = mf.col_transform
+    ct.layers[0].logsigma[...] = rng.standard_normal(N)
+    ct.layers[2].mu[...] = rng.standard_normal(N)
+    if batch:
+        for v in ct.layers[1].logdelta.values + ct.layers[3].theta.values:
+            v[...] = rng.standard_normal(v.shape)
+    return m
+
+
+def snapshot(m):
+    mf, ct = m.matfac, m.matfac.col_transform
+    out = {"X": mf.X.copy(), "Y": mf.Y.copy(), "logsigma": ct.unwrapped(0).logsigma.copy(), "mu": ct.unwrapped(2).mu.copy()}
+    l1 = ct.unwrapped(1)
+    if hasattr(l1, "logdelta"):
+        for i, (a, b) in enumerate(zip(l1.logdelta.values, ct.unwrapped(3).theta.values)):
+            out[f"logdelta{i}"], out[f"theta{i}"] = a.copy(), b.copy()
+    return out
+
+
+def scramble(m):
+    for v in snapshot(m).values():
+        pass
+    mf, ct = m.matfac, m.matfac.col_transform
+    mf.X[...] = -7
+    mf.Y[...] = -7
+    ct.unwrapped(0).logsigma[...] = -7
+    ct.unwrapped(2).mu[...] = -7
+    l1 = ct.unwrapped(1)
+    if hasattr(l1, "logdelta"):
+        for a, b in zip(l1.logdelta.values, ct.unwrapped(3).theta.values):
+            a[...] = -7
+            b[...] = -7
+
+
+def same(a, b):
+    return sorted(a) == sorted(b) and all(np.array_equal(a[k], b[k]) for k in a)
+
+
+fit_kw = dict(lr=0.1, update_X=1, update_Y=1, update_col_layers=1, rel_tol=0.0, abs_tol=0.0)
+
+# ---- S1: every parameter goes to the "device" and comes back unchanged (K = 5 -> Kp = 8, ragged M / N) ---------------------
+m = model_(53, 41, 5, batch_views=2, ordinal=True, lambda_X_l2=1.0)
+want = snapshot(m)
+eng = P.Engine(m)
+launches()
+scramble(m)
+eng.pull_params()
+OUT["s1_round_trip"] = same(snapshot(m), want)
+# thresholds: interior values survive, the outer ones stay infinite
+nm = m.matfac.noise_model
+OUT["s1_thresholds"] = [[float(x) for x in n.ext_thresholds] for n in nm.noises if n.ext_thresholds is not None]
+
+# ---- S2: re-sending an unchanged layout keeps batch parameters and optimiser state; a new layout re-allocates them ------------
+acc = np.full((m.matfac.Y.shape[1], 5), 3.25, np.float32)
+eng._ck(lib.pmf_set_opt_state(eng.h, 1, 0, _lib.fptr(acc)))
+eng.push_structure()                       # what reweight_col_losses / a second mf_fit on a resident model do
+scramble(m)
+eng.pull_params()
+back = np.zeros_like(acc)
+eng._ck(lib.pmf_get_opt_state(eng.h, 1, 0, _lib.fptr(back)))
+OUT["s2_same_layout_keeps_values"] = same(snapshot(m), want)
+OUT["s2_same_layout_keeps_opt_state"] = bool(np.array_equal(back, acc))
+eng.reset_opt_state(1e-8)
+eng._ck(lib.pmf_get_opt_state(eng.h, 1, 0, _lib.fptr(back)))
+accx = np.zeros((53, 5), np.float32)
+eng._ck(lib.pmf_get_opt_state(eng.h, 0, 0, _lib.fptr(accx)))
+OUT["s2_reset_gives_epsilon"] = bool(np.all(back == np.float32(1e-8)) and np.all(accx == np.float32(1e-8)))
+ld = m.matfac.col_transform.unwrapped(1).logdelta
+ld.batch_index[0] = (ld.batch_index[0] + 1) % ld.values[0].shape[0]            # another assignment of samples to batches
+eng.push_structure()
+scramble(m)
+eng.pull_params()
+s = snapshot(m)
+OUT["s2_new_layout_keeps_column_params"] = bool(np.array_equal(s["logsigma"], want["logsigma"]) and np.array_equal(s["mu"], want["mu"])
+                                                and np.array_equal(s["X"], want["X"]))
+OUT["s2_new_layout_zeroes_batch_params"] = bool(not s["theta0"].any() and not s["logdelta1"].any())
+eng.close()
+lib.pmf_release_cached_memory()
+OUT["s2_counters_after_close"] = counters()
+
+# ---- S3: which kernels an epoch launches, per configuration -------------------------------------------------------------------------
+
+
+def epoch_launches(m, kernel, epochs=3, **extra):
+    eng = P.Engine(m)
+    launches()
+    h = eng.fit(eng.make_opts(epoch=1, max_epochs=epochs, kernel=kernel, **{**fit_kw, **extra}))
+    mp = maps()
+    ls = launches()
+    eng.close()
+    names = short([x["name"] for x in ls])
+    return {"names": names, "launches": ls, "maps": mp, "reported": h["kernel_launches"], "term": h["term_code"]}
+
+
+OUT["s3_ffma"] = epoch_launches(model_(60, 45, 6, lambda_X_l2=1.0), _lib.KERNEL_FFMA)
+OUT["s3_tc"] = epoch_launches(model_(300, 400, 16, lambda_X_l2=1.0), _lib.KERNEL_TC)
+OUT["s3_tc_batch"] = epoch_launches(model_(300, 400, 16, batch_views=2, lambda_X_l2=1.0), _lib.KERNEL_TC)
+OUT["s3_tc_wide"] = epoch_launches(model_(300, 400, 128, lambda_X_l2=1.0), _lib.KERNEL_TC)
+OUT["s3_ffma_alternating"] = epoch_launches(model_(60, 45, 6, lambda_X_l2=1.0), _lib.KERNEL_FFMA, alternating=1)
+OUT["s3_auto_small"] = epoch_launches(model_(1999, 3100, 64), _lib.KERNEL_AUTO, epochs=1)["names"]
+OUT["s3_auto_large"] = epoch_launches(model_(2000, 3000, 64), _lib.KERNEL_AUTO, epochs=1)["names"]
+try:
+    epoch_launches(model_(80, 90, 300), _lib.KERNEL_TC, epochs=1)
+    OUT["s3_tc_refuses_k300"] = False
+except _lib.PmfError as e:
+    OUT["s3_tc_refuses_k300"] = str(e)
+lib.pmf_release_cached_memory()
+OUT["s3_counters_after_close"] = counters()
+
+# ---- S4: the host-driven sharded step (dist.ShardedFit's sequence) --------------------------------------------------------------------
+m = model_(40, 30, 4, lambda_X_l2=1.0)
+eng = P.Engine(m, rows=range(10, 30))
+o = eng.make_opts(epoch=1, max_epochs=2, kernel=_lib.KERNEL_FFMA, **fit_kw)
+launches()
+eng._ck(lib.pmf_fit_start(eng.h, C.byref(o)))
+seq = {"start": short([x["name"] for x in launches()])}
+eng._ck(lib.pmf_epoch_begin(eng.h, C.byref(o)))
+seq["begin"] = short([x["name"] for x in launches()])
+p, n = C.c_void_p(), C.c_int64()
+eng._ck(lib.pmf_shared_grad_buffer(eng.h, C.byref(p), C.byref(n)))
+seq["grad_floats"] = n.value
+eng._ck(lib.pmf_shared_scalar_buffer(eng.h, C.byref(p), C.byref(n)))
+seq["scalar_doubles"] = n.value
+eng._ck(lib.pmf_epoch_end(eng.h, C.byref(o)))
+seq["end"] = short([x["name"] for x in launches()])
+OUT["s4_sharded"] = seq
+eng.close()
+
+# ---- S5: error paths -------------------------------------------------------------------------------------------------------------------------
+
+
+def create_error():
+    try:
+        P.Engine(model_(20, 10, 3)).close()
+        return None
+    except _lib.PmfError as e:
+        return str(e)
+
+
+lib.pmf_release_cached_memory()
+before = counters()
+fake.fake_set(0, 10, -1)
+OUT["s5_no_device"] = create_error()
+fake.fake_set(1, 9, -1)
+OUT["s5_wrong_architecture"] = create_error()
+leaks = []
+for k in (0, 3, 9, 20):                              # every cudaMalloc after the k-th fails (the cache is empty: nothing is served from it)
+    lib.pmf_release_cached_memory()
+    fake.fake_set(1, 10, k)
+    err = create_error()
+    fake.fake_set(1, 10, -1)
+    lib.pmf_release_cached_memory()
+    c = counters()
+    leaks.append({"fail_after": k, "error": err, "live_blocks": c["live_blocks"] - before["live_blocks"], "bad_frees": c["bad_frees"]})
+OUT["s5_alloc_failures"] = leaks
+eng = P.Engine(model_(20, 10, 3))
+rc = lib.pmf_set_batch_values(eng.h, 3, None, None)
+OUT["s5_bad_view"] = [rc, lib.pmf_last_error(eng.h).decode()]
+bad = np.array([0, 5], np.int32)
+rc = lib.pmf_set_noise(eng.h, 2, _lib.iptr(bad), _lib.iptr(np.array([5, 9], np.int32)), _lib.iptr(np.array([0, 0], np.int32)), None, None)
+OUT["s5_noise_ranges_must_cover"] = [rc, lib.pmf_last_error(eng.h).decode()]
+eng.close()
+lib.pmf_release_cached_memory()
+OUT["final_counters"] = counters()
+print(json.dumps(OUT))

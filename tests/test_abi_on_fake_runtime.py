@@ -1,0 +1,139 @@
+"""The HOST side of the real libpmf on a machine without a GPU.
+
+libpmf is built a second time with `-cudart shared` (PTX only, so the device compiler does not run) and loaded in a fresh
+interpreter next to tests/cuda_stub/fake_cudart: a host-only libcudart.so.12 that implements the 33 runtime entry points
+the library uses on host memory, logs every kernel launch by name instead of executing it (only `fill_kernel` is carried
+out), and records / sanity-checks every TMA descriptor handed to cuTensorMapEncodeTiled.  tests/fake_runtime_worker.py
+then drives the library through the Python mirror exactly as on a GPU box.  What this pins on CPU:
+
+  * parameters survive the trip host -> "device" -> host for ragged shapes and padded K (the marshalling of mirror and
+    library agree for real, not by reading the header);
+  * handle state: an unchanged batch layout keeps batch parameters and AdaGrad accumulators, a changed one
+    re-allocates them but keeps the column parameters; `pmf_reset_opt_state` gives epsilon;
+  * the kernels an epoch launches per configuration -- 2 per epoch on the FP32 and the tcgen05 path, 4 with batch layers, 6
+    for K > 64, the two-pass `alternating` order, the begin / end halves of the host-driven sharded step -- and that
+    `kernel_launches` (bench.py's `gpu_launches`) equals the launches actually made;
+  * the `PMF_KERNEL_AUTO` size rule and the refusal of unsupported shapes;
+  * launch geometry within the hardware limits, every tensor map within the driver's documented constraints;
+  * error paths (no device, a device that is not sm_100, allocation failures at several depths, bad arguments) and, after
+    every scenario, zero live device blocks, balanced streams / events, no foreign frees, no copy outside an allocation."""
+import json
+import os
+import shutil
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "pathmatfac.jl_b200", "csrc")
+STUB = os.path.join(ROOT, "tests", "cuda_stub", "fake_cudart")
+SOURCES = ["pmf_abi.cu", "fused_ffma.cu", "reg_update.cu", "fsard.cu", "fused_tc.cu", "wide_tc.cu", "guard.cu"]
+
+
+@pytest.fixture(scope="module")
+def out(tmp_path_factory):
+    if shutil.which("nvcc") is None or shutil.which("g++") is None:
+        pytest.skip("nvcc / g++ not available")
+    cuda_inc = os.path.join(os.path.dirname(os.path.dirname(shutil.which("nvcc"))), "include")
+    d = tmp_path_factory.mktemp("fakert")
+    fake, lib = str(d / "libcudart.so.12"), str(d / "libpmf_sharedrt.so")
+    r = subprocess.run(["g++", "-std=c++17", "-O1", "-shared", "-fPIC", "-I", cuda_inc, os.path.join(STUB, "fake_cudart.cpp"),
+                        "-Wl,-soname,libcudart.so.12", "-Wl,--version-script=" + os.path.join(STUB, "version.map"), "-o", fake],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-3000:]
+    # host code is what is under test: PTX only (no ptxas), -O0
+    r = subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=compute_100a", "-O0", "-std=c++17", "-cudart", "shared",
+                        "-Xcompiler", "-fPIC", "-shared", "-o", lib] + SOURCES + ["-ldl"], cwd=CSRC, capture_output=True,
+                       text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-3000:]
+    env = {k: v for k, v in os.environ.items() if k not in ("PMF_GUARD", "PMF_ALLOC_CACHE", "PMF_LIB", "LD_PRELOAD")}
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "fake_runtime_worker.py"), fake, lib], capture_output=True,
+                       text=True, timeout=900, env=env, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    return json.loads(r.stdout.strip().splitlines()[-1])
+
+
+def _clean(c):
+    return (c["live_blocks"] == 0 and c["live_bytes"] == 0 and c["mallocs"] == c["frees"] and c["host_allocs"] == c["host_frees"]
+            and c["streams"] == 0 and c["events"] == 0 and c["bad_frees"] == 0 and c["oob_copies"] == 0)
+
+
+def test_parameters_round_trip_and_handle_state(out):
+    assert out["s1_round_trip"] is True
+    assert out["s1_thresholds"] == [[float("-inf"), -1.0, 1.0, float("inf")]]
+    assert out["s2_same_layout_keeps_values"] and out["s2_same_layout_keeps_opt_state"]
+    assert out["s2_reset_gives_epsilon"]
+    assert out["s2_new_layout_keeps_column_params"] and out["s2_new_layout_zeroes_batch_params"]
+    assert _clean(out["s2_counters_after_close"]) and out["s2_counters_after_close"]["mallocs"] > 10
+
+
+def _per_epoch(names, first):
+    """The launches after the set-up prefix `first`, cut into epochs of equal content."""
+    assert names[:len(first)] == first, names[:6]
+    rest = names[len(first):]
+    assert len(rest) % 3 == 0
+    n = len(rest) // 3
+    assert rest[:n] == rest[n:2 * n] == rest[2 * n:], rest
+    return rest[:n]
+
+
+def test_kernels_launched_per_epoch(out):
+    s = out["s3_ffma"]
+    assert _per_epoch(s["names"], ["multi_pass_kernel"]) == ["data_pass_ffma_kernel<1,0>", "fused_epoch_kernel"]
+    s = out["s3_tc"]                                                     # two launches per epoch
+    assert _per_epoch(s["names"], ["multi_pass_kernel", "prep_operands_kernel"]) == ["data_pass_tc_kernel<0,0,0>", "fused_epoch_kernel"]
+    s = out["s3_tc_batch"]                                               # 4.2: + operand gather and dX combine
+    assert _per_epoch(s["names"], ["multi_pass_kernel", "build_a_tc_kernel"]) == [
+        "prep_operands_kernel", "data_pass_tc_kernel<0,1,0>", "combine_dx_kernel", "fused_epoch_kernel"]
+    s = out["s3_tc_wide"]                                                # 4.3: Z + link, two gradient GEMMs over G'
+    assert _per_epoch(s["names"], ["multi_pass_kernel"]) == [
+        "prep_wide_kernel", "prep_wide_kernel", "zlink_kernel", "grad_gemm_kernel<0>", "grad_gemm_kernel<1>", "fused_epoch_kernel"]
+    s = out["s3_ffma_alternating"]                                       # D1: column-side step, second pass, row-side step
+    assert _per_epoch(s["names"], []) == ["data_pass_ffma_kernel<1,0>", "multi_pass_kernel", "control_kernel", "multi_pass_kernel",
+                                          "data_pass_ffma_kernel<1,0>", "multi_pass_kernel", "multi_pass_kernel"]
+    for k in ("s3_ffma", "s3_tc", "s3_tc_batch", "s3_tc_wide", "s3_ffma_alternating"):
+        assert out[k]["reported"] == len(out[k]["names"]), k             # pmf_history.kernel_launches = bench.py's gpu_launches
+        assert out[k]["term"] == "max_epochs"
+    assert _clean(out["s3_counters_after_close"])
+
+
+def test_auto_size_rule_and_refusals(out):
+    """PMF_KERNEL_AUTO: the tensor-core kernels from M N >= 6e6 (K/64)^2 and min(M, N) >= 2000."""
+    assert "data_pass_ffma_kernel<1,0>" in out["s3_auto_small"] and not any("_tc_" in n for n in out["s3_auto_small"])     # 1999 x 3100
+    assert "data_pass_tc_kernel<0,0,0>" in out["s3_auto_large"] and not any("ffma" in n for n in out["s3_auto_large"])     # 2000 x 3000
+    assert "K > 256" in out["s3_tc_refuses_k300"]
+
+
+def test_launch_geometry_and_tensor_maps(out):
+    for k in ("s3_ffma", "s3_tc", "s3_tc_batch", "s3_tc_wide", "s3_ffma_alternating"):
+        for x in out[k]["launches"]:
+            threads = x["block"][0] * x["block"][1] * x["block"][2]
+            assert 1 <= threads <= 1024 and x["smem"] <= 232448 and min(x["grid"]) >= 1, (k, x)
+            if "data_pass_tc_kernel" in x["name"]:
+                assert threads == 768 and x["grid"][0] <= 148 and x["smem"] > 200 * 1024       # persistent: at most one CTA per SM
+    assert not out["s3_ffma"]["maps"]
+    for k in ("s3_tc", "s3_tc_batch", "s3_tc_wide"):
+        maps = out[k]["maps"]
+        assert maps and all(m["rc"] == 0 and m["rank"] == 2 for m in maps), k            # the driver's documented constraints
+        assert all(m["box0"] * (4 if m["dtype"] == 7 else 2) <= 128 for m in maps)        # inner box within the 128-byte swizzle span
+        assert {m["dtype"] for m in maps} == {7, 9}                                       # FP32 data / gradients, BF16 operand splits
+
+
+def test_host_driven_sharded_step(out):
+    s = out["s4_sharded"]
+    assert s["start"] == [] and s["begin"] == ["data_pass_ffma_kernel<1,0>", "multi_pass_kernel"]      # data pass + rank-local X penalties
+    assert s["end"] == ["multi_pass_kernel", "control_kernel", "multi_pass_kernel"]                     # replicated penalties, test, update
+    Np, Kp = 128, 8
+    assert s["grad_floats"] >= Np * Kp + 2 * Np and s["scalar_doubles"] == 2                            # [dY | dlogsigma | dmu | ...]
+
+
+def test_error_paths_and_allocation_balance(out):
+    assert "no CUDA device" in out["s5_no_device"] and "no CPU path" in out["s5_no_device"]
+    assert "compute capability 9" in out["s5_wrong_architecture"] and "sm_100a" in out["s5_wrong_architecture"]
+    for f in out["s5_alloc_failures"]:
+        assert f["error"] and ("allocation failed" in f["error"] or "out of memory" in f["error"]), f
+        assert f["live_blocks"] == 0 and f["bad_frees"] == 0, f                          # nothing leaks when set-up fails half way
+    assert out["s5_bad_view"][0] == -1 and "does not exist" in out["s5_bad_view"][1]
+    assert out["s5_noise_ranges_must_cover"][0] == -1 and "no noise model" in out["s5_noise_ranges_must_cover"][1]
+    assert _clean(out["final_counters"])
