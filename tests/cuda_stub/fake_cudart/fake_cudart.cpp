@@ -27,6 +27,8 @@ std::map<void*, size_t> g_live;
 std::vector<Launch> g_launches;
 std::vector<MapRec> g_maps;
 std::vector<Cfg> g_cfg;
+struct Fill { std::string match; void* ptr; long n; double value; bool f64; };
+std::vector<Fill> g_fills;          // "what a kernel would have produced": buffers filled when a kernel of that name launches
 long g_mallocs = 0, g_frees = 0, g_host_allocs = 0, g_host_frees = 0, g_streams = 0, g_events = 0, g_syncs = 0, g_bad_frees = 0;
 int g_device = 0, g_device_count = 1, g_cc_major = 10, g_fail_malloc_after = -1;
 cudaError_t g_last = cudaSuccess;
@@ -70,6 +72,11 @@ cudaError_t cudaLaunchKernel(const void* func, dim3 g, dim3 b, void** args, size
     auto it = g_kernels.find(func);
     std::string name = it == g_kernels.end() ? "<unregistered>" : it->second;
     g_launches.push_back({name, g.x, g.y, g.z, b.x, b.y, b.z, smem});
+    for (const Fill& f : g_fills)
+        if (name.find(f.match) != std::string::npos) {
+            if (f.f64) for (long i = 0; i < f.n; ++i) static_cast<double*>(f.ptr)[i] = f.value;
+            else for (long i = 0; i < f.n; ++i) static_cast<float*>(f.ptr)[i] = (float)f.value;
+        }
     if (name.find("fill_kernel") != std::string::npos) {             // fill_kernel(float* p, size_t n, float v)
         float* p = *static_cast<float**>(args[0]);
         size_t n = *static_cast<size_t*>(args[1]);
@@ -208,5 +215,10 @@ int fake_map(int i, long long* out) {   // dtype, rank, swizzle, oob, rc, dim0, 
     std::memcpy(out, v, sizeof v);
     return 0;
 }
+void fake_fill_on_launch(const char* match, void* ptr, long n, double value, int f64) {
+    std::lock_guard<std::mutex> l(mu);
+    g_fills.push_back({match, ptr, n, value, f64 != 0});
+}
+void fake_clear_fills(void) { std::lock_guard<std::mutex> l(mu); g_fills.clear(); }
 void fake_set(int device_count, int cc_major, int fail_malloc_after) { g_device_count = device_count; g_cc_major = cc_major; g_fail_malloc_after = fail_malloc_after; }
 }

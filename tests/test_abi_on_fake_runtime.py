@@ -13,6 +13,9 @@ then drives the library through the Python mirror exactly as on a GPU box.  What
   * the kernels an epoch launches per configuration -- 2 per epoch on the FP32 and the tcgen05 path, 4 with batch layers, 6
     for K > 64, the two-pass `alternating` order, the begin / end halves of the host-driven sharded step -- and that
     `kernel_launches` (bench.py's `gpu_launches`) equals the launches actually made;
+  * the exchange step inside `pmf_fit`: three ranks as threads over a host-only NCCL stand-in (tests/cuda_stub/fake_nccl) that
+    really sums -- one group of two in-place all-reduces per epoch and rank (the whole shared gradient buffer as float32, the
+    two rank-local loss scalars as float64), every rank left with the sum, no mismatched call, communicators destroyed;
   * the `PMF_KERNEL_AUTO` size rule (DESIGN.md 4.1) and the refusal of unsupported shapes;
   * launch geometry within the hardware limits, every tensor map within the driver's documented constraints;
   * error paths (no device, a device that is not sm_100, allocation failures at several depths, bad arguments) and, after
@@ -47,11 +50,21 @@ def out(tmp_path_factory):
                         "-Xcompiler", "-fPIC", "-shared", "-o", lib] + SOURCES + ["-ldl"], cwd=CSRC, capture_output=True,
                        text=True, timeout=900)
     assert r.returncode == 0, r.stderr[-3000:]
+    nccl = str(d / "libnccl.so.2")
+    r = subprocess.run(["g++", "-std=c++17", "-O1", "-shared", "-fPIC", "-pthread",
+                        os.path.join(ROOT, "tests", "cuda_stub", "fake_nccl", "fake_nccl.cpp"), "-Wl,-soname,libnccl.so.2", "-o", nccl],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-3000:]
     env = {k: v for k, v in os.environ.items() if k not in ("PMF_GUARD", "PMF_ALLOC_CACHE", "PMF_LIB", "LD_PRELOAD")}
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "fake_runtime_worker.py"), fake, lib], capture_output=True,
                        text=True, timeout=900, env=env, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
-    return json.loads(r.stdout.strip().splitlines()[-1])
+    res = json.loads(r.stdout.strip().splitlines()[-1])
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "fake_nccl_worker.py"), fake, nccl, lib], capture_output=True,
+                       text=True, timeout=300, env=env, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    res["nccl"] = json.loads(r.stdout.strip().splitlines()[-1])
+    return res
 
 
 def _clean(c):
@@ -137,3 +150,21 @@ def test_error_paths_and_allocation_balance(out):
     assert out["s5_bad_view"][0] == -1 and "does not exist" in out["s5_bad_view"][1]
     assert out["s5_noise_ranges_must_cover"][0] == -1 and "no noise model" in out["s5_noise_ranges_must_cover"][1]
     assert _clean(out["final_counters"])
+
+
+def test_exchange_step_inside_pmf_fit_three_ranks(out):
+    """SURVEY 8e on CPU: the sample-sharded epoch loop of the real library, ncclAllReduce inside pmf_fit (dist.NcclFit's
+    path; GPU: tests/test_gpu_multi.py).  The planted "gradients" (rank r: r + 1) come back as 1 + 2 + 3 on every rank."""
+    n = out["nccl"]
+    assert n["alive"] == [False, False, False] and n["errors"] == []
+    assert n["grad_buffers_all_equal_sum"] and len(set(n["grad_buffer_len"])) == 1
+    assert n["scalars"] == [[60.0, 60.0]] * 3                                  # 10 + 20 + 30 in both rank-local scalars
+    R, E, L = n["ranks"], n["epochs"], n["grad_buffer_len"][0]
+    log = n["nccl_log"]
+    assert len(log) == R * E * 2 and all(x["in_place"] == 1 and x["grouped"] == 1 and x["nranks"] == R for x in log)
+    for r in range(R):
+        mine = [(x["count"], x["dtype"]) for x in log if x["rank"] == r]
+        assert mine == [(L, 7), (2, 8)] * E                                      # float32 gradients, then float64 scalars, per epoch
+    assert n["nccl_mismatches"] == 0 and n["nccl_live_comms"] == 0
+    assert n["term"] == ["max_epochs"] * 3 and len(set(n["kernel_launches"])) == 1
+    assert n["live_blocks"] == 0 and n["bad_frees"] == 0 and n["oob_copies"] == 0
