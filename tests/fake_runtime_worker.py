@@ -191,6 +191,46 @@ except _lib.PmfError as e:
 lib.pmf_release_cached_memory()
 OUT["s3_counters_after_close"] = counters()
 
+# ---- S3b: graph regulariser, statistics passes, the end-to-end call -------------------------------------------------------------------
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+rng = np.random.default_rng(9)
+Ng, Kg = 30, 3
+fids = list(range(1, Ng + 1))
+graphs = []
+for k in range(Kg):
+    el = [[int(a), int(b), 1.0] for a, b in rng.integers(1, Ng + 1, (20, 2)) if a != b]
+    el += [[int(rng.integers(1, Ng + 1)), f"virt{k}", 1.0] for _ in range(3)]
+    graphs.append(el)
+mg = P.PathMatFacModel(rng.standard_normal((25, Ng)).astype(np.float32), feature_ids=fids, feature_graphs=graphs, lambda_Y_graph=1.0)
+OUT["s3_network"] = epoch_launches(mg, _lib.KERNEL_FFMA)
+
+m = model_(50, 40, 4, batch_views=2, lambda_X_l2=1.0)
+eng = P.Engine(m)
+launches()
+eng.column_stats()
+a = short([x["name"] for x in launches()])
+eng.link_col_sqerr()
+b = short([x["name"] for x in launches()])
+cnt, sq = eng.batch_stats()
+c = short([x["name"] for x in launches()])
+OUT["s3_stats"] = {"column_stats": a, "link_col_sqerr": b, "batch_stats": c, "batch_shapes": [list(x.shape) for x in cnt]}
+eng.close()
+
+# mf_fit on a host-resident model = create handle, upload, fit, read back, destroy; from the second call on the allocator
+# cache serves every block
+m = model_(64, 48, 8, lambda_X_l2=1.0)
+lib.pmf_release_cached_memory()
+per_call = []
+for _ in range(3):
+    c0 = counters()
+    h = P.mf_fit(m, lr=0.1, max_epochs=3, update_X=True, update_Y=True, update_col_layers=True, verbosity=0, kernel=_lib.KERNEL_FFMA)
+    c1 = counters()
+    per_call.append({"mallocs": c1["mallocs"] - c0["mallocs"], "frees": c1["frees"] - c0["frees"],
+                     "host_allocs": c1["host_allocs"] - c0["host_allocs"], "h2d": h["h2d_bytes"], "d2h": h["d2h_bytes"]})
+OUT["s3_mf_fit_calls"] = per_call
+lib.pmf_release_cached_memory()
+OUT["s3b_counters"] = counters()
+
 # ---- S4: the host-driven sharded step (dist.ShardedFit's sequence) --------------------------------------------------------------------
 m = model_(40, 30, 4, lambda_X_l2=1.0)
 eng = P.Engine(m, rows=range(10, 30))

@@ -168,3 +168,19 @@ def test_exchange_step_inside_pmf_fit_three_ranks(out):
     assert n["nccl_mismatches"] == 0 and n["nccl_live_comms"] == 0
     assert n["term"] == ["max_epochs"] * 3 and len(set(n["kernel_launches"])) == 1
     assert n["live_blocks"] == 0 and n["bad_frees"] == 0 and n["oob_copies"] == 0
+
+
+def test_graph_regulariser_statistics_passes_and_allocator_cache(out):
+    s = out["s3_network"]                                               # NetworkRegularizer on a transposed copy of Y
+    assert _per_epoch(s["names"], ["multi_pass_kernel"]) == ["data_pass_ffma_kernel<1,0>", "transpose_in_kernel", "network_virtual_kernel",
+                                                             "network_rows_kernel", "transpose_add_kernel", "fused_epoch_kernel"]
+    assert s["reported"] == len(s["names"])
+    st = out["s3_stats"]                                                # one streaming pass behind each staging statistic (8f rank 1)
+    assert st["column_stats"] == st["link_col_sqerr"] == st["batch_stats"] == ["data_pass_ffma_kernel<1,1>"]
+    assert st["batch_shapes"] == [[3, 20], [4, 20]]                     # n_b x N_v per batched view, like the reference's BatchArray
+    first, second, third = out["s3_mf_fit_calls"]                       # mf_fit on a host-resident model, three times
+    assert first["mallocs"] > 10 and first["host_allocs"] == 1
+    for later in (second, third):                                       # no cudaMalloc / cudaFree / pinned allocation at all
+        assert later["mallocs"] == 0 and later["frees"] == 0 and later["host_allocs"] == 0
+        assert later["h2d"] == first["h2d"] > 0 and later["d2h"] == first["d2h"] > 0
+    assert _clean(out["s3b_counters"])
