@@ -343,7 +343,10 @@ def main():
     clocks = sampler.summary() if sampler else None
     n_prof, dp_mean_ms, dp_min_ms = eng.get_profile()
     eng.set_profiling(False)
-    launches = h["kernel_launches"]
+    # pmf_history.kernel_launches counts everything the library enqueued; at N > 1 that includes NCCL's two all-reduces per
+    # epoch (one group), which are not this repo's kernels
+    n_coll = 2 * args.steps if world > 1 else 0
+    launches = h["kernel_launches"] - n_coll
     sec_per_step = ms / 1e3 / args.steps
     value = world / sec_per_step            # C2-equivalent iterations/sec of the whole job
     assert len(h["loss"]) == args.steps and all(np.isfinite(h["loss"])), "timed steps did not all run"
@@ -445,7 +448,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": sec_per_step * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(M, N, K, world), "arm": {"kernel": args.kernel, "precision": args.precision},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
+            "gpu_launches": launches, "nccl_collectives": n_coll, "clocks": clocks, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
             "loss_first_last": [h["loss"][0], h["loss"][-1]]}
     print(json.dumps(line))
     if world > 1:

@@ -76,7 +76,9 @@ class _Engine:
             out.append(self.loss)
         if self.profiling:
             self.n_prof += n
-        return {"term_code": "max_epochs", "epochs": o.max_epochs, "loss": out, "kernel_launches": 2 * n + 1}
+        # 2 kernels per epoch + the first penalty pass, and at N > 1 the two all-reduces per epoch the library also counts
+        return {"term_code": "max_epochs", "epochs": o.max_epochs, "loss": out,
+                "kernel_launches": 2 * n + 1 + (2 * n if dist.is_initialized() and dist.get_world_size() > 1 else 0)}
 
     def reset_opt_state(self, eps=1e-8):
         self.loss = 1000.0

@@ -68,7 +68,7 @@ def test_repo_arm_control_flow_at_two_ranks_on_cpu(tmp_path, n):
     assert len(lines) == 1, r.stdout
     d = json.loads(lines[0])
     assert d["n_gpus"] == n and d["steps"] == 4 and d["warmup"] == 3 and d["scaling"] == "weak"
-    assert d["value"] == pytest.approx(n / (d["ms_per_step"] / 1e3)) and d["gpu_launches"] == 9
+    assert d["value"] == pytest.approx(n / (d["ms_per_step"] / 1e3)) and d["gpu_launches"] == 9 and d["nccl_collectives"] == 8
     assert d["config"]["parallelism"] == f"sample-sharded x{n}" and d["config"]["per_rank_samples"] == 96
     e = d["e2e"]
     assert e["epochs_run"] == 4 and len(e["seconds_each_call"]) == 3 and e["seconds"] == sorted(e["seconds_each_call"])[1]
