@@ -284,6 +284,17 @@ bad = np.array([0, 5], np.int32)
 rc = lib.pmf_set_noise(eng.h, 2, _lib.iptr(bad), _lib.iptr(np.array([5, 9], np.int32)), _lib.iptr(np.array([0, 0], np.int32)), None, None)
 OUT["s5_noise_ranges_must_cover"] = [rc, lib.pmf_last_error(eng.h).decode()]
 eng.close()
+
+# ---- S6: guard zones (PMF_GUARD=1 in the environment; without it there is nothing to check) ----------------------------------------
+m = model_(70, 60, 12, batch_views=2, ordinal=True, lambda_X_l2=1.0)
+eng = P.Engine(m)
+eng.fit(eng.make_opts(epoch=1, max_epochs=2, kernel=_lib.KERNEL_FFMA, **fit_kw))
+eng.fit(eng.make_opts(epoch=1, max_epochs=2, kernel=_lib.KERNEL_TC, **fit_kw))
+eng.column_stats(); eng.batch_stats(); eng.loss_grad(); eng.pull_params(); eng.push_structure(); eng.push_params()
+nb, bad = C.c_int64(0), C.c_int64(0)
+rc = lib.pmf_check_guards(C.byref(nb), C.byref(bad))
+OUT["s6_guards"] = {"rc": rc, "buffers": nb.value, "bad": bad.value, "enabled": os.environ.get("PMF_GUARD") == "1"}
+eng.close()
 lib.pmf_release_cached_memory()
 OUT["final_counters"] = counters()
 print(json.dumps(OUT))

@@ -64,6 +64,10 @@ def out(tmp_path_factory):
                        text=True, timeout=300, env=env, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     res["nccl"] = json.loads(r.stdout.strip().splitlines()[-1])
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "fake_runtime_worker.py"), fake, lib], capture_output=True,
+                       text=True, timeout=900, env=dict(env, PMF_GUARD="1"), cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    res["guarded"] = json.loads(r.stdout.strip().splitlines()[-1])
     return res
 
 
@@ -184,3 +188,13 @@ def test_graph_regulariser_statistics_passes_and_allocator_cache(out):
         assert later["mallocs"] == 0 and later["frees"] == 0 and later["host_allocs"] == 0
         assert later["h2d"] == first["h2d"] > 0 and later["d2h"] == first["d2h"] > 0
     assert _clean(out["s3b_counters"])
+
+
+def test_guard_zones_survive_every_host_side_copy(out):
+    """PMF_GUARD=1 (1 KiB guard zones around every device buffer, csrc/guard.cu): after uploads, downloads, layout changes,
+    fits on both kernel families and the statistics passes no guard byte has changed -- no host-side copy of the library
+    runs past the size it asked for.  (The kernels' side of the same check runs on the GPU: test_guard_zones_stay_intact.)"""
+    g = out["guarded"]["s6_guards"]
+    assert g["enabled"] and g["rc"] == 0 and g["buffers"] > 30 and g["bad"] == 0
+    assert out["guarded"]["s1_round_trip"] and _clean(out["guarded"]["final_counters"])
+    assert out["s6_guards"]["rc"] == -3 and out["s6_guards"]["buffers"] == 0          # not enabled: PMF_ERR_STATE, as documented
