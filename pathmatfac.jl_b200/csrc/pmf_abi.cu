@@ -1495,7 +1495,7 @@ int pmf_model_s::run_data_pass(DataPassParams& p, int kind, int precision) {
     const bool tc_ok = tc_supported(p) && cc_major == 10 && batches_ok;
     const bool wide_ok = wide_supported(p) && cc_major == 10;
     if (kind == PMF_KERNEL_TC && !tc_ok && !wide_ok)
-        return fail(this, PMF_ERR_ARG, "tcgen05 data pass needs an sm_100 device and 8 <= K <= 64 (at most 65533 batches per "
+        return fail(this, PMF_ERR_ARG, "tcgen05 data pass needs an sm_100 device and K <= 64 (at most 65533 batches per "
                                        "view) or 64 < K <= 256 without batch layers");
     // AUTO: the tensor-core kernels take a problem when it is large enough for their single-pass TF32 gradient
     // contractions to stay below the 1e-4 parity bar; smaller ones run the exact-FP32 kernel.  Measured against the

@@ -285,6 +285,32 @@ rc = lib.pmf_set_noise(eng.h, 2, _lib.iptr(bad), _lib.iptr(np.array([5, 9], np.i
 OUT["s5_noise_ranges_must_cover"] = [rc, lib.pmf_last_error(eng.h).decode()]
 eng.close()
 
+# ---- S7: launch geometry and tensor maps over a sweep of ragged / degenerate shapes, both kernel families ------------------------
+sweep = []
+rs = np.random.default_rng(77)
+shapes = [(1, 1, 1), (1, 300, 8), (50, 1, 3), (2, 2, 64), (129, 257, 64), (3000, 3, 2), (3, 3000, 5), (127, 129, 72), (64, 128, 128),
+          (65, 130, 200), (33, 600, 256)]
+shapes += [(int(rs.integers(1, 700)), int(rs.integers(2, 900)), int(rs.choice([1, 3, 8, 10, 25, 64, 65, 100, 128, 256]))) for _ in range(14)]
+for (Ms, Ns, Ks) in shapes:
+    for bv in (0, 2):
+        if bv and (Ns < 4 or Ms < 4):
+            continue
+        for kern in (_lib.KERNEL_FFMA, _lib.KERNEL_TC):
+            rec = {"shape": [Ms, Ns, Ks], "batch_views": bv, "kernel": kern, "error": None}
+            try:
+                r = epoch_launches(model_(Ms, Ns, Ks, batch_views=bv, seed=Ms + Ns), kern, epochs=1)
+                rec["bad_geometry"] = [x for x in r["launches"] if min(x["grid"]) < 1 or x["block"][0] * x["block"][1] * x["block"][2] > 1024
+                                       or x["smem"] > 232448]
+                rec["bad_maps"] = [mm for mm in r["maps"] if mm["rc"] != 0]
+                rec["n_launches"], rec["reported"] = len(r["launches"]), r["reported"]
+                rec["tc"] = any("_tc_" in n or "zlink" in n for n in r["names"])
+            except _lib.PmfError as e:
+                rec["error"] = str(e)
+            sweep.append(rec)
+OUT["s7_sweep"] = sweep
+lib.pmf_release_cached_memory()
+OUT["s7_counters"] = counters()
+
 # ---- S6: guard zones (PMF_GUARD=1 in the environment; without it there is nothing to check) ----------------------------------------
 m = model_(70, 60, 12, batch_views=2, ordinal=True, lambda_X_l2=1.0)
 eng = P.Engine(m)

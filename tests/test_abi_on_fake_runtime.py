@@ -198,3 +198,19 @@ def test_guard_zones_survive_every_host_side_copy(out):
     assert g["enabled"] and g["rc"] == 0 and g["buffers"] > 30 and g["bad"] == 0
     assert out["guarded"]["s1_round_trip"] and _clean(out["guarded"]["final_counters"])
     assert out["s6_guards"]["rc"] == -3 and out["s6_guards"]["buffers"] == 0          # not enabled: PMF_ERR_STATE, as documented
+
+
+def test_shape_sweep_geometry_and_refusals(out):
+    """88 fits over ragged / degenerate shapes (1 x 1 to 3000 x 3, K from 1 to 256), with and without batch layers, on both
+    kernel families: every launch inside the hardware limits, every tensor map inside the driver's constraints, the launch
+    counter equal to the launches made -- and the only refusals are the documented one (tensor-core kernels requested for
+    K > 64 WITH batch layers; PMF_KERNEL_AUTO runs those on the FP32 kernel)."""
+    sw = out["s7_sweep"]
+    assert len(sw) >= 80
+    for r in sw:
+        if r["error"]:
+            assert r["kernel"] == 2 and r["batch_views"] == 2 and r["shape"][2] > 64 and "without batch layers" in r["error"], r
+            continue
+        assert r["bad_geometry"] == [] and r["bad_maps"] == [] and r["n_launches"] == r["reported"], r
+        assert r["tc"] == (r["kernel"] == 2), r                     # an explicit kernel request is honoured, never silently replaced
+    assert _clean(out["s7_counters"])
