@@ -311,6 +311,51 @@ OUT["s7_sweep"] = sweep
 lib.pmf_release_cached_memory()
 OUT["s7_counters"] = counters()
 
+# ---- S8: the ABI in the order julia/PathMatFacB200.jl calls it (create_handle: create, set_data, set_batch_layout; every
+# mf_fit!: factors, column parameters, batch values, regularisers, layer penalties, frozen masks, noise LAST, reset of the
+# optimiser state on first use, fit, read-back) -- the shim cannot be run here, its call order can ------------------------------
+from pathmatfac_b200._lib import pmf_dims  # noqa: E402
+
+m = model_(45, 36, 5, batch_views=2, ordinal=True, lambda_X_l2=1.0)
+want = snapshot(m)
+eng = P.Engine.__new__(P.Engine)
+eng.lib, eng.model, eng.rows, eng.device = lib, m, range(0, 45), 0
+eng.M, eng.N, eng.K, eng.h, eng.n_views, eng.h2d_bytes, eng.d2h_bytes = 45, 36, 5, C.c_void_p(), 0, 0, 0
+steps = []
+
+
+def step(name, rc):
+    steps.append([name, int(rc), lib.pmf_last_error(eng.h).decode() if rc else ""])
+
+
+step("pmf_create", lib.pmf_create(C.byref(pmf_dims(45, 36, 5, 0)), C.byref(eng.h)))
+A = np.ascontiguousarray(np.asarray(m.data, dtype=np.float32).T)
+step("pmf_set_data", lib.pmf_set_data(eng.h, _lib.fptr(A)))
+ld = m.matfac.col_transform.unwrapped(1).logdelta
+bcs = np.array([r.start for r in ld.col_ranges], np.int32)
+bce = np.array([r.stop for r in ld.col_ranges], np.int32)
+nbv = np.array([v.shape[0] for v in ld.values], np.int32)
+bos = np.ascontiguousarray(np.stack(ld.batch_index).astype(np.int32))
+step("pmf_set_batch_layout", lib.pmf_set_batch_layout(eng.h, 2, _lib.iptr(bcs), _lib.iptr(bce), _lib.iptr(nbv), _lib.iptr(bos)))
+eng.n_views = 2
+shim_fits = []
+for call in range(2):
+    try:
+        eng.push_params()                                   # pmf_set_factors, pmf_set_col_params, pmf_set_batch_values
+        eng.push_regs()                                     # pmf_clear_reg / pmf_set_reg_*, layer penalties, pmf_set_frozen, pmf_set_noise
+        if call == 0:
+            eng.reset_opt_state(1e-8)
+        launches()
+        h = eng.fit(eng.make_opts(epoch=1, max_epochs=2, **fit_kw))
+        names = short([x["name"] for x in launches()])
+        scramble(m)
+        eng.pull_params()
+        shim_fits.append({"ok": True, "round_trip": same(snapshot(m), want), "names": names, "term": h["term_code"]})
+    except _lib.PmfError as e:
+        shim_fits.append({"ok": False, "error": str(e)})
+OUT["s8_shim_order"] = {"steps": steps, "fits": shim_fits}
+eng.close()
+
 # ---- S6: guard zones (PMF_GUARD=1 in the environment; without it there is nothing to check) ----------------------------------------
 m = model_(70, 60, 12, batch_views=2, ordinal=True, lambda_X_l2=1.0)
 eng = P.Engine(m)

@@ -214,3 +214,17 @@ def test_shape_sweep_geometry_and_refusals(out):
         assert r["bad_geometry"] == [] and r["bad_maps"] == [] and r["n_launches"] == r["reported"], r
         assert r["tc"] == (r["kernel"] == 2), r                     # an explicit kernel request is honoured, never silently replaced
     assert _clean(out["s7_counters"])
+
+
+def test_abi_in_the_julia_shims_call_order(out):
+    """julia/PathMatFacB200.jl cannot be run here (no Julia), but the ORDER in which it calls the ABI can: create_handle =
+    pmf_create, pmf_set_data, pmf_set_batch_layout (before any noise model is known); every mf_fit! = values, regularisers,
+    frozen masks, pmf_set_noise last, pmf_reset_opt_state on an optimiser's first use, pmf_fit, read-back.  The library's
+    state machine accepts it, twice in a row, and the parameters come back unchanged by the (not executed) kernels."""
+    s = out["s8_shim_order"]
+    assert [x[:2] for x in s["steps"]] == [["pmf_create", 0], ["pmf_set_data", 0], ["pmf_set_batch_layout", 0]]
+    assert len(s["fits"]) == 2
+    for f in s["fits"]:
+        assert f["ok"] and f["round_trip"] and f["term"] == "max_epochs"
+        assert f["names"] == ["multi_pass_kernel", "data_pass_ffma_kernel<1,0>", "fused_epoch_kernel", "data_pass_ffma_kernel<1,0>",
+                              "fused_epoch_kernel"]
