@@ -1,0 +1,61 @@
+"""The barrier choreography of the fused tcgen05 data pass (csrc/fused_tc.cu) checked without a GPU: scripts/tc_protocol_check.py
+transcribes the kernel's roles (TMA producers, the two MMA-issuing threads, 16 epilogue warps in two groups, 4 dX drain
+warps), its 16 mbarrier families with their arrival counts and parity waits, and the asynchronous engines, and runs them
+under random interleavings with a vector-clock race detector over every buffer the roles hand to one another.  The pool's
+compute-sanitizer is closed, so this is the racecheck that can be had: the ORDER imposed by the barriers is sufficient (no
+conflicting accesses unordered, no deadlock, no lost phase), and removing any one of the waits is noticed.  Fence / proxy
+placement inside an ordered pair is outside the model (the GPU parity suite and the guard zones cover the kernel itself)."""
+import importlib.util
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+spec = importlib.util.spec_from_file_location("tc_protocol_check", os.path.join(ROOT, "scripts", "tc_protocol_check.py"))
+T = importlib.util.module_from_spec(spec)
+spec.loader.exec_module(T)
+SRC = open(os.path.join(ROOT, "pathmatfac.jl_b200", "csrc", "fused_tc.cu")).read()
+
+
+def test_the_model_still_describes_the_source():
+    """The constants and arrival counts the model transcribes, as they stand in fused_tc.cu today."""
+    assert re.search(r"#define PMF_SA 3\b", SRC) and "constexpr int SA = PMF_SA;" in SRC
+    assert "constexpr int SXK = SA == 4 ? 2 : 3, SXM = 1;" in SRC and "constexpr int SZ = SA == 4 ? 3 : 4;" in SRC
+    assert "constexpr int LA = SZ - 1;" in SRC and "constexpr int SDX = SA == 4 ? 1 : 2;" in SRC
+    assert "constexpr int RLAG = SDX == 2 ? 5 : 3;" in SRC
+    assert "constexpr int NEPI = 16;" in SRC and "constexpr int W_DRAIN0 = NEPI + 4, NDRAIN = 4;" in SRC
+    assert (T.SA, T.SXK, T.SXM, T.SZ, T.SDX, T.LA, T.RLAG, T.NEPI, T.NDRAIN) == (3, 3, 1, 4, 2, 3, 5, 16, 4)
+    for line in ("if (b == B_Y_READY || b == B_DY_EMPTY) cnt = NEPI;", "if (b >= B_G_READY && b < B_G_READY + SZ) cnt = NEPI / 2;",
+                 "if (b == B_DX_EMPTY || b == B_DX_EMPTY + 1 || (b >= B_DXS_FULL && b < B_DXS_FULL + SDX)) cnt = NDRAIN;"):
+        assert line in SRC, line
+    # every wait / arrive / commit site of the kernel is one the model has: 37 call sites in the source
+    sites = re.findall(r"\b(?:mbar_wait|mbar_arrive|mbar_arrive_relaxed|tc_commit_elect|mbar_expect_tx)\(bar\((B_[A-Z_]+)", SRC)
+    fams = {s[2:] for s in sites}
+    assert fams == {"FULL_XK", "EMPTY_XK", "FULL_XM", "EMPTY_XM", "FULL_A", "EMPTY_AG", "Z_FULL", "G_READY", "DX_FULL", "DX_EMPTY",
+                    "Y_READY", "DY_FULL", "DY_EMPTY", "DXS_FULL", "DXS_DONE", "Z_EMPTY"}
+    assert fams == {k[0] for k in T.Sim([1], 0).bars}
+
+
+@pytest.mark.parametrize("items", [[1], [2], [1, 1, 1], [3, 1, 4], [5, 1, 7, 2], [9, 3, 12, 1, 8], [6] * 6, [23], [1, 17, 1]])
+def test_no_race_no_deadlock(items):
+    """Work items of 1 to 23 tiles (a CTA's share of C2 is ~32 tiles in 2-3 items), item boundaries included."""
+    clean, failure = T.check(items, seeds=40)
+    assert failure is None and clean == 40, failure
+
+
+@pytest.mark.parametrize("mutation", T.MUTATIONS)
+def test_every_needed_ordering_is_noticed_when_removed(mutation):
+    clean, failure = T.check([9, 3, 12, 1, 8], seeds=25, mutate=mutation)
+    assert failure is not None, f"{mutation}: {clean} interleavings ran clean"
+    if mutation == "two_xk_stages":          # the kernel's static_assert(SXK >= LA) names this deadlock
+        assert failure.startswith("Deadlock")
+    else:
+        assert failure.startswith("Race")
+
+
+def test_the_one_implied_wait():
+    """MMA2/3's wait for DY_EMPTY is implied by its wait for Y_READY of the same item (an epilogue warp arrives there
+    after it has read the previous dY tile, in program order): removing it changes nothing."""
+    clean, failure = T.check([9, 3, 12, 1, 8], seeds=60, mutate="no_dy_empty")
+    assert failure is None and clean == 60
