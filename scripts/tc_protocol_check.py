@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""Race and deadlock check of the barrier choreography of the fused tcgen05 data pass (csrc/fused_tc.cu), at the level of
-its PROTOCOL: the 24 warps of a CTA as actors, the 16 mbarrier families with their arrival counts and the parity form of
+"""Race and deadlock check of the barrier choreography of the tcgen05 kernels -- the fused data pass (csrc/fused_tc.cu) and
+the two K > 64 kernels of csrc/wide_tc.cu (`--model zlink`, `--model grad_gemm`) -- at the level of their PROTOCOL.  For
+the fused data pass: the 24 warps of a CTA as actors, the 16 mbarrier families with their arrival counts and the parity form of
 `mbarrier.try_wait`, the asynchronous engines (TMA loads with complete_tx, tcgen05.mma with tcgen05.commit -- in order per
 issuing thread --, TMA reduce-add bulk groups with wait_group.read) and every buffer the roles hand to one another (shared
 memory rings, TMEM accumulators, staging buffers), sliced the way the warps slice them.
@@ -96,22 +97,15 @@ class Sim:
         self.bars = {}
         self.vc = defaultdict(dict)                 # actor -> vector clock
         self.mem = defaultdict(lambda: {"w": None, "r": []})
-        self.mma_q = {"MMA1": deque(), "MMA": deque()}      # tcgen05 pipe, in order per issuing thread
-        self.pipe_clock = {"MMA1": {}, "MMA": {}}
+        self.mma_q = defaultdict(deque)              # tcgen05 pipe, in order per issuing thread
+        self.pipe_clock = defaultdict(dict)
         self.loads = []                              # TMA loads in flight (complete in any order)
-        self.reduces = deque()                       # TMA reduce-add bulk groups of the MMA1 thread (reads complete in order)
-        self.reduce_done_clock = {}
+        self.bulk = defaultdict(deque)               # bulk async-groups per issuing thread (TMA reduce-add / store; reads complete in order)
+        self.bulk_done_clock = defaultdict(dict)
         self.n_async = 0
         self.trace = []
-        sa, sxk, sz = SA, SXK, SZ
-        self.SA = sa
-        # the kernel's static_assert(SXK >= LA): "with fewer XK stages than the MMA1 look-ahead the X producer deadlocks at
-        # item boundaries" -- the XM copy of a tile is issued LA tiles after its XK pair
-        self.SXK = 2 if mutate == "two_xk_stages" else sxk
-        for fam, n, cnt in (("FULL_XK", self.SXK, 1), ("EMPTY_XK", self.SXK, 1), ("FULL_XM", SXM, 1), ("EMPTY_XM", SXM, 1), ("FULL_A", sa, 1),
-                            ("EMPTY_AG", sa, 1), ("Z_FULL", sz, 1), ("G_READY", sz, NEPI // 2), ("DX_FULL", 2, 1), ("DX_EMPTY", 2, NDRAIN),
-                            ("Y_READY", 1, NEPI), ("DY_FULL", 1, 1), ("DY_EMPTY", 1, NEPI), ("DXS_FULL", SDX, NDRAIN), ("DXS_DONE", SDX, 1),
-                            ("Z_EMPTY", sz, 1)):           # mbar_init counts, fused_tc.cu:226-235
+        self.setup()
+        for fam, n, cnt in self.barrier_table():
             for i in range(n):
                 self.bars[(fam, i)] = Barrier(f"{fam}[{i}]", cnt)
 
@@ -173,17 +167,40 @@ class Sim:
         self.access(res, slices, "write", c, (name, 1))
         self.bars[bar].complete_tx(c)
 
-    def issue_reduce(self, res, slices):
-        c = dict(self.tick("MMA1"))
+    def issue_bulk(self, actor, res, slices):
+        """A bulk async-group that READS a shared-memory buffer (TMA reduce-add / TMA store)."""
+        c = dict(self.tick(actor))
         self.n_async += 1
-        self.reduces.append((res, slices, c, f"red:{self.n_async}"))
+        self.bulk[actor].append((res, slices, c, f"bulk:{self.n_async}"))
 
-    def step_reduce(self):
-        res, slices, c, name = self.reduces.popleft()
+    def step_bulk(self, actor):
+        res, slices, c, name = self.bulk[actor].popleft()
         c = dict(c)
         c[name] = 1
         self.access(res, slices, "read", c, (name, 1))
-        join(self.reduce_done_clock, c)
+        join(self.bulk_done_clock[actor], c)
+
+    # ---- what a model provides ---------------------------------------------------------------------------------------
+    def setup(self):
+        sa, sxk = SA, SXK
+        self.SA = sa
+        # the kernel's static_assert(SXK >= LA): "with fewer XK stages than the MMA1 look-ahead the X producer deadlocks at
+        # item boundaries" -- the XM copy of a tile is issued LA tiles after its XK pair
+        self.SXK = 2 if self.mutate == "two_xk_stages" else sxk
+
+    def barrier_table(self):                        # mbar_init counts, fused_tc.cu:226-235
+        return (("FULL_XK", self.SXK, 1), ("EMPTY_XK", self.SXK, 1), ("FULL_XM", SXM, 1), ("EMPTY_XM", SXM, 1), ("FULL_A", SA, 1),
+                ("EMPTY_AG", SA, 1), ("Z_FULL", SZ, 1), ("G_READY", SZ, NEPI // 2), ("DX_FULL", 2, 1), ("DX_EMPTY", 2, NDRAIN),
+                ("Y_READY", 1, NEPI), ("DY_FULL", 1, 1), ("DY_EMPTY", 1, NEPI), ("DXS_FULL", SDX, NDRAIN), ("DXS_DONE", SDX, 1),
+                ("Z_EMPTY", SZ, 1))
+
+    def actors(self):
+        a = {"TMA_A": self.tma_a(), "TMA_X": self.tma_x(), "MMA1": self.mma1(), "MMA": self.mma()}
+        for d in range(NDRAIN):
+            a["DRAIN%d" % d] = self.drain(d)
+        for w in range(NEPI):
+            a["EPI%d" % w] = self.epi(w)
+        return a
 
     # ---- the roles (generators yield ("wait", bar, parity) / ("wait_reduce", n) when they may block) --------------------
     def tiles(self):
@@ -231,7 +248,7 @@ class Sim:
             nonlocal gr
             sb = gr % SDX
             yield ("wait", ("DXS_FULL", sb), (gr // SDX) & 1)
-            self.issue_reduce("DXS%d" % sb, range(NDRAIN))
+            self.issue_bulk("MMA1", "DXS%d" % sb, range(NDRAIN))
             yield ("wait_reduce", 1)                                     # cp.async.bulk.wait_group.read 1
             if gr > 0:
                 self.bars[("DXS_DONE", sb ^ 1)].arrive(self.tick("MMA1"))
@@ -340,11 +357,7 @@ class Sim:
 
     # ---- scheduler -----------------------------------------------------------------------------------------------------------
     def run(self):
-        actors = {"TMA_A": self.tma_a(), "TMA_X": self.tma_x(), "MMA1": self.mma1(), "MMA": self.mma()}
-        for d in range(NDRAIN):
-            actors["DRAIN%d" % d] = self.drain(d)
-        for w in range(NEPI):
-            actors["EPI%d" % w] = self.epi(w)
+        actors = self.actors()
         blocked = {}                                   # actor -> the op it is waiting on
         for a in list(actors):
             try:
@@ -356,15 +369,14 @@ class Sim:
             op = blocked[a]
             if op[0] == "wait":
                 return self.bars[op[1]].parity_passes(op[2])
-            return len(self.reduces) <= op[1]          # wait_group.read n
+            return len(self.bulk[a]) <= op[1]          # cp.async.bulk.wait_group.read n
 
         steps = 0
-        while actors or self.loads or self.reduces or any(self.mma_q.values()):
+        while actors or self.loads or any(self.bulk.values()) or any(self.mma_q.values()):
             choices = [("actor", a) for a in actors if enabled(a)]
             choices += [("pipe", t) for t, q in self.mma_q.items() if q]
             choices += [("load", i) for i in range(len(self.loads))]
-            if self.reduces:
-                choices.append(("reduce", 0))
+            choices += [("bulk", t) for t, q in self.bulk.items() if q]
             if not choices:
                 raise Deadlock("; ".join(f"{a} waits for {blocked[a][1]}" + (f" parity {blocked[a][2]}" if blocked[a][0] == "wait" else "")
                                           for a in sorted(actors)))
@@ -374,14 +386,14 @@ class Sim:
                 self.step_pipe(x)
             elif kind == "load":
                 self.step_load(x)
-            elif kind == "reduce":
-                self.step_reduce()
+            elif kind == "bulk":
+                self.step_bulk(x)
             else:
                 op = blocked[x]
                 if op[0] == "wait":
                     join(self.vc[x], self.bars[op[1]].clock)      # acquire
                 else:
-                    join(self.vc[x], self.reduce_done_clock)
+                    join(self.vc[x], self.bulk_done_clock[x])
                 try:
                     blocked[x] = next(actors[x])
                 except StopIteration:
@@ -391,6 +403,153 @@ class Sim:
 
 
 # every one of these removes an ordering the kernel needs (a race, or for two_xk_stages the deadlock its static_assert names)
+class Zlink(Sim):
+    """zlink_kernel of csrc/wide_tc.cu (K > 64: Z contraction + link epilogue, :150-400).  `items` = 128-sample tiles per
+    range of one CTA; every tile runs `nks` 64-factor slabs through the operand ring and hands two 64-sample sub-tiles of
+    data in / G' out through the A/G ring."""
+    ZS, ZSZ, ZSA, NE = 2, 4, 3, 16                    # wide_tc.cu:130, :135
+    nks = 2                                           # K = 128
+
+    def setup(self):
+        pass
+
+    def barrier_table(self):                          # mbar_init, wide_tc.cu:168-173: ZEMPTY and G_READY take one arrive per epilogue warp
+        return (("FULL", self.ZS, 1), ("EMPTY", self.ZS, 1), ("ZFULL", self.ZSZ, 1), ("ZEMPTY", self.ZSZ, self.NE),
+                ("AG_FULL", self.ZSA, 1), ("AG_EMPTY", self.ZSA, 1), ("G_READY", self.ZSA, self.NE))
+
+    def actors(self):
+        a = {"TMA": self.tma(), "TMA_A": self.tma_a(), "GST": self.gst(), "MMA": self.mma()}
+        for w in range(self.NE):
+            a["EPI%d" % w] = self.epi(w)
+        return a
+
+    def tma(self):
+        """Operand producer, wide_tc.cu:184-204."""
+        r = Ring()
+        for _q, n in self.tiles():
+            for _ in range(n):
+                for _ks in range(self.nks):
+                    if self.mutate != "no_empty":
+                        yield ("wait", ("EMPTY", r.s), r.ph ^ 1)
+                    self.issue_load("TMA", ("FULL", r.s), "ST%d" % r.s, [0])
+                    r.next(self.ZS)
+
+    def tma_a(self):
+        """Data producer, :205-224."""
+        r = Ring()
+        for _q, n in self.tiles():
+            for _ in range(2 * n):
+                if self.mutate != "no_ag_empty":
+                    yield ("wait", ("AG_EMPTY", r.s), r.ph ^ 1)
+                self.issue_load("TMA_A", ("AG_FULL", r.s), "AG%d" % r.s, range(self.NE))
+                r.next(self.ZSA)
+
+    def gst(self):
+        """G' store issuer, :225-249: a buffer returns to the data producer once the store engine has READ it."""
+        r = Ring()
+        prev = -1
+        for _q, n in self.tiles():
+            for _ in range(2 * n):
+                if self.mutate != "no_g_ready":
+                    yield ("wait", ("G_READY", r.s), r.ph)
+                self.issue_bulk("GST", "AG%d" % r.s, range(self.NE))
+                if self.mutate != "no_store_wait":
+                    yield ("wait_reduce", 1)
+                if prev >= 0:
+                    self.bars[("AG_EMPTY", prev)].arrive(self.tick("GST"))
+                prev = r.s
+                r.next(self.ZSA)
+        yield ("wait_reduce", 0)
+        if prev >= 0:
+            self.bars[("AG_EMPTY", prev)].arrive(self.tick("GST"))
+
+    def mma(self):
+        """:250-282."""
+        r, rz = Ring(), Ring()
+        for _q, n in self.tiles():
+            for _ in range(n):
+                if self.mutate != "no_zempty":
+                    yield ("wait", ("ZEMPTY", rz.s), rz.ph ^ 1)
+                for _ks in range(self.nks):
+                    if self.mutate != "no_full":
+                        yield ("wait", ("FULL", r.s), r.ph)
+                    self.issue_mma("MMA", [("ST%d" % r.s, [0], "read"), ("ZACC%d" % rz.s, range(self.NE), "write")])
+                    self.commit("MMA", ("EMPTY", r.s))
+                    r.next(self.ZS)
+                self.commit("MMA", ("ZFULL", rz.s))
+                rz.next(self.ZSZ)
+
+    def epi(self, w):
+        """:283-400: warp = (TMEM lane quarter, 16-sample chunk of the 64-sample sub-tile)."""
+        me = "EPI%d" % w
+        ra, rz = Ring(), Ring()
+        for _q, n in self.tiles():
+            for _ in range(n):
+                if self.mutate != "no_zfull":
+                    yield ("wait", ("ZFULL", rz.s), rz.ph)
+                for h in range(2):
+                    self.sync_access(me, "ZACC%d" % rz.s, [w], "read")
+                    if self.mutate != "no_ag_full":
+                        yield ("wait", ("AG_FULL", ra.s), ra.ph)
+                    self.sync_access(me, "AG%d" % ra.s, [w], "read")
+                    if h == 1:
+                        self.bars[("ZEMPTY", rz.s)].arrive(self.tick(me))
+                    self.sync_access(me, "AG%d" % ra.s, [w], "write")
+                    self.bars[("G_READY", ra.s)].arrive(self.tick(me))
+                    ra.next(self.ZSA)
+                rz.next(self.ZSZ)
+
+
+class GradGemm(Sim):
+    """grad_gemm_kernel<A_MN> of csrc/wide_tc.cu (:440-545): `items` = contraction steps per output group of one CTA."""
+    GS, NE = 3, 4                                     # wide_tc.cu:418-420
+
+    def setup(self):
+        pass
+
+    def barrier_table(self):                          # :447
+        return (("FULL", self.GS, 1), ("EMPTY", self.GS, 1), ("ACC_FULL", 1, 1), ("ACC_EMPTY", 1, self.NE))
+
+    def actors(self):
+        a = {"TMA": self.tma(), "MMA": self.mma()}
+        for w in range(self.NE):
+            a["EPI%d" % w] = self.epi(w)
+        return a
+
+    def tma(self):
+        r = Ring()
+        for _q, n in self.tiles():
+            for _ in range(n):
+                if self.mutate != "no_empty":
+                    yield ("wait", ("EMPTY", r.s), r.ph ^ 1)
+                self.issue_load("TMA", ("FULL", r.s), "ST%d" % r.s, [0])
+                r.next(self.GS)
+
+    def mma(self):
+        r = Ring()
+        for q, n in self.tiles():
+            if self.mutate != "no_acc_empty":
+                yield ("wait", ("ACC_EMPTY", 0), (q & 1) ^ 1)
+            for _ in range(n):
+                if self.mutate != "no_full":
+                    yield ("wait", ("FULL", r.s), r.ph)
+                self.issue_mma("MMA", [("ST%d" % r.s, [0], "read"), ("ACC", range(self.NE), "write")])
+                self.commit("MMA", ("EMPTY", r.s))
+                r.next(self.GS)
+            self.commit("MMA", ("ACC_FULL", 0))
+
+    def epi(self, w):
+        me = "EPI%d" % w
+        for q, _n in self.tiles():
+            if self.mutate != "no_acc_full":
+                yield ("wait", ("ACC_FULL", 0), q & 1)
+            self.sync_access(me, "ACC", [w], "read")
+            self.bars[("ACC_EMPTY", 0)].arrive(self.tick(me))
+
+
+MODELS = {"fused": Sim, "zlink": Zlink, "grad_gemm": GradGemm}
+MODEL_MUTATIONS = {"zlink": ["no_empty", "no_ag_empty", "no_g_ready", "no_store_wait", "no_zempty", "no_full", "no_zfull", "no_ag_full"],
+                   "grad_gemm": ["no_empty", "no_acc_empty", "no_full", "no_acc_full"]}
 MUTATIONS = ["no_z_empty", "no_dx_empty", "no_dxs_done", "no_full_a", "no_dy_full", "no_empty_ag", "no_empty_xk", "no_y_ready",
              "no_g_ready", "no_full_xm", "no_z_full", "two_xk_stages"]
 # removing this wait changes nothing: Y_READY of the next item already implies that every epilogue warp has read the dY
@@ -398,11 +557,11 @@ MUTATIONS = ["no_z_empty", "no_dx_empty", "no_dxs_done", "no_full_a", "no_dy_ful
 IMPLIED = ["no_dy_empty"]
 
 
-def check(items, seeds, mutate=None, first_seed=0):
+def check(items, seeds, mutate=None, first_seed=0, model="fused"):
     """(number of clean runs, first failure or None)."""
     for s in range(first_seed, first_seed + seeds):
         try:
-            Sim(items, s, mutate).run()
+            MODELS[model](items, s, mutate).run()
         except (Race, Deadlock) as e:
             return s - first_seed, f"{type(e).__name__}: {e} (items {items}, seed {s})"
     return seeds, None
@@ -412,11 +571,12 @@ def main(argv=None):
     ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
     ap.add_argument("--items", default="5,1,7,2", help="tiles per work item of one CTA")
     ap.add_argument("--seeds", type=int, default=200)
-    ap.add_argument("--mutate", default=None, choices=MUTATIONS + IMPLIED)
+    ap.add_argument("--mutate", default=None)
+    ap.add_argument("--model", default="fused", choices=sorted(MODELS), help="fused_tc.cu's data pass, or one of wide_tc.cu's kernels")
     a = ap.parse_args(argv)
     items = [int(x) for x in a.items.split(",")]
-    ok, fail = check(items, a.seeds, a.mutate)
-    print(f"items {items}, mutation {a.mutate}: {ok} interleavings clean" + (f"; then {fail}" if fail else ""))
+    ok, fail = check(items, a.seeds, a.mutate, model=a.model)
+    print(f"{a.model}: items {items}, mutation {a.mutate}: {ok} interleavings clean" + (f"; then {fail}" if fail else ""))
     return 1 if fail else 0
 
 

@@ -59,3 +59,31 @@ def test_the_one_implied_wait():
     after it has read the previous dY tile, in program order): removing it changes nothing."""
     clean, failure = T.check([9, 3, 12, 1, 8], seeds=60, mutate="no_dy_empty")
     assert failure is None and clean == 60
+
+
+# ---- the two K > 64 kernels of csrc/wide_tc.cu --------------------------------------------------------------------------
+WIDE = open(os.path.join(ROOT, "pathmatfac.jl_b200", "csrc", "wide_tc.cu")).read()
+
+
+def test_the_wide_models_still_describe_the_source():
+    assert "constexpr int ZBJ = 128, ZBI = 128, ZS = 2, ZSZ = 4, ZSA = 3;" in WIDE and "constexpr int Z_NEPI = 16," in WIDE
+    assert "constexpr int GS = 3;" in WIDE and "constexpr int G_NEPI = 4," in WIDE
+    assert (T.Zlink.ZS, T.Zlink.ZSZ, T.Zlink.ZSA, T.Zlink.NE, T.GradGemm.GS, T.GradGemm.NE) == (2, 4, 3, 16, 3, 4)
+    assert "const bool per_warp = (b >= ZB_ZEMPTY && b < ZB_ZEMPTY + ZSZ) || (b >= ZB_G_READY && b < ZB_G_READY + ZSA);" in WIDE
+    assert "mbar_init(bar(b), b == GB_ACC_EMPTY ? (uint32_t)G_NEPI : 1u);" in WIDE
+    fams = set(re.findall(r"\b(?:mbar_wait|mbar_arrive|mbar_arrive_relaxed|tc_commit|mbar_expect_tx)\(bar\(((?:ZB|GB)_[A-Z_]+)", WIDE))
+    assert fams == {"ZB_FULL", "ZB_EMPTY", "ZB_ZFULL", "ZB_ZEMPTY", "ZB_AG_FULL", "ZB_AG_EMPTY", "ZB_G_READY",
+                    "GB_FULL", "GB_EMPTY", "GB_ACC_FULL", "GB_ACC_EMPTY"}
+
+
+@pytest.mark.parametrize("model", ["zlink", "grad_gemm"])
+@pytest.mark.parametrize("items", [[1], [1, 1, 1], [5, 1, 7, 2], [13, 2, 9]])
+def test_wide_kernels_no_race_no_deadlock(model, items):
+    clean, failure = T.check(items, seeds=40, model=model)
+    assert failure is None and clean == 40, failure
+
+
+@pytest.mark.parametrize("model,mutation", [(m, mu) for m in ("zlink", "grad_gemm") for mu in T.MODEL_MUTATIONS[m]])
+def test_wide_kernels_every_needed_ordering_is_noticed_when_removed(model, mutation):
+    clean, failure = T.check([5, 1, 7, 2], seeds=25, mutate=mutation, model=model)
+    assert failure is not None, f"{model} / {mutation}: {clean} interleavings ran clean"
