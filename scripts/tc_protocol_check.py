@@ -91,9 +91,9 @@ class Barrier:
 
 
 class Sim:
-    def __init__(self, items, seed, mutate=None):
+    def __init__(self, items, seed, mutate=None, ordered_loads=False):
         self.rng = random.Random(seed)
-        self.items, self.mutate = items, mutate
+        self.items, self.mutate, self.ordered_loads = items, mutate, ordered_loads
         self.bars = {}
         self.vc = defaultdict(dict)                 # actor -> vector clock
         self.mem = defaultdict(lambda: {"w": None, "r": []})
@@ -103,7 +103,9 @@ class Sim:
         self.bulk = defaultdict(deque)               # bulk async-groups per issuing thread (TMA reduce-add / store; reads complete in order)
         self.bulk_done_clock = defaultdict(dict)
         self.n_async = 0
-        self.trace = []
+        # odd seeds: every actor and every asynchronous engine gets its own speed (1/50 to 5 times the others), so that
+        # schedules in which one role is starved for many tiles, or an engine lags far behind, are explored too
+        self.weights = {} if seed & 1 else None
         self.setup()
         for fam, n, cnt in self.barrier_table():
             for i in range(n):
@@ -158,10 +160,10 @@ class Sim:
         c = dict(self.tick(actor))
         self.bars[bar].arrive(c, expect_tx=1)                 # mbarrier.arrive.expect_tx by the producer thread
         self.n_async += 1
-        self.loads.append((bar, res, slices, c, f"tma:{self.n_async}"))
+        self.loads.append((bar, res, slices, c, f"tma:{self.n_async}", actor))
 
     def step_load(self, i):
-        bar, res, slices, c, name = self.loads.pop(i)
+        bar, res, slices, c, name, _actor = self.loads.pop(i)
         c = dict(c)
         c[name] = 1
         self.access(res, slices, "write", c, (name, 1))
@@ -189,7 +191,10 @@ class Sim:
         self.SXK = 2 if self.mutate == "two_xk_stages" else sxk
 
     def barrier_table(self):                        # mbar_init counts, fused_tc.cu:226-235
-        return (("FULL_XK", self.SXK, 1), ("EMPTY_XK", self.SXK, 1), ("FULL_XM", SXM, 1), ("EMPTY_XM", SXM, 1), ("FULL_A", SA, 1),
+        # variant "per_group_full_a" (the proposed fix of the finding in tests/test_tc_protocol.py): one FULL_A barrier per
+        # (stage, epilogue group), so that a group sees CONSECUTIVE phases of the barrier it waits on
+        n_full_a = 2 * SA if self.mutate == "per_group_full_a" else SA
+        return (("FULL_XK", self.SXK, 1), ("EMPTY_XK", self.SXK, 1), ("FULL_XM", SXM, 1), ("EMPTY_XM", SXM, 1), ("FULL_A", n_full_a, 1),
                 ("EMPTY_AG", SA, 1), ("Z_FULL", SZ, 1), ("G_READY", SZ, NEPI // 2), ("DX_FULL", 2, 1), ("DX_EMPTY", 2, NDRAIN),
                 ("Y_READY", 1, NEPI), ("DY_FULL", 1, 1), ("DY_EMPTY", 1, NEPI), ("DXS_FULL", SDX, NDRAIN), ("DXS_DONE", SDX, 1),
                 ("Z_EMPTY", SZ, 1))
@@ -210,12 +215,15 @@ class Sim:
     def tma_a(self):
         """fused_tc.cu:257-280."""
         r = Ring()
+        g = 0
         for _q, n in self.tiles():
             for _ in range(n):
                 if self.mutate != "no_empty_ag":
                     yield ("wait", ("EMPTY_AG", r.s), r.ph ^ 1)
-                self.issue_load("TMA_A", ("FULL_A", r.s), "AG%d" % r.s, range(8))
+                full = r.s + SA * (g & 1) if self.mutate == "per_group_full_a" else r.s
+                self.issue_load("TMA_A", ("FULL_A", full), "AG%d" % r.s, range(8))
                 r.next(self.SA)
+                g += 1
 
     def tma_x(self):
         """fused_tc.cu:281-321."""
@@ -341,7 +349,9 @@ class Sim:
                     continue
                 if self.mutate != "no_z_full":
                     yield ("wait", ("Z_FULL", rz.s), rz.ph)
-                if self.mutate != "no_full_a":
+                if self.mutate == "per_group_full_a":       # this group's k-th tile on this stage: k = (g - 1) // (2 SA)
+                    yield ("wait", ("FULL_A", ra.s + SA * grp), ((g - 1) // (2 * SA)) & 1)
+                elif self.mutate != "no_full_a":
                     yield ("wait", ("FULL_A", ra.s), ra.ph)
                 self.sync_access(me, "Z%d" % rz.s, [sl], "read")
                 self.sync_access(me, "AG%d" % ra.s, [sl], "read")
@@ -354,6 +364,13 @@ class Sim:
                 yield ("wait", ("DY_FULL", 0), q & 1)
             self.sync_access(me, "DY", [w], "read")
             self.bars[("DY_EMPTY", 0)].arrive(self.tick(me))
+
+    def weight(self, choice):
+        key = choice[1] if choice[0] in ("actor", "pipe", "bulk") else "tma-engine"
+        key = (choice[0], key)
+        if key not in self.weights:
+            self.weights[key] = self.rng.choice([0.02, 0.2, 1.0, 1.0, 5.0])
+        return self.weights[key]
 
     # ---- scheduler -----------------------------------------------------------------------------------------------------------
     def run(self):
@@ -375,12 +392,23 @@ class Sim:
         while actors or self.loads or any(self.bulk.values()) or any(self.mma_q.values()):
             choices = [("actor", a) for a in actors if enabled(a)]
             choices += [("pipe", t) for t, q in self.mma_q.items() if q]
-            choices += [("load", i) for i in range(len(self.loads))]
+            if self.ordered_loads:                        # TMA loads of one issuing thread complete in issue order
+                seen = set()
+                for i, l in enumerate(self.loads):
+                    if l[5] not in seen:
+                        seen.add(l[5])
+                        choices.append(("load", i))
+            else:                                         # the PTX model: no order among bulk asynchronous copies
+                choices += [("load", i) for i in range(len(self.loads))]
             choices += [("bulk", t) for t, q in self.bulk.items() if q]
             if not choices:
                 raise Deadlock("; ".join(f"{a} waits for {blocked[a][1]}" + (f" parity {blocked[a][2]}" if blocked[a][0] == "wait" else "")
                                           for a in sorted(actors)))
-            kind, x = self.rng.choice(choices)
+            if self.weights is None:
+                kind, x = self.rng.choice(choices)
+            else:                                         # starve some actors / engines, rush others
+                ws = [self.weight(c) for c in choices]
+                kind, x = self.rng.choices(choices, weights=ws)[0]
             steps += 1
             if kind == "pipe":
                 self.step_pipe(x)
@@ -557,11 +585,11 @@ MUTATIONS = ["no_z_empty", "no_dx_empty", "no_dxs_done", "no_full_a", "no_dy_ful
 IMPLIED = ["no_dy_empty"]
 
 
-def check(items, seeds, mutate=None, first_seed=0, model="fused"):
+def check(items, seeds, mutate=None, first_seed=0, model="fused", ordered_loads=False):
     """(number of clean runs, first failure or None)."""
     for s in range(first_seed, first_seed + seeds):
         try:
-            MODELS[model](items, s, mutate).run()
+            MODELS[model](items, s, mutate, ordered_loads).run()
         except (Race, Deadlock) as e:
             return s - first_seed, f"{type(e).__name__}: {e} (items {items}, seed {s})"
     return seeds, None
@@ -573,9 +601,10 @@ def main(argv=None):
     ap.add_argument("--seeds", type=int, default=200)
     ap.add_argument("--mutate", default=None)
     ap.add_argument("--model", default="fused", choices=sorted(MODELS), help="fused_tc.cu's data pass, or one of wide_tc.cu's kernels")
+    ap.add_argument("--ordered-loads", action="store_true", help="TMA loads of one issuing thread complete in issue order")
     a = ap.parse_args(argv)
     items = [int(x) for x in a.items.split(",")]
-    ok, fail = check(items, a.seeds, a.mutate, model=a.model)
+    ok, fail = check(items, a.seeds, a.mutate, model=a.model, ordered_loads=a.ordered_loads)
     print(f"{a.model}: items {items}, mutation {a.mutate}: {ok} interleavings clean" + (f"; then {fail}" if fail else ""))
     return 1 if fail else 0
 
