@@ -58,16 +58,16 @@ def test_finding_full_a_parity_alias_when_tma_loads_complete_far_out_of_order():
     the measured load latency is 0.5 us and no device run has shown it.  With loads completing in issue
     order the protocol is clean (test above); the K > 64 kernels, whose consumers see consecutive phases, are clean either
     way.  An even number of A/G stages (the existing -DPMF_SA=4 build) removes the dependence."""
-    clean, failure = T.check([9, 3, 12, 1, 8], seeds=150)
+    clean, failure = T.check([9, 3, 12, 1, 8], seeds=40, first_seed=61)          # first shown by seed 81
     assert failure is not None and failure.startswith("Race") and "AG" in failure, (clean, failure)
     assert ("tma:" in failure and "EPI" in failure), failure           # a TMA load and an epilogue warp on the same stage, unordered
     for model in ("zlink", "grad_gemm"):
-        clean, failure = T.check([9, 3, 12, 1, 8], seeds=120, model=model)
+        clean, failure = T.check([9, 3, 12, 1, 8], seeds=60, model=model)
         assert failure is None, failure
     # the fix (scripts/experiments/r2_full_a_per_group_barriers.patch, compiled and protocol-checked, never run): one FULL_A
     # barrier per (stage, epilogue group) -- a group then sees consecutive phases of the barrier it waits on
-    for items in ([9, 3, 12, 1, 8], [1, 2, 1, 7, 3], [23]):
-        clean, failure = T.check(items, seeds=120, mutate="per_group_full_a")
+    for items, first in (([9, 3, 12, 1, 8], 61), ([1, 2, 1, 7, 3], 0), ([23], 0)):
+        clean, failure = T.check(items, seeds=50, mutate="per_group_full_a", first_seed=first)
         assert failure is None, failure
     patch = open(os.path.join(ROOT, "scripts", "experiments", "r2_full_a_per_group_barriers.patch")).read()
     assert "SA * (int)(gcount & 1u)" in patch and "(g / (2u * SA)) & 1u" in patch
