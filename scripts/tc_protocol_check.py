@@ -183,21 +183,25 @@ class Sim:
         join(self.bulk_done_clock[actor], c)
 
     # ---- what a model provides ---------------------------------------------------------------------------------------
+    CONST = dict(SA=SA, SXK=SXK, SXM=SXM, SZ=SZ, SDX=SDX)     # the default build (PMF_SA = 3)
+
     def setup(self):
-        sa, sxk = SA, SXK
-        self.SA = sa
+        c = self.CONST
+        self.SA, self.SXK, self.SXM, self.SZ, self.SDX = c["SA"], c["SXK"], c["SXM"], c["SZ"], c["SDX"]
+        self.LA, self.RLAG = self.SZ - 1, (5 if self.SDX == 2 else 3)
         # the kernel's static_assert(SXK >= LA): "with fewer XK stages than the MMA1 look-ahead the X producer deadlocks at
         # item boundaries" -- the XM copy of a tile is issued LA tiles after its XK pair
-        self.SXK = 2 if self.mutate == "two_xk_stages" else sxk
+        if self.mutate == "two_xk_stages":
+            self.SXK = 2
 
     def barrier_table(self):                        # mbar_init counts, fused_tc.cu:226-235
         # variant "per_group_full_a" (the proposed fix of the finding in tests/test_tc_protocol.py): one FULL_A barrier per
         # (stage, epilogue group), so that a group sees CONSECUTIVE phases of the barrier it waits on
-        n_full_a = 2 * SA if self.mutate == "per_group_full_a" else SA
-        return (("FULL_XK", self.SXK, 1), ("EMPTY_XK", self.SXK, 1), ("FULL_XM", SXM, 1), ("EMPTY_XM", SXM, 1), ("FULL_A", n_full_a, 1),
-                ("EMPTY_AG", SA, 1), ("Z_FULL", SZ, 1), ("G_READY", SZ, NEPI // 2), ("DX_FULL", 2, 1), ("DX_EMPTY", 2, NDRAIN),
-                ("Y_READY", 1, NEPI), ("DY_FULL", 1, 1), ("DY_EMPTY", 1, NEPI), ("DXS_FULL", SDX, NDRAIN), ("DXS_DONE", SDX, 1),
-                ("Z_EMPTY", SZ, 1))
+        n_full_a = 2 * self.SA if self.mutate == "per_group_full_a" else self.SA
+        return (("FULL_XK", self.SXK, 1), ("EMPTY_XK", self.SXK, 1), ("FULL_XM", self.SXM, 1), ("EMPTY_XM", self.SXM, 1), ("FULL_A", n_full_a, 1),
+                ("EMPTY_AG", self.SA, 1), ("Z_FULL", self.SZ, 1), ("G_READY", self.SZ, NEPI // 2), ("DX_FULL", 2, 1), ("DX_EMPTY", 2, NDRAIN),
+                ("Y_READY", 1, NEPI), ("DY_FULL", 1, 1), ("DY_EMPTY", 1, NEPI), ("DXS_FULL", self.SDX, NDRAIN), ("DXS_DONE", self.SDX, 1),
+                ("Z_EMPTY", self.SZ, 1))
 
     def actors(self):
         a = {"TMA_A": self.tma_a(), "TMA_X": self.tma_x(), "MMA1": self.mma1(), "MMA": self.mma()}
@@ -220,7 +224,7 @@ class Sim:
             for _ in range(n):
                 if self.mutate != "no_empty_ag":
                     yield ("wait", ("EMPTY_AG", r.s), r.ph ^ 1)
-                full = r.s + SA * (g & 1) if self.mutate == "per_group_full_a" else r.s
+                full = r.s + self.SA * (g & 1) if self.mutate == "per_group_full_a" else r.s
                 self.issue_load("TMA_A", ("FULL_A", full), "AG%d" % r.s, range(8))
                 r.next(self.SA)
                 g += 1
@@ -228,12 +232,12 @@ class Sim:
     def tma_x(self):
         """fused_tc.cu:281-321."""
         rk, rm = Ring(), Ring()
-        pend = [-1] * LA
+        pend = [-1] * self.LA
 
         def load_xm():
             yield ("wait", ("EMPTY_XM", rm.s), rm.ph ^ 1)
             self.issue_load("TMA_X", ("FULL_XM", rm.s), "XM%d" % rm.s, [0])
-            rm.next(SXM)
+            rm.next(self.SXM)
         for _q, n in self.tiles():
             for t in range(n):
                 if self.mutate != "no_empty_xk":
@@ -243,23 +247,27 @@ class Sim:
                 if pend[0] >= 0:
                     yield from load_xm()
                 pend = pend[1:] + [t]
-        for k in range(LA):
+        for k in range(self.LA):
             if pend[k] >= 0:
                 yield from load_xm()
 
     def mma1(self):
-        """fused_tc.cu:322-403: Z = Y X' up to SZ tiles ahead, and the TMA reduce-adds of the staged dX tiles."""
+        """fused_tc.cu:322-403: Z = Y X' up to self.SZ tiles ahead, and the TMA reduce-adds of the staged dX tiles."""
         rx1, rz1 = Ring(), Ring()
         gr = 0
 
         def reduce_tile():
             nonlocal gr
-            sb = gr % SDX
-            yield ("wait", ("DXS_FULL", sb), (gr // SDX) & 1)
+            sb = gr % self.SDX
+            yield ("wait", ("DXS_FULL", sb), (gr // self.SDX) & 1)
             self.issue_bulk("MMA1", "DXS%d" % sb, range(NDRAIN))
-            yield ("wait_reduce", 1)                                     # cp.async.bulk.wait_group.read 1
-            if gr > 0:
-                self.bars[("DXS_DONE", sb ^ 1)].arrive(self.tick("MMA1"))
+            if self.SDX == 2:
+                yield ("wait_reduce", 1)                                 # cp.async.bulk.wait_group.read 1
+                if gr > 0:
+                    self.bars[("DXS_DONE", sb ^ 1)].arrive(self.tick("MMA1"))
+            else:
+                yield ("wait_reduce", 0)
+                self.bars[("DXS_DONE", 0)].arrive(self.tick("MMA1"))
             gr += 1
         for q, n in self.tiles():
             if self.mutate != "no_y_ready":
@@ -273,15 +281,15 @@ class Sim:
                 self.commit("MMA1", ("EMPTY_XK", rx1.s))
                 self.commit("MMA1", ("Z_FULL", rz1.s))
                 rx1.next(self.SXK)
-                rz1.next(SZ)
-                if it - it_r >= RLAG:
+                rz1.next(self.SZ)
+                if it - it_r >= self.RLAG:
                     yield from reduce_tile()
                     it_r += 1
             while it_r < n:
                 yield from reduce_tile()
                 it_r += 1
         yield ("wait_reduce", 0)
-        if gr > 0:
+        if self.SDX == 2 and gr > 0:
             self.bars[("DXS_DONE", (gr - 1) & 1)].arrive(self.tick("MMA1"))
 
     def mma(self):
@@ -307,8 +315,8 @@ class Sim:
                 self.issue_mma("MMA", [("Z%d" % rz.s, range(8), "read"), ("XM%d" % rx3.s, [0], "read"), ("DY", range(NEPI), "write")])
                 self.commit("MMA", ("EMPTY_XM", rx3.s))
                 self.commit("MMA", ("Z_EMPTY", rz.s))
-                rx3.next(SXM)
-                rz.next(SZ)
+                rx3.next(self.SXM)
+                rz.next(self.SZ)
                 g += 1
             self.commit("MMA", ("DY_FULL", 0))
 
@@ -318,12 +326,12 @@ class Sim:
         g = 0
         for _q, n in self.tiles():
             for _ in range(n):
-                b, sb = g & 1, g % SDX
+                b, sb = g & 1, g % self.SDX
                 yield ("wait", ("DX_FULL", b), (g >> 1) & 1)
                 self.sync_access(me, "DX%d" % b, [d], "read")
                 self.bars[("DX_EMPTY", b)].arrive(self.tick(me))
                 if self.mutate != "no_dxs_done":
-                    yield ("wait", ("DXS_DONE", sb), ((g // SDX) - 1) & 1)
+                    yield ("wait", ("DXS_DONE", sb), ((g // self.SDX) - 1) & 1)
                 self.sync_access(me, "DXS%d" % sb, [d], "write")
                 self.bars[("DXS_FULL", sb)].arrive(self.tick(me))
                 g += 1
@@ -335,7 +343,7 @@ class Sim:
         ra, rz = Ring(), Ring()
         if grp == 1:
             ra.next(self.SA)
-            rz.next(SZ)
+            rz.next(self.SZ)
         g = 0
         for q, n in self.tiles():
             # item prologue: this warp's part of the Y operands (TMEM [Yh|Yl], shared-memory Ys), :693-717
@@ -349,8 +357,8 @@ class Sim:
                     continue
                 if self.mutate != "no_z_full":
                     yield ("wait", ("Z_FULL", rz.s), rz.ph)
-                if self.mutate == "per_group_full_a":       # this group's k-th tile on this stage: k = (g - 1) // (2 SA)
-                    yield ("wait", ("FULL_A", ra.s + SA * grp), ((g - 1) // (2 * SA)) & 1)
+                if self.mutate == "per_group_full_a":       # this group's k-th tile on this stage: k = (g - 1) // (2 self.SA)
+                    yield ("wait", ("FULL_A", ra.s + self.SA * grp), ((g - 1) // (2 * self.SA)) & 1)
                 elif self.mutate != "no_full_a":
                     yield ("wait", ("FULL_A", ra.s), ra.ph)
                 self.sync_access(me, "Z%d" % rz.s, [sl], "read")
@@ -359,7 +367,7 @@ class Sim:
                 self.sync_access(me, "AG%d" % ra.s, [sl], "write")       # and over the A values (A operand of MMA2)
                 self.bars[("G_READY", rz.s)].arrive(self.tick(me))
                 ra.next(self.SA); ra.next(self.SA)
-                rz.next(SZ); rz.next(SZ)
+                rz.next(self.SZ); rz.next(self.SZ)
             if self.mutate != "no_dy_full":
                 yield ("wait", ("DY_FULL", 0), q & 1)
             self.sync_access(me, "DY", [w], "read")
@@ -575,7 +583,13 @@ class GradGemm(Sim):
             self.bars[("ACC_EMPTY", 0)].arrive(self.tick(me))
 
 
-MODELS = {"fused": Sim, "zlink": Zlink, "grad_gemm": GradGemm}
+class FusedSA4(Sim):
+    """The -DPMF_SA=4 build of fused_tc.cu (:66-79): four A/G stages, two Xb stages, three Z accumulators, one dX staging
+    buffer.  With an even ring every A/G stage belongs to ONE epilogue group, which then sees consecutive phases."""
+    CONST = dict(SA=4, SXK=2, SXM=1, SZ=3, SDX=1)
+
+
+MODELS = {"fused": Sim, "fused_sa4": FusedSA4, "zlink": Zlink, "grad_gemm": GradGemm}
 MODEL_MUTATIONS = {"zlink": ["no_empty", "no_ag_empty", "no_g_ready", "no_store_wait", "no_zempty", "no_full", "no_zfull", "no_ag_full"],
                    "grad_gemm": ["no_empty", "no_acc_empty", "no_full", "no_acc_full"]}
 MUTATIONS = ["no_z_empty", "no_dx_empty", "no_dxs_done", "no_full_a", "no_dy_full", "no_empty_ag", "no_empty_xk", "no_y_ready",

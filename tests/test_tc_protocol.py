@@ -69,6 +69,11 @@ def test_finding_full_a_parity_alias_when_tma_loads_complete_far_out_of_order():
     for items, first in (([9, 3, 12, 1, 8], 61), ([1, 2, 1, 7, 3], 0), ([23], 0)):
         clean, failure = T.check(items, seeds=50, mutate="per_group_full_a", first_seed=first)
         assert failure is None, failure
+    # the other way out, the existing -DPMF_SA=4 build (four A/G stages: every stage belongs to one group), modelled with
+    # its own constants (two Xb stages, three Z accumulators, one dX staging buffer)
+    assert "constexpr int SXK = SA == 4 ? 2 : 3, SXM = 1;" in SRC and T.FusedSA4.CONST == dict(SA=4, SXK=2, SXM=1, SZ=3, SDX=1)
+    clean, failure = T.check([9, 3, 12, 1, 8], seeds=50, model="fused_sa4", first_seed=61)
+    assert failure is None, failure
     patch = open(os.path.join(ROOT, "scripts", "experiments", "r2_full_a_per_group_barriers.patch")).read()
     assert "SA * (int)(gcount & 1u)" in patch and "(g / (2u * SA)) & 1u" in patch
 
