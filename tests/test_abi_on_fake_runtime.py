@@ -19,7 +19,10 @@ then drives the library through the Python mirror exactly as on a GPU box.  What
   * the `PMF_KERNEL_AUTO` size rule (DESIGN.md 4.1) and the refusal of unsupported shapes;
   * launch geometry within the hardware limits, every tensor map within the driver's documented constraints;
   * error paths (no device, a device that is not sm_100, allocation failures at several depths, bad arguments) and, after
-    every scenario, zero live device blocks, balanced streams / events, no foreign frees, no copy outside an allocation."""
+    every scenario, zero live device blocks, balanced streams / events, no foreign frees, no copy outside an allocation;
+  * BASELINE.json's configs at their FULL dimensions (C2, C3, C4 with the 2 M-edge graph regulariser, the C5 shard): the kernels
+    `PMF_KERNEL_AUTO` picks there, persistent grids of one CTA per SM, shared memory within 227 KB, every TMA descriptor valid
+    at 30 000 / 50 000 features, the launch counter, and the device memory a handle holds."""
 import json
 import os
 import shutil
@@ -56,6 +59,9 @@ def out(tmp_path_factory):
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-3000:]
     env = {k: v for k, v in os.environ.items() if k not in ("PMF_GUARD", "PMF_ALLOC_CACHE", "PMF_LIB", "LD_PRELOAD")}
+    # BASELINE.json's configs at their full dimensions (its own process, next to the scenarios below: ~1.5 minutes of host work)
+    full = subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "fake_runtime_fullsize_worker.py"), fake, lib, "C2", "C3",
+                             "C4a", "C5"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env, cwd=ROOT)
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "fake_runtime_worker.py"), fake, lib], capture_output=True,
                        text=True, timeout=900, env=env, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
@@ -68,6 +74,13 @@ def out(tmp_path_factory):
                        text=True, timeout=900, env=dict(env, PMF_GUARD="1"), cwd=ROOT)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     res["guarded"] = json.loads(r.stdout.strip().splitlines()[-1])
+    try:
+        so, se = full.communicate(timeout=900)
+    except subprocess.TimeoutExpired:
+        full.kill()
+        raise
+    assert full.returncode == 0, so[-2000:] + se[-4000:]
+    res["fullsize"] = json.loads(so.strip().splitlines()[-1])
     return res
 
 
@@ -228,3 +241,42 @@ def test_abi_in_the_julia_shims_call_order(out):
         assert f["ok"] and f["round_trip"] and f["term"] == "max_epochs"
         assert f["names"] == ["multi_pass_kernel", "data_pass_ffma_kernel<1,0>", "fused_epoch_kernel", "data_pass_ffma_kernel<1,0>",
                               "fused_epoch_kernel"]
+
+
+def test_baseline_configs_at_full_size(out):
+    """What the host decides at the sizes BASELINE.json quotes (the GPU suite reaches them only through bench.py and
+    scripts/config_times.py): kernel selection, geometry, TMA descriptors, launch counter, device memory per handle."""
+    full = out["fullsize"]
+    per_epoch = {
+        "C2": (["multi_pass_kernel", "prep_operands_kernel"], ["data_pass_tc_kernel<0,0,0>", "fused_epoch_kernel"]),
+        "C3": (["multi_pass_kernel", "build_a_tc_kernel"],
+               ["prep_operands_kernel", "data_pass_tc_kernel<0,1,0>", "combine_dx_kernel", "fused_epoch_kernel"]),
+        "C4a": (["multi_pass_kernel"],
+                ["prep_wide_kernel", "prep_wide_kernel", "zlink_kernel", "grad_gemm_kernel<0>", "grad_gemm_kernel<1>",
+                 "transpose_in_kernel", "network_virtual_kernel", "network_rows_kernel", "transpose_add_kernel", "fused_epoch_kernel"]),
+        "C5": (["multi_pass_kernel"],
+               ["prep_wide_kernel", "prep_wide_kernel", "zlink_kernel", "grad_gemm_kernel<0>", "grad_gemm_kernel<1>", "fused_epoch_kernel"]),
+    }
+    # device bytes per handle after a fit, as a multiple of the data matrix 4 M N (DESIGN.md 3): A alone on the fused path, A and
+    # its per-view-ordered copy with batch layers, A and G' for K > 64 (+ operand splits, the transposed Y and CG scratch at C4)
+    budget = {"C2": 1.05, "C3": 2.2, "C4a": 2.45, "C5": 2.1}
+    dims = {"C2": (10000, 30000, 64), "C3": (10000, 30000, 64), "C4a": (10000, 30000, 256), "C5": (10000, 50000, 128)}
+    elem = {7: 4, 9: 2}                                               # CU_TENSOR_MAP_DATA_TYPE_FLOAT32 / _BFLOAT16
+    for name, (first, epoch) in per_epoch.items():
+        r = full[name]
+        assert r["error"] is None, (name, r["error"])
+        assert (r["M"], r["N"], r["K"]) == dims[name]
+        assert r["names"] == first + epoch + epoch, (name, r["names"])
+        assert r["reported"] == len(r["launches"]) and r["term"] == "max_epochs"
+        for x in r["launches"]:
+            threads = x["block"][0] * x["block"][1] * x["block"][2]
+            assert min(x["grid"]) >= 1 and x["grid"][1] <= 65535 and threads <= 1024 and x["smem"] <= 232448, (name, x)
+            if x["name"].startswith(("data_pass_tc_kernel", "zlink_kernel", "grad_gemm_kernel")):
+                assert x["grid"] == [148, 1, 1] and x["smem"] > 190000, (name, x)      # persistent: one CTA per SM
+        assert r["maps"] and all(m["rc"] == 0 and m["rank"] == 2 for m in r["maps"]), (name, r["maps"])
+        for m in r["maps"]:
+            assert m["stride0"] == m["dim0"] * elem[m["dtype"]] and m["box0"] * elem[m["dtype"]] in (64, 128), (name, m)
+        M, N, _ = dims[name]
+        assert 4 * M * N <= r["live_bytes"] and r["live_bytes_after_fit"] <= budget[name] * 4 * M * N, \
+            (name, r["live_bytes_after_fit"] / (4.0 * M * N))
+        assert _clean(r["counters_after_close"]), (name, r["counters_after_close"])
