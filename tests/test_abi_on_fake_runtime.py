@@ -187,6 +187,27 @@ def test_exchange_step_inside_pmf_fit_three_ranks(out):
     assert n["live_blocks"] == 0 and n["bad_frees"] == 0 and n["oob_copies"] == 0
 
 
+def test_exchange_step_at_the_payload_of_the_eight_gpu_config(out):
+    """BASELINE configs[4] (80 000 x 50 000, K = 128): the exchange inside pmf_fit on the tcgen05 kernels for K > 64 at the real
+    feature count and latent dimension (two ranks; the payload does not depend on the samples per rank).  One group of two
+    in-place all-reduces per epoch after the gradient contractions: dY (50 000 x 128) + column-parameter gradients as ONE
+    float32 buffer of 26.0 MB, and the two rank-local loss scalars as float64."""
+    n = out["nccl"]["c5"]
+    assert n["alive"] == [False, False] and n["errors"] == []
+    R, E, L = n["ranks"], n["epochs"], n["grad_buffer_len"][0]
+    assert n["grad_buffer_len"] == [L] * R and n["N"] * n["K"] + 2 * n["N"] <= L <= 1.02 * (n["N"] * n["K"] + 2 * n["N"])
+    assert n["grad_buffers_all_equal_sum"] and n["scalars"] == [[30.0, 30.0]] * R
+    log = n["nccl_log"]
+    assert len(log) == R * E * 2 and all(x["in_place"] == 1 and x["grouped"] == 1 and x["nranks"] == R for x in log)
+    for r in range(R):
+        assert [(x["count"], x["dtype"]) for x in log if x["rank"] == r] == [(L, 7), (2, 8)] * E
+    # per rank: the first penalty pass, then per epoch 2 operand splits + link + 2 gradient GEMMs + the fused epoch pass, and
+    # the two collectives the library's counter also holds (bench.py reports them as nccl_collectives, not gpu_launches)
+    assert n["kernel_launches"] == [1 + E * 6 + E * 2] * R and n["term"] == ["max_epochs"] * R
+    assert n["nccl_mismatches"] == 0 and n["nccl_live_comms"] == 0
+    assert n["live_blocks"] == 0 and n["bad_frees"] == 0 and n["oob_copies"] == 0
+
+
 def test_graph_regulariser_statistics_passes_and_allocator_cache(out):
     s = out["s3_network"]                                               # NetworkRegularizer on a transposed copy of Y (DESIGN.md 4)
     assert _per_epoch(s["names"], ["multi_pass_kernel"]) == ["data_pass_ffma_kernel<1,0>", "transpose_in_kernel", "network_virtual_kernel",
