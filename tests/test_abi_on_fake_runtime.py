@@ -59,28 +59,31 @@ def out(tmp_path_factory):
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-3000:]
     env = {k: v for k, v in os.environ.items() if k not in ("PMF_GUARD", "PMF_ALLOC_CACHE", "PMF_LIB", "LD_PRELOAD")}
-    # BASELINE.json's configs at their full dimensions (its own process, next to the scenarios below: ~1.5 minutes of host work)
-    full = subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "fake_runtime_fullsize_worker.py"), fake, lib, "C2", "C3",
-                             "C4a", "C5"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env, cwd=ROOT)
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "fake_runtime_worker.py"), fake, lib], capture_output=True,
-                       text=True, timeout=900, env=env, cwd=ROOT)
-    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
-    res = json.loads(r.stdout.strip().splitlines()[-1])
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "fake_nccl_worker.py"), fake, nccl, lib], capture_output=True,
-                       text=True, timeout=300, env=env, cwd=ROOT)
-    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
-    res["nccl"] = json.loads(r.stdout.strip().splitlines()[-1])
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "fake_runtime_worker.py"), fake, lib], capture_output=True,
-                       text=True, timeout=900, env=dict(env, PMF_GUARD="1"), cwd=ROOT)
-    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
-    res["guarded"] = json.loads(r.stdout.strip().splitlines()[-1])
+    # five independent worker processes, run side by side: the scenarios (plain and with PMF_GUARD=1), the exchange step, and
+    # BASELINE.json's configs at their full dimensions (two processes of two configs each, ~45 s of host work per process)
+    W = os.path.join(ROOT, "tests")
+    jobs = {
+        "main": ([os.path.join(W, "fake_runtime_worker.py"), fake, lib], env),
+        "guarded": ([os.path.join(W, "fake_runtime_worker.py"), fake, lib], dict(env, PMF_GUARD="1")),
+        "nccl": ([os.path.join(W, "fake_nccl_worker.py"), fake, nccl, lib], env),
+        "full_a": ([os.path.join(W, "fake_runtime_fullsize_worker.py"), fake, lib, "C2", "C3"], env),
+        "full_b": ([os.path.join(W, "fake_runtime_fullsize_worker.py"), fake, lib, "C4a", "C5"], env),
+    }
+    procs = {k: subprocess.Popen([sys.executable] + a, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=e, cwd=ROOT)
+             for k, (a, e) in jobs.items()}
+    got = {}
     try:
-        so, se = full.communicate(timeout=900)
-    except subprocess.TimeoutExpired:
-        full.kill()
-        raise
-    assert full.returncode == 0, so[-2000:] + se[-4000:]
-    res["fullsize"] = json.loads(so.strip().splitlines()[-1])
+        for k, pr in procs.items():
+            so, se = pr.communicate(timeout=900)
+            assert pr.returncode == 0, k + ": " + so[-2000:] + se[-4000:]
+            got[k] = json.loads(so.strip().splitlines()[-1])
+    finally:
+        for pr in procs.values():
+            if pr.poll() is None:
+                pr.kill()
+    res = got["main"]
+    res["nccl"], res["guarded"] = got["nccl"], got["guarded"]
+    res["fullsize"] = dict(got["full_a"], **got["full_b"])
     return res
 
 
