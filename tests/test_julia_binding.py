@@ -123,3 +123,82 @@ def test_shim_overrides_the_method_the_reference_calls():
     text = open(SHIM).read()
     assert re.search(r"function PM\.mf_fit!\(model::PM\.PathMatFacModel;", text), "PM.mf_fit!(model; ...) is not overridden"
     assert not re.search(r"function (?:PM\.)?mf_fit!\(model[^;)]*,\s*h\b", text)
+
+
+# ---- the other half of the chain: include/pmf.h against the signatures the mirror binds ------------------------------------------------
+C_SCALARS = {"int": C.c_int, "int32_t": C.c_int32, "uint32_t": C.c_uint32, "int64_t": C.c_int64, "uint16_t": C.c_uint16,
+             "uint8_t": C.c_uint8, "float": C.c_float, "double": C.c_double, "pmf_handle": C.c_void_p,
+             "pmf_dims": _lib.pmf_dims, "pmf_losses": _lib.pmf_losses, "pmf_fit_opts": _lib.pmf_fit_opts, "pmf_history": _lib.pmf_history}
+
+
+def c_type(decl, is_return=False):
+    """ctypes type of one C parameter declaration (`const float* A_host`) or return type (`const char*`)."""
+    d = re.sub(r"\bconst\b", " ", decl).strip()
+    d, n_arr = re.subn(r"\[\d*\]", "", d)                         # an array parameter is a pointer to its element type
+    stars = d.count("*") + n_arr
+    words = d.replace("*", " ").split()
+    base = words[0]
+    assert len(words) == (1 if is_return else 2) or (not is_return and len(words) == 1), decl
+    if base == "void":
+        assert stars >= 1, decl
+        t, stars = C.c_void_p, stars - 1
+    elif base == "char":
+        assert stars == 1, decl
+        return C.c_char_p
+    else:
+        t = C_SCALARS[base]
+    for _ in range(stars):
+        t = C.POINTER(t)
+    return t
+
+
+def header_prototypes():
+    hdr = open(os.path.join(ROOT, "include", "pmf.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    hdr = re.sub(r"//[^\n]*", "", hdr)
+    out = {}
+    for m in re.finditer(r"(?:^|\n)\s*((?:const\s+)?\w+\s*\*?)\s*(pmf_\w+)\s*\(([^)]*)\)\s*;", hdr):
+        ret, name, params = m.group(1).strip(), m.group(2), " ".join(m.group(3).split())
+        plist = [] if params in ("", "void") else [p.strip() for p in params.split(",")]
+        out[name] = (ret, plist)
+    return out
+
+
+def test_header_prototypes_match_the_signatures_the_mirror_binds():
+    protos = header_prototypes()
+    assert set(protos) == set(_lib.SIGNATURES), set(protos) ^ set(_lib.SIGNATURES)
+    for name, (ret, plist) in protos.items():
+        res, args = _lib.SIGNATURES[name]
+        if ret == "void":
+            assert res is None, name
+        else:
+            assert same_ctype(c_type(ret, is_return=True), res), (name, ret, res)
+        assert len(plist) == len(args), (name, plist, args)
+        for pos, (p, a) in enumerate(zip(plist, args)):
+            assert same_ctype(c_type(p), a), f"{name} argument {pos}: header `{p}`, mirror {a}"
+
+
+def test_header_structs_have_the_layout_the_mirror_and_the_shim_use(tmp_path):
+    """The C compiler's own offsets of every field of pmf.h's structs (a program that includes the header) against ctypes."""
+    import shutil
+    import subprocess
+    import pytest
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    structs = {"pmf_dims": _lib.pmf_dims, "pmf_losses": _lib.pmf_losses, "pmf_fit_opts": _lib.pmf_fit_opts, "pmf_history": _lib.pmf_history}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "pmf.h"', "int main(void) {"]
+    for sname, ct in structs.items():
+        lines.append(f'  printf("{sname} %zu\\n", sizeof({sname}));')
+        for fname, _ in ct._fields_:
+            lines.append(f'  printf("{sname}.{fname} %zu\\n", offsetof({sname}, {fname}));')
+    lines += ["  return 0;", "}"]
+    src, exe = tmp_path / "layout.c", tmp_path / "layout"
+    src.write_text("\n".join(lines))
+    r = subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]                       # also: every field the mirror names exists in the header
+    got = dict(l.split() for l in subprocess.run([str(exe)], capture_output=True, text=True).stdout.splitlines())
+    for sname, ct in structs.items():
+        assert int(got[sname]) == C.sizeof(ct), sname
+        for fname, _ in ct._fields_:
+            assert int(got[f"{sname}.{fname}"]) == getattr(ct, fname).offset, (sname, fname)
+    # and no field of the header is missing from the mirror: the sizes agree, so a dropped trailing field would show above
