@@ -174,6 +174,11 @@ static CUresult fake_encode_tiled(CUtensorMap* m, CUtensorMapDataType dt, cuuint
     if (sw == CU_TENSOR_MAP_SWIZZLE_64B && inner > 64) r.rc = 1;
     if (sw >= CU_TENSOR_MAP_SWIZZLE_128B && inner > 128) r.rc = 1;
     if (rank >= 2 && !inside_live(addr, 1)) r.rc = 2;                 // the tensor must be device memory
+    if (r.rc == 0) {                                                  // ... and so must all of it: TMA clamps to the descriptor's dims,
+        uint64_t extent = dim[0] * (uint64_t)esz;                     // not to the allocation, so a descriptor larger than its block
+        for (cuuint32_t i = 1; i < rank; ++i) extent += (dim[i] - 1) * stride[i - 1];   // lets loads / reduce-adds run past it
+        if (!inside_live(addr, extent)) r.rc = 3;
+    }
     g_maps.push_back(r);
     if (m) std::memset(m, 0, sizeof(CUtensorMap));
     return r.rc ? CUDA_ERROR_INVALID_VALUE : CUDA_SUCCESS;

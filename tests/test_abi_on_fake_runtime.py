@@ -17,7 +17,8 @@ then drives the library through the Python mirror exactly as on a GPU box.  What
     really sums -- one group of two in-place all-reduces per epoch and rank (the whole shared gradient buffer as float32, the
     two rank-local loss scalars as float64), every rank left with the sum, no mismatched call, communicators destroyed;
   * the `PMF_KERNEL_AUTO` size rule (DESIGN.md 4.1) and the refusal of unsupported shapes;
-  * launch geometry within the hardware limits, every tensor map within the driver's documented constraints;
+  * launch geometry within the hardware limits, every tensor map within the driver's documented constraints and, whole, inside
+    the device block it points into (TMA clamps to the descriptor's extents, not to the allocation);
   * error paths (no device, a device that is not sm_100, allocation failures at several depths, bad arguments) and, after
     every scenario, zero live device blocks, balanced streams / events, no foreign frees, no copy outside an allocation;
   * BASELINE.json's configs at their FULL dimensions (C2, C3, C4 with the 2 M-edge graph regulariser, the C5 shard): the kernels
