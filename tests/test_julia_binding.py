@@ -202,3 +202,26 @@ def test_header_structs_have_the_layout_the_mirror_and_the_shim_use(tmp_path):
         for fname, _ in ct._fields_:
             assert int(got[f"{sname}.{fname}"]) == getattr(ct, fname).offset, (sname, fname)
     # and no field of the header is missing from the mirror: the sizes agree, so a dropped trailing field would show above
+
+
+def test_struct_constructor_calls_of_the_shim_pass_one_value_per_field():
+    """`PmfFitOpts(...)`, `PmfHistory(...)` and `PmfDims(...)` are built positionally: a missing or extra value would shift every
+    later field (Julia would raise a MethodError only at the first fit)."""
+    text = open(SHIM).read()
+    seen = set()
+    for m in re.finditer(r"(?<![\w{])(PmfFitOpts|PmfHistory|PmfDims)\(", text):
+        depth, k = 1, m.end()
+        while depth:
+            depth += {"(": 1, ")": -1}.get(text[k], 0)
+            k += 1
+        values = top_level_split(text[m.end():k - 1])
+        n = 0
+        for v in values:
+            if v.endswith("..."):                                    # pointer.(losses)...: one pointer per loss component
+                assert v == "pointer.(losses)..." and re.search(r"losses = \[zeros\(Float64, cap\) for _ in 1:5\]", text), v
+                n += 5
+            else:
+                n += 1
+        assert n == len(STRUCTS[m.group(1)]._fields_), (m.group(1), values)
+        seen.add(m.group(1))
+    assert seen == set(STRUCTS)
