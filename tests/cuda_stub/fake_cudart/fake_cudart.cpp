@@ -201,6 +201,7 @@ void fake_counters(long* out) {       // mallocs, frees, live blocks, live bytes
     long v[10] = {g_mallocs, g_frees, (long)g_live.size(), (long)bytes, g_host_allocs, g_host_frees, g_streams, g_events, g_bad_frees, g_oob_copies};
     std::memcpy(out, v, sizeof v);
 }
+long fake_syncs(void) { std::lock_guard<std::mutex> l(mu); return g_syncs; }      // cudaStreamSynchronize + cudaDeviceSynchronize calls so far
 int fake_launch_count(void) { std::lock_guard<std::mutex> l(mu); return (int)g_launches.size(); }
 int fake_launch(int i, char* name, int cap, unsigned* dims, size_t* smem) {
     std::lock_guard<std::mutex> l(mu);

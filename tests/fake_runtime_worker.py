@@ -321,6 +321,25 @@ for call in range(2):
 OUT["s8_shim_order"] = {"steps": steps, "fits": shim_fits}
 eng.close()
 
+# ---- S9: how often the host waits for the device inside pmf_fit: the epoch loop only enqueues (termination is evaluated on the
+# device); the host synchronises once per `check_every` epochs to read the stop flag, and once at the end ----------------
+fake.fake_syncs.restype = C.c_long
+m = model_(300, 400, 16, lambda_X_l2=1.0)
+eng = P.Engine(m)
+eng.reset_opt_state(1e-8)
+eng.fit(eng.make_opts(epoch=1, max_epochs=3, kernel=_lib.KERNEL_TC, **fit_kw))
+sync_rule = []
+launches()
+for kw in (dict(no_terminate=1, check_every=1 << 20), dict(check_every=8), dict(check_every=1)):
+    for E in (40, 400):
+        s0, c0 = fake.fake_syncs(), counters()
+        eng.fit(eng.make_opts(epoch=1, max_epochs=E, kernel=_lib.KERNEL_TC, **{**fit_kw, **kw}))
+        c1 = counters()
+        sync_rule.append({"check_every": kw["check_every"], "epochs": E, "syncs": fake.fake_syncs() - s0, "launches": len(launches()),
+                          "mallocs": c1["mallocs"] - c0["mallocs"], "host_allocs": c1["host_allocs"] - c0["host_allocs"]})
+OUT["s9_sync_rule"] = sync_rule
+eng.close()
+
 # ---- S6: guard zones (PMF_GUARD=1 in the environment; without it there is nothing to check) ----------------------------------------
 m = model_(70, 60, 12, batch_views=2, ordinal=True, lambda_X_l2=1.0)
 eng = P.Engine(m)

@@ -305,3 +305,19 @@ def test_baseline_configs_at_full_size(out):
         assert 4 * M * N <= r["live_bytes"] and r["live_bytes_after_fit"] <= budget[name] * 4 * M * N, \
             (name, r["live_bytes_after_fit"] / (4.0 * M * N))
         assert _clean(r["counters_after_close"]), (name, r["counters_after_close"])
+
+
+def test_epoch_loop_only_enqueues(out):
+    """pmf_fit's epoch loop does not wait for the device: termination is evaluated by the fused epoch pass on the device and every
+    later kernel checks the stop flag; the host synchronises once per `check_every` epochs to read that flag, and
+    once at the end for the history -- so an un-polled fit of 400 epochs waits as often as one of 40 (bench.py's timed region),
+    and no fit allocates device or pinned memory from the second call on."""
+    rule = {(r["check_every"], r["epochs"]): r for r in out["s9_sync_rule"]}
+    for (ce, E), r in rule.items():
+        assert r["launches"] == 2 * E + 1, r                            # the first penalty pass, then two launches per epoch
+        assert r["host_allocs"] == 0, r
+        if ce > 400:
+            assert r["syncs"] <= 3, r
+        else:
+            assert r["syncs"] == E // ce + 1, r
+    assert sum(r["mallocs"] for r in out["s9_sync_rule"][2:]) == 0
