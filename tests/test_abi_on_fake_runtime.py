@@ -16,6 +16,7 @@ then drives the library through the Python mirror exactly as on a GPU box.  What
   * the exchange step inside `pmf_fit`: three ranks as threads over a host-only NCCL stand-in (tests/cuda_stub/fake_nccl) that
     really sums -- one group of two in-place all-reduces per epoch and rank (the whole shared gradient buffer as float32, the
     two rank-local loss scalars as float64), every rank left with the sum, no mismatched call, communicators destroyed;
+  * the epoch loop only enqueues: 2 E + 1 launches, E / check_every + 1 synchronisations, no allocation per fit;
   * the `PMF_KERNEL_AUTO` size rule (DESIGN.md 4.1) and the refusal of unsupported shapes;
   * launch geometry within the hardware limits, every tensor map within the driver's documented constraints and, whole, inside
     the device block it points into (TMA clamps to the descriptor's extents, not to the allocation);
