@@ -25,6 +25,6 @@ for (M,N,K,bv) in ((2000,3000,64,0),(2000,3000,64,2),(2000,3000,128,0)):
     eng.fit(eng.make_opts(epoch=1, max_epochs=5, **kw)); U.launches()
     E=2000
     t0=time.perf_counter(); h=eng.fit(eng.make_opts(epoch=6, max_epochs=5+E, **kw)); dt=time.perf_counter()-t0
-    n=len(U.launches()); nm=len(U.maps())
+    nm=len(U.maps()); n=len(U.launches())
     print(f"M={M} N={N} K={K} batch_views={bv}: {dt/E*1e6:.1f} us of host time per epoch ({n/E:.1f} launches, tensor maps encoded {nm})")
     eng.close()
